@@ -1,0 +1,637 @@
+/* lbm_oracle.c -- CPU restatement of the SFCMM/LBM time step (the parity oracle).
+ *
+ * TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library; it is the checker, never the product.  The product path is the CUDA library
+ * built from lbm_b200/csrc and fails loudly when that library is missing.
+ *
+ * Every function follows the reference (/root/reference, SFCMM/LBM v0.0.2) pass by pass, with the same
+ * operation order, the same array-of-structures storage and the same ascending-index sums, so that on the
+ * reference's own configurations (D2Q9, BGK, fp64) it reproduces the reference's raw m_f / m_fold / m_vars /
+ * m_varsold arrays bit for bit.  That claim is pinned by tests/test_oracle_golden.py against dumps of the
+ * reference binary (oracle/_ref/lbm_ref, built by oracle/ref_build/Makefile) committed under tests/golden/.
+ *
+ * Pinned by the reference (file:line relative to /root/reference):
+ *   storage                       src/lbm/solver.h:156-172,206-210   f[c*Q+i], vars[c*NVAR+v], slots u,v[,w],rho
+ *   time step (8 passes)          src/lbm/solver.cpp:307-320
+ *   currToOldVars                 src/lbm/solver.cpp:505-510
+ *   updateMacroscopicValues       src/lbm/solver.cpp:513-553
+ *   calcEquilibriumMoments        src/lbm/solver.cpp:556-571, src/lbm/equilibrium_func.h:52-54,68-84
+ *   collisionStep (BGK)           src/lbm/solver.cpp:601-613
+ *   forcing                       src/lbm/solver.cpp:626-696
+ *   propagationStep (push)        src/lbm/solver.cpp:715-740
+ *   bounce-back / Dirichlet BB    src/lbm/bnd/bnd_dirichlet.h:79-121, src/lbm/bnd/bnd_wall.h:31-88
+ *   anti-bounce-back pressure     src/lbm/bnd/bnd_pressure.h:32-106
+ *   periodic boundary condition   src/lbm/bnd/bnd_periodic.h:31-119,175-215
+ *   residual                      src/lbm/solver.cpp:233-263,809-815
+ *   initial condition             src/lbm/solver.cpp:267-304
+ *   lattice tables                src/lbm/constants.h:296-422
+ *
+ * NOT pinned by the reference ("parity unpinned", new behaviour):
+ *   - D3Q19 / D3Q27 runs: the reference compiles these templates but cannot reach them
+ *     (src/lbm/solverExe.h:37-90); the dimension-generic source text above is followed literally.
+ *     The pressure BC writes all NDIM velocity components (the reference writes only u and v,
+ *     src/lbm/bnd/bnd_pressure.h:92-93).
+ *   - TRT and MRT collision (literature definitions; equal rates reduce to the BGK path).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_MAXQ 27
+#define ORC_MAXD 3
+
+enum { ORC_BGK = 0, ORC_TRT = 1, ORC_MRT = 2 };
+enum { ORC_BC_BB = 1, ORC_BC_BB_TANGENTIAL = 2, ORC_BC_DIRICHLET_BB = 3, ORC_BC_PRESSURE = 4, ORC_BC_PERIODIC = 5 };
+
+static const double kEps = 2.220446049250313e-16; /* GDoubleEps, include/common/sfcmm_types.h:50 */
+
+/* src/lbm/constants.h:27 -- the reference writes the speed of sound squared as the double 1.0/3.0 */
+static const double kCssq = 1.0 / 3.0;
+
+typedef struct {
+  int    ndim, ndist;
+  double c[ORC_MAXQ][ORC_MAXD];
+  int    opp[ORC_MAXQ];
+  double w[ORC_MAXQ];
+} OrcLattice;
+
+/* src/lbm/constants.h:296-319 */
+static const int kD2Q9c[9][2]   = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}, {1, 1}, {1, -1}, {-1, -1}, {-1, 1}, {0, 0}};
+static const int kD2Q9opp[9]    = {1, 0, 3, 2, 6, 7, 4, 5, 8};
+/* src/lbm/constants.h:322-422 (D3Q19 is the 18-direction prefix of D3Q27 plus the rest population) */
+static const int kD3c[26][3]    = {{-1, 0, 0},  {1, 0, 0},   {0, -1, 0},  {0, 1, 0},  {0, 0, -1}, {0, 0, 1},  {-1, -1, 0},
+                                   {-1, 1, 0},  {1, -1, 0},  {1, 1, 0},   {-1, 0, -1}, {-1, 0, 1}, {1, 0, -1}, {1, 0, 1},
+                                   {0, -1, -1}, {0, -1, 1},  {0, 1, -1},  {0, 1, 1},  {-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1},
+                                   {-1, 1, 1},  {1, -1, -1}, {1, -1, 1},  {1, 1, -1}, {1, 1, 1}};
+static const int kD3Q19opp[19]  = {1, 0, 3, 2, 5, 4, 9, 8, 7, 6, 13, 12, 11, 10, 17, 16, 15, 14, 18};
+static const int kD3Q27opp[27]  = {1,  0,  3,  2,  5,  4,  9,  8,  7,  6,  13, 12, 11, 10,
+                                   17, 16, 15, 14, 25, 24, 23, 22, 21, 20, 19, 18, 26};
+
+static int orc_lattice(OrcLattice* L, int ndim, int ndist) {
+  memset(L, 0, sizeof(*L));
+  L->ndim  = ndim;
+  L->ndist = ndist;
+  if(ndim == 2 && ndist == 9) {
+    for(int i = 0; i < 9; ++i) {
+      L->c[i][0] = kD2Q9c[i][0];
+      L->c[i][1] = kD2Q9c[i][1];
+      L->opp[i]  = kD2Q9opp[i];
+      L->w[i]    = i < 4 ? 1.0 / 9.0 : (i < 8 ? 1.0 / 36.0 : 4.0 / 9.0);
+    }
+    return 0;
+  }
+  if(ndim == 3 && (ndist == 19 || ndist == 27)) {
+    for(int i = 0; i < ndist - 1; ++i) {
+      for(int d = 0; d < 3; ++d) L->c[i][d] = kD3c[i][d];
+    }
+    for(int i = 0; i < ndist; ++i) L->opp[i] = ndist == 19 ? kD3Q19opp[i] : kD3Q27opp[i];
+    if(ndist == 19) {
+      for(int i = 0; i < 19; ++i) L->w[i] = i < 6 ? 1.0 / 18.0 : (i < 18 ? 1.0 / 36.0 : 1.0 / 3.0);
+    } else {
+      for(int i = 0; i < 27; ++i) L->w[i] = i < 6 ? 2.0 / 27.0 : (i < 18 ? 1.0 / 54.0 : (i < 26 ? 1.0 / 216.0 : 8.0 / 27.0));
+    }
+    return 0;
+  }
+  return -1;
+}
+
+typedef struct {
+  int      kind;
+  int64_t  n;
+  int64_t* cells;
+  double*  normals; /* n*ndim; Surface::normal_p(cell) i.e. the LAST normal stored for that cell (surface.h:52-55) */
+  double   value[ORC_MAXD];
+  double   tangential;
+  double   pressure;
+  double*  wallval;  /* ORC_BC_BB_TANGENTIAL: n*ndist, bnd_wall.h:31-72 */
+  int64_t* link;     /* ORC_BC_PERIODIC: n*ndist, bnd_periodic.h:59-98 */
+  int*     linkdist; /* n*ndist */
+  int*     nset;     /* n */
+} OrcBc;
+
+typedef struct {
+  OrcLattice L;
+  int        nvar, stride, model, omp_collide;
+  int64_t    n;
+  int64_t*   nghbr; /* n*stride push table, -1 = no neighbour (cartesiangrid.h:111-124) */
+  double*    center; /* n*ndim or NULL */
+  double     bbmin[ORC_MAXD], bbmax[ORC_MAXD], cell_length;
+  double     omega;
+  double     omega_minus;     /* TRT: odd-moment rate */
+  double     mrt_rates[ORC_MAXQ];
+  double *   f, *fold, *feq, *vars, *varsold;
+  OrcBc*     bc;
+  int        nbc;
+  /* forcing, solver.cpp:626-696 */
+  int      forcing;
+  int64_t *inlet, *outlet;
+  int64_t  ninlet, noutlet;
+  double   p_in, p_out;
+  int64_t  step;
+} Orc;
+
+/* ------------------------------------------------------------------------------------------------ helpers */
+
+static int in_direction(const OrcLattice* L, const double* normal, int dist) {
+  /* constants.h:83-86: normal . c_dist >= eps */
+  double dot = 0;
+  for(int d = 0; d < L->ndim; ++d) dot += normal[d] * L->c[dist][d];
+  return dot >= kEps;
+}
+
+/* equilibrium_func.h:52-54 -- kept with its divisions by constants */
+static inline double default_eq(double w, double rho, double cu, double vsq) {
+  return w * rho * (1.0 + cu / kCssq + cu * cu / (2.0 * kCssq * kCssq) - vsq / (2.0 * kCssq));
+}
+/* equilibrium_func.h:109-111 */
+static inline double symm_eq(double w, double rho, double cu, double vsq) {
+  return w * rho * (1.0 + cu * cu / (2.0 * kCssq * kCssq) - vsq / (2.0 * kCssq));
+}
+
+static inline double eq_dist(const OrcLattice* L, int dist, double rho, const double* u, int symm) {
+  double vsq = 0;
+  for(int d = 0; d < L->ndim; ++d) vsq += u[d] * u[d];
+  double cu = 0;
+  for(int d = 0; d < L->ndim; ++d) cu += u[d] * L->c[dist][d];
+  return symm ? symm_eq(L->w[dist], rho, cu, vsq) : default_eq(L->w[dist], rho, cu, vsq);
+}
+
+/* equilibrium_func.h:68-84 */
+static void eq_all(const OrcLattice* L, double* feq, double rho, const double* u) {
+  double vsq = 0;
+  for(int d = 0; d < L->ndim; ++d) vsq += u[d] * u[d];
+  for(int i = 0; i < L->ndist; ++i) {
+    double cu = 0;
+    for(int d = 0; d < L->ndim; ++d) cu += u[d] * L->c[i][d];
+    feq[i] = default_eq(L->w[i], rho, cu, vsq);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------ lifecycle */
+
+Orc* orc_create(int ndim, int ndist, int64_t ncells, const int64_t* nghbr, int stride, double omega) {
+  Orc* o = (Orc*)calloc(1, sizeof(Orc));
+  if(orc_lattice(&o->L, ndim, ndist) != 0) {
+    free(o);
+    return NULL;
+  }
+  o->nvar   = ndim + 1;
+  o->stride = stride;
+  o->n      = ncells;
+  o->omega  = omega;
+  o->model  = ORC_BGK;
+  o->nghbr  = (int64_t*)malloc(sizeof(int64_t) * (size_t)ncells * (size_t)stride);
+  memcpy(o->nghbr, nghbr, sizeof(int64_t) * (size_t)ncells * (size_t)stride);
+  size_t nq = (size_t)ncells * (size_t)ndist, nv = (size_t)ncells * (size_t)o->nvar;
+  o->f       = (double*)calloc(nq, sizeof(double));
+  o->fold    = (double*)calloc(nq, sizeof(double));
+  o->feq     = (double*)calloc(nq, sizeof(double));
+  o->vars    = (double*)calloc(nv, sizeof(double));
+  o->varsold = (double*)calloc(nv, sizeof(double));
+  return o;
+}
+
+void orc_set_geometry(Orc* o, const double* center, const double* bbmin, const double* bbmax, double cell_length) {
+  size_t nb = sizeof(double) * (size_t)o->n * (size_t)o->L.ndim;
+  o->center = (double*)malloc(nb);
+  memcpy(o->center, center, nb);
+  for(int d = 0; d < o->L.ndim; ++d) {
+    o->bbmin[d] = bbmin[d];
+    o->bbmax[d] = bbmax[d];
+  }
+  o->cell_length = cell_length;
+}
+
+/* New behaviour (not in the reference): two-relaxation-time and multiple-relaxation-time collision.
+ * TRT: f_i' = f_i - omega (f+_i - feq+_i) - omega_minus (f-_i - feq-_i) with the symmetric / antisymmetric
+ * split over opposite pairs.  MRT here is the pairwise "raw-moment by parity" form: rates[i] for the even part of
+ * pair (i, opp i) is rates[min], for the odd part rates[max]; with all rates equal it is exactly the BGK formula. */
+void orc_set_collision(Orc* o, int model, double omega_minus, const double* rates) {
+  o->model       = model;
+  o->omega_minus = omega_minus;
+  if(rates != NULL) memcpy(o->mrt_rates, rates, sizeof(double) * (size_t)o->L.ndist);
+}
+
+void orc_set_omp_collide(Orc* o, int on) { o->omp_collide = on; }
+
+static OrcBc* new_bc(Orc* o, int kind, const int64_t* cells, const double* normals, int64_t n) {
+  o->bc     = (OrcBc*)realloc(o->bc, sizeof(OrcBc) * (size_t)(o->nbc + 1));
+  OrcBc* b  = &o->bc[o->nbc++];
+  memset(b, 0, sizeof(*b));
+  b->kind    = kind;
+  b->n       = n;
+  b->cells   = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+  b->normals = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1) * (size_t)o->L.ndim);
+  memcpy(b->cells, cells, sizeof(int64_t) * (size_t)n);
+  memcpy(b->normals, normals, sizeof(double) * (size_t)n * (size_t)o->L.ndim);
+  b->pressure = NAN;
+  return b;
+}
+
+/* wall bounce-back; tangential == 0 selects the no-slip instantiation (bnd.h:232-240) */
+int orc_add_bc_wall_bb(Orc* o, const int64_t* cells, const double* normals, int64_t n, double tangential) {
+  const OrcLattice* L = &o->L;
+  if(fabs(tangential) > kEps) {
+    if(L->ndim != 2) return -1; /* bnd_wall.h:52-54: TERMM("Not implemented") */
+    OrcBc* b      = new_bc(o, ORC_BC_BB_TANGENTIAL, cells, normals, n);
+    b->tangential = tangential;
+    b->wallval    = (double*)calloc((size_t)n * (size_t)L->ndist, sizeof(double));
+    for(int64_t k = 0; k < n; ++k) {
+      const double* nrm = &b->normals[k * L->ndim];
+      for(int id = 0; id < L->ndist; ++id) {
+        if(in_direction(L, nrm, id)) {
+          const int    inside = L->opp[id];
+          const double t[2]   = {nrm[1], nrm[0]}; /* bnd_wall.h:48-51 */
+          const double tdot   = t[0] * L->c[inside][0] + t[1] * L->c[inside][1];
+          /* bnd_wall.h:57-66: directions anti-parallel to the normal are skipped and stay 0; for axis
+           * normals their tangential projection is 0 as well, so the stored value is 0 either way. */
+          const double ndot = nrm[0] * L->c[inside][0] + nrm[1] * L->c[inside][1];
+          const double nn   = sqrt(L->c[inside][0] * L->c[inside][0] + L->c[inside][1] * L->c[inside][1]);
+          const int parallel = fabs(acos(ndot / nn) - 3.14159265358979323846) < 10 * kEps;
+          if(!parallel) b->wallval[k * L->ndist + inside] = tangential * tdot;
+        }
+      }
+    }
+  } else {
+    new_bc(o, ORC_BC_BB, cells, normals, n);
+  }
+  return 0;
+}
+
+int orc_add_bc_dirichlet_bb(Orc* o, const int64_t* cells, const double* normals, int64_t n, const double* value) {
+  OrcBc* b = new_bc(o, ORC_BC_DIRICHLET_BB, cells, normals, n);
+  for(int d = 0; d < o->L.ndim; ++d) b->value[d] = value[d];
+  return 0;
+}
+
+int orc_add_bc_pressure(Orc* o, const int64_t* cells, const double* normals, int64_t n, double pressure) {
+  OrcBc* b    = new_bc(o, ORC_BC_PRESSURE, cells, normals, n);
+  b->pressure = pressure;
+  return 0;
+}
+
+/* bnd_periodic.h:31-98.  `pressure` NAN selects the plain copy variant. Needs orc_set_geometry. */
+int orc_add_bc_periodic(Orc* o, const int64_t* cells, const double* normals, int64_t n, const int64_t* conn,
+                        int64_t nconn, double pressure) {
+  const OrcLattice* L = &o->L;
+  if(o->center == NULL) return -1;
+  OrcBc* b    = new_bc(o, ORC_BC_PERIODIC, cells, normals, n);
+  b->pressure = pressure;
+  b->link     = (int64_t*)malloc(sizeof(int64_t) * (size_t)n * (size_t)L->ndist);
+  b->linkdist = (int*)malloc(sizeof(int) * (size_t)n * (size_t)L->ndist);
+  b->nset     = (int*)calloc((size_t)n, sizeof(int));
+  const double maxMatch = 10 * kEps;
+  for(int64_t k = 0; k < n; ++k) {
+    const int64_t c   = cells[k];
+    const double* nrm = &b->normals[k * L->ndim];
+    const double* ctr = &o->center[c * L->ndim];
+    int           ns  = 0;
+    for(int dist = 0; dist < L->ndist; ++dist) {
+      if(in_direction(L, nrm, dist)) {
+        double coord[ORC_MAXD];
+        int    inside = 1;
+        for(int d = 0; d < L->ndim; ++d) {
+          coord[d] = fabs(nrm[d]) > 0 ? o->bbmin[d] : ctr[d] + L->c[dist][d] * o->cell_length;
+          if(coord[d] < o->bbmin[d] || coord[d] > o->bbmax[d]) inside = 0;
+        }
+        if(inside) b->linkdist[k * L->ndist + ns++] = dist;
+      }
+    }
+    b->nset[k] = ns;
+    for(int id = 0; id < ns; ++id) {
+      const int dist = b->linkdist[k * L->ndist + id];
+      double    ca[ORC_MAXD];
+      for(int d = 0; d < L->ndim; ++d) ca[d] = fabs(nrm[d]) > 0 ? ctr[d] : ctr[d] + L->c[dist][d] * o->cell_length;
+      int64_t link = -1;
+      for(int64_t j = 0; j < nconn && link < 0; ++j) {
+        const double* cb = &o->center[conn[j] * L->ndim];
+        for(int d = 0; d < L->ndim; ++d) {
+          if(fabs(ca[d] - cb[d]) <= maxMatch) { /* first match in ANY coordinate, bnd_periodic.h:75-91 */
+            link = conn[j];
+            break;
+          }
+        }
+      }
+      b->link[k * L->ndist + id] = link;
+    }
+  }
+  return 0;
+}
+
+/* solver.cpp:640-647: inlet = surface cube_-x, outlet = cube_+x, p_out = 1.0, p_in = 1.0 + gradient */
+int orc_set_forcing(Orc* o, const int64_t* inlet, int64_t ninlet, const int64_t* outlet, int64_t noutlet, double gradient) {
+  if(o->center == NULL) return -1;
+  o->forcing = 1;
+  o->inlet   = (int64_t*)malloc(sizeof(int64_t) * (size_t)ninlet);
+  o->outlet  = (int64_t*)malloc(sizeof(int64_t) * (size_t)noutlet);
+  memcpy(o->inlet, inlet, sizeof(int64_t) * (size_t)ninlet);
+  memcpy(o->outlet, outlet, sizeof(int64_t) * (size_t)noutlet);
+  o->ninlet  = ninlet;
+  o->noutlet = noutlet;
+  o->p_out   = 1.0;
+  o->p_in    = o->p_out + gradient;
+  return 0;
+}
+
+void orc_destroy(Orc* o) {
+  if(o == NULL) return;
+  for(int i = 0; i < o->nbc; ++i) {
+    free(o->bc[i].cells);
+    free(o->bc[i].normals);
+    free(o->bc[i].wallval);
+    free(o->bc[i].link);
+    free(o->bc[i].linkdist);
+    free(o->bc[i].nset);
+  }
+  free(o->bc);
+  free(o->nghbr);
+  free(o->center);
+  free(o->f);
+  free(o->fold);
+  free(o->feq);
+  free(o->vars);
+  free(o->varsold);
+  free(o->inlet);
+  free(o->outlet);
+  free(o);
+}
+
+/* ------------------------------------------------------------------------------------------------ init */
+
+/* solver.cpp:267-304 with bnd_dirichlet.h:44-50 and bnd_pressure.h:32-38 */
+void orc_init(Orc* o) {
+  const OrcLattice* L = &o->L;
+  const int Q = L->ndist, NV = o->nvar, D = L->ndim;
+  memset(o->vars, 0, sizeof(double) * (size_t)o->n * (size_t)NV);
+  memset(o->varsold, 0, sizeof(double) * (size_t)o->n * (size_t)NV);
+  for(int b = 0; b < o->nbc; ++b) {
+    const OrcBc* bc = &o->bc[b];
+    if(bc->kind == ORC_BC_DIRICHLET_BB) {
+      for(int64_t k = 0; k < bc->n; ++k)
+        for(int d = 0; d < D; ++d) o->vars[bc->cells[k] * NV + d] = bc->value[d];
+    } else if(bc->kind == ORC_BC_PRESSURE) {
+      for(int64_t k = 0; k < bc->n; ++k) o->vars[bc->cells[k] * NV + D] = bc->pressure;
+    }
+  }
+  for(int64_t c = 0; c < o->n; ++c) {
+    o->vars[c * NV + D] = 1.0;
+    eq_all(L, &o->feq[c * Q], o->vars[c * NV + D], &o->vars[c * NV]);
+    for(int i = 0; i < Q; ++i) {
+      o->f[c * Q + i]    = o->feq[c * Q + i];
+      o->fold[c * Q + i] = o->feq[c * Q + i];
+    }
+  }
+  o->step = 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ passes */
+
+/* solver.cpp:513-553 */
+static void pass_moments(Orc* o) {
+  const OrcLattice* L = &o->L;
+  const int Q = L->ndist, NV = o->nvar, D = L->ndim;
+#pragma omp parallel for schedule(static)
+  for(int64_t c = 0; c < o->n; ++c) {
+    const double* fo  = &o->fold[c * Q];
+    double        rho = 0.0; /* std::accumulate(..., 0.0), ascending */
+    for(int i = 0; i < Q; ++i) rho += fo[i];
+    o->vars[c * NV + D] = rho;
+    for(int d = 0; d < D; ++d) {
+      double v = 0;
+      for(int i = 0; i < Q - 1; ++i) v += L->c[i][d] * fo[i];
+      o->vars[c * NV + d] = v / rho;
+    }
+  }
+}
+
+/* solver.cpp:556-571 */
+static void pass_equilibrium(Orc* o) {
+  const int Q = o->L.ndist, NV = o->nvar, D = o->L.ndim;
+#pragma omp parallel for schedule(static)
+  for(int64_t c = 0; c < o->n; ++c) eq_all(&o->L, &o->feq[c * Q], o->vars[c * NV + D], &o->vars[c * NV]);
+}
+
+/* solver.cpp:601-613 (BGK); TRT / MRT are new behaviour */
+static void collide_cell(const Orc* o, int64_t c) {
+  const OrcLattice* L = &o->L;
+  const int         Q = L->ndist;
+  double*           f = &o->f[c * Q];
+  const double*     fo = &o->fold[c * Q];
+  const double*     fe = &o->feq[c * Q];
+  if(o->model == ORC_BGK) {
+    for(int i = 0; i < Q; ++i) f[i] = (1 - o->omega) * fo[i] + o->omega * fe[i];
+  } else {
+    for(int i = 0; i < Q; ++i) {
+      const int    j  = L->opp[i];
+      double       wp = o->omega, wm = o->omega_minus;
+      if(o->model == ORC_MRT) {
+        wp = o->mrt_rates[i < j ? i : j];
+        wm = o->mrt_rates[i < j ? j : i];
+      }
+      const double fp  = 0.5 * (fo[i] + fo[j]);
+      const double fm  = 0.5 * (fo[i] - fo[j]);
+      const double fep = 0.5 * (fe[i] + fe[j]);
+      const double fem = 0.5 * (fe[i] - fe[j]);
+      f[i]             = fo[i] - wp * (fp - fep) - wm * (fm - fem);
+    }
+  }
+}
+
+static void pass_collision(Orc* o) {
+  if(o->omp_collide) {
+#pragma omp parallel for schedule(static)
+    for(int64_t c = 0; c < o->n; ++c) collide_cell(o, c);
+  } else {
+    for(int64_t c = 0; c < o->n; ++c) collide_cell(o, c); /* the reference has no OpenMP pragma here */
+  }
+}
+
+/* solver.cpp:626-696 */
+static void pass_forcing(Orc* o) {
+  if(!o->forcing) return;
+  const OrcLattice* L = &o->L;
+  const int Q = L->ndist, NV = o->nvar, D = L->ndim;
+  for(int64_t a = 0; a < o->ninlet; ++a) {
+    const int64_t val = o->nghbr[o->inlet[a] * o->stride + 1];
+    const double* ci  = &o->center[val * D];
+    for(int64_t b = 0; b < o->noutlet; ++b) {
+      const int64_t out = o->outlet[b];
+      if(fabs(ci[1] - o->center[out * D + 1]) < kEps) {
+        double vsq = 0;
+        for(int d = 0; d < D; ++d) vsq += o->vars[val * NV + d] * o->vars[val * NV + d];
+        for(int i = 0; i < Q; ++i) {
+          const double cu = o->vars[val * NV + 0] * L->c[i][0];
+          o->f[out * Q + i] = default_eq(L->w[i], o->p_out, cu, vsq) + o->f[val * Q + i] - o->feq[val * Q + i];
+        }
+      }
+    }
+  }
+  for(int64_t b = 0; b < o->noutlet; ++b) {
+    const int64_t val = o->nghbr[o->outlet[b] * o->stride + 0];
+    const double* co  = &o->center[val * D];
+    for(int64_t a = 0; a < o->ninlet; ++a) {
+      const int64_t in = o->inlet[a];
+      if(fabs(o->center[in * D + 1] - co[1]) < kEps) {
+        double vsq = 0;
+        for(int d = 0; d < D; ++d) vsq += o->vars[val * NV + d] * o->vars[val * NV + d];
+        for(int i = 0; i < Q; ++i) {
+          const double cu = o->vars[val * NV + 0] * L->c[i][0];
+          o->f[in * Q + i] = default_eq(L->w[i], o->p_in, cu, vsq) + o->f[val * Q + i] - o->feq[val * Q + i];
+        }
+      }
+    }
+  }
+}
+
+/* solver.cpp:699-712 -> bnd.h:48-53 */
+static void pass_pre_apply(Orc* o) {
+  const OrcLattice* L = &o->L;
+  const int Q = L->ndist, NV = o->nvar, D = L->ndim;
+  for(int b = 0; b < o->nbc; ++b) {
+    const OrcBc* bc = &o->bc[b];
+    if(bc->kind == ORC_BC_PRESSURE) {
+      for(int64_t k = 0; k < bc->n; ++k) o->vars[bc->cells[k] * NV + D] = bc->pressure;
+    } else if(bc->kind == ORC_BC_PERIODIC) {
+      for(int64_t k = 0; k < bc->n; ++k) {
+        const int64_t c = bc->cells[k];
+        if(!isnan(bc->pressure)) {
+          const int64_t l0 = bc->link[k * Q + 0];
+          for(int i = 0; i < Q; ++i)
+            o->fold[l0 * Q + i] = eq_dist(L, i, bc->pressure, &o->vars[c * NV], 0) + o->f[c * Q + i] - o->feq[c * Q + i];
+          o->vars[l0 * NV + D] = bc->pressure;
+        } else {
+          for(int id = 0; id < bc->nset[k]; ++id) {
+            const int dist                          = bc->linkdist[k * Q + id];
+            o->fold[bc->link[k * Q + id] * Q + dist] = o->f[c * Q + dist];
+          }
+          o->vars[bc->link[k * Q + 0] * NV + D] = 1.0;
+        }
+      }
+    }
+  }
+}
+
+/* solver.cpp:715-740 */
+static void pass_propagation(Orc* o) {
+  const int Q = o->L.ndist;
+#pragma omp parallel for schedule(static)
+  for(int64_t c = 0; c < o->n; ++c) {
+    for(int i = 0; i < Q - 1; ++i) {
+      const int64_t nb = o->nghbr[c * o->stride + i];
+      if(nb != -1) o->fold[nb * Q + i] = o->f[c * Q + i];
+    }
+    o->fold[c * Q + Q - 1] = o->f[c * Q + Q - 1];
+  }
+}
+
+/* bnd_dirichlet.h:79-121 */
+static void bb_cell(Orc* o, int64_t c, const double* nrm, int mode, const double* values) {
+  const OrcLattice* L = &o->L;
+  const int         Q = L->ndist;
+  for(int i = 0; i < Q - 1; ++i) {
+    if(o->nghbr[c * o->stride + i] == -1 && in_direction(L, nrm, i)) {
+      const int op         = L->opp[i];
+      o->fold[c * Q + op] = o->f[c * Q + i];
+      const double density = 1.0;
+      if(mode == 1) { /* SCALAR, bnd_dirichlet.h:111-112 */
+        o->fold[c * Q + op] += density * 2.0 / kCssq * L->w[op] * values[op];
+      } else if(mode == 2) { /* vector, bnd_dirichlet.h:113-117 */
+        for(int d = 0; d < L->ndim; ++d) o->fold[c * Q + op] += density * 2.0 / kCssq * L->w[op] * L->c[op][d] * values[d];
+      }
+    }
+  }
+}
+
+/* solver.cpp:743-755 -> bnd.h:60-65 */
+static void pass_apply(Orc* o) {
+  const OrcLattice* L = &o->L;
+  const int Q = L->ndist, NV = o->nvar, D = L->ndim;
+  for(int b = 0; b < o->nbc; ++b) {
+    const OrcBc* bc = &o->bc[b];
+    switch(bc->kind) {
+      case ORC_BC_BB:
+        for(int64_t k = 0; k < bc->n; ++k) bb_cell(o, bc->cells[k], &bc->normals[k * D], 0, NULL);
+        break;
+      case ORC_BC_BB_TANGENTIAL:
+        for(int64_t k = 0; k < bc->n; ++k) bb_cell(o, bc->cells[k], &bc->normals[k * D], 1, &bc->wallval[k * Q]);
+        break;
+      case ORC_BC_DIRICHLET_BB:
+        for(int64_t k = 0; k < bc->n; ++k) bb_cell(o, bc->cells[k], &bc->normals[k * D], 2, bc->value);
+        break;
+      case ORC_BC_PRESSURE: /* bnd_pressure.h:55-106 */
+        for(int64_t k = 0; k < bc->n; ++k) {
+          const int64_t c   = bc->cells[k];
+          const double* nrm = &bc->normals[k * D];
+          int           ins = -1;
+          for(int d = 0; d < D && ins < 0; ++d) {
+            if(nrm[d] < 0) ins = 2 * d + 1;
+            else if(nrm[d] > 0) ins = 2 * d;
+          }
+          const int64_t n1 = o->nghbr[c * o->stride + ins];
+          const int64_t n2 = o->nghbr[n1 * o->stride + ins];
+          double        ue[ORC_MAXD];
+          for(int d = 0; d < D; ++d) ue[d] = 1.5 * o->vars[n1 * NV + d] - 0.5 * o->vars[n2 * NV + d];
+          o->vars[c * NV + D] = bc->pressure;
+          for(int d = 0; d < D; ++d) o->vars[c * NV + d] = ue[d];
+          for(int i = 0; i < Q - 1; ++i) {
+            if(o->nghbr[c * o->stride + i] == -1 && in_direction(L, nrm, i)) {
+              const int op         = L->opp[i];
+              o->fold[c * Q + op] = -o->f[c * Q + i] + 2 * eq_dist(L, i, bc->pressure, ue, 1);
+            }
+          }
+        }
+        break;
+      default: break; /* periodic: apply is empty (bnd_periodic.h:208-209) */
+    }
+  }
+}
+
+/* solver.cpp:307-320 */
+void orc_step(Orc* o, int64_t nsteps) {
+  for(int64_t s = 0; s < nsteps; ++s) {
+    memcpy(o->varsold, o->vars, sizeof(double) * (size_t)o->n * (size_t)o->nvar); /* currToOldVars :505-510 */
+    pass_moments(o);
+    pass_equilibrium(o);
+    pass_collision(o);
+    pass_forcing(o);
+    pass_pre_apply(o);
+    pass_propagation(o);
+    pass_apply(o);
+    ++o->step;
+  }
+}
+
+/* solver.cpp:336 -- output() recomputes the moments of the current fold */
+void orc_update_moments(Orc* o) { pass_moments(o); }
+
+/* solver.cpp:809-815; returns 1 if NaN/Inf (solver.cpp:254-260) */
+int orc_residual(const Orc* o, double* out) {
+  int bad = 0;
+  for(int v = 0; v < o->nvar; ++v) {
+    double conv = 0.0;
+    for(int64_t c = 0; c < o->n; ++c) conv += fabs(o->vars[c * o->nvar + v] - o->varsold[c * o->nvar + v]);
+    out[v] = conv;
+    if(isnan(conv) || isinf(conv)) bad = 1;
+  }
+  return bad;
+}
+
+double*  orc_f(Orc* o) { return o->f; }
+double*  orc_fold(Orc* o) { return o->fold; }
+double*  orc_feq(Orc* o) { return o->feq; }
+double*  orc_vars(Orc* o) { return o->vars; }
+double*  orc_varsold(Orc* o) { return o->varsold; }
+int64_t  orc_steps_done(const Orc* o) { return o->step; }
+int      orc_nvar(const Orc* o) { return o->nvar; }
+int      orc_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}

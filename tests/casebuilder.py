@@ -1,0 +1,142 @@
+"""Turn a reference configuration + dumped tables into solver set-up calls (test helper).
+
+Mirrors what LBMSolver::loadConfiguration / LBMBndManager::setupBndryCnds do in the reference
+(src/lbm/solver.cpp:71-144, src/lbm/bnd/bnd.h:71-142): boundary conditions are created per geometry and per
+surface key in byte-lexicographic order (nlohmann::json objects are std::map), surfaces without cells are
+skipped, `generateBndry:false` produces a dummy.  The same spec drives the CPU oracle and the CUDA product,
+so both see identical inputs.
+"""
+import json
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@dataclass
+class CaseSpec:
+    name: str
+    ndim: int
+    ndist: int
+    nghbr: np.ndarray            # [n, stride] int64 push table, -1 = none
+    omega: float
+    center: np.ndarray = None    # [n, ndim]
+    bbmin: np.ndarray = None
+    bbmax: np.ndarray = None
+    cell_length: float = 0.0
+    bcs: list = field(default_factory=list)
+    forcing: dict = None
+    golden: dict = None
+
+    @property
+    def n(self):
+        return self.nghbr.shape[0]
+
+    def apply_to(self, solver):
+        """Issue the set-up calls on `solver` (oracle.Oracle or lbm_b200.Solver: same method names)."""
+        if self.center is not None:
+            solver.set_geometry(self.center, self.bbmin, self.bbmax, self.cell_length)
+        for bc in self.bcs:
+            k = bc["kind"]
+            if k == "wall_bb":
+                solver.add_wall_bb(bc["cells"], bc["normals"], bc["tangential"])
+            elif k == "dirichlet_bb":
+                solver.add_dirichlet_bb(bc["cells"], bc["normals"], bc["value"])
+            elif k == "pressure":
+                solver.add_pressure(bc["cells"], bc["normals"], bc["pressure"])
+            elif k == "periodic":
+                solver.add_periodic(bc["cells"], bc["normals"], bc["connected"], bc["pressure"])
+            else:
+                raise ValueError(k)
+        if self.forcing is not None:
+            solver.set_forcing(self.forcing["inlet"], self.forcing["outlet"], self.forcing["gradient"])
+        return solver
+
+
+def omega_from_config(solver_cfg, maxlvl):
+    """src/lbm/solver.cpp:102-123"""
+    if "relaxation" in solver_cfg:
+        return 1.0 / float(solver_cfg["relaxation"])
+    ma = float(solver_cfg["ma"])
+    re = float(solver_cfg["reynoldsnumber"])
+    ref_length = float(solver_cfg.get("refLength", 1.0))
+    nu = ma / re * ref_length
+    return 2.0 / (1.0 + 2.0 * nu * 2.0 ** maxlvl)
+
+
+def geometry_bbox(geometry_cfg, ndim):
+    """GeometryManager::getBoundingBox (src/geometry.h) for analytic objects."""
+    lo = np.full(ndim, np.inf)
+    hi = np.full(ndim, -np.inf)
+    for _, g in sorted(geometry_cfg.items()):
+        if g["type"] == "box":
+            a, b = np.array(g["A"], float), np.array(g["B"], float)
+        elif g["type"] == "sphere":
+            c = np.array(g["center"], float)
+            a, b = c - g["radius"], c + g["radius"]
+        elif g["type"] == "cube":
+            c = np.array(g["center"], float)
+            r = np.sqrt(ndim) * g["length"]
+            a, b = c - r, c + r
+        else:
+            raise ValueError(g["type"])
+        lo, hi = np.minimum(lo, a), np.maximum(hi, b)
+    return lo, hi
+
+
+def bcs_from_config(solver_cfg, surfaces, ndim):
+    """surfaces: name -> (cells, normals).  Returns (bc list in application order, forcing or None)."""
+    bcs = []
+    boundary = solver_cfg["boundary"]
+    for geom in sorted(boundary):
+        keys = boundary[geom]
+        for key in sorted(keys):
+            conf = keys[key]
+            sname = f"{geom}_{key}" if len(keys) > 1 else geom
+            cells, normals = surfaces.get(sname, (np.zeros(0, np.int64), np.zeros((0, ndim))))
+            if len(cells) == 0:
+                continue  # bnd.h:83-86
+            if not conf.get("generateBndry", True):
+                continue  # LBMBnd_dummy, bnd.h:149-159
+            t = conf["type"]
+            if t == "periodic":
+                conn = surfaces[conf["connection"]][0]
+                bcs.append(dict(kind="periodic", cells=cells, normals=normals, connected=conn,
+                                pressure=float(conf.get("pressure", "nan"))))
+            elif t == "wall":
+                if conf["model"] != "bounceback":
+                    raise NotImplementedError(f"wall model {conf['model']} (SURVEY section 8f N1)")
+                bcs.append(dict(kind="wall_bb", cells=cells, normals=normals,
+                                tangential=float(conf.get("tangentialVelocity", 0.0))))
+            elif t == "pressure":
+                bcs.append(dict(kind="pressure", cells=cells, normals=normals, pressure=float(conf["pressure"])))
+            elif t == "dirichlet" and conf["model"] == "bounceback":
+                bcs.append(dict(kind="dirichlet_bb", cells=cells, normals=normals,
+                                value=np.array(conf["value"], float)[:ndim]))
+            else:
+                raise NotImplementedError(f"boundary type {t}")
+    forcing = None
+    if solver_cfg.get("forcing", ""):
+        forcing = dict(inlet=surfaces["cube_-x"][0], outlet=surfaces["cube_+x"][0],
+                       gradient=float(solver_cfg["poiseuillePressureGradient"]))
+    return bcs, forcing
+
+
+def load_golden(name):
+    g = dict(np.load(os.path.join(GOLDEN, f"{name}.npz"), allow_pickle=False))
+    cfg = json.loads(str(g["config_json"]))
+    ndim, ndist = int(g["ndim"]), int(g["ndist"])
+    surfaces = {}
+    for k, sname in enumerate(g["surface_names"]):
+        surfaces[str(sname)] = (g[f"surf{k}_cells"].astype(np.int64), g[f"surf{k}_normals"])
+    lo, hi = geometry_bbox(cfg["geometry"], ndim)
+    l0 = float(np.max(hi - lo))
+    spec = CaseSpec(name=name, ndim=ndim, ndist=ndist, nghbr=g["nghbr"].astype(np.int64), omega=float(g["omega"]),
+                    center=g["center"], bbmin=lo, bbmax=hi, cell_length=l0 / 2.0 ** int(g["maxlvl"]), golden=g)
+    spec.bcs, spec.forcing = bcs_from_config(cfg["solver"], surfaces, ndim)
+    spec.config = cfg
+    spec.surfaces = surfaces
+    spec.digests = json.loads(str(g["digests_json"]))
+    return spec

@@ -1,0 +1,118 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures in tests/golden/ from the reference binary.
+
+Runs oracle/_ref/lbm_ref (the reference's own solver built by oracle/ref_build/Makefile, arithmetic
+untouched) on the reference's own test configurations (/root/reference/test/...), with only
+`solver.maxSteps` shortened, and stores what the dump hook wrote:
+
+  * tables : neighbour table (cartesiangrid.h:111-124), property bits, cell centres, boundary surfaces
+             (cell list + per-entry normal) in boundary-condition application order
+  * state  : raw m_fold, m_f, m_vars, m_varsold right after timeStep() number s for the listed steps
+
+Small cases keep the full arrays; the sphere case (63 576 cells) keeps the tables, `vars`, and SHA-256
+digests of the population arrays (the C oracle is bit-exact, so a digest pins it).
+
+Needs /root/reference and oracle/_ref/lbm_ref, i.e. it only runs in the build container.  The fixtures it
+writes are committed, so tests never need the reference at run time.
+
+usage: python tests/golden/make_golden.py [case ...]
+"""
+import hashlib
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+BIN = os.path.join(ROOT, "oracle", "_ref", "lbm_ref")
+
+# name -> (config relative to REF/test, maxSteps, dump steps, keep full populations?)
+CASES = {
+    "couette": ("couette/couette.json", 200, [1, 2, 10, 100, 200], True),
+    "couette_bnd": ("couette/couette_bnd.json", 100, [1, 10, 100], True),
+    "couette_bnd_bbDirichlet": ("couette/couette_bnd_bbDirichlet.json", 100, [1, 10, 100], True),
+    "poiseuille": ("poiseuille/poiseuille.json", 200, [1, 2, 10, 200], True),
+    "poiseuille_bnd": ("poiseuille/poiseuille_bnd.json", 100, [1, 10, 100], True),
+    "step_ns": ("step/step_ns.json", 200, [1, 10, 200], True),
+    "sphere_ns": ("sphere/sphere_ns.json", 300, [1, 300], False),
+}
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def parse_surfaces(path, ndim):
+    surfaces = []
+    cur = None
+    for line in open(path):
+        t = line.split()
+        if not t:
+            continue
+        if t[0] == "surface":
+            cur = {"name": t[1], "cells": [], "normals": [], "declared": int(t[2])}
+            surfaces.append(cur)
+        else:
+            cur["cells"].append(int(t[0]))
+            cur["normals"].append([float(x) for x in t[1:1 + ndim]])
+    return surfaces
+
+
+def run_case(name):
+    rel, max_steps, steps, full = CASES[name]
+    cfg = json.load(open(os.path.join(REF, "test", rel)))
+    cfg["solver"]["maxSteps"] = max_steps
+    # keep the run quiet and free of early termination; none of these keys touches the arithmetic
+    cfg["solver"]["solution_interval"] = 10 ** 9
+    cfg["solver"]["convergence"] = 0.0
+    cfg["solver"].pop("analyticalSolution", None)
+    cfg["solver"].pop("postprocessing", None)
+    tmp = tempfile.mkdtemp(prefix="lbm_golden_")
+    try:
+        os.makedirs(os.path.join(tmp, "dump"))
+        json.dump(cfg, open(os.path.join(tmp, "case.json"), "w"), indent=1)
+        env = dict(os.environ, SFCMM_DUMP="dump", SFCMM_DUMP_STEPS=",".join(map(str, steps)), OMP_NUM_THREADS="2")
+        r = subprocess.run([BIN, "case.json"], cwd=tmp, env=env, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"{name}: reference exited {r.returncode}\n{r.stderr[-2000:]}")
+        d = os.path.join(tmp, "dump")
+        meta = dict(l.split() for l in open(os.path.join(d, "meta.txt")))
+        n, ndim, q, nvar, nn = (int(meta[k]) for k in ("ncells", "ndim", "ndist", "nvar", "nnghbr"))
+        out = {
+            "config_json": np.array(json.dumps(cfg)),
+            "ncells": n, "ndim": ndim, "ndist": q, "nvar": nvar, "nnghbr": nn,
+            "omega": float(meta["omega"]), "nu": float(meta["nu"]), "maxlvl": int(meta["maxlvl"]),
+            "nghbr": np.fromfile(os.path.join(d, "nghbr.i64"), dtype=np.int64).reshape(n, nn).astype(np.int32),
+            "props": np.fromfile(os.path.join(d, "props.u64"), dtype=np.uint64).astype(np.uint16),
+            "center": np.fromfile(os.path.join(d, "center.f64"), dtype=np.float64).reshape(n, ndim),
+            "steps": np.array(steps, dtype=np.int64),
+        }
+        surfaces = parse_surfaces(os.path.join(d, "surfaces.txt"), ndim)
+        out["surface_names"] = np.array([s["name"] for s in surfaces])
+        for k, s in enumerate(surfaces):
+            out[f"surf{k}_cells"] = np.array(s["cells"], dtype=np.int32)
+            out[f"surf{k}_normals"] = np.array(s["normals"], dtype=np.float64).reshape(len(s["cells"]), ndim)
+        digests = {}
+        for s in steps:
+            for arr, width in (("fold", q), ("f", q), ("vars", nvar), ("varsold", nvar)):
+                a = np.fromfile(os.path.join(d, f"{arr}_{s}.f64"), dtype=np.float64).reshape(n, width)
+                digests[f"{arr}_{s}"] = sha(a)
+                if full or arr == "vars":
+                    out[f"{arr}_{s}"] = a
+        out["digests_json"] = np.array(json.dumps(digests))
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+        sz = os.path.getsize(os.path.join(HERE, f"{name}.npz"))
+        print(f"{name}: {n} cells, {len(surfaces)} surfaces, steps {steps} -> {sz / 1024:.0f} KiB")
+    finally:
+        shutil.rmtree(tmp)
+
+
+if __name__ == "__main__":
+    for c in (sys.argv[1:] or list(CASES)):
+        run_case(c)
