@@ -1,0 +1,159 @@
+/* lbm_b200.h -- C ABI of the B200-native lattice-Boltzmann time step.
+ *
+ * This is the drop-in boundary for the hot path of SFCMM/LBM (reference: /root/reference, v0.0.2):
+ * everything LBMSolver::run does between allocateMemory() and the end of the step loop
+ * (src/lbm/solver.cpp:176-197), i.e. the 8-pass timeStep (src/lbm/solver.cpp:307-320), the boundary
+ * kernels (src/lbm/bnd/), the forcing (src/lbm/solver.cpp:626-696) and the residual reduction
+ * (src/lbm/solver.cpp:233-263,809-815).  The reference keeps its grid generator, JSON configuration and
+ * output; it hands this library the tables it already owns and asks for steps.  INTEGRATION.md shows the
+ * binding a maintainer adds to src/lbm/solver.cpp.
+ *
+ * Conventions
+ *   - plain C types; the caller owns every host buffer it passes, the library owns all device memory;
+ *   - every function returns 0 on success and a negative LBM_B200_E* code on failure; the message is
+ *     available from lbm_b200_last_error() (thread-local).  The reference-side wrapper turns a non-zero
+ *     return into TERMM(-1, msg) (src/common/term.h:6-35);
+ *   - one host thread per handle, one CUDA device per handle (reference: single caller thread,
+ *     SURVEY.md section 8b);
+ *   - cell ids, direction indices and variable slots are the reference's: populations i = 0..Q-1 in the
+ *     order of LBMethod<>::m_dirs (src/lbm/constants.h:296-422, rest population last), variables
+ *     u,v[,w],rho (src/lbm/variables.h:12-79), host arrays in the reference's array-of-structures layout
+ *     f[cell*Q + i], vars[cell*NVAR + v] (src/lbm/solver.h:156-172);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     LBM_B200_ECUDA.
+ */
+#ifndef LBM_B200_H
+#define LBM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBM_B200_ABI_VERSION 1
+
+typedef struct lbm_b200_solver lbm_b200_solver;
+
+enum {
+  LBM_B200_OK      = 0,
+  LBM_B200_EINVAL  = -1, /* bad argument / unsupported configuration */
+  LBM_B200_ESTATE  = -2, /* call order violated (e.g. step before init) */
+  LBM_B200_ECUDA   = -3, /* CUDA runtime error or no device */
+  LBM_B200_ENOMEM  = -4,
+  LBM_B200_EUNSUP  = -5  /* semantics of the reference that the device plan cannot reproduce exactly */
+};
+
+enum { LBM_B200_FP64 = 0, LBM_B200_FP32 = 1 };
+/* collision operator: the reference parses only "bgk" (src/lbm/constants.h:70-76); TRT / MRT are extensions */
+enum { LBM_B200_BGK = 0, LBM_B200_TRT = 1, LBM_B200_MRT = 2 };
+/* LBM_B200_STRICT: the reference's operation order, divisions kept, no FMA contraction -> bit-identical to
+ * the reference in fp64.  LBM_B200_FAST: algebraically equal, reciprocal multiplies + FMA (<= 1e-12 rel.). */
+enum { LBM_B200_STRICT = 0, LBM_B200_FAST = 1 };
+
+typedef struct {
+  int32_t abi_version;  /* LBM_B200_ABI_VERSION */
+  int32_t ndim;         /* 2 or 3 */
+  int32_t ndist;        /* 9 (D2Q9), 19 (D3Q19), 27 (D3Q27) -- src/lbm/constants.h:145-162 */
+  int32_t precision;    /* LBM_B200_FP64 / LBM_B200_FP32 */
+  int32_t collision;    /* LBM_B200_BGK / TRT / MRT */
+  int32_t arithmetic;   /* LBM_B200_STRICT / LBM_B200_FAST */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t track_vars;   /* 0: m_vars/m_varsold not kept (residual unavailable, get_moments still works);
+                           1: kept every step; k>1: kept for the two steps before every multiple of k
+                           (k = solver.conv_interval, src/lbm/solver.cpp:76-77,233-234) */
+  double  omega;        /* m_omega, src/lbm/solver.cpp:108-123 */
+  double  omega_minus;  /* TRT: relaxation rate of the antisymmetric part */
+  double  mrt_rates[27]; /* MRT: per-direction-pair rates, see DESIGN.md */
+} lbm_b200_config;
+
+/* Fills *cfg with defaults (D2Q9, fp64, BGK, strict, device 0, track_vars 1, omega 1). */
+void lbm_b200_default_config(lbm_b200_config* cfg);
+
+/* Replaces allocateMemory() (src/lbm/solver.cpp:166-173). ncells = grid().totalSize(). */
+int lbm_b200_create(const lbm_b200_config* cfg, int64_t ncells, lbm_b200_solver** out);
+void lbm_b200_destroy(lbm_b200_solver* s);
+
+/* The push table the reference streams through: nghbr[cell*stride + dir] = CartesianGrid::neighbor(cell,dir)
+ * (src/cartesiangrid.h:111-124), -1 = INVALID_CELLID.  stride = cartesian::maxNoNghbrsDiag<NDIM>() (8 / 26);
+ * only the first Q-1 columns are read.  The table need not be symmetric and is used as is. */
+int lbm_b200_set_topology(lbm_b200_solver* s, const int64_t* nghbr, int32_t stride);
+
+/* Cell centres (grid().center(cell,dir)), the grid bounding box and the cell length on the finest level.
+ * Needed only by the periodic boundary condition and the forcing, which match cells by coordinates
+ * (src/lbm/bnd/bnd_periodic.h:31-98, src/lbm/solver.cpp:651-693). */
+int lbm_b200_set_geometry(lbm_b200_solver* s, const double* center, const double* bbmin, const double* bbmax,
+                          double cell_length);
+
+/* Boundary conditions, to be added in the reference's application order (LBMBndManager::m_bndrys,
+ * src/lbm/bnd/bnd.h:71-142).  cells[k] / normals[k*ndim..] = Surface::getCellList() / normal_p(cell)
+ * (src/common/surface.h:37,69); duplicates in the list are allowed and behave as in the reference. */
+/* LBMBnd_wallBB<..., TANGENTIALVELO> (src/lbm/bnd/bnd_wall.h:9-95); tangential == 0 -> no slip. */
+int lbm_b200_add_wall_bb(lbm_b200_solver* s, const int64_t* cells, const double* normals, int64_t n, double tangential);
+/* LBMBnd_DirichletBB (src/lbm/bnd/bnd_dirichlet.h:24-121); value[ndim] = wall velocity. */
+int lbm_b200_add_dirichlet_bb(lbm_b200_solver* s, const int64_t* cells, const double* normals, int64_t n,
+                              const double* value);
+/* LBMBnd_Pressure, anti-bounce-back (src/lbm/bnd/bnd_pressure.h:12-113). */
+int lbm_b200_add_pressure(lbm_b200_solver* s, const int64_t* cells, const double* normals, int64_t n, double pressure);
+/* LBMBnd_Periodic (src/lbm/bnd/bnd_periodic.h:175-215); connected = cell list of the connected surface;
+ * pressure = NAN for the plain variant. Needs lbm_b200_set_geometry. */
+int lbm_b200_add_periodic(lbm_b200_solver* s, const int64_t* cells, const double* normals, int64_t n,
+                          const int64_t* connected, int64_t nconnected, double pressure);
+/* LBMSolver::forcing (src/lbm/solver.cpp:626-696): inlet = surface "cube_-x", outlet = "cube_+x",
+ * gradient = solver.poiseuillePressureGradient.  Needs lbm_b200_set_geometry. */
+int lbm_b200_set_forcing(lbm_b200_solver* s, const int64_t* inlet, int64_t ninlet, const int64_t* outlet,
+                         int64_t noutlet, double gradient);
+
+/* Optional: run the kernels on this cudaStream_t (default: the legacy default stream). */
+int lbm_b200_set_stream(lbm_b200_solver* s, void* cuda_stream);
+
+/* Replaces initialCondition() (src/lbm/solver.cpp:267-304): builds the device plan, uploads it and sets
+ * rho = 1, u = boundary preset, f = fold = feq.  After this call the topology and BCs are frozen. */
+int lbm_b200_init(lbm_b200_solver* s);
+
+/* Replaces `nsteps` iterations of timeStep() (src/lbm/solver.cpp:307-320). Asynchronous on the stream. */
+int lbm_b200_step(lbm_b200_solver* s, int64_t nsteps);
+int lbm_b200_synchronize(lbm_b200_solver* s);
+
+/* Replaces sumAbsDiff for every variable (src/lbm/solver.cpp:809-815) and the NaN/Inf test
+ * (src/lbm/solver.cpp:254-260): out[v] = sum over cells |vars - varsold|.  Requires track_vars. */
+int lbm_b200_residual(lbm_b200_solver* s, double* out, int32_t* diverged);
+
+/* State read-back in the reference's layout.  Any pointer may be NULL.
+ *   f, fold      : m_f (post-collision) and m_fold (after streaming + boundary conditions) [ncells*Q]
+ *   vars, varsold: m_vars / m_varsold as convergenceCondition() would see them now [ncells*NVAR] (track_vars)
+ *   moments      : what output() recomputes from the current fold (src/lbm/solver.cpp:336) [ncells*NVAR] */
+int lbm_b200_get_populations(lbm_b200_solver* s, double* f, double* fold);
+int lbm_b200_get_vars(lbm_b200_solver* s, double* vars, double* varsold);
+int lbm_b200_get_moments(lbm_b200_solver* s, double* moments);
+/* Overwrites m_f and m_fold (restart / tests).  Both [ncells*Q], reference layout. */
+int lbm_b200_set_populations(lbm_b200_solver* s, const double* f, const double* fold);
+
+int64_t lbm_b200_steps_done(const lbm_b200_solver* s);
+
+/* Plan statistics for DESIGN.md / bench.py. */
+typedef struct {
+  int64_t ncells;          /* cells owned */
+  int64_t cells_fast;      /* cells updated by the template-indexed chunk path (no index traffic) */
+  int64_t cells_generic;   /* cells updated through per-slot link codes */
+  int64_t chunk_cells;     /* cells per SFC chunk */
+  int64_t slots_bc;        /* (cell,dir) slots written by a boundary condition */
+  int64_t slots_stale;     /* slots nothing ever writes (keep their initial value) */
+  int64_t device_bytes;    /* device memory held */
+  int64_t launches;        /* kernels launched since init */
+  int64_t launches_main;   /* of which: fused stream+collide launches */
+  double  bytes_per_cell_alg; /* 2*Q*sizeof(real) */
+} lbm_b200_stats;
+int lbm_b200_get_stats(const lbm_b200_solver* s, lbm_b200_stats* out);
+
+/* Time `nsteps` steps with CUDA events on the solver's stream; *ms_total covers all kernels of those steps,
+ * *ms_main only the fused stream+collide kernel (events around each launch). Synchronous. */
+int lbm_b200_step_timed(lbm_b200_solver* s, int64_t nsteps, float* ms_total, float* ms_main);
+
+const char* lbm_b200_last_error(void);
+int         lbm_b200_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBM_B200_H */

@@ -1,0 +1,241 @@
+"""ctypes binding of the C ABI (include/lbm_b200.h).
+
+`Solver` mirrors the call sequence the reference's LBMSolver::run performs (src/lbm/solver.cpp:176-214):
+create -> set_topology -> (set_geometry) -> add_* boundary conditions in application order -> (set_forcing) ->
+init -> step / residual / read-back.  Errors surface as LbmB200Error carrying the library's message, the way the
+reference surfaces them through TERMM (src/common/term.h:37).
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+_LIB = None
+
+FP64, FP32 = 0, 1
+BGK, TRT, MRT = 0, 1, 2
+STRICT, FAST = 0, 1
+ABI_VERSION = 1
+
+
+class LbmB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"lbm_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("ndim", C.c_int32), ("ndist", C.c_int32), ("precision", C.c_int32),
+                ("collision", C.c_int32), ("arithmetic", C.c_int32), ("device", C.c_int32), ("track_vars", C.c_int32),
+                ("omega", C.c_double), ("omega_minus", C.c_double), ("mrt_rates", C.c_double * 27)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("ncells", C.c_int64), ("cells_fast", C.c_int64), ("cells_generic", C.c_int64), ("chunk_cells", C.c_int64),
+                ("slots_bc", C.c_int64), ("slots_stale", C.c_int64), ("device_bytes", C.c_int64), ("launches", C.c_int64),
+                ("launches_main", C.c_int64), ("bytes_per_cell_alg", C.c_double)]
+
+
+def library_path():
+    return os.path.join(_HERE, "liblbm_b200.so")
+
+
+def build(force=False):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    if force and os.path.exists(library_path()):
+        os.remove(library_path())
+    subprocess.check_call(["make", "-s", "-C", os.path.join(_HERE, "csrc")])
+    return library_path()
+
+
+def abi_symbols():
+    """Every function include/lbm_b200.h declares (used by the CPU-side ABI test)."""
+    text = open(os.path.join(_ROOT, "include", "lbm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lbm_b200_[a-z_0-9]+)\s*\(", text)))
+
+
+def load_library():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise LbmB200Error(-3, f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_double
+    pi64 = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+    pdbl = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+    L.lbm_b200_default_config.argtypes = [C.POINTER(Config)]
+    L.lbm_b200_default_config.restype = None
+    L.lbm_b200_create.argtypes = [C.POINTER(Config), i64, C.POINTER(vp)]
+    L.lbm_b200_destroy.argtypes = [vp]
+    L.lbm_b200_destroy.restype = None
+    L.lbm_b200_set_topology.argtypes = [vp, pi64, i32]
+    L.lbm_b200_set_geometry.argtypes = [vp, pdbl, pdbl, pdbl, dbl]
+    L.lbm_b200_add_wall_bb.argtypes = [vp, pi64, pdbl, i64, dbl]
+    L.lbm_b200_add_dirichlet_bb.argtypes = [vp, pi64, pdbl, i64, pdbl]
+    L.lbm_b200_add_pressure.argtypes = [vp, pi64, pdbl, i64, dbl]
+    L.lbm_b200_add_periodic.argtypes = [vp, pi64, pdbl, i64, pi64, i64, dbl]
+    L.lbm_b200_set_forcing.argtypes = [vp, pi64, i64, pi64, i64, dbl]
+    L.lbm_b200_set_stream.argtypes = [vp, vp]
+    L.lbm_b200_init.argtypes = [vp]
+    L.lbm_b200_step.argtypes = [vp, i64]
+    L.lbm_b200_step_timed.argtypes = [vp, i64, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.lbm_b200_synchronize.argtypes = [vp]
+    L.lbm_b200_residual.argtypes = [vp, pdbl, C.POINTER(i32)]
+    L.lbm_b200_get_populations.argtypes = [vp, vp, vp]
+    L.lbm_b200_set_populations.argtypes = [vp, pdbl, pdbl]
+    L.lbm_b200_get_vars.argtypes = [vp, vp, vp]
+    L.lbm_b200_get_moments.argtypes = [vp, pdbl]
+    L.lbm_b200_steps_done.argtypes = [vp]
+    L.lbm_b200_steps_done.restype = i64
+    L.lbm_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.lbm_b200_last_error.restype = C.c_char_p
+    L.lbm_b200_abi_version.restype = C.c_int
+    _LIB = L
+    return L
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Solver:
+    """One LBM solver instance on one CUDA device (reference: LBMSolver, src/lbm/solver.h:14)."""
+
+    def __init__(self, ndim, ndist, nghbr, omega, *, precision=FP64, collision=BGK, arithmetic=STRICT, device=0,
+                 track_vars=1, omega_minus=None, mrt_rates=None, stream=None):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        nghbr = _i64(nghbr)
+        if nghbr.ndim != 2:
+            raise ValueError("nghbr must be [ncells, stride]")
+        self.ndim, self.ndist, self.nvar = int(ndim), int(ndist), int(ndim) + 1
+        self.n = nghbr.shape[0]
+        cfg = Config()
+        self._lib.lbm_b200_default_config(C.byref(cfg))
+        cfg.ndim, cfg.ndist = self.ndim, self.ndist
+        cfg.precision, cfg.collision, cfg.arithmetic = precision, collision, arithmetic
+        cfg.device, cfg.track_vars = device, track_vars
+        cfg.omega = float(omega)
+        cfg.omega_minus = float(omega if omega_minus is None else omega_minus)
+        rates = np.full(27, float(omega)) if mrt_rates is None else _f64(mrt_rates)
+        for i in range(min(27, len(rates))):
+            cfg.mrt_rates[i] = float(rates[i])
+        self._check(self._lib.lbm_b200_create(C.byref(cfg), self.n, C.byref(self._h)))
+        self._check(self._lib.lbm_b200_set_topology(self._h, nghbr, nghbr.shape[1]))
+        if stream is not None:
+            self.set_stream(stream)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise LbmB200Error(rc, self._lib.lbm_b200_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lbm_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- set-up (same names as oracle.Oracle so tests drive both with one spec)
+    def set_geometry(self, center, bbmin, bbmax, cell_length):
+        self._check(self._lib.lbm_b200_set_geometry(self._h, _f64(center), _f64(bbmin), _f64(bbmax), float(cell_length)))
+
+    def add_wall_bb(self, cells, normals, tangential=0.0):
+        self._check(self._lib.lbm_b200_add_wall_bb(self._h, _i64(cells), _f64(normals), len(cells), float(tangential)))
+
+    def add_dirichlet_bb(self, cells, normals, value):
+        self._check(self._lib.lbm_b200_add_dirichlet_bb(self._h, _i64(cells), _f64(normals), len(cells), _f64(value)))
+
+    def add_pressure(self, cells, normals, pressure):
+        self._check(self._lib.lbm_b200_add_pressure(self._h, _i64(cells), _f64(normals), len(cells), float(pressure)))
+
+    def add_periodic(self, cells, normals, connected, pressure=float("nan")):
+        self._check(self._lib.lbm_b200_add_periodic(self._h, _i64(cells), _f64(normals), len(cells), _i64(connected),
+                                                    len(connected), float(pressure)))
+
+    def set_forcing(self, inlet, outlet, gradient):
+        self._check(self._lib.lbm_b200_set_forcing(self._h, _i64(inlet), len(inlet), _i64(outlet), len(outlet),
+                                                   float(gradient)))
+
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.lbm_b200_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    # ---- run
+    def init(self):
+        self._check(self._lib.lbm_b200_init(self._h))
+
+    def step(self, n=1):
+        self._check(self._lib.lbm_b200_step(self._h, int(n)))
+
+    def step_timed(self, n=1):
+        """Returns (ms over all kernels of the n steps, ms inside the fused stream+collide kernel)."""
+        a, b = C.c_float(), C.c_float()
+        self._check(self._lib.lbm_b200_step_timed(self._h, int(n), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def synchronize(self):
+        self._check(self._lib.lbm_b200_synchronize(self._h))
+
+    def residual(self):
+        out = np.zeros(self.nvar)
+        bad = C.c_int32()
+        self._check(self._lib.lbm_b200_residual(self._h, out, C.byref(bad)))
+        return out, bool(bad.value)
+
+    # ---- read-back (reference layout)
+    def _get2(self, fn, width, want_a, want_b):
+        a = np.empty((self.n, width)) if want_a else None
+        b = np.empty((self.n, width)) if want_b else None
+        pa = a.ctypes.data_as(C.c_void_p) if want_a else None
+        pb = b.ctypes.data_as(C.c_void_p) if want_b else None
+        self._check(fn(self._h, pa, pb))
+        return a, b
+
+    @property
+    def f(self):
+        return self._get2(self._lib.lbm_b200_get_populations, self.ndist, True, False)[0]
+
+    @property
+    def fold(self):
+        return self._get2(self._lib.lbm_b200_get_populations, self.ndist, False, True)[1]
+
+    @property
+    def vars(self):
+        return self._get2(self._lib.lbm_b200_get_vars, self.nvar, True, False)[0]
+
+    @property
+    def varsold(self):
+        return self._get2(self._lib.lbm_b200_get_vars, self.nvar, False, True)[1]
+
+    def moments(self):
+        out = np.empty((self.n, self.nvar))
+        self._check(self._lib.lbm_b200_get_moments(self._h, out))
+        return out
+
+    def set_populations(self, f, fold):
+        self._check(self._lib.lbm_b200_set_populations(self._h, _f64(f), _f64(fold)))
+
+    @property
+    def steps_done(self):
+        return int(self._lib.lbm_b200_steps_done(self._h))
+
+    def stats(self):
+        st = Stats()
+        self._check(self._lib.lbm_b200_get_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in Stats._fields_}

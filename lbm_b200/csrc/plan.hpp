@@ -1,0 +1,548 @@
+// plan.hpp -- host-side device plan: turns the reference's tables into the B200 data layout.
+//
+// Input  (reference semantics): the push table CartesianGrid::neighbor(cell,dir)
+//         (/root/reference/src/cartesiangrid.h:111-124), boundary conditions in application order
+//         (src/lbm/bnd/bnd.h:71-142), optional forcing (src/lbm/solver.cpp:626-696).
+// Output (device semantics): for every population slot fold[c,j] exactly one *link* that says where its value
+//         comes from after the reference's passes 6-8 (preApply -> push -> apply) have all run:
+//           PULL(src)    the push source (inverse of the push table; the table is NOT assumed symmetric)
+//           BB / BB_ADD  bounce back (+ moving-wall addends, added one by one like the reference does)
+//           ABB          anti bounce back pressure
+//           COPY         periodic boundary condition copy
+//           VALUE        a stored number: slots nothing ever writes keep their initial value (the reference never
+//                        clears m_fold), periodic-with-pressure slots get a value recomputed every step
+//         "last writer wins" is resolved here, once, in the reference's order.
+// Layout: cells are regrouped into SFC chunks (aligned cubes of the reference's curve: 8^3 cells in 3D, 32^2 in
+//         2D).  Chunks in which every slot is a plain pull that follows the curve's template ("fast" chunks) need
+//         no per-cell index at all: one shared template + 3^D neighbour-chunk bases per chunk.  Everything else
+//         goes through 32-bit link codes.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "lattice.h"
+
+namespace lbm {
+
+static constexpr double kEps = std::numeric_limits<double>::epsilon(); // GDoubleEps, include/common/sfcmm_types.h:50
+
+enum BcKind { BC_WALL_BB = 1, BC_WALL_BB_TANGENTIAL = 2, BC_DIRICHLET_BB = 3, BC_PRESSURE = 4, BC_PERIODIC = 5 };
+
+struct BcInput {
+  int                  kind = 0;
+  std::vector<int64_t> cells;
+  std::vector<double>  normals;   // n * D
+  double               value[3] = {0, 0, 0};
+  double               tangential = 0;
+  double               pressure   = std::numeric_limits<double>::quiet_NaN();
+  std::vector<int64_t> connected; // periodic
+};
+
+struct PlanInput {
+  LatticeRT            L;
+  int64_t              n = 0;
+  int                  stride = 0;
+  const int64_t*       nghbr = nullptr; // caller memory, valid during build
+  std::vector<double>  center;          // n*D or empty
+  double               bbmin[3] = {0, 0, 0}, bbmax[3] = {0, 0, 0}, cell_length = 0;
+  std::vector<BcInput> bcs;
+  bool                 forcing = false;
+  std::vector<int64_t> inlet, outlet;
+  double               gradient = 0;
+};
+
+struct CopySrc { int32_t cell, dir; };
+struct AddEntry { double v[3]; int32_t n; int32_t pad; };
+// one anti-bounce-back (pressure) boundary entry: u_ext = 1.5 u(n1) - 0.5 u(n2)   (bnd_pressure.h:78-84)
+struct AbbEntry { int32_t cell, n1, n2, pad; double p; };
+// forcing: f[target,:] = eq(w, p, cu(val), vsq(val)) + f[val,:] - feq[val,:]      (solver.cpp:651-693)
+struct ForceEntry { int32_t target, val; double p; };
+// periodic with pressure: value[vbase+i] = eq(i,p,u(c)) + f[c,i] - feq[c,i]        (bnd_periodic.h:101-108)
+struct PerPEntry { int32_t cell, vbase; double p; };
+// m_vars fix-ups done by boundary conditions after the moments pass, resolved to the last writer
+struct VarFix { int32_t cell, var, abb, comp; double value; }; // abb >= 0: vars = uext[abb][comp]; else constant
+
+struct Plan {
+  LatticeRT L;
+  int64_t   n = 0;         // reference cells
+  int64_t   npad = 0;      // device cells (stride of the SoA arrays)
+  int       CH = 0;
+  int64_t   n_fast_chunks = 0, n_slow_chunks = 0, n_loose = 0;
+  int64_t   gen_begin = 0; // first device cell of the generic range
+  int64_t   n_gen = 0;     // cells in the generic range
+  int64_t   gen_stride = 0;
+  std::vector<int32_t>  ref2dev, dev2ref;
+  std::vector<uint16_t> tmpl;       // (Q-1) * CH : sel << 10 | off
+  std::vector<int32_t>  chunk_nb;   // n_fast_chunks * NSEL device bases
+  std::vector<int32_t>  codes;      // (Q-1) * gen_stride
+  std::vector<CopySrc>  copytab;
+  std::vector<AddEntry> addtab;
+  std::vector<AbbEntry> abb;
+  std::vector<double>   values;     // static part first, then dynamic part
+  std::vector<int64_t>  stale_ref;  // per static value k>=1: device cell * Q + dir of the stale slot it backs
+  int64_t               n_values_static = 0;
+  std::vector<ForceEntry> force;
+  std::vector<PerPEntry>  perp;
+  std::vector<VarFix>     varfix;
+  std::vector<int32_t>    u0_cells; // cells with a preset initial velocity (Dirichlet BB, bnd_dirichlet.h:44-50)
+  std::vector<double>     u0_vals;  // D per entry
+  int64_t slots_bc = 0, slots_stale = 0;
+  std::string error;
+};
+
+inline bool in_direction(const LatticeRT& L, const double* normal, int dist) {
+  double dot = 0; // constants.h:83-86
+  for(int d = 0; d < L.D; ++d) dot += normal[d] * L.c[dist][d];
+  return dot >= kEps;
+}
+
+// offset along the curve inside one chunk <-> local coordinates (see sfc_lut in lattice.h)
+inline void chunk_offset_to_xyz(const LatticeRT& L, int off, int* xyz) {
+  xyz[0] = xyz[1] = xyz[2] = 0;
+  const int bits = L.D;
+  for(int l = 0; l < L.CHUNK_LEVELS; ++l) {
+    const int digit = (off >> (bits * (L.CHUNK_LEVELS - 1 - l))) & ((1 << bits) - 1);
+    const int q     = sfc_lut_inv(digit);
+    for(int d = 0; d < L.D; ++d) xyz[d] = (xyz[d] << 1) | ((q >> d) & 1);
+  }
+}
+inline int chunk_xyz_to_offset(const LatticeRT& L, const int* xyz) {
+  int off = 0;
+  for(int l = 0; l < L.CHUNK_LEVELS; ++l) {
+    int q = 0;
+    for(int d = 0; d < L.D; ++d) q |= ((xyz[d] >> (L.CHUNK_LEVELS - 1 - l)) & 1) << d;
+    off = (off << L.D) | sfc_lut(q);
+  }
+  return off;
+}
+
+// template entry for slot (offset o, direction j): which neighbour chunk the pull source lies in and where
+inline void build_template(const LatticeRT& L, std::vector<uint16_t>& tmpl) {
+  const int S = 1 << L.CHUNK_LEVELS;
+  tmpl.assign(static_cast<size_t>(L.Q - 1) * L.CHUNK, 0);
+  for(int o = 0; o < L.CHUNK; ++o) {
+    int xyz[3];
+    chunk_offset_to_xyz(L, o, xyz);
+    for(int j = 0; j < L.Q - 1; ++j) {
+      int src[3] = {0, 0, 0}, sel = 0, mul = 1;
+      for(int d = 0; d < L.D; ++d) {
+        int v = xyz[d] - L.c[j][d]; // pull: the source sits one step against the direction
+        int s = 1;
+        if(v < 0) { v += S; s = 0; }
+        else if(v >= S) { v -= S; s = 2; }
+        src[d] = v;
+        sel += s * mul;
+        mul *= 3;
+      }
+      tmpl[static_cast<size_t>(j) * L.CHUNK + o] = static_cast<uint16_t>((sel << 10) | chunk_xyz_to_offset(L, src));
+    }
+  }
+}
+
+struct SlotDesc {
+  int     kind;      // LinkKind, or -1 for "dynamic value of periodic-with-pressure"
+  int64_t a = 0;     // COPY: src cell (ref id); ABB: entry id; VALUE(dyn): value index
+  int     b = 0;     // COPY: dir
+  double  add[3] = {0, 0, 0};
+  int     nadd = 0;
+};
+
+inline int self_sel(const LatticeRT& L) { return L.D == 2 ? 4 : 13; }
+
+inline bool build_plan(const PlanInput& in, Plan& P) {
+  const LatticeRT& L = in.L;
+  const int     Q = L.Q, D = L.D, QM = L.Q - 1, CH = L.CHUNK;
+  const int64_t N = in.n;
+  P = Plan();
+  P.L = L;
+  P.n = N;
+  P.CH = CH;
+  if(N <= 0 || in.nghbr == nullptr) { P.error = "no topology set"; return false; }
+  if(N >= (int64_t(1) << 28) * 8) { P.error = "too many cells for 32-bit device indices"; return false; }
+  if(in.stride < QM) { P.error = "neighbour table stride smaller than Q-1"; return false; }
+  auto NB = [&](int64_t c, int j) -> int64_t { return in.nghbr[c * in.stride + j]; };
+
+  // ---- 1. pull table = inverse of the push table (serial order: the highest source wins, like the
+  //         reference's loop would leave it if two cells pushed to one slot)
+  std::vector<int32_t> pull(static_cast<size_t>(N) * QM, -1);
+#pragma omp parallel for schedule(static)
+  for(int j = 0; j < QM; ++j) {
+    for(int64_t s = 0; s < N; ++s) {
+      const int64_t t = NB(s, j);
+      if(t >= 0 && t < N) pull[static_cast<size_t>(t) * QM + j] = static_cast<int32_t>(s);
+    }
+  }
+  for(int64_t s = 0; s < N; ++s)
+    for(int j = 0; j < QM; ++j)
+      if(NB(s, j) >= N || NB(s, j) < -1) { P.error = "neighbour id out of range"; return false; }
+
+  // ---- 2. boundary conditions, in the reference's order: preApply writes, then the push, then apply writes
+  std::unordered_map<int64_t, SlotDesc> over;  // slot key c*Q+j -> final descriptor
+  auto key = [&](int64_t c, int j) { return c * Q + j; };
+  std::vector<char> is_bc_cell(static_cast<size_t>(N), 0);
+
+  // 2a. preApply (periodic). A slot that also has a push source is overwritten by the push afterwards.
+  for(const BcInput& bc : in.bcs) {
+    if(bc.kind != BC_PERIODIC) continue;
+    if(in.center.empty()) { P.error = "periodic boundary condition needs set_geometry"; return false; }
+    const int64_t nb = static_cast<int64_t>(bc.cells.size());
+    const double  maxMatch = 10 * kEps;
+    for(int64_t k = 0; k < nb; ++k) {
+      const int64_t c   = bc.cells[k];
+      const double* nrm = &bc.normals[k * D];
+      const double* ctr = &in.center[c * D];
+      // bnd_periodic.h:42-57: outward directions whose tangentially shifted target stays inside the bounding box
+      int    setd[27], ns = 0;
+      for(int dist = 0; dist < Q; ++dist) {
+        if(!in_direction(L, nrm, dist)) continue;
+        bool inside = true;
+        for(int d = 0; d < D; ++d) {
+          const double x = std::abs(nrm[d]) > 0 ? in.bbmin[d] : ctr[d] + L.c[dist][d] * in.cell_length;
+          if(x < in.bbmin[d] || x > in.bbmax[d]) inside = false;
+        }
+        if(inside) setd[ns++] = dist;
+      }
+      // bnd_periodic.h:59-98: first cell of the connected surface that matches in ANY coordinate
+      int64_t links[27];
+      for(int id = 0; id < ns; ++id) {
+        double ca[3];
+        for(int d = 0; d < D; ++d) ca[d] = std::abs(nrm[d]) > 0 ? ctr[d] : ctr[d] + L.c[setd[id]][d] * in.cell_length;
+        int64_t link = -1;
+        for(size_t q = 0; q < bc.connected.size() && link < 0; ++q) {
+          const double* cb = &in.center[bc.connected[q] * D];
+          for(int d = 0; d < D; ++d)
+            if(std::abs(ca[d] - cb[d]) <= maxMatch) { link = bc.connected[q]; break; }
+        }
+        if(link < 0) { P.error = "periodic boundary: no cell to link"; return false; }
+        links[id] = link;
+      }
+      if(ns == 0) { P.error = "periodic boundary cell without outward direction"; return false; }
+      if(!std::isnan(bc.pressure)) {
+        // bnd_periodic.h:101-108: all Q populations of the first linked cell get a recomputed value
+        PerPEntry e;
+        e.cell  = static_cast<int32_t>(c); // ref id for now
+        e.vbase = static_cast<int32_t>(P.perp.size()) * Q; // dynamic value index, rebased below
+        e.p     = bc.pressure;
+        P.perp.push_back(e);
+        for(int i = 0; i < Q; ++i) {
+          SlotDesc sd;
+          sd.kind = -1;
+          sd.a    = e.vbase + i;
+          over[key(links[0], i)] = sd;
+        }
+        P.varfix.push_back(VarFix{static_cast<int32_t>(links[0]), D, -1, 0, bc.pressure});
+      } else {
+        for(int id = 0; id < ns; ++id) {
+          SlotDesc sd;
+          sd.kind = LK_COPY;
+          sd.a    = c;
+          sd.b    = setd[id];
+          over[key(links[id], setd[id])] = sd;
+        }
+        P.varfix.push_back(VarFix{static_cast<int32_t>(links[0]), D, -1, 0, 1.0});
+      }
+    }
+  }
+  // preApply of the pressure BC only sets rho (bnd_pressure.h:43-50); apply sets it again to the same value.
+  // 2b. the push overrides preApply writes
+  for(auto it = over.begin(); it != over.end();) {
+    const int64_t c = it->first / Q;
+    const int     j = static_cast<int>(it->first % Q);
+    if(j < QM && pull[static_cast<size_t>(c) * QM + j] >= 0) it = over.erase(it);
+    else ++it;
+  }
+  // the rest population is "pushed" onto itself (solver.cpp:737): fold[c,Q-1] = f[c,Q-1] always wins over preApply
+  for(auto it = over.begin(); it != over.end();) {
+    if(static_cast<int>(it->first % Q) == QM) it = over.erase(it);
+    else ++it;
+  }
+
+  // 2c. apply, in order
+  std::vector<char> abb_cell(static_cast<size_t>(N), 0);
+  for(const BcInput& bc : in.bcs) {
+    const int64_t nb = static_cast<int64_t>(bc.cells.size());
+    if(bc.kind == BC_WALL_BB_TANGENTIAL && D != 2) {
+      P.error = "tangential wall velocity is implemented for 2D only (reference: bnd_wall.h:52-54)";
+      return false;
+    }
+    for(int64_t k = 0; k < nb; ++k) {
+      const int64_t c = bc.cells[k];
+      if(c < 0 || c >= N) { P.error = "boundary cell id out of range"; return false; }
+      const double* nrm = &bc.normals[k * D];
+      if(bc.kind == BC_PERIODIC) continue;
+      int abb_id = -1;
+      if(bc.kind == BC_PRESSURE) {
+        // bnd_pressure.h:58-84
+        int ins = -1;
+        for(int d = 0; d < D && ins < 0; ++d) {
+          if(nrm[d] < 0) ins = 2 * d + 1;
+          else if(nrm[d] > 0) ins = 2 * d;
+        }
+        if(ins < 0) { P.error = "pressure boundary: zero normal"; return false; }
+        const int64_t n1 = NB(c, ins);
+        const int64_t n2 = n1 >= 0 ? NB(n1, ins) : -1;
+        if(n1 < 0 || n2 < 0) { P.error = "pressure boundary: cell without two inward neighbours"; return false; }
+        // the reference applies entries one after the other and reads m_vars of n1/n2: if one of them had its
+        // velocity rewritten by an earlier pressure entry of the same pass the result depends on that order
+        if(abb_cell[n1] || abb_cell[n2]) {
+          P.error = "pressure boundary: inward neighbour is itself a pressure boundary cell (order-dependent in the reference)";
+          return false;
+        }
+        AbbEntry e;
+        e.cell = static_cast<int32_t>(c);
+        e.n1   = static_cast<int32_t>(n1);
+        e.n2   = static_cast<int32_t>(n2);
+        e.pad  = 0;
+        e.p    = bc.pressure;
+        abb_id = static_cast<int>(P.abb.size());
+        P.abb.push_back(e);
+        P.varfix.push_back(VarFix{static_cast<int32_t>(c), D, -1, 0, bc.pressure});
+        for(int d = 0; d < D; ++d) P.varfix.push_back(VarFix{static_cast<int32_t>(c), d, abb_id, d, 0.0});
+      }
+      for(int i = 0; i < QM; ++i) {
+        if(NB(c, i) != -1 || !in_direction(L, nrm, i)) continue; // bnd_dirichlet.h:86-88
+        const int op = L.opp[i];
+        SlotDesc  sd;
+        switch(bc.kind) {
+          case BC_WALL_BB: sd.kind = LK_BB; break;
+          case BC_WALL_BB_TANGENTIAL: {
+            // bnd_wall.h:31-72: value[inside dir] = u_t * (t . c_inside), t = (n_y, n_x); bnd_dirichlet.h:111-112
+            const double t[2] = {nrm[1], nrm[0]};
+            const double tdot = t[0] * L.c[op][0] + t[1] * L.c[op][1];
+            const double ndot = nrm[0] * L.c[op][0] + nrm[1] * L.c[op][1];
+            const double nn   = std::sqrt(double(L.c[op][0] * L.c[op][0] + L.c[op][1] * L.c[op][1]));
+            const bool parallel = std::abs(std::acos(ndot / nn) - 3.14159265358979323846) < 10 * kEps;
+            const double val    = parallel ? 0.0 : bc.tangential * tdot;
+            sd.kind   = LK_BB_ADD;
+            sd.add[0] = 1.0 * 2.0 / (1.0 / 3.0) * L.w[op] * val;
+            sd.nadd   = 1;
+            break;
+          }
+          case BC_DIRICHLET_BB: {
+            // bnd_dirichlet.h:113-117: one addition per dimension, in order
+            sd.kind = LK_BB_ADD;
+            sd.nadd = D;
+            for(int d = 0; d < D; ++d) sd.add[d] = 1.0 * 2.0 / (1.0 / 3.0) * L.w[op] * L.c[op][d] * bc.value[d];
+            break;
+          }
+          case BC_PRESSURE: sd.kind = LK_ABB; sd.a = abb_id; break;
+          default: P.error = "unknown boundary kind"; return false;
+        }
+        over[key(c, op)] = sd;
+      }
+      if(bc.kind == BC_PRESSURE) abb_cell[c] = 1;
+      if(bc.kind == BC_DIRICHLET_BB) {
+        P.u0_cells.push_back(static_cast<int32_t>(c));
+        for(int d = 0; d < D; ++d) P.u0_vals.push_back(bc.value[d]);
+      }
+    }
+  }
+  // a pressure entry that reads the velocity of a cell which a LATER entry rewrites is fine (it reads the raw
+  // moments, as the reference does); an EARLIER one was rejected above.
+
+  // ---- 3. forcing pairs (solver.cpp:651-693), resolved once instead of an O(N_in*N_out) search per step
+  if(in.forcing) {
+    if(in.center.empty()) { P.error = "forcing needs set_geometry"; return false; }
+    std::unordered_map<int32_t, size_t> written;
+    auto add_force = [&](int64_t target, int64_t val, double p) -> bool {
+      if(val < 0) { P.error = "forcing: boundary cell without x-neighbour"; return false; }
+      auto it = written.find(static_cast<int32_t>(target));
+      ForceEntry e{static_cast<int32_t>(target), static_cast<int32_t>(val), p};
+      if(it != written.end()) P.force[it->second] = e; // a later match overwrites an earlier one
+      else { written[static_cast<int32_t>(target)] = P.force.size(); P.force.push_back(e); }
+      return true;
+    };
+    for(int64_t a : in.inlet) {
+      const int64_t val = NB(a, 1);
+      if(val < 0) { P.error = "forcing: inlet cell without +x neighbour"; return false; }
+      for(int64_t b : in.outlet)
+        if(std::abs(in.center[val * D + 1] - in.center[b * D + 1]) < kEps)
+          if(!add_force(b, val, 1.0)) return false;
+    }
+    for(int64_t b : in.outlet) {
+      const int64_t val = NB(b, 0);
+      if(val < 0) { P.error = "forcing: outlet cell without -x neighbour"; return false; }
+      for(int64_t a : in.inlet)
+        if(std::abs(in.center[a * D + 1] - in.center[val * D + 1]) < kEps)
+          if(!add_force(a, val, 1.0 + in.gradient)) return false;
+    }
+    for(const ForceEntry& e : P.force)
+      if(written.count(e.val)) { P.error = "forcing: value cell is itself a forced cell (order-dependent in the reference)"; return false; }
+  }
+
+  // ---- 4. classify cells: plain = every slot is a pull
+  std::vector<char> plain(static_cast<size_t>(N), 1);
+#pragma omp parallel for schedule(static)
+  for(int64_t c = 0; c < N; ++c)
+    for(int j = 0; j < QM; ++j)
+      if(pull[static_cast<size_t>(c) * QM + j] < 0) { plain[c] = 0; break; }
+  for(const auto& kv : over) plain[kv.first / Q] = 0;
+
+  // ---- 5. SFC chunks: runs of CH consecutive cells that are internally ordered like the curve template
+  build_template(L, P.tmpl);
+  const int SELF = self_sel(L);
+  std::vector<int64_t> cand_base; // reference index of the first cell of every candidate chunk
+  std::vector<int32_t> chunk_of(static_cast<size_t>(N), -1);
+  {
+    int64_t b = 0;
+    while(b + CH <= N) {
+      bool ok = true;
+      for(int o = 0; o < CH && ok; ++o) {
+        for(int j = 0; j < QM; ++j) {
+          const uint16_t t = P.tmpl[static_cast<size_t>(j) * CH + o];
+          if((t >> 10) != SELF) continue;
+          if(pull[static_cast<size_t>(b + o) * QM + j] != b + (t & 1023)) { ok = false; break; }
+        }
+      }
+      if(ok) {
+        for(int o = 0; o < CH; ++o) chunk_of[b + o] = static_cast<int32_t>(cand_base.size());
+        cand_base.push_back(b);
+        b += CH;
+      } else {
+        b += 1;
+      }
+    }
+  }
+  const int64_t nc = static_cast<int64_t>(cand_base.size());
+  // fast chunk: all cells plain, every cross-chunk pull lands in a candidate chunk at the template offset
+  std::vector<char>    fast(static_cast<size_t>(nc), 0);
+  std::vector<int64_t> nbref(static_cast<size_t>(nc) * L.NSEL, -1);
+#pragma omp parallel for schedule(dynamic, 64)
+  for(int64_t k = 0; k < nc; ++k) {
+    const int64_t b = cand_base[k];
+    bool ok = true;
+    int64_t* nbk = &nbref[static_cast<size_t>(k) * L.NSEL];
+    nbk[SELF] = b;
+    for(int o = 0; o < CH && ok; ++o) {
+      if(!plain[b + o]) { ok = false; break; }
+      for(int j = 0; j < QM; ++j) {
+        const uint16_t t   = P.tmpl[static_cast<size_t>(j) * CH + o];
+        const int      sel = t >> 10;
+        const int64_t  src = pull[static_cast<size_t>(b + o) * QM + j];
+        const int64_t  nb0 = src - (t & 1023);
+        if(nbk[sel] == -1) {
+          if(nb0 < 0 || nb0 + CH > N || chunk_of[nb0] < 0 || cand_base[chunk_of[nb0]] != nb0) { ok = false; break; }
+          nbk[sel] = nb0;
+        } else if(nbk[sel] != nb0) { ok = false; break; }
+      }
+    }
+    fast[k] = ok ? 1 : 0;
+  }
+
+  // ---- 6. device layout: fast chunks, slow chunks (kept contiguous so fast chunks can address them by
+  //         template), loose cells; all in reference (SFC) order within their group
+  P.ref2dev.assign(static_cast<size_t>(N), -1);
+  std::vector<int64_t> cand_dev(static_cast<size_t>(nc), -1);
+  int64_t pos = 0;
+  for(int64_t k = 0; k < nc; ++k) if(fast[k]) { cand_dev[k] = pos; pos += CH; ++P.n_fast_chunks; }
+  P.gen_begin = pos;
+  for(int64_t k = 0; k < nc; ++k) if(!fast[k]) { cand_dev[k] = pos; pos += CH; ++P.n_slow_chunks; }
+  for(int64_t k = 0; k < nc; ++k)
+    for(int o = 0; o < CH; ++o) P.ref2dev[cand_base[k] + o] = static_cast<int32_t>(cand_dev[k] + o);
+  for(int64_t c = 0; c < N; ++c)
+    if(chunk_of[c] < 0) { P.ref2dev[c] = static_cast<int32_t>(pos++); ++P.n_loose; }
+  P.n_gen  = pos - P.gen_begin;
+  P.npad   = (pos + 63) / 64 * 64;
+  P.gen_stride = (P.n_gen + 63) / 64 * 64;
+  P.dev2ref.assign(static_cast<size_t>(P.npad), -1);
+  for(int64_t c = 0; c < N; ++c) P.dev2ref[P.ref2dev[c]] = static_cast<int32_t>(c);
+
+  P.chunk_nb.assign(static_cast<size_t>(P.n_fast_chunks) * L.NSEL, 0);
+  {
+    int64_t f = 0;
+    for(int64_t k = 0; k < nc; ++k) {
+      if(!fast[k]) continue;
+      for(int s = 0; s < L.NSEL; ++s) {
+        const int64_t r = nbref[static_cast<size_t>(k) * L.NSEL + s];
+        // a selector no slot uses (e.g. cube corners for D3Q19) stays at the chunk itself
+        P.chunk_nb[static_cast<size_t>(f) * L.NSEL + s] = static_cast<int32_t>(r < 0 ? cand_dev[k] : cand_dev[chunk_of[r]]);
+      }
+      ++f;
+    }
+  }
+
+  // ---- 7. link codes of the generic range
+  // dynamic values (periodic with pressure) come after the static ones in the value table
+  P.codes.assign(static_cast<size_t>(QM) * P.gen_stride, link_code(LK_VALUE, 0));
+  // value 0 is a dummy for padding cells
+  P.values.assign(1, 0.0);
+  std::vector<std::pair<int64_t, int64_t>> stale_slots; // (ref cell, dir) -> static value index, filled at init
+  std::vector<std::pair<size_t, int64_t>>  dyn_codes;   // code position -> dynamic value index
+  for(int64_t c = 0; c < N; ++c) {
+    const int64_t dv = P.ref2dev[c];
+    if(dv < P.gen_begin) continue;
+    const int64_t g = dv - P.gen_begin;
+    for(int j = 0; j < QM; ++j) {
+      const size_t  at = static_cast<size_t>(j) * P.gen_stride + g;
+      auto          it = over.find(key(c, j));
+      const int32_t ps = pull[static_cast<size_t>(c) * QM + j];
+      if(it == over.end()) {
+        if(ps >= 0) P.codes[at] = P.ref2dev[ps];
+        else {
+          // nothing ever writes this slot: it keeps the value initialCondition() gave it
+          P.codes[at] = link_code(LK_VALUE, static_cast<int32_t>(P.values.size()));
+          stale_slots.emplace_back(c, j);
+          P.values.push_back(0.0);
+          ++P.slots_stale;
+        }
+        continue;
+      }
+      const SlotDesc& sd = it->second;
+      ++P.slots_bc;
+      switch(sd.kind) {
+        case LK_COPY:
+          P.codes[at] = link_code(LK_COPY, static_cast<int32_t>(P.copytab.size()));
+          P.copytab.push_back(CopySrc{P.ref2dev[sd.a], sd.b});
+          break;
+        case LK_BB: P.codes[at] = link_code(LK_BB, 0); break;
+        case LK_BB_ADD: {
+          AddEntry e;
+          e.n = sd.nadd;
+          e.pad = 0;
+          for(int d = 0; d < 3; ++d) e.v[d] = sd.add[d];
+          P.codes[at] = link_code(LK_BB_ADD, static_cast<int32_t>(P.addtab.size()));
+          P.addtab.push_back(e);
+          break;
+        }
+        case LK_ABB: P.codes[at] = link_code(LK_ABB, static_cast<int32_t>(sd.a)); break;
+        case -1: dyn_codes.emplace_back(at, sd.a); break;
+        default: P.error = "internal: bad slot kind"; return false;
+      }
+    }
+  }
+  P.n_values_static = static_cast<int64_t>(P.values.size());
+  for(auto& dc : dyn_codes) P.codes[dc.first] = link_code(LK_VALUE, static_cast<int32_t>(P.n_values_static + dc.second));
+  P.values.resize(P.values.size() + P.perp.size() * Q, 0.0);
+  if(P.values.size() >= (size_t(1) << 28) || P.copytab.size() >= (size_t(1) << 28) || P.addtab.size() >= (size_t(1) << 28)) {
+    P.error = "too many boundary slots for 28-bit payloads";
+    return false;
+  }
+  // stale slot bookkeeping: remember (cell, dir) so init can store the initial equilibrium there
+  P.stale_ref.reserve(stale_slots.size());
+  for(auto& s : stale_slots) P.stale_ref.push_back(static_cast<int64_t>(P.ref2dev[s.first]) * Q + s.second);
+
+  // ---- 8. translate the remaining reference ids to device ids
+  for(AbbEntry& e : P.abb) { e.cell = P.ref2dev[e.cell]; e.n1 = P.ref2dev[e.n1]; e.n2 = P.ref2dev[e.n2]; }
+  for(ForceEntry& e : P.force) { e.target = P.ref2dev[e.target]; e.val = P.ref2dev[e.val]; }
+  for(PerPEntry& e : P.perp) { e.cell = P.ref2dev[e.cell]; e.vbase += static_cast<int32_t>(P.n_values_static); }
+  for(VarFix& v : P.varfix) v.cell = P.ref2dev[v.cell];
+  for(int32_t& c : P.u0_cells) c = P.ref2dev[c];
+  {
+    // m_vars fix-ups: keep only the last writer of every (cell, variable), in the reference's order
+    std::unordered_map<int64_t, size_t> last;
+    for(size_t i = 0; i < P.varfix.size(); ++i) last[static_cast<int64_t>(P.varfix[i].cell) * 8 + P.varfix[i].var] = i;
+    std::vector<VarFix> kept;
+    for(size_t i = 0; i < P.varfix.size(); ++i)
+      if(last[static_cast<int64_t>(P.varfix[i].cell) * 8 + P.varfix[i].var] == i) kept.push_back(P.varfix[i]);
+    P.varfix.swap(kept);
+  }
+  return true;
+}
+
+} // namespace lbm

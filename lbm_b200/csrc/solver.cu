@@ -1,0 +1,736 @@
+// solver.cu -- C ABI (include/lbm_b200.h) on top of the device plan (plan.hpp) and the kernels (kernels.cuh).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/lbm_b200.h"
+#include "kernels.cuh"
+#include "plan.hpp"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) {
+  g_error = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                                  \
+  do {                                                                                                  \
+    cudaError_t e_ = (expr);                                                                            \
+    if(e_ != cudaSuccess)                                                                               \
+      return fail(LBM_B200_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));                  \
+  } while(0)
+
+template <class T>
+struct DevBuf {
+  T*     p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { if(p) cudaFree(p); }
+  cudaError_t alloc(size_t count) {
+    if(p) cudaFree(p);
+    p = nullptr;
+    n = count;
+    if(count == 0) return cudaSuccess;
+    return cudaMalloc(&p, count * sizeof(T));
+  }
+  cudaError_t upload(const std::vector<T>& h) {
+    cudaError_t e = alloc(h.size());
+    if(e != cudaSuccess || h.empty()) return e;
+    return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+struct SolverBase {
+  virtual ~SolverBase() = default;
+  virtual int init()                                                     = 0;
+  virtual int step(int64_t n, float* ms_total, float* ms_main)           = 0;
+  virtual int sync()                                                     = 0;
+  virtual int residual(double* out, int32_t* diverged)                   = 0;
+  virtual int get_populations(double* f, double* fold)                   = 0;
+  virtual int set_populations(const double* f, const double* fold)       = 0;
+  virtual int get_vars(double* vars, double* varsold)                    = 0;
+  virtual int get_moments(double* m)                                     = 0;
+  virtual void stats(lbm_b200_stats* st) const                           = 0;
+  lbm_b200_config cfg{};
+  lbm::PlanInput  in;
+  std::vector<int64_t> nghbr_copy;
+  cudaStream_t    stream = nullptr;
+  bool            inited = false;
+  int64_t         t      = 0;
+};
+
+template <class L, class Real>
+struct Solver final : SolverBase {
+  static constexpr int Q = L::Q, D = L::D, NVAR = L::D + 1;
+  lbm::Plan plan;
+  // device state
+  DevBuf<Real>     f[2];      // populations, double buffered; f[cur] = m_f of the reference after t steps
+  DevBuf<Real>     prev_fold; // only after set_populations: an explicit m_fold to start from
+  DevBuf<Real>     vars[2];   // tracked m_vars / m_varsold
+  DevBuf<Real>     scratch;   // [max(Q,NVAR)][npad] read-back staging
+  DevBuf<uint16_t> d_tmpl;
+  DevBuf<int32_t>  d_chunk_nb, d_codes;
+  DevBuf<lbm::CopySrcDev>       d_copy;
+  DevBuf<lbm::AddEntryT<Real>>  d_add;
+  DevBuf<lbm::AbbDev<Real>>     d_abb;
+  DevBuf<lbm::ForceDev<Real>>   d_force;
+  DevBuf<lbm::PerPDev<Real>>    d_perp;
+  DevBuf<lbm::VarFixDev<Real>>  d_varfix;
+  DevBuf<Real>     d_uext[2], d_values[2];
+  DevBuf<double>   d_partial;
+  int cur = 0;       // f[cur] holds the current post-collision populations
+  int dyn = 0;       // d_uext[dyn] / d_values[dyn] are the ones the next gather must use
+  int vcur = 0;      // vars[vcur] = m_vars, vars[vcur^1] = m_varsold
+  int64_t vars_step[2] = {-1, -1};
+  bool    first = true; // next step is step 0 of the reference loop (m_fold = initial condition)
+  int     n_fast_blocks = 0, n_gen_blocks = 0;
+  int64_t launches = 0, launches_main = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr;
+
+  ~Solver() override {
+    if(ev0) cudaEventDestroy(ev0);
+    if(ev1) cudaEventDestroy(ev1);
+    if(evm0) cudaEventDestroy(evm0);
+    if(evm1) cudaEventDestroy(evm1);
+  }
+
+  lbm::DevParams<Real> params(int src, int dst, Real* vars_out) const {
+    lbm::DevParams<Real> p{};
+    p.A = f[src].p;
+    p.B = f[dst].p;
+    p.stride = plan.npad;
+    p.tmpl = d_tmpl.p;
+    p.chunk_nb = d_chunk_nb.p;
+    p.n_fast_chunks = static_cast<int32_t>(plan.n_fast_chunks);
+    p.n_fast_blocks = n_fast_blocks;
+    p.gen_begin = static_cast<int32_t>(plan.gen_begin);
+    p.n_gen = static_cast<int32_t>(plan.n_gen);
+    p.n_gen_blocks = n_gen_blocks;
+    p.gen_stride = plan.gen_stride;
+    p.codes = d_codes.p;
+    p.tabs.copytab = d_copy.p;
+    p.tabs.addtab = d_add.p;
+    p.tabs.abb = d_abb.p;
+    p.tabs.uext = d_uext[dyn].p;
+    p.tabs.values = d_values[dyn].p;
+    p.tabs.stride = plan.npad;
+    p.omega = static_cast<Real>(cfg.omega);
+    p.om1 = static_cast<Real>(1 - cfg.omega);
+    p.omega_minus = static_cast<Real>(cfg.omega_minus);
+    for(int i = 0; i < 27; ++i) p.rates[i] = static_cast<Real>(cfg.mrt_rates[i]);
+    p.vars_out = vars_out;
+    p.first = first ? 1 : 0;
+    return p;
+  }
+
+  template <bool STRICT, int COLL>
+  static auto kernel_ptr() { return &lbm::k_step<L, Real, STRICT, COLL>; }
+
+  using KernelFn = void (*)(const lbm::DevParams<Real>);
+  KernelFn main_kernel() const {
+    const bool strict = cfg.arithmetic == LBM_B200_STRICT;
+    switch(cfg.collision) {
+      case LBM_B200_TRT: return strict ? kernel_ptr<true, lbm::COLL_TRT>() : kernel_ptr<false, lbm::COLL_TRT>();
+      case LBM_B200_MRT: return strict ? kernel_ptr<true, lbm::COLL_MRT>() : kernel_ptr<false, lbm::COLL_MRT>();
+      default: return strict ? kernel_ptr<true, lbm::COLL_BGK>() : kernel_ptr<false, lbm::COLL_BGK>();
+    }
+  }
+
+  int init() override {
+    if(!lbm::build_plan(in, plan)) return fail(plan.error.find("order-dependent") != std::string::npos ? LBM_B200_EUNSUP : LBM_B200_EINVAL, plan.error);
+    nghbr_copy.clear();
+    nghbr_copy.shrink_to_fit();
+    in.nghbr = nullptr;
+    CUDA_TRY(cudaSetDevice(cfg.device));
+    const size_t npad = static_cast<size_t>(plan.npad);
+    for(int b = 0; b < 2; ++b) {
+      CUDA_TRY(f[b].alloc(npad * Q));
+      CUDA_TRY(cudaMemset(f[b].p, 0, f[b].bytes()));
+    }
+    if(cfg.track_vars > 0) {
+      for(int b = 0; b < 2; ++b) {
+        CUDA_TRY(vars[b].alloc(npad * NVAR));
+        CUDA_TRY(cudaMemset(vars[b].p, 0, vars[b].bytes()));
+      }
+    }
+    CUDA_TRY(scratch.alloc(npad * (Q > NVAR ? Q : NVAR)));
+    CUDA_TRY(cudaMemset(scratch.p, 0, scratch.bytes()));
+    CUDA_TRY(d_tmpl.upload(plan.tmpl));
+    CUDA_TRY(d_chunk_nb.upload(plan.chunk_nb));
+    CUDA_TRY(d_codes.upload(plan.codes));
+    {
+      std::vector<lbm::CopySrcDev> h;
+      for(auto& c : plan.copytab) h.push_back({c.cell, c.dir});
+      CUDA_TRY(d_copy.upload(h));
+    }
+    {
+      std::vector<lbm::AddEntryT<Real>> h;
+      for(auto& a : plan.addtab) {
+        lbm::AddEntryT<Real> e{};
+        for(int d = 0; d < 3; ++d) e.v[d] = static_cast<Real>(a.v[d]);
+        e.n = a.n;
+        h.push_back(e);
+      }
+      CUDA_TRY(d_add.upload(h));
+    }
+    {
+      std::vector<lbm::AbbDev<Real>> h;
+      for(auto& a : plan.abb) h.push_back({a.cell, a.n1, a.n2, static_cast<Real>(a.p)});
+      CUDA_TRY(d_abb.upload(h));
+    }
+    {
+      std::vector<lbm::ForceDev<Real>> h;
+      for(auto& a : plan.force) h.push_back({a.target, a.val, static_cast<Real>(a.p)});
+      CUDA_TRY(d_force.upload(h));
+    }
+    {
+      std::vector<lbm::PerPDev<Real>> h;
+      for(auto& a : plan.perp) h.push_back({a.cell, a.vbase, static_cast<Real>(a.p)});
+      CUDA_TRY(d_perp.upload(h));
+    }
+    {
+      std::vector<lbm::VarFixDev<Real>> h;
+      for(auto& a : plan.varfix) h.push_back({a.cell, a.var, a.abb, a.comp, static_cast<Real>(a.value)});
+      CUDA_TRY(d_varfix.upload(h));
+    }
+    for(int b = 0; b < 2; ++b) {
+      CUDA_TRY(d_uext[b].alloc(plan.abb.size() * 3 + 3));
+      CUDA_TRY(cudaMemset(d_uext[b].p, 0, d_uext[b].bytes()));
+    }
+    CUDA_TRY(cudaEventCreate(&ev0));
+    CUDA_TRY(cudaEventCreate(&ev1));
+    CUDA_TRY(cudaEventCreate(&evm0));
+    CUDA_TRY(cudaEventCreate(&evm1));
+
+    // launch geometry: generic blocks first, then persistent fast blocks (a multiple of the SM count)
+    n_gen_blocks = static_cast<int>((plan.n_gen + lbm::kThreads - 1) / lbm::kThreads);
+    {
+      cudaDeviceProp prop{};
+      CUDA_TRY(cudaGetDeviceProperties(&prop, cfg.device));
+      int per_sm = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, main_kernel(), lbm::kThreads, 0));
+      if(per_sm < 1) per_sm = 1;
+      int64_t want = static_cast<int64_t>(prop.multiProcessorCount) * per_sm;
+      if(want > plan.n_fast_chunks) want = plan.n_fast_chunks;
+      n_fast_blocks = static_cast<int>(want);
+    }
+
+    // ---- initialCondition(): vars = 0, boundary presets, rho = 1, f = fold = feq   (solver.cpp:267-295)
+    {
+      std::vector<Real> v0(npad * NVAR, Real(0));
+      for(size_t k = 0; k < plan.u0_cells.size(); ++k)
+        for(int d = 0; d < D; ++d) v0[static_cast<size_t>(d) * npad + plan.u0_cells[k]] = static_cast<Real>(plan.u0_vals[k * D + d]);
+      for(size_t c = 0; c < npad; ++c) v0[static_cast<size_t>(D) * npad + c] = plan.dev2ref[c] >= 0 ? Real(1) : Real(0);
+      Real* d_v0 = cfg.track_vars > 0 ? vars[0].p : scratch.p;
+      CUDA_TRY(cudaMemcpy(d_v0, v0.data(), v0.size() * sizeof(Real), cudaMemcpyHostToDevice));
+      const int nb = static_cast<int>((npad + 255) / 256);
+      if(cfg.arithmetic == LBM_B200_STRICT)
+        lbm::k_init<L, Real, true><<<nb, 256, 0, stream>>>(f[0].p, d_v0, plan.npad, static_cast<int32_t>(npad));
+      else
+        lbm::k_init<L, Real, false><<<nb, 256, 0, stream>>>(f[0].p, d_v0, plan.npad, static_cast<int32_t>(npad));
+      CUDA_TRY(cudaGetLastError());
+      // padding cells must stay zero (rho preset 0 gives feq = 0)
+      // slots nothing ever writes keep their initial m_fold value: fetch it once
+      std::vector<double> values = plan.values;
+      if(!plan.stale_ref.empty()) {
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        std::vector<Real> h(npad * Q);
+        CUDA_TRY(cudaMemcpy(h.data(), f[0].p, h.size() * sizeof(Real), cudaMemcpyDeviceToHost));
+        for(size_t k = 0; k < plan.stale_ref.size(); ++k) {
+          const int64_t cell = plan.stale_ref[k] / Q;
+          const int     dir  = static_cast<int>(plan.stale_ref[k] % Q);
+          values[k + 1]      = static_cast<double>(h[static_cast<size_t>(dir) * npad + cell]);
+        }
+      }
+      std::vector<Real> hv(values.size());
+      for(size_t k = 0; k < values.size(); ++k) hv[k] = static_cast<Real>(values[k]);
+      for(int b = 0; b < 2; ++b) CUDA_TRY(d_values[b].upload(hv));
+    }
+    CUDA_TRY(d_partial.alloc(static_cast<size_t>(NVAR) * 1024));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    cur = 0;
+    dyn = 0;
+    vcur = 0;
+    vars_step[0] = 0;
+    vars_step[1] = -1;
+    first = true;
+    t = 0;
+    inited = true;
+    return LBM_B200_OK;
+  }
+
+  bool want_vars(int64_t s) const {
+    // kernel of reference step s produces m_vars as seen at loop index s+1
+    if(cfg.track_vars <= 0) return false;
+    if(cfg.track_vars == 1) return true;
+    const int64_t k = cfg.track_vars;
+    return (s + 1) % k == 0 || (s + 2) % k == 0;
+  }
+
+  template <bool STRICT>
+  int aux_kernels(const lbm::DevParams<Real>& p, Real* vars_out) {
+    const int nd = dyn ^ 1;
+    bool dyn_written = false;
+    if(d_force.n > 0) {
+      const int n = static_cast<int>(d_force.n);
+      lbm::k_forcing<L, Real, STRICT><<<(n + 127) / 128, 128, 0, stream>>>(p, d_force.p, n);
+      ++launches;
+    }
+    if(d_perp.n > 0) {
+      const int n = static_cast<int>(d_perp.n);
+      lbm::k_periodic_pressure<L, Real, STRICT><<<(n + 127) / 128, 128, 0, stream>>>(p, d_perp.p, n, d_values[nd].p);
+      ++launches;
+      dyn_written = true;
+    }
+    if(d_abb.n > 0) {
+      const int n = static_cast<int>(d_abb.n);
+      lbm::k_pressure_extrapolate<L, Real, STRICT><<<(n + 127) / 128, 128, 0, stream>>>(p, n, d_uext[nd].p);
+      ++launches;
+      dyn_written = true;
+    }
+    if(vars_out != nullptr && d_varfix.n > 0) {
+      const int n = static_cast<int>(d_varfix.n);
+      lbm::k_varfix<Real><<<(n + 127) / 128, 128, 0, stream>>>(d_varfix.p, n, d_uext[nd].p, vars_out, plan.npad);
+      ++launches;
+    }
+    if(dyn_written) dyn = nd;
+    CUDA_TRY(cudaGetLastError());
+    return LBM_B200_OK;
+  }
+
+  int one_step(bool time_main) {
+    const int src = cur, dst = cur ^ 1;
+    Real*     vout = nullptr;
+    if(want_vars(t)) vout = vars[vcur ^ 1].p;
+    lbm::DevParams<Real> p = params(src, dst, vout);
+    if(prev_fold.p != nullptr) p.A = prev_fold.p; // explicit m_fold supplied by set_populations
+    const int grid = n_gen_blocks + n_fast_blocks;
+    if(time_main) cudaEventRecord(evm0, stream);
+    main_kernel()<<<grid, lbm::kThreads, 0, stream>>>(p);
+    if(time_main) cudaEventRecord(evm1, stream);
+    ++launches;
+    ++launches_main;
+    CUDA_TRY(cudaGetLastError());
+    int rc = cfg.arithmetic == LBM_B200_STRICT ? aux_kernels<true>(p, vout) : aux_kernels<false>(p, vout);
+    if(rc != LBM_B200_OK) return rc;
+    if(vout != nullptr) {
+      vcur ^= 1;
+      vars_step[vcur] = t + 1;
+    }
+    if(prev_fold.p != nullptr) {
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      prev_fold.alloc(0);
+    }
+    cur   = dst;
+    first = false;
+    ++t;
+    return LBM_B200_OK;
+  }
+
+  int step(int64_t n, float* ms_total, float* ms_main) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "lbm_b200_step before lbm_b200_init");
+    const bool timed = ms_total != nullptr;
+    double     main_acc = 0;
+    if(timed) CUDA_TRY(cudaEventRecord(ev0, stream));
+    for(int64_t s = 0; s < n; ++s) {
+      int rc = one_step(timed && ms_main != nullptr);
+      if(rc != LBM_B200_OK) return rc;
+      if(timed && ms_main != nullptr) {
+        CUDA_TRY(cudaEventSynchronize(evm1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, evm0, evm1));
+        main_acc += ms;
+      }
+    }
+    if(timed) {
+      CUDA_TRY(cudaEventRecord(ev1, stream));
+      CUDA_TRY(cudaEventSynchronize(ev1));
+      CUDA_TRY(cudaEventElapsedTime(ms_total, ev0, ev1));
+      if(ms_main) *ms_main = static_cast<float>(main_acc);
+    }
+    return LBM_B200_OK;
+  }
+
+  int sync() override {
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return LBM_B200_OK;
+  }
+
+  // SoA device array [width][npad] -> AoS host array [n][width] in reference cell order
+  int download(const Real* dsrc, int width, double* out) {
+    const size_t npad = static_cast<size_t>(plan.npad);
+    std::vector<Real> h(npad * width);
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaMemcpy(h.data(), dsrc, h.size() * sizeof(Real), cudaMemcpyDeviceToHost));
+#pragma omp parallel for schedule(static)
+    for(int64_t c = 0; c < plan.n; ++c) {
+      const size_t dv = static_cast<size_t>(plan.ref2dev[c]);
+      for(int j = 0; j < width; ++j) out[c * width + j] = static_cast<double>(h[static_cast<size_t>(j) * npad + dv]);
+    }
+    return LBM_B200_OK;
+  }
+  int upload_aos(const double* src, int width, Real* ddst) {
+    const size_t npad = static_cast<size_t>(plan.npad);
+    std::vector<Real> h(npad * width, Real(0));
+    for(int64_t c = 0; c < plan.n; ++c) {
+      const size_t dv = static_cast<size_t>(plan.ref2dev[c]);
+      for(int j = 0; j < width; ++j) h[static_cast<size_t>(j) * npad + dv] = static_cast<Real>(src[c * width + j]);
+    }
+    CUDA_TRY(cudaMemcpy(ddst, h.data(), h.size() * sizeof(Real), cudaMemcpyHostToDevice));
+    return LBM_B200_OK;
+  }
+
+  int gather_all(Real* fold_out, Real* mom_out) {
+    lbm::DevParams<Real> p = params(cur, cur ^ 1, nullptr);
+    const int32_t nc = static_cast<int32_t>(plan.npad);
+    // padding cells of the generic range carry VALUE(0) codes and read zeros; chunk ranges have no padding
+    const int nb = (nc + 127) / 128;
+    if(prev_fold.p != nullptr) {
+      p.A = prev_fold.p;
+    }
+    if(cfg.arithmetic == LBM_B200_STRICT) lbm::k_gather_all<L, Real, true><<<nb, 128, 0, stream>>>(p, nc, fold_out, mom_out);
+    else lbm::k_gather_all<L, Real, false><<<nb, 128, 0, stream>>>(p, nc, fold_out, mom_out);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    return LBM_B200_OK;
+  }
+
+  int get_populations(double* fo, double* foldo) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
+    if(fo != nullptr) {
+      int rc = download(f[cur].p, Q, fo);
+      if(rc) return rc;
+    }
+    if(foldo != nullptr) {
+      if(prev_fold.p != nullptr) return download(prev_fold.p, Q, foldo);
+      int rc = gather_all(scratch.p, nullptr);
+      if(rc) return rc;
+      return download(scratch.p, Q, foldo);
+    }
+    return LBM_B200_OK;
+  }
+
+  int set_populations(const double* fi, const double* foldi) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
+    if(fi == nullptr || foldi == nullptr) return fail(LBM_B200_EINVAL, "set_populations needs both f and fold");
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    int rc = upload_aos(fi, Q, f[cur].p);
+    if(rc) return rc;
+    CUDA_TRY(prev_fold.alloc(static_cast<size_t>(plan.npad) * Q));
+    rc = upload_aos(foldi, Q, prev_fold.p);
+    if(rc) return rc;
+    // slots nothing ever writes now keep the supplied m_fold value
+    if(!plan.stale_ref.empty()) {
+      std::vector<Real> hv(d_values[0].n, Real(0));
+      CUDA_TRY(cudaMemcpy(hv.data(), d_values[dyn].p, hv.size() * sizeof(Real), cudaMemcpyDeviceToHost));
+      for(size_t k = 0; k < plan.stale_ref.size(); ++k) {
+        const int64_t ref = plan.dev2ref[plan.stale_ref[k] / Q];
+        hv[k + 1]         = static_cast<Real>(foldi[ref * Q + plan.stale_ref[k] % Q]);
+      }
+      for(int b = 0; b < 2; ++b) CUDA_TRY(cudaMemcpy(d_values[b].p, hv.data(), hv.size() * sizeof(Real), cudaMemcpyHostToDevice));
+    }
+    first = true; // the next step consumes the supplied m_fold directly
+    return LBM_B200_OK;
+  }
+
+  int get_vars(double* v, double* vo) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
+    if(cfg.track_vars <= 0) return fail(LBM_B200_ESTATE, "m_vars is not tracked (config.track_vars = 0)");
+    if(vars_step[vcur] != t) return fail(LBM_B200_ESTATE, "m_vars of this step was not kept (track_vars interval)");
+    if(v != nullptr) {
+      int rc = download(vars[vcur].p, NVAR, v);
+      if(rc) return rc;
+    }
+    if(vo != nullptr) {
+      if(t == 0) {
+        std::memset(vo, 0, sizeof(double) * static_cast<size_t>(plan.n) * NVAR); // solver.cpp:270
+      } else {
+        if(vars_step[vcur ^ 1] != t - 1) return fail(LBM_B200_ESTATE, "m_varsold of this step was not kept (track_vars interval)");
+        return download(vars[vcur ^ 1].p, NVAR, vo);
+      }
+    }
+    return LBM_B200_OK;
+  }
+
+  int get_moments(double* m) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
+    int rc = gather_all(nullptr, scratch.p);
+    if(rc) return rc;
+    return download(scratch.p, NVAR, m);
+  }
+
+  int residual(double* out, int32_t* diverged) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
+    if(cfg.track_vars <= 0) return fail(LBM_B200_ESTATE, "residual needs config.track_vars");
+    if(vars_step[vcur] != t || (t > 0 && vars_step[vcur ^ 1] != t - 1))
+      return fail(LBM_B200_ESTATE, "m_vars / m_varsold of this step were not kept (track_vars interval)");
+    const int nb = 592; // 4 x 148 SMs
+    lbm::k_residual<Real><<<nb, 256, 0, stream>>>(vars[vcur].p, vars[vcur ^ 1].p, plan.npad, plan.npad, NVAR, d_partial.p);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    std::vector<double> h(static_cast<size_t>(NVAR) * nb);
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaMemcpy(h.data(), d_partial.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    int bad = 0;
+    for(int v = 0; v < NVAR; ++v) {
+      double s = 0;
+      for(int b = 0; b < nb; ++b) s += h[static_cast<size_t>(v) * nb + b];
+      out[v] = s;
+      if(std::isnan(s) || std::isinf(s)) bad = 1;
+    }
+    if(diverged) *diverged = bad;
+    return LBM_B200_OK;
+  }
+
+  void stats(lbm_b200_stats* st) const override {
+    std::memset(st, 0, sizeof(*st));
+    st->ncells        = plan.n;
+    st->cells_fast    = plan.n_fast_chunks * plan.CH;
+    st->cells_generic = plan.n - st->cells_fast;
+    st->chunk_cells   = plan.CH;
+    st->slots_bc      = plan.slots_bc;
+    st->slots_stale   = plan.slots_stale;
+    st->device_bytes  = static_cast<int64_t>(f[0].bytes() + f[1].bytes() + vars[0].bytes() + vars[1].bytes() + scratch.bytes() + d_codes.bytes()
+                                             + d_chunk_nb.bytes() + d_tmpl.bytes());
+    st->launches      = launches;
+    st->launches_main = launches_main;
+    st->bytes_per_cell_alg = 2.0 * Q * sizeof(Real);
+  }
+};
+
+SolverBase* make_solver(const lbm_b200_config& c) {
+  const bool dbl = c.precision == LBM_B200_FP64;
+  if(c.ndim == 2 && c.ndist == 9) return dbl ? static_cast<SolverBase*>(new Solver<lbm::Lattice<2, 9>, double>()) : new Solver<lbm::Lattice<2, 9>, float>();
+  if(c.ndim == 3 && c.ndist == 19) return dbl ? static_cast<SolverBase*>(new Solver<lbm::Lattice<3, 19>, double>()) : new Solver<lbm::Lattice<3, 19>, float>();
+  if(c.ndim == 3 && c.ndist == 27) return dbl ? static_cast<SolverBase*>(new Solver<lbm::Lattice<3, 27>, double>()) : new Solver<lbm::Lattice<3, 27>, float>();
+  return nullptr;
+}
+
+} // namespace
+
+struct lbm_b200_solver {
+  std::unique_ptr<SolverBase> impl;
+};
+
+extern "C" {
+
+void lbm_b200_default_config(lbm_b200_config* cfg) {
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->abi_version = LBM_B200_ABI_VERSION;
+  cfg->ndim        = 2;
+  cfg->ndist       = 9;
+  cfg->precision   = LBM_B200_FP64;
+  cfg->collision   = LBM_B200_BGK;
+  cfg->arithmetic  = LBM_B200_STRICT;
+  cfg->device      = 0;
+  cfg->track_vars  = 1;
+  cfg->omega       = 1.0;
+  cfg->omega_minus = 1.0;
+  for(double& r : cfg->mrt_rates) r = 1.0;
+}
+
+int lbm_b200_create(const lbm_b200_config* cfg, int64_t ncells, lbm_b200_solver** out) {
+  if(cfg == nullptr || out == nullptr) return fail(LBM_B200_EINVAL, "null argument");
+  *out = nullptr;
+  if(cfg->abi_version != LBM_B200_ABI_VERSION) return fail(LBM_B200_EINVAL, "ABI version mismatch");
+  if(ncells <= 0) return fail(LBM_B200_EINVAL, "ncells must be positive");
+  if(cfg->precision != LBM_B200_FP64 && cfg->precision != LBM_B200_FP32) return fail(LBM_B200_EINVAL, "unknown precision");
+  if(cfg->collision < LBM_B200_BGK || cfg->collision > LBM_B200_MRT) return fail(LBM_B200_EINVAL, "Invalid equation configuration!"); // constants.h:75
+  if(cfg->arithmetic != LBM_B200_STRICT && cfg->arithmetic != LBM_B200_FAST) return fail(LBM_B200_EINVAL, "unknown arithmetic policy");
+  if(!(cfg->omega > 0.0) || !(cfg->omega < 2.0)) return fail(LBM_B200_EINVAL, "omega must be in (0,2)");
+  SolverBase* s = make_solver(*cfg);
+  if(s == nullptr) return fail(LBM_B200_EINVAL, "Unsupported model"); // solverExe.h:90
+  s->cfg = *cfg;
+  if(!lbm::lattice_rt(cfg->ndim, cfg->ndist, &s->in.L)) {
+    delete s;
+    return fail(LBM_B200_EINVAL, "Unsupported model");
+  }
+  s->in.n = ncells;
+  // no silent CPU path: a missing device is an error right here
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if(e != cudaSuccess || ndev <= cfg->device) {
+    delete s;
+    return fail(LBM_B200_ECUDA, std::string("no CUDA device ") + std::to_string(cfg->device) + ": " + cudaGetErrorString(e));
+  }
+  *out = new lbm_b200_solver{std::unique_ptr<SolverBase>(s)};
+  return LBM_B200_OK;
+}
+
+void lbm_b200_destroy(lbm_b200_solver* s) { delete s; }
+
+#define CHECK_HANDLE(s)                                               \
+  if((s) == nullptr || !(s)->impl) return fail(LBM_B200_EINVAL, "null solver handle")
+#define CHECK_NOT_INITED(s) \
+  if((s)->impl->inited) return fail(LBM_B200_ESTATE, "topology and boundary conditions are frozen after lbm_b200_init")
+
+int lbm_b200_set_topology(lbm_b200_solver* s, const int64_t* nghbr, int32_t stride) {
+  CHECK_HANDLE(s);
+  CHECK_NOT_INITED(s);
+  if(nghbr == nullptr || stride < s->impl->in.L.Q - 1) return fail(LBM_B200_EINVAL, "bad neighbour table");
+  auto& im = *s->impl;
+  im.nghbr_copy.assign(nghbr, nghbr + static_cast<size_t>(im.in.n) * stride);
+  im.in.nghbr  = im.nghbr_copy.data();
+  im.in.stride = stride;
+  return LBM_B200_OK;
+}
+
+int lbm_b200_set_geometry(lbm_b200_solver* s, const double* center, const double* bbmin, const double* bbmax, double cell_length) {
+  CHECK_HANDLE(s);
+  CHECK_NOT_INITED(s);
+  if(center == nullptr || bbmin == nullptr || bbmax == nullptr) return fail(LBM_B200_EINVAL, "null argument");
+  auto& in = s->impl->in;
+  in.center.assign(center, center + static_cast<size_t>(in.n) * in.L.D);
+  for(int d = 0; d < in.L.D; ++d) {
+    in.bbmin[d] = bbmin[d];
+    in.bbmax[d] = bbmax[d];
+  }
+  in.cell_length = cell_length;
+  return LBM_B200_OK;
+}
+
+static int add_bc(lbm_b200_solver* s, lbm::BcInput& bc, const int64_t* cells, const double* normals, int64_t n) {
+  CHECK_HANDLE(s);
+  CHECK_NOT_INITED(s);
+  if(n < 0 || (n > 0 && (cells == nullptr || normals == nullptr))) return fail(LBM_B200_EINVAL, "bad cell list");
+  auto& in = s->impl->in;
+  for(int64_t k = 0; k < n; ++k)
+    if(cells[k] < 0 || cells[k] >= in.n) return fail(LBM_B200_EINVAL, "boundary cell id out of range");
+  bc.cells.assign(cells, cells + n);
+  bc.normals.assign(normals, normals + n * in.L.D);
+  in.bcs.push_back(std::move(bc));
+  return LBM_B200_OK;
+}
+
+int lbm_b200_add_wall_bb(lbm_b200_solver* s, const int64_t* cells, const double* normals, int64_t n, double tangential) {
+  lbm::BcInput bc;
+  // bnd.h:232-240: |tangentialVelocity| > eps selects the moving-wall instantiation
+  bc.kind       = std::abs(tangential) > lbm::kEps ? lbm::BC_WALL_BB_TANGENTIAL : lbm::BC_WALL_BB;
+  bc.tangential = tangential;
+  return add_bc(s, bc, cells, normals, n);
+}
+
+int lbm_b200_add_dirichlet_bb(lbm_b200_solver* s, const int64_t* cells, const double* normals, int64_t n, const double* value) {
+  CHECK_HANDLE(s);
+  if(value == nullptr) return fail(LBM_B200_EINVAL, "null value");
+  lbm::BcInput bc;
+  bc.kind = lbm::BC_DIRICHLET_BB;
+  for(int d = 0; d < s->impl->in.L.D; ++d) bc.value[d] = value[d];
+  return add_bc(s, bc, cells, normals, n);
+}
+
+int lbm_b200_add_pressure(lbm_b200_solver* s, const int64_t* cells, const double* normals, int64_t n, double pressure) {
+  lbm::BcInput bc;
+  bc.kind     = lbm::BC_PRESSURE;
+  bc.pressure = pressure;
+  return add_bc(s, bc, cells, normals, n);
+}
+
+int lbm_b200_add_periodic(lbm_b200_solver* s, const int64_t* cells, const double* normals, int64_t n, const int64_t* connected,
+                          int64_t nconnected, double pressure) {
+  CHECK_HANDLE(s);
+  if(nconnected <= 0 || connected == nullptr) return fail(LBM_B200_EINVAL, "Invalid connected surface"); // bnd_periodic.h:180
+  for(int64_t k = 0; k < nconnected; ++k)
+    if(connected[k] < 0 || connected[k] >= s->impl->in.n) return fail(LBM_B200_EINVAL, "connected cell id out of range");
+  lbm::BcInput bc;
+  bc.kind     = lbm::BC_PERIODIC;
+  bc.pressure = pressure;
+  bc.connected.assign(connected, connected + nconnected);
+  return add_bc(s, bc, cells, normals, n);
+}
+
+int lbm_b200_set_forcing(lbm_b200_solver* s, const int64_t* inlet, int64_t ninlet, const int64_t* outlet, int64_t noutlet, double gradient) {
+  CHECK_HANDLE(s);
+  CHECK_NOT_INITED(s);
+  if(ninlet < 0 || noutlet < 0 || (ninlet > 0 && inlet == nullptr) || (noutlet > 0 && outlet == nullptr)) return fail(LBM_B200_EINVAL, "bad forcing lists");
+  auto& in = s->impl->in;
+  for(int64_t k = 0; k < ninlet; ++k)
+    if(inlet[k] < 0 || inlet[k] >= in.n) return fail(LBM_B200_EINVAL, "inlet cell id out of range");
+  for(int64_t k = 0; k < noutlet; ++k)
+    if(outlet[k] < 0 || outlet[k] >= in.n) return fail(LBM_B200_EINVAL, "outlet cell id out of range");
+  in.forcing = true;
+  in.inlet.assign(inlet, inlet + ninlet);
+  in.outlet.assign(outlet, outlet + noutlet);
+  in.gradient = gradient;
+  return LBM_B200_OK;
+}
+
+int lbm_b200_set_stream(lbm_b200_solver* s, void* cuda_stream) {
+  CHECK_HANDLE(s);
+  s->impl->stream = static_cast<cudaStream_t>(cuda_stream);
+  return LBM_B200_OK;
+}
+
+int lbm_b200_init(lbm_b200_solver* s) {
+  CHECK_HANDLE(s);
+  CHECK_NOT_INITED(s);
+  if(s->impl->in.nghbr == nullptr) return fail(LBM_B200_ESTATE, "lbm_b200_set_topology has not been called");
+  return s->impl->init();
+}
+
+int lbm_b200_step(lbm_b200_solver* s, int64_t nsteps) {
+  CHECK_HANDLE(s);
+  if(nsteps < 0) return fail(LBM_B200_EINVAL, "negative step count");
+  return s->impl->step(nsteps, nullptr, nullptr);
+}
+
+int lbm_b200_step_timed(lbm_b200_solver* s, int64_t nsteps, float* ms_total, float* ms_main) {
+  CHECK_HANDLE(s);
+  if(nsteps < 0 || ms_total == nullptr) return fail(LBM_B200_EINVAL, "bad argument");
+  return s->impl->step(nsteps, ms_total, ms_main);
+}
+
+int lbm_b200_synchronize(lbm_b200_solver* s) {
+  CHECK_HANDLE(s);
+  return s->impl->sync();
+}
+
+int lbm_b200_residual(lbm_b200_solver* s, double* out, int32_t* diverged) {
+  CHECK_HANDLE(s);
+  if(out == nullptr) return fail(LBM_B200_EINVAL, "null argument");
+  return s->impl->residual(out, diverged);
+}
+
+int lbm_b200_get_populations(lbm_b200_solver* s, double* f, double* fold) {
+  CHECK_HANDLE(s);
+  return s->impl->get_populations(f, fold);
+}
+
+int lbm_b200_set_populations(lbm_b200_solver* s, const double* f, const double* fold) {
+  CHECK_HANDLE(s);
+  return s->impl->set_populations(f, fold);
+}
+
+int lbm_b200_get_vars(lbm_b200_solver* s, double* vars, double* varsold) {
+  CHECK_HANDLE(s);
+  return s->impl->get_vars(vars, varsold);
+}
+
+int lbm_b200_get_moments(lbm_b200_solver* s, double* moments) {
+  CHECK_HANDLE(s);
+  if(moments == nullptr) return fail(LBM_B200_EINVAL, "null argument");
+  return s->impl->get_moments(moments);
+}
+
+int64_t lbm_b200_steps_done(const lbm_b200_solver* s) { return (s && s->impl) ? s->impl->t : -1; }
+
+int lbm_b200_get_stats(const lbm_b200_solver* s, lbm_b200_stats* out) {
+  CHECK_HANDLE(s);
+  if(out == nullptr) return fail(LBM_B200_EINVAL, "null argument");
+  if(!s->impl->inited) return fail(LBM_B200_ESTATE, "not initialised");
+  s->impl->stats(out);
+  return LBM_B200_OK;
+}
+
+const char* lbm_b200_last_error(void) { return g_error.c_str(); }
+int         lbm_b200_abi_version(void) { return LBM_B200_ABI_VERSION; }
+
+} // extern "C"

@@ -1,0 +1,142 @@
+"""Parity of the CUDA product (through the C ABI) against the CPU oracle and the reference's golden dumps.
+
+fp64 STRICT arithmetic must be BIT-IDENTICAL to the oracle (which is itself bit-identical to the reference,
+tests/test_oracle_golden.py).  fp64 FAST must agree within 1e-12 relative (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+
+import lbm_b200
+from casebuilder import CaseSpec, load_golden
+from gridgen import box_grid
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_CASES = ["couette", "couette_bnd", "couette_bnd_bbDirichlet", "poiseuille", "poiseuille_bnd", "step_ns", "sphere_ns"]
+
+
+def rel_err(a, b):
+    scale = np.max(np.abs(b))
+    return float(np.max(np.abs(a - b)) / (scale if scale > 0 else 1.0))
+
+
+def run_pair(spec, oracle_mod, steps, **kw):
+    o = spec.apply_to(oracle_mod.Oracle(spec.ndim, spec.ndist, spec.nghbr, spec.omega))
+    g = spec.apply_to(lbm_b200.Solver(spec.ndim, spec.ndist, spec.nghbr, spec.omega, **kw))
+    o.init()
+    g.init()
+    return o, g
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_strict_fp64_is_bit_identical_on_reference_cases(name, oracle_mod):
+    spec = load_golden(name)
+    o, g = run_pair(spec, oracle_mod, 0)
+    assert np.array_equal(g.f, o.f) and np.array_equal(g.fold, o.fold), "initial condition differs"
+    done = 0
+    for s in spec.golden["steps"]:
+        s = int(s)
+        o.step(s - done)
+        g.step(s - done)
+        done = s
+        for arr in ("f", "fold", "vars", "varsold"):
+            a, b = getattr(g, arr), getattr(o, arr)
+            assert np.array_equal(a, b), f"{name} step {s}: {arr} differs, max abs {np.max(np.abs(a - b))}"
+            key = f"{arr}_{s}"
+            if key in spec.golden:
+                assert np.array_equal(a, spec.golden[key]), f"{name} step {s}: {arr} differs from the reference dump"
+        ro, _ = o.residual()
+        rg, bad = g.residual()
+        assert not bad
+        assert np.allclose(rg, ro, rtol=1e-12, atol=1e-300)
+    o.update_moments()
+    assert np.array_equal(g.moments(), o.vars)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_fast_fp64_within_1e12(name, oracle_mod):
+    spec = load_golden(name)
+    o, g = run_pair(spec, oracle_mod, 0, arithmetic=lbm_b200.FAST)
+    n = int(spec.golden["steps"][-1])
+    o.step(n)
+    g.step(n)
+    assert rel_err(g.f, o.f) < 1e-12
+    assert rel_err(g.fold, o.fold) < 1e-12
+    vo, vg = o.vars, g.vars
+    assert rel_err(vg[:, -1], vo[:, -1]) < 1e-12          # density
+    # velocities are ~1e-5 of the lattice speed: 1e-12 relative to the flow's velocity scale
+    assert np.max(np.abs(vg[:, :-1] - vo[:, :-1])) < 1e-12 * max(np.max(np.abs(vo[:, :-1])), 1e-30) + 1e-17
+
+
+def box_spec(shape, ndist, periodic, omega=1.0 / 0.6, lid=None):
+    g = box_grid(shape, periodic)
+    ndim = len(shape)
+    spec = CaseSpec(name=f"box{shape}", ndim=ndim, ndist=ndist, nghbr=g["nghbr"], omega=omega, center=g["center"],
+                    bbmin=g["bbmin"], bbmax=g["bbmax"], cell_length=g["cell_length"])
+    names = ["-x", "+x", "-y", "+y", "-z", "+z"][:2 * ndim]
+    for nm in sorted(names):  # lexicographic like the reference
+        cells, normals = g["surfaces"][nm]
+        if len(cells) == 0:
+            continue
+        if lid is not None and nm == lid[0]:
+            spec.bcs.append(dict(kind="dirichlet_bb", cells=cells, normals=normals, value=np.array(lid[1], float)))
+        else:
+            spec.bcs.append(dict(kind="wall_bb", cells=cells, normals=normals, tangential=0.0))
+    return spec
+
+
+BOXES = [
+    # 3D Couette-type benchmark shape: periodic x, walls y, moving lid +z
+    ((32, 32, 32), 19, (True, False, False), ("+z", (0.05, 0.0, 0.0))),
+    ((32, 32, 32), 27, (True, False, False), ("+z", (0.05, 0.0, 0.0))),
+    ((32, 16, 24), 19, (True, True, False), ("+z", (0.05, 0.02, 0.0))),
+    ((16, 16, 16), 19, (True, True, True), None),
+    ((128, 128), 9, (True, False), ("+y", (0.05, 0.0))),
+    ((96, 64), 9, (False, False), ("+y", (0.05, 0.0))),
+]
+
+
+@pytest.mark.parametrize("shape,ndist,periodic,lid", BOXES)
+def test_strict_fp64_boxes_fast_chunks(shape, ndist, periodic, lid, oracle_mod):
+    spec = box_spec(shape, ndist, periodic, lid=lid)
+    o, g = run_pair(spec, oracle_mod, 0)
+    # perturb the start so that all populations differ: a few steps of lid-driven flow first on the oracle
+    o.step(3)
+    g.set_populations(o.f, o.fold)
+    for chunk in (1, 1, 5, 20):
+        o.step(chunk)
+        g.step(chunk)
+        assert np.array_equal(g.f, o.f), f"f differs after {chunk}"
+        assert np.array_equal(g.fold, o.fold)
+    st = g.stats()
+    if all(periodic):
+        assert st["cells_fast"] == st["ncells"]
+    if min(shape) >= 32:
+        assert st["cells_fast"] > 0, "this case is meant to exercise the template-indexed chunk path"
+
+
+@pytest.mark.parametrize("collision", [lbm_b200.TRT, lbm_b200.MRT])
+@pytest.mark.parametrize("ndist,shape,periodic,lid", [(19, (32, 32, 32), (True, False, False), ("+z", (0.05, 0, 0))),
+                                                      (9, (64, 64), (True, False), ("+y", (0.05, 0)))])
+def test_trt_mrt_strict_match_oracle(collision, ndist, shape, periodic, lid, oracle_mod):
+    spec = box_spec(shape, ndist, periodic, lid=lid)
+    rates = np.linspace(1.1, 1.7, 27)
+    o = spec.apply_to(oracle_mod.Oracle(spec.ndim, spec.ndist, spec.nghbr, spec.omega))
+    o.set_collision(collision, 1.3, rates)
+    g = spec.apply_to(lbm_b200.Solver(spec.ndim, spec.ndist, spec.nghbr, spec.omega, collision=collision,
+                                     omega_minus=1.3, mrt_rates=rates))
+    o.init()
+    g.init()
+    o.step(30)
+    g.step(30)
+    assert np.array_equal(g.f, o.f)
+
+
+def test_fp32_opt_in_tolerance(oracle_mod):
+    """fp32 is an opt-in; stated tolerance: 2e-6 relative on populations after 100 steps of the couette case."""
+    spec = load_golden("couette")
+    o, g = run_pair(spec, oracle_mod, 0, precision=lbm_b200.FP32, arithmetic=lbm_b200.FAST)
+    o.step(100)
+    g.step(100)
+    assert rel_err(g.f, o.f) < 2e-6
+    assert np.max(np.abs(g.vars[:, 0] - o.vars[:, 0])) < 5e-5 * 0.1  # wall speed 0.1
