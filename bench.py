@@ -1,0 +1,321 @@
+#!/usr/bin/env python3
+"""bench.py -- MLUPS of the lattice-Boltzmann time step on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[2], SURVEY.md section 8d "S3 bench-3D"): cube of S^3 cells, D3Q19, BGK, fp64,
+omega = 1/0.6, periodic in x (grid level), no-slip bounce-back walls on -y/+y/-z, moving lid on +z
+(Dirichlet bounce-back, u = (0.05, 0, 0)), reference initial condition (rho = 1, u = 0 except the lid preset).
+A "step" is one LBM time step of the whole box.  Default S = 256 (16.8 M cells, 5.1 GB of populations: far
+larger than the 126 MB L2, so no L2 flush is needed between timed steps).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size S] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (CUDA events on the solver's stream, max over
+ranks); `e2e` is the same metric through the C ABI with the state in pinned HOST buffers: upload m_f/m_fold,
+K steps, download the macroscopic fields -- all inside the timed region.  `--impl reference` times the CPU
+restatement of the reference's own time step (oracle/lbm_oracle.c: the reference's algorithm, pass by pass,
+with its OpenMP pragmas) on the host cores; the reference binary itself cannot run D3Q19.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LATTICES = {"D2Q9": (2, 9), "D3Q19": (3, 19), "D3Q27": (3, 27)}
+OMEGA = 1.0 / 0.6
+LID_U = 0.05
+
+
+def workload(size, lattice):
+    """Tables of the benchmark box in the reference's format + boundary conditions in application order."""
+    from lbm_b200.capi import box_topology
+    ndim, ndist = LATTICES[lattice]
+    shape = (size,) * ndim
+    periodic = (1,) + (0,) * (ndim - 1)
+    nghbr, center, _ = box_topology(shape, periodic, want_center=True)
+    names = ["-x", "+x", "-y", "+y", "-z", "+z"][:2 * ndim]
+    lid = names[-1]
+    bcs = []
+    for d, nm in sorted(enumerate(names), key=lambda t: t[1]):  # lexicographic, like the reference (bnd.h:71-142)
+        cells = np.nonzero(nghbr[:, d] < 0)[0].astype(np.int64)
+        if len(cells) == 0:
+            continue
+        normal = np.zeros(ndim)
+        normal[d // 2] = -1.0 if d % 2 == 0 else 1.0
+        normals = np.tile(normal, (len(cells), 1))
+        if nm == lid:
+            value = np.zeros(ndim)
+            value[0] = LID_U
+            bcs.append(("dirichlet_bb", cells, normals, value))
+        else:
+            bcs.append(("wall_bb", cells, normals, 0.0))
+    return dict(ndim=ndim, ndist=ndist, nghbr=nghbr, center=center, bcs=bcs, shape=shape)
+
+
+def apply_bcs(solver, wl):
+    for kind, cells, normals, val in wl["bcs"]:
+        if kind == "dirichlet_bb":
+            solver.add_dirichlet_bb(cells, normals, val)
+        else:
+            solver.add_wall_bb(cells, normals, val)
+    return solver
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.path = tempfile.mktemp(prefix="lbm_clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(device)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            t = [x.strip() for x in line.split(",")]
+            if len(t) < 7:
+                continue
+            try:
+                sm.append(float(t[0]))
+                smax.append(float(t[1]))
+                power.append(float(t[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, t[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def ncu_traffic(lattice, size):
+    """bytes per launch of the fused kernel from the committed ncu capture, if one exists for this workload"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        t = json.load(open(p))
+        key = f"{lattice}_{size}"
+        if key in t:
+            return t[key]
+    return None
+
+
+def cpu_sample(lattice, sample_size, budget_s, omp_collide=False):
+    """Time the CPU restatement of the reference step (oracle port) on a bounded sample of the same workload."""
+    from oracle import oracle
+    wl = workload(sample_size, lattice)
+    o = oracle.Oracle(wl["ndim"], wl["ndist"], wl["nghbr"], OMEGA)
+    apply_bcs(o, wl)
+    o.set_omp_collide(omp_collide)
+    o.init()
+    o.step(1)
+    t0 = time.perf_counter()
+    o.step(2)
+    per = (time.perf_counter() - t0) / 2
+    steps = int(max(3, min(200, budget_s / max(per, 1e-6))))
+    t0 = time.perf_counter()
+    o.step(steps)
+    dt = time.perf_counter() - t0
+    n = wl["nghbr"].shape[0]
+    o.close()
+    return n * steps / dt / 1e6, steps, n, oracle.threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    oracle.build()
+    sample = args.cpu_size
+    wl = workload(sample, args.lattice)
+    o = oracle.Oracle(wl["ndim"], wl["ndist"], wl["nghbr"], OMEGA)
+    apply_bcs(o, wl)
+    o.init()
+    o.step(args.warmup)
+    t0 = time.perf_counter()
+    o.step(args.steps)
+    dt = time.perf_counter() - t0
+    n = wl["nghbr"].shape[0]
+    mlups = n * args.steps / dt / 1e6
+    unit = "MLUPS"
+    line = {
+        "impl": "reference", "metric": "MLUPS", "value": mlups, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, "CPU port of the reference time step (oracle/lbm_oracle.c), OpenMP like the reference"),
+        "cpu_baseline": {"value": mlups, "unit": unit, "cores": oracle.threads(), "kind": "port",
+                         "sample": f"{args.lattice} {sample}^{wl['ndim']} box ({n} cells), same BCs/omega as the workload, "
+                                   f"{args.steps} steps; the reference binary cannot run D3Q19 (SURVEY section 0)"},
+        "e2e": {"value": mlups, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, note):
+    ndim, ndist = LATTICES[args.lattice]
+    return {"workload": f"bench-3D cube {args.size}^{ndim} {args.lattice} BGK fp64 (BASELINE.json configs[2]; SURVEY 8d S3): "
+                        f"periodic x, bounce-back walls, moving lid u={LID_U}, omega={OMEGA:.6f}",
+            "cells_per_gpu": args.size ** ndim, "lattice": args.lattice, "collision": "bgk", "arithmetic": args.arithmetic,
+            "l2_policy": "inputs larger than L2 (no flush needed)", "parallelism": f"{args.gpus} x independent SFC-ordered box"
+            if args.gpus > 1 else "single GPU", "note": note}
+
+
+def run_ours(args):
+    import torch
+    import lbm_b200
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    ndim, ndist = LATTICES[args.lattice]
+    arithmetic = lbm_b200.FAST if args.arithmetic == "fast" else lbm_b200.STRICT
+    t_setup = time.perf_counter()
+    wl = workload(args.size, args.lattice)
+    n = wl["nghbr"].shape[0]
+    stream = torch.cuda.current_stream().cuda_stream
+    s = lbm_b200.Solver(ndim, ndist, wl["nghbr"], OMEGA, arithmetic=arithmetic, device=local, track_vars=0, stream=stream)
+    apply_bcs(s, wl)
+    s.init()
+    del wl["nghbr"]
+    t_setup = time.perf_counter() - t_setup
+    st0 = s.stats()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    s.step(args.warmup)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = s.stats()["launches"]
+    ms_total, ms_main = s.step_timed(args.steps)
+    launches = s.stats()["launches"] - l0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms_total, ms_main], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_main = float(t[0]), float(t[1])
+    value = n * world * args.steps / (ms_total * 1e-3) / 1e6
+
+    # ---- e2e: state in pinned host buffers, through the C ABI: upload m_f + m_fold, K steps, download the fields
+    e2e = None
+    if not args.no_e2e:
+        f_host = torch.empty((n, ndist), dtype=torch.float64, pin_memory=True)
+        fold_host = torch.empty((n, ndist), dtype=torch.float64, pin_memory=True)
+        mom_host = torch.empty((n, ndim + 1), dtype=torch.float64, pin_memory=True)
+        import ctypes as C
+        lib = s._lib
+        lib.lbm_b200_get_populations(s._h, C.c_void_p(f_host.data_ptr()), C.c_void_p(fold_host.data_ptr()))
+        k = args.steps
+        barrier()
+        b0 = s.stats()
+        t0 = time.perf_counter()
+        rc = lib.lbm_b200_set_populations(s._h, f_host.numpy(), fold_host.numpy())
+        assert rc == 0, lib.lbm_b200_last_error()
+        s.step(k)
+        rc = lib.lbm_b200_get_moments(s._h, mom_host.numpy())
+        assert rc == 0, lib.lbm_b200_last_error()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        b1 = s.stats()
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+        e2e = {"value": n * world * k / dt / 1e6, "unit": "MLUPS",
+               "h2d_bytes_per_step": (b1["h2d_bytes"] - b0["h2d_bytes"]) / k, "d2h_bytes_per_step": (b1["d2h_bytes"] - b0["d2h_bytes"]) / k,
+               "region": f"lbm_b200_set_populations(pinned m_f, m_fold) + {k} x lbm_b200_step + lbm_b200_get_moments(pinned)",
+               "finite": bool(torch.isfinite(mom_host).all())}
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    b_alg = st0["bytes_per_cell_alg"]
+    achieved = b_alg * n * args.steps / (ms_main * 1e-3) / 1e9
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": ncu_traffic(args.lattice, args.size), "peak_source": peak_src,
+            "kernel": "lbm::k_step (fused pull-stream + BC + moments + BGK collide)",
+            "bytes_per_cell_alg": b_alg, "cells_per_launch": n, "ms_per_launch": ms_main / args.steps}
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import oracle
+        oracle.build()
+        v, steps, nc, cores = cpu_sample(args.lattice, args.cpu_size, args.cpu_budget)
+        cpu = {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port",
+               "sample": f"{args.lattice} {args.cpu_size}^{ndim} box ({nc} cells), same BCs/omega, {steps} steps of oracle/lbm_oracle.c "
+                         f"(reference algorithm; serial collision pass like src/lbm/solver.cpp:601)"}
+    line = {
+        "metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": config_dict(args, f"{st0['cells_fast']} of {st0['ncells']} cells on the index-free chunk path; setup {t_setup:.1f} s"),
+        "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--lattice", default="D3Q19", choices=sorted(LATTICES))
+    ap.add_argument("--arithmetic", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-size", type=int, default=128, dest="cpu_size")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, dest="cpu_budget")
+    ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    ap.add_argument("--no-e2e", action="store_true", dest="no_e2e")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

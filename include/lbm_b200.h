@@ -143,12 +143,26 @@ typedef struct {
   int64_t launches;        /* kernels launched since init */
   int64_t launches_main;   /* of which: fused stream+collide launches */
   double  bytes_per_cell_alg; /* 2*Q*sizeof(real) */
+  int64_t h2d_bytes;       /* bytes copied host->device / device->host by set_/get_ calls since init */
+  int64_t d2h_bytes;
 } lbm_b200_stats;
 int lbm_b200_get_stats(const lbm_b200_solver* s, lbm_b200_stats* out);
 
 /* Time `nsteps` steps with CUDA events on the solver's stream; *ms_total covers all kernels of those steps,
  * *ms_main only the fused stream+collide kernel (events around each launch). Synchronous. */
 int lbm_b200_step_timed(lbm_b200_solver* s, int64_t nsteps, float* ms_total, float* ms_main);
+
+/* Synthetic benchmark grid.  The reference's `--bench` is unimplemented for the LBM solver (initBenchmark:
+ * TERMM("Not implemented!"), src/lbm/solver.cpp:39-46) and its grid generator's bench set-up aborts
+ * (src/gridgenerator/gridGenerator.cpp:43-54); this builds what that path would hand to the solver for a uniform box of
+ * shape[0] x shape[1] (x shape[2]) cells: cells in the order of the reference's space-filling curve
+ * (include/common/math/hilbert.h:16-48), nghbr[cell*stride + dir] with axis neighbours (grid-level periodic links
+ * where periodic[d] != 0, src/cartesiangrid.h:608-706) and diagonal neighbours composed from axis steps in x, y, z
+ * order (src/cartesiangrid.h:451-493, extended to 3D in LBMethod<D3Q27>::m_dirs order).  stride >= 8 (2D) / 26 (3D).
+ * center[cell*ndim + d] = (coord + 0.5) / max(shape) and coords[cell*ndim + d] (integer) are optional. */
+int64_t lbm_b200_box_ncells(int32_t ndim, const int64_t* shape);
+int lbm_b200_box_topology(int32_t ndim, const int64_t* shape, const int32_t* periodic, int64_t* nghbr, int32_t stride,
+                          double* center, int64_t* coords);
 
 const char* lbm_b200_last_error(void);
 int         lbm_b200_abi_version(void);

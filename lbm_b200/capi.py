@@ -37,7 +37,7 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("ncells", C.c_int64), ("cells_fast", C.c_int64), ("cells_generic", C.c_int64), ("chunk_cells", C.c_int64),
                 ("slots_bc", C.c_int64), ("slots_stale", C.c_int64), ("device_bytes", C.c_int64), ("launches", C.c_int64),
-                ("launches_main", C.c_int64), ("bytes_per_cell_alg", C.c_double)]
+                ("launches_main", C.c_int64), ("bytes_per_cell_alg", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
 def library_path():
@@ -96,6 +96,9 @@ def load_library():
     L.lbm_b200_steps_done.argtypes = [vp]
     L.lbm_b200_steps_done.restype = i64
     L.lbm_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.lbm_b200_box_ncells.argtypes = [i32, pi64]
+    L.lbm_b200_box_ncells.restype = i64
+    L.lbm_b200_box_topology.argtypes = [i32, pi64, np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS"), pi64, i32, vp, vp]
     L.lbm_b200_last_error.restype = C.c_char_p
     L.lbm_b200_abi_version.restype = C.c_int
     _LIB = L
@@ -239,3 +242,24 @@ class Solver:
         st = Stats()
         self._check(self._lib.lbm_b200_get_stats(self._h, C.byref(st)))
         return {k: getattr(st, k) for k, _ in Stats._fields_}
+
+
+def box_topology(shape, periodic, want_center=True, want_coords=False):
+    """Synthetic benchmark box in the reference's table format (include/lbm_b200.h: lbm_b200_box_topology)."""
+    L = load_library()
+    shape = _i64(shape)
+    ndim = len(shape)
+    per = np.ascontiguousarray(periodic, dtype=np.int32)
+    n = int(L.lbm_b200_box_ncells(ndim, shape))
+    if n <= 0:
+        raise ValueError("bad shape")
+    stride = 8 if ndim == 2 else 26
+    nghbr = np.empty((n, stride), dtype=np.int64)
+    center = np.empty((n, ndim)) if want_center else None
+    coords = np.empty((n, ndim), dtype=np.int64) if want_coords else None
+    rc = L.lbm_b200_box_topology(ndim, shape, per, nghbr.reshape(-1), stride,
+                                 center.ctypes.data_as(C.c_void_p) if want_center else None,
+                                 coords.ctypes.data_as(C.c_void_p) if want_coords else None)
+    if rc != 0:
+        raise LbmB200Error(rc, L.lbm_b200_last_error().decode())
+    return nghbr, center, coords

@@ -504,6 +504,22 @@ __global__ void k_gather_all(const __grid_constant__ DevParams<Real> p, int32_t 
   }
 }
 
+// host layout (reference: array of structures, double, reference cell order) <-> device layout (SoA, Real, plan order)
+template <class Real>
+__global__ void k_unpack_aos(const double* __restrict__ aos, const int32_t* __restrict__ ref2dev, int64_t n, int width, Real* __restrict__ soa, int64_t stride) {
+  const int64_t c = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if(c >= n) return;
+  const int32_t dv = ref2dev[c];
+  for(int j = 0; j < width; ++j) soa[static_cast<size_t>(j) * stride + dv] = static_cast<Real>(aos[c * width + j]);
+}
+template <class Real>
+__global__ void k_pack_aos(const Real* __restrict__ soa, const int32_t* __restrict__ ref2dev, int64_t n, int width, double* __restrict__ aos, int64_t stride) {
+  const int64_t c = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if(c >= n) return;
+  const int32_t dv = ref2dev[c];
+  for(int j = 0; j < width; ++j) aos[c * width + j] = static_cast<double>(soa[static_cast<size_t>(j) * stride + dv]);
+}
+
 // initialCondition(): rho = 1, u = preset, f = feq  (solver.cpp:267-295)
 template <class L, class Real, bool STRICT>
 __global__ void k_init(Real* __restrict__ f, const Real* __restrict__ vars0, int64_t stride, int32_t ncells) {

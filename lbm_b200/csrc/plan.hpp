@@ -47,8 +47,7 @@ struct BcInput {
 struct PlanInput {
   LatticeRT            L;
   int64_t              n = 0;
-  int                  stride = 0;
-  const int64_t*       nghbr = nullptr; // caller memory, valid during build
+  std::vector<int32_t> nghbr;           // n * (Q-1) push table, compacted from the caller's int64 table
   std::vector<double>  center;          // n*D or empty
   double               bbmin[3] = {0, 0, 0}, bbmax[3] = {0, 0, 0}, cell_length = 0;
   std::vector<BcInput> bcs;
@@ -163,10 +162,9 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
   P.L = L;
   P.n = N;
   P.CH = CH;
-  if(N <= 0 || in.nghbr == nullptr) { P.error = "no topology set"; return false; }
+  if(N <= 0 || in.nghbr.empty()) { P.error = "no topology set"; return false; }
   if(N >= (int64_t(1) << 28) * 8) { P.error = "too many cells for 32-bit device indices"; return false; }
-  if(in.stride < QM) { P.error = "neighbour table stride smaller than Q-1"; return false; }
-  auto NB = [&](int64_t c, int j) -> int64_t { return in.nghbr[c * in.stride + j]; };
+  auto NB = [&](int64_t c, int j) -> int64_t { return in.nghbr[static_cast<size_t>(c) * QM + j]; };
 
   // ---- 1. pull table = inverse of the push table (serial order: the highest source wins, like the
   //         reference's loop would leave it if two cells pushed to one slot)
@@ -178,9 +176,6 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
       if(t >= 0 && t < N) pull[static_cast<size_t>(t) * QM + j] = static_cast<int32_t>(s);
     }
   }
-  for(int64_t s = 0; s < N; ++s)
-    for(int j = 0; j < QM; ++j)
-      if(NB(s, j) >= N || NB(s, j) < -1) { P.error = "neighbour id out of range"; return false; }
 
   // ---- 2. boundary conditions, in the reference's order: preApply writes, then the push, then apply writes
   std::unordered_map<int64_t, SlotDesc> over;  // slot key c*Q+j -> final descriptor

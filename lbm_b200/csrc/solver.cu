@@ -11,6 +11,7 @@
 #include "../../include/lbm_b200.h"
 #include "kernels.cuh"
 #include "plan.hpp"
+#include "grid_box.hpp"
 
 namespace {
 
@@ -61,7 +62,6 @@ struct SolverBase {
   virtual void stats(lbm_b200_stats* st) const                           = 0;
   lbm_b200_config cfg{};
   lbm::PlanInput  in;
-  std::vector<int64_t> nghbr_copy;
   cudaStream_t    stream = nullptr;
   bool            inited = false;
   int64_t         t      = 0;
@@ -86,6 +86,9 @@ struct Solver final : SolverBase {
   DevBuf<lbm::VarFixDev<Real>>  d_varfix;
   DevBuf<Real>     d_uext[2], d_values[2];
   DevBuf<double>   d_partial;
+  DevBuf<double>   stage;     // AoS staging for host transfers [n][Q]
+  DevBuf<int32_t>  d_ref2dev;
+  int64_t          h2d_bytes = 0, d2h_bytes = 0;
   int cur = 0;       // f[cur] holds the current post-collision populations
   int dyn = 0;       // d_uext[dyn] / d_values[dyn] are the ones the next gather must use
   int vcur = 0;      // vars[vcur] = m_vars, vars[vcur^1] = m_varsold
@@ -146,9 +149,7 @@ struct Solver final : SolverBase {
 
   int init() override {
     if(!lbm::build_plan(in, plan)) return fail(plan.error.find("order-dependent") != std::string::npos ? LBM_B200_EUNSUP : LBM_B200_EINVAL, plan.error);
-    nghbr_copy.clear();
-    nghbr_copy.shrink_to_fit();
-    in.nghbr = nullptr;
+    std::vector<int32_t>().swap(in.nghbr);
     CUDA_TRY(cudaSetDevice(cfg.device));
     const size_t npad = static_cast<size_t>(plan.npad);
     for(int b = 0; b < 2; ++b) {
@@ -166,6 +167,7 @@ struct Solver final : SolverBase {
     CUDA_TRY(d_tmpl.upload(plan.tmpl));
     CUDA_TRY(d_chunk_nb.upload(plan.chunk_nb));
     CUDA_TRY(d_codes.upload(plan.codes));
+    CUDA_TRY(d_ref2dev.upload(plan.ref2dev));
     {
       std::vector<lbm::CopySrcDev> h;
       for(auto& c : plan.copytab) h.push_back({c.cell, c.dir});
@@ -364,27 +366,35 @@ struct Solver final : SolverBase {
     return LBM_B200_OK;
   }
 
-  // SoA device array [width][npad] -> AoS host array [n][width] in reference cell order
+  // SoA device array [width][npad] -> AoS host array [n][width] in reference cell order (and back).
+  // The transposition runs on the device; the host side is one cudaMemcpy of the reference's own layout, so a
+  // pinned caller buffer moves at PCIe speed.
+  int ensure_stage() {
+    if(stage.p == nullptr) CUDA_TRY(stage.alloc(static_cast<size_t>(plan.n) * Q));
+    return LBM_B200_OK;
+  }
   int download(const Real* dsrc, int width, double* out) {
-    const size_t npad = static_cast<size_t>(plan.npad);
-    std::vector<Real> h(npad * width);
+    int rc = ensure_stage();
+    if(rc) return rc;
+    const int nb = static_cast<int>((plan.n + 255) / 256);
+    lbm::k_pack_aos<Real><<<nb, 256, 0, stream>>>(dsrc, d_ref2dev.p, plan.n, width, stage.p, plan.npad);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, stage.p, sizeof(double) * static_cast<size_t>(plan.n) * width, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
-    CUDA_TRY(cudaMemcpy(h.data(), dsrc, h.size() * sizeof(Real), cudaMemcpyDeviceToHost));
-#pragma omp parallel for schedule(static)
-    for(int64_t c = 0; c < plan.n; ++c) {
-      const size_t dv = static_cast<size_t>(plan.ref2dev[c]);
-      for(int j = 0; j < width; ++j) out[c * width + j] = static_cast<double>(h[static_cast<size_t>(j) * npad + dv]);
-    }
+    d2h_bytes += static_cast<int64_t>(sizeof(double)) * plan.n * width;
     return LBM_B200_OK;
   }
   int upload_aos(const double* src, int width, Real* ddst) {
-    const size_t npad = static_cast<size_t>(plan.npad);
-    std::vector<Real> h(npad * width, Real(0));
-    for(int64_t c = 0; c < plan.n; ++c) {
-      const size_t dv = static_cast<size_t>(plan.ref2dev[c]);
-      for(int j = 0; j < width; ++j) h[static_cast<size_t>(j) * npad + dv] = static_cast<Real>(src[c * width + j]);
-    }
-    CUDA_TRY(cudaMemcpy(ddst, h.data(), h.size() * sizeof(Real), cudaMemcpyHostToDevice));
+    int rc = ensure_stage();
+    if(rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(stage.p, src, sizeof(double) * static_cast<size_t>(plan.n) * width, cudaMemcpyHostToDevice, stream));
+    const int nb = static_cast<int>((plan.n + 255) / 256);
+    lbm::k_unpack_aos<Real><<<nb, 256, 0, stream>>>(stage.p, d_ref2dev.p, plan.n, width, ddst, plan.npad);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    h2d_bytes += static_cast<int64_t>(sizeof(double)) * plan.n * width;
     return LBM_B200_OK;
   }
 
@@ -425,6 +435,7 @@ struct Solver final : SolverBase {
     int rc = upload_aos(fi, Q, f[cur].p);
     if(rc) return rc;
     CUDA_TRY(prev_fold.alloc(static_cast<size_t>(plan.npad) * Q));
+    CUDA_TRY(cudaMemset(prev_fold.p, 0, prev_fold.bytes()));
     rc = upload_aos(foldi, Q, prev_fold.p);
     if(rc) return rc;
     // slots nothing ever writes now keep the supplied m_fold value
@@ -503,6 +514,8 @@ struct Solver final : SolverBase {
     st->launches      = launches;
     st->launches_main = launches_main;
     st->bytes_per_cell_alg = 2.0 * Q * sizeof(Real);
+    st->h2d_bytes = h2d_bytes;
+    st->d2h_bytes = d2h_bytes;
   }
 };
 
@@ -576,10 +589,22 @@ int lbm_b200_set_topology(lbm_b200_solver* s, const int64_t* nghbr, int32_t stri
   CHECK_HANDLE(s);
   CHECK_NOT_INITED(s);
   if(nghbr == nullptr || stride < s->impl->in.L.Q - 1) return fail(LBM_B200_EINVAL, "bad neighbour table");
-  auto& im = *s->impl;
-  im.nghbr_copy.assign(nghbr, nghbr + static_cast<size_t>(im.in.n) * stride);
-  im.in.nghbr  = im.nghbr_copy.data();
-  im.in.stride = stride;
+  auto&         in = s->impl->in;
+  const int     QM = in.L.Q - 1;
+  const int64_t N  = in.n;
+  in.nghbr.resize(static_cast<size_t>(N) * QM);
+  int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+  for(int64_t c = 0; c < N; ++c)
+    for(int j = 0; j < QM; ++j) {
+      const int64_t t = nghbr[c * stride + j];
+      if(t < -1 || t >= N) bad |= 1;
+      in.nghbr[static_cast<size_t>(c) * QM + j] = static_cast<int32_t>(t);
+    }
+  if(bad) {
+    std::vector<int32_t>().swap(in.nghbr);
+    return fail(LBM_B200_EINVAL, "neighbour id out of range");
+  }
   return LBM_B200_OK;
 }
 
@@ -672,7 +697,7 @@ int lbm_b200_set_stream(lbm_b200_solver* s, void* cuda_stream) {
 int lbm_b200_init(lbm_b200_solver* s) {
   CHECK_HANDLE(s);
   CHECK_NOT_INITED(s);
-  if(s->impl->in.nghbr == nullptr) return fail(LBM_B200_ESTATE, "lbm_b200_set_topology has not been called");
+  if(s->impl->in.nghbr.empty()) return fail(LBM_B200_ESTATE, "lbm_b200_set_topology has not been called");
   return s->impl->init();
 }
 
@@ -727,6 +752,24 @@ int lbm_b200_get_stats(const lbm_b200_solver* s, lbm_b200_stats* out) {
   if(out == nullptr) return fail(LBM_B200_EINVAL, "null argument");
   if(!s->impl->inited) return fail(LBM_B200_ESTATE, "not initialised");
   s->impl->stats(out);
+  return LBM_B200_OK;
+}
+
+int64_t lbm_b200_box_ncells(int32_t ndim, const int64_t* shape) {
+  if(shape == nullptr || ndim < 2 || ndim > 3) return -1;
+  int64_t n = 1;
+  for(int d = 0; d < ndim; ++d) {
+    if(shape[d] <= 0) return -1;
+    n *= shape[d];
+  }
+  return n;
+}
+
+int lbm_b200_box_topology(int32_t ndim, const int64_t* shape, const int32_t* periodic, int64_t* nghbr, int32_t stride, double* center,
+                          int64_t* coords) {
+  if(shape == nullptr || periodic == nullptr || nghbr == nullptr) return fail(LBM_B200_EINVAL, "null argument");
+  std::string err;
+  if(!lbm::box_topology(ndim, shape, periodic, nghbr, stride, center, coords, &err)) return fail(LBM_B200_EINVAL, err);
   return LBM_B200_OK;
 }
 

@@ -64,8 +64,9 @@ def test_fast_fp64_within_1e12(name, oracle_mod):
     assert rel_err(g.fold, o.fold) < 1e-12
     vo, vg = o.vars, g.vars
     assert rel_err(vg[:, -1], vo[:, -1]) < 1e-12          # density
-    # velocities are ~1e-5 of the lattice speed: 1e-12 relative to the flow's velocity scale
-    assert np.max(np.abs(vg[:, :-1] - vo[:, :-1])) < 1e-12 * max(np.max(np.abs(vo[:, :-1])), 1e-30) + 1e-17
+    # velocities: these flows run at Ma 1e-4..1e-2, so u is a 1e-6..1e-3 difference of O(0.1) populations and cannot
+    # be more accurate than the populations' own rounding; the tolerance is 1e-12 of the lattice speed of sound
+    assert np.max(np.abs(vg[:, :-1] - vo[:, :-1])) < 1e-12 / np.sqrt(3.0)
 
 
 def box_spec(shape, ndist, periodic, omega=1.0 / 0.6, lid=None):
