@@ -161,6 +161,9 @@ int lbm_b200_step_timed(lbm_b200_solver* s, int64_t nsteps, float* ms_total, flo
  * order (src/cartesiangrid.h:451-493, extended to 3D in LBMethod<D3Q27>::m_dirs order).  stride >= 8 (2D) / 26 (3D).
  * center[cell*ndim + d] = (coord + 0.5) / max(shape) and coords[cell*ndim + d] (integer) are optional. */
 int64_t lbm_b200_box_ncells(int32_t ndim, const int64_t* shape);
+/* hilbert::index<NDIM>(x, level) of the reference (include/common/math/hilbert.h:16-48): x in unit-cube coordinates,
+ * 1 <= ndim <= 4.  Returns -1 on bad arguments. */
+int64_t lbm_b200_sfc_index(int32_t ndim, const double* x, int32_t level);
 int lbm_b200_box_topology(int32_t ndim, const int64_t* shape, const int32_t* periodic, int64_t* nghbr, int32_t stride,
                           double* center, int64_t* coords);
 

@@ -41,7 +41,8 @@ class Stats(C.Structure):
 
 
 def library_path():
-    return os.path.join(_HERE, "liblbm_b200.so")
+    # LBM_B200_LIB selects a tuning build of the same library (kernel experiments); never a different backend
+    return os.environ.get("LBM_B200_LIB") or os.path.join(_HERE, "liblbm_b200.so")
 
 
 def build(force=False):
@@ -99,6 +100,8 @@ def load_library():
     L.lbm_b200_box_ncells.argtypes = [i32, pi64]
     L.lbm_b200_box_ncells.restype = i64
     L.lbm_b200_box_topology.argtypes = [i32, pi64, np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS"), pi64, i32, vp, vp]
+    L.lbm_b200_sfc_index.argtypes = [i32, pdbl, i32]
+    L.lbm_b200_sfc_index.restype = i64
     L.lbm_b200_last_error.restype = C.c_char_p
     L.lbm_b200_abi_version.restype = C.c_int
     _LIB = L
@@ -263,3 +266,9 @@ def box_topology(shape, periodic, want_center=True, want_coords=False):
     if rc != 0:
         raise LbmB200Error(rc, L.lbm_b200_last_error().decode())
     return nghbr, center, coords
+
+
+def sfc_index(x, level):
+    """hilbert::index of the reference for unit-cube coordinates x (host code of the library)."""
+    x = _f64(x)
+    return int(load_library().lbm_b200_sfc_index(len(x), x, int(level)))

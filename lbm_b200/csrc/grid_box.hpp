@@ -36,6 +36,22 @@ inline int64_t xyz_to_key(int ndim, int level, const int64_t* xyz) {
   return key;
 }
 
+// hilbert::index as the reference evaluates it: on unit-cube coordinates, by repeated halving in floating point
+// (/root/reference/include/common/math/hilbert.h:16-48). Supports up to 4 dimensions like the reference.
+inline int64_t sfc_index_unit(int ndim, const double* x, int level) {
+  double pos[4] = {0, 0, 0, 0};
+  for(int d = 0; d < ndim; ++d) pos[d] = x[d];
+  int64_t index = 0;
+  for(int l = 0; l < level; ++l) {
+    int q = 0;
+    for(int d = 0; d < ndim; ++d)
+      if(pos[d] >= 0.5) q |= 1 << d;
+    index = (index << ndim) | sfc_lut(q);
+    for(int d = 0; d < ndim; ++d) pos[d] = 2 * pos[d] - ((q >> d) & 1);
+  }
+  return index;
+}
+
 inline bool box_topology(int ndim, const int64_t* shape, const int32_t* periodic, int64_t* nghbr, int stride, double* center,
                          int64_t* coords, std::string* err) {
   if(ndim != 2 && ndim != 3) { *err = "box: ndim must be 2 or 3"; return false; }

@@ -356,13 +356,19 @@ __device__ __forceinline__ void update_and_store(const DevParams<Real>& p, int32
   }
 }
 
-constexpr int kThreads = 256;
+#ifndef LBM_THREADS
+#define LBM_THREADS 256
+#endif
+#ifndef LBM_MINBLOCKS
+#define LBM_MINBLOCKS 2
+#endif
+constexpr int kThreads = LBM_THREADS;
 
 template <class L, class Real, bool STRICT, int COLL>
-__global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevParams<Real> p) {
+__global__ void __launch_bounds__(kThreads, LBM_MINBLOCKS) k_step(const __grid_constant__ DevParams<Real> p) {
   constexpr int Q = L::Q, QM = Q - 1, CH = L::CHUNK, NSEL = L::NSEL;
   __shared__ uint16_t s_tmpl[QM * CH];
-  __shared__ int32_t  s_nb[NSEL];
+  __shared__ int32_t  s_nb[2][NSEL];
   const Real* __restrict__ Abuf = p.A;
 
   if(static_cast<int>(blockIdx.x) < p.n_gen_blocks) {
@@ -379,10 +385,14 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPa
   // ---- fast path: persistent CTA over SFC chunks, template in shared memory, no per-cell index traffic
   const int fb = blockIdx.x - p.n_gen_blocks;
   for(int t = threadIdx.x; t < QM * CH; t += kThreads) s_tmpl[t] = p.tmpl[t];
+  int buf = 0;
   for(int chunk = fb; chunk < p.n_fast_chunks; chunk += p.n_fast_blocks) {
+    // neighbour-chunk bases are double buffered: one barrier per chunk is enough (a thread can run at most one
+    // chunk ahead of the slowest one, and then it writes the other buffer)
+    buf ^= 1;
+    if(threadIdx.x < NSEL) s_nb[buf][threadIdx.x] = p.chunk_nb[static_cast<size_t>(chunk) * NSEL + threadIdx.x];
     __syncthreads();
-    if(threadIdx.x < NSEL) s_nb[threadIdx.x] = p.chunk_nb[static_cast<size_t>(chunk) * NSEL + threadIdx.x];
-    __syncthreads();
+    const int32_t* nb  = s_nb[buf];
     const int32_t base = chunk * CH;
 #pragma unroll 1
     for(int o = threadIdx.x; o < CH; o += kThreads) {
@@ -395,7 +405,7 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPa
 #pragma unroll
         for(int j = 0; j < QM; ++j) {
           const uint32_t t   = s_tmpl[j * CH + o];
-          const int32_t  src = s_nb[t >> 10] + static_cast<int32_t>(t & 1023u);
+          const int32_t  src = nb[t >> 10] + static_cast<int32_t>(t & 1023u);
           fold[j]            = Abuf[static_cast<size_t>(j) * p.stride + src];
         }
         fold[QM] = Abuf[static_cast<size_t>(QM) * p.stride + cell];

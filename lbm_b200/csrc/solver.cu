@@ -521,6 +521,11 @@ struct Solver final : SolverBase {
 
 SolverBase* make_solver(const lbm_b200_config& c) {
   const bool dbl = c.precision == LBM_B200_FP64;
+#ifdef LBM_EXPERIMENT_D3Q19_F64
+  // tuning builds: one instantiation only, to keep compile times short
+  if(c.ndim == 3 && c.ndist == 19 && dbl) return new Solver<lbm::Lattice<3, 19>, double>();
+  return nullptr;
+#endif
   if(c.ndim == 2 && c.ndist == 9) return dbl ? static_cast<SolverBase*>(new Solver<lbm::Lattice<2, 9>, double>()) : new Solver<lbm::Lattice<2, 9>, float>();
   if(c.ndim == 3 && c.ndist == 19) return dbl ? static_cast<SolverBase*>(new Solver<lbm::Lattice<3, 19>, double>()) : new Solver<lbm::Lattice<3, 19>, float>();
   if(c.ndim == 3 && c.ndist == 27) return dbl ? static_cast<SolverBase*>(new Solver<lbm::Lattice<3, 27>, double>()) : new Solver<lbm::Lattice<3, 27>, float>();
@@ -753,6 +758,11 @@ int lbm_b200_get_stats(const lbm_b200_solver* s, lbm_b200_stats* out) {
   if(!s->impl->inited) return fail(LBM_B200_ESTATE, "not initialised");
   s->impl->stats(out);
   return LBM_B200_OK;
+}
+
+int64_t lbm_b200_sfc_index(int32_t ndim, const double* x, int32_t level) {
+  if(x == nullptr || ndim < 1 || ndim > 4 || level < 0 || ndim * level > 62) return -1;
+  return lbm::sfc_index_unit(ndim, x, level);
 }
 
 int64_t lbm_b200_box_ncells(int32_t ndim, const int64_t* shape) {

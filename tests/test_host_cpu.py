@@ -1,0 +1,76 @@
+"""CPU-side tests: the C ABI loads and exports what include/lbm_b200.h declares, the host-side grid code agrees with the
+reference's known answers and with the brute-force numpy restatement, and the library refuses to compute without a GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import lbm_b200
+from gridgen import box_grid, sfc_key, sfc_key_from_unit
+from lbm_b200.capi import box_topology, sfc_index
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = lbm_b200.load_library()
+    names = lbm_b200.abi_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"liblbm_b200.so does not export {n}"
+    assert lib.lbm_b200_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device creating a solver must fail loudly (there is no CPU path in the product)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    nghbr = np.full((16, 8), -1, dtype=np.int64)
+    with pytest.raises(lbm_b200.LbmB200Error) as e:
+        lbm_b200.Solver(2, 9, nghbr, 1.0)
+    assert e.value.code == -3
+
+
+def test_sfc_index_reference_known_answers():
+    """UnitTest/test_hilbert.cpp of the reference: every EXPECT_EQ, for the library's host code and the numpy restatement."""
+    kats = json.load(open(os.path.join(HERE, "golden", "hilbert_kat.json")))["kats"]
+    assert len(kats) >= 100
+    for k in kats:
+        assert sfc_index(k["x"], k["level"]) == k["index"], k
+        assert sfc_key_from_unit(k["x"], k["level"]) == k["index"], k
+
+
+def test_integer_key_equals_unit_cube_key():
+    rng = np.random.default_rng(1)
+    for ndim, level in ((2, 5), (3, 4), (3, 9)):
+        c = rng.integers(0, 2 ** level, size=(200, ndim))
+        keys = sfc_key(c, level)
+        for row, key in zip(c, keys):
+            assert sfc_index((row + 0.5) / 2 ** level, level) == key
+
+
+@pytest.mark.parametrize("shape,periodic", [((4, 4), (1, 0)), ((12, 7), (0, 1)), ((33, 20), (0, 0)), ((8, 8, 8), (1, 0, 0)),
+                                            ((5, 9, 6), (1, 1, 0)), ((16, 16, 16), (1, 1, 1)), ((20, 12, 9), (0, 0, 0))])
+def test_box_topology_matches_numpy_restatement(shape, periodic):
+    nb, ce, co = box_topology(shape, periodic, True, True)
+    g = box_grid(shape, [bool(p) for p in periodic])
+    assert np.array_equal(nb, g["nghbr"])
+    assert np.array_equal(co, g["coords"])
+    assert np.allclose(ce, g["center"], rtol=0, atol=0)
+
+
+def test_box_order_is_ascending_key():
+    _, _, co = box_topology((24, 17, 9), (0, 0, 0), False, True)
+    keys = sfc_key(co, 5)
+    assert np.all(np.diff(keys) > 0)
+
+
+def test_push_table_invariants_of_periodic_box():
+    nb, _, _ = box_topology((8, 8, 8), (1, 1, 1), False, False)
+    opp = [1, 0, 3, 2, 5, 4, 9, 8, 7, 6, 13, 12, 11, 10, 17, 16, 15, 14, 25, 24, 23, 22, 21, 20, 19, 18]
+    n = nb.shape[0]
+    for i in range(26):
+        assert sorted(nb[:, i]) == list(range(n))              # every direction is a permutation
+        assert np.array_equal(nb[nb[:, i], opp[i]], np.arange(n))  # and the opposite direction inverts it
