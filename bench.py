@@ -33,18 +33,40 @@ OMEGA = 1.0 / 0.6
 LID_U = 0.05
 
 
-def workload(size, lattice):
-    """Tables of the benchmark box in the reference's format + boundary conditions in application order."""
+def global_shape(size, ndim, world):
+    """weak scaling: every rank owns one size^ndim cube; the global box doubles along x, then y, then z"""
+    mult = [1] * ndim
+    w, d = world, 0
+    while w > 1:
+        if w % 2:
+            raise SystemExit("--gpus must be a power of two")
+        mult[d % ndim] *= 2
+        w //= 2
+        d += 1
+    return tuple(size * m for m in mult)
+
+
+def workload(size, lattice, rank=0, world=1):
+    """Tables of the benchmark box in the reference's format + boundary conditions in application order.
+    world > 1: this rank's contiguous range of the SFC-ordered list plus ghost cells (lbm_b200/partition.py)."""
     from lbm_b200.capi import box_topology
     ndim, ndist = LATTICES[lattice]
-    shape = (size,) * ndim
     periodic = (1,) + (0,) * (ndim - 1)
-    nghbr, center, _ = box_topology(shape, periodic, want_center=True)
+    lp = None
+    if world == 1:
+        shape = (size,) * ndim
+        nghbr, center, _ = box_topology(shape, periodic, want_center=True)
+        n_owned = nghbr.shape[0]
+    else:
+        from lbm_b200 import partition
+        shape = global_shape(size, ndim, world)
+        lp = partition.plan_rank(partition.BoxRows(shape, periodic, ndist), rank, world, 8 if ndim == 2 else 26)
+        nghbr, center, n_owned = lp.nghbr, None, lp.n_owned
     names = ["-x", "+x", "-y", "+y", "-z", "+z"][:2 * ndim]
     lid = names[-1]
     bcs = []
     for d, nm in sorted(enumerate(names), key=lambda t: t[1]):  # lexicographic, like the reference (bnd.h:71-142)
-        cells = np.nonzero(nghbr[:, d] < 0)[0].astype(np.int64)
+        cells = np.nonzero(nghbr[:n_owned, d] < 0)[0].astype(np.int64)
         if len(cells) == 0:
             continue
         normal = np.zeros(ndim)
@@ -56,7 +78,7 @@ def workload(size, lattice):
             bcs.append(("dirichlet_bb", cells, normals, value))
         else:
             bcs.append(("wall_bb", cells, normals, 0.0))
-    return dict(ndim=ndim, ndist=ndist, nghbr=nghbr, center=center, bcs=bcs, shape=shape)
+    return dict(ndim=ndim, ndist=ndist, nghbr=nghbr, center=center, bcs=bcs, shape=shape, lp=lp, n_owned=n_owned)
 
 
 def apply_bcs(solver, wl):
@@ -189,7 +211,8 @@ def config_dict(args, note):
     return {"workload": f"bench-3D cube {args.size}^{ndim} {args.lattice} BGK fp64 (BASELINE.json configs[2]; SURVEY 8d S3): "
                         f"periodic x, bounce-back walls, moving lid u={LID_U}, omega={OMEGA:.6f}",
             "cells_per_gpu": args.size ** ndim, "lattice": args.lattice, "collision": "bgk", "arithmetic": args.arithmetic,
-            "l2_policy": "inputs larger than L2 (no flush needed)", "parallelism": f"{args.gpus} x independent SFC-ordered box"
+            "l2_policy": "inputs larger than L2 (no flush needed)", "parallelism": (f"one box of {'x'.join(map(str, global_shape(args.size, ndim, args.gpus)))} cells cut into {args.gpus} contiguous "
+                            f"SFC ranges, ncclSend/ncclRecv halo exchange of outgoing populations every step")
             if args.gpus > 1 else "single GPU", "note": note}
 
 
@@ -206,11 +229,18 @@ def run_ours(args):
     ndim, ndist = LATTICES[args.lattice]
     arithmetic = lbm_b200.FAST if args.arithmetic == "fast" else lbm_b200.STRICT
     t_setup = time.perf_counter()
-    wl = workload(args.size, args.lattice)
-    n = wl["nghbr"].shape[0]
+    wl = workload(args.size, args.lattice, rank, world)
+    n = wl["n_owned"]
+    n_local = wl["nghbr"].shape[0]
     stream = torch.cuda.current_stream().cuda_stream
     s = lbm_b200.Solver(ndim, ndist, wl["nghbr"], OMEGA, arithmetic=arithmetic, device=local, track_vars=0, stream=stream)
     apply_bcs(s, wl)
+    if world > 1:
+        from lbm_b200.capi import comm_unique_id
+        uid = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        wl["lp"].apply_halo(s)
+        s.comm_init(uid[0], rank, world)
     s.init()
     del wl["nghbr"]
     t_setup = time.perf_counter() - t_setup
@@ -234,14 +264,14 @@ def run_ours(args):
         t = torch.tensor([ms_total, ms_main], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, ms_main = float(t[0]), float(t[1])
-    value = n * world * args.steps / (ms_total * 1e-3) / 1e6
+    value = args.size ** ndim * world * args.steps / (ms_total * 1e-3) / 1e6
 
     # ---- e2e: state in pinned host buffers, through the C ABI: upload m_f + m_fold, K steps, download the fields
     e2e = None
     if not args.no_e2e:
-        f_host = torch.empty((n, ndist), dtype=torch.float64, pin_memory=True)
-        fold_host = torch.empty((n, ndist), dtype=torch.float64, pin_memory=True)
-        mom_host = torch.empty((n, ndim + 1), dtype=torch.float64, pin_memory=True)
+        f_host = torch.empty((n_local, ndist), dtype=torch.float64, pin_memory=True)
+        fold_host = torch.empty((n_local, ndist), dtype=torch.float64, pin_memory=True)
+        mom_host = torch.empty((n_local, ndim + 1), dtype=torch.float64, pin_memory=True)
         import ctypes as C
         lib = s._lib
         lib.lbm_b200_get_populations(s._h, C.c_void_p(f_host.data_ptr()), C.c_void_p(fold_host.data_ptr()))
@@ -264,7 +294,7 @@ def run_ours(args):
         e2e = {"value": n * world * k / dt / 1e6, "unit": "MLUPS",
                "h2d_bytes_per_step": (b1["h2d_bytes"] - b0["h2d_bytes"]) / k, "d2h_bytes_per_step": (b1["d2h_bytes"] - b0["d2h_bytes"]) / k,
                "region": f"lbm_b200_set_populations(pinned m_f, m_fold) + {k} x lbm_b200_step + lbm_b200_get_moments(pinned)",
-               "finite": bool(torch.isfinite(mom_host).all())}
+               "finite": bool(torch.isfinite(mom_host[:n]).all())}
 
     if rank != 0:
         return

@@ -104,6 +104,26 @@ int lbm_b200_add_periodic(lbm_b200_solver* s, const int64_t* cells, const double
 int lbm_b200_set_forcing(lbm_b200_solver* s, const int64_t* inlet, int64_t ninlet, const int64_t* outlet,
                          int64_t noutlet, double gradient);
 
+/* ---- multi-GPU (one process per GPU). The reference has no domain decomposition (the MPI calls carry
+ * no simulation data); this is the B200-native replacement for the exchange its CHANGELOG only plans.
+ * The SFC-ordered cell list is cut into contiguous ranges, one per rank. A rank passes to lbm_b200_create / set_topology its
+ * owned cells followed by `nghost` ghost cells (copies of the remote cells its owned cells push to or pull from), with
+ * neighbour ids local to that list. After every step the library sends exactly the post-collision populations
+ * (cell, direction) that a peer's pull needs and receives the ones its own ghosts must hold: ncclSend/ncclRecv in one
+ * group on the solver's stream over NVLink. Lists are per peer, concatenated in peer order; both sides must use the
+ * same order (lbm_b200/partition.py derives them deterministically from the tables, without communication). */
+int lbm_b200_set_ghosts(lbm_b200_solver* s, int64_t nghost);
+int lbm_b200_set_halo(lbm_b200_solver* s, int32_t npeers, const int32_t* peers, const int64_t* send_count,
+                      const int64_t* send_cell, const int32_t* send_dir, const int64_t* recv_count,
+                      const int64_t* recv_cell, const int32_t* recv_dir);
+/* NCCL bootstrap: rank 0 creates the 128-byte id, the host program broadcasts it (torch.distributed / MPI), every rank
+ * calls lbm_b200_comm_init before lbm_b200_init. */
+int lbm_b200_comm_unique_id(char* out128);
+int lbm_b200_comm_init(lbm_b200_solver* s, const char* id128, int32_t rank, int32_t nranks);
+/* Rows of the synthetic box's table for an arbitrary list of global cell ids (what one rank of a partitioned run needs). */
+int lbm_b200_box_rows(int32_t ndim, const int64_t* shape, const int32_t* periodic, const int64_t* cells, int64_t ncells,
+                      int64_t* nghbr, int32_t stride, double* center);
+
 /* Optional: run the kernels on this cudaStream_t (default: the legacy default stream). */
 int lbm_b200_set_stream(lbm_b200_solver* s, void* cuda_stream);
 
@@ -145,6 +165,8 @@ typedef struct {
   double  bytes_per_cell_alg; /* 2*Q*sizeof(real) */
   int64_t h2d_bytes;       /* bytes copied host->device / device->host by set_/get_ calls since init */
   int64_t d2h_bytes;
+  int64_t cells_ghost;     /* copies of cells owned by other ranks */
+  int64_t halo_bytes;      /* bytes sent + received by the halo exchange since init */
 } lbm_b200_stats;
 int lbm_b200_get_stats(const lbm_b200_solver* s, lbm_b200_stats* out);
 

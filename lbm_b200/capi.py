@@ -37,7 +37,7 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("ncells", C.c_int64), ("cells_fast", C.c_int64), ("cells_generic", C.c_int64), ("chunk_cells", C.c_int64),
                 ("slots_bc", C.c_int64), ("slots_stale", C.c_int64), ("device_bytes", C.c_int64), ("launches", C.c_int64),
-                ("launches_main", C.c_int64), ("bytes_per_cell_alg", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("launches_main", C.c_int64), ("bytes_per_cell_alg", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("cells_ghost", C.c_int64), ("halo_bytes", C.c_int64)]
 
 
 def library_path():
@@ -100,6 +100,12 @@ def load_library():
     L.lbm_b200_box_ncells.argtypes = [i32, pi64]
     L.lbm_b200_box_ncells.restype = i64
     L.lbm_b200_box_topology.argtypes = [i32, pi64, np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS"), pi64, i32, vp, vp]
+    pi32 = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+    L.lbm_b200_set_ghosts.argtypes = [vp, i64]
+    L.lbm_b200_set_halo.argtypes = [vp, i32, pi32, pi64, pi64, pi32, pi64, pi64, pi32]
+    L.lbm_b200_comm_unique_id.argtypes = [C.c_char_p]
+    L.lbm_b200_comm_init.argtypes = [vp, C.c_char_p, i32, i32]
+    L.lbm_b200_box_rows.argtypes = [i32, pi64, pi32, pi64, i64, pi64, i32, vp]
     L.lbm_b200_sfc_index.argtypes = [i32, pdbl, i32]
     L.lbm_b200_sfc_index.restype = i64
     L.lbm_b200_last_error.restype = C.c_char_p
@@ -178,6 +184,18 @@ class Solver:
     def set_forcing(self, inlet, outlet, gradient):
         self._check(self._lib.lbm_b200_set_forcing(self._h, _i64(inlet), len(inlet), _i64(outlet), len(outlet),
                                                    float(gradient)))
+
+    # ---- multi-GPU
+    def set_ghosts(self, nghost):
+        self._check(self._lib.lbm_b200_set_ghosts(self._h, int(nghost)))
+
+    def set_halo(self, peers, send_count, send_cell, send_dir, recv_count, recv_cell, recv_dir):
+        i32a = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        self._check(self._lib.lbm_b200_set_halo(self._h, len(peers), i32a(peers), _i64(send_count), _i64(send_cell), i32a(send_dir),
+                                                _i64(recv_count), _i64(recv_cell), i32a(recv_dir)))
+
+    def comm_init(self, unique_id, rank, nranks):
+        self._check(self._lib.lbm_b200_comm_init(self._h, bytes(unique_id), int(rank), int(nranks)))
 
     def set_stream(self, cuda_stream):
         self._check(self._lib.lbm_b200_set_stream(self._h, C.c_void_p(int(cuda_stream))))
@@ -272,3 +290,30 @@ def sfc_index(x, level):
     """hilbert::index of the reference for unit-cube coordinates x (host code of the library)."""
     x = _f64(x)
     return int(load_library().lbm_b200_sfc_index(len(x), x, int(level)))
+
+
+def comm_unique_id():
+    """128-byte NCCL id (rank 0 creates it, the caller broadcasts it)."""
+    L = load_library()
+    buf = C.create_string_buffer(128)
+    rc = L.lbm_b200_comm_unique_id(buf)
+    if rc != 0:
+        raise LbmB200Error(rc, L.lbm_b200_last_error().decode())
+    return buf.raw
+
+
+def box_rows(shape, periodic, cells, want_center=False):
+    """Rows of the synthetic box table for the given global cell ids."""
+    L = load_library()
+    shape = _i64(shape)
+    ndim = len(shape)
+    per = np.ascontiguousarray(periodic, dtype=np.int32)
+    cells = _i64(cells)
+    stride = 8 if ndim == 2 else 26
+    nghbr = np.empty((len(cells), stride), dtype=np.int64)
+    center = np.empty((len(cells), ndim)) if want_center else None
+    rc = L.lbm_b200_box_rows(ndim, shape, per, cells, len(cells), nghbr.reshape(-1), stride,
+                             center.ctypes.data_as(C.c_void_p) if want_center else None)
+    if rc != 0:
+        raise LbmB200Error(rc, L.lbm_b200_last_error().decode())
+    return nghbr, center

@@ -530,6 +530,18 @@ __global__ void k_pack_aos(const Real* __restrict__ soa, const int32_t* __restri
   for(int j = 0; j < width; ++j) aos[c * width + j] = static_cast<double>(soa[static_cast<size_t>(j) * stride + dv]);
 }
 
+// halo exchange: gather the outgoing populations into one contiguous buffer / scatter the received ones into the ghosts
+template <class Real>
+__global__ void k_halo_pack(const Real* __restrict__ f, const int64_t* __restrict__ index, int64_t n, Real* __restrict__ out) {
+  const int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if(k < n) out[k] = f[index[k]];
+}
+template <class Real>
+__global__ void k_halo_unpack(Real* __restrict__ f, const int64_t* __restrict__ index, int64_t n, const Real* __restrict__ in) {
+  const int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if(k < n) f[index[k]] = in[k];
+}
+
 // initialCondition(): rho = 1, u = preset, f = feq  (solver.cpp:267-295)
 template <class L, class Real, bool STRICT>
 __global__ void k_init(Real* __restrict__ f, const Real* __restrict__ vars0, int64_t stride, int32_t ncells) {

@@ -54,6 +54,13 @@ struct PlanInput {
   bool                 forcing = false;
   std::vector<int64_t> inlet, outlet;
   double               gradient = 0;
+  // multi-GPU: the last n_ghost cells of the list are copies of cells owned by other ranks (never updated here, their
+  // populations arrive by halo exchange); halo lists are (local cell, direction) pairs per peer, already in wire order
+  int64_t              n_ghost = 0;
+  std::vector<int32_t> peers;
+  std::vector<int64_t> send_count, recv_count;
+  std::vector<int64_t> send_cell, recv_cell;
+  std::vector<int32_t> send_dir, recv_dir;
 };
 
 struct CopySrc { int32_t cell, dir; };
@@ -92,6 +99,8 @@ struct Plan {
   std::vector<int32_t>    u0_cells; // cells with a preset initial velocity (Dirichlet BB, bnd_dirichlet.h:44-50)
   std::vector<double>     u0_vals;  // D per entry
   int64_t slots_bc = 0, slots_stale = 0;
+  int64_t n_owned = 0, n_ghost = 0, ghost_begin = 0; // device range [ghost_begin, ghost_begin + n_ghost) holds the ghosts
+  std::vector<int64_t> send_index, recv_index;       // flat device indices dir * npad + cell, wire order
   std::string error;
 };
 
@@ -371,12 +380,20 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
       if(written.count(e.val)) { P.error = "forcing: value cell is itself a forced cell (order-dependent in the reference)"; return false; }
   }
 
-  // ---- 4. classify cells: plain = every slot is a pull
+  // ---- 4. classify cells: plain = every slot is a pull from an owned cell
+  const int64_t NO = N - in.n_ghost; // owned cells come first, ghosts last
+  if(NO <= 0) { P.error = "no owned cells"; return false; }
+  P.n_owned = NO;
+  P.n_ghost = in.n_ghost;
   std::vector<char> plain(static_cast<size_t>(N), 1);
 #pragma omp parallel for schedule(static)
-  for(int64_t c = 0; c < N; ++c)
-    for(int j = 0; j < QM; ++j)
-      if(pull[static_cast<size_t>(c) * QM + j] < 0) { plain[c] = 0; break; }
+  for(int64_t c = 0; c < N; ++c) {
+    if(c >= NO) { plain[c] = 0; continue; }
+    for(int j = 0; j < QM; ++j) {
+      const int32_t ps = pull[static_cast<size_t>(c) * QM + j];
+      if(ps < 0 || ps >= NO) { plain[c] = 0; break; }
+    }
+  }
   for(const auto& kv : over) plain[kv.first / Q] = 0;
 
   // ---- 5. SFC chunks: runs of CH consecutive cells that are internally ordered like the curve template
@@ -386,7 +403,7 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
   std::vector<int32_t> chunk_of(static_cast<size_t>(N), -1);
   {
     int64_t b = 0;
-    while(b + CH <= N) {
+    while(b + CH <= NO) {
       bool ok = true;
       for(int o = 0; o < CH && ok; ++o) {
         for(int j = 0; j < QM; ++j) {
@@ -422,7 +439,7 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
         const int64_t  src = pull[static_cast<size_t>(b + o) * QM + j];
         const int64_t  nb0 = src - (t & 1023);
         if(nbk[sel] == -1) {
-          if(nb0 < 0 || nb0 + CH > N || chunk_of[nb0] < 0 || cand_base[chunk_of[nb0]] != nb0) { ok = false; break; }
+          if(nb0 < 0 || nb0 + CH > NO || chunk_of[nb0] < 0 || cand_base[chunk_of[nb0]] != nb0) { ok = false; break; }
           nbk[sel] = nb0;
         } else if(nbk[sel] != nb0) { ok = false; break; }
       }
@@ -440,9 +457,11 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
   for(int64_t k = 0; k < nc; ++k) if(!fast[k]) { cand_dev[k] = pos; pos += CH; ++P.n_slow_chunks; }
   for(int64_t k = 0; k < nc; ++k)
     for(int o = 0; o < CH; ++o) P.ref2dev[cand_base[k] + o] = static_cast<int32_t>(cand_dev[k] + o);
-  for(int64_t c = 0; c < N; ++c)
+  for(int64_t c = 0; c < NO; ++c)
     if(chunk_of[c] < 0) { P.ref2dev[c] = static_cast<int32_t>(pos++); ++P.n_loose; }
   P.n_gen  = pos - P.gen_begin;
+  P.ghost_begin = pos;
+  for(int64_t c = NO; c < N; ++c) P.ref2dev[c] = static_cast<int32_t>(pos++);
   P.npad   = (pos + 63) / 64 * 64;
   P.gen_stride = (P.n_gen + 63) / 64 * 64;
   P.dev2ref.assign(static_cast<size_t>(P.npad), -1);
@@ -469,7 +488,7 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
   P.values.assign(1, 0.0);
   std::vector<std::pair<int64_t, int64_t>> stale_slots; // (ref cell, dir) -> static value index, filled at init
   std::vector<std::pair<size_t, int64_t>>  dyn_codes;   // code position -> dynamic value index
-  for(int64_t c = 0; c < N; ++c) {
+  for(int64_t c = 0; c < NO; ++c) {
     const int64_t dv = P.ref2dev[c];
     if(dv < P.gen_begin) continue;
     const int64_t g = dv - P.gen_begin;
@@ -528,6 +547,29 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
   for(PerPEntry& e : P.perp) { e.cell = P.ref2dev[e.cell]; e.vbase += static_cast<int32_t>(P.n_values_static); }
   for(VarFix& v : P.varfix) v.cell = P.ref2dev[v.cell];
   for(int32_t& c : P.u0_cells) c = P.ref2dev[c];
+  // halo lists -> flat device indices into the SoA population arrays
+  {
+    int64_t ns = 0, nr = 0;
+    for(int64_t v : in.send_count) ns += v;
+    for(int64_t v : in.recv_count) nr += v;
+    if(ns != static_cast<int64_t>(in.send_cell.size()) || nr != static_cast<int64_t>(in.recv_cell.size())
+       || in.send_cell.size() != in.send_dir.size() || in.recv_cell.size() != in.recv_dir.size()) {
+      P.error = "halo lists are inconsistent";
+      return false;
+    }
+    P.send_index.resize(in.send_cell.size());
+    P.recv_index.resize(in.recv_cell.size());
+    for(size_t k = 0; k < in.send_cell.size(); ++k) {
+      const int64_t c = in.send_cell[k];
+      if(c < 0 || c >= NO || in.send_dir[k] < 0 || in.send_dir[k] >= Q) { P.error = "halo send entry out of range"; return false; }
+      P.send_index[k] = static_cast<int64_t>(in.send_dir[k]) * P.npad + P.ref2dev[c];
+    }
+    for(size_t k = 0; k < in.recv_cell.size(); ++k) {
+      const int64_t c = in.recv_cell[k];
+      if(c < NO || c >= N || in.recv_dir[k] < 0 || in.recv_dir[k] >= Q) { P.error = "halo receive entry is not a ghost cell"; return false; }
+      P.recv_index[k] = static_cast<int64_t>(in.recv_dir[k]) * P.npad + P.ref2dev[c];
+    }
+  }
   {
     // m_vars fix-ups: keep only the last writer of every (cell, variable), in the reference's order
     std::unordered_map<int64_t, size_t> last;

@@ -12,6 +12,7 @@
 #include "kernels.cuh"
 #include "plan.hpp"
 #include "grid_box.hpp"
+#include "nccl_dyn.hpp"
 
 namespace {
 
@@ -21,6 +22,13 @@ int fail(int code, const std::string& msg) {
   g_error = msg;
   return code;
 }
+
+#define NCCL_TRY(expr)                                                                                  \
+  do {                                                                                                  \
+    ncclResult_t r_ = (expr);                                                                           \
+    if(r_ != ncclSuccess)                                                                               \
+      return fail(LBM_B200_ECUDA, std::string(#expr) + ": " + lbm::nccl_api().GetErrorString(r_));      \
+  } while(0)
 
 #define CUDA_TRY(expr)                                                                                  \
   do {                                                                                                  \
@@ -60,9 +68,12 @@ struct SolverBase {
   virtual int get_vars(double* vars, double* varsold)                    = 0;
   virtual int get_moments(double* m)                                     = 0;
   virtual void stats(lbm_b200_stats* st) const                           = 0;
+  virtual int64_t owned() const                                          = 0;
   lbm_b200_config cfg{};
   lbm::PlanInput  in;
   cudaStream_t    stream = nullptr;
+  ncclComm_t      comm   = nullptr;
+  int             comm_rank = 0, comm_size = 1;
   bool            inited = false;
   int64_t         t      = 0;
 };
@@ -88,6 +99,9 @@ struct Solver final : SolverBase {
   DevBuf<double>   d_partial;
   DevBuf<double>   stage;     // AoS staging for host transfers [n][Q]
   DevBuf<int32_t>  d_ref2dev;
+  DevBuf<int64_t>  d_send_idx, d_recv_idx;
+  DevBuf<Real>     d_sendbuf, d_recvbuf;
+  int64_t          halo_bytes = 0;
   int64_t          h2d_bytes = 0, d2h_bytes = 0;
   int cur = 0;       // f[cur] holds the current post-collision populations
   int dyn = 0;       // d_uext[dyn] / d_values[dyn] are the ones the next gather must use
@@ -168,6 +182,13 @@ struct Solver final : SolverBase {
     CUDA_TRY(d_chunk_nb.upload(plan.chunk_nb));
     CUDA_TRY(d_codes.upload(plan.codes));
     CUDA_TRY(d_ref2dev.upload(plan.ref2dev));
+    if(!in.peers.empty()) {
+      if(comm == nullptr) return fail(LBM_B200_ESTATE, "halo lists set but lbm_b200_comm_init has not been called");
+      CUDA_TRY(d_send_idx.upload(plan.send_index));
+      CUDA_TRY(d_recv_idx.upload(plan.recv_index));
+      CUDA_TRY(d_sendbuf.alloc(plan.send_index.size() + 1));
+      CUDA_TRY(d_recvbuf.alloc(plan.recv_index.size() + 1));
+    }
     {
       std::vector<lbm::CopySrcDev> h;
       for(auto& c : plan.copytab) h.push_back({c.cell, c.dir});
@@ -308,6 +329,35 @@ struct Solver final : SolverBase {
     return LBM_B200_OK;
   }
 
+  // Outgoing populations of this step -> peers, theirs -> my ghost cells.  One pack kernel, one NCCL group of
+  // send/recv pairs over NVLink, one unpack kernel, all on the solver's stream.
+  int halo_exchange(Real* buf) {
+    if(in.peers.empty()) return LBM_B200_OK;
+    auto& nc = lbm::nccl_api();
+    const int64_t ns = static_cast<int64_t>(plan.send_index.size()), nr = static_cast<int64_t>(plan.recv_index.size());
+    if(ns > 0) {
+      lbm::k_halo_pack<Real><<<static_cast<int>((ns + 255) / 256), 256, 0, stream>>>(buf, d_send_idx.p, ns, d_sendbuf.p);
+      ++launches;
+    }
+    const ncclDataType_t dt = sizeof(Real) == 8 ? ncclFloat64 : ncclFloat32;
+    NCCL_TRY(nc.GroupStart());
+    int64_t so = 0, ro = 0;
+    for(size_t k = 0; k < in.peers.size(); ++k) {
+      if(in.send_count[k] > 0) NCCL_TRY(nc.Send(d_sendbuf.p + so, static_cast<size_t>(in.send_count[k]), dt, in.peers[k], comm, stream));
+      if(in.recv_count[k] > 0) NCCL_TRY(nc.Recv(d_recvbuf.p + ro, static_cast<size_t>(in.recv_count[k]), dt, in.peers[k], comm, stream));
+      so += in.send_count[k];
+      ro += in.recv_count[k];
+    }
+    NCCL_TRY(nc.GroupEnd());
+    if(nr > 0) {
+      lbm::k_halo_unpack<Real><<<static_cast<int>((nr + 255) / 256), 256, 0, stream>>>(buf, d_recv_idx.p, nr, d_recvbuf.p);
+      ++launches;
+    }
+    halo_bytes += (ns + nr) * static_cast<int64_t>(sizeof(Real));
+    CUDA_TRY(cudaGetLastError());
+    return LBM_B200_OK;
+  }
+
   int one_step(bool time_main) {
     const int src = cur, dst = cur ^ 1;
     Real*     vout = nullptr;
@@ -322,6 +372,8 @@ struct Solver final : SolverBase {
     ++launches_main;
     CUDA_TRY(cudaGetLastError());
     int rc = cfg.arithmetic == LBM_B200_STRICT ? aux_kernels<true>(p, vout) : aux_kernels<false>(p, vout);
+    if(rc != LBM_B200_OK) return rc;
+    rc = halo_exchange(f[dst].p);
     if(rc != LBM_B200_OK) return rc;
     if(vout != nullptr) {
       vcur ^= 1;
@@ -484,7 +536,7 @@ struct Solver final : SolverBase {
     if(vars_step[vcur] != t || (t > 0 && vars_step[vcur ^ 1] != t - 1))
       return fail(LBM_B200_ESTATE, "m_vars / m_varsold of this step were not kept (track_vars interval)");
     const int nb = 592; // 4 x 148 SMs
-    lbm::k_residual<Real><<<nb, 256, 0, stream>>>(vars[vcur].p, vars[vcur ^ 1].p, plan.npad, plan.npad, NVAR, d_partial.p);
+    lbm::k_residual<Real><<<nb, 256, 0, stream>>>(vars[vcur].p, vars[vcur ^ 1].p, plan.npad, plan.ghost_begin, NVAR, d_partial.p);
     ++launches;
     CUDA_TRY(cudaGetLastError());
     std::vector<double> h(static_cast<size_t>(NVAR) * nb);
@@ -501,11 +553,15 @@ struct Solver final : SolverBase {
     return LBM_B200_OK;
   }
 
+  int64_t owned() const override { return plan.n_owned; }
+
   void stats(lbm_b200_stats* st) const override {
     std::memset(st, 0, sizeof(*st));
-    st->ncells        = plan.n;
+    st->ncells        = plan.n_owned;
     st->cells_fast    = plan.n_fast_chunks * plan.CH;
-    st->cells_generic = plan.n - st->cells_fast;
+    st->cells_generic = plan.n_owned - st->cells_fast;
+    st->cells_ghost   = plan.n_ghost;
+    st->halo_bytes    = halo_bytes;
     st->chunk_cells   = plan.CH;
     st->slots_bc      = plan.slots_bc;
     st->slots_stale   = plan.slots_stale;
@@ -583,7 +639,10 @@ int lbm_b200_create(const lbm_b200_config* cfg, int64_t ncells, lbm_b200_solver*
   return LBM_B200_OK;
 }
 
-void lbm_b200_destroy(lbm_b200_solver* s) { delete s; }
+void lbm_b200_destroy(lbm_b200_solver* s) {
+  if(s != nullptr && s->impl && s->impl->comm != nullptr) lbm::nccl_api().CommDestroy(s->impl->comm);
+  delete s;
+}
 
 #define CHECK_HANDLE(s)                                               \
   if((s) == nullptr || !(s)->impl) return fail(LBM_B200_EINVAL, "null solver handle")
@@ -690,6 +749,71 @@ int lbm_b200_set_forcing(lbm_b200_solver* s, const int64_t* inlet, int64_t ninle
   in.inlet.assign(inlet, inlet + ninlet);
   in.outlet.assign(outlet, outlet + noutlet);
   in.gradient = gradient;
+  return LBM_B200_OK;
+}
+
+int lbm_b200_set_ghosts(lbm_b200_solver* s, int64_t nghost) {
+  CHECK_HANDLE(s);
+  CHECK_NOT_INITED(s);
+  if(nghost < 0 || nghost >= s->impl->in.n) return fail(LBM_B200_EINVAL, "bad ghost count");
+  s->impl->in.n_ghost = nghost;
+  return LBM_B200_OK;
+}
+
+int lbm_b200_set_halo(lbm_b200_solver* s, int32_t npeers, const int32_t* peers, const int64_t* send_count, const int64_t* send_cell,
+                      const int32_t* send_dir, const int64_t* recv_count, const int64_t* recv_cell, const int32_t* recv_dir) {
+  CHECK_HANDLE(s);
+  CHECK_NOT_INITED(s);
+  if(npeers < 0 || (npeers > 0 && (!peers || !send_count || !recv_count))) return fail(LBM_B200_EINVAL, "bad halo description");
+  auto& in = s->impl->in;
+  in.peers.assign(peers, peers + npeers);
+  in.send_count.assign(send_count, send_count + npeers);
+  in.recv_count.assign(recv_count, recv_count + npeers);
+  int64_t ns = 0, nr = 0;
+  for(int k = 0; k < npeers; ++k) {
+    if(send_count[k] < 0 || recv_count[k] < 0) return fail(LBM_B200_EINVAL, "negative halo count");
+    ns += send_count[k];
+    nr += recv_count[k];
+  }
+  if((ns > 0 && (!send_cell || !send_dir)) || (nr > 0 && (!recv_cell || !recv_dir))) return fail(LBM_B200_EINVAL, "null halo list");
+  in.send_cell.assign(send_cell, send_cell + ns);
+  in.send_dir.assign(send_dir, send_dir + ns);
+  in.recv_cell.assign(recv_cell, recv_cell + nr);
+  in.recv_dir.assign(recv_dir, recv_dir + nr);
+  return LBM_B200_OK;
+}
+
+int lbm_b200_comm_unique_id(char* out128) {
+  if(out128 == nullptr) return fail(LBM_B200_EINVAL, "null argument");
+  std::string err;
+  if(!lbm::nccl_api().load(&err)) return fail(LBM_B200_ECUDA, err);
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  NCCL_TRY(lbm::nccl_api().GetUniqueId(&id));
+  std::memcpy(out128, &id, 128);
+  return LBM_B200_OK;
+}
+
+int lbm_b200_comm_init(lbm_b200_solver* s, const char* id128, int32_t rank, int32_t nranks) {
+  CHECK_HANDLE(s);
+  CHECK_NOT_INITED(s);
+  if(id128 == nullptr || nranks < 1 || rank < 0 || rank >= nranks) return fail(LBM_B200_EINVAL, "bad communicator description");
+  std::string err;
+  if(!lbm::nccl_api().load(&err)) return fail(LBM_B200_ECUDA, err);
+  CUDA_TRY(cudaSetDevice(s->impl->cfg.device));
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  NCCL_TRY(lbm::nccl_api().CommInitRank(&s->impl->comm, nranks, id, rank));
+  s->impl->comm_rank = rank;
+  s->impl->comm_size = nranks;
+  return LBM_B200_OK;
+}
+
+int lbm_b200_box_rows(int32_t ndim, const int64_t* shape, const int32_t* periodic, const int64_t* cells, int64_t ncells, int64_t* nghbr,
+                      int32_t stride, double* center) {
+  if(shape == nullptr || periodic == nullptr || nghbr == nullptr || (ncells > 0 && cells == nullptr)) return fail(LBM_B200_EINVAL, "null argument");
+  std::string err;
+  if(!lbm::box_rows(ndim, shape, periodic, cells, ncells, nghbr, stride, center, &err)) return fail(LBM_B200_EINVAL, err);
   return LBM_B200_OK;
 }
 

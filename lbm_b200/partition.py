@@ -1,0 +1,165 @@
+"""Partition of the SFC-ordered cell list into contiguous ranges, one per GPU (host logic, numpy).
+
+The reference has no domain decomposition (`partitionLevel`, halo/window cell properties and the
+load-balancing weights are declared but every implementation is a stub, src/cartesiangrid.h:709-710,
+src/loadbalancing_weights.h:6-31).  This is the B200-native design of SURVEY.md section 8e: equal-count contiguous ranges
+of the curve (uniform weights, the reference's only WeightMethod), ghost copies of the remote cells an owned cell pushes
+to or pulls from, and per-peer lists of exactly the (cell, direction) populations that cross the cut.
+
+Both sides of every exchange derive their list from the tables alone, in (global cell id, direction) order, so no
+set-up communication is needed and the partitioned run is bit-identical to the single-GPU run.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+OPP = {9: [1, 0, 3, 2, 6, 7, 4, 5, 8],
+       19: [1, 0, 3, 2, 5, 4, 9, 8, 7, 6, 13, 12, 11, 10, 17, 16, 15, 14, 18],
+       27: [1, 0, 3, 2, 5, 4, 9, 8, 7, 6, 13, 12, 11, 10, 17, 16, 15, 14, 25, 24, 23, 22, 21, 20, 19, 18, 26]}
+
+
+def bounds(n, world):
+    """Equal-count contiguous ranges: rank r owns [b[r], b[r+1])."""
+    return np.array([r * n // world for r in range(world + 1)], dtype=np.int64)
+
+
+class TableRows:
+    """Row provider over a full neighbour table held in memory (reference-sized cases)."""
+
+    def __init__(self, nghbr, ndist):
+        self.nghbr = np.ascontiguousarray(nghbr, dtype=np.int64)
+        self.n = self.nghbr.shape[0]
+        self.qm = ndist - 1
+        # inverse of the push table; the table need not be symmetric, so it is inverted explicitly
+        self.pull = np.full((self.n, self.qm), -1, dtype=np.int64)
+        src = np.arange(self.n, dtype=np.int64)
+        for j in range(self.qm):
+            t = self.nghbr[:, j]
+            ok = t >= 0
+            self.pull[t[ok], j] = src[ok]
+
+    def rows(self, ids):
+        return self.nghbr[ids][:, :self.qm]
+
+    def sources(self, ids):
+        return self.pull[ids]
+
+
+class BoxRows:
+    """Row provider for the synthetic benchmark box: rows are generated on demand (lbm_b200_box_rows), the full table of a
+    multi-GPU box never exists on any rank.  A box table is symmetric, so pull sources are the opposite-direction rows."""
+
+    def __init__(self, shape, periodic, ndist):
+        self.shape, self.periodic = tuple(shape), tuple(periodic)
+        self.n = int(np.prod(self.shape))
+        self.qm = ndist - 1
+        self.opp = OPP[ndist][:self.qm]
+
+    def rows(self, ids):
+        from .capi import box_rows
+        return box_rows(self.shape, self.periodic, ids)[0][:, :self.qm]
+
+    def sources(self, ids):
+        return self.rows(ids)[:, self.opp]
+
+    def centers(self, ids):
+        from .capi import box_rows
+        return box_rows(self.shape, self.periodic, ids, want_center=True)[1]
+
+
+@dataclass
+class LocalProblem:
+    rank: int
+    world: int
+    lo: int
+    hi: int
+    ghosts: np.ndarray                 # global ids of the ghost cells, ascending
+    nghbr: np.ndarray                  # [n_owned + n_ghost, stride] local ids
+    peers: list = field(default_factory=list)
+    send_count: list = field(default_factory=list)
+    recv_count: list = field(default_factory=list)
+    send_cell: np.ndarray = None       # local ids, concatenated in peer order
+    send_dir: np.ndarray = None
+    recv_cell: np.ndarray = None
+    recv_dir: np.ndarray = None
+
+    @property
+    def n_owned(self):
+        return self.hi - self.lo
+
+    @property
+    def n_ghost(self):
+        return len(self.ghosts)
+
+    def to_local(self, gids):
+        gids = np.asarray(gids, dtype=np.int64)
+        out = np.full(gids.shape, -1, dtype=np.int64)
+        own = (gids >= self.lo) & (gids < self.hi)
+        out[own] = gids[own] - self.lo
+        rest = ~own & (gids >= 0)
+        if rest.any() and len(self.ghosts):
+            pos = np.searchsorted(self.ghosts, gids[rest])
+            pos = np.minimum(pos, len(self.ghosts) - 1)
+            hit = self.ghosts[pos] == gids[rest]
+            out[rest] = np.where(hit, self.n_owned + pos, -1)
+        return out
+
+    def restrict(self, cells, normals):
+        """Boundary-condition entries of the cells this rank owns, order kept (application order is per cell)."""
+        cells = np.asarray(cells, dtype=np.int64)
+        m = (cells >= self.lo) & (cells < self.hi)
+        return cells[m] - self.lo, np.asarray(normals)[m]
+
+    def apply_halo(self, solver):
+        solver.set_ghosts(self.n_ghost)
+        solver.set_halo(self.peers, self.send_count, self.send_cell, self.send_dir, self.recv_count, self.recv_cell, self.recv_dir)
+
+
+def plan_rank(provider, rank, world, stride):
+    n, qm = provider.n, provider.qm
+    b = bounds(n, world)
+    lo, hi = int(b[rank]), int(b[rank + 1])
+    own = np.arange(lo, hi, dtype=np.int64)
+    rows_own = provider.rows(own)
+    src_own = provider.sources(own)
+
+    def outside(a):
+        a = a[a >= 0]
+        return a[(a < lo) | (a >= hi)]
+
+    ghosts = np.unique(np.concatenate([outside(rows_own.ravel()), outside(src_own.ravel())]))
+    lp = LocalProblem(rank=rank, world=world, lo=lo, hi=hi, ghosts=ghosts, nghbr=None)
+    n_local = (hi - lo) + len(ghosts)
+    table = np.full((n_local, stride), -1, dtype=np.int64)
+    table[:hi - lo, :qm] = lp.to_local(rows_own)
+    if len(ghosts):
+        rows_g = provider.rows(ghosts)
+        into_me = (rows_g >= lo) & (rows_g < hi)
+        table[hi - lo:, :qm] = np.where(into_me, rows_g - lo, -1)
+    lp.nghbr = table
+    owner_of = lambda g: np.searchsorted(b, g, side="right") - 1
+    # send: my cell s pushes (direction j) into a cell another rank owns
+    s_idx, s_dir = np.nonzero((rows_own >= 0) & ((rows_own < lo) | (rows_own >= hi)))
+    s_owner = owner_of(rows_own[s_idx, s_dir])
+    # receive: a ghost pushes (direction j) into a cell I own
+    if len(ghosts):
+        g_idx, g_dir = np.nonzero(table[hi - lo:, :qm] >= 0)
+        g_owner = owner_of(ghosts[g_idx])
+    else:
+        g_idx = g_dir = g_owner = np.zeros(0, dtype=np.int64)
+    peers = sorted(set(s_owner.tolist()) | set(g_owner.tolist()))
+    sc, sd, rc, rd = [], [], [], []
+    for q in peers:
+        m = s_owner == q
+        sc.append(s_idx[m])
+        sd.append(s_dir[m])
+        lp.send_count.append(int(m.sum()))
+        m = g_owner == q
+        rc.append(g_idx[m] + (hi - lo))
+        rd.append(g_dir[m])
+        lp.recv_count.append(int(m.sum()))
+    cat = lambda parts, dt: np.concatenate(parts).astype(dt) if parts else np.zeros(0, dt)
+    lp.peers = [int(q) for q in peers]
+    lp.send_cell, lp.send_dir = cat(sc, np.int64), cat(sd, np.int32)
+    lp.recv_cell, lp.recv_dir = cat(rc, np.int64), cat(rd, np.int32)
+    return lp

@@ -606,6 +606,23 @@ void orc_step(Orc* o, int64_t nsteps) {
   }
 }
 
+/* The same step cut in two, so that a test can emulate a domain-decomposed run: everything before the propagation
+ * (which produces m_f), then -- after the test has copied the m_f entries that cross a partition cut into its ghost
+ * cells -- the propagation and the boundary conditions. */
+void orc_step_collide(Orc* o) {
+  memcpy(o->varsold, o->vars, sizeof(double) * (size_t)o->n * (size_t)o->nvar);
+  pass_moments(o);
+  pass_equilibrium(o);
+  pass_collision(o);
+  pass_forcing(o);
+  pass_pre_apply(o);
+}
+void orc_step_stream(Orc* o) {
+  pass_propagation(o);
+  pass_apply(o);
+  ++o->step;
+}
+
 /* solver.cpp:336 -- output() recomputes the moments of the current fold */
 void orc_update_moments(Orc* o) { pass_moments(o); }
 

@@ -43,6 +43,8 @@ def lib():
         L.orc_init.argtypes = [vp]
         L.orc_step.argtypes = [vp, i64]
         L.orc_update_moments.argtypes = [vp]
+        L.orc_step_collide.argtypes = [vp]
+        L.orc_step_stream.argtypes = [vp]
         L.orc_residual.argtypes = [vp, pdbl]
         L.orc_residual.restype = i32
         for name in ("orc_f", "orc_fold", "orc_feq", "orc_vars", "orc_varsold"):
@@ -118,6 +120,12 @@ class Oracle:
 
     def step(self, n=1):
         lib().orc_step(self._h, int(n))
+
+    def step_collide(self):
+        lib().orc_step_collide(self._h)
+
+    def step_stream(self):
+        lib().orc_step_stream(self._h)
 
     def update_moments(self):
         lib().orc_update_moments(self._h)
