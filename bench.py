@@ -23,6 +23,11 @@ import sys
 import tempfile
 import time
 
+# torchrun exports OMP_NUM_THREADS=1; the host-side set-up (table generation, device plan) is OpenMP code, so give every
+# rank its share of the host cores before any OpenMP runtime is loaded
+if os.environ.get("OMP_NUM_THREADS", "1") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -296,6 +301,12 @@ def run_ours(args):
                "region": f"lbm_b200_set_populations(pinned m_f, m_fold) + {k} x lbm_b200_step + lbm_b200_get_moments(pinned)",
                "finite": bool(torch.isfinite(mom_host[:n]).all())}
 
+    if world > 1:
+        # orderly teardown: every rank destroys its NCCL communicator and leaves the process group together
+        barrier()
+        s.close()
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = measured_peak()
@@ -321,8 +332,6 @@ def run_ours(args):
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():

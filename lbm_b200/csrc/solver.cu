@@ -452,8 +452,8 @@ struct Solver final : SolverBase {
 
   int gather_all(Real* fold_out, Real* mom_out) {
     lbm::DevParams<Real> p = params(cur, cur ^ 1, nullptr);
-    const int32_t nc = static_cast<int32_t>(plan.npad);
-    // padding cells of the generic range carry VALUE(0) codes and read zeros; chunk ranges have no padding
+    // owned cells only: ghost cells have no links of their own (their populations arrive by halo exchange)
+    const int32_t nc = static_cast<int32_t>(plan.ghost_begin);
     const int nb = (nc + 127) / 128;
     if(prev_fold.p != nullptr) {
       p.A = prev_fold.p;

@@ -136,6 +136,9 @@ def main():
         mine_f, mine_fold = s.f[:lp.n_owned], s.fold[:lp.n_owned]
         st = s.stats()
         assert st["cells_ghost"] == lp.n_ghost and (world == 1 or st["halo_bytes"] > 0)
+        torch.cuda.synchronize()
+        dist.barrier()
+        s.close()
     ok = np.array_equal(mine_f, ref.f[lp.lo:lp.hi]) and np.array_equal(mine_fold, ref.fold[lp.lo:lp.hi])
     flags = [None] * world
     dist.all_gather_object(flags, bool(ok))
