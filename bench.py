@@ -28,7 +28,16 @@ import time
 if os.environ.get("OMP_NUM_THREADS", "1") == "1":
     os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
 
+# stdout carries exactly ONE JSON line: everything libraries print (NCCL banner, torchrun notes) goes to stderr
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
 import numpy as np
+
+
+def emit(line):
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -208,7 +217,7 @@ def run_reference(args):
                                    f"{args.steps} steps; the reference binary cannot run D3Q19 (SURVEY section 0)"},
         "e2e": {"value": mlups, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_dict(args, note):
@@ -331,7 +340,7 @@ def run_ours(args):
         "config": config_dict(args, f"{st0['cells_fast']} of {st0['ncells']} cells on the index-free chunk path; setup {t_setup:.1f} s"),
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():

@@ -59,7 +59,8 @@ struct DevParams {
   int64_t     stride;
   // fast chunks
   const uint16_t* tmpl;     // [(Q-1)][CHUNK]
-  const int32_t*  chunk_nb; // [n_fast_chunks][NSEL]
+  const int32_t*  chunk_nb; // [n_fast_chunks][NSEL + 1]: neighbour chunk bases (-1 = wall), wall descriptor id
+  const AddEntryT<Real>* wall_desc; // [n_wall_desc][Q-1] bounce-back addends of wall chunks
   int32_t         n_fast_chunks;
   int32_t         n_fast_blocks;
   // generic range
@@ -319,22 +320,48 @@ __device__ __forceinline__ void gather_generic(const DevParams<Real>& p, const R
 }
 
 // m_fold of a cell of a fast chunk, template taken from global memory (used by the small auxiliary kernels)
-template <class L, class Real>
+// one slot of a fast chunk: pull at the template offset, or bounce back (+ addends) when the neighbour chunk is a wall
+template <class L, class Real, bool STRICT, int J>
+__device__ __forceinline__ Real fast_slot(const DevParams<Real>& p, const Real* __restrict__ Abuf, int32_t cell, int32_t nbv, uint32_t off,
+                                          const AddEntryT<Real>* __restrict__ wall) {
+  using A = Ar<Real, STRICT>;
+  if(nbv >= 0) return Abuf[static_cast<size_t>(J) * p.stride + nbv + static_cast<int32_t>(off)];
+  Real v = Abuf[static_cast<size_t>(L::opp(J)) * p.stride + cell]; // bnd_dirichlet.h:92
+  const int n = wall[J].n;
+  for(int t = 0; t < n; ++t) v = A::add(v, wall[J].v[t]);            // bnd_dirichlet.h:111-117
+  return v;
+}
+
+template <class L, class Real, bool STRICT, int J>
+__device__ __forceinline__ void gather_fast_global_rec(const DevParams<Real>& p, const Real* __restrict__ Abuf, int32_t cell, int chunk, int o,
+                                                       const AddEntryT<Real>* __restrict__ wall, Real (&fold)[L::Q]) {
+  if constexpr(J < L::Q - 1) {
+    const uint32_t t   = p.tmpl[J * L::CHUNK + o];
+    const int32_t  nbv = p.chunk_nb[static_cast<size_t>(chunk) * (L::NSEL + 1) + (t >> 10)];
+    fold[J]            = fast_slot<L, Real, STRICT, J>(p, Abuf, cell, nbv, t & 1023u, wall);
+    gather_fast_global_rec<L, Real, STRICT, J + 1>(p, Abuf, cell, chunk, o, wall, fold);
+  }
+}
+
+// m_fold of a cell of a fast chunk, template taken from global memory (used by the small auxiliary kernels)
+template <class L, class Real, bool STRICT>
 __device__ __forceinline__ void gather_fast_global(const DevParams<Real>& p, const Real* __restrict__ Abuf, int32_t cell, Real (&fold)[L::Q]) {
   constexpr int Q = L::Q, CH = L::CHUNK;
-  const int chunk = cell / CH, o = cell % CH;
+  if(p.first) {
 #pragma unroll
-  for(int j = 0; j < Q - 1; ++j) {
-    const uint32_t t   = p.tmpl[j * CH + o];
-    const int32_t  src = p.first ? cell : p.chunk_nb[static_cast<size_t>(chunk) * L::NSEL + (t >> 10)] + static_cast<int32_t>(t & 1023u);
-    fold[j]            = Abuf[static_cast<size_t>(j) * p.stride + src];
+    for(int j = 0; j < Q; ++j) fold[j] = Abuf[static_cast<size_t>(j) * p.stride + cell];
+    return;
   }
+  const int chunk = cell / CH, o = cell % CH;
+  const int32_t wid = p.chunk_nb[static_cast<size_t>(chunk) * (L::NSEL + 1) + L::NSEL];
+  const AddEntryT<Real>* wall = p.wall_desc + static_cast<size_t>(wid < 0 ? 0 : wid) * (Q - 1);
+  gather_fast_global_rec<L, Real, STRICT, 0>(p, Abuf, cell, chunk, o, wall, fold);
   fold[Q - 1] = Abuf[static_cast<size_t>(Q - 1) * p.stride + cell];
 }
 
 template <class L, class Real, bool STRICT>
 __device__ __forceinline__ void gather_any(const DevParams<Real>& p, const Real* __restrict__ Abuf, int32_t cell, Real (&fold)[L::Q]) {
-  if(cell < p.gen_begin) gather_fast_global<L, Real>(p, Abuf, cell, fold);
+  if(cell < p.gen_begin) gather_fast_global<L, Real, STRICT>(p, Abuf, cell, fold);
   else gather_generic<L, Real, STRICT>(p, Abuf, cell, fold);
 }
 
@@ -364,11 +391,22 @@ __device__ __forceinline__ void update_and_store(const DevParams<Real>& p, int32
 #endif
 constexpr int kThreads = LBM_THREADS;
 
+template <class L, class Real, bool STRICT, int J>
+__device__ __forceinline__ void fast_wall_gather(const DevParams<Real>& p, const Real* __restrict__ Abuf, int32_t cell, int o,
+                                                 const uint16_t* __restrict__ s_tmpl, const int32_t* __restrict__ nb,
+                                                 const AddEntryT<Real>* __restrict__ wall, Real (&fold)[L::Q]) {
+  if constexpr(J < L::Q - 1) {
+    const uint32_t t = s_tmpl[J * L::CHUNK + o];
+    fold[J]          = fast_slot<L, Real, STRICT, J>(p, Abuf, cell, nb[t >> 10], t & 1023u, wall);
+    fast_wall_gather<L, Real, STRICT, J + 1>(p, Abuf, cell, o, s_tmpl, nb, wall, fold);
+  }
+}
+
 template <class L, class Real, bool STRICT, int COLL>
 __global__ void __launch_bounds__(kThreads, LBM_MINBLOCKS) k_step(const __grid_constant__ DevParams<Real> p) {
   constexpr int Q = L::Q, QM = Q - 1, CH = L::CHUNK, NSEL = L::NSEL;
   __shared__ uint16_t s_tmpl[QM * CH];
-  __shared__ int32_t  s_nb[2][NSEL];
+  __shared__ int32_t  s_nb[2][NSEL + 1];
   const Real* __restrict__ Abuf = p.A;
 
   if(static_cast<int>(blockIdx.x) < p.n_gen_blocks) {
@@ -390,9 +428,11 @@ __global__ void __launch_bounds__(kThreads, LBM_MINBLOCKS) k_step(const __grid_c
     // neighbour-chunk bases are double buffered: one barrier per chunk is enough (a thread can run at most one
     // chunk ahead of the slowest one, and then it writes the other buffer)
     buf ^= 1;
-    if(threadIdx.x < NSEL) s_nb[buf][threadIdx.x] = p.chunk_nb[static_cast<size_t>(chunk) * NSEL + threadIdx.x];
+    if(threadIdx.x < NSEL + 1) s_nb[buf][threadIdx.x] = p.chunk_nb[static_cast<size_t>(chunk) * (NSEL + 1) + threadIdx.x];
     __syncthreads();
     const int32_t* nb  = s_nb[buf];
+    const int32_t  wid = nb[NSEL]; // wall descriptor of this chunk, -1: interior chunk
+    const AddEntryT<Real>* wall = p.wall_desc + static_cast<size_t>(wid < 0 ? 0 : wid) * QM;
     const int32_t base = chunk * CH;
 #pragma unroll 1
     for(int o = threadIdx.x; o < CH; o += kThreads) {
@@ -401,13 +441,18 @@ __global__ void __launch_bounds__(kThreads, LBM_MINBLOCKS) k_step(const __grid_c
       if(p.first) {
 #pragma unroll
         for(int j = 0; j < Q; ++j) fold[j] = Abuf[static_cast<size_t>(j) * p.stride + cell];
-      } else {
+      } else if(wid < 0) {
+        // interior chunk: pure pulls
 #pragma unroll
         for(int j = 0; j < QM; ++j) {
           const uint32_t t   = s_tmpl[j * CH + o];
           const int32_t  src = nb[t >> 10] + static_cast<int32_t>(t & 1023u);
           fold[j]            = Abuf[static_cast<size_t>(j) * p.stride + src];
         }
+        fold[QM] = Abuf[static_cast<size_t>(QM) * p.stride + cell];
+      } else {
+        // wall chunk: slots whose neighbour chunk is a wall bounce back
+        fast_wall_gather<L, Real, STRICT, 0>(p, Abuf, cell, o, s_tmpl, nb, wall, fold);
         fold[QM] = Abuf[static_cast<size_t>(QM) * p.stride + cell];
       }
       update_and_store<L, Real, STRICT, COLL>(p, cell, fold);

@@ -85,7 +85,8 @@ struct Plan {
   int64_t   gen_stride = 0;
   std::vector<int32_t>  ref2dev, dev2ref;
   std::vector<uint16_t> tmpl;       // (Q-1) * CH : sel << 10 | off
-  std::vector<int32_t>  chunk_nb;   // n_fast_chunks * NSEL device bases
+  std::vector<int32_t>  chunk_nb;   // n_fast_chunks * (NSEL + 1): device bases (-1: wall selector), then the wall descriptor id
+  std::vector<AddEntry> wall_desc;  // per wall descriptor: Q-1 addend entries (bounce-back slots of wall chunks)
   std::vector<int32_t>  codes;      // (Q-1) * gen_stride
   std::vector<CopySrc>  copytab;
   std::vector<AddEntry> addtab;
@@ -422,22 +423,53 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
     }
   }
   const int64_t nc = static_cast<int64_t>(cand_base.size());
-  // fast chunk: all cells plain, every cross-chunk pull lands in a candidate chunk at the template offset
+  // fast chunk: every slot is either a pull that lands in a candidate chunk at the template offset, or -- for all slots
+  // that would pull from one and the same (missing) neighbour chunk -- a bounce-back written by a wall boundary condition,
+  // with the same addends for every cell of the chunk in a given direction (no-slip wall, moving lid).  Wall chunks of a
+  // box therefore need no per-cell index either; chunks on edges where two different walls meet stay generic.
+  std::vector<char> odd(static_cast<size_t>(N), 0); // a BC overrides a slot that also has a push source (asymmetric tables)
+  for(const auto& kv : over) {
+    const int64_t c = kv.first / Q;
+    const int     j = static_cast<int>(kv.first % Q);
+    if(kv.second.kind != LK_BB && kv.second.kind != LK_BB_ADD) odd[c] = 1;
+    else if(j < QM && pull[static_cast<size_t>(c) * QM + j] >= 0) odd[c] = 1;
+  }
+  const int64_t WALL = -2;
   std::vector<char>    fast(static_cast<size_t>(nc), 0);
   std::vector<int64_t> nbref(static_cast<size_t>(nc) * L.NSEL, -1);
+  std::vector<int32_t> wall_of(static_cast<size_t>(nc), -1);      // wall descriptor per candidate chunk
+  std::vector<std::vector<AddEntry>> chunk_wall(static_cast<size_t>(nc));
 #pragma omp parallel for schedule(dynamic, 64)
   for(int64_t k = 0; k < nc; ++k) {
     const int64_t b = cand_base[k];
-    bool ok = true;
+    bool ok = true, has_wall = false;
     int64_t* nbk = &nbref[static_cast<size_t>(k) * L.NSEL];
     nbk[SELF] = b;
+    std::vector<AddEntry> wd(static_cast<size_t>(QM));
+    std::vector<char>     wd_set(static_cast<size_t>(QM), 0);
     for(int o = 0; o < CH && ok; ++o) {
-      if(!plain[b + o]) { ok = false; break; }
+      const int64_t c = b + o;
+      if(odd[c]) { ok = false; break; }
       for(int j = 0; j < QM; ++j) {
         const uint16_t t   = P.tmpl[static_cast<size_t>(j) * CH + o];
         const int      sel = t >> 10;
-        const int64_t  src = pull[static_cast<size_t>(b + o) * QM + j];
-        const int64_t  nb0 = src - (t & 1023);
+        const int64_t  src = pull[static_cast<size_t>(c) * QM + j];
+        if(src < 0) {
+          if(plain[c] || sel == SELF) { ok = false; break; }
+          auto it = over.find(key(c, j)); // read-only lookups: safe from several threads
+          if(it == over.end()) { ok = false; break; } // stale slot
+          AddEntry e{};
+          e.n = it->second.kind == LK_BB_ADD ? it->second.nadd : 0;
+          for(int d = 0; d < 3; ++d) e.v[d] = d < e.n ? it->second.add[d] : 0.0;
+          if(!wd_set[j]) { wd[j] = e; wd_set[j] = 1; }
+          else if(wd[j].n != e.n || std::memcmp(wd[j].v, e.v, sizeof(e.v)) != 0) { ok = false; break; }
+          if(nbk[sel] == -1) nbk[sel] = WALL;
+          else if(nbk[sel] != WALL) { ok = false; break; }
+          has_wall = true;
+          continue;
+        }
+        if(src >= NO) { ok = false; break; } // pull from a ghost cell
+        const int64_t nb0 = src - (t & 1023);
         if(nbk[sel] == -1) {
           if(nb0 < 0 || nb0 + CH > NO || chunk_of[nb0] < 0 || cand_base[chunk_of[nb0]] != nb0) { ok = false; break; }
           nbk[sel] = nb0;
@@ -445,6 +477,29 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
       }
     }
     fast[k] = ok ? 1 : 0;
+    if(ok && has_wall) {
+      for(int j = 0; j < QM; ++j) if(!wd_set[j]) { wd[j] = AddEntry{}; }
+      chunk_wall[k] = wd;
+    }
+  }
+  // deduplicate wall descriptors (a box has a handful)
+  for(int64_t k = 0; k < nc; ++k) {
+    if(!fast[k] || chunk_wall[k].empty()) continue;
+    int32_t id = -1;
+    for(size_t w = 0; w < P.wall_desc.size() / QM && id < 0; ++w) {
+      bool same = true;
+      for(int j = 0; j < QM && same; ++j) {
+        const AddEntry& a = P.wall_desc[w * QM + j];
+        const AddEntry& c2 = chunk_wall[k][j];
+        same = a.n == c2.n && std::memcmp(a.v, c2.v, sizeof(a.v)) == 0;
+      }
+      if(same) id = static_cast<int32_t>(w);
+    }
+    if(id < 0) {
+      id = static_cast<int32_t>(P.wall_desc.size() / QM);
+      P.wall_desc.insert(P.wall_desc.end(), chunk_wall[k].begin(), chunk_wall[k].end());
+    }
+    wall_of[k] = id;
   }
 
   // ---- 6. device layout: fast chunks, slow chunks (kept contiguous so fast chunks can address them by
@@ -467,7 +522,8 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
   P.dev2ref.assign(static_cast<size_t>(P.npad), -1);
   for(int64_t c = 0; c < N; ++c) P.dev2ref[P.ref2dev[c]] = static_cast<int32_t>(c);
 
-  P.chunk_nb.assign(static_cast<size_t>(P.n_fast_chunks) * L.NSEL, 0);
+  const int NBW = L.NSEL + 1;
+  P.chunk_nb.assign(static_cast<size_t>(P.n_fast_chunks) * NBW, 0);
   {
     int64_t f = 0;
     for(int64_t k = 0; k < nc; ++k) {
@@ -475,8 +531,12 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
       for(int s = 0; s < L.NSEL; ++s) {
         const int64_t r = nbref[static_cast<size_t>(k) * L.NSEL + s];
         // a selector no slot uses (e.g. cube corners for D3Q19) stays at the chunk itself
-        P.chunk_nb[static_cast<size_t>(f) * L.NSEL + s] = static_cast<int32_t>(r < 0 ? cand_dev[k] : cand_dev[chunk_of[r]]);
+        int32_t v = static_cast<int32_t>(cand_dev[k]);
+        if(r == WALL) v = -1;
+        else if(r >= 0) v = static_cast<int32_t>(cand_dev[chunk_of[r]]);
+        P.chunk_nb[static_cast<size_t>(f) * NBW + s] = v;
       }
+      P.chunk_nb[static_cast<size_t>(f) * NBW + L.NSEL] = wall_of[k];
       ++f;
     }
   }

@@ -89,6 +89,7 @@ struct Solver final : SolverBase {
   DevBuf<Real>     scratch;   // [max(Q,NVAR)][npad] read-back staging
   DevBuf<uint16_t> d_tmpl;
   DevBuf<int32_t>  d_chunk_nb, d_codes;
+  DevBuf<lbm::AddEntryT<Real>> d_wall;
   DevBuf<lbm::CopySrcDev>       d_copy;
   DevBuf<lbm::AddEntryT<Real>>  d_add;
   DevBuf<lbm::AbbDev<Real>>     d_abb;
@@ -126,6 +127,7 @@ struct Solver final : SolverBase {
     p.stride = plan.npad;
     p.tmpl = d_tmpl.p;
     p.chunk_nb = d_chunk_nb.p;
+    p.wall_desc = d_wall.p;
     p.n_fast_chunks = static_cast<int32_t>(plan.n_fast_chunks);
     p.n_fast_blocks = n_fast_blocks;
     p.gen_begin = static_cast<int32_t>(plan.gen_begin);
@@ -203,6 +205,17 @@ struct Solver final : SolverBase {
         h.push_back(e);
       }
       CUDA_TRY(d_add.upload(h));
+    }
+    {
+      std::vector<lbm::AddEntryT<Real>> h;
+      for(auto& a : plan.wall_desc) {
+        lbm::AddEntryT<Real> e{};
+        for(int d = 0; d < 3; ++d) e.v[d] = static_cast<Real>(a.v[d]);
+        e.n = a.n;
+        h.push_back(e);
+      }
+      if(h.empty()) h.resize(Q - 1); // so that the pointer arithmetic in the kernel always has a valid base
+      CUDA_TRY(d_wall.upload(h));
     }
     {
       std::vector<lbm::AbbDev<Real>> h;
