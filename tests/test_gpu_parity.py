@@ -115,7 +115,8 @@ def test_strict_fp64_boxes_fast_chunks(shape, ndist, periodic, lid, oracle_mod):
     side = 8 if len(shape) == 3 else 32
     interior = [s // side - (0 if p else 2) for s, p in zip(shape, periodic)]
     if all(s % side == 0 for s in shape) and min(interior) > 0:
-        assert st["cells_fast"] == int(np.prod(interior)) * side ** len(shape), "template-indexed chunk path not taken"
+        # interior chunks always qualify; chunks on a single wall qualify too (bounce-back selectors)
+        assert st["cells_fast"] >= int(np.prod(interior)) * side ** len(shape), "template-indexed chunk path not taken"
 
 
 @pytest.mark.parametrize("collision", [lbm_b200.TRT, lbm_b200.MRT])
