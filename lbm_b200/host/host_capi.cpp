@@ -1,0 +1,104 @@
+// host_capi.cpp -- C entry points over the host-side mirror (grid pipeline + LBMSolver) for tests and embedding.
+#include <cstring>
+#include <string>
+
+#include "lbm_solver.hpp"
+
+using namespace lbmhost;
+
+namespace {
+void set_err(char* err, int n, const std::string& msg) {
+  if(err != nullptr && n > 0) {
+    std::strncpy(err, msg.c_str(), static_cast<size_t>(n - 1));
+    err[n - 1] = 0;
+  }
+}
+struct GridHandle {
+  GridGenerator gen;
+  LBMSolver     solver;
+};
+} // namespace
+
+extern "C" {
+
+// gridder run + transferGrid: the tables the LBM solver would stream through (no GPU needed)
+void* lbmhost_grid_build(const char* config_path, char* err, int errlen) {
+  auto* h = new GridHandle();
+  try {
+    h->gen.init(0, nullptr, config_path);
+    h->gen.run();
+    h->solver.init(0, nullptr, config_path);
+    h->solver.transferGrid(h->gen.grid());
+    h->solver.markBoundaryProperties(); // state after loadConfiguration(), which is where the reference's dump was taken
+  } catch(const std::exception& e) {
+    set_err(err, errlen, e.what());
+    delete h;
+    return nullptr;
+  }
+  return h;
+}
+void lbmhost_grid_free(void* h) { delete static_cast<GridHandle*>(h); }
+int64_t lbmhost_grid_ncells(void* h) { return static_cast<GridHandle*>(h)->solver.solverGrid().n; }
+int lbmhost_grid_ndim(void* h) { return static_cast<GridHandle*>(h)->solver.solverGrid().ndim; }
+int lbmhost_grid_stride(void* h) { return static_cast<GridHandle*>(h)->solver.solverGrid().nn_diag; }
+double lbmhost_grid_cell_length(void* h) { return static_cast<GridHandle*>(h)->solver.solverGrid().cell_length; }
+void lbmhost_grid_copy(void* h, int64_t* nghbr, double* center, uint16_t* props) {
+  const SolverGrid& g = static_cast<GridHandle*>(h)->solver.solverGrid();
+  if(nghbr) std::memcpy(nghbr, g.nghbr.data(), g.nghbr.size() * sizeof(int64_t));
+  if(center) std::memcpy(center, g.center.data(), g.center.size() * sizeof(double));
+  if(props) std::memcpy(props, g.props.data(), g.props.size() * sizeof(uint16_t));
+}
+int lbmhost_grid_nsurfaces(void* h) { return static_cast<int>(static_cast<GridHandle*>(h)->solver.solverGrid().surfaces.size()); }
+const char* lbmhost_grid_surface_name(void* h, int k) { return static_cast<GridHandle*>(h)->solver.solverGrid().surfaces[k].name.c_str(); }
+int64_t lbmhost_grid_surface_size(void* h, int k) {
+  return static_cast<int64_t>(static_cast<GridHandle*>(h)->solver.solverGrid().surfaces[k].cells.size());
+}
+void lbmhost_grid_surface_copy(void* h, int k, int64_t* cells, double* normals) {
+  const SolverGrid& g = static_cast<GridHandle*>(h)->solver.solverGrid();
+  const Surface&    s = g.surfaces[k];
+  for(size_t i = 0; i < s.cells.size(); ++i) {
+    cells[i] = s.cells[i];
+    for(int d = 0; d < g.ndim; ++d) normals[i * g.ndim + d] = s.normal.at(s.cells[i])[d];
+  }
+}
+
+// full pipeline like main(): gridder -> transferGrid -> LBMSolver::run. Returns 0 or the TERMM code.
+// out[0..5] = max error, L2 error, global relative error, steps run, converged flag, last residual; vars (optional) = n*NVAR
+int lbmhost_run(const char* config_path, double* out, double* vars, int64_t nvars, char* err, int errlen) {
+  try {
+    GridGenerator gen;
+    gen.init(0, nullptr, config_path);
+    gen.run();
+    LBMSolver solver;
+    solver.init(0, nullptr, config_path);
+    solver.transferGrid(gen.grid());
+    int rc = 0;
+    try {
+      rc = static_cast<int>(solver.run());
+    } catch(const TermError& e) {
+      set_err(err, errlen, e.what());
+      rc = e.code;
+    }
+    if(out != nullptr) {
+      out[0] = solver.maxError;
+      out[1] = solver.l2Error;
+      out[2] = solver.gre;
+      out[3] = static_cast<double>(solver.stepsRun);
+      out[4] = solver.converged ? 1.0 : 0.0;
+      out[5] = solver.lastResidual;
+    }
+    if(vars != nullptr) {
+      const int64_t n = std::min<int64_t>(nvars, static_cast<int64_t>(solver.vars.size()));
+      std::memcpy(vars, solver.vars.data(), static_cast<size_t>(n) * sizeof(double));
+    }
+    return rc;
+  } catch(const TermError& e) {
+    set_err(err, errlen, e.what());
+    return e.code;
+  } catch(const std::exception& e) {
+    set_err(err, errlen, e.what());
+    return -1;
+  }
+}
+
+} // extern "C"

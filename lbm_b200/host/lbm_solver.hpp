@@ -1,0 +1,452 @@
+// lbm_solver.hpp -- host-side mirror of the reference's solver interface, driving the CUDA core through the C ABI.
+//
+// Same names, argument meaning and error behaviour as the reference:
+//   Runnable        /root/reference/src/interface/solver_interface.h:6-24  (init / initBenchmark / run / grid / transferGrid)
+//   GridGenerator   /root/reference/src/gridgenerator/gridGenerator.cpp:72-229 (configuration keys :124-143,240-281)
+//   LBMSolver       /root/reference/src/lbm/solver.cpp: loadConfiguration :71-163, run :176-214, writeInfo :217-230,
+//                   convergenceCondition :233-263, output :323-384, compareToAnalyticalResult :388-482
+//   boundary set-up /root/reference/src/lbm/bnd/bnd.h:71-142 (lexicographic order, empty surfaces skipped, dummies)
+// The time step itself, the boundary kernels, forcing and the residual run on the GPU (include/lbm_b200.h); there is no CPU
+// path here.  TERMM(code, msg) of the reference (src/common/term.h:37) becomes a TermError that main() turns into the same
+// stderr text and exit status.
+#pragma once
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <functional>
+#include <iomanip>
+#include <iostream>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+#include "../../include/lbm_b200.h"
+#include "grid.hpp"
+#include "json.hpp"
+
+namespace lbmhost {
+
+struct TermError : std::runtime_error {
+  int code;
+  TermError(int c, const std::string& where, const std::string& msg) : std::runtime_error("Error in " + where + ": " + msg), code(c) {}
+};
+#define LBMHOST_STR2(x) #x
+#define LBMHOST_STR(x) LBMHOST_STR2(x)
+#define TERMM(code, msg) throw ::lbmhost::TermError((code), std::string(__FILE__ ":" LBMHOST_STR(__LINE__)), (msg))
+
+class GridInterface {
+ public:
+  virtual ~GridInterface()       = default;
+  virtual int     dim() const     = 0;
+  virtual int64_t noCells() const = 0;
+  virtual int     maxLvl() const  = 0;
+};
+
+class Runnable {
+ public:
+  virtual ~Runnable() = default;
+  virtual void                 init(int argc, char** argv, std::string config_file) = 0;
+  virtual void                 initBenchmark(int argc, char** argv)                 = 0;
+  virtual int64_t              run()                                                = 0;
+  virtual const GridInterface& grid() const                                         = 0;
+  virtual void                 transferGrid(const GridInterface& grid)              = 0;
+};
+
+class GeneratedGrid final : public GridInterface {
+ public:
+  GridGen gen;
+  int     dim() const override { return gen.ndim; }
+  int64_t noCells() const override { return static_cast<int64_t>(gen.cells.size()); }
+  int     maxLvl() const override { return gen.level; }
+};
+
+class GridGenerator final : public Runnable {
+ public:
+  void init(int /*argc*/, char** /*argv*/, std::string config_file) override {
+    m_config = Json::parse_file(config_file);
+    std::cout << "Grid generator started ||>" << std::endl;
+  }
+  void initBenchmark(int /*argc*/, char** /*argv*/) override {
+    // gridGenerator.cpp:43-54: 3D, uniform level 5, default cube geometry
+    m_config = Json::parse(R"({"dim":3,"partitionLevel":5,"uniformLevel":5,"maxNoCells":100000,
+      "geometry":{"cube":{"type":"box","A":[0.0,0.0,0.0],"B":[1.0,1.0,1.0]}}})");
+  }
+  int64_t run() override {
+    m_grid.gen.configure(m_config);
+    m_grid.gen.generate();
+    std::cout << "    * grid has " << m_grid.noCells() << " cells" << std::endl;
+    const long long maxc = m_config.opt_int("maxNoCells", -1);
+    if(maxc >= 0 && m_grid.noCells() > maxc) TERMM(-1, "Out of memory!"); // cartesiangrid_generation.h:336
+    return 0;
+  }
+  const GridInterface& grid() const override { return m_grid; }
+  void transferGrid(const GridInterface&) override { TERMM(-1, "Not implemented!"); }
+  const Json& config() const { return m_config; }
+
+ private:
+  Json          m_config;
+  GeneratedGrid m_grid;
+};
+
+class LBMGrid final : public GridInterface {
+ public:
+  SolverGrid g;
+  int     dim() const override { return g.ndim; }
+  int64_t noCells() const override { return g.n; }
+  int     maxLvl() const override { return g.max_level; }
+};
+
+class LBMSolver final : public Runnable {
+ public:
+  ~LBMSolver() override {
+    if(m_gpu != nullptr) lbm_b200_destroy(m_gpu);
+  }
+
+  void init(int /*argc*/, char** /*argv*/, std::string config_file) override {
+    m_configFile = config_file;
+    const Json all = Json::parse_file(config_file);
+    if(!all.has("solver")) TERMM(-1, "The required configuration value is missing: solver");
+    m_cfg = all.at("solver");
+    // solverExe.h:19-93
+    m_model = m_cfg.opt_str("model", "D2Q9");
+    const std::string eq = m_cfg.opt_str("equation", "navierstokes");
+    if(eq != "navierstokes") TERMM(-1, "Only the Navier-Stokes equation type runs on this host (poisson: SURVEY.md section 8f N4)");
+    if(m_model == "D2Q9") { m_ndim = 2; m_ndist = 9; }
+    else if(m_model == "D3Q19") { m_ndim = 3; m_ndist = 19; }
+    else if(m_model == "D3Q27") { m_ndim = 3; m_ndist = 27; }
+    else if(m_model == "D1Q3" || m_model == "D2Q5") TERMM(-1, "Unsupported model");
+    else TERMM(-1, "Invalid model configuration!");
+    std::cout << m_ndim << "D LBM Solver started ||>" << std::endl;
+  }
+
+  void initBenchmark(int /*argc*/, char** /*argv*/) override {
+    // the reference: TERMM(-1, "Not implemented!") (solver.cpp:39-46). Here: the synthetic cube of SURVEY.md section 8d S3.
+    m_benchmark = true;
+    m_ndim = 3; m_ndist = 19; m_model = "D3Q19";
+  }
+
+  void transferGrid(const GridInterface& grid) override {
+    std::cerr << "Transferring " << m_ndim << "D Grid to LBM solver" << std::endl;
+    if(grid.dim() != m_ndim) TERMM(-1, "Invalid configuration the grid dimensionality is not matching!");
+    const auto* gen = dynamic_cast<const GeneratedGrid*>(&grid);
+    if(gen == nullptr) TERMM(-1, "transferGrid expects the generator's grid");
+    try {
+      m_grid.g.load(gen->gen, m_cfg);
+    } catch(const std::runtime_error& e) {
+      TERMM(-1, e.what());
+    }
+  }
+
+  const GridInterface& grid() const override { return m_grid; }
+  const SolverGrid& solverGrid() const { return m_grid.g; }
+
+  // LBMBndManager::addPeriodicBndry marks the cells of both surfaces of a periodic boundary CONDITION as periodic
+  // (src/lbm/bnd/bnd.h:217-221, CellProperties::periodic = bit 0); dummies (generateBndry:false) are left alone
+  void markBoundaryProperties() {
+    SolverGrid& g = m_grid.g;
+    for(const auto& gk : m_cfg.at("boundary").obj) {
+      const size_t nkeys = gk.second.size();
+      for(const auto& sk : gk.second.obj) {
+        const Json& bc = sk.second;
+        if(bc.opt_str("type", "") != "periodic" || !bc.opt_bool("generateBndry", true)) continue;
+        const Surface* a = g.find(nkeys > 1 ? gk.first + "_" + sk.first : gk.first);
+        const Surface* b = g.find(bc.at("connection").as_string());
+        if(a == nullptr || a->cells.empty() || b == nullptr) continue;
+        for(int64_t c : a->cells) g.props[c] |= 1u;
+        for(int64_t c : b->cells) g.props[c] |= 1u;
+      }
+    }
+  }
+
+  // results for callers that embed the solver (tests): macroscopic fields of the last output(), errors of the analytic check
+  std::vector<double> vars;
+  double  maxError = NAN, l2Error = NAN, gre = NAN;
+  int64_t stepsRun = 0;
+  bool    converged = false;
+  double  lastResidual = NAN;
+
+  int64_t run() override {
+    loadConfiguration();
+    setupGpu();
+    using clk = std::chrono::steady_clock;
+    auto    lastInfo = clk::now();
+    int64_t lastStep = 0;
+    const int NVAR = m_ndim + 1;
+    vars.assign(static_cast<size_t>(m_grid.g.n) * NVAR, 0.0);
+    for(m_timeStep = 0; m_timeStep < m_maxTimeStep && !converged; ++m_timeStep) {
+      // writeInfo, solver.cpp:217-230
+      if(m_timeStep > 0 && m_timeStep % m_infoInterval == 0) {
+        const double dt = std::chrono::duration<double>(clk::now() - lastInfo).count();
+        std::cerr << m_timeStep << "/" << m_maxTimeStep << " " << (m_timeStep - lastStep) / dt << "it/s \n";
+        lastInfo = clk::now();
+        lastStep = m_timeStep;
+      }
+      converged = convergenceCondition();
+      call(lbm_b200_step(m_gpu, 1));
+      output(m_timeStep == m_maxTimeStep - 1 || converged);
+    }
+    stepsRun = m_timeStep;
+    if(m_diverged) TERMM(-1, "Solution diverged");
+    if(m_cfg.has("analyticalSolution")) compareToAnalyticalResult();
+    std::cout << "LBM Solver finished <||" << std::endl;
+    return 0;
+  }
+
+ private:
+  void call(int rc) {
+    if(rc != 0) TERMM(-1, std::string("lbm_b200: ") + lbm_b200_last_error());
+  }
+
+  // solver.cpp:71-163
+  void loadConfiguration() {
+    const std::string method = m_cfg.opt_str("method", "bgk");
+    if(method == "bgk") m_collision = LBM_B200_BGK;
+    else if(method == "trt") m_collision = LBM_B200_TRT;   // extension
+    else if(method == "mrt") m_collision = LBM_B200_MRT;   // extension
+    else TERMM(-1, "Invalid equation configuration!");     // constants.h:75
+    m_infoInterval = m_cfg.opt_int("info_interval", 10);
+    m_convInterval = m_cfg.opt_int("conv_interval", m_infoInterval);
+    if(!m_cfg.has("maxSteps")) TERMM(-1, "The required configuration value is missing: maxSteps");
+    m_maxTimeStep = m_cfg.at("maxSteps").as_int();
+    m_outputDir   = m_cfg.opt_str("output_dir", "out/");
+    m_solutionInterval = m_cfg.opt_int("solution_interval", 100);
+    m_solutionName     = m_cfg.opt_str("solution_filename", "solution");
+    if(m_outputDir.empty()) TERMM(-1, "Invalid output directory set! (value: " + m_outputDir + ")");
+    if(m_outputDir.back() != '/') m_outputDir += '/';
+    m_refLength = m_cfg.opt("refLength", 1.0);
+    if(m_cfg.has("reynoldsnumber") && m_cfg.has("relaxation")) TERMM(-1, "Only set either reynoldsnumber or relaxation");
+    if(!m_cfg.has("ma")) TERMM(-1, "The required configuration value is missing: ma");
+    m_ma = m_cfg.at("ma").as_double();
+    if(m_cfg.has("relaxation")) {
+      m_relaxTime = m_cfg.at("relaxation").as_double();
+      m_omega     = 1.0 / m_relaxTime;
+      m_nu        = (2 * m_relaxTime - 1) / 6.0;
+      m_re        = m_ma * m_refLength / m_nu;
+    } else {
+      if(!m_cfg.has("reynoldsnumber")) TERMM(-1, "The required configuration value is missing: reynoldsnumber");
+      m_re        = m_cfg.at("reynoldsnumber").as_double();
+      m_nu        = m_ma / m_re * m_refLength;
+      m_omega     = 2.0 / (1.0 + 2.0 * m_nu * std::pow(2.0, m_grid.g.max_level)); // solver.cpp:119
+      m_relaxTime = 1.0 / m_omega;
+    }
+    std::cerr << "<<<<<<<<<<<<>>>>>>>>>>>>>\nLBM Type " << method << "\nLBM Model " << m_model << "\nNo. of variables " << m_ndim + 1
+              << "\nNo. Leaf cells: " << m_grid.g.n_leaf << "\nMax Mesh Level: " << m_grid.g.max_level << "\nNo. Bnd cells: " << m_grid.g.n_bnd
+              << "\nRelaxation Time: " << m_relaxTime << "\nOmega: " << m_omega << "\nReynolds Number: " << m_re << "\nViscosity: " << m_nu
+              << "\n+++++++++++++++++++++++++" << std::endl;
+  }
+
+  void setupGpu() {
+    markBoundaryProperties();
+    const SolverGrid& g = m_grid.g;
+    lbm_b200_config cfg;
+    lbm_b200_default_config(&cfg);
+    cfg.ndim = m_ndim;
+    cfg.ndist = m_ndist;
+    cfg.collision = m_collision;
+    cfg.precision = m_cfg.opt_str("precision", "fp64") == "fp32" ? LBM_B200_FP32 : LBM_B200_FP64;       // extension key
+    cfg.arithmetic = m_cfg.opt_str("arithmetic", "strict") == "fast" ? LBM_B200_FAST : LBM_B200_STRICT; // extension key
+    cfg.omega = m_omega;
+    cfg.omega_minus = m_cfg.opt("omega_minus", m_omega);
+    if(m_cfg.has("trt_magic")) { // Lambda = (1/w+ - 1/2)(1/w- - 1/2)
+      const double lam = m_cfg.at("trt_magic").as_double();
+      cfg.omega_minus  = 1.0 / (lam / (1.0 / m_omega - 0.5) + 0.5);
+    }
+    for(double& r : cfg.mrt_rates) r = m_omega;
+    if(m_cfg.has("mrt_rates")) {
+      const auto r = m_cfg.at("mrt_rates").as_doubles();
+      for(size_t i = 0; i < r.size() && i < 27; ++i) cfg.mrt_rates[i] = r[i];
+    }
+    cfg.track_vars = static_cast<int32_t>(m_convInterval > 1 ? m_convInterval : 1);
+    call(lbm_b200_create(&cfg, g.n, &m_gpu));
+    call(lbm_b200_set_topology(m_gpu, g.nghbr.data(), g.nn_diag));
+    call(lbm_b200_set_geometry(m_gpu, g.center.data(), g.bbmin, g.bbmax, g.cell_length));
+    // setupBndryCnds, bnd.h:71-142
+    const Json& boundary = m_cfg.at("boundary");
+    for(const auto& gk : boundary.obj) {
+      const size_t nkeys = gk.second.size();
+      for(const auto& sk : gk.second.obj) {
+        const std::string sname = nkeys > 1 ? gk.first + "_" + sk.first : gk.first;
+        const Surface*    srf   = g.find(sname);
+        if(srf == nullptr) TERMM(-1, "Invalid bndryId \"" + sname + "\"");
+        if(srf->cells.empty()) continue; // "WARNING: Skipping ... no valid cells!"
+        const Json&       bc   = sk.second;
+        if(!bc.has("type")) TERMM(-1, "The required configuration value is missing: type");
+        const std::string type = bc.at("type").as_string();
+        std::vector<double> normals;
+        for(int64_t c : srf->cells)
+          for(int d = 0; d < m_ndim; ++d) normals.push_back(srf->normal.at(c)[d]);
+        const int64_t* cells = srf->cells.data();
+        const int64_t  nc    = static_cast<int64_t>(srf->cells.size());
+        const bool generate = bc.opt_bool("generateBndry", true);
+        if(type == "periodic") {
+          const Surface* other = g.find(bc.at("connection").as_string());
+          if(other == nullptr) TERMM(-1, "Invalid bndryId \"" + bc.at("connection").as_string() + "\"");
+          if(!generate) continue; // LBMBnd_dummy
+          call(lbm_b200_add_periodic(m_gpu, cells, normals.data(), nc, other->cells.data(), static_cast<int64_t>(other->cells.size()),
+                                     bc.has("pressure") ? bc.at("pressure").as_double() : NAN));
+        } else if(type == "wall") {
+          if(!generate) continue;
+          const std::string model = bc.at("model").as_string();
+          if(model == "bounceback") call(lbm_b200_add_wall_bb(m_gpu, cells, normals.data(), nc, bc.opt("tangentialVelocity", 0.0)));
+          else if(model == "equilibrium" || model == "neem" || model == "nebb")
+            TERMM(-1, "wall boundary model " + model + " is not available on the GPU path yet (SURVEY.md section 8f N1)");
+          else TERMM(-1, "Invalid wall boundary model: " + model);
+        } else if(type == "pressure") {
+          if(!generate) continue;
+          call(lbm_b200_add_pressure(m_gpu, cells, normals.data(), nc, bc.at("pressure").as_double()));
+        } else if(type == "outlet" || type == "inlet") {
+          TERMM(-1, "Broken"); // bnd.h:176-183
+        } else if(type == "dirichlet") {
+          if(!generate) continue;
+          const std::string model = bc.at("model").as_string();
+          if(model != "bounceback") TERMM(-1, "dirichlet model " + model + " is not available on the GPU path yet (SURVEY.md section 8f N1)");
+          const auto v = bc.at("value").as_doubles();
+          if(static_cast<int>(v.size()) < m_ndim) TERMM(-1, "dirichlet value needs one entry per dimension");
+          call(lbm_b200_add_dirichlet_bb(m_gpu, cells, normals.data(), nc, v.data()));
+        } else {
+          TERMM(-1, "Invalid bndCndType: " + type);
+        }
+      }
+    }
+    if(!m_cfg.opt_str("forcing", "").empty()) { // solver.cpp:630-647
+      std::cerr << "Using forcing!" << std::endl;
+      const Surface *in = g.find("cube_-x"), *out = g.find("cube_+x");
+      if(in == nullptr || out == nullptr) TERMM(-1, "Invalid bndryId \"cube_-x\"");
+      call(lbm_b200_set_forcing(m_gpu, in->cells.data(), static_cast<int64_t>(in->cells.size()), out->cells.data(),
+                                static_cast<int64_t>(out->cells.size()), m_cfg.at("poiseuillePressureGradient").as_double()));
+    }
+    call(lbm_b200_init(m_gpu));
+  }
+
+  // solver.cpp:233-263
+  bool convergenceCondition() {
+    if(!(m_timeStep > 0 && m_timeStep % m_convInterval == 0)) return false;
+    const int NVAR = m_ndim + 1;
+    std::vector<double> conv(NVAR);
+    int32_t bad = 0;
+    call(lbm_b200_residual(m_gpu, conv.data(), &bad));
+    static const char* names3[4] = {"U", "V", "W", "rho"};
+    std::cerr << m_timeStep << ": ";
+    for(int v = 0; v < NVAR; ++v) std::cerr << "d" << (v == m_ndim ? "rho" : names3[v]) << "=" << conv[v] << " ";
+    std::cerr << std::endl;
+    double maxConv = conv[0];
+    for(double c : conv) maxConv = std::max(maxConv, c);
+    lastResidual = maxConv;
+    const double crit = m_cfg.opt("convergence", 1E-12);
+    if(m_timeStep > 1 && maxConv < crit) {
+      std::cerr << "Reached convergence to: " << maxConv << std::endl;
+      return true;
+    }
+    if(m_timeStep > 1 && (bad || std::isnan(maxConv) || std::isinf(maxConv))) {
+      std::cerr << "Solution diverged!" << std::endl;
+      m_diverged = true;
+      return true;
+    }
+    return false;
+  }
+
+  // solver.cpp:323-384: the moments of the current fold; written as a VTK PolyData point file (ASCII flavour)
+  void output(bool forced) {
+    if(!((m_timeStep > 0 && m_timeStep % m_solutionInterval == 0) || forced)) return;
+    call(lbm_b200_get_moments(m_gpu, vars.data()));
+    if(m_cfg.opt_bool("write_output", true)) writeVtp(m_outputDir + m_solutionName + "_" + std::to_string(m_timeStep) + ".vtp");
+  }
+
+  void writeVtp(const std::string& path) {
+    ::mkdir(m_outputDir.c_str(), 0755);
+    const SolverGrid& g = m_grid.g;
+    std::ofstream o(path);
+    if(!o) TERMM(-1, "Invalid output directory set! (value: " + m_outputDir + ")");
+    const int NVAR = m_ndim + 1;
+    std::cerr << "  Writing " << path << " with #" << g.n << " cells" << std::endl;
+    o << "<?xml version=\"1.0\"?>\n<VTKFile type=\"PolyData\" version=\"0.1\" byte_order=\"LittleEndian\">\n<PolyData>\n<Piece NumberOfPoints=\""
+      << g.n << "\" NumberOfVerts=\"0\" NumberOfLines=\"0\" NumberOfStrips=\"0\" NumberOfPolys=\"0\">\n<Points>\n"
+      << "<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n";
+    o << std::setprecision(17);
+    for(int64_t c = 0; c < g.n; ++c) {
+      for(int d = 0; d < 3; ++d) o << (d < m_ndim ? g.center[c * m_ndim + d] : 0.0) << " ";
+      o << "\n";
+    }
+    o << "</DataArray>\n</Points>\n<PointData>\n";
+    static const char* names[4] = {"U", "V", "W", "rho"};
+    for(int v = 0; v < NVAR; ++v) {
+      o << "<DataArray type=\"Float64\" Name=\"" << (v == m_ndim ? "rho" : names[v]) << "\" format=\"ascii\">\n";
+      for(int64_t c = 0; c < g.n; ++c) o << vars[c * NVAR + v] << "\n";
+      o << "</DataArray>\n";
+    }
+    o << "</PointData>\n</Piece>\n</PolyData>\n</VTKFile>\n";
+  }
+
+  // solver.cpp:388-482 with analytical_solutions.h:16-33,51-59
+  void compareToAnalyticalResult() {
+    const std::string name = m_cfg.at("analyticalSolution").as_string();
+    if(m_ndim != 2) TERMM(-1, "Invalid analyticalSolution :" + name + " selected!");
+    std::function<void(const double*, double*)> sol;
+    if(name == "couette2D_1_5") {
+      const double reynoldsNum = 0.75, relaxTime = 0.9, refL = 1.0;
+      const double dynViscosity = (2.0 * relaxTime - 1.0) / 6.0;
+      const double refV = reynoldsNum * dynViscosity / refL;
+      sol = [refV](const double* x, double* u) { u[0] = refV / 5.0 * x[1]; u[1] = 0; };
+    } else if(name == "poiseuille2D_1") {
+      const double dp = m_cfg.at("poiseuillePressureGradient").as_double(), nu = m_nu;
+      sol = [dp, nu](const double* x, double* u) { u[0] = dp / (2.0 * nu) * x[1] * (1.0 - 0.0 - x[1]); u[1] = 0; };
+    } else {
+      TERMM(-1, "Invalid analyticalSolution :" + name + " selected!");
+    }
+    const SolverGrid& g = m_grid.g;
+    std::vector<char> excluded(static_cast<size_t>(g.n), 0);
+    if(m_cfg.has("analyticalSolutionExcludeSurface"))
+      for(const Json& s : m_cfg.at("analyticalSolutionExcludeSurface").arr) {
+        const Surface* srf = g.find(s.as_string());
+        if(srf == nullptr) TERMM(-1, "Invalid bndryId \"" + s.as_string() + "\"");
+        for(int64_t c : srf->cells) excluded[c] = 1;
+      }
+    const int NVAR = m_ndim + 1;
+    double sumError = 0, sumErrorSq = 0, sumSolution = 0, sumSolutionSq = 0;
+    maxError = 0;
+    for(int64_t c = 0; c < g.n; ++c) {
+      if(excluded[c]) continue;
+      double u[2];
+      sol(&g.center[c * 2], u);
+      const double dx = vars[c * NVAR] - u[0], dy = vars[c * NVAR + 1] - u[1];
+      const double delta = std::sqrt(dx * dx + dy * dy);
+      sumError += delta;
+      sumErrorSq += delta * delta;
+      sumSolution += std::sqrt(u[0] * u[0] + u[1] * u[1]);
+      sumSolutionSq += u[0] * u[0] + u[1] * u[1];
+      maxError = std::max(delta, maxError);
+    }
+    l2Error = (std::sqrt(sumErrorSq) / std::sqrt(sumSolutionSq)) / std::pow(static_cast<double>(g.n), 1.0 / m_ndim);
+    gre     = sumError / sumSolution;
+    std::cerr << "Comparing to analytical result " << name << "\nmax. Error: " << maxError << "\navg. L2: " << l2Error
+              << "\nglobal relative error: " << gre << std::endl;
+    bool failed = false;
+    if(m_cfg.opt("errorMax", 1.0) < maxError) {
+      failed = true;
+      std::cerr << "Error bounds for the maximum error have failed!!! ( < " << m_cfg.opt("errorMax", 1.0) << ")" << std::endl;
+    }
+    if(m_cfg.opt("errorL2", 1.0) < l2Error || std::isnan(l2Error)) {
+      failed = true;
+      std::cerr << "Error bounds for the L2 error have failed!!! ( < " << m_cfg.opt("errorL2", 1.0) << ")" << std::endl;
+    }
+    if(m_cfg.opt("errorGRE", 1.0) < gre || std::isnan(gre)) {
+      failed = true;
+      std::cerr << "Error bounds for the global relative error have failed!!! ( < " << m_cfg.opt("errorGRE", 1.0) << ")" << std::endl;
+    }
+    if(failed) TERMM(-1, "Analytical testcase failed");
+  }
+
+  Json        m_cfg;
+  std::string m_configFile, m_model = "D2Q9", m_outputDir = "out/", m_solutionName = "solution";
+  int         m_ndim = 2, m_ndist = 9, m_collision = LBM_B200_BGK;
+  bool        m_benchmark = false, m_diverged = false;
+  long long   m_infoInterval = 10, m_convInterval = 10, m_solutionInterval = 100, m_maxTimeStep = 0, m_timeStep = 0;
+  double      m_refLength = 1.0, m_ma = 0.01, m_re = 1, m_nu = 0, m_relaxTime = 0.9, m_omega = 1.0 / 0.9;
+  LBMGrid     m_grid;
+  lbm_b200_solver* m_gpu = nullptr;
+};
+
+} // namespace lbmhost

@@ -1,0 +1,80 @@
+"""ctypes binding of the host-side mirror (lbm_b200/host: grid pipeline + LBMSolver), used by the tests."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(_HERE, "host")])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liblbm_host.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        vp = C.c_void_p
+        L.lbmhost_grid_build.restype = vp
+        L.lbmhost_grid_build.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        L.lbmhost_grid_free.argtypes = [vp]
+        L.lbmhost_grid_ncells.restype = C.c_int64
+        L.lbmhost_grid_ncells.argtypes = [vp]
+        L.lbmhost_grid_ndim.argtypes = [vp]
+        L.lbmhost_grid_stride.argtypes = [vp]
+        L.lbmhost_grid_cell_length.restype = C.c_double
+        L.lbmhost_grid_cell_length.argtypes = [vp]
+        L.lbmhost_grid_copy.argtypes = [vp, vp, vp, vp]
+        L.lbmhost_grid_nsurfaces.argtypes = [vp]
+        L.lbmhost_grid_surface_name.restype = C.c_char_p
+        L.lbmhost_grid_surface_name.argtypes = [vp, C.c_int]
+        L.lbmhost_grid_surface_size.restype = C.c_int64
+        L.lbmhost_grid_surface_size.argtypes = [vp, C.c_int]
+        L.lbmhost_grid_surface_copy.argtypes = [vp, C.c_int, vp, vp]
+        L.lbmhost_run.argtypes = [C.c_char_p, vp, vp, C.c_int64, C.c_char_p, C.c_int]
+        _LIB = L
+    return _LIB
+
+
+def build_grid(config_path):
+    """Grid generator run + transferGrid of the host mirror -> dict of tables in the reference's format."""
+    L = lib()
+    err = C.create_string_buffer(1024)
+    h = L.lbmhost_grid_build(config_path.encode(), err, 1024)
+    if not h:
+        raise RuntimeError(err.value.decode())
+    try:
+        n, ndim, stride = L.lbmhost_grid_ncells(h), L.lbmhost_grid_ndim(h), L.lbmhost_grid_stride(h)
+        nghbr = np.empty((n, stride), dtype=np.int64)
+        center = np.empty((n, ndim))
+        props = np.empty(n, dtype=np.uint16)
+        L.lbmhost_grid_copy(h, nghbr.ctypes.data, center.ctypes.data, props.ctypes.data)
+        surfaces = []
+        for k in range(L.lbmhost_grid_nsurfaces(h)):
+            m = L.lbmhost_grid_surface_size(h, k)
+            cells = np.empty(m, dtype=np.int64)
+            normals = np.empty((m, ndim))
+            if m:
+                L.lbmhost_grid_surface_copy(h, k, cells.ctypes.data, normals.ctypes.data)
+            surfaces.append((L.lbmhost_grid_surface_name(h, k).decode(), cells, normals))
+        return dict(n=n, ndim=ndim, nghbr=nghbr, center=center, props=props, surfaces=surfaces,
+                    cell_length=L.lbmhost_grid_cell_length(h))
+    finally:
+        L.lbmhost_grid_free(h)
+
+
+def run(config_path, nvars=0):
+    """Whole pipeline like the `lbm` executable. Returns (rc, message, dict of results, vars or None)."""
+    L = lib()
+    err = C.create_string_buffer(2048)
+    out = np.zeros(6)
+    vars_ = np.zeros(nvars) if nvars else None
+    rc = L.lbmhost_run(config_path.encode(), out.ctypes.data, vars_.ctypes.data if nvars else None, nvars, err, 2048)
+    keys = ["max_error", "l2_error", "gre", "steps", "converged", "residual"]
+    return rc, err.value.decode(), dict(zip(keys, out.tolist())), vars_

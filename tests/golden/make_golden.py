@@ -67,6 +67,7 @@ def parse_surfaces(path, ndim):
 def run_case(name):
     rel, max_steps, steps, full = CASES[name]
     cfg = json.load(open(os.path.join(REF, "test", rel)))
+    original = json.dumps(cfg)
     cfg["solver"]["maxSteps"] = max_steps
     # keep the run quiet and free of early termination; none of these keys touches the arithmetic
     cfg["solver"]["solution_interval"] = 10 ** 9
@@ -86,6 +87,7 @@ def run_case(name):
         n, ndim, q, nvar, nn = (int(meta[k]) for k in ("ncells", "ndim", "ndist", "nvar", "nnghbr"))
         out = {
             "config_json": np.array(json.dumps(cfg)),
+            "config_orig_json": np.array(original),  # the reference's test configuration, unmodified
             "ncells": n, "ndim": ndim, "ndist": q, "nvar": nvar, "nnghbr": nn,
             "omega": float(meta["omega"]), "nu": float(meta["nu"]), "maxlvl": int(meta["maxlvl"]),
             "nghbr": np.fromfile(os.path.join(d, "nghbr.i64"), dtype=np.int64).reshape(n, nn).astype(np.int32),
