@@ -61,10 +61,12 @@ struct DevParams {
   const uint16_t* tmpl;     // [(Q-1)][CHUNK]
   const int32_t*  chunk_nb; // [n_fast_chunks][NSEL + 1]: neighbour chunk bases (-1 = wall), wall descriptor id
   const AddEntryT<Real>* wall_desc; // [n_wall_desc][Q-1] bounce-back addends of wall chunks
-  int32_t         n_fast_chunks;
+  int32_t         n_fast_chunks;    // fast chunks [chunk_off, chunk_off + n_fast_chunks) are updated by this launch
+  int32_t         chunk_off;
   int32_t         n_fast_blocks;
   // generic range
-  int32_t        gen_begin, n_gen, n_gen_blocks;
+  int32_t        gen_begin, n_gen, n_gen_blocks; // generic cells [gen_off, gen_off + n_gen) of the generic range
+  int32_t        gen_off;
   int64_t        gen_stride;
   const int32_t* codes; // [(Q-1)][gen_stride]
   SlotTables<Real> tabs;
@@ -411,9 +413,9 @@ __global__ void __launch_bounds__(kThreads, LBM_MINBLOCKS) k_step(const __grid_c
 
   if(static_cast<int>(blockIdx.x) < p.n_gen_blocks) {
     // ---- generic path: one thread per cell, per-slot link codes. Scheduled first: these blocks are the slow ones.
-    const int32_t g = blockIdx.x * kThreads + threadIdx.x;
-    if(g >= p.n_gen) return;
-    const int32_t cell = p.gen_begin + g;
+    const int32_t gl = blockIdx.x * kThreads + threadIdx.x;
+    if(gl >= p.n_gen) return;
+    const int32_t cell = p.gen_begin + p.gen_off + gl;
     Real          fold[Q];
     gather_generic<L, Real, STRICT>(p, Abuf, cell, fold);
     update_and_store<L, Real, STRICT, COLL>(p, cell, fold);
@@ -424,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, LBM_MINBLOCKS) k_step(const __grid_c
   const int fb = blockIdx.x - p.n_gen_blocks;
   for(int t = threadIdx.x; t < QM * CH; t += kThreads) s_tmpl[t] = p.tmpl[t];
   int buf = 0;
-  for(int chunk = fb; chunk < p.n_fast_chunks; chunk += p.n_fast_blocks) {
+  for(int chunk = p.chunk_off + fb; chunk < p.chunk_off + p.n_fast_chunks; chunk += p.n_fast_blocks) {
     // neighbour-chunk bases are double buffered: one barrier per chunk is enough (a thread can run at most one
     // chunk ahead of the slowest one, and then it writes the other buffer)
     buf ^= 1;

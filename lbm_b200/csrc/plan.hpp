@@ -80,6 +80,7 @@ struct Plan {
   int64_t   npad = 0;      // device cells (stride of the SoA arrays)
   int       CH = 0;
   int64_t   n_fast_chunks = 0, n_slow_chunks = 0, n_loose = 0;
+  int64_t   n_fast_outer = 0, n_gen_outer = 0; // leading fast chunks / generic cells that feed the halo exchange
   int64_t   gen_begin = 0; // first device cell of the generic range
   int64_t   n_gen = 0;     // cells in the generic range
   int64_t   gen_stride = 0;
@@ -503,17 +504,39 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
   }
 
   // ---- 6. device layout: fast chunks, slow chunks (kept contiguous so fast chunks can address them by
-  //         template), loose cells; all in reference (SFC) order within their group
+  //         template), loose cells; all in reference (SFC) order within their group.  In a partitioned run the "outer"
+  //         units -- chunks / loose cells holding a cell whose populations a peer needs -- come first in their group, so
+  //         that they can be updated by a first launch and exchanged while a second launch updates the rest.
+  std::vector<char> is_send(static_cast<size_t>(N), 0);
+  for(int64_t c : in.send_cell)
+    if(c >= 0 && c < NO) is_send[c] = 1;
+  std::vector<char> outer_chunk(static_cast<size_t>(nc), 0);
+  for(int64_t k = 0; k < nc; ++k)
+    for(int o = 0; o < CH; ++o)
+      if(is_send[cand_base[k] + o]) { outer_chunk[k] = 1; break; }
   P.ref2dev.assign(static_cast<size_t>(N), -1);
   std::vector<int64_t> cand_dev(static_cast<size_t>(nc), -1);
+  std::vector<int64_t> fast_order;
   int64_t pos = 0;
-  for(int64_t k = 0; k < nc; ++k) if(fast[k]) { cand_dev[k] = pos; pos += CH; ++P.n_fast_chunks; }
+  for(int pass = 0; pass < 2; ++pass)
+    for(int64_t k = 0; k < nc; ++k)
+      if(fast[k] && (outer_chunk[k] != 0) == (pass == 0)) {
+        cand_dev[k] = pos;
+        pos += CH;
+        fast_order.push_back(k);
+        if(pass == 0) ++P.n_fast_outer;
+      }
+  P.n_fast_chunks = static_cast<int64_t>(fast_order.size());
   P.gen_begin = pos;
-  for(int64_t k = 0; k < nc; ++k) if(!fast[k]) { cand_dev[k] = pos; pos += CH; ++P.n_slow_chunks; }
+  for(int pass = 0; pass < 2; ++pass) {
+    for(int64_t k = 0; k < nc; ++k)
+      if(!fast[k] && (outer_chunk[k] != 0) == (pass == 0)) { cand_dev[k] = pos; pos += CH; ++P.n_slow_chunks; }
+    for(int64_t c = 0; c < NO; ++c)
+      if(chunk_of[c] < 0 && (is_send[c] != 0) == (pass == 0)) { P.ref2dev[c] = static_cast<int32_t>(pos++); ++P.n_loose; }
+    if(pass == 0) P.n_gen_outer = pos - P.gen_begin;
+  }
   for(int64_t k = 0; k < nc; ++k)
     for(int o = 0; o < CH; ++o) P.ref2dev[cand_base[k] + o] = static_cast<int32_t>(cand_dev[k] + o);
-  for(int64_t c = 0; c < NO; ++c)
-    if(chunk_of[c] < 0) { P.ref2dev[c] = static_cast<int32_t>(pos++); ++P.n_loose; }
   P.n_gen  = pos - P.gen_begin;
   P.ghost_begin = pos;
   for(int64_t c = NO; c < N; ++c) P.ref2dev[c] = static_cast<int32_t>(pos++);
@@ -524,21 +547,17 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
 
   const int NBW = L.NSEL + 1;
   P.chunk_nb.assign(static_cast<size_t>(P.n_fast_chunks) * NBW, 0);
-  {
-    int64_t f = 0;
-    for(int64_t k = 0; k < nc; ++k) {
-      if(!fast[k]) continue;
-      for(int s = 0; s < L.NSEL; ++s) {
-        const int64_t r = nbref[static_cast<size_t>(k) * L.NSEL + s];
-        // a selector no slot uses (e.g. cube corners for D3Q19) stays at the chunk itself
-        int32_t v = static_cast<int32_t>(cand_dev[k]);
-        if(r == WALL) v = -1;
-        else if(r >= 0) v = static_cast<int32_t>(cand_dev[chunk_of[r]]);
-        P.chunk_nb[static_cast<size_t>(f) * NBW + s] = v;
-      }
-      P.chunk_nb[static_cast<size_t>(f) * NBW + L.NSEL] = wall_of[k];
-      ++f;
+  for(size_t f = 0; f < fast_order.size(); ++f) {
+    const int64_t k = fast_order[f];
+    for(int s = 0; s < L.NSEL; ++s) {
+      const int64_t r = nbref[static_cast<size_t>(k) * L.NSEL + s];
+      // a selector no slot uses (e.g. cube corners for D3Q19) stays at the chunk itself
+      int32_t v = static_cast<int32_t>(cand_dev[k]);
+      if(r == WALL) v = -1;
+      else if(r >= 0) v = static_cast<int32_t>(cand_dev[chunk_of[r]]);
+      P.chunk_nb[f * NBW + s] = v;
     }
+    P.chunk_nb[f * NBW + L.NSEL] = wall_of[k];
   }
 
   // ---- 7. link codes of the generic range

@@ -3,6 +3,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -108,8 +109,12 @@ struct Solver final : SolverBase {
   int dyn = 0;       // d_uext[dyn] / d_values[dyn] are the ones the next gather must use
   int vcur = 0;      // vars[vcur] = m_vars, vars[vcur^1] = m_varsold
   int64_t vars_step[2] = {-1, -1};
+  bool    overlap_enabled = true;
   bool    first = true; // next step is step 0 of the reference loop (m_fold = initial condition)
-  int     n_fast_blocks = 0, n_gen_blocks = 0;
+  int     n_fast_blocks = 0, n_gen_blocks = 0, max_resident = 0;
+  cudaStream_t comm_stream = nullptr;   // halo exchange runs here, overlapped with the update of the inner cells
+  cudaEvent_t  ev_outer = nullptr, ev_halo = nullptr;
+  bool         halo_pending = false;
   int64_t launches = 0, launches_main = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr;
 
@@ -118,6 +123,9 @@ struct Solver final : SolverBase {
     if(ev1) cudaEventDestroy(ev1);
     if(evm0) cudaEventDestroy(evm0);
     if(evm1) cudaEventDestroy(evm1);
+    if(ev_outer) cudaEventDestroy(ev_outer);
+    if(ev_halo) cudaEventDestroy(ev_halo);
+    if(comm_stream) cudaStreamDestroy(comm_stream);
   }
 
   lbm::DevParams<Real> params(int src, int dst, Real* vars_out) const {
@@ -129,6 +137,8 @@ struct Solver final : SolverBase {
     p.chunk_nb = d_chunk_nb.p;
     p.wall_desc = d_wall.p;
     p.n_fast_chunks = static_cast<int32_t>(plan.n_fast_chunks);
+    p.chunk_off = 0;
+    p.gen_off = 0;
     p.n_fast_blocks = n_fast_blocks;
     p.gen_begin = static_cast<int32_t>(plan.gen_begin);
     p.n_gen = static_cast<int32_t>(plan.n_gen);
@@ -164,6 +174,7 @@ struct Solver final : SolverBase {
   }
 
   int init() override {
+    if(const char* e = std::getenv("LBM_B200_NO_OVERLAP")) overlap_enabled = e[0] == '0' || e[0] == 0;
     if(!lbm::build_plan(in, plan)) return fail(plan.error.find("order-dependent") != std::string::npos ? LBM_B200_EUNSUP : LBM_B200_EINVAL, plan.error);
     std::vector<int32_t>().swap(in.nghbr);
     CUDA_TRY(cudaSetDevice(cfg.device));
@@ -254,9 +265,15 @@ struct Solver final : SolverBase {
       int per_sm = 0;
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, main_kernel(), lbm::kThreads, 0));
       if(per_sm < 1) per_sm = 1;
-      int64_t want = static_cast<int64_t>(prop.multiProcessorCount) * per_sm;
+      max_resident  = prop.multiProcessorCount * per_sm;
+      int64_t want  = max_resident;
       if(want > plan.n_fast_chunks) want = plan.n_fast_chunks;
       n_fast_blocks = static_cast<int>(want);
+    }
+    if(!in.peers.empty()) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&ev_outer, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&ev_halo, cudaEventDisableTiming));
     }
 
     // ---- initialCondition(): vars = 0, boundary presets, rho = 1, f = fold = feq   (solver.cpp:267-295)
@@ -344,7 +361,7 @@ struct Solver final : SolverBase {
 
   // Outgoing populations of this step -> peers, theirs -> my ghost cells.  One pack kernel, one NCCL group of
   // send/recv pairs over NVLink, one unpack kernel, all on the solver's stream.
-  int halo_exchange(Real* buf) {
+  int halo_exchange(Real* buf, cudaStream_t stream) {
     if(in.peers.empty()) return LBM_B200_OK;
     auto& nc = lbm::nccl_api();
     const int64_t ns = static_cast<int64_t>(plan.send_index.size()), nr = static_cast<int64_t>(plan.recv_index.size());
@@ -377,23 +394,58 @@ struct Solver final : SolverBase {
     if(want_vars(t)) vout = vars[vcur ^ 1].p;
     lbm::DevParams<Real> p = params(src, dst, vout);
     if(prev_fold.p != nullptr) p.A = prev_fold.p; // explicit m_fold supplied by set_populations
-    const int grid = n_gen_blocks + n_fast_blocks;
+    // a launch over generic cells [g0, g0+ng) and fast chunks [c0, c0+ncnk)
+    auto launch = [&](int64_t g0, int64_t ng, int64_t c0, int64_t ncnk) {
+      lbm::DevParams<Real> q = p;
+      q.gen_off       = static_cast<int32_t>(g0);
+      q.n_gen         = static_cast<int32_t>(ng);
+      q.n_gen_blocks  = static_cast<int>((ng + lbm::kThreads - 1) / lbm::kThreads);
+      q.chunk_off     = static_cast<int32_t>(c0);
+      q.n_fast_chunks = static_cast<int32_t>(ncnk);
+      q.n_fast_blocks = static_cast<int32_t>(ncnk < max_resident ? ncnk : max_resident);
+      const int grid  = q.n_gen_blocks + q.n_fast_blocks;
+      if(grid > 0) {
+        main_kernel()<<<grid, lbm::kThreads, 0, stream>>>(q);
+        ++launches;
+        ++launches_main;
+      }
+    };
+    const bool has_aux = d_force.n > 0 || d_perp.n > 0 || d_abb.n > 0 || (vout != nullptr && d_varfix.n > 0);
+    const bool overlap = !in.peers.empty() && !has_aux && overlap_enabled;
+    if(halo_pending) { // ghosts of the buffer we are about to read were filled on the communication stream
+      CUDA_TRY(cudaStreamWaitEvent(stream, ev_halo, 0));
+      halo_pending = false;
+    }
     if(time_main) cudaEventRecord(evm0, stream);
-    main_kernel()<<<grid, lbm::kThreads, 0, stream>>>(p);
-    if(time_main) cudaEventRecord(evm1, stream);
-    ++launches;
-    ++launches_main;
-    CUDA_TRY(cudaGetLastError());
-    int rc = cfg.arithmetic == LBM_B200_STRICT ? aux_kernels<true>(p, vout) : aux_kernels<false>(p, vout);
-    if(rc != LBM_B200_OK) return rc;
-    rc = halo_exchange(f[dst].p);
-    if(rc != LBM_B200_OK) return rc;
+    int rc = LBM_B200_OK;
+    if(overlap) {
+      // outer cells first; their populations travel while the inner cells are updated
+      launch(0, plan.n_gen_outer, 0, plan.n_fast_outer);
+      CUDA_TRY(cudaEventRecord(ev_outer, stream));
+      CUDA_TRY(cudaStreamWaitEvent(comm_stream, ev_outer, 0));
+      rc = halo_exchange(f[dst].p, comm_stream);
+      if(rc != LBM_B200_OK) return rc;
+      CUDA_TRY(cudaEventRecord(ev_halo, comm_stream));
+      halo_pending = true;
+      launch(plan.n_gen_outer, plan.n_gen - plan.n_gen_outer, plan.n_fast_outer, plan.n_fast_chunks - plan.n_fast_outer);
+      if(time_main) cudaEventRecord(evm1, stream);
+      CUDA_TRY(cudaGetLastError());
+    } else {
+      launch(0, plan.n_gen, 0, plan.n_fast_chunks);
+      if(time_main) cudaEventRecord(evm1, stream);
+      CUDA_TRY(cudaGetLastError());
+      rc = cfg.arithmetic == LBM_B200_STRICT ? aux_kernels<true>(p, vout) : aux_kernels<false>(p, vout);
+      if(rc != LBM_B200_OK) return rc;
+      rc = halo_exchange(f[dst].p, stream);
+      if(rc != LBM_B200_OK) return rc;
+    }
     if(vout != nullptr) {
       vcur ^= 1;
       vars_step[vcur] = t + 1;
     }
     if(prev_fold.p != nullptr) {
       CUDA_TRY(cudaStreamSynchronize(stream));
+      if(comm_stream) CUDA_TRY(cudaStreamSynchronize(comm_stream));
       prev_fold.alloc(0);
     }
     cur   = dst;
@@ -417,6 +469,10 @@ struct Solver final : SolverBase {
         main_acc += ms;
       }
     }
+    if(halo_pending) { // the step is complete only when the ghosts have arrived
+      CUDA_TRY(cudaStreamWaitEvent(stream, ev_halo, 0));
+      halo_pending = false;
+    }
     if(timed) {
       CUDA_TRY(cudaEventRecord(ev1, stream));
       CUDA_TRY(cudaEventSynchronize(ev1));
@@ -427,6 +483,7 @@ struct Solver final : SolverBase {
   }
 
   int sync() override {
+    if(comm_stream) CUDA_TRY(cudaStreamSynchronize(comm_stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     return LBM_B200_OK;
   }
