@@ -35,7 +35,7 @@ def test_couette_3d_analytic_profile():
     m = s.moments()
     exact = U * (coords[:, 2] + 0.5) / shape[2]
     assert np.max(np.abs(m[:, 0] - exact)) < 1e-10
-    assert np.max(np.abs(m[:, 1])) < 1e-14 and np.max(np.abs(m[:, 2])) < 1e-14
+    assert np.max(np.abs(m[:, 1])) < 1e-12 and np.max(np.abs(m[:, 2])) < 1e-12  # rounding-level drift only
     assert np.max(np.abs(m[:, 3] - 1.0)) < 1e-12
 
 
