@@ -36,7 +36,7 @@ def test_couette_3d_analytic_profile():
     exact = U * (coords[:, 2] + 0.5) / shape[2]
     assert np.max(np.abs(m[:, 0] - exact)) < 1e-10
     assert np.max(np.abs(m[:, 1])) < 1e-12 and np.max(np.abs(m[:, 2])) < 1e-12  # rounding-level drift only
-    assert np.max(np.abs(m[:, 3] - 1.0)) < 1e-12
+    assert np.max(np.abs(m[:, 3] - 1.0)) < 1e-10  # 40 000 steps of rounding in the wall addends
 
 
 def channel(ndim, ndist, shape, periodic):
