@@ -377,7 +377,15 @@ __device__ __forceinline__ void update_and_store(const DevParams<Real>& p, int32
   P::equilibrium(rho, u, feq);
   P::template collide<COLL>(p, fold, feq, f);
 #pragma unroll
-  for(int j = 0; j < Q; ++j) p.B[static_cast<size_t>(j) * p.stride + cell] = f[j];
+  for(int j = 0; j < Q; ++j) {
+#if defined(LBM_STORE_CS)
+    __stcs(&p.B[static_cast<size_t>(j) * p.stride + cell], f[j]);
+#elif defined(LBM_STORE_CG)
+    __stcg(&p.B[static_cast<size_t>(j) * p.stride + cell], f[j]);
+#else
+    p.B[static_cast<size_t>(j) * p.stride + cell] = f[j];
+#endif
+  }
   if(p.vars_out != nullptr) {
 #pragma unroll
     for(int d = 0; d < D; ++d) p.vars_out[static_cast<size_t>(d) * p.stride + cell] = u[d];
@@ -449,7 +457,13 @@ __global__ void __launch_bounds__(kThreads, LBM_MINBLOCKS) k_step(const __grid_c
         for(int j = 0; j < QM; ++j) {
           const uint32_t t   = s_tmpl[j * CH + o];
           const int32_t  src = nb[t >> 10] + static_cast<int32_t>(t & 1023u);
+#if defined(LBM_LOAD_NC)
+          fold[j]            = __ldg(&Abuf[static_cast<size_t>(j) * p.stride + src]);
+#elif defined(LBM_LOAD_CG)
+          fold[j]            = __ldcg(&Abuf[static_cast<size_t>(j) * p.stride + src]);
+#else
           fold[j]            = Abuf[static_cast<size_t>(j) * p.stride + src];
+#endif
         }
         fold[QM] = Abuf[static_cast<size_t>(QM) * p.stride + cell];
       } else {

@@ -109,7 +109,7 @@ struct Solver final : SolverBase {
   int dyn = 0;       // d_uext[dyn] / d_values[dyn] are the ones the next gather must use
   int vcur = 0;      // vars[vcur] = m_vars, vars[vcur^1] = m_varsold
   int64_t vars_step[2] = {-1, -1};
-  bool    overlap_enabled = true;
+  bool    overlap_enabled = true, debug_identity = false;
   bool    first = true; // next step is step 0 of the reference loop (m_fold = initial condition)
   int     n_fast_blocks = 0, n_gen_blocks = 0, max_resident = 0;
   cudaStream_t comm_stream = nullptr;   // halo exchange runs here, overlapped with the update of the inner cells
@@ -157,6 +157,7 @@ struct Solver final : SolverBase {
     for(int i = 0; i < 27; ++i) p.rates[i] = static_cast<Real>(cfg.mrt_rates[i]);
     p.vars_out = vars_out;
     p.first = first ? 1 : 0;
+    if(debug_identity) p.first = 1; // timing experiments only (LBM_B200_DEBUG_IDENTITY): every step reads its own cell, no gather
     return p;
   }
 
@@ -174,6 +175,7 @@ struct Solver final : SolverBase {
   }
 
   int init() override {
+    debug_identity = std::getenv("LBM_B200_DEBUG_IDENTITY") != nullptr;
     if(const char* e = std::getenv("LBM_B200_NO_OVERLAP")) overlap_enabled = e[0] == '0' || e[0] == 0;
     if(!lbm::build_plan(in, plan)) return fail(plan.error.find("order-dependent") != std::string::npos ? LBM_B200_EUNSUP : LBM_B200_EINVAL, plan.error);
     std::vector<int32_t>().swap(in.nghbr);
