@@ -654,6 +654,10 @@ SolverBase* make_solver(const lbm_b200_config& c) {
   if(c.ndim == 3 && c.ndist == 19 && dbl) return new Solver<lbm::Lattice<3, 19>, double>();
   return nullptr;
 #endif
+#ifdef LBM_EXPERIMENT_D3Q27_F64
+  if(c.ndim == 3 && c.ndist == 27 && dbl) return new Solver<lbm::Lattice<3, 27>, double>();
+  return nullptr;
+#endif
   if(c.ndim == 2 && c.ndist == 9) return dbl ? static_cast<SolverBase*>(new Solver<lbm::Lattice<2, 9>, double>()) : new Solver<lbm::Lattice<2, 9>, float>();
   if(c.ndim == 3 && c.ndist == 19) return dbl ? static_cast<SolverBase*>(new Solver<lbm::Lattice<3, 19>, double>()) : new Solver<lbm::Lattice<3, 19>, float>();
   if(c.ndim == 3 && c.ndist == 27) return dbl ? static_cast<SolverBase*>(new Solver<lbm::Lattice<3, 27>, double>()) : new Solver<lbm::Lattice<3, 27>, float>();
