@@ -21,6 +21,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <string>
 #include <unordered_map>
@@ -80,6 +81,7 @@ struct Plan {
   int64_t   npad = 0;      // device cells (stride of the SoA arrays)
   int       CH = 0;
   int64_t   n_fast_chunks = 0, n_slow_chunks = 0, n_loose = 0;
+  int64_t   n_ghost_blocks = 0;               // remote chunks mirrored as CH-cell blocks in the ghost range
   int64_t   n_fast_outer = 0, n_gen_outer = 0; // leading fast chunks / generic cells that feed the halo exchange
   int64_t   gen_begin = 0; // first device cell of the generic range
   int64_t   n_gen = 0;     // cells in the generic range
@@ -463,6 +465,77 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
     if(kv.second.kind != LK_BB && kv.second.kind != LK_BB_ADD) odd[c] = 1;
     else if(j < QM && pull[static_cast<size_t>(c) * QM + j] >= 0) odd[c] = 1;
   }
+  // ---- ghost blocks (partitioned runs): a chunk at a partition cut pulls from ghost cells.  If all ghosts that one (chunk,
+  // selector) pair needs sit at consistent template offsets they are the visible part of ONE remote chunk: that chunk gets
+  // a CH-cell block of its own in the ghost range, its ghosts are stored at their template offsets, and the cut chunk stays
+  // on the index-free path (the block is mostly padding; only the cells that cross the cut are ever filled by the halo).
+  std::vector<int32_t> ghost_group(static_cast<size_t>(in.n_ghost), -1); // ghost (index c - NO) -> block
+  std::vector<int32_t> ghost_off(static_cast<size_t>(in.n_ghost), -1);   // its curve offset inside the block
+  std::vector<int32_t> key_group;                                        // (chunk k, selector) -> block or -1, size nc * NSEL
+  int32_t n_ghost_blocks = 0;
+  if(in.n_ghost > 0 && nc > 0) {
+    const size_t nkeys = static_cast<size_t>(nc) * L.NSEL;
+    std::vector<int32_t> parent(nkeys);
+    for(size_t i = 0; i < nkeys; ++i) parent[i] = static_cast<int32_t>(i);
+    std::function<int32_t(int32_t)> find = [&](int32_t x) {
+      while(parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
+      return x;
+    };
+    std::vector<char>    key_used(nkeys, 0), key_bad(nkeys, 0);
+    std::vector<int32_t> ghost_key(static_cast<size_t>(in.n_ghost), -1);
+    for(int64_t k = 0; k < nc; ++k) {
+      const int64_t b = cand_base[k];
+      for(int o = 0; o < CH; ++o) {
+        for(int j = 0; j < QM; ++j) {
+          const int64_t src = pull[static_cast<size_t>(b + o) * QM + j];
+          if(src < NO) continue;
+          const uint16_t t   = tmpl_sfc[static_cast<size_t>(j) * CH + o];
+          const int32_t  ky  = static_cast<int32_t>(k * L.NSEL + (t >> 10));
+          const int32_t  off = t & 1023;
+          const size_t   g   = static_cast<size_t>(src - NO);
+          key_used[ky] = 1;
+          if((t >> 10) == SELF) key_bad[ky] = 1;
+          if(ghost_off[g] == -1) { ghost_off[g] = off; ghost_key[g] = ky; }
+          else {
+            if(ghost_off[g] != off) key_bad[ky] = key_bad[ghost_key[g]] = 1;
+            const int32_t ra = find(ky), rb = find(ghost_key[g]);
+            if(ra != rb) parent[ra] = rb;
+          }
+        }
+      }
+    }
+    // a block is valid if no key in it is bad and no two ghosts claim the same offset
+    std::vector<char> root_bad(nkeys, 0);
+    for(size_t i = 0; i < nkeys; ++i)
+      if(key_used[i] && key_bad[i]) root_bad[find(static_cast<int32_t>(i))] = 1;
+    {
+      std::unordered_map<int64_t, int32_t> taken; // (root, offset) -> ghost
+      for(size_t g = 0; g < ghost_off.size(); ++g) {
+        if(ghost_key[g] < 0) continue;
+        const int32_t r  = find(ghost_key[g]);
+        const int64_t kk = static_cast<int64_t>(r) * 1024 + ghost_off[g];
+        auto it = taken.find(kk);
+        if(it == taken.end()) taken[kk] = static_cast<int32_t>(g);
+        else root_bad[r] = 1;
+      }
+    }
+    std::vector<int32_t> root_block(nkeys, -1);
+    key_group.assign(nkeys, -1);
+    for(size_t i = 0; i < nkeys; ++i) {
+      if(!key_used[i]) continue;
+      const int32_t r = find(static_cast<int32_t>(i));
+      if(root_bad[r]) continue;
+      if(root_block[r] < 0) root_block[r] = n_ghost_blocks++;
+      key_group[i] = root_block[r];
+    }
+    for(size_t g = 0; g < ghost_off.size(); ++g) {
+      if(ghost_key[g] < 0) continue;
+      const int32_t r = find(ghost_key[g]);
+      ghost_group[g] = root_bad[r] ? -1 : root_block[r];
+    }
+  }
+  const int64_t GHOSTBLOCK = -1000; // nbref marker: GHOSTBLOCK - block id
+
   const int64_t WALL = -2;
   std::vector<char>    fast(static_cast<size_t>(nc), 0);
   std::vector<int64_t> nbref(static_cast<size_t>(nc) * L.NSEL, -1);
@@ -497,7 +570,13 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
           has_wall = true;
           continue;
         }
-        if(src >= NO) { ok = false; break; } // pull from a ghost cell
+        if(src >= NO) { // pull from a ghost cell: fine if it sits in a ghost block at the template offset
+          const int32_t grp = key_group.empty() ? -1 : key_group[static_cast<size_t>(k) * L.NSEL + sel];
+          if(grp < 0) { ok = false; break; }
+          if(nbk[sel] == -1) nbk[sel] = GHOSTBLOCK - grp;
+          else if(nbk[sel] != GHOSTBLOCK - grp) { ok = false; break; }
+          continue;
+        }
         const int64_t nb0 = src - (t & 1023);
         if(nbk[sel] == -1) {
           if(nb0 < 0 || nb0 + CH > NO || chunk_of[nb0] < 0 || cand_base[chunk_of[nb0]] != nb0) { ok = false; break; }
@@ -567,7 +646,14 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
     for(int o = 0; o < CH; ++o) P.ref2dev[cand_base[k] + o] = static_cast<int32_t>(cand_dev[k] + sfc2lex[o]);
   P.n_gen  = pos - P.gen_begin;
   P.ghost_begin = pos;
-  for(int64_t c = NO; c < N; ++c) P.ref2dev[c] = static_cast<int32_t>(pos++);
+  const int64_t ghost_block_base = pos;
+  pos += static_cast<int64_t>(n_ghost_blocks) * CH;
+  P.n_ghost_blocks = n_ghost_blocks;
+  for(int64_t c = NO; c < N; ++c) {
+    const size_t g = static_cast<size_t>(c - NO);
+    if(ghost_group[g] >= 0) P.ref2dev[c] = static_cast<int32_t>(ghost_block_base + static_cast<int64_t>(ghost_group[g]) * CH + sfc2lex[ghost_off[g]]);
+    else P.ref2dev[c] = static_cast<int32_t>(pos++);
+  }
   P.npad   = (pos + 63) / 64 * 64;
   P.gen_stride = (P.n_gen + 63) / 64 * 64;
   P.dev2ref.assign(static_cast<size_t>(P.npad), -1);
@@ -582,6 +668,7 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
       // a selector no slot uses (e.g. cube corners for D3Q19) stays at the chunk itself
       int32_t v = static_cast<int32_t>(cand_dev[k]);
       if(r == WALL) v = -1;
+      else if(r <= GHOSTBLOCK) v = static_cast<int32_t>(ghost_block_base + (GHOSTBLOCK - r) * CH);
       else if(r >= 0) v = static_cast<int32_t>(cand_dev[chunk_of[r]]);
       P.chunk_nb[f * NBW + s] = v;
     }
