@@ -273,7 +273,9 @@ struct Solver final : SolverBase {
       n_fast_blocks = static_cast<int>(want);
     }
     if(!in.peers.empty()) {
-      CUDA_TRY(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
+      int prio_lo = 0, prio_hi = 0;
+      CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      CUDA_TRY(cudaStreamCreateWithPriority(&comm_stream, cudaStreamNonBlocking, prio_hi));
       CUDA_TRY(cudaEventCreateWithFlags(&ev_outer, cudaEventDisableTiming));
       CUDA_TRY(cudaEventCreateWithFlags(&ev_halo, cudaEventDisableTiming));
     }
@@ -421,11 +423,15 @@ struct Solver final : SolverBase {
     if(time_main) cudaEventRecord(evm0, stream);
     int rc = LBM_B200_OK;
     if(overlap) {
-      // outer cells first; their populations travel while the inner cells are updated
-      launch(0, plan.n_gen_outer, 0, plan.n_fast_outer);
-      CUDA_TRY(cudaEventRecord(ev_outer, stream));
+      // The outer cells (whatever a peer needs) are updated on the high-priority communication stream and sent right away;
+      // the inner cells are updated on the solver's stream at the same time and fill the GPU around them.
+      CUDA_TRY(cudaEventRecord(ev_outer, stream)); // everything this step reads is complete at this point of the solver's stream
       CUDA_TRY(cudaStreamWaitEvent(comm_stream, ev_outer, 0));
+      cudaStream_t main_stream = stream;
+      stream = comm_stream;
+      launch(0, plan.n_gen_outer, 0, plan.n_fast_outer);
       rc = halo_exchange(f[dst].p, comm_stream);
+      stream = main_stream;
       if(rc != LBM_B200_OK) return rc;
       CUDA_TRY(cudaEventRecord(ev_halo, comm_stream));
       halo_pending = true;
