@@ -399,14 +399,14 @@ struct Solver final : SolverBase {
     lbm::DevParams<Real> p = params(src, dst, vout);
     if(prev_fold.p != nullptr) p.A = prev_fold.p; // explicit m_fold supplied by set_populations
     // a launch over generic cells [g0, g0+ng) and fast chunks [c0, c0+ncnk)
-    auto launch = [&](int64_t g0, int64_t ng, int64_t c0, int64_t ncnk) {
+    auto launch = [&](int64_t g0, int64_t ng, int64_t c0, int64_t ncnk, int resident_cap) {
       lbm::DevParams<Real> q = p;
       q.gen_off       = static_cast<int32_t>(g0);
       q.n_gen         = static_cast<int32_t>(ng);
       q.n_gen_blocks  = static_cast<int>((ng + lbm::kThreads - 1) / lbm::kThreads);
       q.chunk_off     = static_cast<int32_t>(c0);
       q.n_fast_chunks = static_cast<int32_t>(ncnk);
-      q.n_fast_blocks = static_cast<int32_t>(ncnk < max_resident ? ncnk : max_resident);
+      q.n_fast_blocks = static_cast<int32_t>(ncnk < resident_cap ? ncnk : resident_cap);
       const int grid  = q.n_gen_blocks + q.n_fast_blocks;
       if(grid > 0) {
         main_kernel()<<<grid, lbm::kThreads, 0, stream>>>(q);
@@ -429,17 +429,19 @@ struct Solver final : SolverBase {
       CUDA_TRY(cudaStreamWaitEvent(comm_stream, ev_outer, 0));
       cudaStream_t main_stream = stream;
       stream = comm_stream;
-      launch(0, plan.n_gen_outer, 0, plan.n_fast_outer);
+      // a quarter of the resident CTA slots: the inner launch starts at once in the others, the outer cells still finish
+      // early enough for their populations to travel while the inner cells are being updated
+      launch(0, plan.n_gen_outer, 0, plan.n_fast_outer, max_resident / 4 > 0 ? max_resident / 4 : 1);
       rc = halo_exchange(f[dst].p, comm_stream);
       stream = main_stream;
       if(rc != LBM_B200_OK) return rc;
       CUDA_TRY(cudaEventRecord(ev_halo, comm_stream));
       halo_pending = true;
-      launch(plan.n_gen_outer, plan.n_gen - plan.n_gen_outer, plan.n_fast_outer, plan.n_fast_chunks - plan.n_fast_outer);
+      launch(plan.n_gen_outer, plan.n_gen - plan.n_gen_outer, plan.n_fast_outer, plan.n_fast_chunks - plan.n_fast_outer, max_resident);
       if(time_main) cudaEventRecord(evm1, stream);
       CUDA_TRY(cudaGetLastError());
     } else {
-      launch(0, plan.n_gen, 0, plan.n_fast_chunks);
+      launch(0, plan.n_gen, 0, plan.n_fast_chunks, max_resident);
       if(time_main) cudaEventRecord(evm1, stream);
       CUDA_TRY(cudaGetLastError());
       rc = cfg.arithmetic == LBM_B200_STRICT ? aux_kernels<true>(p, vout) : aux_kernels<false>(p, vout);
