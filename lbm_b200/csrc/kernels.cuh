@@ -64,6 +64,8 @@ struct DevParams {
   int32_t         n_fast_chunks;    // fast chunks [chunk_off, chunk_off + n_fast_chunks) are updated by this launch
   int32_t         chunk_off;
   int32_t         n_fast_blocks;
+  unsigned long long* ticket;      // global chunk ticket counter of this launch class
+  unsigned long long  ticket_base; // value of the counter when this launch starts
   // generic range
   int32_t        gen_begin, n_gen, n_gen_blocks; // generic cells [gen_off, gen_off + n_gen) of the generic range
   int32_t        gen_off;
@@ -417,6 +419,7 @@ __global__ void __launch_bounds__(kThreads, LBM_MINBLOCKS) k_step(const __grid_c
   constexpr int Q = L::Q, QM = Q - 1, CH = L::CHUNK, NSEL = L::NSEL;
   __shared__ uint16_t s_tmpl[QM * CH];
   __shared__ int32_t  s_nb[2][NSEL + 1];
+  __shared__ int32_t  s_ticket[2];
   const Real* __restrict__ Abuf = p.A;
 
   if(static_cast<int>(blockIdx.x) < p.n_gen_blocks) {
@@ -431,16 +434,25 @@ __global__ void __launch_bounds__(kThreads, LBM_MINBLOCKS) k_step(const __grid_c
   }
 
   // ---- fast path: persistent CTA over SFC chunks, template in shared memory, no per-cell index traffic
-  const int fb = blockIdx.x - p.n_gen_blocks;
+  // Chunks are handed out dynamically, in curve order, from a global ticket counter: a CTA that becomes resident late
+  // (another kernel holds its slot) simply takes fewer chunks, and there is no tail of unevenly loaded CTAs.  The counter
+  // only ever grows: a launch over n chunks with B CTAs advances it by exactly n + B (every CTA draws one ticket past the
+  // end), so the host knows the first ticket of every launch and never has to reset anything.
   for(int t = threadIdx.x; t < QM * CH; t += kThreads) s_tmpl[t] = p.tmpl[t];
-  int buf = 0;
-  for(int chunk = p.chunk_off + fb; chunk < p.chunk_off + p.n_fast_chunks; chunk += p.n_fast_blocks) {
-    // neighbour-chunk bases are double buffered: one barrier per chunk is enough (a thread can run at most one
-    // chunk ahead of the slowest one, and then it writes the other buffer)
-    buf ^= 1;
+  if(threadIdx.x == 0) s_ticket[0] = static_cast<int32_t>(atomicAdd(p.ticket, 1ull) - p.ticket_base);
+  __syncthreads();
+  int32_t ticket = s_ticket[0];
+  int     buf    = 0;
+  while(ticket < p.n_fast_chunks) {
+    const int chunk = p.chunk_off + ticket;
+    // neighbour-chunk bases and the next ticket are double buffered: one barrier per chunk is enough (a thread can run at
+    // most one chunk ahead of the slowest one, and then it touches the other buffer)
     if(threadIdx.x < NSEL + 1) s_nb[buf][threadIdx.x] = p.chunk_nb[static_cast<size_t>(chunk) * (NSEL + 1) + threadIdx.x];
+    if(threadIdx.x == 0) s_ticket[buf ^ 1] = static_cast<int32_t>(atomicAdd(p.ticket, 1ull) - p.ticket_base);
     __syncthreads();
+    ticket = s_ticket[buf ^ 1];
     const int32_t* nb  = s_nb[buf];
+    buf ^= 1;
     const int32_t  wid = nb[NSEL]; // wall descriptor of this chunk, -1: interior chunk
     const AddEntryT<Real>* wall = p.wall_desc + static_cast<size_t>(wid < 0 ? 0 : wid) * QM;
     const int32_t base = chunk * CH;

@@ -102,6 +102,8 @@ struct Solver final : SolverBase {
   DevBuf<double>   stage;     // AoS staging for host transfers [n][Q]
   DevBuf<int32_t>  d_ref2dev;
   DevBuf<int64_t>  d_send_idx, d_recv_idx;
+  DevBuf<unsigned long long> d_ticket; // [0]: inner / whole-domain launches, [1]: outer launches
+  unsigned long long ticket_next[2] = {0, 0};
   DevBuf<Real>     d_sendbuf, d_recvbuf;
   int64_t          halo_bytes = 0;
   int64_t          h2d_bytes = 0, d2h_bytes = 0;
@@ -312,6 +314,9 @@ struct Solver final : SolverBase {
       for(int b = 0; b < 2; ++b) CUDA_TRY(d_values[b].upload(hv));
     }
     CUDA_TRY(d_partial.alloc(static_cast<size_t>(NVAR) * 1024));
+    CUDA_TRY(d_ticket.alloc(2));
+    CUDA_TRY(cudaMemset(d_ticket.p, 0, d_ticket.bytes()));
+    ticket_next[0] = ticket_next[1] = 0;
     CUDA_TRY(cudaStreamSynchronize(stream));
     cur = 0;
     dyn = 0;
@@ -399,7 +404,7 @@ struct Solver final : SolverBase {
     lbm::DevParams<Real> p = params(src, dst, vout);
     if(prev_fold.p != nullptr) p.A = prev_fold.p; // explicit m_fold supplied by set_populations
     // a launch over generic cells [g0, g0+ng) and fast chunks [c0, c0+ncnk)
-    auto launch = [&](int64_t g0, int64_t ng, int64_t c0, int64_t ncnk, int resident_cap) {
+    auto launch = [&](int64_t g0, int64_t ng, int64_t c0, int64_t ncnk, int resident_cap, int cls) {
       lbm::DevParams<Real> q = p;
       q.gen_off       = static_cast<int32_t>(g0);
       q.n_gen         = static_cast<int32_t>(ng);
@@ -407,6 +412,9 @@ struct Solver final : SolverBase {
       q.chunk_off     = static_cast<int32_t>(c0);
       q.n_fast_chunks = static_cast<int32_t>(ncnk);
       q.n_fast_blocks = static_cast<int32_t>(ncnk < resident_cap ? ncnk : resident_cap);
+      q.ticket        = d_ticket.p + cls;
+      q.ticket_base   = ticket_next[cls];
+      ticket_next[cls] += static_cast<unsigned long long>(ncnk) + static_cast<unsigned long long>(q.n_fast_blocks);
       const int grid  = q.n_gen_blocks + q.n_fast_blocks;
       if(grid > 0) {
         main_kernel()<<<grid, lbm::kThreads, 0, stream>>>(q);
@@ -431,17 +439,17 @@ struct Solver final : SolverBase {
       stream = comm_stream;
       // a quarter of the resident CTA slots: the inner launch starts at once in the others, the outer cells still finish
       // early enough for their populations to travel while the inner cells are being updated
-      launch(0, plan.n_gen_outer, 0, plan.n_fast_outer, max_resident / 4 > 0 ? max_resident / 4 : 1);
+      launch(0, plan.n_gen_outer, 0, plan.n_fast_outer, max_resident / 4 > 0 ? max_resident / 4 : 1, 1);
       rc = halo_exchange(f[dst].p, comm_stream);
       stream = main_stream;
       if(rc != LBM_B200_OK) return rc;
       CUDA_TRY(cudaEventRecord(ev_halo, comm_stream));
       halo_pending = true;
-      launch(plan.n_gen_outer, plan.n_gen - plan.n_gen_outer, plan.n_fast_outer, plan.n_fast_chunks - plan.n_fast_outer, max_resident);
+      launch(plan.n_gen_outer, plan.n_gen - plan.n_gen_outer, plan.n_fast_outer, plan.n_fast_chunks - plan.n_fast_outer, max_resident, 0);
       if(time_main) cudaEventRecord(evm1, stream);
       CUDA_TRY(cudaGetLastError());
     } else {
-      launch(0, plan.n_gen, 0, plan.n_fast_chunks, max_resident);
+      launch(0, plan.n_gen, 0, plan.n_fast_chunks, max_resident, 0);
       if(time_main) cudaEventRecord(evm1, stream);
       CUDA_TRY(cudaGetLastError());
       rc = cfg.arithmetic == LBM_B200_STRICT ? aux_kernels<true>(p, vout) : aux_kernels<false>(p, vout);
