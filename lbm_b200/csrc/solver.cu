@@ -437,9 +437,15 @@ struct Solver final : SolverBase {
       CUDA_TRY(cudaStreamWaitEvent(comm_stream, ev_outer, 0));
       cudaStream_t main_stream = stream;
       stream = comm_stream;
-      // a quarter of the resident CTA slots: the inner launch starts at once in the others, the outer cells still finish
-      // early enough for their populations to travel while the inner cells are being updated
-      launch(0, plan.n_gen_outer, 0, plan.n_fast_outer, max_resident / 4 > 0 ? max_resident / 4 : 1, 1);
+      // The outer launch gets a share of the resident CTA slots of about twice its share of the cells (at least 1/8): the
+      // inner launch starts at once in the other slots, and the outer cells still finish early enough for their
+      // populations to travel while the inner cells are being updated.
+      const double f_outer = static_cast<double>(plan.n_fast_outer * plan.CH + plan.n_gen_outer) / static_cast<double>(plan.n_owned);
+      double share = 2.0 * f_outer;
+      share = share < 0.125 ? 0.125 : (share > 1.0 ? 1.0 : share);
+      int cap_outer = static_cast<int>(max_resident * share);
+      if(cap_outer < 1) cap_outer = 1;
+      launch(0, plan.n_gen_outer, 0, plan.n_fast_outer, cap_outer, 1);
       rc = halo_exchange(f[dst].p, comm_stream);
       stream = main_stream;
       if(rc != LBM_B200_OK) return rc;
