@@ -115,7 +115,7 @@ struct Solver final : SolverBase {
   bool    first = true; // next step is step 0 of the reference loop (m_fold = initial condition)
   int     n_fast_blocks = 0, n_gen_blocks = 0, max_resident = 0;
   cudaStream_t comm_stream = nullptr;   // halo exchange runs here, overlapped with the update of the inner cells
-  cudaEvent_t  ev_outer = nullptr, ev_halo = nullptr;
+  cudaEvent_t  ev_outer = nullptr, ev_halo = nullptr, ev_pack = nullptr;
   bool         halo_pending = false;
   int64_t launches = 0, launches_main = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr;
@@ -127,6 +127,7 @@ struct Solver final : SolverBase {
     if(evm1) cudaEventDestroy(evm1);
     if(ev_outer) cudaEventDestroy(ev_outer);
     if(ev_halo) cudaEventDestroy(ev_halo);
+    if(ev_pack) cudaEventDestroy(ev_pack);
     if(comm_stream) cudaStreamDestroy(comm_stream);
   }
 
@@ -280,6 +281,7 @@ struct Solver final : SolverBase {
       CUDA_TRY(cudaStreamCreateWithPriority(&comm_stream, cudaStreamNonBlocking, prio_hi));
       CUDA_TRY(cudaEventCreateWithFlags(&ev_outer, cudaEventDisableTiming));
       CUDA_TRY(cudaEventCreateWithFlags(&ev_halo, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&ev_pack, cudaEventDisableTiming));
     }
 
     // ---- initialCondition(): vars = 0, boundary presets, rho = 1, f = fold = feq   (solver.cpp:267-295)
@@ -370,7 +372,7 @@ struct Solver final : SolverBase {
 
   // Outgoing populations of this step -> peers, theirs -> my ghost cells.  One pack kernel, one NCCL group of
   // send/recv pairs over NVLink, one unpack kernel, all on the solver's stream.
-  int halo_exchange(Real* buf, cudaStream_t stream) {
+  int halo_exchange(Real* buf, cudaStream_t stream, cudaEvent_t after_pack = nullptr) {
     if(in.peers.empty()) return LBM_B200_OK;
     auto& nc = lbm::nccl_api();
     const int64_t ns = static_cast<int64_t>(plan.send_index.size()), nr = static_cast<int64_t>(plan.recv_index.size());
@@ -378,6 +380,7 @@ struct Solver final : SolverBase {
       lbm::k_halo_pack<Real><<<static_cast<int>((ns + 255) / 256), 256, 0, stream>>>(buf, d_send_idx.p, ns, d_sendbuf.p);
       ++launches;
     }
+    if(after_pack != nullptr) CUDA_TRY(cudaEventRecord(after_pack, stream));
     const ncclDataType_t dt = sizeof(Real) == 8 ? ncclFloat64 : ncclFloat32;
     NCCL_TRY(nc.GroupStart());
     int64_t so = 0, ro = 0;
@@ -431,26 +434,18 @@ struct Solver final : SolverBase {
     if(time_main) cudaEventRecord(evm0, stream);
     int rc = LBM_B200_OK;
     if(overlap) {
-      // The outer cells (whatever a peer needs) are updated on the high-priority communication stream and sent right away;
-      // the inner cells are updated on the solver's stream at the same time and fill the GPU around them.
-      CUDA_TRY(cudaEventRecord(ev_outer, stream)); // everything this step reads is complete at this point of the solver's stream
+      // 1. outer cells (whatever a peer needs) with the whole GPU; 2. their populations are packed and travel (NCCL group on
+      // the high-priority communication stream) while 3. the inner cells are updated.  The inner launch is released by the
+      // same event that releases the NCCL kernel, so the (higher-priority, whole-SM-sized) NCCL CTAs are placed first and
+      // the persistent inner CTAs fill the remaining SMs; with ticket scheduling late inner CTAs just take fewer chunks.
+      launch(0, plan.n_gen_outer, 0, plan.n_fast_outer, max_resident, 1);
+      CUDA_TRY(cudaEventRecord(ev_outer, stream));
       CUDA_TRY(cudaStreamWaitEvent(comm_stream, ev_outer, 0));
-      cudaStream_t main_stream = stream;
-      stream = comm_stream;
-      // The outer launch gets a share of the resident CTA slots of about twice its share of the cells (at least 1/8): the
-      // inner launch starts at once in the other slots, and the outer cells still finish early enough for their
-      // populations to travel while the inner cells are being updated.
-      const double f_outer = static_cast<double>(plan.n_fast_outer * plan.CH + plan.n_gen_outer) / static_cast<double>(plan.n_owned);
-      double share = 2.0 * f_outer;
-      share = share < 0.125 ? 0.125 : (share > 1.0 ? 1.0 : share);
-      int cap_outer = static_cast<int>(max_resident * share);
-      if(cap_outer < 1) cap_outer = 1;
-      launch(0, plan.n_gen_outer, 0, plan.n_fast_outer, cap_outer, 1);
-      rc = halo_exchange(f[dst].p, comm_stream);
-      stream = main_stream;
+      rc = halo_exchange(f[dst].p, comm_stream, ev_pack);
       if(rc != LBM_B200_OK) return rc;
       CUDA_TRY(cudaEventRecord(ev_halo, comm_stream));
       halo_pending = true;
+      CUDA_TRY(cudaStreamWaitEvent(stream, ev_pack, 0));
       launch(plan.n_gen_outer, plan.n_gen - plan.n_gen_outer, plan.n_fast_outer, plan.n_fast_chunks - plan.n_fast_outer, max_resident, 0);
       if(time_main) cudaEventRecord(evm1, stream);
       CUDA_TRY(cudaGetLastError());
