@@ -25,6 +25,9 @@
  *   residual                      src/lbm/solver.cpp:233-263,809-815
  *   initial condition             src/lbm/solver.cpp:267-304
  *   lattice tables                src/lbm/constants.h:296-422
+ *   wet-node walls                src/lbm/bnd/bnd_wetnode.h:12-72 (limited distribution sets), src/lbm/bnd/bnd_dirichlet.h:134-248
+ *                                 (equilibrium), src/lbm/bnd/bnd_wall.h:101-306 (NEEM), :313-479 (NEBB, D2Q9 only),
+ *                                 src/lbm/moments.h:120-154 (density from a limited set)
  *
  * NOT pinned by the reference ("parity unpinned", new behaviour):
  *   - D3Q19 / D3Q27 runs: the reference compiles these templates but cannot reach them
@@ -46,7 +49,8 @@
 #define ORC_MAXD 3
 
 enum { ORC_BGK = 0, ORC_TRT = 1, ORC_MRT = 2 };
-enum { ORC_BC_BB = 1, ORC_BC_BB_TANGENTIAL = 2, ORC_BC_DIRICHLET_BB = 3, ORC_BC_PRESSURE = 4, ORC_BC_PERIODIC = 5 };
+enum { ORC_BC_BB = 1, ORC_BC_BB_TANGENTIAL = 2, ORC_BC_DIRICHLET_BB = 3, ORC_BC_PRESSURE = 4, ORC_BC_PERIODIC = 5,
+       ORC_BC_WALL_EQ = 6, ORC_BC_WALL_NEEM = 7, ORC_BC_WALL_NEBB = 8 };
 
 static const double kEps = 2.220446049250313e-16; /* GDoubleEps, include/common/sfcmm_types.h:50 */
 
@@ -112,6 +116,13 @@ typedef struct {
   int64_t* link;     /* ORC_BC_PERIODIC: n*ndist, bnd_periodic.h:59-98 */
   int*     linkdist; /* n*ndist */
   int*     nset;     /* n */
+  /* wet-node walls */
+  int      has_velocity;      /* configuration key "velocity" present */
+  int*     lim_n;             /* n: size of the limited set (0 marks a corner), bnd_wetnode.h:54-61 */
+  int*     lim_dist;          /* n*ndist: the set, ascending (std::set) */
+  double*  lim_const;         /* n*ndist */
+  int64_t* cell2bnd;          /* n: index used for entry k = LAST entry with the same cell (unordered_map, bnd_dirichlet.h:176-181) */
+  int64_t* ext;               /* NEEM: extrapolation cell per entry, bnd_wall.h:212-246 */
 } OrcBc;
 
 typedef struct {
@@ -125,6 +136,7 @@ typedef struct {
   double     omega_minus;     /* TRT: odd-moment rate */
   double     mrt_rates[ORC_MAXQ];
   double *   f, *fold, *feq, *vars, *varsold;
+  unsigned char* periodic; /* CellProperties::periodic, set when a periodic boundary condition is added (bnd.h:217-221) */
   OrcBc*     bc;
   int        nbc;
   /* forcing, solver.cpp:626-696 */
@@ -193,6 +205,7 @@ Orc* orc_create(int ndim, int ndist, int64_t ncells, const int64_t* nghbr, int s
   o->feq     = (double*)calloc(nq, sizeof(double));
   o->vars    = (double*)calloc(nv, sizeof(double));
   o->varsold = (double*)calloc(nv, sizeof(double));
+  o->periodic = (unsigned char*)calloc((size_t)ncells, 1);
   return o;
 }
 
@@ -282,6 +295,8 @@ int orc_add_bc_periodic(Orc* o, const int64_t* cells, const double* normals, int
   if(o->center == NULL) return -1;
   OrcBc* b    = new_bc(o, ORC_BC_PERIODIC, cells, normals, n);
   b->pressure = pressure;
+  for(int64_t k = 0; k < n; ++k) o->periodic[cells[k]] = 1; /* surfA.setProperty(periodic), bnd.h:219 */
+  for(int64_t k = 0; k < nconn; ++k) o->periodic[conn[k]] = 1; /* surfB.setProperty(periodic), bnd.h:220 */
   b->link     = (int64_t*)malloc(sizeof(int64_t) * (size_t)n * (size_t)L->ndist);
   b->linkdist = (int*)malloc(sizeof(int) * (size_t)n * (size_t)L->ndist);
   b->nset     = (int*)calloc((size_t)n, sizeof(int));
@@ -323,6 +338,75 @@ int orc_add_bc_periodic(Orc* o, const int64_t* cells, const double* normals, int
   return 0;
 }
 
+/* Wet-node wall family: kind = ORC_BC_WALL_EQ / _NEEM / _NEBB; has_velocity = the "velocity" key is present.
+ * LBMBnd_wallWetnode constructor, bnd_wetnode.h:24-63. */
+static int orthogonal(const OrcLattice* L, const double* normal, int dist) {
+  double dot = 0; /* constants.h:88-91 */
+  for(int d = 0; d < L->ndim; ++d) dot += normal[d] * L->c[dist][d];
+  return fabs(dot) <= kEps;
+}
+
+int orc_add_bc_wall_wetnode(Orc* o, int kind, const int64_t* cells, const double* normals, int64_t n, int has_velocity,
+                            const double* velocity) {
+  const OrcLattice* L = &o->L;
+  const int Q = L->ndist, D = L->ndim;
+  if(kind == ORC_BC_WALL_NEBB && !(D == 2 && Q == 9)) return -1; /* bnd_wall.h:325-328 */
+  OrcBc* b        = new_bc(o, kind, cells, normals, n);
+  b->has_velocity = has_velocity;
+  for(int d = 0; d < D; ++d) b->value[d] = has_velocity ? velocity[d] : 0.0;
+  b->lim_n     = (int*)calloc((size_t)n, sizeof(int));
+  b->lim_dist  = (int*)calloc((size_t)n * (size_t)Q, sizeof(int));
+  b->lim_const = (double*)calloc((size_t)n * (size_t)Q, sizeof(double));
+  b->cell2bnd  = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+  for(int64_t k = 0; k < n; ++k) {
+    const int64_t c   = cells[k];
+    const double* nrm = &b->normals[k * D];
+    double*       cst = &b->lim_const[k * Q];
+    int           m   = 0;
+    for(int dir = 0; dir < Q - 1; ++dir) {
+      const int     op     = L->opp[dir];
+      const int     per    = o->periodic[c];
+      const int64_t nb_opp = o->nghbr[c * o->stride + op];
+      if(in_direction(L, nrm, dir) && (per || nb_opp != -1)) {
+        b->lim_dist[k * Q + m++] = dir;
+        cst[dir]                 = 2;
+      } else if(orthogonal(L, nrm, dir) && (per || nb_opp != -1)) {
+        b->lim_dist[k * Q + m++] = dir;
+        cst[dir] = (o->nghbr[c * o->stride + dir] == -1 && !per) ? 2 : 1; /* corner, bnd_wetnode.h:43-50 */
+      }
+    }
+    int sumC = 0; /* std::accumulate(..., 0): integer accumulation */
+    for(int i = 0; i < Q; ++i) sumC = (int)(sumC + cst[i]);
+    if(sumC != Q - 1) {
+      m = 0; /* "we clear to mark a corner" */
+    } else {
+      b->lim_dist[k * Q + m++] = Q - 1;
+      cst[Q - 1]               = 1;
+    }
+    b->lim_n[k] = m;
+  }
+  for(int64_t k = 0; k < n; ++k) { /* cell2Bnd: the last entry of a cell wins */
+    int64_t idx = k;
+    for(int64_t j = n - 1; j > k; --j)
+      if(cells[j] == cells[k]) { idx = j; break; }
+    b->cell2bnd[k] = idx;
+  }
+  if(kind == ORC_BC_WALL_NEEM) {
+    b->ext = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+    for(int64_t k = 0; k < n; ++k) {
+      const double* nrm = &b->normals[k * D];
+      int           ex  = -1;
+      for(int d = 0; d < D && ex < 0; ++d) {
+        if(nrm[d] < 0) ex = 2 * d + 1;
+        else if(nrm[d] > 0) ex = 2 * d;
+      }
+      b->ext[k] = ex < 0 ? -1 : o->nghbr[cells[k] * o->stride + ex];
+      if(b->ext[k] == -1) return -2; /* TERMM("No valid extrapolation cellId"), bnd_wall.h:243-246 */
+    }
+  }
+  return 0;
+}
+
 /* solver.cpp:640-647: inlet = surface cube_-x, outlet = cube_+x, p_out = 1.0, p_in = 1.0 + gradient */
 int orc_set_forcing(Orc* o, const int64_t* inlet, int64_t ninlet, const int64_t* outlet, int64_t noutlet, double gradient) {
   if(o->center == NULL) return -1;
@@ -347,7 +431,13 @@ void orc_destroy(Orc* o) {
     free(o->bc[i].link);
     free(o->bc[i].linkdist);
     free(o->bc[i].nset);
+    free(o->bc[i].lim_n);
+    free(o->bc[i].lim_dist);
+    free(o->bc[i].lim_const);
+    free(o->bc[i].cell2bnd);
+    free(o->bc[i].ext);
   }
+  free(o->periodic);
   free(o->bc);
   free(o->nghbr);
   free(o->center);
@@ -547,6 +637,113 @@ static void bb_cell(Orc* o, int64_t c, const double* nrm, int mode, const double
   }
 }
 
+/* moments.h:120-154 */
+static void density_limited(Orc* o, int64_t c, const OrcBc* bc, int64_t idx, int noslip) {
+  const int Q = o->L.ndist, NV = o->nvar, D = o->L.ndim;
+  if(bc->lim_n[idx] == 0) return; /* corner: the density of the moments pass stays */
+  double rho = 0;
+  for(int m = 0; m < bc->lim_n[idx]; ++m) {
+    const int dist = bc->lim_dist[idx * Q + m];
+    rho += bc->lim_const[idx * Q + dist] * o->fold[c * Q + dist];
+  }
+  if(!noslip) {
+    const double* nrm = &bc->normals[idx * D];
+    for(int d = 0; d < D; ++d) {
+      if(nrm[d] > kEps) rho *= 1.0 / (1.0 + o->vars[c * NV + d]);
+      else if(nrm[d] < 0) rho *= 1.0 / (1.0 - o->vars[c * NV + d]);
+    }
+  }
+  o->vars[c * NV + D] = rho;
+}
+
+/* LBMBnd_DirichletEQ::apply<VALZERO>, bnd_dirichlet.h:211-241 */
+static void wall_eq_cell(Orc* o, const OrcBc* bc, int64_t k) {
+  const OrcLattice* L = &o->L;
+  const int Q = L->ndist, NV = o->nvar, D = L->ndim;
+  const int64_t c   = bc->cells[k];
+  const int64_t idx = bc->cell2bnd[k];
+  const int     valzero = !bc->has_velocity;
+  for(int d = 0; d < D; ++d) o->vars[c * NV + d] = bc->value[d];
+  density_limited(o, c, bc, idx, valzero);
+  if(valzero) {
+    for(int i = 0; i < Q; ++i) o->fold[c * Q + i] = default_eq(L->w[i], o->vars[c * NV + D], 0, 0);
+  } else {
+    eq_all(L, &o->fold[c * Q], o->vars[c * NV + D], &o->vars[c * NV]);
+  }
+}
+
+/* LBMBnd_wallNEBB, bnd_wall.h:366-466 (D2Q9 slots: 0 -x, 1 +x, 2 -y, 3 +y, 4 ++, 5 +-, 6 --, 7 -+) */
+static void wall_nebb(Orc* o, const OrcBc* bc) {
+  const int Q = 9, NV = 3, D = 2;
+  double*   fo = o->fold;
+  if(!bc->has_velocity) {
+    for(int64_t k = 0; k < bc->n; ++k)
+      for(int d = 0; d < D; ++d) o->vars[bc->cells[k] * NV + d] = 0;
+    for(int64_t k = 0; k < bc->n; ++k) density_limited(o, bc->cells[k], bc, k, 1);
+    for(int64_t k = 0; k < bc->n; ++k) {
+      const int64_t c = bc->cells[k];
+      for(int dist = 0; dist < 4; ++dist)
+        if(o->nghbr[c * o->stride + dist] == -1) fo[c * Q + (dist ^ 1)] = fo[c * Q + dist];
+    }
+    /* bnd_wall.h:393-414: the entry index is never advanced inside this loop -> the normal of entry 0 is used for all cells */
+    const double* nrm = &bc->normals[0];
+    for(int64_t k = 0; k < bc->n; ++k) {
+      double* f = &fo[bc->cells[k] * Q];
+      if(nrm[0] < 0) {
+        f[6] = f[4] + 0.5 * (f[3] - f[2]);
+        f[7] = f[5] - 0.5 * (f[3] - f[2]);
+      } else if(nrm[0] > 0) {
+        f[4] = f[6] - 0.5 * (f[3] - f[2]);
+        f[5] = f[7] + 0.5 * (f[3] - f[2]);
+      } else if(nrm[1] < 0) {
+        f[5] = f[7] - 0.5 * (f[1] - f[0]);
+        f[6] = f[4] + 0.5 * (f[1] - f[0]);
+      } else if(nrm[1] > 0) {
+        f[7] = f[5] + 0.5 * (f[1] - f[0]);
+        f[4] = f[6] - 0.5 * (f[1] - f[0]);
+      }
+    }
+  } else {
+    const double* wv = bc->value;
+    for(int64_t k = 0; k < bc->n; ++k) {
+      const int64_t c = bc->cells[k];
+      density_limited(o, c, bc, k, 0);
+      for(int d = 0; d < D; ++d) o->vars[c * NV + d] = wv[d];
+    }
+    for(int64_t k = 0; k < bc->n; ++k) {
+      const int64_t c   = bc->cells[k];
+      const double* nrm = &bc->normals[k * D];
+      for(int dist = 0; dist < 4; ++dist) {
+        const int dir = dist / 2;
+        if(o->nghbr[c * o->stride + dist] == -1 && fabs(nrm[dir]) > 0) {
+          fo[c * Q + (dist ^ 1)] = fo[c * Q + dist];
+          if(nrm[dir] < 0) fo[c * Q + (dist ^ 1)] -= 2.0 / 3.0 * o->vars[c * NV + D] * wv[dir];
+          else fo[c * Q + (dist ^ 1)] += 2.0 / 3.0 * o->vars[c * NV + D] * wv[dir];
+        }
+      }
+    }
+    for(int64_t k = 0; k < bc->n; ++k) {
+      const int64_t c   = bc->cells[k];
+      const double  rho = o->vars[c * NV + D];
+      const double* nrm = &bc->normals[k * D];
+      double*       f   = &fo[c * Q];
+      if(nrm[0] > 0) {
+        f[6] = f[4] + 0.5 * (f[3] - f[2]) - 0.5 * rho * wv[1] - 1.0 / 6.0 * rho * wv[0];
+        f[7] = f[5] - 0.5 * (f[3] - f[2]) + 0.5 * rho * wv[1] - 1.0 / 6.0 * rho * wv[0];
+      } else if(nrm[0] < 0) {
+        f[4] = f[6] - 0.5 * (f[3] - f[2]) + 0.5 * rho * wv[1] + 1.0 / 6.0 * rho * wv[0];
+        f[5] = f[7] + 0.5 * (f[3] - f[2]) - 0.5 * rho * wv[1] + 1.0 / 6.0 * rho * wv[0];
+      } else if(nrm[1] > 0) {
+        f[5] = f[7] - 0.5 * (f[1] - f[0]) + 0.5 * rho * wv[0] - 1.0 / 6.0 * rho * wv[1];
+        f[6] = f[4] + 0.5 * (f[1] - f[0]) - 0.5 * rho * wv[0] - 1.0 / 6.0 * rho * wv[1];
+      } else if(nrm[1] < 0) {
+        f[7] = f[5] + 0.5 * (f[1] - f[0]) - 0.5 * rho * wv[0] + 1.0 / 6.0 * rho * wv[1];
+        f[4] = f[6] - 0.5 * (f[1] - f[0]) + 0.5 * rho * wv[0] + 1.0 / 6.0 * rho * wv[1];
+      }
+    }
+  }
+}
+
 /* solver.cpp:743-755 -> bnd.h:60-65 */
 static void pass_apply(Orc* o) {
   const OrcLattice* L = &o->L;
@@ -586,6 +783,33 @@ static void pass_apply(Orc* o) {
           }
         }
         break;
+      case ORC_BC_WALL_EQ:
+        for(int64_t k = 0; k < bc->n; ++k) wall_eq_cell(o, bc, k);
+        break;
+      case ORC_BC_WALL_NEEM: { /* bnd_wall.h:262-298 */
+        for(int64_t k = 0; k < bc->n; ++k) wall_eq_cell(o, bc, k);
+        for(int64_t k = 0; k < bc->n; ++k) { /* calcDensity, moments.h:68-76 */
+          const int64_t e = bc->ext[k];
+          double rho = o->fold[e * Q];
+          for(int i = 1; i < Q; ++i) rho += o->fold[e * Q + i];
+          o->vars[e * NV + D] = rho;
+        }
+        for(int64_t k = 0; k < bc->n; ++k) { /* calcVelocity, moments.h:17-35 */
+          const int64_t e = bc->ext[k];
+          for(int d = 0; d < D; ++d) {
+            double v = 0;
+            for(int i = 0; i < Q - 1; ++i) v += L->c[i][d] * o->fold[e * Q + i];
+            o->vars[e * NV + d] = v / o->vars[e * NV + D];
+          }
+        }
+        for(int64_t k = 0; k < bc->n; ++k) {
+          const int64_t c = bc->cells[k], e = bc->ext[k];
+          for(int i = 0; i < Q; ++i)
+            o->fold[c * Q + i] += o->fold[e * Q + i] - eq_dist(L, i, o->vars[e * NV + D], &o->vars[e * NV], 0);
+        }
+        break;
+      }
+      case ORC_BC_WALL_NEBB: wall_nebb(o, bc); break;
       default: break; /* periodic: apply is empty (bnd_periodic.h:208-209) */
     }
   }

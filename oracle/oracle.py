@@ -39,6 +39,7 @@ def lib():
         L.orc_add_bc_pressure.argtypes = [vp, pi64, pdbl, i64, dbl]
         L.orc_add_bc_periodic.argtypes = [vp, pi64, pdbl, i64, pi64, i64, dbl]
         L.orc_set_forcing.argtypes = [vp, pi64, i64, pi64, i64, dbl]
+        L.orc_add_bc_wall_wetnode.argtypes = [vp, i32, pi64, pdbl, i64, i32, pdbl]
         L.orc_destroy.argtypes = [vp]
         L.orc_init.argtypes = [vp]
         L.orc_step.argtypes = [vp, i64]
@@ -109,6 +110,15 @@ class Oracle:
                                        float(pressure))
         if rc != 0:
             raise ValueError("periodic BC needs set_geometry first")
+
+    def add_wall_wetnode(self, model, cells, normals, velocity=None):
+        kind = {"equilibrium": 6, "neem": 7, "nebb": 8}[model]
+        v = _f64(np.zeros(self.ndim) if velocity is None else velocity)
+        rc = lib().orc_add_bc_wall_wetnode(self._h, kind, _i64(cells), _f64(normals), len(cells), int(velocity is not None), v)
+        if rc == -1:
+            raise ValueError("Not implemented for this distribution!")
+        if rc == -2:
+            raise ValueError("No valid extrapolation cellId")
 
     def set_forcing(self, inlet, outlet, gradient):
         rc = lib().orc_set_forcing(self._h, _i64(inlet), len(inlet), _i64(outlet), len(outlet), float(gradient))

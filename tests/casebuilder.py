@@ -48,6 +48,8 @@ class CaseSpec:
                 solver.add_pressure(bc["cells"], bc["normals"], bc["pressure"])
             elif k == "periodic":
                 solver.add_periodic(bc["cells"], bc["normals"], bc["connected"], bc["pressure"])
+            elif k == "wall_wetnode":
+                solver.add_wall_wetnode(bc["model"], bc["cells"], bc["normals"], bc["velocity"])
             else:
                 raise ValueError(k)
         if self.forcing is not None:
@@ -106,10 +108,14 @@ def bcs_from_config(solver_cfg, surfaces, ndim):
                 bcs.append(dict(kind="periodic", cells=cells, normals=normals, connected=conn,
                                 pressure=float(conf.get("pressure", "nan"))))
             elif t == "wall":
-                if conf["model"] != "bounceback":
-                    raise NotImplementedError(f"wall model {conf['model']} (SURVEY section 8f N1)")
-                bcs.append(dict(kind="wall_bb", cells=cells, normals=normals,
-                                tangential=float(conf.get("tangentialVelocity", 0.0))))
+                if conf["model"] == "bounceback":
+                    bcs.append(dict(kind="wall_bb", cells=cells, normals=normals,
+                                    tangential=float(conf.get("tangentialVelocity", 0.0))))
+                elif conf["model"] in ("equilibrium", "neem", "nebb"):
+                    vel = np.array(conf["velocity"], float)[:ndim] if "velocity" in conf else None
+                    bcs.append(dict(kind="wall_wetnode", model=conf["model"], cells=cells, normals=normals, velocity=vel))
+                else:
+                    raise ValueError(f"Invalid wall boundary model: {conf['model']}")
             elif t == "pressure":
                 bcs.append(dict(kind="pressure", cells=cells, normals=normals, pressure=float(conf["pressure"])))
             elif t == "dirichlet" and conf["model"] == "bounceback":
@@ -134,7 +140,7 @@ def load_golden(name):
     lo, hi = geometry_bbox(cfg["geometry"], ndim)
     l0 = float(np.max(hi - lo))
     spec = CaseSpec(name=name, ndim=ndim, ndist=ndist, nghbr=g["nghbr"].astype(np.int64), omega=float(g["omega"]),
-                    center=g["center"], bbmin=lo, bbmax=hi, cell_length=l0 / 2.0 ** int(g["maxlvl"]), golden=g)
+                    center=g["center"], bbmin=lo, bbmax=hi, cell_length=float(g["cell_length"]), golden=g)
     spec.bcs, spec.forcing = bcs_from_config(cfg["solver"], surfaces, ndim)
     spec.config = cfg
     spec.surfaces = surfaces

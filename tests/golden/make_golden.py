@@ -41,6 +41,17 @@ CASES = {
     "poiseuille_bnd": ("poiseuille/poiseuille_bnd.json", 100, [1, 10, 100], True),
     "step_ns": ("step/step_ns.json", 200, [1, 10, 200], True),
     "sphere_ns": ("sphere/sphere_ns.json", 300, [1, 300], False),
+    # wet-node wall family and the remaining run.sh Navier-Stokes cases
+    "couette_bnd_eq": ("couette/couette_bnd_eq.json", 100, [1, 2, 10, 100], True),
+    "couette_bnd_eq2": ("couette/couette_bnd_eq2.json", 100, [1, 10, 100], True),
+    "couette_bnd_eq_aligned": ("couette/couette_bnd_eq_aligned.json", 100, [1, 10, 100], True),
+    "couette_bnd_NEEM": ("couette/couette_bnd_NEEM.json", 100, [1, 2, 10, 100], True),
+    "couette_bnd_NEBB": ("couette/couette_bnd_NEBB.json", 100, [1, 2, 10, 100], True),
+    "poiseuille_bnd_eq": ("poiseuille/poiseuille_bnd_eq.json", 100, [1, 10, 100], True),
+    "poiseuille_bnd_NEEM": ("poiseuille/poiseuille_bnd_NEEM.json", 100, [1, 10, 100], True),
+    "poiseuille_bnd_NEBB": ("poiseuille/poiseuille_bnd_NEBB.json", 100, [1, 10, 100], True),
+    "poiseuille_bnd_pressure": ("poiseuille/poiseuille_bnd_pressure.json", 100, [1, 2, 10, 100], True),
+    "poiseuille_bnd_pressure_neem2": ("poiseuille/poiseuille_bnd_pressure_neem2.json", 100, [1, 10, 100], True),
 }
 
 
@@ -90,6 +101,7 @@ def run_case(name):
             "config_orig_json": np.array(original),  # the reference's test configuration, unmodified
             "ncells": n, "ndim": ndim, "ndist": q, "nvar": nvar, "nnghbr": nn,
             "omega": float(meta["omega"]), "nu": float(meta["nu"]), "maxlvl": int(meta["maxlvl"]),
+            "cell_length": float(meta["celllength"]),  # grid().lengthOnLvl(maxLvl()) of the solver grid (after alignment)
             "nghbr": np.fromfile(os.path.join(d, "nghbr.i64"), dtype=np.int64).reshape(n, nn).astype(np.int32),
             "props": np.fromfile(os.path.join(d, "props.u64"), dtype=np.uint64).astype(np.uint16),
             "center": np.fromfile(os.path.join(d, "center.f64"), dtype=np.float64).reshape(n, ndim),

@@ -10,7 +10,11 @@ import pytest
 
 from casebuilder import load_golden, omega_from_config
 
-CASES = ["couette", "couette_bnd", "couette_bnd_bbDirichlet", "poiseuille", "poiseuille_bnd", "step_ns", "sphere_ns"]
+CASES = ["couette", "couette_bnd", "couette_bnd_bbDirichlet", "poiseuille", "poiseuille_bnd", "step_ns", "sphere_ns",
+         # wet-node wall family + the remaining Navier-Stokes cases of the reference's test/run.sh
+         "couette_bnd_eq", "couette_bnd_eq2", "couette_bnd_eq_aligned", "couette_bnd_NEEM", "couette_bnd_NEBB",
+         "poiseuille_bnd_eq", "poiseuille_bnd_NEEM", "poiseuille_bnd_NEBB", "poiseuille_bnd_pressure",
+         "poiseuille_bnd_pressure_neem2"]
 
 
 def sha(a):
