@@ -9,8 +9,8 @@
 //   SolverGrid::load    leaf/bndry properties (src/cartesiangrid.h:502-546), named boundary surfaces with first-come
 //                       (cell,dir) assignment and last-normal-wins (:553-603, src/common/surface.h:52-55), grid-level periodic
 //                       links (:608-706), diagonal neighbours by composition of axis steps (:451-493)
-// Supported: partitionLevel == uniformLevel == maxRfnmtLvl (true for every reference configuration); multi-level grids and
-// alignNodesWithSurface are SURVEY.md section 8f rows N3 and are rejected with a clear error.
+// Supported: partitionLevel == uniformLevel == maxRfnmtLvl (true for every reference configuration), with or without
+// alignNodesWithSurface; multi-level grids are SURVEY.md section 8f row N3 and are rejected with a clear error.
 #pragma once
 #include <algorithm>
 #include <array>
@@ -59,7 +59,9 @@ class GridGen {
   double bbmin[3] = {0, 0, 0}, bbmax[3] = {0, 0, 0}, cog[3] = {0, 0, 0};
   double length_on_level[64] = {0};
   std::shared_ptr<GeometryManager> geom;
-  std::vector<GenCell> cells; // final level, SFC order
+  std::vector<GenCell> cells; // final level, SFC order (after alignment: with the holes of deleted cells filled from the end)
+  bool   align = false;
+  int    align_dir = 1;
 
   void configure(const Json& cfg) {
     ndim = static_cast<int>(cfg.at("dim").as_int());
@@ -70,8 +72,9 @@ class GridGen {
     if(maxr < uni) throw std::runtime_error("Invalid definition of grid level uniformLevel >= maxRfnmtLvl");
     if(part != uni || maxr != uni)
       throw std::runtime_error("multi-level grids (partitionLevel < uniformLevel or maxRfnmtLvl > uniformLevel) are not supported yet");
-    if(cfg.opt_bool("alignNodesWithSurface", false))
-      throw std::runtime_error("alignNodesWithSurface is not supported yet");
+    align = cfg.opt_bool("alignNodesWithSurface", false);
+    align_dir = static_cast<int>(cfg.opt_int("alignDir", 1));
+    if(align && (align_dir < 0 || align_dir >= ndim)) throw std::runtime_error("Invalid alignDir");
     level = static_cast<int>(uni);
     geom  = std::make_shared<GeometryManager>();
     if(!cfg.has("geometry")) throw std::runtime_error("The required configuration value is missing: geometry");
@@ -210,7 +213,61 @@ class GridGen {
         if(cells[i].nghbr[dir] != -1) cells[i].nghbr[dir] = newpos[cells[i].nghbr[dir]];
       for(int c = 0; c < 8; ++c) cells[i].child[c] = -1;
     }
+    if(align) transform_to_extent();
   }
+
+ private:
+  // transformMaxRfnmtLvlToExtent, cartesiangrid_generation.h:256-304: stretch the cell centres so that the outermost
+  // centres lie ON the bounding box in alignDir (all directions for a square domain), scale the cell length, then delete what
+  // is now outside (deleteOutsideCells<CHECKALL = true>, :508-525,556-561)
+  void transform_to_extent() {
+    const int NN = 2 * ndim;
+    double emin[3], emax[3];
+    for(int d = 0; d < ndim; ++d) {
+      emin[d] = std::numeric_limits<double>::max();
+      emax[d] = std::numeric_limits<double>::min(); // sic: the smallest positive double, as in the reference
+    }
+    for(const GenCell& c : cells)
+      for(int d = 0; d < ndim; ++d) {
+        if(emin[d] > c.center[d]) emin[d] = c.center[d];
+        if(emax[d] < c.center[d]) emax[d] = c.center[d];
+      }
+    bool identical = true;
+    for(int d = 0; d < ndim && identical; ++d)
+      for(int e = d + 1; e < ndim; ++e)
+        if(!(std::abs(emin[d] - emin[e]) < kEps) || !(std::abs(emax[d] - emax[e]) < kEps)) { identical = false; break; }
+    const double t = bbmax[align_dir] / (emax[align_dir] - emin[align_dir]);
+    for(GenCell& c : cells)
+      for(int d = 0; d < ndim; ++d) {
+        if(d == align_dir || identical) c.center[d] = c.center[d] * t - (t * emax[d] - bbmax[d]);
+        else c.center[d] = c.center[d] * t;
+      }
+    length_on_level[level] *= t;
+    const double len = length_on_level[level];
+    for(GenCell& c : cells) {
+      c.bndry  = geom->cut_with_cell(c.center, len);
+      c.inside = c.bndry || geom->point_inside(c.center);
+    }
+    int64_t end = static_cast<int64_t>(cells.size());
+    for(int64_t i = end - 1; i >= 0; --i) {
+      if(cells[i].inside) continue;
+      for(int dir = 0; dir < NN; ++dir) {
+        const int64_t nb = cells[i].nghbr[dir];
+        if(nb != -1) cells[nb].nghbr[dir ^ 1] = -1;
+      }
+      if(i != end - 1) {
+        cells[i] = cells[end - 1];
+        for(int dir = 0; dir < NN; ++dir) {
+          const int64_t nb = cells[i].nghbr[dir];
+          if(nb != -1) cells[nb].nghbr[dir ^ 1] = i;
+        }
+      }
+      --end;
+    }
+    cells.resize(static_cast<size_t>(end));
+  }
+
+ public:
 };
 
 struct Surface {

@@ -10,7 +10,10 @@ import pytest
 from casebuilder import load_golden
 from lbm_b200 import host_api
 
-CASES = ["couette", "couette_bnd", "couette_bnd_bbDirichlet", "poiseuille", "poiseuille_bnd", "step_ns", "sphere_ns"]
+CASES = ["couette", "couette_bnd", "couette_bnd_bbDirichlet", "poiseuille", "poiseuille_bnd", "step_ns", "sphere_ns",
+         "couette_bnd_eq", "couette_bnd_eq2", "couette_bnd_eq_aligned", "couette_bnd_NEEM", "couette_bnd_NEBB",
+         "poiseuille_bnd_eq", "poiseuille_bnd_NEEM", "poiseuille_bnd_NEBB", "poiseuille_bnd_pressure",
+         "poiseuille_bnd_pressure_neem2"]  # the *_aligned / poiseuille_bnd_* cases use alignNodesWithSurface
 
 
 @pytest.mark.parametrize("name", CASES)
