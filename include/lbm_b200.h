@@ -93,6 +93,12 @@ int lbm_b200_add_wall_bb(lbm_b200_solver* s, const int64_t* cells, const double*
 /* LBMBnd_DirichletBB (src/lbm/bnd/bnd_dirichlet.h:24-121); value[ndim] = wall velocity. */
 int lbm_b200_add_dirichlet_bb(lbm_b200_solver* s, const int64_t* cells, const double* normals, int64_t n,
                               const double* value);
+/* Wet-node walls: LBMBnd_wallEq / LBMBnd_wallNEEM / LBMBnd_wallNEBB (src/lbm/bnd/bnd_wall.h:101-479; NEBB is D2Q9 only).
+ * has_velocity = the configuration has a "velocity" key (velocity[ndim]); without it the no-slip variants are used.
+ * A solver that contains one of these runs the reference's passes in the reference's order on the GPU. */
+enum { LBM_B200_WALL_EQUILIBRIUM = 0, LBM_B200_WALL_NEEM = 1, LBM_B200_WALL_NEBB = 2 };
+int lbm_b200_add_wall_wetnode(lbm_b200_solver* s, int32_t model, const int64_t* cells, const double* normals, int64_t n,
+                              int32_t has_velocity, const double* velocity);
 /* LBMBnd_Pressure, anti-bounce-back (src/lbm/bnd/bnd_pressure.h:12-113). */
 int lbm_b200_add_pressure(lbm_b200_solver* s, const int64_t* cells, const double* normals, int64_t n, double pressure);
 /* LBMBnd_Periodic (src/lbm/bnd/bnd_periodic.h:175-215); connected = cell list of the connected surface;

@@ -82,6 +82,7 @@ def load_library():
     L.lbm_b200_add_wall_bb.argtypes = [vp, pi64, pdbl, i64, dbl]
     L.lbm_b200_add_dirichlet_bb.argtypes = [vp, pi64, pdbl, i64, pdbl]
     L.lbm_b200_add_pressure.argtypes = [vp, pi64, pdbl, i64, dbl]
+    L.lbm_b200_add_wall_wetnode.argtypes = [vp, i32, pi64, pdbl, i64, i32, pdbl]
     L.lbm_b200_add_periodic.argtypes = [vp, pi64, pdbl, i64, pi64, i64, dbl]
     L.lbm_b200_set_forcing.argtypes = [vp, pi64, i64, pi64, i64, dbl]
     L.lbm_b200_set_stream.argtypes = [vp, vp]
@@ -173,6 +174,12 @@ class Solver:
 
     def add_dirichlet_bb(self, cells, normals, value):
         self._check(self._lib.lbm_b200_add_dirichlet_bb(self._h, _i64(cells), _f64(normals), len(cells), _f64(value)))
+
+    def add_wall_wetnode(self, model, cells, normals, velocity=None):
+        kind = {"equilibrium": 0, "neem": 1, "nebb": 2}[model]
+        v = _f64(np.zeros(self.ndim) if velocity is None else velocity)
+        self._check(self._lib.lbm_b200_add_wall_wetnode(self._h, kind, _i64(cells), _f64(normals), len(cells),
+                                                        int(velocity is not None), v))
 
     def add_pressure(self, cells, normals, pressure):
         self._check(self._lib.lbm_b200_add_pressure(self._h, _i64(cells), _f64(normals), len(cells), float(pressure)))

@@ -33,7 +33,8 @@ namespace lbm {
 
 static constexpr double kEps = std::numeric_limits<double>::epsilon(); // GDoubleEps, include/common/sfcmm_types.h:50
 
-enum BcKind { BC_WALL_BB = 1, BC_WALL_BB_TANGENTIAL = 2, BC_DIRICHLET_BB = 3, BC_PRESSURE = 4, BC_PERIODIC = 5 };
+enum BcKind { BC_WALL_BB = 1, BC_WALL_BB_TANGENTIAL = 2, BC_DIRICHLET_BB = 3, BC_PRESSURE = 4, BC_PERIODIC = 5,
+              BC_WALL_EQ = 6, BC_WALL_NEEM = 7, BC_WALL_NEBB = 8 }; // 6..8: wet-node walls, handled by sequential.cuh
 
 struct BcInput {
   int                  kind = 0;
@@ -43,6 +44,7 @@ struct BcInput {
   double               tangential = 0;
   double               pressure   = std::numeric_limits<double>::quiet_NaN();
   std::vector<int64_t> connected; // periodic
+  bool                 has_velocity = false; // wet-node walls: the "velocity" key is present (value[] holds it)
 };
 
 struct PlanInput {
@@ -177,6 +179,46 @@ inline void build_template(const LatticeRT& L, std::vector<uint16_t>& tmpl, bool
   }
 }
 
+// LBMBndCell_periodic::init (bnd_periodic.h:31-98) for entry k of a periodic boundary condition: the outward directions whose
+// tangentially shifted target stays inside the bounding box, and for each the first cell of the connected surface whose
+// centre matches the shifted centre in ANY coordinate.  Returns false (with *err) where the reference would abort.
+inline bool periodic_links(const PlanInput& in, const BcInput& bc, int64_t k, int* setd, int64_t* links, int* nset, std::string* err) {
+  const LatticeRT& L = in.L;
+  const int D = L.D, Q = L.Q;
+  const double  maxMatch = 10 * kEps;
+  const int64_t c   = bc.cells[k];
+  const double* nrm = &bc.normals[k * D];
+  const double* ctr = &in.center[c * D];
+  int ns = 0;
+  for(int dist = 0; dist < Q; ++dist) {
+    if(!in_direction(L, nrm, dist)) continue;
+    bool inside = true;
+    for(int d = 0; d < D; ++d) {
+      const double x = std::abs(nrm[d]) > 0 ? in.bbmin[d] : ctr[d] + L.c[dist][d] * in.cell_length;
+      if(x < in.bbmin[d] || x > in.bbmax[d]) inside = false;
+    }
+    if(inside) setd[ns++] = dist;
+  }
+  for(int id = 0; id < ns; ++id) {
+    double ca[3];
+    for(int d = 0; d < D; ++d) ca[d] = std::abs(nrm[d]) > 0 ? ctr[d] : ctr[d] + L.c[setd[id]][d] * in.cell_length;
+    int64_t link = -1;
+    for(size_t q = 0; q < bc.connected.size() && link < 0; ++q) {
+      const double* cb = &in.center[bc.connected[q] * D];
+      for(int d = 0; d < D; ++d)
+        if(std::abs(ca[d] - cb[d]) <= maxMatch) { link = bc.connected[q]; break; }
+    }
+    if(link < 0) { *err = "periodic boundary: no cell to link"; return false; }
+    links[id] = link;
+  }
+  if(ns == 0) { *err = "periodic boundary cell without outward direction"; return false; }
+  for(int a = 0; a < ns; ++a)
+    for(int b = a + 1; b < ns; ++b)
+      if(links[a] == links[b]) { *err = "Invalid periodic bnd (cell has been linked twice)"; return false; } // bnd_periodic.h:158-166
+  *nset = ns;
+  return true;
+}
+
 struct SlotDesc {
   int     kind;      // LinkKind, or -1 for "dynamic value of periodic-with-pressure"
   int64_t a = 0;     // COPY: src cell (ref id); ABB: entry id; VALUE(dyn): value index
@@ -210,6 +252,8 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
     }
   }
 
+  for(const BcInput& bc : in.bcs)
+    if(bc.kind >= BC_WALL_EQ) { P.error = "internal: wet-node walls are handled by the sequential path"; return false; }
   // ---- 2. boundary conditions, in the reference's order: preApply writes, then the push, then apply writes
   std::unordered_map<int64_t, SlotDesc> over;  // slot key c*Q+j -> final descriptor
   auto key = [&](int64_t c, int j) { return c * Q + j; };
@@ -220,37 +264,11 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
     if(bc.kind != BC_PERIODIC) continue;
     if(in.center.empty()) { P.error = "periodic boundary condition needs set_geometry"; return false; }
     const int64_t nb = static_cast<int64_t>(bc.cells.size());
-    const double  maxMatch = 10 * kEps;
     for(int64_t k = 0; k < nb; ++k) {
-      const int64_t c   = bc.cells[k];
-      const double* nrm = &bc.normals[k * D];
-      const double* ctr = &in.center[c * D];
-      // bnd_periodic.h:42-57: outward directions whose tangentially shifted target stays inside the bounding box
-      int    setd[27], ns = 0;
-      for(int dist = 0; dist < Q; ++dist) {
-        if(!in_direction(L, nrm, dist)) continue;
-        bool inside = true;
-        for(int d = 0; d < D; ++d) {
-          const double x = std::abs(nrm[d]) > 0 ? in.bbmin[d] : ctr[d] + L.c[dist][d] * in.cell_length;
-          if(x < in.bbmin[d] || x > in.bbmax[d]) inside = false;
-        }
-        if(inside) setd[ns++] = dist;
-      }
-      // bnd_periodic.h:59-98: first cell of the connected surface that matches in ANY coordinate
+      const int64_t c = bc.cells[k];
+      int     setd[27], ns = 0;
       int64_t links[27];
-      for(int id = 0; id < ns; ++id) {
-        double ca[3];
-        for(int d = 0; d < D; ++d) ca[d] = std::abs(nrm[d]) > 0 ? ctr[d] : ctr[d] + L.c[setd[id]][d] * in.cell_length;
-        int64_t link = -1;
-        for(size_t q = 0; q < bc.connected.size() && link < 0; ++q) {
-          const double* cb = &in.center[bc.connected[q] * D];
-          for(int d = 0; d < D; ++d)
-            if(std::abs(ca[d] - cb[d]) <= maxMatch) { link = bc.connected[q]; break; }
-        }
-        if(link < 0) { P.error = "periodic boundary: no cell to link"; return false; }
-        links[id] = link;
-      }
-      if(ns == 0) { P.error = "periodic boundary cell without outward direction"; return false; }
+      if(!periodic_links(in, bc, k, setd, links, &ns, &P.error)) return false;
       if(!std::isnan(bc.pressure)) {
         // bnd_periodic.h:101-108: all Q populations of the first linked cell get a recomputed value
         PerPEntry e;

@@ -14,6 +14,7 @@
 #include "plan.hpp"
 #include "grid_box.hpp"
 #include "nccl_dyn.hpp"
+#include "sequential.cuh"
 
 namespace {
 
@@ -664,6 +665,375 @@ struct Solver final : SolverBase {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Reference-order pipeline (sequential.cuh) behind the same SolverBase interface: used when a configuration contains a
+// wet-node wall, whose result depends on the order in which boundary conditions touch a cell.
+template <class L>
+struct SequentialSolver final : SolverBase {
+  static constexpr int Q = L::Q, D = L::D, NV = L::D + 1, QM = L::Q - 1;
+  DevBuf<double>  d_f, d_fold, d_feq, d_vars, d_varsold, d_scratch, d_partial;
+  DevBuf<int32_t> d_pull;
+  DevBuf<int64_t> d_nghbr;
+  DevBuf<lbm::ForceEntry> d_force;
+  std::vector<lbm::seq::BcDev> bcs;
+  // owners of the per-BC device arrays
+  std::vector<std::unique_ptr<DevBuf<int64_t>>> keep_i64;
+  std::vector<std::unique_ptr<DevBuf<double>>>  keep_f64;
+  std::vector<std::unique_ptr<DevBuf<int>>>     keep_i32;
+  int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+
+  template <class T, class Keep>
+  const T* up(Keep& keep, const std::vector<T>& h, cudaError_t* err) {
+    keep.emplace_back(new DevBuf<T>());
+    std::vector<T> tmp = h;
+    if(tmp.empty()) tmp.resize(1);
+    cudaError_t e = keep.back()->upload(tmp);
+    if(e != cudaSuccess) *err = e;
+    return keep.back()->p;
+  }
+
+  lbm::seq::State state() const {
+    lbm::seq::State s{};
+    s.f = d_f.p; s.fold = d_fold.p; s.feq = d_feq.p; s.vars = d_vars.p; s.varsold = d_varsold.p;
+    s.pull = d_pull.p; s.nghbr = d_nghbr.p; s.stride = QM; s.n = in.n;
+    s.omega = cfg.omega; s.om1 = 1 - cfg.omega; s.omega_minus = cfg.omega_minus;
+    for(int i = 0; i < 27; ++i) s.rates[i] = cfg.mrt_rates[i];
+    return s;
+  }
+  static int blocks(int64_t n) { return static_cast<int>((n + 127) / 128); }
+
+  int init() override {
+    const lbm::LatticeRT& LR = in.L;
+    const int64_t N = in.n;
+    if(cfg.precision != LBM_B200_FP64) return fail(LBM_B200_EUNSUP, "wet-node wall boundary conditions run in fp64 only");
+    if(!in.peers.empty() || in.n_ghost > 0) return fail(LBM_B200_EUNSUP, "wet-node wall boundary conditions are not partitioned yet");
+    if(in.nghbr.empty()) return fail(LBM_B200_ESTATE, "no topology set");
+    CUDA_TRY(cudaSetDevice(cfg.device));
+    auto NB = [&](int64_t c, int j) -> int64_t { return in.nghbr[static_cast<size_t>(c) * QM + j]; };
+    // inverse of the push table (the highest source wins, like the reference's serial loop)
+    std::vector<int32_t> pull(static_cast<size_t>(N) * QM, -1);
+    for(int64_t c = 0; c < N; ++c)
+      for(int j = 0; j < QM; ++j) {
+        const int64_t t = NB(c, j);
+        if(t >= 0) pull[static_cast<size_t>(t) * QM + j] = static_cast<int32_t>(c);
+      }
+    std::vector<int64_t> nb64(in.nghbr.begin(), in.nghbr.end());
+    CUDA_TRY(d_pull.upload(pull));
+    CUDA_TRY(d_nghbr.upload(nb64));
+    const size_t nq = static_cast<size_t>(N) * Q, nv = static_cast<size_t>(N) * NV;
+    CUDA_TRY(d_f.alloc(nq)); CUDA_TRY(d_fold.alloc(nq)); CUDA_TRY(d_feq.alloc(nq));
+    CUDA_TRY(d_vars.alloc(nv)); CUDA_TRY(d_varsold.alloc(nv)); CUDA_TRY(d_scratch.alloc(nq));
+    CUDA_TRY(d_partial.alloc(static_cast<size_t>(NV) * 64));
+    CUDA_TRY(cudaMemset(d_varsold.p, 0, d_varsold.bytes()));
+
+    std::vector<char>   periodic(static_cast<size_t>(N), 0); // CellProperties::periodic, set in boundary-condition order
+    std::vector<double> vars0(nv, 0.0);
+    cudaError_t cerr = cudaSuccess;
+    for(const lbm::BcInput& bc : in.bcs) {
+      lbm::seq::BcDev b{};
+      const int64_t n = static_cast<int64_t>(bc.cells.size());
+      b.kind = bc.kind;
+      b.n = n;
+      b.cells = up<int64_t>(keep_i64, bc.cells, &cerr);
+      b.normals = up<double>(keep_f64, bc.normals, &cerr);
+      for(int d = 0; d < 3; ++d) b.value[d] = bc.value[d];
+      b.has_pressure = !std::isnan(bc.pressure);
+      b.pressure = b.has_pressure ? bc.pressure : 0.0;
+      b.has_velocity = bc.has_velocity ? 1 : 0;
+      std::vector<int64_t> first(static_cast<size_t>(n), 1);
+      for(int64_t k = 0; k < n; ++k)
+        for(int64_t j = 0; j < k; ++j)
+          if(bc.cells[j] == bc.cells[k]) { first[k] = 0; break; }
+      b.first_of_cell = up<int64_t>(keep_i64, first, &cerr);
+      if(bc.kind == lbm::BC_WALL_BB_TANGENTIAL) {
+        if(D != 2) return fail(LBM_B200_EINVAL, "tangential wall velocity is implemented for 2D only (reference: bnd_wall.h:52-54)");
+        std::vector<double> wv(static_cast<size_t>(n) * Q, 0.0);
+        for(int64_t k = 0; k < n; ++k) {
+          const double* nrm = &bc.normals[k * D];
+          for(int id = 0; id < Q; ++id) {
+            if(!lbm::in_direction(LR, nrm, id)) continue;
+            const int    inside = LR.opp[id];
+            const double tdot = nrm[1] * LR.c[inside][0] + nrm[0] * LR.c[inside][1];
+            const double ndot = nrm[0] * LR.c[inside][0] + nrm[1] * LR.c[inside][1];
+            const double nn   = std::sqrt(double(LR.c[inside][0] * LR.c[inside][0] + LR.c[inside][1] * LR.c[inside][1]));
+            const bool parallel = std::abs(std::acos(ndot / nn) - 3.14159265358979323846) < 10 * lbm::kEps;
+            if(!parallel) wv[k * Q + inside] = bc.tangential * tdot;
+          }
+        }
+        b.wallval = up<double>(keep_f64, wv, &cerr);
+      } else if(bc.kind == lbm::BC_DIRICHLET_BB) {
+        for(int64_t k = 0; k < n; ++k)
+          for(int d = 0; d < D; ++d) vars0[bc.cells[k] * NV + d] = bc.value[d]; // initCnd, bnd_dirichlet.h:44-50
+      } else if(bc.kind == lbm::BC_PRESSURE) {
+        std::vector<int64_t> n1(static_cast<size_t>(n)), n2(static_cast<size_t>(n));
+        std::vector<char> seen(static_cast<size_t>(N), 0);
+        for(int64_t k = 0; k < n; ++k) {
+          const double* nrm = &bc.normals[k * D];
+          int ins = -1;
+          for(int d = 0; d < D && ins < 0; ++d) {
+            if(nrm[d] < 0) ins = 2 * d + 1;
+            else if(nrm[d] > 0) ins = 2 * d;
+          }
+          if(ins < 0) return fail(LBM_B200_EINVAL, "pressure boundary: zero normal");
+          n1[k] = NB(bc.cells[k], ins);
+          n2[k] = n1[k] >= 0 ? NB(n1[k], ins) : -1;
+          if(n1[k] < 0 || n2[k] < 0) return fail(LBM_B200_EINVAL, "pressure boundary: cell without two inward neighbours");
+          if(seen[n1[k]] || seen[n2[k]])
+            return fail(LBM_B200_EUNSUP, "pressure boundary: inward neighbour is an earlier entry of the same surface (order-dependent in the reference)");
+          seen[bc.cells[k]] = 1;
+        }
+        b.n1 = up<int64_t>(keep_i64, n1, &cerr);
+        b.n2 = up<int64_t>(keep_i64, n2, &cerr);
+      } else if(bc.kind == lbm::BC_PERIODIC) {
+        if(in.center.empty()) return fail(LBM_B200_EINVAL, "periodic boundary condition needs set_geometry");
+        std::vector<int64_t> link(static_cast<size_t>(n) * Q, -1);
+        std::vector<int>     ldist(static_cast<size_t>(n) * Q, 0), nset(static_cast<size_t>(n), 0);
+        for(int64_t k = 0; k < n; ++k) {
+          int     setd[27], ns = 0;
+          int64_t links[27];
+          std::string err;
+          if(!lbm::periodic_links(in, bc, k, setd, links, &ns, &err)) return fail(LBM_B200_EINVAL, err);
+          nset[k] = ns;
+          for(int id = 0; id < ns; ++id) { link[k * Q + id] = links[id]; ldist[k * Q + id] = setd[id]; }
+        }
+        b.link = up<int64_t>(keep_i64, link, &cerr);
+        b.linkdist = up<int>(keep_i32, ldist, &cerr);
+        b.nset = up<int>(keep_i32, nset, &cerr);
+        for(int64_t c : bc.cells) periodic[c] = 1;     // surfA.setProperty(periodic), bnd.h:219
+        for(int64_t c : bc.connected) periodic[c] = 1; // surfB
+      } else if(bc.kind >= lbm::BC_WALL_EQ) {
+        if(bc.kind == lbm::BC_WALL_NEBB && !(D == 2 && Q == 9)) return fail(LBM_B200_EINVAL, "Not implemented for this distribution!"); // bnd_wall.h:325-328
+        // LBMBnd_wallWetnode, bnd_wetnode.h:24-63
+        std::vector<int>    lim_n(static_cast<size_t>(n), 0), lim_dist(static_cast<size_t>(n) * Q, 0);
+        std::vector<double> lim_const(static_cast<size_t>(n) * Q, 0.0);
+        std::vector<int64_t> c2b(static_cast<size_t>(n)), ext(static_cast<size_t>(n), -1);
+        for(int64_t k = 0; k < n; ++k) {
+          const int64_t c   = bc.cells[k];
+          const double* nrm = &bc.normals[k * D];
+          double*       cst = &lim_const[k * Q];
+          int           m   = 0;
+          for(int dir = 0; dir < QM; ++dir) {
+            const int  op  = LR.opp[dir];
+            const bool per = periodic[c] != 0;
+            double dot = 0;
+            for(int d = 0; d < D; ++d) dot += nrm[d] * LR.c[dir][d];
+            const bool has_opp = per || NB(c, op) != -1;
+            if(dot >= lbm::kEps && has_opp) {
+              lim_dist[k * Q + m++] = dir;
+              cst[dir] = 2;
+            } else if(std::abs(dot) <= lbm::kEps && has_opp) {
+              lim_dist[k * Q + m++] = dir;
+              cst[dir] = (NB(c, dir) == -1 && !per) ? 2 : 1;
+            }
+          }
+          int sumC = 0;
+          for(int i = 0; i < Q; ++i) sumC = static_cast<int>(sumC + cst[i]);
+          if(sumC != Q - 1) m = 0;
+          else { lim_dist[k * Q + m++] = Q - 1; cst[Q - 1] = 1; }
+          lim_n[k] = m;
+          int64_t idx = k;
+          for(int64_t j = n - 1; j > k; --j)
+            if(bc.cells[j] == c) { idx = j; break; }
+          c2b[k] = idx;
+          if(bc.kind == lbm::BC_WALL_NEEM) {
+            int ex = -1;
+            for(int d = 0; d < D && ex < 0; ++d) {
+              if(nrm[d] < 0) ex = 2 * d + 1;
+              else if(nrm[d] > 0) ex = 2 * d;
+            }
+            ext[k] = ex < 0 ? -1 : NB(c, ex);
+            if(ext[k] < 0) return fail(LBM_B200_EINVAL, "No valid extrapolation cellId"); // bnd_wall.h:243-246
+          }
+        }
+        if(bc.kind == lbm::BC_WALL_NEEM) {
+          std::vector<char> mine(static_cast<size_t>(N), 0);
+          for(int64_t c : bc.cells) mine[c] = 1;
+          for(int64_t e : ext)
+            if(mine[e]) return fail(LBM_B200_EUNSUP, "NEEM wall: extrapolation cell lies on the same surface (order-dependent in the reference)");
+        }
+        b.lim_n = up<int>(keep_i32, lim_n, &cerr);
+        b.lim_dist = up<int>(keep_i32, lim_dist, &cerr);
+        b.lim_const = up<double>(keep_f64, lim_const, &cerr);
+        b.cell2bnd = up<int64_t>(keep_i64, c2b, &cerr);
+        b.ext = up<int64_t>(keep_i64, ext, &cerr);
+      }
+      bcs.push_back(b);
+    }
+    if(cerr != cudaSuccess) return fail(LBM_B200_ECUDA, cudaGetErrorString(cerr));
+    // forcing pairs, solver.cpp:651-693
+    if(in.forcing) {
+      if(in.center.empty()) return fail(LBM_B200_EINVAL, "forcing needs set_geometry");
+      std::vector<lbm::ForceEntry> fe;
+      for(int64_t a : in.inlet) {
+        const int64_t val = NB(a, 1);
+        if(val < 0) return fail(LBM_B200_EINVAL, "forcing: inlet cell without +x neighbour");
+        for(int64_t o : in.outlet)
+          if(std::abs(in.center[val * D + 1] - in.center[o * D + 1]) < lbm::kEps) fe.push_back({static_cast<int32_t>(o), static_cast<int32_t>(val), 1.0});
+      }
+      for(int64_t o : in.outlet) {
+        const int64_t val = NB(o, 0);
+        if(val < 0) return fail(LBM_B200_EINVAL, "forcing: outlet cell without -x neighbour");
+        for(int64_t a : in.inlet)
+          if(std::abs(in.center[a * D + 1] - in.center[val * D + 1]) < lbm::kEps) fe.push_back({static_cast<int32_t>(a), static_cast<int32_t>(val), 1.0 + in.gradient});
+      }
+      std::vector<char> target(static_cast<size_t>(N), 0);
+      for(auto& e : fe) {
+        if(target[e.target]) return fail(LBM_B200_EUNSUP, "forcing: a cell is forced twice (order-dependent in the reference)");
+        target[e.target] = 1;
+      }
+      for(auto& e : fe)
+        if(target[e.val]) return fail(LBM_B200_EUNSUP, "forcing: value cell is itself a forced cell (order-dependent in the reference)");
+      CUDA_TRY(d_force.upload(fe));
+    }
+    CUDA_TRY(cudaMemcpy(d_vars.p, vars0.data(), nv * sizeof(double), cudaMemcpyHostToDevice));
+    lbm::seq::k_init<L><<<blocks(N), 128, 0, stream>>>(state());
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    std::vector<int32_t>().swap(in.nghbr);
+    t = 0;
+    inited = true;
+    return LBM_B200_OK;
+  }
+
+  template <int COLL>
+  void launch_cell(const lbm::seq::State& s) { lbm::seq::k_cell<L, COLL><<<blocks(s.n), 128, 0, stream>>>(s); }
+
+  int step(int64_t n, float* ms_total, float* ms_main) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "lbm_b200_step before lbm_b200_init");
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if(ms_total != nullptr) {
+      CUDA_TRY(cudaEventCreate(&e0));
+      CUDA_TRY(cudaEventCreate(&e1));
+      CUDA_TRY(cudaEventRecord(e0, stream));
+    }
+    const lbm::seq::State s = state();
+    for(int64_t it = 0; it < n; ++it) {
+      CUDA_TRY(cudaMemcpyAsync(d_varsold.p, d_vars.p, d_vars.bytes(), cudaMemcpyDeviceToDevice, stream)); // currToOldVars
+      if(cfg.collision == LBM_B200_TRT) launch_cell<lbm::COLL_TRT>(s);
+      else if(cfg.collision == LBM_B200_MRT) launch_cell<lbm::COLL_MRT>(s);
+      else launch_cell<lbm::COLL_BGK>(s);
+      ++launches;
+      if(d_force.n > 0) {
+        lbm::seq::k_forcing<L><<<blocks(static_cast<int64_t>(d_force.n)), 128, 0, stream>>>(s, d_force.p, static_cast<int>(d_force.n));
+        ++launches;
+      }
+      for(const auto& b : bcs)
+        if((b.kind == lbm::BC_PRESSURE || b.kind == lbm::BC_PERIODIC) && b.n > 0) {
+          lbm::seq::k_pre_apply<L><<<blocks(b.n), 128, 0, stream>>>(s, b);
+          ++launches;
+        }
+      lbm::seq::k_stream<L><<<blocks(s.n), 128, 0, stream>>>(s);
+      ++launches;
+      for(const auto& b : bcs) {
+        if(b.n == 0 || b.kind == lbm::BC_PERIODIC) continue;
+        int nphase = 1, first_phase = 0;
+        if(b.kind == lbm::BC_PRESSURE) first_phase = 1, nphase = 1;
+        if(b.kind == lbm::BC_WALL_NEEM) nphase = 4;
+        if(b.kind == lbm::BC_WALL_NEBB) nphase = b.has_velocity ? 3 : 4;
+        for(int ph = first_phase; ph < first_phase + nphase; ++ph) {
+          if(b.kind == lbm::BC_WALL_NEBB) {
+            if constexpr(D == 2 && Q == 9) lbm::seq::k_nebb<<<blocks(b.n), 128, 0, stream>>>(s, b, ph);
+          } else {
+            lbm::seq::k_apply<L><<<blocks(b.n), 128, 0, stream>>>(s, b, ph);
+          }
+          ++launches;
+        }
+      }
+      ++t;
+    }
+    CUDA_TRY(cudaGetLastError());
+    if(ms_total != nullptr) {
+      CUDA_TRY(cudaEventRecord(e1, stream));
+      CUDA_TRY(cudaEventSynchronize(e1));
+      CUDA_TRY(cudaEventElapsedTime(ms_total, e0, e1));
+      if(ms_main) *ms_main = *ms_total;
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
+    return LBM_B200_OK;
+  }
+
+  int sync() override {
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return LBM_B200_OK;
+  }
+  int d2h(const double* src, double* dst, size_t count) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    d2h_bytes += static_cast<int64_t>(count * sizeof(double));
+    return LBM_B200_OK;
+  }
+  int get_populations(double* fo, double* foldo) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
+    const size_t nq = static_cast<size_t>(in.n) * Q;
+    if(fo != nullptr) { int rc = d2h(d_f.p, fo, nq); if(rc) return rc; }
+    if(foldo != nullptr) { int rc = d2h(d_fold.p, foldo, nq); if(rc) return rc; }
+    return LBM_B200_OK;
+  }
+  int set_populations(const double* fi, const double* foldi) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
+    if(fi == nullptr || foldi == nullptr) return fail(LBM_B200_EINVAL, "set_populations needs both f and fold");
+    const size_t nq = static_cast<size_t>(in.n) * Q;
+    CUDA_TRY(cudaMemcpyAsync(d_f.p, fi, nq * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(d_fold.p, foldi, nq * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    h2d_bytes += static_cast<int64_t>(2 * nq * sizeof(double));
+    return LBM_B200_OK;
+  }
+  int get_vars(double* v, double* vo) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
+    const size_t nv = static_cast<size_t>(in.n) * NV;
+    if(v != nullptr) { int rc = d2h(d_vars.p, v, nv); if(rc) return rc; }
+    if(vo != nullptr) { int rc = d2h(d_varsold.p, vo, nv); if(rc) return rc; }
+    return LBM_B200_OK;
+  }
+  int get_moments(double* m) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
+    lbm::seq::k_moments<L><<<blocks(in.n), 128, 0, stream>>>(state(), d_scratch.p);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    return d2h(d_scratch.p, m, static_cast<size_t>(in.n) * NV);
+  }
+  int residual(double* out, int32_t* diverged) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
+    const int nb = 64;
+    lbm::seq::k_residual_aos<<<nb, 256, 0, stream>>>(d_vars.p, d_varsold.p, in.n, NV, d_partial.p);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    std::vector<double> h(static_cast<size_t>(NV) * nb);
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaMemcpy(h.data(), d_partial.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    int bad = 0;
+    for(int v = 0; v < NV; ++v) {
+      double sum = 0;
+      for(int b = 0; b < nb; ++b) sum += h[static_cast<size_t>(v) * nb + b];
+      out[v] = sum;
+      if(std::isnan(sum) || std::isinf(sum)) bad = 1;
+    }
+    if(diverged) *diverged = bad;
+    return LBM_B200_OK;
+  }
+  int64_t owned() const override { return in.n; }
+  void stats(lbm_b200_stats* st) const override {
+    std::memset(st, 0, sizeof(*st));
+    st->ncells = in.n;
+    st->cells_generic = in.n; // none on the fused chunk path
+    st->device_bytes = static_cast<int64_t>(d_f.bytes() * 4 + d_vars.bytes() * 2);
+    st->launches = launches;
+    st->launches_main = 0;
+    st->bytes_per_cell_alg = 2.0 * Q * sizeof(double);
+    st->h2d_bytes = h2d_bytes;
+    st->d2h_bytes = d2h_bytes;
+  }
+};
+
+SolverBase* make_sequential(const lbm_b200_config& c) {
+  if(c.ndim == 2 && c.ndist == 9) return new SequentialSolver<lbm::Lattice<2, 9>>();
+  if(c.ndim == 3 && c.ndist == 19) return new SequentialSolver<lbm::Lattice<3, 19>>();
+  if(c.ndim == 3 && c.ndist == 27) return new SequentialSolver<lbm::Lattice<3, 27>>();
+  return nullptr;
+}
+
 SolverBase* make_solver(const lbm_b200_config& c) {
   const bool dbl = c.precision == LBM_B200_FP64;
 #ifdef LBM_EXPERIMENT_D3Q19_F64
@@ -809,6 +1179,18 @@ int lbm_b200_add_dirichlet_bb(lbm_b200_solver* s, const int64_t* cells, const do
   return add_bc(s, bc, cells, normals, n);
 }
 
+int lbm_b200_add_wall_wetnode(lbm_b200_solver* s, int32_t model, const int64_t* cells, const double* normals, int64_t n,
+                              int32_t has_velocity, const double* velocity) {
+  CHECK_HANDLE(s);
+  if(model < LBM_B200_WALL_EQUILIBRIUM || model > LBM_B200_WALL_NEBB) return fail(LBM_B200_EINVAL, "Invalid wall boundary model");
+  if(has_velocity && velocity == nullptr) return fail(LBM_B200_EINVAL, "null velocity");
+  lbm::BcInput bc;
+  bc.kind = model == LBM_B200_WALL_EQUILIBRIUM ? lbm::BC_WALL_EQ : (model == LBM_B200_WALL_NEEM ? lbm::BC_WALL_NEEM : lbm::BC_WALL_NEBB);
+  bc.has_velocity = has_velocity != 0;
+  for(int d = 0; d < s->impl->in.L.D; ++d) bc.value[d] = has_velocity ? velocity[d] : 0.0;
+  return add_bc(s, bc, cells, normals, n);
+}
+
 int lbm_b200_add_pressure(lbm_b200_solver* s, const int64_t* cells, const double* normals, int64_t n, double pressure) {
   lbm::BcInput bc;
   bc.kind     = lbm::BC_PRESSURE;
@@ -920,6 +1302,17 @@ int lbm_b200_init(lbm_b200_solver* s) {
   CHECK_HANDLE(s);
   CHECK_NOT_INITED(s);
   if(s->impl->in.nghbr.empty()) return fail(LBM_B200_ESTATE, "lbm_b200_set_topology has not been called");
+  bool wet = false;
+  for(const lbm::BcInput& bc : s->impl->in.bcs) wet = wet || bc.kind >= lbm::BC_WALL_EQ;
+  if(wet) {
+    // order-dependent boundary conditions: hand the same inputs to the reference-order pipeline (sequential.cuh)
+    SolverBase* q = make_sequential(s->impl->cfg);
+    if(q == nullptr) return fail(LBM_B200_EINVAL, "Unsupported model");
+    q->cfg    = s->impl->cfg;
+    q->in     = std::move(s->impl->in);
+    q->stream = s->impl->stream;
+    s->impl.reset(q);
+  }
   return s->impl->init();
 }
 

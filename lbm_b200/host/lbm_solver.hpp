@@ -291,8 +291,16 @@ class LBMSolver final : public Runnable {
           if(!generate) continue;
           const std::string model = bc.at("model").as_string();
           if(model == "bounceback") call(lbm_b200_add_wall_bb(m_gpu, cells, normals.data(), nc, bc.opt("tangentialVelocity", 0.0)));
-          else if(model == "equilibrium" || model == "neem" || model == "nebb")
-            TERMM(-1, "wall boundary model " + model + " is not available on the GPU path yet (SURVEY.md section 8f N1)");
+          else if(model == "equilibrium" || model == "neem" || model == "nebb") {
+            const int kind = model == "equilibrium" ? LBM_B200_WALL_EQUILIBRIUM : (model == "neem" ? LBM_B200_WALL_NEEM : LBM_B200_WALL_NEBB);
+            std::vector<double> vel(3, 0.0);
+            const bool has_v = bc.has("velocity");
+            if(has_v) {
+              const auto v = bc.at("velocity").as_doubles();
+              for(int d = 0; d < m_ndim && d < static_cast<int>(v.size()); ++d) vel[d] = v[d];
+            }
+            call(lbm_b200_add_wall_wetnode(m_gpu, kind, cells, normals.data(), nc, has_v ? 1 : 0, vel.data()));
+          }
           else TERMM(-1, "Invalid wall boundary model: " + model);
         } else if(type == "pressure") {
           if(!generate) continue;

@@ -12,7 +12,11 @@ from gridgen import box_grid
 
 pytestmark = pytest.mark.gpu
 
-GOLDEN_CASES = ["couette", "couette_bnd", "couette_bnd_bbDirichlet", "poiseuille", "poiseuille_bnd", "step_ns", "sphere_ns"]
+GOLDEN_CASES = ["couette", "couette_bnd", "couette_bnd_bbDirichlet", "poiseuille", "poiseuille_bnd", "step_ns", "sphere_ns",
+                # wet-node wall family (reference-order pipeline on the GPU, lbm_b200/csrc/sequential.cuh)
+                "couette_bnd_eq", "couette_bnd_eq2", "couette_bnd_eq_aligned", "couette_bnd_NEEM", "couette_bnd_NEBB",
+                "poiseuille_bnd_eq", "poiseuille_bnd_NEEM", "poiseuille_bnd_NEBB", "poiseuille_bnd_pressure",
+                "poiseuille_bnd_pressure_neem2"]
 
 
 def rel_err(a, b):

@@ -52,16 +52,29 @@ def test_couette_dirichlet_bb_case(tmp_path):
     assert out["steps"] == 1301 and abs(out["max_error"] - 1.76069e-12) < 1e-16
 
 
+@pytest.mark.parametrize("name,steps,max_error", [
+    ("couette_bnd_eq", 14801, 1.39587e-12),          # wet-node equilibrium wall + bounce-back lid, periodic BC
+    ("couette_bnd_NEBB", 14801, 6.30746e-13),        # non-equilibrium bounce-back walls
+    ("poiseuille_bnd_pressure", 122801, 9.98514e-06),  # pressure in/outlet + equilibrium walls on an aligned grid
+])
+def test_wet_node_reference_cases_end_to_end(name, steps, max_error, tmp_path):
+    """The numbers are what the reference binary prints for its own configuration."""
+    (rc, msg, out, _), _ = run_case(name, tmp_path, solution_interval=10 ** 9)
+    assert rc == 0, msg
+    assert out["converged"] == 1.0 and out["steps"] == steps
+    assert abs(out["max_error"] - max_error) < 2e-6 * max_error
+
+
 def test_failed_threshold_terminates_like_termm(tmp_path):
     (rc, msg, out, _), _ = run_case("couette", tmp_path, errorMax=1e-20)
     assert rc == -1 and "Analytical testcase failed" in msg
 
 
-def test_unsupported_wall_model_is_reported(tmp_path):
+def test_invalid_wall_model_is_reported(tmp_path):
     spec = load_golden("couette")
     cfg = json.loads(str(spec.golden["config_orig_json"]))
-    cfg["solver"]["boundary"]["cube"]["-y"] = {"type": "wall", "model": "nebb"}
+    cfg["solver"]["boundary"]["cube"]["-y"] = {"type": "wall", "model": "slippery"}
     p = tmp_path / "c.json"
     p.write_text(json.dumps(cfg))
     rc, msg, _, _ = host_api.run(str(p))
-    assert rc == -1 and "nebb" in msg
+    assert rc == -1 and "Invalid wall boundary model: slippery" in msg
