@@ -189,6 +189,46 @@ def cpu_sample(lattice, sample_size, budget_s, omp_collide=False):
     return n * steps / dt / 1e6, steps, n, oracle.threads()
 
 
+def reference_binary_d2q9(level=9, steps=60):
+    """The reference binary itself (oracle/_ref/lbm_ref, built from the reference's sources) on the largest kind of case it can
+    run: D2Q9 BGK fp64, (2^level)^2 box, periodic x, bounce-back walls, moving top wall -- timed by the reference's own
+    'Computation' timer (src/lbm/solver.cpp:57,308-319) with all host cores.  Reported beside the D3Q19 port number because the
+    reference cannot run the D3Q19 workload at all.  Returns None if the binary is not there."""
+    import re
+    import shutil
+    binary = os.path.join(ROOT, "oracle", "_ref", "lbm_ref")
+    if not os.path.exists(binary):
+        return None
+    cfg = {"dim": 2, "partitionLevel": level, "uniformLevel": level, "maxRfnmtLvl": level, "maxNoCells": 4 ** level * 2, "outputDir": "out",
+           "gridFileName": "g", "output": {"format": "VTKB", "cellFilter": "leafCells", "type": "points", "outputValues": ["level"]},
+           "geometry": {"cube": {"type": "box", "A": [0.0, 0.0], "B": [1.0, 1.0]}},
+           "solver": {"type": "lbm", "method": "bgk", "relaxation": 0.6, "ma": 0.01, "maxSteps": steps, "info_interval": 10 ** 6,
+                      "solution_interval": 10 ** 9, "output_dir": "out", "convergence": 0.0, "assumeAxisAligned": True,
+                      "boundary": {"cube": {"+x": {"type": "periodic", "generateBndry": False, "connection": "cube_-x"},
+                                            "-x": {"type": "periodic", "generateBndry": False, "connection": "cube_+x"},
+                                            "+y": {"type": "wall", "model": "bounceback", "tangentialVelocity": LID_U},
+                                            "-y": {"type": "wall", "model": "bounceback"}}}}}
+    tmp = tempfile.mkdtemp(prefix="lbm_refbin_")
+    try:
+        json.dump(cfg, open(os.path.join(tmp, "case.json"), "w"))
+        cores = os.cpu_count() or 1
+        env = dict(os.environ, OMP_NUM_THREADS=str(cores))
+        r = subprocess.run([binary, "case.json"], cwd=tmp, env=env, capture_output=True, text=True, timeout=600)
+        if r.returncode != 0:
+            return {"error": f"reference binary exited {r.returncode}"}
+        log = open(os.path.join(tmp, "lbm_log")).read()
+        m = re.search(r"Computation\s+([0-9.eE+-]+) \[sec\]", log)
+        if not m:
+            return {"error": "no Computation timer in lbm_log"}
+        sec = float(m.group(1))
+        cells = 4 ** level
+        return {"value": cells * steps / sec / 1e6, "unit": "MLUPS", "cores": cores, "kind": "reference",
+                "sample": f"reference binary, D2Q9 BGK fp64 {2 ** level}^2 box ({cells} cells), {steps} steps, its own 'Computation' timer "
+                          f"({sec:.3f} s); the reference has no 3D LBM"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -217,6 +257,7 @@ def run_reference(args):
                                    f"{args.steps} steps; the reference binary cannot run D3Q19 (SURVEY section 0)"},
         "e2e": {"value": mlups, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    line["cpu_baseline"]["reference_binary_d2q9"] = reference_binary_d2q9()
     emit(line)
 
 
@@ -332,7 +373,8 @@ def run_ours(args):
         v, steps, nc, cores = cpu_sample(args.lattice, args.cpu_size, args.cpu_budget)
         cpu = {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port",
                "sample": f"{args.lattice} {args.cpu_size}^{ndim} box ({nc} cells), same BCs/omega, {steps} steps of oracle/lbm_oracle.c "
-                         f"(reference algorithm; serial collision pass like src/lbm/solver.cpp:601)"}
+                         f"(reference algorithm; serial collision pass like src/lbm/solver.cpp:601)",
+               "reference_binary_d2q9": reference_binary_d2q9()}
     line = {
         "metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
