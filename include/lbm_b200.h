@@ -176,6 +176,37 @@ typedef struct {
 } lbm_b200_stats;
 int lbm_b200_get_stats(const lbm_b200_solver* s, lbm_b200_stats* out);
 
+/* Inspection of the device plan (host-side layout planning of lbm_b200/csrc/plan.hpp; no arithmetic, no CUDA call).  Works on
+ * a normal handle and on an inspection-only handle created with config.device = -1 (which refuses init / step).  The tests
+ * use it to check on a machine without a GPU that the plan resolves the reference's preApply -> push -> apply order, the chunk
+ * templates, wall descriptors, ghost blocks and halo lists correctly.  Pointers stay valid until lbm_b200_destroy. */
+typedef struct {
+  int64_t n, n_owned, npad, chunk, nsel, n_fast_chunks, n_fast_outer, gen_begin, n_gen, n_gen_outer, gen_stride, ghost_begin,
+      n_ghost_blocks, n_values_static;
+  const int32_t*  ref2dev;   /* [n] reference cell -> device slot */
+  const uint16_t* tmpl;      /* [(Q-1)*chunk] sel << 10 | offset (device in-chunk order) */
+  const int32_t*  chunk_nb;  /* [n_fast_chunks*(nsel+1)] neighbour-chunk bases (-1 wall), wall descriptor id */
+  const int32_t*  codes;     /* [(Q-1)*gen_stride] link codes of the generic range */
+  const int32_t*  copytab;   /* [n_copy*2] cell, dir */
+  int64_t         n_copy;
+  const double*   addtab;    /* [n_add*4] v0, v1, v2, count */
+  int64_t         n_add;
+  const double*   wall_desc; /* [n_wall*4] per wall descriptor Q-1 entries of v0, v1, v2, count */
+  int64_t         n_wall;
+  const double*   abb_p;     /* [n_abb] pressure of every anti-bounce-back entry */
+  const int32_t*  abb_cells; /* [n_abb*3] device cell, inward neighbours n1, n2 */
+  int64_t         n_abb;
+  const double*   values;    /* [n_values] stored slot values (static part filled at init) */
+  int64_t         n_values;
+  const int64_t*  stale_ref; /* [n_stale] device cell * Q + dir of every slot nothing writes */
+  int64_t         n_stale;
+  const int64_t*  send_index; /* flat device indices dir * npad + cell, wire order */
+  int64_t         n_send;
+  const int64_t*  recv_index;
+  int64_t         n_recv;
+} lbm_b200_plan_view;
+int lbm_b200_debug_plan(lbm_b200_solver* s, lbm_b200_plan_view* out);
+
 /* Time `nsteps` steps with CUDA events on the solver's stream; *ms_total covers all kernels of those steps,
  * *ms_main only the fused stream+collide kernel (events around each launch). Synchronous. */
 int lbm_b200_step_timed(lbm_b200_solver* s, int64_t nsteps, float* ms_total, float* ms_main);

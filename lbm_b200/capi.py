@@ -40,6 +40,17 @@ class Stats(C.Structure):
                 ("launches_main", C.c_int64), ("bytes_per_cell_alg", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("cells_ghost", C.c_int64), ("halo_bytes", C.c_int64)]
 
 
+class PlanView(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("n", "n_owned", "npad", "chunk", "nsel", "n_fast_chunks", "n_fast_outer", "gen_begin", "n_gen",
+                                         "n_gen_outer", "gen_stride", "ghost_begin", "n_ghost_blocks", "n_values_static")] + [
+        ("ref2dev", C.POINTER(C.c_int32)), ("tmpl", C.POINTER(C.c_uint16)), ("chunk_nb", C.POINTER(C.c_int32)),
+        ("codes", C.POINTER(C.c_int32)), ("copytab", C.POINTER(C.c_int32)), ("n_copy", C.c_int64),
+        ("addtab", C.POINTER(C.c_double)), ("n_add", C.c_int64), ("wall_desc", C.POINTER(C.c_double)), ("n_wall", C.c_int64),
+        ("abb_p", C.POINTER(C.c_double)), ("abb_cells", C.POINTER(C.c_int32)), ("n_abb", C.c_int64),
+        ("values", C.POINTER(C.c_double)), ("n_values", C.c_int64), ("stale_ref", C.POINTER(C.c_int64)), ("n_stale", C.c_int64),
+        ("send_index", C.POINTER(C.c_int64)), ("n_send", C.c_int64), ("recv_index", C.POINTER(C.c_int64)), ("n_recv", C.c_int64)]
+
+
 def library_path():
     # LBM_B200_LIB selects a tuning build of the same library (kernel experiments); never a different backend
     return os.environ.get("LBM_B200_LIB") or os.path.join(_HERE, "liblbm_b200.so")
@@ -109,6 +120,7 @@ def load_library():
     L.lbm_b200_box_rows.argtypes = [i32, pi64, pi32, pi64, i64, pi64, i32, vp]
     L.lbm_b200_sfc_index.argtypes = [i32, pdbl, i32]
     L.lbm_b200_sfc_index.restype = i64
+    L.lbm_b200_debug_plan.argtypes = [vp, C.POINTER(PlanView)]
     L.lbm_b200_last_error.restype = C.c_char_p
     L.lbm_b200_abi_version.restype = C.c_int
     _LIB = L
@@ -206,6 +218,31 @@ class Solver:
 
     def set_stream(self, cuda_stream):
         self._check(self._lib.lbm_b200_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def debug_plan(self):
+        """The device plan as numpy arrays (host-side layout planning only; works on a handle created with device=-1)."""
+        v = PlanView()
+        self._check(self._lib.lbm_b200_debug_plan(self._h, C.byref(v)))
+        qm = self.ndist - 1
+
+        def arr(ptr, count, shape=None):
+            a = np.ctypeslib.as_array(ptr, shape=(int(count),)).copy() if count else np.zeros(0)
+            return a.reshape(shape) if shape is not None and count else a
+        out = {k: int(getattr(v, k)) for k, t in PlanView._fields_ if t is C.c_int64}
+        out["ref2dev"] = arr(v.ref2dev, v.n)
+        out["tmpl"] = arr(v.tmpl, qm * v.chunk, (qm, int(v.chunk)))
+        out["chunk_nb"] = arr(v.chunk_nb, v.n_fast_chunks * (v.nsel + 1), (int(v.n_fast_chunks), int(v.nsel) + 1))
+        out["codes"] = arr(v.codes, qm * v.gen_stride, (qm, int(v.gen_stride)))
+        out["copytab"] = arr(v.copytab, v.n_copy * 2, (int(v.n_copy), 2))
+        out["addtab"] = arr(v.addtab, v.n_add * 4, (int(v.n_add), 4))
+        out["wall_desc"] = arr(v.wall_desc, v.n_wall * 4, (int(v.n_wall) // qm if v.n_wall else 0, qm, 4))
+        out["abb_p"] = arr(v.abb_p, v.n_abb)
+        out["abb_cells"] = arr(v.abb_cells, v.n_abb * 3, (int(v.n_abb), 3))
+        out["values"] = arr(v.values, v.n_values)
+        out["stale_ref"] = arr(v.stale_ref, v.n_stale)
+        out["send_index"] = arr(v.send_index, v.n_send)
+        out["recv_index"] = arr(v.recv_index, v.n_recv)
+        return out
 
     # ---- run
     def init(self):

@@ -71,6 +71,7 @@ struct SolverBase {
   virtual int get_moments(double* m)                                     = 0;
   virtual void stats(lbm_b200_stats* st) const                           = 0;
   virtual int64_t owned() const                                          = 0;
+  virtual int debug_plan(lbm_b200_plan_view* out) { (void)out; return fail(LBM_B200_EUNSUP, "no device plan for this solver kind"); }
   lbm_b200_config cfg{};
   lbm::PlanInput  in;
   cudaStream_t    stream = nullptr;
@@ -645,6 +646,40 @@ struct Solver final : SolverBase {
 
   int64_t owned() const override { return plan.n_owned; }
 
+  // host-side layout planning only (tests inspect it on machines without a GPU); the views stay valid until destroy
+  std::vector<double> dbg_add, dbg_wall, dbg_abb;
+  std::vector<int32_t> dbg_copy, dbg_abb_cells;
+  int debug_plan(lbm_b200_plan_view* v) override {
+    if(!inited) {
+      if(in.nghbr.empty()) return fail(LBM_B200_ESTATE, "lbm_b200_set_topology has not been called");
+      lbm::PlanInput copy = in; // keep the inputs: a later lbm_b200_init must still see them
+      if(!lbm::build_plan(copy, plan)) return fail(LBM_B200_EINVAL, plan.error);
+    }
+    std::memset(v, 0, sizeof(*v));
+    v->n = plan.n; v->n_owned = plan.n_owned; v->npad = plan.npad; v->chunk = plan.CH; v->nsel = plan.L.NSEL;
+    v->n_fast_chunks = plan.n_fast_chunks; v->n_fast_outer = plan.n_fast_outer; v->gen_begin = plan.gen_begin; v->n_gen = plan.n_gen;
+    v->n_gen_outer = plan.n_gen_outer; v->gen_stride = plan.gen_stride; v->ghost_begin = plan.ghost_begin;
+    v->n_ghost_blocks = plan.n_ghost_blocks; v->n_values_static = plan.n_values_static;
+    v->ref2dev = plan.ref2dev.data(); v->tmpl = plan.tmpl.data(); v->chunk_nb = plan.chunk_nb.data(); v->codes = plan.codes.data();
+    dbg_copy.clear();
+    for(auto& c : plan.copytab) { dbg_copy.push_back(c.cell); dbg_copy.push_back(c.dir); }
+    v->copytab = dbg_copy.data(); v->n_copy = static_cast<int64_t>(plan.copytab.size());
+    dbg_add.clear();
+    for(auto& a : plan.addtab) { dbg_add.push_back(a.v[0]); dbg_add.push_back(a.v[1]); dbg_add.push_back(a.v[2]); dbg_add.push_back(a.n); }
+    v->addtab = dbg_add.data(); v->n_add = static_cast<int64_t>(plan.addtab.size());
+    dbg_wall.clear();
+    for(auto& a : plan.wall_desc) { dbg_wall.push_back(a.v[0]); dbg_wall.push_back(a.v[1]); dbg_wall.push_back(a.v[2]); dbg_wall.push_back(a.n); }
+    v->wall_desc = dbg_wall.data(); v->n_wall = static_cast<int64_t>(plan.wall_desc.size());
+    dbg_abb.clear(); dbg_abb_cells.clear();
+    for(auto& a : plan.abb) { dbg_abb.push_back(a.p); dbg_abb_cells.push_back(a.cell); dbg_abb_cells.push_back(a.n1); dbg_abb_cells.push_back(a.n2); }
+    v->abb_p = dbg_abb.data(); v->abb_cells = dbg_abb_cells.data(); v->n_abb = static_cast<int64_t>(plan.abb.size());
+    v->values = plan.values.data(); v->n_values = static_cast<int64_t>(plan.values.size());
+    v->stale_ref = plan.stale_ref.data(); v->n_stale = static_cast<int64_t>(plan.stale_ref.size());
+    v->send_index = plan.send_index.data(); v->n_send = static_cast<int64_t>(plan.send_index.size());
+    v->recv_index = plan.recv_index.data(); v->n_recv = static_cast<int64_t>(plan.recv_index.size());
+    return LBM_B200_OK;
+  }
+
   void stats(lbm_b200_stats* st) const override {
     std::memset(st, 0, sizeof(*st));
     st->ncells        = plan.n_owned;
@@ -1091,10 +1126,11 @@ int lbm_b200_create(const lbm_b200_config* cfg, int64_t ncells, lbm_b200_solver*
     return fail(LBM_B200_EINVAL, "Unsupported model");
   }
   s->in.n = ncells;
-  // no silent CPU path: a missing device is an error right here
+  // no silent CPU path: a missing device is an error right here.  device == -1 creates an INSPECTION-ONLY handle: it accepts
+  // the set-up calls and lbm_b200_debug_plan (host-side layout planning, no arithmetic), and refuses init / step / read-back.
   int ndev = 0;
-  cudaError_t e = cudaGetDeviceCount(&ndev);
-  if(e != cudaSuccess || ndev <= cfg->device) {
+  cudaError_t e = cfg->device == -1 ? cudaSuccess : cudaGetDeviceCount(&ndev);
+  if(cfg->device < -1 || (cfg->device >= 0 && (e != cudaSuccess || ndev <= cfg->device))) {
     delete s;
     return fail(LBM_B200_ECUDA, std::string("no CUDA device ") + std::to_string(cfg->device) + ": " + cudaGetErrorString(e));
   }
@@ -1302,6 +1338,7 @@ int lbm_b200_init(lbm_b200_solver* s) {
   CHECK_HANDLE(s);
   CHECK_NOT_INITED(s);
   if(s->impl->in.nghbr.empty()) return fail(LBM_B200_ESTATE, "lbm_b200_set_topology has not been called");
+  if(s->impl->cfg.device < 0) return fail(LBM_B200_ECUDA, "inspection-only handle (device -1): there is no CPU compute path");
   bool wet = false;
   for(const lbm::BcInput& bc : s->impl->in.bcs) wet = wet || bc.kind >= lbm::BC_WALL_EQ;
   if(wet) {
@@ -1391,6 +1428,14 @@ int lbm_b200_box_topology(int32_t ndim, const int64_t* shape, const int32_t* per
   std::string err;
   if(!lbm::box_topology(ndim, shape, periodic, nghbr, stride, center, coords, &err)) return fail(LBM_B200_EINVAL, err);
   return LBM_B200_OK;
+}
+
+int lbm_b200_debug_plan(lbm_b200_solver* s, lbm_b200_plan_view* out) {
+  CHECK_HANDLE(s);
+  if(out == nullptr) return fail(LBM_B200_EINVAL, "null argument");
+  for(const lbm::BcInput& bc : s->impl->in.bcs)
+    if(bc.kind >= lbm::BC_WALL_EQ) return fail(LBM_B200_EUNSUP, "configurations with wet-node walls have no fused device plan");
+  return s->impl->debug_plan(out);
 }
 
 const char* lbm_b200_last_error(void) { return g_error.c_str(); }

@@ -41,11 +41,8 @@ struct GeomBox final : Geom {
     const double h = 0.5 * len;
     if(ndim == 1) return std::abs(A[0] - c[0]) <= h || std::abs(B[0] - c[0]) <= h;
     // for every axis a: the cell lies within the box extended by h in all OTHER axes and touches face A_a or B_a.
-    // 2D: exactly the reference's two blocks (x-range -> y faces, y-range -> x faces).
-    for(int range_axis = 0; range_axis < ndim; ++range_axis) {
-      // the reference tests "range in axis r, faces of the other axis"; in 3D the natural extension is
-      // "range in all axes but a, faces of axis a", which reduces to the same thing in 2D
-    }
+    // In 2D this is exactly the reference's two blocks (x-range -> y faces :779-786, y-range -> x faces :787-794); the 3D
+    // form ("range in all axes but a, faces of axis a") is the extension the reference leaves as TERMM("impl").
     for(int a = ndim - 1; a >= 0; --a) { // 2D order of the reference: y faces first (:779-786), then x faces (:787-794)
       bool in_range = true;
       for(int r = 0; r < ndim; ++r) {

@@ -222,7 +222,7 @@ class GridGen {
   // is now outside (deleteOutsideCells<CHECKALL = true>, :508-525,556-561)
   void transform_to_extent() {
     const int NN = 2 * ndim;
-    double emin[3], emax[3];
+    double emin[3] = {0, 0, 0}, emax[3] = {0, 0, 0};
     for(int d = 0; d < ndim; ++d) {
       emin[d] = std::numeric_limits<double>::max();
       emax[d] = std::numeric_limits<double>::min(); // sic: the smallest positive double, as in the reference
