@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <functional>
 #include <iomanip>
@@ -188,7 +189,60 @@ class LBMSolver final : public Runnable {
   bool    converged = false;
   double  lastResidual = NAN;
 
+  // `lbm --bench`: the synthetic cube of SURVEY.md section 8d (S3) through the same C ABI: S^3 cells (LBM_BENCH_SIZE, default 256),
+  // D3Q19 BGK fp64, omega = 1/0.6, periodic x, bounce-back walls on -y/+y/-z, moving lid on +z; 50 warm-up + 200 timed steps.
+  int64_t runBenchmark() {
+    const char* env = std::getenv("LBM_BENCH_SIZE");
+    const int64_t S = env != nullptr ? std::atoll(env) : 256;
+    if(S < 8 || S > 640) TERMM(-1, "LBM_BENCH_SIZE must be in [8, 640]");
+    const int64_t shape[3] = {S, S, S};
+    const int32_t periodic[3] = {1, 0, 0};
+    const int64_t n = lbm_b200_box_ncells(3, shape);
+    std::vector<int64_t> nghbr(static_cast<size_t>(n) * 26);
+    call(lbm_b200_box_topology(3, shape, periodic, nghbr.data(), 26, nullptr, nullptr));
+    lbm_b200_config cfg;
+    lbm_b200_default_config(&cfg);
+    cfg.ndim = 3;
+    cfg.ndist = 19;
+    cfg.arithmetic = LBM_B200_FAST;
+    cfg.track_vars = 0;
+    cfg.omega = 1.0 / 0.6;
+    call(lbm_b200_create(&cfg, n, &m_gpu));
+    call(lbm_b200_set_topology(m_gpu, nghbr.data(), 26));
+    // surfaces in the reference's (lexicographic) order: +y, +z, -y, -z; x is periodic
+    const int order[4] = {3, 5, 2, 4};
+    for(int dir : order) {
+      std::vector<int64_t> cells;
+      for(int64_t c = 0; c < n; ++c)
+        if(nghbr[static_cast<size_t>(c) * 26 + dir] < 0) cells.push_back(c);
+      std::vector<double> normals(cells.size() * 3, 0.0);
+      for(size_t k = 0; k < cells.size(); ++k) normals[k * 3 + dir / 2] = dir % 2 ? 1.0 : -1.0;
+      if(dir == 5) {
+        const double lid[3] = {0.05, 0.0, 0.0};
+        call(lbm_b200_add_dirichlet_bb(m_gpu, cells.data(), normals.data(), static_cast<int64_t>(cells.size()), lid));
+      } else {
+        call(lbm_b200_add_wall_bb(m_gpu, cells.data(), normals.data(), static_cast<int64_t>(cells.size()), 0.0));
+      }
+    }
+    std::vector<int64_t>().swap(nghbr);
+    call(lbm_b200_init(m_gpu));
+    call(lbm_b200_step(m_gpu, 50));
+    float ms_total = 0, ms_main = 0;
+    const int64_t steps = 200;
+    call(lbm_b200_step_timed(m_gpu, steps, &ms_total, &ms_main));
+    lbm_b200_stats st;
+    call(lbm_b200_get_stats(m_gpu, &st));
+    const double mlups = static_cast<double>(n) * steps / (ms_total * 1e-3) / 1e6;
+    const double gbs   = st.bytes_per_cell_alg * static_cast<double>(n) * steps / (ms_main * 1e-3) / 1e9;
+    std::cout << "bench: " << S << "^3 D3Q19 BGK fp64, " << n << " cells (" << st.cells_fast << " on the chunk path), " << steps << " steps in "
+              << ms_total << " ms\n"
+              << "bench: " << mlups << " MLUPS, " << gbs << " GB/s algorithmic (2*Q*8 B per cell update)" << std::endl;
+    stepsRun = steps;
+    return 0;
+  }
+
   int64_t run() override {
+    if(m_benchmark) return runBenchmark();
     loadConfiguration();
     setupGpu();
     using clk = std::chrono::steady_clock;
