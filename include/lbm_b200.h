@@ -152,7 +152,9 @@ int lbm_b200_residual(lbm_b200_solver* s, double* out, int32_t* diverged);
 int lbm_b200_get_populations(lbm_b200_solver* s, double* f, double* fold);
 int lbm_b200_get_vars(lbm_b200_solver* s, double* vars, double* varsold);
 int lbm_b200_get_moments(lbm_b200_solver* s, double* moments);
-/* Overwrites m_f and m_fold (restart / tests).  Both [ncells*Q], reference layout. */
+/* Overwrites m_fold and, if f != NULL, m_f (restart / tests).  Both [ncells*Q], reference layout.  m_fold alone is the input of the
+ * next time step: collisionStep overwrites all of m_f before anything reads it (solver.cpp:601-613), so f may be NULL, in which
+ * case lbm_b200_get_populations returns the previous m_f until a step has run. */
 int lbm_b200_set_populations(lbm_b200_solver* s, const double* f, const double* fold);
 
 int64_t lbm_b200_steps_done(const lbm_b200_solver* s);

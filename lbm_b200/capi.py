@@ -103,7 +103,7 @@ def load_library():
     L.lbm_b200_synchronize.argtypes = [vp]
     L.lbm_b200_residual.argtypes = [vp, pdbl, C.POINTER(i32)]
     L.lbm_b200_get_populations.argtypes = [vp, vp, vp]
-    L.lbm_b200_set_populations.argtypes = [vp, pdbl, pdbl]
+    L.lbm_b200_set_populations.argtypes = [vp, vp, pdbl]
     L.lbm_b200_get_vars.argtypes = [vp, vp, vp]
     L.lbm_b200_get_moments.argtypes = [vp, pdbl]
     L.lbm_b200_steps_done.argtypes = [vp]
@@ -297,7 +297,9 @@ class Solver:
         return out
 
     def set_populations(self, f, fold):
-        self._check(self._lib.lbm_b200_set_populations(self._h, _f64(f), _f64(fold)))
+        """m_fold (and m_f unless None: it is not an input of the next step) in the reference's layout."""
+        f = None if f is None else _f64(f)
+        self._check(self._lib.lbm_b200_set_populations(self._h, None if f is None else f.ctypes.data, _f64(fold)))
 
     @property
     def steps_done(self):

@@ -573,10 +573,13 @@ struct Solver final : SolverBase {
 
   int set_populations(const double* fi, const double* foldi) override {
     if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
-    if(fi == nullptr || foldi == nullptr) return fail(LBM_B200_EINVAL, "set_populations needs both f and fold");
+    if(foldi == nullptr) return fail(LBM_B200_EINVAL, "set_populations needs m_fold");
     CUDA_TRY(cudaStreamSynchronize(stream));
-    int rc = upload_aos(fi, Q, f[cur].p);
-    if(rc) return rc;
+    int rc = LBM_B200_OK;
+    if(fi != nullptr) { // m_f is not an input of the next step (the collision overwrites it, solver.cpp:603); kept for read-back only
+      rc = upload_aos(fi, Q, f[cur].p);
+      if(rc) return rc;
+    }
     CUDA_TRY(prev_fold.alloc(static_cast<size_t>(plan.npad) * Q));
     CUDA_TRY(cudaMemset(prev_fold.p, 0, prev_fold.bytes()));
     rc = upload_aos(foldi, Q, prev_fold.p);
@@ -1007,12 +1010,12 @@ struct SequentialSolver final : SolverBase {
   }
   int set_populations(const double* fi, const double* foldi) override {
     if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
-    if(fi == nullptr || foldi == nullptr) return fail(LBM_B200_EINVAL, "set_populations needs both f and fold");
+    if(foldi == nullptr) return fail(LBM_B200_EINVAL, "set_populations needs m_fold");
     const size_t nq = static_cast<size_t>(in.n) * Q;
-    CUDA_TRY(cudaMemcpyAsync(d_f.p, fi, nq * sizeof(double), cudaMemcpyHostToDevice, stream));
+    if(fi != nullptr) CUDA_TRY(cudaMemcpyAsync(d_f.p, fi, nq * sizeof(double), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(d_fold.p, foldi, nq * sizeof(double), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
-    h2d_bytes += static_cast<int64_t>(2 * nq * sizeof(double));
+    h2d_bytes += static_cast<int64_t>((fi != nullptr ? 2 : 1) * nq * sizeof(double));
     return LBM_B200_OK;
   }
   int get_vars(double* v, double* vo) override {

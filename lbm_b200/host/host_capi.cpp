@@ -101,4 +101,16 @@ int lbmhost_run(const char* config_path, double* out, double* vars, int64_t nvar
   }
 }
 
+// the reference's solution file (vtk_writer.hpp) from caller-supplied fields: vars = [n][nvar] as m_vars, names = nvar C strings.
+// Returns 0, or -1 if the file cannot be written.  No GPU involved: this is the host-side formatting only.
+int lbmhost_write_points(const char* path, int ndim, int64_t n, const double* center, const uint8_t* keep, int nvar, const double* vars,
+                         const char* const* names) {
+  std::vector<vtk::Column> cols;
+  for(int v = 0; v < nvar; ++v) cols.push_back(vtk::Column{names[v], vars + v, nvar});
+  return vtk::write_points(path, ndim, n, center, keep, cols) ? 0 : -1;
+}
+void lbmhost_round15(const double* in, double* out, int64_t n) {
+  for(int64_t i = 0; i < n; ++i) out[i] = vtk::round15(in[i]);
+}
+
 } // extern "C"

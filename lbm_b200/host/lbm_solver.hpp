@@ -27,6 +27,7 @@
 #include "../../include/lbm_b200.h"
 #include "grid.hpp"
 #include "json.hpp"
+#include "vtk_writer.hpp"
 
 namespace lbmhost {
 
@@ -430,15 +431,56 @@ class LBMSolver final : public Runnable {
     return false;
   }
 
-  // solver.cpp:323-384: the moments of the current fold; written as a VTK PolyData point file (ASCII flavour)
+  // solver.cpp:323-384: the moments of the current fold go to out/<solution_filename>_<step>.vtp in the reference's own binary
+  // VTK flavour (vtk_writer.hpp, byte-identical to the reference's file); "output_format": "ascii" is an extension
   void output(bool forced) {
     if(!((m_timeStep > 0 && m_timeStep % m_solutionInterval == 0) || forced)) return;
     call(lbm_b200_get_moments(m_gpu, vars.data()));
-    if(m_cfg.opt_bool("write_output", true)) writeVtp(m_outputDir + m_solutionName + "_" + std::to_string(m_timeStep) + ".vtp");
+    if(!m_cfg.opt_bool("write_output", true)) return;
+    const std::string stem = m_outputDir + m_solutionName + "_" + std::to_string(m_timeStep);
+    ::mkdir(m_outputDir.c_str(), 0755);
+    const std::string format = m_cfg.opt_str("output_format", "binary");
+    if(format == "ascii") return writeVtpAscii(stem + ".vtp");
+    if(format != "binary") TERMM(-1, "Invalid output_format: " + format);
+    const SolverGrid&     g    = m_grid.g;
+    const int             NVAR = m_ndim + 1;
+    std::vector<uint8_t>  keep = cellFilter();
+    int64_t               nout = 0;
+    for(uint8_t k : keep) nout += k;
+    std::cerr << "  Writing " << stem << ".vtp with #" << nout << " cells" << std::endl; // IO.h:423
+    static const char* names[4] = {"U", "V", "W", "rho"};                                // variables.h: VELSTR, "rho"
+    std::vector<vtk::Column> cols;
+    for(int v = 0; v < NVAR; ++v) cols.push_back(vtk::Column{v == m_ndim ? "rho" : names[v], vars.data() + v, NVAR});
+    if(nout == 0) TERMM(-1, "ERROR: Invalid call to encodeLE() with length = 0"); // base64.h:219-223 (the reference exits there)
+    if(!vtk::write_points(stem + ".vtp", m_ndim, g.n, g.center.data(), keep.data(), cols))
+      TERMM(-1, "Invalid output directory set! (value: " + m_outputDir + ")");
   }
 
-  void writeVtp(const std::string& path) {
-    ::mkdir(m_outputDir.c_str(), 0755);
+  // CellFilterManager (cell_filter.h:60-96) on a single-level grid: every cell is a leaf and sits on the one level there is
+  std::vector<uint8_t> cellFilter() const {
+    const SolverGrid&    g = m_grid.g;
+    std::vector<uint8_t> keep(static_cast<size_t>(g.n), 1);
+    if(!m_cfg.has("cellFilter")) return keep; // default {"cellFilter": "leafCells"} (solver.cpp:86)
+    const Json& fc = m_cfg.at("cellFilter");
+    if(!fc.has("cellFilter")) TERMM(-1, "Invalid output configuration missing \"cellFilter\" key"); // cell_filter.h:78
+    const Json&              f = fc.at("cellFilter");
+    std::vector<std::string> list;
+    if(f.is_array()) TERMM(-1, "untested"); // cell_filter.h:74
+    list.push_back(f.as_string());
+    for(const std::string& name : list) {
+      if(name == "highestLvl" || name == "lowestLvl" || name == "partitionLvl" || name == "leafCells") continue;
+      if(name == "targetLvl") {
+        if(!fc.has("outputLvl")) TERMM(-1, "The required configuration value is missing: outputLvl");
+        if(fc.at("outputLvl").as_int() < g.max_level) TERMM(-1, "Outputting a lvl below the partition lvl is not possible!");
+        if(fc.at("outputLvl").as_int() != g.max_level) std::fill(keep.begin(), keep.end(), uint8_t(0));
+        continue;
+      }
+      TERMM(-1, "Unknown output filter " + name);
+    }
+    return keep;
+  }
+
+  void writeVtpAscii(const std::string& path) {
     const SolverGrid& g = m_grid.g;
     std::ofstream o(path);
     if(!o) TERMM(-1, "Invalid output directory set! (value: " + m_outputDir + ")");

@@ -1,7 +1,9 @@
 """End to end like the reference's test/run.sh: the reference's OWN configuration files through the host mirror
 (grid generator -> transferGrid -> LBMSolver::run on the GPU), pass/fail decided by the in-solver analytic thresholds
 (src/lbm/solver.cpp:457-481), and the printed numbers compared with what the reference binary prints."""
+import hashlib
 import json
+import os
 
 import numpy as np
 import pytest
@@ -10,6 +12,9 @@ from casebuilder import load_golden
 from lbm_b200 import host_api
 
 pytestmark = pytest.mark.gpu
+
+# final solution file of each full run as the reference binary writes it (tests/golden/make_vtp_golden.py --full)
+VTP_FULL = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vtp", "index_full.json")))
 
 
 def run_case(name, tmp_path, **override):
@@ -67,6 +72,12 @@ def test_reference_run_sh_case(name, steps, converged, max_error, l2_error, tmp_
     assert abs(out["max_error"] - max_error) <= 6e-6 * max_error   # the reference prints 6 significant digits
     if l2_error is not None:
         assert abs(out["l2_error"] - l2_error) <= 6e-6 * l2_error
+    # the solution file the run leaves behind: same name, same bytes as the reference's (fields bit-identical, writer byte-identical)
+    ref = VTP_FULL[name]
+    written = tmp_path / "out" / ref["file"]
+    assert written.exists(), sorted(p.name for p in (tmp_path / "out").iterdir())
+    data = written.read_bytes()
+    assert len(data) == ref["bytes"] and hashlib.sha256(data).hexdigest() == ref["sha256"]
 
 
 def test_failed_threshold_terminates_like_termm(tmp_path):
