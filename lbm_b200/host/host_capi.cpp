@@ -109,6 +109,22 @@ int lbmhost_write_points(const char* path, int ndim, int64_t n, const double* ce
   for(int v = 0; v < nvar; ++v) cols.push_back(vtk::Column{names[v], vars + v, nvar});
   return vtk::write_points(path, ndim, n, center, keep, cols) ? 0 : -1;
 }
+// postprocessing type "line" of a configuration on caller-supplied m_vars ([n][ndim+1]): writes what the reference's atEnd hook
+// writes to ./line.csv into `out_path`.  Returns the number of cells on the (last configured) line, -1 on error.
+int64_t lbmhost_postprocess_line(void* h, const double* vars, const char* out_path, char* err, int errlen) {
+  auto* gh = static_cast<GridHandle*>(h);
+  try {
+    if(gh->solver.postprocessLines(3).empty()) gh->solver.setupPostprocess();
+    const auto& lines = gh->solver.postprocessLines(3);
+    if(lines.empty()) return 0;
+    const SolverGrid& g = gh->solver.solverGrid();
+    for(const auto& cells : lines) LBMSolver::writeLineCsv(out_path, cells, g, vars, g.ndim + 1);
+    return static_cast<int64_t>(lines.back().size());
+  } catch(const std::exception& e) {
+    set_err(err, errlen, e.what());
+    return -1;
+  }
+}
 void lbmhost_round15(const double* in, double* out, int64_t n) {
   for(int64_t i = 0; i < n; ++i) out[i] = vtk::round15(in[i]);
 }

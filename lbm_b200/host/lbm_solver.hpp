@@ -10,6 +10,7 @@
 // path here.  TERMM(code, msg) of the reference (src/common/term.h:37) becomes a TermError that main() turns into the same
 // stderr text and exit status.
 #pragma once
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -245,12 +246,13 @@ class LBMSolver final : public Runnable {
   int64_t run() override {
     if(m_benchmark) return runBenchmark();
     loadConfiguration();
+    initPostprocess();
     setupGpu();
+    vars.assign(static_cast<size_t>(m_grid.g.n) * (m_ndim + 1), 0.0);
+    executePostprocess(PP_ATSTART);
     using clk = std::chrono::steady_clock;
     auto    lastInfo = clk::now();
     int64_t lastStep = 0;
-    const int NVAR = m_ndim + 1;
-    vars.assign(static_cast<size_t>(m_grid.g.n) * NVAR, 0.0);
     for(m_timeStep = 0; m_timeStep < m_maxTimeStep && !converged; ++m_timeStep) {
       // writeInfo, solver.cpp:217-230
       if(m_timeStep > 0 && m_timeStep % m_infoInterval == 0) {
@@ -264,6 +266,7 @@ class LBMSolver final : public Runnable {
       output(m_timeStep == m_maxTimeStep - 1 || converged);
     }
     stepsRun = m_timeStep;
+    executePostprocess(PP_ATEND);
     if(m_diverged) TERMM(-1, "Solution diverged");
     if(m_cfg.has("analyticalSolution")) compareToAnalyticalResult();
     std::cout << "LBM Solver finished <||" << std::endl;
@@ -503,6 +506,89 @@ class LBMSolver final : public Runnable {
     }
     o << "</PointData>\n</Piece>\n</PolyData>\n</VTKFile>\n";
   }
+
+  // ---- postprocessing (src/postprocess/postprocessing.h:45-122): functions of type "line" hooked to atStart / beforeTimestep /
+  // afterTimestep / atEnd; each execution writes ./line.csv = x,y,u of the leaf cells whose centre is within half a cell of the line
+  enum PpHook { PP_ATSTART, PP_BEFORETIMESTEP, PP_AFTERTIMESTEP, PP_ATEND, PP_NUM };
+  std::vector<std::vector<int64_t>> m_ppLines[PP_NUM];
+
+  void initPostprocess() {
+    if(!m_cfg.has("postprocessing")) return;
+    const SolverGrid& g = m_grid.g;
+    for(const auto& kv : m_cfg.at("postprocessing").obj) {
+      const Json& conf = kv.second;
+      if(!conf.is_object()) continue; // getAllObjects, configuration.h:281-292
+      if(!conf.has("type")) TERMM(-1, "The required configuration value is missing: type");
+      if(!conf.has("execute")) TERMM(-1, "The required configuration value is missing: execute");
+      if(conf.at("type").as_string() != "line") TERMM(-1, "Invalid functype"); // postprocessing_func.h:7-12
+      const std::string at = conf.at("execute").as_string();
+      int hook = -1;
+      if(at == "atStart") hook = PP_ATSTART;
+      else if(at == "beforeTimestep") hook = PP_BEFORETIMESTEP;
+      else if(at == "afterTimestep") hook = PP_AFTERTIMESTEP;
+      else if(at == "atEnd") hook = PP_ATEND;
+      else TERMM(-1, "Invalid hook");
+      if(hook == PP_BEFORETIMESTEP || hook == PP_AFTERTIMESTEP)
+        TERMM(-1, "postprocessing at every time step would read m_vars back from the GPU each step; only atStart / atEnd are available");
+      // PostprocessCartesianFunctionLine::init (postprocessing_cartesian.h:17-44), Line = Eigen::Hyperplane::Through(A, B)
+      // (common/line.h:7-21): unit normal (-dy, dx) / |AB|, offset -A.n, distance |n.p + offset|
+      if(m_ndim != 2) TERMM(-1, "postprocessing type \"line\" exists for 2D only");
+      if(!conf.has("A")) TERMM(-1, "The required configuration value is missing: A");
+      if(!conf.has("B")) TERMM(-1, "The required configuration value is missing: B");
+      const auto   A = conf.at("A").as_doubles(), B = conf.at("B").as_doubles();
+      const double tx = B[0] - A[0], ty = B[1] - A[1];
+      double       nx = -ty, ny = tx;
+      const double z  = nx * nx + ny * ny;
+      if(z > 0) { const double r = std::sqrt(z); nx /= r; ny /= r; }
+      const double offset = -(A[0] * nx + A[1] * ny);
+      std::vector<int64_t> cells;
+      for(int64_t c = 0; c < g.n; ++c) { // every cell of a single-level grid is a leaf
+        const double distance = std::abs(nx * g.center[c * 2] + ny * g.center[c * 2 + 1] + offset);
+        if(0.5 * g.cell_length >= distance) cells.push_back(c);
+      }
+      // the reference's comparator ("some coordinate is smaller") is not a strict weak ordering; the same std::sort on the same
+      // input reproduces its order (ascending y for the axis-parallel lines of the reference's configurations)
+      std::sort(cells.begin(), cells.end(), [&g](int64_t a, int64_t b) {
+        for(int d = 0; d < 2; ++d)
+          if(g.center[a * 2 + d] < g.center[b * 2 + d]) return true;
+        return false;
+      });
+      m_ppLines[hook].push_back(std::move(cells));
+    }
+  }
+
+  void executePostprocess(int hook) {
+    if(m_ppLines[hook].empty()) return;
+    static const char* hookName[PP_NUM] = {"atStart", "beforeTimestep", "afterTimestep", "atEnd"};
+    std::cerr << "Executing postprocessing at hook:" << hookName[hook] << std::endl;
+    const SolverGrid& g    = m_grid.g;
+    const int         NVAR = m_ndim + 1;
+    if(hook == PP_ATSTART) call(lbm_b200_get_moments(m_gpu, vars.data())); // atEnd: `vars` holds the last, forced output()
+    for(const auto& cells : m_ppLines[hook]) {
+      std::cerr << "  Writing line.csv" << std::endl;
+      writeLineCsv("line.csv", cells, g, vars.data(), NVAR); // relative to the working directory, like the reference
+    }
+  }
+
+ public:
+  // ASCII::writePointsCSV (IO.h:36-81): coordinates at 15 significant digits, values as toStringVector prints them (fixed, 15 decimals)
+  static void writeLineCsv(const std::string& path, const std::vector<int64_t>& cells, const SolverGrid& g, const double* v, int nvar) {
+    std::ofstream o;
+    o << std::setprecision(15);
+    o.open(path);
+    o << "x,y,u\n";
+    for(int64_t c : cells) {
+      std::ostringstream t;
+      t.precision(15);
+      t << std::fixed << v[c * nvar];
+      o << g.center[c * 2] << "," << g.center[c * 2 + 1] << "," << t.str() << "\n";
+    }
+  }
+  // tests: the cell lists of the configured "line" functions, hook by hook
+  void                                     setupPostprocess() { initPostprocess(); }
+  const std::vector<std::vector<int64_t>>& postprocessLines(int hook) const { return m_ppLines[hook]; }
+
+ private:
 
   // solver.cpp:388-482 with analytical_solutions.h:16-33,51-59
   void compareToAnalyticalResult() {

@@ -37,6 +37,8 @@ def lib():
         L.lbmhost_grid_surface_size.restype = C.c_int64
         L.lbmhost_grid_surface_size.argtypes = [vp, C.c_int]
         L.lbmhost_grid_surface_copy.argtypes = [vp, C.c_int, vp, vp]
+        L.lbmhost_postprocess_line.restype = C.c_int64
+        L.lbmhost_postprocess_line.argtypes = [vp, vp, C.c_char_p, C.c_char_p, C.c_int]
         L.lbmhost_run.argtypes = [C.c_char_p, vp, vp, C.c_int64, C.c_char_p, C.c_int]
         _LIB = L
     return _LIB
@@ -65,6 +67,25 @@ def build_grid(config_path):
             surfaces.append((L.lbmhost_grid_surface_name(h, k).decode(), cells, normals))
         return dict(n=n, ndim=ndim, nghbr=nghbr, center=center, props=props, surfaces=surfaces,
                     cell_length=L.lbmhost_grid_cell_length(h))
+    finally:
+        L.lbmhost_grid_free(h)
+
+
+def postprocess_line(config_path, vars_, out_path):
+    """What the reference's postprocessing function "line" (hook atEnd) writes to ./line.csv, from caller-supplied m_vars
+    ([ncells][ndim+1]); returns the number of cells on the line.  Host-side only (grid pipeline + formatting), no GPU."""
+    L = lib()
+    err = C.create_string_buffer(1024)
+    h = L.lbmhost_grid_build(config_path.encode(), err, 1024)
+    if not h:
+        raise RuntimeError(err.value.decode())
+    try:
+        v = np.ascontiguousarray(vars_, dtype=np.float64)
+        assert v.size == L.lbmhost_grid_ncells(h) * (L.lbmhost_grid_ndim(h) + 1)
+        n = L.lbmhost_postprocess_line(h, v.ctypes.data, out_path.encode(), err, 1024)
+        if n < 0:
+            raise RuntimeError(err.value.decode())
+        return int(n)
     finally:
         L.lbmhost_grid_free(h)
 

@@ -53,10 +53,13 @@ def main():
             assert len(files) == 1, (name, files)
             data = open(files[0], "rb").read()
             index[name] = {"file": os.path.basename(files[0]), "bytes": len(data), "sha256": hashlib.sha256(data).hexdigest()}
+            line = os.path.join(tmp, "line.csv")  # postprocessing type "line" (postprocessing.h:104-114), written to the cwd
+            if full and os.path.exists(line):
+                index[name]["line_csv"] = open(line).read()
             if name in KEEP_WHOLE and not full:
                 with gzip.GzipFile(os.path.join(HERE, "vtp", f"{name}.vtp.gz"), "wb", mtime=0) as f:
                     f.write(data)
-            print(name, index[name])
+            print(name, {k: v for k, v in index[name].items() if k != "line_csv"})
         finally:
             shutil.rmtree(tmp)
     json.dump(index, open(os.path.join(HERE, "vtp", "index_full.json" if full else "index.json"), "w"), indent=1, sort_keys=True)

@@ -25,7 +25,12 @@ def run_case(name, tmp_path, **override):
     path = tmp_path / "case.json"
     path.write_text(json.dumps(cfg))
     n = int(spec.golden["ncells"]) * (spec.ndim + 1)
-    return host_api.run(str(path), nvars=n), spec
+    cwd = os.getcwd()
+    os.chdir(tmp_path)  # postprocessing writes ./line.csv, like the reference
+    try:
+        return host_api.run(str(path), nvars=n), spec
+    finally:
+        os.chdir(cwd)
 
 
 def test_couette_reference_case_converges_like_the_reference(tmp_path):
@@ -78,6 +83,8 @@ def test_reference_run_sh_case(name, steps, converged, max_error, l2_error, tmp_
     assert written.exists(), sorted(p.name for p in (tmp_path / "out").iterdir())
     data = written.read_bytes()
     assert len(data) == ref["bytes"] and hashlib.sha256(data).hexdigest() == ref["sha256"]
+    if "line_csv" in ref:  # postprocessing type "line", hook atEnd
+        assert (tmp_path / "line.csv").read_text() == ref["line_csv"]
 
 
 def test_failed_threshold_terminates_like_termm(tmp_path):

@@ -72,6 +72,32 @@ def test_solution_file_is_byte_identical_to_the_reference(name, hostlib, oracle_
     assert hashlib.sha256(data).hexdigest() == INDEX[name]["sha256"]
 
 
+# executed steps of the full runs (tests/test_host_run_gpu.py::RUN_SH); the oracle reaches them in seconds for these three
+LINE_CASES = [("poiseuille", 34250), ("couette_bnd_eq", 14801), ("couette_bnd_eq_aligned", 14801)]
+
+
+@pytest.mark.parametrize("name,steps", LINE_CASES)
+def test_line_csv_matches_the_reference(name, steps, hostlib, oracle_mod, tmp_path):
+    """postprocessing type "line", hook atEnd (postprocessing.h:104-114): ./line.csv of the reference's full run, text for text.
+    Cell selection and order come from the host's grid pipeline, u from the oracle's final moments."""
+    from lbm_b200 import host_api
+    full = json.load(open(os.path.join(HERE, "golden", "vtp", "index_full.json")))
+    spec = load_golden(name)
+    o = spec.apply_to(oracle_mod.Oracle(spec.ndim, spec.ndist, spec.nghbr, spec.omega))
+    o.init()
+    o.step(steps)
+    o.update_moments()
+    v = np.array(o.vars)
+    o.close()
+    cfg = tmp_path / "case.json"
+    cfg.write_text(str(spec.golden["config_orig_json"]))
+    out = tmp_path / "line.csv"
+    n = host_api.postprocess_line(str(cfg), v, str(out))
+    ref = full[name]["line_csv"]
+    assert n == ref.count("\n") - 1
+    assert out.read_text() == ref
+
+
 def test_round15_equals_the_decimal_round_trip(hostlib):
     """round15(x) == float('%.15f' % x) (what toStringVector + std::stod do), including ties, signed zeros, subnormals, big values."""
     rng = np.random.default_rng(7)
