@@ -122,6 +122,14 @@ int lbm_b200_set_ghosts(lbm_b200_solver* s, int64_t nghost);
 int lbm_b200_set_halo(lbm_b200_solver* s, int32_t npeers, const int32_t* peers, const int64_t* send_count,
                       const int64_t* send_cell, const int32_t* send_dir, const int64_t* recv_count,
                       const int64_t* recv_cell, const int32_t* recv_dir);
+/* Velocity halo of the pressure boundary condition.  LBMBnd_Pressure::apply extrapolates the boundary velocity from m_vars of the
+ * two inward neighbours n1 = N(c, inside), n2 = N(n1, inside) (src/lbm/bnd/bnd_pressure.h:68-84).  Where a partition cut separates
+ * a pressure cell from n1 or n2, the owner of the neighbour sends its velocity with every halo exchange.  Per peer of
+ * lbm_b200_set_halo (same order, call it first): send_cell = owned cells whose velocity that peer needs, recv_cell = ghost
+ * cells whose velocity arrives from it; the k-th item a rank sends is the k-th item the peer receives.  The ghost rows of the
+ * table must contain the links c -> n1 -> n2 (lbm_b200/partition.py writes them). */
+int lbm_b200_set_vars_halo(lbm_b200_solver* s, const int64_t* send_count, const int64_t* send_cell, const int64_t* recv_count,
+                           const int64_t* recv_cell);
 /* NCCL bootstrap: rank 0 creates the 128-byte id, the host program broadcasts it (torch.distributed / MPI), every rank
  * calls lbm_b200_comm_init before lbm_b200_init. */
 int lbm_b200_comm_unique_id(char* out128);
@@ -196,7 +204,7 @@ typedef struct {
   const double*   wall_desc; /* [n_wall*4] per wall descriptor Q-1 entries of v0, v1, v2, count */
   int64_t         n_wall;
   const double*   abb_p;     /* [n_abb] pressure of every anti-bounce-back entry */
-  const int32_t*  abb_cells; /* [n_abb*3] device cell, inward neighbours n1, n2 */
+  const int32_t*  abb_cells; /* [n_abb*3] device cell, inward neighbours n1, n2 (< 0: -(slot+1) of the received velocity halo) */
   int64_t         n_abb;
   const double*   values;    /* [n_values] stored slot values (static part filled at init) */
   int64_t         n_values;
@@ -206,6 +214,9 @@ typedef struct {
   int64_t         n_send;
   const int64_t*  recv_index;
   int64_t         n_recv;
+  const int32_t*  vsend_cells; /* [n_vsend] device cells whose velocity is sent, wire order */
+  int64_t         n_vsend;
+  int64_t         n_vrecv;     /* received velocity items */
 } lbm_b200_plan_view;
 int lbm_b200_debug_plan(lbm_b200_solver* s, lbm_b200_plan_view* out);
 

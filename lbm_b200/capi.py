@@ -48,7 +48,8 @@ class PlanView(C.Structure):
         ("addtab", C.POINTER(C.c_double)), ("n_add", C.c_int64), ("wall_desc", C.POINTER(C.c_double)), ("n_wall", C.c_int64),
         ("abb_p", C.POINTER(C.c_double)), ("abb_cells", C.POINTER(C.c_int32)), ("n_abb", C.c_int64),
         ("values", C.POINTER(C.c_double)), ("n_values", C.c_int64), ("stale_ref", C.POINTER(C.c_int64)), ("n_stale", C.c_int64),
-        ("send_index", C.POINTER(C.c_int64)), ("n_send", C.c_int64), ("recv_index", C.POINTER(C.c_int64)), ("n_recv", C.c_int64)]
+        ("send_index", C.POINTER(C.c_int64)), ("n_send", C.c_int64), ("recv_index", C.POINTER(C.c_int64)), ("n_recv", C.c_int64),
+        ("vsend_cells", C.POINTER(C.c_int32)), ("n_vsend", C.c_int64), ("n_vrecv", C.c_int64)]
 
 
 def library_path():
@@ -115,6 +116,7 @@ def load_library():
     pi32 = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
     L.lbm_b200_set_ghosts.argtypes = [vp, i64]
     L.lbm_b200_set_halo.argtypes = [vp, i32, pi32, pi64, pi64, pi32, pi64, pi64, pi32]
+    L.lbm_b200_set_vars_halo.argtypes = [vp, pi64, pi64, pi64, pi64]
     L.lbm_b200_comm_unique_id.argtypes = [C.c_char_p]
     L.lbm_b200_comm_init.argtypes = [vp, C.c_char_p, i32, i32]
     L.lbm_b200_box_rows.argtypes = [i32, pi64, pi32, pi64, i64, pi64, i32, vp]
@@ -213,6 +215,9 @@ class Solver:
         self._check(self._lib.lbm_b200_set_halo(self._h, len(peers), i32a(peers), _i64(send_count), _i64(send_cell), i32a(send_dir),
                                                 _i64(recv_count), _i64(recv_cell), i32a(recv_dir)))
 
+    def set_vars_halo(self, send_count, send_cell, recv_count, recv_cell):
+        self._check(self._lib.lbm_b200_set_vars_halo(self._h, _i64(send_count), _i64(send_cell), _i64(recv_count), _i64(recv_cell)))
+
     def comm_init(self, unique_id, rank, nranks):
         self._check(self._lib.lbm_b200_comm_init(self._h, bytes(unique_id), int(rank), int(nranks)))
 
@@ -242,6 +247,7 @@ class Solver:
         out["stale_ref"] = arr(v.stale_ref, v.n_stale)
         out["send_index"] = arr(v.send_index, v.n_send)
         out["recv_index"] = arr(v.recv_index, v.n_recv)
+        out["vsend_cells"] = arr(v.vsend_cells, v.n_vsend)
         return out
 
     # ---- run

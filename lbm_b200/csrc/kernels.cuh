@@ -538,22 +538,46 @@ __global__ void k_periodic_pressure(const __grid_constant__ DevParams<Real> p, c
   }
 }
 
+// velocity (this step's m_vars) of an inward neighbour of a pressure cell: rebuilt from the populations when this rank owns
+// the cell, taken from the received velocity halo when another rank does (n < 0: -(slot + 1), plan.hpp section 8)
+template <class L, class Real, bool STRICT>
+__device__ __forceinline__ void neighbour_velocity(const DevParams<Real>& p, int32_t n, const Real* __restrict__ vrecv, Real (&u)[L::D]) {
+  if(n < 0) {
+#pragma unroll
+    for(int d = 0; d < L::D; ++d) u[d] = vrecv[static_cast<size_t>(-n - 1) * 3 + d];
+    return;
+  }
+  Real fold[L::Q], rho;
+  gather_any<L, Real, STRICT>(p, p.A, n, fold);
+  Phys<L, Real, STRICT>::moments(fold, rho, u);
+}
+
 // pressure boundary: u_ext = 1.5 u(n1) - 0.5 u(n2) from this step's m_vars  (bnd_pressure.h:78-84)
 template <class L, class Real, bool STRICT>
-__global__ void k_pressure_extrapolate(const __grid_constant__ DevParams<Real> p, int n, Real* __restrict__ uext_next) {
-  using P = Phys<L, Real, STRICT>;
+__global__ void k_pressure_extrapolate(const __grid_constant__ DevParams<Real> p, int n, Real* __restrict__ uext_next,
+                                       const Real* __restrict__ vrecv) {
   using A = Ar<Real, STRICT>;
-  constexpr int Q = L::Q, D = L::D;
+  constexpr int D = L::D;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if(k >= n) return;
   const AbbDev<Real> e = p.tabs.abb[k];
-  Real fold[Q], rho, u1[D], u2[D];
-  gather_any<L, Real, STRICT>(p, p.A, e.n1, fold);
-  P::moments(fold, rho, u1);
-  gather_any<L, Real, STRICT>(p, p.A, e.n2, fold);
-  P::moments(fold, rho, u2);
+  Real u1[D], u2[D];
+  neighbour_velocity<L, Real, STRICT>(p, e.n1, vrecv, u1);
+  neighbour_velocity<L, Real, STRICT>(p, e.n2, vrecv, u2);
 #pragma unroll
   for(int d = 0; d < D; ++d) uext_next[static_cast<size_t>(k) * 3 + d] = A::sub(A::mul(Real(1.5), u1[d]), A::mul(Real(0.5), u2[d]));
+}
+
+// velocity halo, sending side: this step's m_vars velocity of the listed owned cells, 3 reals per item (wire order)
+template <class L, class Real, bool STRICT>
+__global__ void k_velocity_pack(const __grid_constant__ DevParams<Real> p, const int32_t* __restrict__ cells, int n, Real* __restrict__ out) {
+  constexpr int D = L::D;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if(k >= n) return;
+  Real u[D];
+  neighbour_velocity<L, Real, STRICT>(p, cells[k], nullptr, u);
+#pragma unroll
+  for(int d = 0; d < 3; ++d) out[static_cast<size_t>(k) * 3 + d] = d < D ? u[d < D ? d : 0] : Real(0);
 }
 
 // what the boundary conditions write into m_vars after the moments pass (residual bookkeeping only)

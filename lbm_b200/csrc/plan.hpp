@@ -64,6 +64,8 @@ struct PlanInput {
   std::vector<int64_t> send_count, recv_count;
   std::vector<int64_t> send_cell, recv_cell;
   std::vector<int32_t> send_dir, recv_dir;
+  // velocity halo of the pressure boundary condition: per peer, owned cells whose velocity is sent / ghost cells that receive one
+  std::vector<int64_t> vsend_count, vrecv_count, vsend_cell, vrecv_cell;
 };
 
 struct CopySrc { int32_t cell, dir; };
@@ -107,6 +109,8 @@ struct Plan {
   int64_t slots_bc = 0, slots_stale = 0;
   int64_t n_owned = 0, n_ghost = 0, ghost_begin = 0; // device range [ghost_begin, ghost_begin + n_ghost) holds the ghosts
   std::vector<int64_t> send_index, recv_index;       // flat device indices dir * npad + cell, wire order
+  std::vector<int32_t> vsend_cells;                  // device cells whose velocity travels with the halo, wire order
+  int64_t              n_vrecv = 0;                  // velocity items received (3 reals each)
   std::string error;
 };
 
@@ -754,7 +758,45 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
   for(auto& s : stale_slots) P.stale_ref.push_back(static_cast<int64_t>(P.ref2dev[s.first]) * Q + s.second);
 
   // ---- 8. translate the remaining reference ids to device ids
-  for(AbbEntry& e : P.abb) { e.cell = P.ref2dev[e.cell]; e.n1 = P.ref2dev[e.n1]; e.n2 = P.ref2dev[e.n2]; }
+  {
+    // inward neighbours of a pressure cell that another rank owns: their velocity arrives with the halo; the entry then
+    // refers to the slot of the receive buffer, encoded as -(slot + 1)
+    int64_t nvs = 0, nvr = 0;
+    for(int64_t v : in.vsend_count) nvs += v;
+    for(int64_t v : in.vrecv_count) nvr += v;
+    if(nvs != static_cast<int64_t>(in.vsend_cell.size()) || nvr != static_cast<int64_t>(in.vrecv_cell.size())
+       || (!in.vsend_count.empty() && in.vsend_count.size() != in.peers.size()) || (!in.vrecv_count.empty() && in.vrecv_count.size() != in.peers.size())) {
+      P.error = "velocity halo lists are inconsistent";
+      return false;
+    }
+    std::unordered_map<int64_t, int32_t> vslot;
+    for(size_t k = 0; k < in.vrecv_cell.size(); ++k) {
+      const int64_t c = in.vrecv_cell[k];
+      if(c < NO || c >= N) { P.error = "velocity halo receive entry is not a ghost cell"; return false; }
+      vslot.emplace(c, static_cast<int32_t>(k)); // a ghost may be listed more than once: every copy carries the same value
+    }
+    P.n_vrecv = nvr;
+    P.vsend_cells.resize(in.vsend_cell.size());
+    for(size_t k = 0; k < in.vsend_cell.size(); ++k) {
+      const int64_t c = in.vsend_cell[k];
+      if(c < 0 || c >= NO) { P.error = "velocity halo send entry is not an owned cell"; return false; }
+      P.vsend_cells[k] = P.ref2dev[c];
+    }
+    auto nb_dev = [&](int32_t ref, int32_t* out) -> bool {
+      if(ref < NO) { *out = P.ref2dev[ref]; return true; }
+      auto it = vslot.find(ref);
+      if(it == vslot.end()) return false;
+      *out = -(it->second + 1);
+      return true;
+    };
+    for(AbbEntry& e : P.abb) {
+      e.cell = P.ref2dev[e.cell];
+      if(!nb_dev(e.n1, &e.n1) || !nb_dev(e.n2, &e.n2)) {
+        P.error = "pressure boundary: an inward neighbour belongs to another rank and lbm_b200_set_vars_halo does not list it";
+        return false;
+      }
+    }
+  }
   for(ForceEntry& e : P.force) { e.target = P.ref2dev[e.target]; e.val = P.ref2dev[e.val]; }
   for(PerPEntry& e : P.perp) { e.cell = P.ref2dev[e.cell]; e.vbase += static_cast<int32_t>(P.n_values_static); }
   for(VarFix& v : P.varfix) v.cell = P.ref2dev[v.cell];

@@ -107,6 +107,8 @@ struct Solver final : SolverBase {
   DevBuf<unsigned long long> d_ticket; // [0]: inner / whole-domain launches, [1]: outer launches
   unsigned long long ticket_next[2] = {0, 0};
   DevBuf<Real>     d_sendbuf, d_recvbuf;
+  DevBuf<int32_t>  d_vsend_cells;          // velocity halo of the pressure boundary condition
+  DevBuf<Real>     d_vsendbuf, d_vrecvbuf; // 3 reals per item
   int64_t          halo_bytes = 0;
   int64_t          h2d_bytes = 0, d2h_bytes = 0;
   int cur = 0;       // f[cur] holds the current post-collision populations
@@ -208,7 +210,11 @@ struct Solver final : SolverBase {
       CUDA_TRY(d_recv_idx.upload(plan.recv_index));
       CUDA_TRY(d_sendbuf.alloc(plan.send_index.size() + 1));
       CUDA_TRY(d_recvbuf.alloc(plan.recv_index.size() + 1));
+      CUDA_TRY(d_vsend_cells.upload(plan.vsend_cells));
+      CUDA_TRY(d_vsendbuf.alloc(plan.vsend_cells.size() * 3 + 3));
     }
+    CUDA_TRY(d_vrecvbuf.alloc(static_cast<size_t>(plan.n_vrecv) * 3 + 3)); // never null: the pressure kernel takes the pointer
+    CUDA_TRY(cudaMemset(d_vrecvbuf.p, 0, d_vrecvbuf.bytes()));
     {
       std::vector<lbm::CopySrcDev> h;
       for(auto& c : plan.copytab) h.push_back({c.cell, c.dir});
@@ -341,45 +347,56 @@ struct Solver final : SolverBase {
     return (s + 1) % k == 0 || (s + 2) % k == 0;
   }
 
+  // phase 1: forcing, periodic-with-pressure values; phase 2: pressure extrapolation (needs the velocity halo of THIS step when
+  // a partition cut separates a pressure cell from its inward neighbours) and the m_vars fix-ups.  nd = the dynamic buffers
+  // written for the next step; the caller flips `dyn` once both phases have run.
   template <bool STRICT>
-  int aux_kernels(const lbm::DevParams<Real>& p, Real* vars_out) {
-    const int nd = dyn ^ 1;
+  int aux_kernels(const lbm::DevParams<Real>& p, Real* vars_out, int nd, int phases, bool* dyn_written_out) {
     bool dyn_written = false;
-    if(d_force.n > 0) {
+    if((phases & 1) && d_force.n > 0) {
       const int n = static_cast<int>(d_force.n);
       lbm::k_forcing<L, Real, STRICT><<<(n + 127) / 128, 128, 0, stream>>>(p, d_force.p, n);
       ++launches;
     }
-    if(d_perp.n > 0) {
+    if((phases & 1) && d_perp.n > 0) {
       const int n = static_cast<int>(d_perp.n);
       lbm::k_periodic_pressure<L, Real, STRICT><<<(n + 127) / 128, 128, 0, stream>>>(p, d_perp.p, n, d_values[nd].p);
       ++launches;
       dyn_written = true;
     }
-    if(d_abb.n > 0) {
+    if((phases & 2) && d_abb.n > 0) {
       const int n = static_cast<int>(d_abb.n);
-      lbm::k_pressure_extrapolate<L, Real, STRICT><<<(n + 127) / 128, 128, 0, stream>>>(p, n, d_uext[nd].p);
+      lbm::k_pressure_extrapolate<L, Real, STRICT><<<(n + 127) / 128, 128, 0, stream>>>(p, n, d_uext[nd].p, d_vrecvbuf.p);
       ++launches;
       dyn_written = true;
     }
-    if(vars_out != nullptr && d_varfix.n > 0) {
+    if((phases & 2) && vars_out != nullptr && d_varfix.n > 0) {
       const int n = static_cast<int>(d_varfix.n);
       lbm::k_varfix<Real><<<(n + 127) / 128, 128, 0, stream>>>(d_varfix.p, n, d_uext[nd].p, vars_out, plan.npad);
       ++launches;
     }
-    if(dyn_written) dyn = nd;
+    if(dyn_written) *dyn_written_out = true;
     CUDA_TRY(cudaGetLastError());
     return LBM_B200_OK;
   }
 
   // Outgoing populations of this step -> peers, theirs -> my ghost cells.  One pack kernel, one NCCL group of
   // send/recv pairs over NVLink, one unpack kernel, all on the solver's stream.
-  int halo_exchange(Real* buf, cudaStream_t stream, cudaEvent_t after_pack = nullptr) {
+  // `vp` (only with a velocity halo): the parameters of this step, from which the sending side rebuilds the velocity of the
+  // cells a peer's pressure boundary condition extrapolates from.
+  int halo_exchange(Real* buf, cudaStream_t stream, cudaEvent_t after_pack = nullptr, const lbm::DevParams<Real>* vp = nullptr) {
     if(in.peers.empty()) return LBM_B200_OK;
     auto& nc = lbm::nccl_api();
     const int64_t ns = static_cast<int64_t>(plan.send_index.size()), nr = static_cast<int64_t>(plan.recv_index.size());
     if(ns > 0) {
       lbm::k_halo_pack<Real><<<static_cast<int>((ns + 255) / 256), 256, 0, stream>>>(buf, d_send_idx.p, ns, d_sendbuf.p);
+      ++launches;
+    }
+    const bool with_velocity = vp != nullptr && has_velocity_halo();
+    if(with_velocity && !plan.vsend_cells.empty()) {
+      const int n = static_cast<int>(plan.vsend_cells.size());
+      if(cfg.arithmetic == LBM_B200_STRICT) lbm::k_velocity_pack<L, Real, true><<<(n + 127) / 128, 128, 0, stream>>>(*vp, d_vsend_cells.p, n, d_vsendbuf.p);
+      else lbm::k_velocity_pack<L, Real, false><<<(n + 127) / 128, 128, 0, stream>>>(*vp, d_vsend_cells.p, n, d_vsendbuf.p);
       ++launches;
     }
     if(after_pack != nullptr) CUDA_TRY(cudaEventRecord(after_pack, stream));
@@ -392,6 +409,17 @@ struct Solver final : SolverBase {
       so += in.send_count[k];
       ro += in.recv_count[k];
     }
+    if(with_velocity) { // second message per peer pair, matched in order inside the same group
+      int64_t vso = 0, vro = 0;
+      for(size_t k = 0; k < in.peers.size(); ++k) {
+        const int64_t vs = in.vsend_count.empty() ? 0 : in.vsend_count[k], vr = in.vrecv_count.empty() ? 0 : in.vrecv_count[k];
+        if(vs > 0) NCCL_TRY(nc.Send(d_vsendbuf.p + 3 * vso, static_cast<size_t>(3 * vs), dt, in.peers[k], comm, stream));
+        if(vr > 0) NCCL_TRY(nc.Recv(d_vrecvbuf.p + 3 * vro, static_cast<size_t>(3 * vr), dt, in.peers[k], comm, stream));
+        vso += vs;
+        vro += vr;
+        halo_bytes += 3 * (vs + vr) * static_cast<int64_t>(sizeof(Real));
+      }
+    }
     NCCL_TRY(nc.GroupEnd());
     if(nr > 0) {
       lbm::k_halo_unpack<Real><<<static_cast<int>((nr + 255) / 256), 256, 0, stream>>>(buf, d_recv_idx.p, nr, d_recvbuf.p);
@@ -401,6 +429,8 @@ struct Solver final : SolverBase {
     CUDA_TRY(cudaGetLastError());
     return LBM_B200_OK;
   }
+
+  bool has_velocity_halo() const { return !in.vsend_cell.empty() || !in.vrecv_cell.empty(); }
 
   int one_step(bool time_main) {
     const int src = cur, dst = cur ^ 1;
@@ -428,7 +458,7 @@ struct Solver final : SolverBase {
       }
     };
     const bool has_aux = d_force.n > 0 || d_perp.n > 0 || d_abb.n > 0 || (vout != nullptr && d_varfix.n > 0);
-    const bool overlap = !in.peers.empty() && !has_aux && overlap_enabled;
+    const bool overlap = !in.peers.empty() && !has_aux && !has_velocity_halo() && overlap_enabled;
     if(halo_pending) { // ghosts of the buffer we are about to read were filled on the communication stream
       CUDA_TRY(cudaStreamWaitEvent(stream, ev_halo, 0));
       halo_pending = false;
@@ -455,10 +485,25 @@ struct Solver final : SolverBase {
       launch(0, plan.n_gen, 0, plan.n_fast_chunks, max_resident, 0);
       if(time_main) cudaEventRecord(evm1, stream);
       CUDA_TRY(cudaGetLastError());
-      rc = cfg.arithmetic == LBM_B200_STRICT ? aux_kernels<true>(p, vout) : aux_kernels<false>(p, vout);
-      if(rc != LBM_B200_OK) return rc;
-      rc = halo_exchange(f[dst].p, stream);
-      if(rc != LBM_B200_OK) return rc;
+      const int  nd = dyn ^ 1;
+      bool       dyn_written = false;
+      const bool strict = cfg.arithmetic == LBM_B200_STRICT;
+      auto aux = [&](int phases) { return strict ? aux_kernels<true>(p, vout, nd, phases, &dyn_written) : aux_kernels<false>(p, vout, nd, phases, &dyn_written); };
+      if(has_velocity_halo()) {
+        // the pressure extrapolation of this step reads velocities that arrive with this step's exchange
+        rc = aux(1);
+        if(rc != LBM_B200_OK) return rc;
+        rc = halo_exchange(f[dst].p, stream, nullptr, &p);
+        if(rc != LBM_B200_OK) return rc;
+        rc = aux(2);
+        if(rc != LBM_B200_OK) return rc;
+      } else {
+        rc = aux(3);
+        if(rc != LBM_B200_OK) return rc;
+        rc = halo_exchange(f[dst].p, stream);
+        if(rc != LBM_B200_OK) return rc;
+      }
+      if(dyn_written) dyn = nd;
     }
     if(vout != nullptr) {
       vcur ^= 1;
@@ -680,6 +725,7 @@ struct Solver final : SolverBase {
     v->stale_ref = plan.stale_ref.data(); v->n_stale = static_cast<int64_t>(plan.stale_ref.size());
     v->send_index = plan.send_index.data(); v->n_send = static_cast<int64_t>(plan.send_index.size());
     v->recv_index = plan.recv_index.data(); v->n_recv = static_cast<int64_t>(plan.recv_index.size());
+    v->vsend_cells = plan.vsend_cells.data(); v->n_vsend = static_cast<int64_t>(plan.vsend_cells.size()); v->n_vrecv = plan.n_vrecv;
     return LBM_B200_OK;
   }
 
@@ -1294,6 +1340,28 @@ int lbm_b200_set_halo(lbm_b200_solver* s, int32_t npeers, const int32_t* peers, 
   in.send_dir.assign(send_dir, send_dir + ns);
   in.recv_cell.assign(recv_cell, recv_cell + nr);
   in.recv_dir.assign(recv_dir, recv_dir + nr);
+  return LBM_B200_OK;
+}
+
+int lbm_b200_set_vars_halo(lbm_b200_solver* s, const int64_t* send_count, const int64_t* send_cell, const int64_t* recv_count,
+                           const int64_t* recv_cell) {
+  CHECK_HANDLE(s);
+  CHECK_NOT_INITED(s);
+  auto& in = s->impl->in;
+  const size_t np = in.peers.size();
+  if(np == 0) return fail(LBM_B200_ESTATE, "lbm_b200_set_vars_halo: call lbm_b200_set_halo first (the peer list is shared)");
+  if(send_count == nullptr || recv_count == nullptr) return fail(LBM_B200_EINVAL, "null argument");
+  int64_t ns = 0, nr = 0;
+  for(size_t k = 0; k < np; ++k) {
+    if(send_count[k] < 0 || recv_count[k] < 0) return fail(LBM_B200_EINVAL, "negative velocity halo count");
+    ns += send_count[k];
+    nr += recv_count[k];
+  }
+  if((ns > 0 && send_cell == nullptr) || (nr > 0 && recv_cell == nullptr)) return fail(LBM_B200_EINVAL, "null velocity halo list");
+  in.vsend_count.assign(send_count, send_count + np);
+  in.vrecv_count.assign(recv_count, recv_count + np);
+  in.vsend_cell.assign(send_cell, send_cell + ns);
+  in.vrecv_cell.assign(recv_cell, recv_cell + nr);
   return LBM_B200_OK;
 }
 

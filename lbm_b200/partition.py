@@ -85,6 +85,12 @@ class LocalProblem:
     send_dir: np.ndarray = None
     recv_cell: np.ndarray = None
     recv_dir: np.ndarray = None
+    # velocity halo of the pressure boundary condition (bnd_pressure.h:78-84 reads m_vars of the two inward neighbours):
+    # per peer, the owned cells whose velocity the peer's pressure cells extrapolate from / the ghost cells that receive one
+    vsend_count: list = field(default_factory=list)
+    vrecv_count: list = field(default_factory=list)
+    vsend_cell: np.ndarray = None      # local ids of owned cells
+    vrecv_cell: np.ndarray = None      # local ids of ghost cells
 
     @property
     def n_owned(self):
@@ -116,21 +122,80 @@ class LocalProblem:
     def apply_halo(self, solver):
         solver.set_ghosts(self.n_ghost)
         solver.set_halo(self.peers, self.send_count, self.send_cell, self.send_dir, self.recv_count, self.recv_cell, self.recv_dir)
+        if sum(self.vsend_count) + sum(self.vrecv_count) > 0:
+            solver.set_vars_halo(self.vsend_count, self.vsend_cell, self.vrecv_count, self.vrecv_cell)
 
 
-def plan_rank(provider, rank, world, stride):
+def inward_direction(normals):
+    """LBMBnd_Pressure::apply (bnd_pressure.h:58-66): the inside direction is the axis direction against the first non-zero
+    component of the normal."""
+    normals = np.asarray(normals, dtype=np.float64)
+    ins = np.full(len(normals), -1, dtype=np.int64)
+    for d in range(normals.shape[1] - 1, -1, -1):
+        ins = np.where(normals[:, d] < 0, 2 * d + 1, np.where(normals[:, d] > 0, 2 * d, ins))
+    return ins
+
+
+def pressure_stencil(provider, pressure):
+    """For every entry of every pressure surface (application order): the cell and its two inward neighbours, global ids."""
+    cs, n1s, n2s = [], [], []
+    for cells, normals in pressure:
+        cells = np.asarray(cells, dtype=np.int64)
+        if len(cells) == 0:
+            continue
+        ins = inward_direction(normals)
+        if (ins < 0).any():
+            raise ValueError("pressure boundary: zero normal")
+        n1 = np.ascontiguousarray(provider.rows(cells)[np.arange(len(cells)), ins])
+        if (n1 < 0).any():
+            raise ValueError("pressure boundary: cell without two inward neighbours")
+        n2 = np.ascontiguousarray(provider.rows(n1)[np.arange(len(cells)), ins])
+        if (n2 < 0).any():
+            raise ValueError("pressure boundary: cell without two inward neighbours")
+        cs.append(cells)
+        n1s.append(n1)
+        n2s.append(n2)
+    if not cs:
+        z = np.zeros(0, dtype=np.int64)
+        return z, z, z
+    c, n1, n2 = np.concatenate(cs), np.concatenate(n1s), np.concatenate(n2s)
+    # the reference applies the entries one after the other and reads m_vars of n1 / n2: a neighbour that an earlier entry
+    # has already rewritten makes the result order-dependent (plan.hpp rejects the same thing inside one rank)
+    first = {}
+    for k, cell in enumerate(c.tolist()):
+        first.setdefault(cell, k)
+    for k in range(len(c)):
+        for nb in (int(n1[k]), int(n2[k])):
+            if first.get(nb, len(c)) < k:
+                raise ValueError("pressure boundary: inward neighbour is itself a pressure boundary cell (order-dependent in the reference)")
+    return c, n1, n2
+
+
+def plan_rank(provider, rank, world, stride, pressure=None):
+    """pressure: [(cells, normals), ...] = the GLOBAL cell lists of all pressure boundary conditions in application order (every
+    rank passes the same lists); needed only when such a surface exists, so that the velocity of inward neighbours that
+    another rank owns travels with the halo."""
     n, qm = provider.n, provider.qm
     b = bounds(n, world)
     lo, hi = int(b[rank]), int(b[rank + 1])
     own = np.arange(lo, hi, dtype=np.int64)
     rows_own = provider.rows(own)
     src_own = provider.sources(own)
+    owner_of = lambda g: np.searchsorted(b, g, side="right") - 1
 
     def outside(a):
         a = a[a >= 0]
         return a[(a < lo) | (a >= hi)]
 
-    ghosts = np.unique(np.concatenate([outside(rows_own.ravel()), outside(src_own.ravel())]))
+    # velocity halo: items (entry, which of n1 / n2) whose pressure cell and inward neighbour have different owners, in entry order
+    pc, pn1, pn2 = pressure_stencil(provider, pressure or [])
+    item_cell = np.stack([pc, pc], axis=1).ravel()
+    item_nb = np.stack([pn1, pn2], axis=1).ravel()
+    item_cown, item_nown = owner_of(item_cell), owner_of(item_nb)
+    v_recv = (item_cown == rank) & (item_nown != rank)   # I own the pressure cell, a peer owns the neighbour
+    v_send = (item_nown == rank) & (item_cown != rank)   # I own the neighbour, a peer owns the pressure cell
+
+    ghosts = np.unique(np.concatenate([outside(rows_own.ravel()), outside(src_own.ravel()), item_nb[v_recv]]))
     lp = LocalProblem(rank=rank, world=world, lo=lo, hi=hi, ghosts=ghosts, nghbr=None)
     n_local = (hi - lo) + len(ghosts)
     table = np.full((n_local, stride), -1, dtype=np.int64)
@@ -140,7 +205,6 @@ def plan_rank(provider, rank, world, stride):
         into_me = (rows_g >= lo) & (rows_g < hi)
         table[hi - lo:, :qm] = np.where(into_me, rows_g - lo, -1)
     lp.nghbr = table
-    owner_of = lambda g: np.searchsorted(b, g, side="right") - 1
     # send: my cell s pushes (direction j) into a cell another rank owns
     s_idx, s_dir = np.nonzero((rows_own >= 0) & ((rows_own < lo) | (rows_own >= hi)))
     s_owner = owner_of(rows_own[s_idx, s_dir])
@@ -150,7 +214,27 @@ def plan_rank(provider, rank, world, stride):
         g_owner = owner_of(ghosts[g_idx])
     else:
         g_idx = g_dir = g_owner = np.zeros(0, dtype=np.int64)
-    peers = sorted(set(s_owner.tolist()) | set(g_owner.tolist()))
+    # the pressure boundary condition finds n1 = N(c, inside), n2 = N(n1, inside) in the table: give it the links of the
+    # ghost cells it walks over (ghost rows otherwise only keep links into owned cells)
+    if len(pc):
+        mine = item_cown[0::2] == rank
+        ins_dir = np.zeros(len(pc), dtype=np.int64)
+        k0 = 0
+        for cells, normals in pressure:
+            ins_dir[k0:k0 + len(cells)] = inward_direction(normals)
+            k0 += len(cells)
+        l1, l2 = lp.to_local(pn1[mine]), lp.to_local(pn2[mine])
+        assert (l1 >= 0).all() and (l2 >= 0).all()
+        table[l1, ins_dir[mine]] = l2
+    peers = sorted(set(s_owner.tolist()) | set(g_owner.tolist()) | set(item_cown[v_send].tolist()) | set(item_nown[v_recv].tolist()))
+    vs, vr = [], []
+    for q in peers:
+        m = v_send & (item_cown == q)
+        vs.append(item_nb[m] - lo)
+        lp.vsend_count.append(int(m.sum()))
+        m = v_recv & (item_nown == q)
+        vr.append(lp.to_local(item_nb[m]))
+        lp.vrecv_count.append(int(m.sum()))
     sc, sd, rc, rd = [], [], [], []
     for q in peers:
         m = s_owner == q
@@ -165,4 +249,5 @@ def plan_rank(provider, rank, world, stride):
     lp.peers = [int(q) for q in peers]
     lp.send_cell, lp.send_dir = cat(sc, np.int64), cat(sd, np.int32)
     lp.recv_cell, lp.recv_dir = cat(rc, np.int64), cat(rd, np.int32)
+    lp.vsend_cell, lp.vrecv_cell = cat(vs, np.int64), cat(vr, np.int64)
     return lp

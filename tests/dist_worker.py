@@ -25,14 +25,18 @@ from oracle import oracle  # noqa: E402
 OMEGA = 1.0 / 0.6
 
 
-def bcs_for(g, ndim):
+def bcs_for(g, ndim, pressure=False):
     names = ["-x", "+x", "-y", "+y", "-z", "+z"][:2 * ndim]
     out = []
     for nm in sorted(names):
         cells, normals = g["surfaces"][nm]
         if len(cells) == 0:
             continue
-        if nm == names[-1]:
+        if pressure and nm in ("-x", "+x"):
+            # anti-bounce-back pressure in- and outlet (sphere_ns.json / step_ns.json of the reference); the wall surfaces that
+            # come first in the order own the edge cells' wall slots, the pressure surface rewrites their x slots afterwards
+            out.append(("pressure", cells, normals, 1.0005 if nm == "-x" else 1.0))
+        elif nm == names[-1]:
             v = np.zeros(ndim)
             v[0] = 0.05
             out.append(("dirichlet", cells, normals, v))
@@ -49,6 +53,8 @@ def add_bcs(solver, bcs, lp=None):
                 continue
         if kind == "dirichlet":
             solver.add_dirichlet_bb(cells, normals, val)
+        elif kind == "pressure":
+            solver.add_pressure(cells, normals, val)
         else:
             solver.add_wall_bb(cells, normals, val)
 
@@ -75,16 +81,40 @@ def exchange_host(lp, f):
         f[lp.recv_cell[ro:ro + nr], lp.recv_dir[ro:ro + nr]] = rb.numpy()
 
 
+def exchange_velocity_host(lp, vars_, ndim):
+    """velocity halo of the pressure boundary condition: m_vars velocity of the listed owned cells -> the peers' ghost cells"""
+    ops, recv_bufs = [], []
+    so = ro = 0
+    for k, q in enumerate(lp.peers):
+        ns, nr = lp.vsend_count[k], lp.vrecv_count[k]
+        if ns:
+            sb = torch.from_numpy(np.ascontiguousarray(vars_[lp.vsend_cell[so:so + ns], :ndim]))
+            ops.append(dist.P2POp(dist.isend, sb, q))
+        if nr:
+            rb = torch.empty((nr, ndim), dtype=torch.float64)
+            recv_bufs.append((rb, ro, nr))
+            ops.append(dist.P2POp(dist.irecv, rb, q))
+        so += ns
+        ro += nr
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    for rb, ro, nr in recv_bufs:
+        vars_[lp.vrecv_cell[ro:ro + nr], :ndim] = rb.numpy()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mode", default="oracle")
     ap.add_argument("--shape", default="16,12,10")
     ap.add_argument("--ndist", type=int, default=19)
     ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--bc", default="walls", help="walls: periodic x, walls, moving lid; pressure: pressure in-/outlet on -x/+x")
     args = ap.parse_args()
     shape = tuple(int(x) for x in args.shape.split(","))
     ndim = len(shape)
-    periodic = (True,) + (False,) * (ndim - 1)
+    with_pressure = args.bc == "pressure"
+    periodic = (not with_pressure,) + (False,) * (ndim - 1)
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.mode == "gpu":
@@ -95,7 +125,8 @@ def main():
 
     g = box_grid(shape, periodic)
     stride = g["nghbr"].shape[1]
-    bcs = bcs_for(g, ndim)
+    bcs = bcs_for(g, ndim, with_pressure)
+    pressure = [(cells, normals) for kind, cells, normals, _ in bcs if kind == "pressure"]
     # single-domain reference run (CPU oracle)
     ref = oracle.Oracle(ndim, args.ndist, g["nghbr"], OMEGA)
     add_bcs(ref, bcs)
@@ -103,15 +134,20 @@ def main():
     ref.step(args.steps)
 
     # partition: the table-driven provider and the on-demand box provider must give the same plan
-    lp = partition.plan_rank(partition.TableRows(g["nghbr"], args.ndist), rank, world, stride)
-    lp2 = partition.plan_rank(partition.BoxRows(shape, [int(p) for p in periodic], args.ndist), rank, world, stride)
+    lp = partition.plan_rank(partition.TableRows(g["nghbr"], args.ndist), rank, world, stride, pressure)
+    lp2 = partition.plan_rank(partition.BoxRows(shape, [int(p) for p in periodic], args.ndist), rank, world, stride, pressure)
     assert np.array_equal(lp.nghbr, lp2.nghbr) and np.array_equal(lp.ghosts, lp2.ghosts)
     assert lp.peers == lp2.peers and np.array_equal(lp.send_cell, lp2.send_cell) and np.array_equal(lp.recv_dir, lp2.recv_dir)
+    assert np.array_equal(lp.vsend_cell, lp2.vsend_cell) and np.array_equal(lp.vrecv_cell, lp2.vrecv_cell)
     # send counts of mine must equal the receive counts of the peer
     counts = [None] * world
-    dist.all_gather_object(counts, {q: (lp.send_count[k], lp.recv_count[k]) for k, q in enumerate(lp.peers)})
+    dist.all_gather_object(counts, {q: (lp.send_count[k], lp.recv_count[k], lp.vsend_count[k], lp.vrecv_count[k]) for k, q in enumerate(lp.peers)})
     for k, q in enumerate(lp.peers):
-        assert counts[q][rank] == (lp.recv_count[k], lp.send_count[k]), "halo lists of the two sides do not match"
+        assert counts[q][rank] == (lp.recv_count[k], lp.send_count[k], lp.vrecv_count[k], lp.vsend_count[k]), "halo lists of the two sides do not match"
+    nvel = [None] * world
+    dist.all_gather_object(nvel, sum(lp.vrecv_count))
+    if with_pressure and world > 1:
+        assert sum(nvel) > 0, "test set-up: no pressure cell is separated from its inward neighbours by the cut"
 
     if args.mode == "oracle":
         o = oracle.Oracle(ndim, args.ndist, lp.nghbr, OMEGA)
@@ -120,6 +156,7 @@ def main():
         for _ in range(args.steps):
             o.step_collide()
             exchange_host(lp, o.f)
+            exchange_velocity_host(lp, o.vars, ndim)
             o.step_stream()
         mine_f, mine_fold = o.f[:lp.n_owned].copy(), o.fold[:lp.n_owned].copy()
     else:

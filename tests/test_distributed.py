@@ -19,10 +19,10 @@ def free_port():
     return p
 
 
-def launch(world, mode, shape, ndist, steps=12, timeout=600):
+def launch(world, mode, shape, ndist, steps=12, timeout=600, bc="walls"):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(free_port()), os.path.join(HERE, "dist_worker.py"), "--mode", mode, "--shape", shape,
-           "--ndist", str(ndist), "--steps", str(steps)]
+           "--ndist", str(ndist), "--steps", str(steps), "--bc", bc]
     env = dict(os.environ, OMP_NUM_THREADS="2")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     assert r.returncode == 0 and "PARTITION_PARITY OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
@@ -33,6 +33,12 @@ def test_partitioned_oracle_matches_single_domain_gloo(world, shape, ndist):
     launch(world, "oracle", shape, ndist)
 
 
+@pytest.mark.parametrize("world,shape,ndist", [(2, "18,16,16", 19), (3, "10,10,10", 27), (2, "34,64", 9), (3, "10,40", 9)])
+def test_partitioned_pressure_boundary_velocity_halo_gloo(world, shape, ndist):
+    """Pressure in-/outlet whose inward neighbours lie across the cut: the velocity halo."""
+    launch(world, "oracle", shape, ndist, bc="pressure")
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape,ndist", [("32,32,32", 19), ("24,16,16", 27), ("64,64", 9)])
 def test_partitioned_gpu_matches_single_domain_nccl(shape, ndist):
@@ -40,3 +46,12 @@ def test_partitioned_gpu_matches_single_domain_nccl(shape, ndist):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     launch(2, "gpu", shape, ndist)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,ndist", [("18,16,16", 19), ("17,16,16", 27), ("34,64", 9)])
+def test_partitioned_gpu_pressure_boundary_nccl(shape, ndist):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    launch(2, "gpu", shape, ndist, bc="pressure")

@@ -121,3 +121,106 @@ def test_partitioned_plan_ghost_blocks_and_halo_lists(world, oracle_mod):
         assert np.array_equal(mine, o.fold[own]), f"rank {r}"
     # the chunks at the cut stay on the index-free path wherever a chunk touches at most one wall
     assert sum(p["n_fast_chunks"] for p in plans) > 0 or world > 2
+
+
+def _pressure_box(shape, ndist):
+    from dist_worker import bcs_for
+    ndim = len(shape)
+    g = box_grid(shape, (False,) * ndim)
+    spec = CaseSpec(name=f"pbox{shape}", ndim=ndim, ndist=ndist, nghbr=g["nghbr"], omega=1.0 / 0.6, center=g["center"],
+                    bbmin=g["bbmin"], bbmax=g["bbmax"], cell_length=g["cell_length"])
+    for kind, cells, normals, val in bcs_for(g, ndim, pressure=True):
+        if kind == "pressure":
+            spec.bcs.append(dict(kind="pressure", cells=cells, normals=normals, pressure=val))
+        elif kind == "dirichlet":
+            spec.bcs.append(dict(kind="dirichlet_bb", cells=cells, normals=normals, value=val))
+        else:
+            spec.bcs.append(dict(kind="wall_bb", cells=cells, normals=normals, tangential=0.0))
+    return spec
+
+
+def _add_restricted(s, spec, lp):
+    for bc in spec.bcs:
+        cells, normals = lp.restrict(bc["cells"], bc["normals"])
+        if len(cells) == 0:
+            continue
+        if bc["kind"] == "dirichlet_bb":
+            s.add_dirichlet_bb(cells, normals, bc["value"])
+        elif bc["kind"] == "pressure":
+            s.add_pressure(cells, normals, bc["pressure"])
+        else:
+            s.add_wall_bb(cells, normals, 0.0)
+
+
+@pytest.mark.parametrize("shape,ndist", [((18, 16, 16), 19), ((34, 64), 9)])
+def test_plan_pressure_boundary_single_domain(shape, ndist, oracle_mod):
+    """anti-bounce-back entries: the plan's (cell, n1, n2, p) table + the interpreter's extrapolation reproduce the oracle"""
+    spec = _pressure_box(shape, ndist)
+    plan = plan_only_solver(spec).debug_plan()
+    assert plan["n_abb"] > 0
+    o = spec.apply_to(oracle_mod.Oracle(spec.ndim, ndist, spec.nghbr, spec.omega))
+    o.init()
+    dev2ref = np.full(plan["npad"], -1)
+    dev2ref[plan["ref2dev"]] = np.arange(plan["n"])
+    for _ in range(3):
+        o.step(1)
+        ab = plan["abb_cells"]
+        uext = 1.5 * o.vars[dev2ref[ab[:, 1]], :spec.ndim] - 0.5 * o.vars[dev2ref[ab[:, 2]], :spec.ndim]
+        mine = gather(plan, to_device(plan, o.f, ndist), ndist, uext=uext)
+        assert np.array_equal(mine, o.fold)
+
+
+@pytest.mark.parametrize("world,shape,ndist", [(2, (18, 16, 16), 19), (3, (10, 10, 10), 27), (2, (34, 64), 9)])
+def test_partitioned_plan_pressure_velocity_halo(world, shape, ndist, oracle_mod):
+    """A partition cut between a pressure cell and its inward neighbours: the plan refers to slots of the
+    received velocity halo, the peers' send lists fill exactly those slots, and the gather reproduces the single-domain m_fold."""
+    spec = _pressure_box(shape, ndist)
+    ndim = spec.ndim
+    pressure = [(bc["cells"], bc["normals"]) for bc in spec.bcs if bc["kind"] == "pressure"]
+    o = spec.apply_to(oracle_mod.Oracle(ndim, ndist, spec.nghbr, spec.omega))
+    o.init()
+    plans, lps = [], []
+    for r in range(world):
+        lp = partition.plan_rank(partition.TableRows(spec.nghbr, ndist), r, world, spec.nghbr.shape[1], pressure)
+        s = lbm_b200.Solver(ndim, ndist, lp.nghbr, spec.omega, device=-1)
+        _add_restricted(s, spec, lp)
+        lp.apply_halo(s)
+        plans.append(s.debug_plan())
+        lps.append(lp)
+    assert sum(p["n_vrecv"] for p in plans) > 0 and sum(p["n_vrecv"] for p in plans) == sum(len(p["vsend_cells"]) for p in plans)
+    for _ in range(3):
+        o.step(1)
+        for r, (plan, lp) in enumerate(zip(plans, lps)):
+            own = np.arange(lp.lo, lp.hi)
+            dev2glob = np.full(plan["npad"], -1)
+            dev2glob[plan["ref2dev"][:lp.n_owned]] = own
+            A = np.zeros((ndist, plan["npad"]))
+            A[:, plan["ref2dev"][:lp.n_owned]] = o.f[own].T
+            vrecv = np.zeros((plan["n_vrecv"], ndim))
+            ro = vo = 0
+            for k, q in enumerate(lp.peers):
+                pq, lq = plans[q], lps[q]
+                kq = lq.peers.index(r)
+                q2glob = np.full(pq["npad"], -1)
+                q2glob[pq["ref2dev"][:lq.n_owned]] = np.arange(lq.lo, lq.hi)
+                Aq = np.zeros((ndist, pq["npad"]))
+                Aq[:, pq["ref2dev"][:lq.n_owned]] = o.f[np.arange(lq.lo, lq.hi)].T
+                so, ns = sum(lq.send_count[:kq]), lq.send_count[kq]
+                assert ns == lp.recv_count[k]
+                A.reshape(-1)[plan["recv_index"][ro:ro + ns]] = Aq.reshape(-1)[pq["send_index"][so:so + ns]]
+                ro += ns
+                vso, vns = sum(lq.vsend_count[:kq]), lq.vsend_count[kq]
+                assert vns == lp.vrecv_count[k]
+                vrecv[vo:vo + vns] = o.vars[q2glob[pq["vsend_cells"][vso:vso + vns].astype(np.int64)], :ndim]  # what rank q's k_velocity_pack sends
+                vo += vns
+
+            def vel(n):
+                out = np.empty((len(n), ndim))
+                loc = n >= 0
+                out[loc] = o.vars[dev2glob[n[loc]], :ndim]
+                out[~loc] = vrecv[-n[~loc] - 1]
+                return out
+            ab = plan["abb_cells"]
+            uext = 1.5 * vel(ab[:, 1]) - 0.5 * vel(ab[:, 2]) if len(ab) else None
+            mine = gather(plan, A, ndist, uext=uext)
+            assert np.array_equal(mine, o.fold[own]), f"rank {r}"
