@@ -1,0 +1,102 @@
+"""3D versions of the reference's sphere and step cases (test helper): BASELINE.json configs[3] and configs[4].
+
+The reference's own test/sphere/sphere_ns.json and test/step/step_ns.json are 2D (D2Q9); its executable rejects D3Q19 / D3Q27
+(src/lbm/solverExe.h:37-90).  The configurations below keep their geometry objects, boundary keys and pressure values and add the
+third dimension (walls on -z / +z); the host-side grid pipeline (lbm_b200/host, bit-exact against the reference's 2D dumps) turns
+them into the tables the solver consumes.  Parity for these cases is UNPINNED by the reference: the CUDA path is
+compared with the CPU oracle, which follows the reference's dimension-generic source text.
+"""
+import json
+import os
+import tempfile
+
+import numpy as np
+
+from casebuilder import CaseSpec, bcs_from_config, geometry_bbox
+
+WALL = {"type": "wall", "model": "bounceback"}
+
+
+def sphere3d_config(level, model="D3Q27"):
+    """sphere_ns.json (box [0,10]^2 minus a sphere of radius 1 at the centre, pressure in-/outlet on -x/+x) in 3D"""
+    return {"dim": 3, "partitionLevel": level, "uniformLevel": level, "maxRfnmtLvl": level, "maxNoCells": 100000000,
+            "outputDir": "out", "gridFileName": "gridD",
+            "geometry": {"cube": {"type": "box", "body": "flowregion", "A": [0.0, 0.0, 0.0], "B": [10.0, 10.0, 10.0]},
+                         "sphere": {"type": "sphere", "body": "flowregion", "subtract": True, "center": [5.0, 5.0, 5.0], "radius": 1.0}},
+            "solver": {"type": "lbm", "model": model, "relaxation": 0.6, "maxSteps": 10,
+                       "boundary": {"cube": {"+x": {"type": "pressure", "pressure": 1.0}, "-x": {"type": "pressure", "pressure": 1.0000008},
+                                             "-y": WALL, "+y": WALL, "-z": WALL, "+z": WALL},
+                                    "sphere": {"all": WALL}}}}
+
+
+def step3d_config(level, model="D3Q19"):
+    """step_ns.json (channel [0,10]x[0,9] with two side pockets, i.e. a block on the upper wall, pressure in-/outlet) extruded in z"""
+    return {"dim": 3, "partitionLevel": level, "uniformLevel": level, "maxRfnmtLvl": level, "maxNoCells": 100000000,
+            "outputDir": "out", "gridFileName": "gridD",
+            "geometry": {"cube": {"type": "box", "body": "flowregion", "A": [0.0, 0.0, 0.0], "B": [10.0, 9.0, 10.0]},
+                         "step_a": {"type": "box", "body": "flowregion", "subtract": False, "A": [0.0, 9.0, 0.0], "B": [4.0, 10.0, 10.0]},
+                         "step_b": {"type": "box", "body": "flowregion", "subtract": False, "A": [6.0, 9.0, 0.0], "B": [10.0, 10.0, 10.0]}},
+            "solver": {"type": "lbm", "model": model, "relaxation": 0.6, "maxSteps": 10,
+                       "boundary": {"cube": {"+x": {"type": "pressure", "pressure": 1.0}, "-x": {"type": "pressure", "pressure": 1.0000008},
+                                             "-y": WALL, "+y": WALL, "-z": WALL, "+z": WALL},
+                                    "step_a": {"+x": WALL, "-x": {"type": "pressure", "pressure": 1.0000008}, "+y": WALL, "-y": WALL,
+                                               "-z": WALL, "+z": WALL},
+                                    "step_b": {"+x": {"type": "pressure", "pressure": 1.0}, "-x": WALL, "+y": WALL, "-y": WALL,
+                                               "-z": WALL, "+z": WALL}}}}
+
+
+CONFIGS = {"sphere3d": sphere3d_config, "step3d": step3d_config}
+NDIST = {"D3Q19": 19, "D3Q27": 27}
+
+
+def build_case(name, level, model=None):
+    """Configuration -> host grid pipeline -> CaseSpec (tables + boundary conditions in the reference's application order)."""
+    from lbm_b200 import host_api
+    cfg = CONFIGS[name](level) if model is None else CONFIGS[name](level, model)
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, f"{name}.json")
+        with open(path, "w") as fh:
+            json.dump(cfg, fh)
+        cwd = os.getcwd()
+        os.chdir(tmp)  # the grid generator writes its log into the working directory, like the reference
+        try:
+            g = host_api.build_grid(path)
+        finally:
+            os.chdir(cwd)
+    ndim = 3
+    surfaces = {nm: (cells, normals) for nm, cells, normals in g["surfaces"]}
+    lo, hi = geometry_bbox(cfg["geometry"], ndim)
+    spec = CaseSpec(name=f"{name}_l{level}", ndim=ndim, ndist=NDIST[cfg["solver"]["model"]], nghbr=g["nghbr"],
+                    omega=1.0 / float(cfg["solver"]["relaxation"]), center=g["center"], bbmin=lo, bbmax=hi, cell_length=g["cell_length"])
+    spec.bcs, spec.forcing = bcs_from_config(cfg["solver"], surfaces, ndim)
+    spec.config = cfg
+    spec.surfaces = surfaces
+    return spec
+
+
+def pressure_surfaces(spec):
+    return [(bc["cells"], bc["normals"]) for bc in spec.bcs if bc["kind"] == "pressure"]
+
+
+def add_restricted(solver, spec, lp):
+    """the boundary-condition entries of the cells rank `lp.rank` owns, local ids, order kept"""
+    for bc in spec.bcs:
+        cells, normals = lp.restrict(bc["cells"], bc["normals"])
+        if len(cells) == 0:
+            continue
+        if bc["kind"] == "pressure":
+            solver.add_pressure(cells, normals, bc["pressure"])
+        elif bc["kind"] == "wall_bb":
+            solver.add_wall_bb(cells, normals, bc["tangential"])
+        elif bc["kind"] == "dirichlet_bb":
+            solver.add_dirichlet_bb(cells, normals, bc["value"])
+        else:
+            raise NotImplementedError(bc["kind"])
+    return solver
+
+
+# per-pair MRT rates used by the tests (distinct even / odd rates so that a mix-up shows)
+def mrt_rates(ndist, omega):
+    r = np.full(27, omega)
+    r[:ndist] = omega * (1.0 + 0.01 * np.arange(ndist) / ndist)
+    return r

@@ -109,10 +109,14 @@ def main():
     ap.add_argument("--shape", default="16,12,10")
     ap.add_argument("--ndist", type=int, default=19)
     ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--case", default="box", help="box, or a 3D case of tests/cases3d.py: sphere3d, step3d (BASELINE.json configs[3], [4])")
+    ap.add_argument("--level", type=int, default=5)
+    ap.add_argument("--collision", default="bgk", choices=["bgk", "trt", "mrt"])
     ap.add_argument("--bc", default="walls", help="walls: periodic x, walls, moving lid; pressure: pressure in-/outlet on -x/+x")
     args = ap.parse_args()
     shape = tuple(int(x) for x in args.shape.split(","))
-    ndim = len(shape)
+    ndim = len(shape) if args.case == "box" else 3
+    coll = {"bgk": 0, "trt": 1, "mrt": 2}[args.collision]
     with_pressure = args.bc == "pressure"
     periodic = (not with_pressure,) + (False,) * (ndim - 1)
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -123,22 +127,38 @@ def main():
     else:
         dist.init_process_group("gloo")
 
-    g = box_grid(shape, periodic)
+    if args.case == "box":
+        g = box_grid(shape, periodic)
+        bcs = bcs_for(g, ndim, with_pressure)
+    else:
+        from cases3d import build_case, mrt_rates
+        spec = build_case(args.case, args.level)
+        args.ndist = spec.ndist
+        g = {"nghbr": spec.nghbr}
+        kinds = {"wall_bb": "wall", "pressure": "pressure", "dirichlet_bb": "dirichlet"}
+        bcs = [(kinds[bc["kind"]], bc["cells"], bc["normals"], bc.get("pressure", bc.get("value", bc.get("tangential")))) for bc in spec.bcs]
     stride = g["nghbr"].shape[1]
-    bcs = bcs_for(g, ndim, with_pressure)
     pressure = [(cells, normals) for kind, cells, normals, _ in bcs if kind == "pressure"]
+    rates = OMEGA * (1.0 + 0.01 * np.arange(27) / 27)
+    om_minus = 1.0 / 0.8
+
+    def make_oracle(table):
+        orc = oracle.Oracle(ndim, args.ndist, table, OMEGA)
+        orc.set_collision(coll, om_minus, rates)
+        return orc
     # single-domain reference run (CPU oracle)
-    ref = oracle.Oracle(ndim, args.ndist, g["nghbr"], OMEGA)
+    ref = make_oracle(g["nghbr"])
     add_bcs(ref, bcs)
     ref.init()
     ref.step(args.steps)
 
     # partition: the table-driven provider and the on-demand box provider must give the same plan
     lp = partition.plan_rank(partition.TableRows(g["nghbr"], args.ndist), rank, world, stride, pressure)
-    lp2 = partition.plan_rank(partition.BoxRows(shape, [int(p) for p in periodic], args.ndist), rank, world, stride, pressure)
-    assert np.array_equal(lp.nghbr, lp2.nghbr) and np.array_equal(lp.ghosts, lp2.ghosts)
-    assert lp.peers == lp2.peers and np.array_equal(lp.send_cell, lp2.send_cell) and np.array_equal(lp.recv_dir, lp2.recv_dir)
-    assert np.array_equal(lp.vsend_cell, lp2.vsend_cell) and np.array_equal(lp.vrecv_cell, lp2.vrecv_cell)
+    if args.case == "box":
+        lp2 = partition.plan_rank(partition.BoxRows(shape, [int(p) for p in periodic], args.ndist), rank, world, stride, pressure)
+        assert np.array_equal(lp.nghbr, lp2.nghbr) and np.array_equal(lp.ghosts, lp2.ghosts)
+        assert lp.peers == lp2.peers and np.array_equal(lp.send_cell, lp2.send_cell) and np.array_equal(lp.recv_dir, lp2.recv_dir)
+        assert np.array_equal(lp.vsend_cell, lp2.vsend_cell) and np.array_equal(lp.vrecv_cell, lp2.vrecv_cell)
     # send counts of mine must equal the receive counts of the peer
     counts = [None] * world
     dist.all_gather_object(counts, {q: (lp.send_count[k], lp.recv_count[k], lp.vsend_count[k], lp.vrecv_count[k]) for k, q in enumerate(lp.peers)})
@@ -146,11 +166,11 @@ def main():
         assert counts[q][rank] == (lp.recv_count[k], lp.send_count[k], lp.vrecv_count[k], lp.vsend_count[k]), "halo lists of the two sides do not match"
     nvel = [None] * world
     dist.all_gather_object(nvel, sum(lp.vrecv_count))
-    if with_pressure and world > 1:
+    if with_pressure and world > 1 and args.case == "box":
         assert sum(nvel) > 0, "test set-up: no pressure cell is separated from its inward neighbours by the cut"
 
     if args.mode == "oracle":
-        o = oracle.Oracle(ndim, args.ndist, lp.nghbr, OMEGA)
+        o = make_oracle(lp.nghbr)
         add_bcs(o, bcs, lp)
         o.init()
         for _ in range(args.steps):
@@ -164,7 +184,7 @@ def main():
         from lbm_b200.capi import comm_unique_id
         uid = [comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
-        s = lbm_b200.Solver(ndim, args.ndist, lp.nghbr, OMEGA, device=local)
+        s = lbm_b200.Solver(ndim, args.ndist, lp.nghbr, OMEGA, device=local, collision=coll, omega_minus=om_minus, mrt_rates=rates)
         add_bcs(s, bcs, lp)
         lp.apply_halo(s)
         s.comm_init(uid[0], rank, world)

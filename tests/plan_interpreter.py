@@ -91,3 +91,64 @@ def gather(plan, A, q, values=None, uext=None):
                 fold_dev[j, cell] = values[pl]
         fold_dev[qm, cell] = A[qm, cell]
     return fold_dev[:, plan["ref2dev"][:plan["n_owned"]]].T
+
+
+def stale_values(plan, init_fold_rows, q):
+    """value table with the slots nothing ever writes filled from the initial m_fold (what lbm_b200_init does on the device);
+    init_fold_rows[k] = initial m_fold row of the plan's reference cell k"""
+    values = plan["values"].copy()
+    dev2ref = np.full(plan["npad"], -1)
+    dev2ref[plan["ref2dev"]] = np.arange(plan["n"])
+    for k, sr in enumerate(plan["stale_ref"].astype(np.int64)):
+        values[k + 1] = init_fold_rows[dev2ref[sr // q], sr % q]
+    return values
+
+
+def extrapolated_velocity(plan, vel_of_dev, vrecv, ndim):
+    """u_ext of every anti-bounce-back entry: 1.5 u(n1) - 0.5 u(n2) (bnd_pressure.h:78-84); n < 0 = slot of the received halo"""
+    ab = plan["abb_cells"].astype(np.int64)
+    if len(ab) == 0:
+        return None
+
+    def vel(n):
+        out = np.empty((len(n), ndim))
+        loc = n >= 0
+        out[loc] = vel_of_dev(n[loc])
+        if (~loc).any():
+            out[~loc] = vrecv[-n[~loc] - 1]
+        return out
+    return 1.5 * vel(ab[:, 1]) - 0.5 * vel(ab[:, 2])
+
+
+def partitioned_fold(r, plans, lps, f_glob, vars_glob, init_fold_glob, q, ndim):
+    """m_fold of the cells rank r owns, computed from ITS plan: owned populations from the global post-collision state, ghost
+    populations and remote velocities only through what the peers' send lists put on the wire (emulates k_halo_pack /
+    k_velocity_pack -> NCCL -> k_halo_unpack without a GPU)."""
+    plan, lp = plans[r], lps[r]
+    own = np.arange(lp.lo, lp.hi)
+    glob_of_local = np.concatenate([own, lp.ghosts])
+    dev2glob = np.full(plan["npad"], -1)
+    dev2glob[plan["ref2dev"][:lp.n_owned]] = own
+    A = np.zeros((q, plan["npad"]))
+    A[:, plan["ref2dev"][:lp.n_owned]] = f_glob[own].T
+    vrecv = np.zeros((plan["n_vrecv"], ndim))
+    ro = vo = 0
+    for k, peer in enumerate(lp.peers):
+        pq, lq = plans[peer], lps[peer]
+        kq = lq.peers.index(r)
+        ownq = np.arange(lq.lo, lq.hi)
+        q2glob = np.full(pq["npad"], -1)
+        q2glob[pq["ref2dev"][:lq.n_owned]] = ownq
+        Aq = np.zeros((q, pq["npad"]))
+        Aq[:, pq["ref2dev"][:lq.n_owned]] = f_glob[ownq].T
+        so, ns = sum(lq.send_count[:kq]), lq.send_count[kq]
+        assert ns == lp.recv_count[k]
+        A.reshape(-1)[plan["recv_index"][ro:ro + ns].astype(np.int64)] = Aq.reshape(-1)[pq["send_index"][so:so + ns].astype(np.int64)]
+        ro += ns
+        vso, vns = sum(lq.vsend_count[:kq]), lq.vsend_count[kq]
+        assert vns == lp.vrecv_count[k]
+        vrecv[vo:vo + vns] = vars_glob[q2glob[pq["vsend_cells"][vso:vso + vns].astype(np.int64)], :ndim]
+        vo += vns
+    uext = extrapolated_velocity(plan, lambda n: vars_glob[dev2glob[n], :ndim], vrecv, ndim)
+    values = stale_values(plan, init_fold_glob[glob_of_local], q)
+    return gather(plan, A, q, values=values, uext=uext)

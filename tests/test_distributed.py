@@ -19,10 +19,10 @@ def free_port():
     return p
 
 
-def launch(world, mode, shape, ndist, steps=12, timeout=600, bc="walls"):
+def launch(world, mode, shape, ndist, steps=12, timeout=600, bc="walls", extra=()):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(free_port()), os.path.join(HERE, "dist_worker.py"), "--mode", mode, "--shape", shape,
-           "--ndist", str(ndist), "--steps", str(steps), "--bc", bc]
+           "--ndist", str(ndist), "--steps", str(steps), "--bc", bc, *extra]
     env = dict(os.environ, OMP_NUM_THREADS="2")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     assert r.returncode == 0 and "PARTITION_PARITY OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
@@ -37,6 +37,12 @@ def test_partitioned_oracle_matches_single_domain_gloo(world, shape, ndist):
 def test_partitioned_pressure_boundary_velocity_halo_gloo(world, shape, ndist):
     """Pressure in-/outlet whose inward neighbours lie across the cut: the velocity halo."""
     launch(world, "oracle", shape, ndist, bc="pressure")
+
+
+@pytest.mark.parametrize("world,case,collision", [(4, "sphere3d", "mrt"), (3, "step3d", "trt")])
+def test_partitioned_baseline_configs_gloo(world, case, collision):
+    """BASELINE.json configs[3] / [4] (3D sphere D3Q27 MRT, 3D step D3Q19 TRT with pressure outflow) cut into SFC ranges."""
+    launch(world, "oracle", "0,0,0", 0, steps=8, extra=("--case", case, "--level", "5", "--collision", collision))
 
 
 @pytest.mark.gpu
@@ -55,3 +61,12 @@ def test_partitioned_gpu_pressure_boundary_nccl(shape, ndist):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     launch(2, "gpu", shape, ndist, bc="pressure")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,collision,level", [("sphere3d", "mrt", 6), ("step3d", "trt", 6)])
+def test_partitioned_gpu_baseline_configs_nccl(case, collision, level):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    launch(2, "gpu", "0,0,0", 0, steps=10, extra=("--case", case, "--level", str(level), "--collision", collision))
