@@ -9,8 +9,12 @@
 //   SolverGrid::load    leaf/bndry properties (src/cartesiangrid.h:502-546), named boundary surfaces with first-come
 //                       (cell,dir) assignment and last-normal-wins (:553-603, src/common/surface.h:52-55), grid-level periodic
 //                       links (:608-706), diagonal neighbours by composition of axis steps (:451-493)
-// Supported: partitionLevel == uniformLevel == maxRfnmtLvl (true for every reference configuration), with or without
-// alignNodesWithSurface; multi-level grids are SURVEY.md section 8f row N3 and are rejected with a clear error.
+// Multi-level grids: partitionLevel < uniformLevel keeps the cells of every level from the partition
+// level up in the list (partition cells in curve order, then one block per level in parent order with the deletion swaps of
+// cartesiangrid_generation.h:508-552), maxRfnmtLvl > uniformLevel adds the children of the cut cells of the highest level
+// (gridGenerator.cpp:206-216, markBndryCells / refineMarkedCells :186-230).  The reference steps every level as its own lattice
+// ("todo: skip non-leaf cells", solver.cpp:525), so the tables are all the solver needs.  alignNodesWithSurface is supported
+// on single-level grids only (every reference configuration that uses it is single-level).
 #pragma once
 #include <algorithm>
 #include <array>
@@ -33,6 +37,7 @@ struct GenCell {
   int64_t child[8]  = {-1, -1, -1, -1, -1, -1, -1, -1};
   int64_t parent    = -1;
   bool    bndry = false, inside = false, marked = false;
+  int     level = 0;
 };
 
 // cartesian::childDir / nghbrInside / nghbrParentChildId (include/common/math/cartesian.h:72-153) for up to 3 dimensions:
@@ -55,7 +60,8 @@ inline int nghbr_parent_child(int c, int dir) {
 
 class GridGen {
  public:
-  int    ndim = 2, level = 0;
+  int    ndim = 2, level = 0;         // level = maxRfnmtLvl (CartesianGrid::maxLvl, gridGenerator.cpp:185)
+  int    part_level = 0, uni_level = 0;
   double bbmin[3] = {0, 0, 0}, bbmax[3] = {0, 0, 0}, cog[3] = {0, 0, 0};
   double length_on_level[64] = {0};
   std::shared_ptr<GeometryManager> geom;
@@ -70,12 +76,14 @@ class GridGen {
     const long long maxr = cfg.opt_int("maxRfnmtLvl", uni);
     if(part > uni) throw std::runtime_error("Invalid definition of grid level partitionLevel >= uniformLevel");
     if(maxr < uni) throw std::runtime_error("Invalid definition of grid level uniformLevel >= maxRfnmtLvl");
-    if(part != uni || maxr != uni)
-      throw std::runtime_error("multi-level grids (partitionLevel < uniformLevel or maxRfnmtLvl > uniformLevel) are not supported yet");
     align = cfg.opt_bool("alignNodesWithSurface", false);
+    if(align && (part != uni || maxr != uni))
+      throw std::runtime_error("alignNodesWithSurface on a multi-level grid is not supported");
     align_dir = static_cast<int>(cfg.opt_int("alignDir", 1));
     if(align && (align_dir < 0 || align_dir >= ndim)) throw std::runtime_error("Invalid alignDir");
-    level = static_cast<int>(uni);
+    level = static_cast<int>(maxr);
+    part_level = static_cast<int>(part);
+    uni_level  = static_cast<int>(uni);
     geom  = std::make_shared<GeometryManager>();
     if(!cfg.has("geometry")) throw std::runtime_error("The required configuration value is missing: geometry");
     geom->setup(cfg.at("geometry"), ndim);
@@ -104,7 +112,7 @@ class GridGen {
     std::vector<GenCell> cur(1);
     for(int d = 0; d < ndim; ++d) cur[0].center[d] = cog[d];
     cur[0].bndry = true; // cartesiangrid_generation.h:108
-    for(int l = 0; l < level; ++l) {
+    for(int l = 0; l < part_level; ++l) {
       const double len = length_on_level[l + 1];
       std::vector<GenCell> next(cur.size() * NC);
       // refineCell :419-451
@@ -196,7 +204,7 @@ class GridGen {
     for(size_t i = 0; i < cur.size(); ++i) {
       double x[3];
       for(int d = 0; d < ndim; ++d) x[d] = ((cur[i].center[d] - cog[d]) + 0.5 * L0) / L0;
-      key[i] = lbm::sfc_index_unit(ndim, x, level);
+      key[i] = lbm::sfc_index_unit(ndim, x, part_level);
     }
     std::vector<int64_t> order(cur.size());
     for(size_t i = 0; i < order.size(); ++i) order[i] = static_cast<int64_t>(i);
@@ -212,11 +220,111 @@ class GridGen {
       for(int dir = 0; dir < NN; ++dir)
         if(cells[i].nghbr[dir] != -1) cells[i].nghbr[dir] = newpos[cells[i].nghbr[dir]];
       for(int c = 0; c < 8; ++c) cells[i].child[c] = -1;
+      cells[i].level = part_level;
     }
+    // uniformRefineGrid :151-171: every level up to uniformLevel is appended behind the list, the parents stay
+    int64_t lb = 0, le = static_cast<int64_t>(cells.size());
+    for(int l = part_level; l < uni_level; ++l) refine_block(l, &lb, &le, false);
+    // boundary refinement, gridGenerator.cpp:206-210: children of the cut cells of the highest level only
+    for(int l = uni_level; l < level; ++l) refine_block(l, &lb, &le, true);
     if(align) transform_to_extent();
   }
 
  private:
+  // refineGrid<true, UNIFORM> (:339-376) of the level block [*lb, *le): refineCell (:419-451) for all / for the cut cells only
+  // (refineGridMarkedOnly :407-415), findChildLevelNghbrs (:453-506), deleteOutsideCells (:508-552).  On return [*lb, *le) is the
+  // new level's block.
+  void refine_block(int l, int64_t* lb, int64_t* le, bool marked_only) {
+    const int NC = 1 << ndim, NN = 2 * ndim;
+    const double  len = length_on_level[l + 1];
+    const int64_t pb = *lb, pe = *le, cb = static_cast<int64_t>(cells.size());
+    int64_t k = 0;
+    for(int64_t p = pb; p < pe; ++p) {
+      if(marked_only && !cells[p].bndry) continue; // markBndryCells :212-225
+      cells.resize(cells.size() + NC);
+      for(int c = 0; c < NC; ++c) {
+        const int64_t id = cb + k * NC + c;
+        GenCell&      ch = cells[id];
+        ch = GenCell();
+        for(int d = 0; d < ndim; ++d) ch.center[d] = cells[p].center[d] + 0.5 * len * child_dir(c, d);
+        ch.level  = l + 1;
+        ch.parent = p;
+        if(cells[p].bndry) ch.bndry = geom->cut_with_cell(ch.center, len);
+        cells[p].child[c] = id;
+      }
+      ++k;
+    }
+    for(int64_t p = pb; p < pe; ++p) {
+      for(int c = 0; c < NC; ++c) {
+        const int64_t id = cells[p].child[c];
+        if(id < 0) continue;
+        for(int dir = 0; dir < NN; ++dir) {
+          if(cells[id].nghbr[dir] != -1) continue;
+          const int in = nghbr_inside(c, dir);
+          if(in >= 0) {
+            cells[id].nghbr[dir] = cells[p].child[in];
+          } else {
+            const int     pc = nghbr_parent_child(c, dir);
+            const int64_t pn = cells[p].nghbr[dir];
+            if(pn != -1 && pc >= 0 && cells[pn].child[pc] != -1) cells[id].nghbr[dir] = cells[pn].child[pc];
+          }
+        }
+      }
+    }
+    int64_t end = static_cast<int64_t>(cells.size());
+    // markOutsideCells / floodCells :554-603
+    for(int64_t i = cb; i < end; ++i) cells[i].marked = false;
+    for(int64_t i = cb; i < end; ++i) {
+      if(cells[i].marked) continue;
+      cells[i].marked = true;
+      cells[i].inside = cells[i].bndry || geom->point_inside(cells[i].center);
+      if(cells[i].bndry) continue;
+      const bool inside = cells[i].inside;
+      std::stack<int64_t> st;
+      st.push(i);
+      while(!st.empty()) {
+        const int64_t cc = st.top();
+        st.pop();
+        for(int dir = 0; dir < NN; ++dir) {
+          const int64_t nb = cells[cc].nghbr[dir];
+          if(nb == -1 || cells[nb].marked) continue;
+          cells[nb].marked = true;
+          if(!cells[nb].bndry) {
+            cells[nb].inside = inside;
+            st.push(nb);
+          } else {
+            cells[nb].inside = true;
+          }
+        }
+      }
+    }
+    // deleteCell :527-552 from the end of the block to its begin, the hole is filled with the block's last cell (copyCell :616-646)
+    for(int64_t i = end - 1; i >= cb; --i) {
+      if(cells[i].inside) continue;
+      const int64_t par = cells[i].parent;
+      for(int c = 0; c < NC; ++c)
+        if(cells[par].child[c] == i) { cells[par].child[c] = -1; break; }
+      for(int dir = 0; dir < NN; ++dir) {
+        const int64_t nb = cells[i].nghbr[dir];
+        if(nb != -1) cells[nb].nghbr[dir ^ 1] = -1;
+      }
+      if(i != end - 1) {
+        cells[i] = cells[end - 1];
+        for(int dir = 0; dir < NN; ++dir) {
+          const int64_t nb = cells[i].nghbr[dir];
+          if(nb != -1) cells[nb].nghbr[dir ^ 1] = i;
+        }
+        const int64_t mp = cells[i].parent;
+        for(int c = 0; c < NC; ++c)
+          if(cells[mp].child[c] == end - 1) { cells[mp].child[c] = i; break; }
+      }
+      --end;
+    }
+    cells.resize(static_cast<size_t>(end));
+    *lb = cb;
+    *le = end;
+  }
+
   // transformMaxRfnmtLvlToExtent, cartesiangrid_generation.h:256-304: stretch the cell centres so that the outermost
   // centres lie ON the bounding box in alignDir (all directions for a square domain), scale the cell length, then delete what
   // is now outside (deleteOutsideCells<CHECKALL = true>, :508-525,556-561)
@@ -280,7 +388,11 @@ class SolverGrid {
  public:
   int     ndim = 2, nn_axis = 4, nn_diag = 8, max_level = 0;
   int64_t n = 0;
-  double  cell_length = 0, bbmin[3] = {0, 0, 0}, bbmax[3] = {0, 0, 0};
+  double  cell_length = 0, bbmin[3] = {0, 0, 0}, bbmax[3] = {0, 0, 0}; // cell_length = lengthOnLvl(maxLvl)
+  double  length_on_level[64] = {0};
+  std::vector<int> level;        // per cell
+  bool    multi_level = false;
+  int     part_level = 0;        // partitionLvl; max_level doubles as currentHighestLvl (the generator always reaches maxRfnmtLvl)
   std::vector<int64_t>  nghbr;  // n * nn_diag
   std::vector<double>   center; // n * ndim
   std::vector<uint16_t> props;  // CellProperties bits (gridcell_properties.h:7-26): bndry = bit 4, leaf = bit 14
@@ -310,6 +422,11 @@ class SolverGrid {
     max_level = g.level;
     n = static_cast<int64_t>(g.cells.size());
     cell_length = g.length_on_level[g.level];
+    for(int l = 0; l < 64; ++l) length_on_level[l] = g.length_on_level[l];
+    multi_level = g.part_level != g.level;
+    part_level  = g.part_level;
+    level.resize(static_cast<size_t>(n));
+    for(int64_t c = 0; c < n; ++c) level[c] = multi_level ? g.cells[c].level : g.level;
     for(int d = 0; d < ndim; ++d) { bbmin[d] = g.bbmin[d]; bbmax[d] = g.bbmax[d]; }
     nghbr.assign(static_cast<size_t>(n) * nn_diag, -1);
     center.resize(static_cast<size_t>(n) * ndim);
@@ -318,18 +435,28 @@ class SolverGrid {
       for(int dir = 0; dir < nn_axis; ++dir) nb(c, dir) = g.cells[c].nghbr[dir];
       for(int d = 0; d < ndim; ++d) center[c * ndim + d] = g.cells[c].center[d];
     }
-    // setProperties :502-508 -- single level: every cell is a leaf
-    for(int64_t c = 0; c < n; ++c) props[c] |= 1u << 14;
-    n_leaf = n;
-    // determineBoundaryCells :510-546 (all cells are parent-less here)
+    // setProperties :502-508: leaf = no children
+    n_leaf = 0;
     for(int64_t c = 0; c < n; ++c) {
-      bool b = g.geom->cut_with_cell(&center[c * ndim], cell_length);
+      bool leaf = true;
+      for(int k = 0; k < 8; ++k) leaf = leaf && g.cells[c].child[k] < 0;
+      if(leaf) { props[c] |= 1u << 14; ++n_leaf; }
+    }
+    // determineBoundaryCells :510-546: only parent-less cells and children of boundary cells are tested (parents precede their
+    // children in the list)
+    for(int64_t c = 0; c < n; ++c) {
+      const int64_t par = g.cells[c].parent;
+      if(par != -1 && !(props[par] & (1u << 4))) continue;
+      bool b = g.geom->cut_with_cell(&center[c * ndim], length_on_level[level[c]]);
       if(b) {
         int have = 0;
         for(int dir = 0; dir < nn_axis; ++dir) have += nb(c, dir) != -1;
         if(have == nn_axis) b = false;
       }
-      if(b) { props[c] |= 1u << 4; ++n_bnd; }
+      if(b) {
+        props[c] |= 1u << 4;
+        if(props[c] & (1u << 14)) ++n_bnd;
+      }
     }
     // identifyBndrySurfaces :553-603
     const Json& boundary = solver_cfg.at("boundary");
@@ -344,7 +471,7 @@ class SolverGrid {
         for(int dir = d0; dir < d1; ++dir) {
           for(int64_t c = 0; c < n; ++c) {
             if(!(props[c] & (1u << 4)) || nb(c, dir) != -1) continue;
-            if(!g.geom->cut_with_cell(gk.first, &center[c * ndim], cell_length)) continue;
+            if(!g.geom->cut_with_cell(gk.first, &center[c * ndim], length_on_level[level[c]])) continue;
             if(!assigned.insert({c, dir}).second) continue;
             s.cells.push_back(c);
             std::array<double, 3> nrm = {0, 0, 0};
@@ -357,19 +484,29 @@ class SolverGrid {
     }
     // setupPeriodicConnections :608-641 (grid-level periodicity: type periodic with generateBndry false)
     {
-      std::map<std::string, std::string> conn;
+      // The reference collects the connections in a std::unordered_map and walks it while erasing the partner of every entry it
+      // visits (:611-639).  libstdc++ links a new node at the head of its list, so the walk visits the entries in REVERSE
+      // insertion order: for "cube_+x" <-> "cube_-x" the pairing runs as (A = cube_-x, B = cube_+x).  The order only matters on
+      // multi-level grids, where one cell finds several partners and the last assignment wins (pinned by the
+      // couette_ml_p4u5m7 fixture).
+      std::vector<std::pair<std::string, std::string>> conn;
       for(const auto& gk : boundary.obj)
         for(const auto& sk : gk.second.obj) {
           const Json& c = sk.second;
           if(c.opt_str("type", "notset") == "periodic" && !c.opt_bool("generateBndry", true))
-            conn[gk.first + "_" + sk.first] = c.at("connection").as_string();
+            conn.emplace_back(gk.first + "_" + sk.first, c.at("connection").as_string());
         }
+      auto has = [&](const std::string& k) {
+        for(const auto& kv : conn)
+          if(kv.first == k) return true;
+        return false;
+      };
       std::set<std::string> done;
-      for(const auto& kv : conn) {
-        if(done.count(kv.first)) continue;
-        if(conn.count(kv.second) == 0) throw std::runtime_error("Invalid periodic setup!");
-        done.insert(kv.second);
-        const Surface *a = find(kv.first), *b = find(kv.second);
+      for(auto it = conn.rbegin(); it != conn.rend(); ++it) {
+        if(done.count(it->first)) continue;
+        if(!has(it->second)) throw std::runtime_error("Invalid periodic setup!");
+        done.insert(it->second);
+        const Surface *a = find(it->first), *b = find(it->second);
         if(a == nullptr || b == nullptr) throw std::runtime_error("Invalid periodic setup!");
         add_periodic(*a, *b);
       }

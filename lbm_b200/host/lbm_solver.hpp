@@ -459,11 +459,20 @@ class LBMSolver final : public Runnable {
       TERMM(-1, "Invalid output directory set! (value: " + m_outputDir + ")");
   }
 
-  // CellFilterManager (cell_filter.h:60-96) on a single-level grid: every cell is a leaf and sits on the one level there is
+  // CellFilterManager (cell_filter.h:60-96): leafCells = childless cells, the level filters compare the cell's level
   std::vector<uint8_t> cellFilter() const {
     const SolverGrid&    g = m_grid.g;
     std::vector<uint8_t> keep(static_cast<size_t>(g.n), 1);
-    if(!m_cfg.has("cellFilter")) return keep; // default {"cellFilter": "leafCells"} (solver.cpp:86)
+    auto leaf_only = [&]() {
+      for(int64_t c = 0; c < g.n; ++c) keep[c] = keep[c] && (g.props[c] & (1u << 14)) != 0;
+    };
+    auto level_only = [&](long long lvl) {
+      for(int64_t c = 0; c < g.n; ++c) keep[c] = keep[c] && g.level[c] == lvl;
+    };
+    if(!m_cfg.has("cellFilter")) { // default {"cellFilter": "leafCells"} (solver.cpp:86)
+      leaf_only();
+      return keep;
+    }
     const Json& fc = m_cfg.at("cellFilter");
     if(!fc.has("cellFilter")) TERMM(-1, "Invalid output configuration missing \"cellFilter\" key"); // cell_filter.h:78
     const Json&              f = fc.at("cellFilter");
@@ -471,11 +480,13 @@ class LBMSolver final : public Runnable {
     if(f.is_array()) TERMM(-1, "untested"); // cell_filter.h:74
     list.push_back(f.as_string());
     for(const std::string& name : list) {
-      if(name == "highestLvl" || name == "lowestLvl" || name == "partitionLvl" || name == "leafCells") continue;
+      if(name == "highestLvl") { level_only(g.max_level); continue; }
+      if(name == "lowestLvl" || name == "partitionLvl") { level_only(g.part_level); continue; }
+      if(name == "leafCells") { leaf_only(); continue; }
       if(name == "targetLvl") {
         if(!fc.has("outputLvl")) TERMM(-1, "The required configuration value is missing: outputLvl");
-        if(fc.at("outputLvl").as_int() < g.max_level) TERMM(-1, "Outputting a lvl below the partition lvl is not possible!");
-        if(fc.at("outputLvl").as_int() != g.max_level) std::fill(keep.begin(), keep.end(), uint8_t(0));
+        if(fc.at("outputLvl").as_int() < g.part_level) TERMM(-1, "Outputting a lvl below the partition lvl is not possible!");
+        level_only(fc.at("outputLvl").as_int());
         continue;
       }
       TERMM(-1, "Unknown output filter " + name);
@@ -542,9 +553,11 @@ class LBMSolver final : public Runnable {
       if(z > 0) { const double r = std::sqrt(z); nx /= r; ny /= r; }
       const double offset = -(A[0] * nx + A[1] * ny);
       std::vector<int64_t> cells;
-      for(int64_t c = 0; c < g.n; ++c) { // every cell of a single-level grid is a leaf
+      for(int64_t c = 0; c < g.n; ++c) { // leaf cells within half of their own length (postprocessing_cartesian.h:22-30)
+        if(!(g.props[c] & (1u << 14))) continue;
         const double distance = std::abs(nx * g.center[c * 2] + ny * g.center[c * 2 + 1] + offset);
-        if(0.5 * g.cell_length >= distance) cells.push_back(c);
+        const double len = g.multi_level ? g.length_on_level[g.level[c]] : g.cell_length;
+        if(0.5 * len >= distance) cells.push_back(c);
       }
       // the reference's comparator ("some coordinate is smaller") is not a strict weak ordering; the same std::sort on the same
       // input reproduces its order (ascending y for the axis-parallel lines of the reference's configurations)

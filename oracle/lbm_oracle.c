@@ -128,6 +128,7 @@ typedef struct {
 typedef struct {
   OrcLattice L;
   int        nvar, stride, model, omp_collide;
+  int        push_conflict; /* two cells push into one slot (multi-level grids with grid-level periodic links) */
   int64_t    n;
   int64_t*   nghbr; /* n*stride push table, -1 = no neighbour (cartesiangrid.h:111-124) */
   double*    center; /* n*ndim or NULL */
@@ -206,6 +207,22 @@ Orc* orc_create(int ndim, int ndist, int64_t ncells, const int64_t* nghbr, int s
   o->vars    = (double*)calloc(nv, sizeof(double));
   o->varsold = (double*)calloc(nv, sizeof(double));
   o->periodic = (unsigned char*)calloc((size_t)ncells, 1);
+  /* The reference's propagation is an OpenMP loop (solver.cpp:728): where two cells push into the same slot it races; run
+   * serially there, so that the highest source wins as in the reference's single-thread order (the fixtures of such cases are
+   * generated with one thread, tests/golden/make_golden.py). */
+  {
+    unsigned char* seen = (unsigned char*)calloc((size_t)ncells, 1);
+    for(int i = 0; i < ndist - 1 && !o->push_conflict; ++i) {
+      memset(seen, 0, (size_t)ncells);
+      for(int64_t c = 0; c < ncells; ++c) {
+        const int64_t nb = nghbr[c * stride + i];
+        if(nb < 0) continue;
+        if(seen[nb]) { o->push_conflict = 1; break; }
+        seen[nb] = 1;
+      }
+    }
+    free(seen);
+  }
   return o;
 }
 
@@ -609,7 +626,7 @@ static void pass_pre_apply(Orc* o) {
 /* solver.cpp:715-740 */
 static void pass_propagation(Orc* o) {
   const int Q = o->L.ndist;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if(!o->push_conflict)
   for(int64_t c = 0; c < o->n; ++c) {
     for(int i = 0; i < Q - 1; ++i) {
       const int64_t nb = o->nghbr[c * o->stride + i];

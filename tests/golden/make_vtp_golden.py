@@ -32,10 +32,16 @@ KEEP_WHOLE = ("couette", "poiseuille_bnd_pressure")
 
 def main():
     full = "--full" in sys.argv
-    index = {}
+    only = [a for a in sys.argv[1:] if not a.startswith("--")]  # case names: update just these entries of the index
+    index_path = os.path.join(HERE, "vtp", "index_full.json" if full else "index.json")
+    index = json.load(open(index_path)) if only and os.path.exists(index_path) else {}
     os.makedirs(os.path.join(HERE, "vtp"), exist_ok=True)
     for path in sorted(glob.glob(os.path.join(HERE, "*.npz"))):
         name = os.path.basename(path)[:-4]
+        if only and name not in only:
+            continue
+        if full and "_ml_" in name:  # multi-level variants are not reference test cases; their short runs are pinned instead
+            continue
         cfg = json.loads(str(np.load(path)["config_orig_json" if full else "config_json"]))
         if full:
             if name in ("step_ns", "sphere_ns"):  # not part of run.sh (no analytic solution, 10^4..10^5 steps)
@@ -44,7 +50,7 @@ def main():
         tmp = tempfile.mkdtemp(prefix="lbm_vtp_")
         try:
             json.dump(cfg, open(os.path.join(tmp, "case.json"), "w"))
-            r = subprocess.run([BIN, "case.json"], cwd=tmp, env=dict(os.environ, OMP_NUM_THREADS="1" if full else "2"), capture_output=True,
+            r = subprocess.run([BIN, "case.json"], cwd=tmp, env=dict(os.environ, OMP_NUM_THREADS="1" if full or "_ml_" in name else "2"), capture_output=True,
                                text=True)
             if r.returncode != 0:
                 raise RuntimeError(f"{name}: reference exited {r.returncode}\n{r.stderr[-2000:]}")
@@ -62,7 +68,7 @@ def main():
             print(name, {k: v for k, v in index[name].items() if k != "line_csv"})
         finally:
             shutil.rmtree(tmp)
-    json.dump(index, open(os.path.join(HERE, "vtp", "index_full.json" if full else "index.json"), "w"), indent=1, sort_keys=True)
+    json.dump(index, open(index_path, "w"), indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":

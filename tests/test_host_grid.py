@@ -13,7 +13,9 @@ from lbm_b200 import host_api
 CASES = ["couette", "couette_bnd", "couette_bnd_bbDirichlet", "poiseuille", "poiseuille_bnd", "step_ns", "sphere_ns",
          "couette_bnd_eq", "couette_bnd_eq2", "couette_bnd_eq_aligned", "couette_bnd_NEEM", "couette_bnd_NEBB",
          "poiseuille_bnd_eq", "poiseuille_bnd_NEEM", "poiseuille_bnd_NEBB", "poiseuille_bnd_pressure",
-         "poiseuille_bnd_pressure_neem2"]  # the *_aligned / poiseuille_bnd_* cases use alignNodesWithSurface
+         "poiseuille_bnd_pressure_neem2",  # the *_aligned / poiseuille_bnd_* cases use alignNodesWithSurface
+         # multi-level grids: partitionLevel < uniformLevel and / or boundary refinement
+         "couette_ml_p3u5", "couette_ml_u5m6", "couette_ml_p4u5m7", "sphere_ml_p4u6", "step_ml_p3u5"]
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -14,7 +14,9 @@ CASES = ["couette", "couette_bnd", "couette_bnd_bbDirichlet", "poiseuille", "poi
          # wet-node wall family + the remaining Navier-Stokes cases of the reference's test/run.sh
          "couette_bnd_eq", "couette_bnd_eq2", "couette_bnd_eq_aligned", "couette_bnd_NEEM", "couette_bnd_NEBB",
          "poiseuille_bnd_eq", "poiseuille_bnd_NEEM", "poiseuille_bnd_NEBB", "poiseuille_bnd_pressure",
-         "poiseuille_bnd_pressure_neem2"]
+         "poiseuille_bnd_pressure_neem2",
+         # multi-level grids: every level is stepped as its own lattice
+         "couette_ml_p3u5", "couette_ml_u5m6", "couette_ml_p4u5m7", "sphere_ml_p4u6", "step_ml_p3u5"]
 
 
 def sha(a):

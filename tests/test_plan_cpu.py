@@ -41,6 +41,24 @@ def test_inspection_handle_refuses_to_compute():
     assert e.value.code == -3 and "no CPU compute path" in str(e.value)
 
 
+@pytest.mark.parametrize("name", ["couette_ml_p3u5", "couette_ml_u5m6", "couette_ml_p4u5m7", "sphere_ml_p4u6", "step_ml_p3u5"])
+def test_plan_gather_on_multi_level_grids(name, oracle_mod):
+    """every level is its own lattice; several cells may push into one slot (highest source wins)."""
+    from plan_interpreter import extrapolated_velocity, stale_values
+    spec = load_golden(name)
+    plan = plan_only_solver(spec).debug_plan()
+    o = spec.apply_to(oracle_mod.Oracle(spec.ndim, spec.ndist, spec.nghbr, spec.omega))
+    o.init()
+    values = stale_values(plan, o.fold.copy(), spec.ndist)
+    dev2ref = np.full(plan["npad"], -1)
+    dev2ref[plan["ref2dev"]] = np.arange(plan["n"])
+    for _ in range(3):
+        o.step(1)
+        uext = extrapolated_velocity(plan, lambda n: o.vars[dev2ref[n], :spec.ndim], None, spec.ndim)
+        mine = gather(plan, to_device(plan, o.f, spec.ndist), spec.ndist, values=values, uext=uext)
+        assert np.array_equal(mine, o.fold)
+
+
 @pytest.mark.parametrize("name", ["couette", "couette_bnd", "couette_bnd_bbDirichlet"])
 def test_plan_gather_equals_oracle_fold_on_reference_cases(name, oracle_mod):
     spec = load_golden(name)

@@ -60,7 +60,9 @@ def test_solution_file_is_byte_identical_to_the_reference(name, hostlib, oracle_
     spec = load_golden(name)
     v = final_moments(spec, oracle_mod)
     out = str(tmp_path / INDEX[name]["file"])
-    assert write(hostlib, out, spec.center, v, ["U", "V", "rho"]) == 0
+    # default cell filter "leafCells" (solver.cpp:86, cell_filter.h:60-96): on multi-level grids only the childless cells are written
+    keep = ((spec.golden["props"] >> 14) & 1).astype(np.uint8)
+    assert write(hostlib, out, spec.center, v, ["U", "V", "rho"], None if keep.all() else keep) == 0
     data = open(out, "rb").read()
     whole = os.path.join(HERE, "golden", "vtp", f"{name}.vtp.gz")
     if os.path.exists(whole):
