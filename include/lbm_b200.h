@@ -151,6 +151,8 @@ int lbm_b200_synchronize(lbm_b200_solver* s);
 
 /* Replaces sumAbsDiff for every variable (src/lbm/solver.cpp:809-815) and the NaN/Inf test
  * (src/lbm/solver.cpp:254-260): out[v] = sum over cells |vars - varsold|.  Requires track_vars. */
+/* In a partitioned run (lbm_b200_comm_init) the sums cover the whole domain: one ncclAllReduce of NVAR + 1 doubles over the
+ * ranks' owned cells; the call is then collective (every rank calls it at the same step). */
 int lbm_b200_residual(lbm_b200_solver* s, double* out, int32_t* diverged);
 
 /* State read-back in the reference's layout.  Any pointer may be NULL.

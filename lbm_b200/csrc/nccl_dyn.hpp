@@ -17,6 +17,7 @@ struct NcclApi {
   ncclResult_t (*GroupEnd)()                                                                        = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)          = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)                = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t)                                                       = nullptr;
 
   bool load(std::string* err) {
@@ -35,7 +36,8 @@ struct NcclApi {
     Send           = reinterpret_cast<decltype(Send)>(sym("ncclSend"));
     Recv           = reinterpret_cast<decltype(Recv)>(sym("ncclRecv"));
     GetErrorString = reinterpret_cast<decltype(GetErrorString)>(sym("ncclGetErrorString"));
-    if(!GetUniqueId || !CommInitRank || !CommDestroy || !GroupStart || !GroupEnd || !Send || !Recv || !GetErrorString) {
+    AllReduce      = reinterpret_cast<decltype(AllReduce)>(sym("ncclAllReduce"));
+    if(!AllReduce || !GetUniqueId || !CommInitRank || !CommDestroy || !GroupStart || !GroupEnd || !Send || !Recv || !GetErrorString) {
       *err = "NCCL library lacks a required symbol";
       return false;
     }

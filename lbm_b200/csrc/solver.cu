@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <memory>
 #include <string>
 #include <vector>
@@ -687,6 +688,19 @@ struct Solver final : SolverBase {
       for(int b = 0; b < nb; ++b) s += h[static_cast<size_t>(v) * nb + b];
       out[v] = s;
       if(std::isnan(s) || std::isinf(s)) bad = 1;
+    }
+    if(comm != nullptr && comm_size > 1) {
+      // partitioned run: the residual of the whole domain = sum over the ranks' owned cells, one
+      // ncclAllReduce of NVAR + 1 doubles (the last one carries the NaN/Inf flag).  Collective: every rank calls residual().
+      double h2[NVAR + 1];
+      for(int v = 0; v < NVAR; ++v) h2[v] = (std::isnan(out[v]) || std::isinf(out[v])) ? 0.0 : out[v];
+      h2[NVAR] = bad;
+      CUDA_TRY(cudaMemcpyAsync(d_partial.p, h2, sizeof(h2), cudaMemcpyHostToDevice, stream));
+      NCCL_TRY(lbm::nccl_api().AllReduce(d_partial.p, d_partial.p, NVAR + 1, ncclFloat64, ncclSum, comm, stream));
+      CUDA_TRY(cudaMemcpyAsync(h2, d_partial.p, sizeof(h2), cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      bad = h2[NVAR] > 0.0 ? 1 : 0;
+      for(int v = 0; v < NVAR; ++v) out[v] = bad ? std::numeric_limits<double>::quiet_NaN() : h2[v];
     }
     if(diverged) *diverged = bad;
     return LBM_B200_OK;

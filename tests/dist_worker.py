@@ -191,6 +191,10 @@ def main():
         s.init()
         s.step(args.steps)
         mine_f, mine_fold = s.f[:lp.n_owned], s.fold[:lp.n_owned]
+        # residual of the whole domain: ncclAllReduce over the ranks' owned cells (order of the sum differs from the serial one)
+        res, bad = s.residual()
+        ref_res, _ = ref.residual()
+        assert not bad and np.allclose(res, ref_res, rtol=1e-11, atol=1e-300), (res, ref_res)
         st = s.stats()
         assert st["cells_ghost"] == lp.n_ghost and (world == 1 or st["halo_bytes"] > 0)
         torch.cuda.synchronize()
