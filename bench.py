@@ -99,9 +99,45 @@ def apply_bcs(solver, wl):
     for kind, cells, normals, val in wl["bcs"]:
         if kind == "dirichlet_bb":
             solver.add_dirichlet_bb(cells, normals, val)
+        elif kind == "pressure":
+            solver.add_pressure(cells, normals, val)
         else:
             solver.add_wall_bb(cells, normals, val)
     return solver
+
+
+def case_workload(name, size, rank=0, world=1):
+    """BASELINE.json configs[3] ("sphere": flow past a sphere, D3Q27, MRT) and configs[4] ("step": channel with a step, D3Q19, TRT,
+    pressure outflow) as 3D cases on a cube of size^3 cells (lbm_b200/cases.py), cut into `world` contiguous SFC ranges.  The grid
+    comes from the host pipeline's on-demand row provider (lbm_b200/host/uniform_grid.hpp), so no rank ever holds the whole table."""
+    import math
+    from lbm_b200 import cases, host_api, partition
+    level = int(round(math.log2(size)))
+    if 2 ** level != size:
+        raise SystemExit("--size must be a power of two for the sphere / step workloads (cells per side of the cube)")
+    cfg = cases.CONFIGS[name + "3d"](level)
+    ndim, ndist = 3, cases.NDIST[cfg["solver"]["model"]]
+    tmp = tempfile.mkdtemp(prefix="lbm_case_")
+    path = os.path.join(tmp, "case.json")
+    with open(path, "w") as fh:
+        json.dump(cfg, fh)
+    ug = host_api.UniformGrid(path)
+    surfaces = {nm: (cells, normals) for nm, cells, normals in ug.surfaces()}
+    bcs, _ = cases.bcs_from_config(cfg["solver"], surfaces, ndim)
+    lp = None
+    if world == 1:
+        nghbr = ug.rows(np.arange(ug.n, dtype=np.int64))[0]
+        n_owned = ug.n
+    else:
+        pressure = [(bc["cells"], bc["normals"]) for bc in bcs if bc["kind"] == "pressure"]
+        lp = partition.plan_rank(partition.GridRows(ug, ndist), rank, world, ug.stride, pressure)
+        bcs = cases.restrict_bcs(bcs, lp)
+        nghbr, n_owned = lp.nghbr, lp.n_owned
+    flat = [(bc["kind"], bc["cells"], bc["normals"], bc.get("pressure", bc.get("tangential", 0.0))) for bc in bcs]
+    n_global = int(ug.n)
+    ug.close()
+    return dict(ndim=ndim, ndist=ndist, nghbr=nghbr, center=None, bcs=flat, shape=(size,) * 3, lp=lp, n_owned=n_owned, n_global=n_global,
+                lattice=cfg["solver"]["model"], collision={"sphere": "mrt", "step": "trt"}[name])
 
 
 class ClockSampler:
@@ -263,6 +299,16 @@ def run_reference(args):
 
 def config_dict(args, note):
     ndim, ndist = LATTICES[args.lattice]
+    if args.workload != "box":
+        what = {"sphere": "flow past a sphere (radius L/10 at the centre of a cube, pressure in-/outlet on -x/+x, bounce-back walls and "
+                          "sphere; BASELINE.json configs[3], 3D form of test/sphere/sphere_ns.json)",
+                "step": "channel with a step (block on the upper wall, pressure in-/outlet, bounce-back walls; BASELINE.json configs[4], "
+                        "3D form of test/step/step_ns.json)"}[args.workload]
+        return {"workload": f"{args.workload}-3D {args.size}^3 {args.lattice} {args.collision.upper()} fp64: {what}, omega={OMEGA:.6f}",
+                "lattice": args.lattice, "collision": args.collision, "arithmetic": args.arithmetic,
+                "l2_policy": "inputs larger than L2 (no flush needed)" if args.size >= 128 else "SMALL CASE: fits L2, not a bandwidth measurement",
+                "parallelism": (f"one cube of {args.size}^3 cells cut into {args.gpus} contiguous SFC ranges (fixed total size), ncclSend/ncclRecv "
+                                f"halo exchange of outgoing populations every step") if args.gpus > 1 else "single GPU", "note": note}
     return {"workload": f"bench-3D cube {args.size}^{ndim} {args.lattice} BGK fp64 (BASELINE.json configs[2]; SURVEY 8d S3): "
                         f"periodic x, bounce-back walls, moving lid u={LID_U}, omega={OMEGA:.6f}",
             "cells_per_gpu": args.size ** ndim, "lattice": args.lattice, "collision": "bgk", "arithmetic": args.arithmetic,
@@ -281,14 +327,25 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    ndim, ndist = LATTICES[args.lattice]
     arithmetic = lbm_b200.FAST if args.arithmetic == "fast" else lbm_b200.STRICT
     t_setup = time.perf_counter()
-    wl = workload(args.size, args.lattice, rank, world)
+    if args.workload == "box":
+        wl = workload(args.size, args.lattice, rank, world)
+        args.collision = "bgk"
+    else:
+        wl = case_workload(args.workload, args.size, rank, world)
+        args.lattice, args.collision = wl["lattice"], wl["collision"]
+    ndim, ndist = LATTICES[args.lattice]
     n = wl["n_owned"]
     n_local = wl["nghbr"].shape[0]
     stream = torch.cuda.current_stream().cuda_stream
-    s = lbm_b200.Solver(ndim, ndist, wl["nghbr"], OMEGA, arithmetic=arithmetic, device=local, track_vars=0, stream=stream)
+    from lbm_b200.cases import trt_omega_minus
+    coll = {"bgk": lbm_b200.BGK, "trt": lbm_b200.TRT, "mrt": lbm_b200.MRT}[args.collision]
+    om_minus = trt_omega_minus(OMEGA)
+    # MRT: per-direction-pair rates; even part relaxed with omega, odd part with the TRT 'magic' rate
+    rates = np.array([OMEGA if i % 2 == 0 else om_minus for i in range(27)])
+    s = lbm_b200.Solver(ndim, ndist, wl["nghbr"], OMEGA, arithmetic=arithmetic, device=local, track_vars=0, stream=stream,
+                        collision=coll, omega_minus=om_minus, mrt_rates=rates)
     apply_bcs(s, wl)
     if world > 1:
         from lbm_b200.capi import comm_unique_id
@@ -319,7 +376,8 @@ def run_ours(args):
         t = torch.tensor([ms_total, ms_main], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, ms_main = float(t[0]), float(t[1])
-    value = args.size ** ndim * world * args.steps / (ms_total * 1e-3) / 1e6
+    n_global = args.size ** ndim * world if args.workload == "box" else wl["n_global"]
+    value = n_global * args.steps / (ms_total * 1e-3) / 1e6
 
     # ---- e2e: state in pinned host buffers, through the C ABI: upload m_fold (the input of a time step; m_f is overwritten by the
     # collision before anything reads it, solver.cpp:601-613), K steps, download the fields
@@ -346,7 +404,7 @@ def run_ours(args):
             t = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t[0])
-        e2e = {"value": n * world * k / dt / 1e6, "unit": "MLUPS",
+        e2e = {"value": n_global * k / dt / 1e6, "unit": "MLUPS",
                "h2d_bytes_per_step": (b1["h2d_bytes"] - b0["h2d_bytes"]) / k, "d2h_bytes_per_step": (b1["d2h_bytes"] - b0["d2h_bytes"]) / k,
                "region": f"lbm_b200_set_populations(pinned m_fold) + {k} x lbm_b200_step + lbm_b200_get_moments(pinned)",
                "finite": bool(torch.isfinite(mom_host[:n]).all())}
@@ -364,10 +422,10 @@ def run_ours(args):
     achieved = b_alg * n * args.steps / (ms_main * 1e-3) / 1e9
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": ncu_traffic(args.lattice, args.size), "peak_source": peak_src,
-            "kernel": "lbm::k_step (fused pull-stream + BC + moments + BGK collide)",
+            "kernel": f"lbm::k_step (fused pull-stream + BC + moments + {args.collision.upper()} collide)",
             "bytes_per_cell_alg": b_alg, "cells_per_launch": n, "ms_per_launch": ms_main / args.steps}
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and args.workload == "box":
         from oracle import oracle
         oracle.build()
         v, steps, nc, cores = cpu_sample(args.lattice, args.cpu_size, args.cpu_budget)
@@ -377,8 +435,8 @@ def run_ours(args):
                "reference_binary_d2q9": reference_binary_d2q9()}
     line = {
         "metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak" if args.workload == "box" else "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(args, f"{st0['cells_fast']} of {st0['ncells']} cells on the index-free chunk path; setup {t_setup:.1f} s"),
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
@@ -391,6 +449,9 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--workload", default="box", choices=["box", "sphere", "step"],
+                    help="box: BASELINE.json configs[2] (default, the metric's configuration); sphere / step: configs[3] / configs[4] in 3D, "
+                         "--size = cells per side of the whole cube")
     ap.add_argument("--lattice", default="D3Q19", choices=sorted(LATTICES))
     ap.add_argument("--arithmetic", default="fast", choices=["fast", "strict"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

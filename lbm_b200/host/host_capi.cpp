@@ -3,6 +3,7 @@
 #include <string>
 
 #include "lbm_solver.hpp"
+#include "uniform_grid.hpp"
 
 using namespace lbmhost;
 
@@ -125,6 +126,61 @@ int64_t lbmhost_postprocess_line(void* h, const double* vars, const char* out_pa
     return -1;
   }
 }
+// ---- single-level grid, rows on demand (uniform_grid.hpp): what one rank of a partitioned run asks the grid pipeline
+void* lbmhost_ugrid_build(const char* config_path, char* err, int errlen) {
+  auto* u = new UniformGrid();
+  try {
+    u->configure(Json::parse_file(config_path));
+  } catch(const std::exception& e) {
+    set_err(err, errlen, e.what());
+    delete u;
+    return nullptr;
+  }
+  return u;
+}
+void lbmhost_ugrid_free(void* h) { delete static_cast<UniformGrid*>(h); }
+int64_t lbmhost_ugrid_ncells(void* h) { return static_cast<UniformGrid*>(h)->n; }
+int lbmhost_ugrid_ndim(void* h) { return static_cast<UniformGrid*>(h)->ndim; }
+int lbmhost_ugrid_stride(void* h) { return static_cast<UniformGrid*>(h)->nn_diag; }
+int lbmhost_ugrid_level(void* h) { return static_cast<UniformGrid*>(h)->level; }
+double lbmhost_ugrid_cell_length(void* h) { return static_cast<UniformGrid*>(h)->cell_length(); }
+void lbmhost_ugrid_bbox(void* h, double* lo, double* hi) {
+  const auto* u = static_cast<UniformGrid*>(h);
+  for(int d = 0; d < u->ndim; ++d) { lo[d] = u->bbmin[d]; hi[d] = u->bbmax[d]; }
+}
+int lbmhost_ugrid_rows(void* h, const int64_t* ids, int64_t count, int64_t* nghbr, int stride, double* center, char* err, int errlen) {
+  std::string e;
+  if(static_cast<UniformGrid*>(h)->rows(ids, count, nghbr, stride, center, &e)) return 0;
+  set_err(err, errlen, e);
+  return -1;
+}
+int lbmhost_ugrid_sources(void* h, const int64_t* ids, int64_t count, int64_t* src, int stride, char* err, int errlen) {
+  std::string e;
+  if(static_cast<UniformGrid*>(h)->sources(ids, count, src, stride, &e)) return 0;
+  set_err(err, errlen, e);
+  return -1;
+}
+int lbmhost_ugrid_nsurfaces(void* h, char* err, int errlen) {
+  auto* u = static_cast<UniformGrid*>(h);
+  try {
+    if(u->surfaces.empty()) u->build_surfaces();
+  } catch(const std::exception& e) {
+    set_err(err, errlen, e.what());
+    return -1;
+  }
+  return static_cast<int>(u->surfaces.size());
+}
+const char* lbmhost_ugrid_surface_name(void* h, int k) { return static_cast<UniformGrid*>(h)->surfaces[k].name.c_str(); }
+int64_t lbmhost_ugrid_surface_size(void* h, int k) { return static_cast<int64_t>(static_cast<UniformGrid*>(h)->surfaces[k].cells.size()); }
+void lbmhost_ugrid_surface_copy(void* h, int k, int64_t* cells, double* normals) {
+  const auto*    u = static_cast<UniformGrid*>(h);
+  const Surface& s = u->surfaces[k];
+  for(size_t i = 0; i < s.cells.size(); ++i) {
+    cells[i] = s.cells[i];
+    for(int d = 0; d < u->ndim; ++d) normals[i * u->ndim + d] = s.normal.at(s.cells[i])[d];
+  }
+}
+
 void lbmhost_round15(const double* in, double* out, int64_t n) {
   for(int64_t i = 0; i < n; ++i) out[i] = vtk::round15(in[i]);
 }

@@ -40,6 +40,24 @@ def lib():
         L.lbmhost_postprocess_line.restype = C.c_int64
         L.lbmhost_postprocess_line.argtypes = [vp, vp, C.c_char_p, C.c_char_p, C.c_int]
         L.lbmhost_run.argtypes = [C.c_char_p, vp, vp, C.c_int64, C.c_char_p, C.c_int]
+        L.lbmhost_ugrid_build.restype = vp
+        L.lbmhost_ugrid_build.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        L.lbmhost_ugrid_free.argtypes = [vp]
+        L.lbmhost_ugrid_ncells.restype = C.c_int64
+        L.lbmhost_ugrid_ncells.argtypes = [vp]
+        for fn in ("ndim", "stride", "level"):
+            getattr(L, f"lbmhost_ugrid_{fn}").argtypes = [vp]
+        L.lbmhost_ugrid_cell_length.restype = C.c_double
+        L.lbmhost_ugrid_cell_length.argtypes = [vp]
+        L.lbmhost_ugrid_bbox.argtypes = [vp, vp, vp]
+        L.lbmhost_ugrid_rows.argtypes = [vp, vp, C.c_int64, vp, C.c_int, vp, C.c_char_p, C.c_int]
+        L.lbmhost_ugrid_sources.argtypes = [vp, vp, C.c_int64, vp, C.c_int, C.c_char_p, C.c_int]
+        L.lbmhost_ugrid_nsurfaces.argtypes = [vp, C.c_char_p, C.c_int]
+        L.lbmhost_ugrid_surface_name.restype = C.c_char_p
+        L.lbmhost_ugrid_surface_name.argtypes = [vp, C.c_int]
+        L.lbmhost_ugrid_surface_size.restype = C.c_int64
+        L.lbmhost_ugrid_surface_size.argtypes = [vp, C.c_int]
+        L.lbmhost_ugrid_surface_copy.argtypes = [vp, C.c_int, vp, vp]
         _LIB = L
     return _LIB
 
@@ -99,3 +117,71 @@ def run(config_path, nvars=0):
     rc = L.lbmhost_run(config_path.encode(), out.ctypes.data, vars_.ctypes.data if nvars else None, nvars, err, 2048)
     keys = ["max_error", "l2_error", "gre", "steps", "converged", "residual"]
     return rc, err.value.decode(), dict(zip(keys, out.tolist())), vars_
+
+
+class UniformGrid:
+    """Single-level grid of a configuration with table rows ON DEMAND (lbm_b200/host/uniform_grid.hpp): what one rank of a partitioned
+    run asks the grid pipeline.  Same cell order, neighbour rows, centres and boundary surfaces as build_grid() on the same
+    configuration (tests/test_uniform_grid.py), without ever holding a table over the whole domain."""
+
+    def __init__(self, config_path):
+        self._L = lib()
+        err = C.create_string_buffer(1024)
+        self._h = self._L.lbmhost_ugrid_build(str(config_path).encode(), err, 1024)
+        if not self._h:
+            raise RuntimeError(err.value.decode())
+        L, h = self._L, self._h
+        self.n, self.ndim, self.stride, self.level = L.lbmhost_ugrid_ncells(h), L.lbmhost_ugrid_ndim(h), L.lbmhost_ugrid_stride(h), L.lbmhost_ugrid_level(h)
+        self.cell_length = L.lbmhost_ugrid_cell_length(h)
+        self.bbmin, self.bbmax = np.zeros(self.ndim), np.zeros(self.ndim)
+        L.lbmhost_ugrid_bbox(h, self.bbmin.ctypes.data, self.bbmax.ctypes.data)
+        self._surfaces = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lbmhost_ugrid_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def _call(self, fn, ids, want_center=False):
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        out = np.empty((len(ids), self.stride), dtype=np.int64)
+        err = C.create_string_buffer(512)
+        if fn == "rows":
+            center = np.empty((len(ids), self.ndim)) if want_center else None
+            rc = self._L.lbmhost_ugrid_rows(self._h, ids.ctypes.data, len(ids), out.ctypes.data, self.stride,
+                                            center.ctypes.data if want_center else None, err, 512)
+        else:
+            center = None
+            rc = self._L.lbmhost_ugrid_sources(self._h, ids.ctypes.data, len(ids), out.ctypes.data, self.stride, err, 512)
+        if rc != 0:
+            raise RuntimeError(err.value.decode())
+        return out, center
+
+    def rows(self, ids, want_center=False):
+        """push-table rows [len(ids), stride] (global ids, -1 = none) and optionally the cell centres"""
+        return self._call("rows", ids, want_center)
+
+    def sources(self, ids):
+        """pull sources: out[r, s] = the cell whose push in direction s lands in ids[r]"""
+        return self._call("sources", ids)[0]
+
+    def surfaces(self):
+        """[(name, cells, normals)] in creation order, like build_grid()["surfaces"]"""
+        if self._surfaces is None:
+            err = C.create_string_buffer(512)
+            ns = self._L.lbmhost_ugrid_nsurfaces(self._h, err, 512)
+            if ns < 0:
+                raise RuntimeError(err.value.decode())
+            out = []
+            for k in range(ns):
+                m = self._L.lbmhost_ugrid_surface_size(self._h, k)
+                cells = np.empty(m, dtype=np.int64)
+                normals = np.empty((m, self.ndim))
+                if m:
+                    self._L.lbmhost_ugrid_surface_copy(self._h, k, cells.ctypes.data, normals.ctypes.data)
+                out.append((self._L.lbmhost_ugrid_surface_name(self._h, k).decode(), cells, normals))
+            self._surfaces = out
+        return self._surfaces

@@ -70,6 +70,29 @@ class BoxRows:
         return box_rows(self.shape, self.periodic, ids, want_center=True)[1]
 
 
+class GridRows:
+    """Row provider over a configuration's single-level grid, rows generated on demand (lbm_b200.host_api.UniformGrid): box / sphere /
+    step geometries of any size without a table over the whole domain.  Composed diagonal steps make the table asymmetric next to
+    cut cells, so the pull sources come from the grid object (it evaluates the source's own composition)."""
+
+    def __init__(self, grid, ndist):
+        self.grid = grid
+        self.n = int(grid.n)
+        self.qm = ndist - 1
+
+    def rows(self, ids):
+        if getattr(self, "_last_ids", None) is ids:
+            return self._last_rows
+        self._last_ids, self._last_rows = ids, np.ascontiguousarray(self.grid.rows(ids)[0][:, :self.qm])
+        return self._last_rows
+
+    def sources(self, ids):
+        return np.ascontiguousarray(self.grid.sources(ids)[:, :self.qm])
+
+    def centers(self, ids):
+        return self.grid.rows(ids, want_center=True)[1]
+
+
 @dataclass
 class LocalProblem:
     rank: int

@@ -12,6 +12,8 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
+from lbm_b200.cases import bcs_from_config, omega_from_config  # noqa: F401  (re-exported: the tests use the product's own mapping)
+
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
@@ -57,17 +59,6 @@ class CaseSpec:
         return solver
 
 
-def omega_from_config(solver_cfg, maxlvl):
-    """src/lbm/solver.cpp:102-123"""
-    if "relaxation" in solver_cfg:
-        return 1.0 / float(solver_cfg["relaxation"])
-    ma = float(solver_cfg["ma"])
-    re = float(solver_cfg["reynoldsnumber"])
-    ref_length = float(solver_cfg.get("refLength", 1.0))
-    nu = ma / re * ref_length
-    return 2.0 / (1.0 + 2.0 * nu * 2.0 ** maxlvl)
-
-
 def geometry_bbox(geometry_cfg, ndim):
     """GeometryManager::getBoundingBox (src/geometry.h) for analytic objects."""
     lo = np.full(ndim, np.inf)
@@ -86,48 +77,6 @@ def geometry_bbox(geometry_cfg, ndim):
             raise ValueError(g["type"])
         lo, hi = np.minimum(lo, a), np.maximum(hi, b)
     return lo, hi
-
-
-def bcs_from_config(solver_cfg, surfaces, ndim):
-    """surfaces: name -> (cells, normals).  Returns (bc list in application order, forcing or None)."""
-    bcs = []
-    boundary = solver_cfg["boundary"]
-    for geom in sorted(boundary):
-        keys = boundary[geom]
-        for key in sorted(keys):
-            conf = keys[key]
-            sname = f"{geom}_{key}" if len(keys) > 1 else geom
-            cells, normals = surfaces.get(sname, (np.zeros(0, np.int64), np.zeros((0, ndim))))
-            if len(cells) == 0:
-                continue  # bnd.h:83-86
-            if not conf.get("generateBndry", True):
-                continue  # LBMBnd_dummy, bnd.h:149-159
-            t = conf["type"]
-            if t == "periodic":
-                conn = surfaces[conf["connection"]][0]
-                bcs.append(dict(kind="periodic", cells=cells, normals=normals, connected=conn,
-                                pressure=float(conf.get("pressure", "nan"))))
-            elif t == "wall":
-                if conf["model"] == "bounceback":
-                    bcs.append(dict(kind="wall_bb", cells=cells, normals=normals,
-                                    tangential=float(conf.get("tangentialVelocity", 0.0))))
-                elif conf["model"] in ("equilibrium", "neem", "nebb"):
-                    vel = np.array(conf["velocity"], float)[:ndim] if "velocity" in conf else None
-                    bcs.append(dict(kind="wall_wetnode", model=conf["model"], cells=cells, normals=normals, velocity=vel))
-                else:
-                    raise ValueError(f"Invalid wall boundary model: {conf['model']}")
-            elif t == "pressure":
-                bcs.append(dict(kind="pressure", cells=cells, normals=normals, pressure=float(conf["pressure"])))
-            elif t == "dirichlet" and conf["model"] == "bounceback":
-                bcs.append(dict(kind="dirichlet_bb", cells=cells, normals=normals,
-                                value=np.array(conf["value"], float)[:ndim]))
-            else:
-                raise NotImplementedError(f"boundary type {t}")
-    forcing = None
-    if solver_cfg.get("forcing", ""):
-        forcing = dict(inlet=surfaces["cube_-x"][0], outlet=surfaces["cube_+x"][0],
-                       gradient=float(solver_cfg["poiseuillePressureGradient"]))
-    return bcs, forcing
 
 
 def load_golden(name):

@@ -13,40 +13,10 @@ import tempfile
 import numpy as np
 
 from casebuilder import CaseSpec, bcs_from_config, geometry_bbox
-
-WALL = {"type": "wall", "model": "bounceback"}
-
-
-def sphere3d_config(level, model="D3Q27"):
-    """sphere_ns.json (box [0,10]^2 minus a sphere of radius 1 at the centre, pressure in-/outlet on -x/+x) in 3D"""
-    return {"dim": 3, "partitionLevel": level, "uniformLevel": level, "maxRfnmtLvl": level, "maxNoCells": 100000000,
-            "outputDir": "out", "gridFileName": "gridD",
-            "geometry": {"cube": {"type": "box", "body": "flowregion", "A": [0.0, 0.0, 0.0], "B": [10.0, 10.0, 10.0]},
-                         "sphere": {"type": "sphere", "body": "flowregion", "subtract": True, "center": [5.0, 5.0, 5.0], "radius": 1.0}},
-            "solver": {"type": "lbm", "model": model, "relaxation": 0.6, "maxSteps": 10,
-                       "boundary": {"cube": {"+x": {"type": "pressure", "pressure": 1.0}, "-x": {"type": "pressure", "pressure": 1.0000008},
-                                             "-y": WALL, "+y": WALL, "-z": WALL, "+z": WALL},
-                                    "sphere": {"all": WALL}}}}
+from lbm_b200.cases import CONFIGS, NDIST, sphere3d_config, step3d_config  # noqa: F401
 
 
-def step3d_config(level, model="D3Q19"):
-    """step_ns.json (channel [0,10]x[0,9] with two side pockets, i.e. a block on the upper wall, pressure in-/outlet) extruded in z"""
-    return {"dim": 3, "partitionLevel": level, "uniformLevel": level, "maxRfnmtLvl": level, "maxNoCells": 100000000,
-            "outputDir": "out", "gridFileName": "gridD",
-            "geometry": {"cube": {"type": "box", "body": "flowregion", "A": [0.0, 0.0, 0.0], "B": [10.0, 9.0, 10.0]},
-                         "step_a": {"type": "box", "body": "flowregion", "subtract": False, "A": [0.0, 9.0, 0.0], "B": [4.0, 10.0, 10.0]},
-                         "step_b": {"type": "box", "body": "flowregion", "subtract": False, "A": [6.0, 9.0, 0.0], "B": [10.0, 10.0, 10.0]}},
-            "solver": {"type": "lbm", "model": model, "relaxation": 0.6, "maxSteps": 10,
-                       "boundary": {"cube": {"+x": {"type": "pressure", "pressure": 1.0}, "-x": {"type": "pressure", "pressure": 1.0000008},
-                                             "-y": WALL, "+y": WALL, "-z": WALL, "+z": WALL},
-                                    "step_a": {"+x": WALL, "-x": {"type": "pressure", "pressure": 1.0000008}, "+y": WALL, "-y": WALL,
-                                               "-z": WALL, "+z": WALL},
-                                    "step_b": {"+x": {"type": "pressure", "pressure": 1.0}, "-x": WALL, "+y": WALL, "-y": WALL,
-                                               "-z": WALL, "+z": WALL}}}}
 
-
-CONFIGS = {"sphere3d": sphere3d_config, "step3d": step3d_config}
-NDIST = {"D3Q19": 19, "D3Q27": 27}
 
 
 def build_case(name, level, model=None):
