@@ -421,7 +421,7 @@ def run_ours(args):
     b_alg = st0["bytes_per_cell_alg"]
     achieved = b_alg * n * args.steps / (ms_main * 1e-3) / 1e9
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": ncu_traffic(args.lattice, args.size), "peak_source": peak_src,
+            "traffic": ncu_traffic(args.lattice, args.size) if args.workload == "box" else None, "peak_source": peak_src,
             "kernel": f"lbm::k_step (fused pull-stream + BC + moments + {args.collision.upper()} collide)",
             "bytes_per_cell_alg": b_alg, "cells_per_launch": n, "ms_per_launch": ms_main / args.steps}
     cpu = None
