@@ -203,7 +203,7 @@ typedef struct {
   int64_t         n_copy;
   const double*   addtab;    /* [n_add*4] v0, v1, v2, count */
   int64_t         n_add;
-  const double*   wall_desc; /* [n_wall*4] per wall descriptor Q-1 entries of v0, v1, v2, count */
+  const double*   wall_desc; /* [n_wall*4] per wall descriptor Q-1 entries of v0, v1, v2, count (count -1: anti-bounce-back slot) */
   int64_t         n_wall;
   const double*   abb_p;     /* [n_abb] pressure of every anti-bounce-back entry */
   const int32_t*  abb_cells; /* [n_abb*3] device cell, inward neighbours n1, n2 (< 0: -(slot+1) of the received velocity halo) */
@@ -219,6 +219,9 @@ typedef struct {
   const int32_t*  vsend_cells; /* [n_vsend] device cells whose velocity is sent, wire order */
   int64_t         n_vsend;
   int64_t         n_vrecv;     /* received velocity items */
+  const int32_t*  chunk_abb_base; /* [n_fast_chunks] row of chunk_abb (chunks on a pressure face), -1 otherwise */
+  const int32_t*  chunk_abb;      /* [n_chunk_abb_rows*chunk] anti-bounce-back entry of the cell at that device offset, -1 elsewhere */
+  int64_t         n_chunk_abb_rows;
 } lbm_b200_plan_view;
 int lbm_b200_debug_plan(lbm_b200_solver* s, lbm_b200_plan_view* out);
 

@@ -49,7 +49,8 @@ class PlanView(C.Structure):
         ("abb_p", C.POINTER(C.c_double)), ("abb_cells", C.POINTER(C.c_int32)), ("n_abb", C.c_int64),
         ("values", C.POINTER(C.c_double)), ("n_values", C.c_int64), ("stale_ref", C.POINTER(C.c_int64)), ("n_stale", C.c_int64),
         ("send_index", C.POINTER(C.c_int64)), ("n_send", C.c_int64), ("recv_index", C.POINTER(C.c_int64)), ("n_recv", C.c_int64),
-        ("vsend_cells", C.POINTER(C.c_int32)), ("n_vsend", C.c_int64), ("n_vrecv", C.c_int64)]
+        ("vsend_cells", C.POINTER(C.c_int32)), ("n_vsend", C.c_int64), ("n_vrecv", C.c_int64),
+        ("chunk_abb_base", C.POINTER(C.c_int32)), ("chunk_abb", C.POINTER(C.c_int32)), ("n_chunk_abb_rows", C.c_int64)]
 
 
 def library_path():
@@ -248,6 +249,8 @@ class Solver:
         out["send_index"] = arr(v.send_index, v.n_send)
         out["recv_index"] = arr(v.recv_index, v.n_recv)
         out["vsend_cells"] = arr(v.vsend_cells, v.n_vsend)
+        out["chunk_abb_base"] = arr(v.chunk_abb_base, v.n_fast_chunks)
+        out["chunk_abb"] = arr(v.chunk_abb, v.n_chunk_abb_rows * v.chunk, (int(v.n_chunk_abb_rows), int(v.chunk)))
         return out
 
     # ---- run

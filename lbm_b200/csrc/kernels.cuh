@@ -60,7 +60,9 @@ struct DevParams {
   // fast chunks
   const uint16_t* tmpl;     // [(Q-1)][CHUNK]
   const int32_t*  chunk_nb; // [n_fast_chunks][NSEL + 1]: neighbour chunk bases (-1 = wall), wall descriptor id
-  const AddEntryT<Real>* wall_desc; // [n_wall_desc][Q-1] bounce-back addends of wall chunks
+  const AddEntryT<Real>* wall_desc; // [n_wall_desc][Q-1] bounce-back addends of wall chunks (n < 0: anti-bounce-back slot)
+  const int32_t*  chunk_abb_base;   // [n_fast_chunks] row of chunk_abb for chunks on a pressure face, -1 otherwise
+  const int32_t*  chunk_abb;        // [rows][CHUNK] pressure entry of the cell at that offset
   int32_t         n_fast_chunks;    // fast chunks [chunk_off, chunk_off + n_fast_chunks) are updated by this launch
   int32_t         chunk_off;
   int32_t         n_fast_blocks;
@@ -330,8 +332,14 @@ __device__ __forceinline__ Real fast_slot(const DevParams<Real>& p, const Real* 
                                           const AddEntryT<Real>* __restrict__ wall) {
   using A = Ar<Real, STRICT>;
   if(nbv >= 0) return Abuf[static_cast<size_t>(J) * p.stride + nbv + static_cast<int32_t>(off)];
-  Real v = Abuf[static_cast<size_t>(L::opp(J)) * p.stride + cell]; // bnd_dirichlet.h:92
   const int n = wall[J].n;
+  if(n < 0) {
+    // chunk on a pressure in-/outlet face: anti-bounce-back with the cell's own pressure entry, evaluated by the same
+    // out-of-line routine as on the generic path (bnd_pressure.h:100)
+    const int32_t entry = p.chunk_abb[static_cast<size_t>(p.chunk_abb_base[cell / L::CHUNK]) * L::CHUNK + cell % L::CHUNK];
+    return special_slot<L, Real, STRICT>(p.tabs, Abuf, link_code(LK_ABB, entry), cell, J);
+  }
+  Real v = Abuf[static_cast<size_t>(L::opp(J)) * p.stride + cell]; // bnd_dirichlet.h:92
   for(int t = 0; t < n; ++t) v = A::add(v, wall[J].v[t]);            // bnd_dirichlet.h:111-117
   return v;
 }

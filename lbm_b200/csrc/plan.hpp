@@ -93,7 +93,10 @@ struct Plan {
   std::vector<int32_t>  ref2dev, dev2ref;
   std::vector<uint16_t> tmpl;       // (Q-1) * CH : sel << 10 | off
   std::vector<int32_t>  chunk_nb;   // n_fast_chunks * (NSEL + 1): device bases (-1: wall selector), then the wall descriptor id
-  std::vector<AddEntry> wall_desc;  // per wall descriptor: Q-1 addend entries (bounce-back slots of wall chunks)
+  std::vector<AddEntry> wall_desc;  // per wall descriptor: Q-1 addend entries (bounce-back slots of wall chunks); n = -1 marks an
+                                    // anti-bounce-back (pressure) slot, whose entry id comes from chunk_abb
+  std::vector<int32_t>  chunk_abb_base; // per fast chunk: row of chunk_abb, -1 if the chunk has no pressure cell
+  std::vector<int32_t>  chunk_abb;      // [rows][CH] anti-bounce-back entry of the cell at that (device) offset, -1 elsewhere
   std::vector<int32_t>  codes;      // (Q-1) * gen_stride
   std::vector<CopySrc>  copytab;
   std::vector<AddEntry> addtab;
@@ -484,7 +487,7 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
   for(const auto& kv : over) {
     const int64_t c = kv.first / Q;
     const int     j = static_cast<int>(kv.first % Q);
-    if(kv.second.kind != LK_BB && kv.second.kind != LK_BB_ADD) odd[c] = 1;
+    if(kv.second.kind != LK_BB && kv.second.kind != LK_BB_ADD && kv.second.kind != LK_ABB) odd[c] = 1;
     else if(j < QM && pull[static_cast<size_t>(c) * QM + j] >= 0) odd[c] = 1;
   }
   // ---- ghost blocks (partitioned runs): a chunk at a partition cut pulls from ghost cells.  If all ghosts that one (chunk,
@@ -563,6 +566,9 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
   std::vector<int64_t> nbref(static_cast<size_t>(nc) * L.NSEL, -1);
   std::vector<int32_t> wall_of(static_cast<size_t>(nc), -1);      // wall descriptor per candidate chunk
   std::vector<std::vector<AddEntry>> chunk_wall(static_cast<size_t>(nc));
+  // pressure (anti-bounce-back) chunks: a chunk on a pressure in-/outlet face stays index-free as well -- every slot that would
+  // pull from the missing neighbour chunk is an anti-bounce-back slot of the cell's pressure entry (curve offset -> entry id)
+  std::vector<std::vector<int32_t>> chunk_abb_ids(static_cast<size_t>(nc));
 #pragma omp parallel for schedule(dynamic, 64)
   for(int64_t k = 0; k < nc; ++k) {
     const int64_t b = cand_base[k];
@@ -571,6 +577,7 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
     nbk[SELF] = b;
     std::vector<AddEntry> wd(static_cast<size_t>(QM));
     std::vector<char>     wd_set(static_cast<size_t>(QM), 0);
+    std::vector<int32_t>  abb_of;
     for(int o = 0; o < CH && ok; ++o) {
       const int64_t c = b + o;
       if(odd[c]) { ok = false; break; }
@@ -583,7 +590,15 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
           auto it = over.find(key(c, j)); // read-only lookups: safe from several threads
           if(it == over.end()) { ok = false; break; } // stale slot
           AddEntry e{};
-          e.n = it->second.kind == LK_BB_ADD ? it->second.nadd : 0;
+          if(it->second.kind == LK_ABB) {
+            e.n = -1;
+            if(abb_of.empty()) abb_of.assign(static_cast<size_t>(CH), -1);
+            const int32_t id = static_cast<int32_t>(it->second.a);
+            if(abb_of[o] != -1 && abb_of[o] != id) { ok = false; break; } // a corner cell of two pressure surfaces: generic
+            abb_of[o] = id;
+          } else {
+            e.n = it->second.kind == LK_BB_ADD ? it->second.nadd : 0;
+          }
           for(int d = 0; d < 3; ++d) e.v[d] = d < e.n ? it->second.add[d] : 0.0;
           if(!wd_set[j]) { wd[j] = e; wd_set[j] = 1; }
           else if(wd[j].n != e.n || std::memcmp(wd[j].v, e.v, sizeof(e.v)) != 0) { ok = false; break; }
@@ -610,6 +625,7 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
     if(ok && has_wall) {
       for(int j = 0; j < QM; ++j) if(!wd_set[j]) { wd[j] = AddEntry{}; }
       chunk_wall[k] = wd;
+      chunk_abb_ids[k] = abb_of;
     }
   }
   // deduplicate wall descriptors (a box has a handful)
@@ -695,6 +711,15 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
       P.chunk_nb[f * NBW + s] = v;
     }
     P.chunk_nb[f * NBW + L.NSEL] = wall_of[k];
+  }
+  P.chunk_abb_base.assign(static_cast<size_t>(P.n_fast_chunks), -1);
+  for(size_t f = 0; f < fast_order.size(); ++f) {
+    const std::vector<int32_t>& ids = chunk_abb_ids[fast_order[f]];
+    if(ids.empty()) continue;
+    P.chunk_abb_base[f] = static_cast<int32_t>(P.chunk_abb.size() / CH);
+    P.chunk_abb.resize(P.chunk_abb.size() + CH, -1);
+    int32_t* row = &P.chunk_abb[P.chunk_abb.size() - CH];
+    for(int o = 0; o < CH; ++o) row[sfc2lex[o]] = ids[o];
   }
 
   // ---- 7. link codes of the generic range

@@ -92,7 +92,7 @@ struct Solver final : SolverBase {
   DevBuf<Real>     vars[2];   // tracked m_vars / m_varsold
   DevBuf<Real>     scratch;   // [max(Q,NVAR)][npad] read-back staging
   DevBuf<uint16_t> d_tmpl;
-  DevBuf<int32_t>  d_chunk_nb, d_codes;
+  DevBuf<int32_t>  d_chunk_nb, d_codes, d_chunk_abb_base, d_chunk_abb;
   DevBuf<lbm::AddEntryT<Real>> d_wall;
   DevBuf<lbm::CopySrcDev>       d_copy;
   DevBuf<lbm::AddEntryT<Real>>  d_add;
@@ -144,6 +144,8 @@ struct Solver final : SolverBase {
     p.tmpl = d_tmpl.p;
     p.chunk_nb = d_chunk_nb.p;
     p.wall_desc = d_wall.p;
+    p.chunk_abb_base = d_chunk_abb_base.p;
+    p.chunk_abb = d_chunk_abb.p;
     p.n_fast_chunks = static_cast<int32_t>(plan.n_fast_chunks);
     p.chunk_off = 0;
     p.gen_off = 0;
@@ -203,6 +205,8 @@ struct Solver final : SolverBase {
     CUDA_TRY(cudaMemset(scratch.p, 0, scratch.bytes()));
     CUDA_TRY(d_tmpl.upload(plan.tmpl));
     CUDA_TRY(d_chunk_nb.upload(plan.chunk_nb));
+    CUDA_TRY(d_chunk_abb_base.upload(plan.chunk_abb_base));
+    CUDA_TRY(d_chunk_abb.upload(plan.chunk_abb));
     CUDA_TRY(d_codes.upload(plan.codes));
     CUDA_TRY(d_ref2dev.upload(plan.ref2dev));
     if(!in.peers.empty()) {
@@ -739,6 +743,8 @@ struct Solver final : SolverBase {
     v->stale_ref = plan.stale_ref.data(); v->n_stale = static_cast<int64_t>(plan.stale_ref.size());
     v->send_index = plan.send_index.data(); v->n_send = static_cast<int64_t>(plan.send_index.size());
     v->recv_index = plan.recv_index.data(); v->n_recv = static_cast<int64_t>(plan.recv_index.size());
+    v->chunk_abb_base = plan.chunk_abb_base.data(); v->chunk_abb = plan.chunk_abb.data();
+    v->n_chunk_abb_rows = static_cast<int64_t>(plan.chunk_abb.size() / (plan.CH > 0 ? plan.CH : 1));
     v->vsend_cells = plan.vsend_cells.data(); v->n_vsend = static_cast<int64_t>(plan.vsend_cells.size()); v->n_vrecv = plan.n_vrecv;
     return LBM_B200_OK;
   }

@@ -53,7 +53,21 @@ def gather(plan, A, q, values=None, uext=None):
             if (~pull).any():
                 v = A[opp[j], cells[~pull]].copy()
                 e = plan["wall_desc"][wid, j]
-                for a in range(int(e[3])):
+                if e[3] < 0:
+                    # chunk on a pressure face: anti-bounce-back with the cell's own pressure entry (bnd_pressure.h:100)
+                    ent = plan["chunk_abb"][int(plan["chunk_abb_base"][k])][~pull].astype(np.int64)
+                    assert (ent >= 0).all()
+                    u = uext[ent]
+                    cu = np.zeros(len(ent))
+                    for d in range(u.shape[1]):  # Phys::cu_rt / vsq: sums in ascending dimension order
+                        cu = cu + u[:, d] * c[opp[j]][d]
+                    vs = u[:, 0] * u[:, 0]
+                    for d in range(1, u.shape[1]):
+                        vs = vs + u[:, d] * u[:, d]
+                    cs = 1.0 / 3.0
+                    se = w[opp[j]] * plan["abb_p"][ent] * (1.0 + cu * cu / (2.0 * cs * cs) - vs / (2.0 * cs))
+                    v = -v + 2 * se
+                for a in range(max(int(e[3]), 0)):
                     v = v + e[a]
                 val[~pull] = v
             fold_dev[j, cells] = val
