@@ -53,20 +53,3 @@ def test_partitioned_gpu_matches_single_domain_nccl(shape, ndist):
         pytest.skip("needs 2 GPUs")
     launch(2, "gpu", shape, ndist)
 
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("shape,ndist", [("18,16,16", 19), ("17,16,16", 27), ("34,64", 9)])
-def test_partitioned_gpu_pressure_boundary_nccl(shape, ndist):
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    launch(2, "gpu", shape, ndist, bc="pressure")
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("case,collision,level", [("sphere3d", "mrt", 6), ("step3d", "trt", 6)])
-def test_partitioned_gpu_baseline_configs_nccl(case, collision, level):
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    launch(2, "gpu", "0,0,0", 0, steps=10, extra=("--case", case, "--level", str(level), "--collision", collision))
