@@ -28,8 +28,25 @@ def omega_from_config(solver_cfg, maxlvl):
 
 
 
-def bcs_from_config(solver_cfg, surfaces, ndim):
-    """surfaces: name -> (cells, normals).  Returns (bc list in application order, forcing or None)."""
+def poisson_parameters(solver_cfg, ncells, ndim):
+    """m_dt and poisson_D of the Poisson equation types (src/lbm/solver.cpp:100,128-137,589-599): the time step follows from the cell
+    count (m_finestGridSpacing = 1 / (size^(1/NDIM) - 1)), the reaction rate is `equation_th` for "simple_diff_reaction" and the
+    Debye-Hueckel constant 27.79 otherwise."""
+    spacing = 1.0 / (float(ncells) ** (1.0 / ndim) - 1)
+    lbm_cs = 1.0 / np.sqrt(3.0)
+    ma = 1.0 / lbm_cs
+    dt = spacing * ma * lbm_cs / float(solver_cfg.get("refLength", 1.0))
+    if solver_cfg.get("equation_application", "debye_huckel") == "simple_diff_reaction":
+        rate = float(solver_cfg["equation_th"])
+    else:
+        rate = 27.79
+    return dt, rate
+
+
+def bcs_from_config(solver_cfg, surfaces, ndim, expr_values=None):
+    """surfaces: name -> (cells, normals).  Returns (bc list in application order, forcing or None).
+    expr_values: name -> per-entry values for boundary conditions whose "value" is a math expression (the reference evaluates it
+    with exprtk at the cell centres, bnd_dirichlet.h:268-281); the caller supplies the evaluated numbers."""
     bcs = []
     boundary = solver_cfg["boundary"]
     for geom in sorted(boundary):
@@ -58,6 +75,15 @@ def bcs_from_config(solver_cfg, surfaces, ndim):
                     raise ValueError(f"Invalid wall boundary model: {conf['model']}")
             elif t == "pressure":
                 bcs.append(dict(kind="pressure", cells=cells, normals=normals, pressure=float(conf["pressure"])))
+            elif t in ("dirichlet", "neumann") and conf["model"] == "neem":  # Poisson equation types, bnd.h:116-137
+                val = conf["value"]
+                if isinstance(val, str):
+                    if expr_values is None or sname not in expr_values:
+                        raise ValueError(f"boundary {sname}: the expression {val!r} must be evaluated by the caller (expr_values)")
+                    values = np.asarray(expr_values[sname], dtype=np.float64)
+                else:
+                    values = np.full(len(cells), float(val))
+                bcs.append(dict(kind="poisson_neem", neumann=t == "neumann", cells=cells, normals=normals, values=values, grad=0.0))
             elif t == "dirichlet" and conf["model"] == "bounceback":
                 bcs.append(dict(kind="dirichlet_bb", cells=cells, normals=normals,
                                 value=np.array(conf["value"], float)[:ndim]))
@@ -118,6 +144,8 @@ def apply_bcs(solver, bcs, forcing=None):
             solver.add_periodic(bc["cells"], bc["normals"], bc["connected"], bc["pressure"])
         elif k == "wall_wetnode":
             solver.add_wall_wetnode(bc["model"], bc["cells"], bc["normals"], bc["velocity"])
+        elif k == "poisson_neem":
+            solver.add_poisson_neem("neumann" if bc["neumann"] else "dirichlet", bc["cells"], bc["normals"], bc["values"], bc["grad"])
         else:
             raise ValueError(k)
     if forcing is not None:

@@ -29,6 +29,12 @@
  *                                 (equilibrium), src/lbm/bnd/bnd_wall.h:101-306 (NEEM), :313-479 (NEBB, D2Q9 only),
  *                                 src/lbm/moments.h:120-154 (density from a limited set)
  *
+ *   Poisson equation src/lbm/solver.cpp:283-293 (initial condition), :540-543 (potential), :562-566 with
+ *                                 src/lbm/equilibrium_func.h:149-163 (equilibrium), :589-612 (collision + source term), lattices
+ *                                 D1Q3 / D2Q5 src/lbm/constants.h:248-292, Dirichlet NEEM src/lbm/bnd/bnd_dirichlet.h:250-368,
+ *                                 Neumann NEEM src/lbm/bnd/bnd_neumann.h:15-66, potential from a cell's populations
+ *                                 src/lbm/moments.h:70-91 -- pinned on the five Poisson cases of the reference's test/run.sh
+ *
  * NOT pinned by the reference ("parity unpinned", new behaviour):
  *   - D3Q19 / D3Q27 runs: the reference compiles these templates but cannot reach them
  *     (src/lbm/solverExe.h:37-90); the dimension-generic source text above is followed literally.
@@ -50,7 +56,8 @@
 
 enum { ORC_BGK = 0, ORC_TRT = 1, ORC_MRT = 2 };
 enum { ORC_BC_BB = 1, ORC_BC_BB_TANGENTIAL = 2, ORC_BC_DIRICHLET_BB = 3, ORC_BC_PRESSURE = 4, ORC_BC_PERIODIC = 5,
-       ORC_BC_WALL_EQ = 6, ORC_BC_WALL_NEEM = 7, ORC_BC_WALL_NEBB = 8 };
+       ORC_BC_WALL_EQ = 6, ORC_BC_WALL_NEEM = 7, ORC_BC_WALL_NEBB = 8, ORC_BC_DIRICHLET_NEEM = 9, ORC_BC_NEUMANN_NEEM = 10 };
+enum { ORC_EQ_NAVIER_STOKES = 0, ORC_EQ_POISSON = 1 };
 
 static const double kEps = 2.220446049250313e-16; /* GDoubleEps, include/common/sfcmm_types.h:50 */
 
@@ -62,6 +69,7 @@ typedef struct {
   double c[ORC_MAXQ][ORC_MAXD];
   int    opp[ORC_MAXQ];
   double w[ORC_MAXQ];
+  double poisson_alpha, poisson_w[ORC_MAXQ]; /* CHAI08 eq. 2.3, constants.h:262-265,283-286,305-307 */
 } OrcLattice;
 
 /* src/lbm/constants.h:296-319 */
@@ -80,13 +88,36 @@ static int orc_lattice(OrcLattice* L, int ndim, int ndist) {
   memset(L, 0, sizeof(*L));
   L->ndim  = ndim;
   L->ndist = ndist;
+  if(ndim == 1 && ndist == 3) { /* constants.h:248-270 */
+    L->c[0][0] = -1; L->c[1][0] = 1; L->c[2][0] = 0;
+    L->opp[0] = 1; L->opp[1] = 0; L->opp[2] = 2;
+    L->w[0] = 1.0 / 6.0; L->w[1] = 1.0 / 6.0; L->w[2] = 2.0 / 3.0;
+    L->poisson_alpha = 1.0 / 3.0;
+    L->poisson_w[0] = 0.5; L->poisson_w[1] = 0.5; L->poisson_w[2] = 0;
+    return 0;
+  }
+  if(ndim == 2 && ndist == 5) { /* constants.h:272-292 */
+    static const int c5[5][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}, {0, 0}};
+    static const int o5[5]    = {1, 0, 3, 2, 4};
+    for(int i = 0; i < 5; ++i) {
+      L->c[i][0] = c5[i][0];
+      L->c[i][1] = c5[i][1];
+      L->opp[i]  = o5[i];
+      L->w[i]    = i < 4 ? 1.0 / 6.0 : 1.0 / 3.0;
+      L->poisson_w[i] = i < 4 ? 0.25 : 0.0;
+    }
+    L->poisson_alpha = 1.0 / 2.0;
+    return 0;
+  }
   if(ndim == 2 && ndist == 9) {
     for(int i = 0; i < 9; ++i) {
       L->c[i][0] = kD2Q9c[i][0];
       L->c[i][1] = kD2Q9c[i][1];
       L->opp[i]  = kD2Q9opp[i];
       L->w[i]    = i < 4 ? 1.0 / 9.0 : (i < 8 ? 1.0 / 36.0 : 4.0 / 9.0);
+      L->poisson_w[i] = i < 8 ? 1.0 / 8.0 : 0.0;
     }
+    L->poisson_alpha = 1.0 / 3.0;
     return 0;
   }
   if(ndim == 3 && (ndist == 19 || ndist == 27)) {
@@ -123,12 +154,18 @@ typedef struct {
   double*  lim_const;         /* n*ndist */
   int64_t* cell2bnd;          /* n: index used for entry k = LAST entry with the same cell (unordered_map, bnd_dirichlet.h:176-181) */
   int64_t* ext;               /* NEEM: extrapolation cell per entry, bnd_wall.h:212-246 */
+  /* Poisson: Dirichlet / Neumann NEEM, bnd_dirichlet.h:250-368, bnd_neumann.h:15-66 */
+  double*  values;            /* n: m_value[bndId][0] (Neumann: rewritten every step) */
+  int*     extdir;            /* n: direction from the boundary cell to its extrapolation cell */
+  double   grad;              /* m_gradValue */
 } OrcBc;
 
 typedef struct {
   OrcLattice L;
   int        nvar, stride, model, omp_collide;
   int        push_conflict; /* two cells push into one slot (multi-level grids with grid-level periodic links) */
+  int        equation;      /* ORC_EQ_* */
+  double     poisson_dt, poisson_rate; /* m_dt (solver.cpp:136) and poisson_D (solver.cpp:589-599) */
   int64_t    n;
   int64_t*   nghbr; /* n*stride push table, -1 = no neighbour (cartesiangrid.h:111-124) */
   double*    center; /* n*ndim or NULL */
@@ -425,6 +462,52 @@ int orc_add_bc_wall_wetnode(Orc* o, int kind, const int64_t* cells, const double
 }
 
 /* solver.cpp:640-647: inlet = surface cube_-x, outlet = cube_+x, p_out = 1.0, p_in = 1.0 + gradient */
+/* Poisson equation (solver.cpp EQ == LBEquationType::Poisson): one variable (the potential) instead of velocity + density.
+ * dt = m_dt (solver.cpp:100,136), rate = poisson_D (equation_th for "simple_diff_reaction", else the Debye-Hueckel constant 27.79,
+ * solver.cpp:589-599).  Call before adding boundary conditions. */
+void orc_set_poisson(Orc* o, double dt, double rate) {
+  o->equation     = ORC_EQ_POISSON;
+  o->poisson_dt   = dt;
+  o->poisson_rate = rate;
+  o->nvar         = 1;
+  free(o->vars);
+  free(o->varsold);
+  o->vars    = (double*)calloc((size_t)o->n, sizeof(double));
+  o->varsold = (double*)calloc((size_t)o->n, sizeof(double));
+}
+
+/* LBMBnd_DirichletNEEM / LBMBnd_NeumannNEEM constructor (bnd_dirichlet.h:265-332): per entry the value and the extrapolation cell
+ * = the neighbour opposite to the first missing axis neighbour, or the diagonal one at a 2D corner.  Returns -2 where the reference
+ * aborts ("No valid extrapolation cellId"). */
+int orc_add_bc_poisson_neem(Orc* o, int neumann, const int64_t* cells, const double* normals, int64_t n, const double* values, double grad) {
+  OrcBc* bc = new_bc(o, neumann ? ORC_BC_NEUMANN_NEEM : ORC_BC_DIRICHLET_NEEM, cells, normals, n);
+  const int D = o->L.ndim;
+  bc->values = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  bc->ext    = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+  bc->extdir = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  bc->grad   = grad;
+  static const int opp8[8] = {1, 0, 3, 2, 6, 7, 4, 5}; /* cartesian::oppositeDir incl. the 2D diagonals */
+  for(int64_t k = 0; k < n; ++k) {
+    bc->values[k] = values[k];
+    int ed = -1;
+    for(int dist = 0; dist < 2 * D; ++dist) {
+      if(o->nghbr[cells[k] * o->stride + dist] != -1) continue;
+      if(ed < 0) ed = dist;
+      else {
+        if(ed == 0 && dist == 2) ed = 6;
+        if(ed == 0 && dist == 3) ed = 7;
+        if(ed == 1 && dist == 3) ed = 4;
+        if(ed == 1 && dist == 2) ed = 5;
+      }
+    }
+    if(ed < 0) return -2;
+    bc->extdir[k] = D == 3 ? (ed ^ 1) : opp8[ed];
+    bc->ext[k]    = o->nghbr[cells[k] * o->stride + bc->extdir[k]];
+    if(bc->ext[k] < 0) return -2;
+  }
+  return 0;
+}
+
 int orc_set_forcing(Orc* o, const int64_t* inlet, int64_t ninlet, const int64_t* outlet, int64_t noutlet, double gradient) {
   if(o->center == NULL) return -1;
   o->forcing = 1;
@@ -453,6 +536,8 @@ void orc_destroy(Orc* o) {
     free(o->bc[i].lim_const);
     free(o->bc[i].cell2bnd);
     free(o->bc[i].ext);
+    free(o->bc[i].values);
+    free(o->bc[i].extdir);
   }
   free(o->periodic);
   free(o->bc);
@@ -476,6 +561,24 @@ void orc_init(Orc* o) {
   const int Q = L->ndist, NV = o->nvar, D = L->ndim;
   memset(o->vars, 0, sizeof(double) * (size_t)o->n * (size_t)NV);
   memset(o->varsold, 0, sizeof(double) * (size_t)o->n * (size_t)NV);
+  if(o->equation == ORC_EQ_POISSON) { /* solver.cpp:283-293; initCnd of the Dirichlet NEEM condition bnd_dirichlet.h:335-341 */
+    for(int b = 0; b < o->nbc; ++b) {
+      const OrcBc* bc = &o->bc[b];
+      if(bc->kind == ORC_BC_DIRICHLET_NEEM)
+        for(int64_t k = 0; k < bc->n; ++k) o->vars[bc->cells[k]] = bc->values[k];
+    }
+    for(int64_t c = 0; c < o->n; ++c) {
+      const double phi = o->vars[c];
+      for(int i = 0; i < Q - 1; ++i) {
+        const double v = L->w[i] * phi;
+        o->feq[c * Q + i] = o->f[c * Q + i] = o->fold[c * Q + i] = v;
+      }
+      const double v0 = (L->w[Q - 1] - 1.0) * phi;
+      o->feq[c * Q + Q - 1] = o->f[c * Q + Q - 1] = o->fold[c * Q + Q - 1] = v0;
+    }
+    o->step = 0;
+    return;
+  }
   for(int b = 0; b < o->nbc; ++b) {
     const OrcBc* bc = &o->bc[b];
     if(bc->kind == ORC_BC_DIRICHLET_BB) {
@@ -499,9 +602,21 @@ void orc_init(Orc* o) {
 /* ------------------------------------------------------------------------------------------------ passes */
 
 /* solver.cpp:513-553 */
+/* moments.h:83-91: potential = 1/(1 - w_rest) * sum of the moving populations, ascending from 0 */
+static inline double potential_of(const OrcLattice* L, const double* fo) {
+  double acc = 0;
+  for(int i = 0; i < L->ndist - 1; ++i) acc += fo[i];
+  return 1.0 / (1.0 - L->w[L->ndist - 1]) * acc;
+}
+
 static void pass_moments(Orc* o) {
   const OrcLattice* L = &o->L;
   const int Q = L->ndist, NV = o->nvar, D = L->ndim;
+  if(o->equation == ORC_EQ_POISSON) { /* solver.cpp:540-543 */
+#pragma omp parallel for schedule(static)
+    for(int64_t c = 0; c < o->n; ++c) o->vars[c] = potential_of(L, &o->fold[c * Q]);
+    return;
+  }
 #pragma omp parallel for schedule(static)
   for(int64_t c = 0; c < o->n; ++c) {
     const double* fo  = &o->fold[c * Q];
@@ -519,6 +634,14 @@ static void pass_moments(Orc* o) {
 /* solver.cpp:556-571 */
 static void pass_equilibrium(Orc* o) {
   const int Q = o->L.ndist, NV = o->nvar, D = o->L.ndim;
+  if(o->equation == ORC_EQ_POISSON) { /* equilibrium_func.h:149-163 */
+#pragma omp parallel for schedule(static)
+    for(int64_t c = 0; c < o->n; ++c) {
+      for(int i = 0; i < Q - 1; ++i) o->feq[c * Q + i] = o->L.w[i] * o->vars[c];
+      o->feq[c * Q + Q - 1] = (o->L.w[Q - 1] - 1.0) * o->vars[c];
+    }
+    return;
+  }
 #pragma omp parallel for schedule(static)
   for(int64_t c = 0; c < o->n; ++c) eq_all(&o->L, &o->feq[c * Q], o->vars[c * NV + D], &o->vars[c * NV]);
 }
@@ -530,6 +653,16 @@ static void collide_cell(const Orc* o, int64_t c) {
   double*           f = &o->f[c * Q];
   const double*     fo = &o->fold[c * Q];
   const double*     fe = &o->feq[c * Q];
+  if(o->equation == ORC_EQ_POISSON) { /* solver.cpp:601-612 */
+    const double relax_time  = 1.0 / o->omega; /* omega = 1.0 / m_relaxTime, solver.cpp:132-134 */
+    const double diffusivity = L->poisson_alpha * 1.0 * (0.5 - relax_time) * o->poisson_dt; /* gcem::pow(m_latticeVelocity = 1, 2) */
+    const double rhs         = o->poisson_rate * o->poisson_rate * o->vars[c];
+    for(int i = 0; i < Q; ++i) {
+      f[i] = (1 - o->omega) * fo[i] + o->omega * fe[i];
+      if(i != Q - 1) f[i] += o->poisson_dt * diffusivity * L->poisson_w[i] * rhs;
+    }
+    return;
+  }
   if(o->model == ORC_BGK) {
     for(int i = 0; i < Q; ++i) f[i] = (1 - o->omega) * fo[i] + o->omega * fe[i];
   } else {
@@ -827,6 +960,23 @@ static void pass_apply(Orc* o) {
         break;
       }
       case ORC_BC_WALL_NEBB: wall_nebb(o, bc); break;
+      case ORC_BC_NEUMANN_NEEM: /* bnd_neumann.h:47-60: the boundary value follows from the normal gradient, then Dirichlet */
+        for(int64_t k = 0; k < bc->n; ++k) {
+          const int64_t e  = bc->ext[k];
+          const int64_t e2 = o->nghbr[e * o->stride + bc->extdir[k]];
+          o->vars[e2]      = potential_of(L, &o->fold[e2 * Q]);
+          bc->values[k]    = (4.0 * o->vars[e] - o->vars[e2] + bc->grad) / 3.0;
+        }
+        /* fall through */
+      case ORC_BC_DIRICHLET_NEEM: /* bnd_dirichlet.h:347-365 */
+        for(int64_t k = 0; k < bc->n; ++k) o->vars[bc->ext[k]] = potential_of(L, &o->fold[bc->ext[k] * Q]);
+        for(int64_t k = 0; k < bc->n; ++k) {
+          const int64_t c = bc->cells[k], e = bc->ext[k];
+          o->vars[c] = bc->values[k];
+          for(int i = 0; i < Q - 1; ++i) o->fold[c * Q + i] = L->w[i] * bc->values[k] + o->fold[e * Q + i] - L->w[i] * o->vars[e];
+          o->fold[c * Q + Q - 1] = (L->w[Q - 1] - 1.0) * bc->values[k] + o->fold[e * Q + Q - 1] - (L->w[Q - 1] - 1.0) * o->vars[e];
+        }
+        break;
       default: break; /* periodic: apply is empty (bnd_periodic.h:208-209) */
     }
   }

@@ -40,6 +40,8 @@ def lib():
         L.orc_add_bc_periodic.argtypes = [vp, pi64, pdbl, i64, pi64, i64, dbl]
         L.orc_set_forcing.argtypes = [vp, pi64, i64, pi64, i64, dbl]
         L.orc_add_bc_wall_wetnode.argtypes = [vp, i32, pi64, pdbl, i64, i32, pdbl]
+        L.orc_set_poisson.argtypes = [vp, dbl, dbl]
+        L.orc_add_bc_poisson_neem.argtypes = [vp, i32, pi64, pdbl, i64, pdbl, dbl]
         L.orc_destroy.argtypes = [vp]
         L.orc_init.argtypes = [vp]
         L.orc_step.argtypes = [vp, i64]
@@ -118,6 +120,16 @@ class Oracle:
         if rc == -1:
             raise ValueError("Not implemented for this distribution!")
         if rc == -2:
+            raise ValueError("No valid extrapolation cellId")
+
+    def set_poisson(self, dt, rate):
+        """switch to the Poisson equation (one variable: the potential); call before adding boundary conditions"""
+        lib().orc_set_poisson(self._h, float(dt), float(rate))
+        self.nvar = 1
+
+    def add_poisson_neem(self, kind, cells, normals, values, grad=0.0):
+        rc = lib().orc_add_bc_poisson_neem(self._h, int(kind == "neumann"), _i64(cells), _f64(normals), len(cells), _f64(values), float(grad))
+        if rc != 0:
             raise ValueError("No valid extrapolation cellId")
 
     def set_forcing(self, inlet, outlet, gradient):

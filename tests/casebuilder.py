@@ -31,6 +31,8 @@ class CaseSpec:
     bcs: list = field(default_factory=list)
     forcing: dict = None
     golden: dict = None
+    equation: str = "navierstokes"
+    poisson: dict = None         # dt, rate (lbm_b200.cases.poisson_parameters)
 
     @property
     def n(self):
@@ -40,6 +42,8 @@ class CaseSpec:
         """Issue the set-up calls on `solver` (oracle.Oracle or lbm_b200.Solver: same method names)."""
         if self.center is not None:
             solver.set_geometry(self.center, self.bbmin, self.bbmax, self.cell_length)
+        if self.equation == "poisson":
+            solver.set_poisson(self.poisson["dt"], self.poisson["rate"])
         for bc in self.bcs:
             k = bc["kind"]
             if k == "wall_bb":
@@ -52,6 +56,8 @@ class CaseSpec:
                 solver.add_periodic(bc["cells"], bc["normals"], bc["connected"], bc["pressure"])
             elif k == "wall_wetnode":
                 solver.add_wall_wetnode(bc["model"], bc["cells"], bc["normals"], bc["velocity"])
+            elif k == "poisson_neem":
+                solver.add_poisson_neem("neumann" if bc["neumann"] else "dirichlet", bc["cells"], bc["normals"], bc["values"], bc["grad"])
             else:
                 raise ValueError(k)
         if self.forcing is not None:
@@ -90,7 +96,13 @@ def load_golden(name):
     l0 = float(np.max(hi - lo))
     spec = CaseSpec(name=name, ndim=ndim, ndist=ndist, nghbr=g["nghbr"].astype(np.int64), omega=float(g["omega"]),
                     center=g["center"], bbmin=lo, bbmax=hi, cell_length=float(g["cell_length"]), golden=g)
-    spec.bcs, spec.forcing = bcs_from_config(cfg["solver"], surfaces, ndim)
+    expr_values = {str(s): g[f"surf{k}_values"] for k, s in enumerate(g["surface_names"]) if f"surf{k}_values" in g}
+    spec.bcs, spec.forcing = bcs_from_config(cfg["solver"], surfaces, ndim, expr_values)
+    if cfg["solver"].get("equation", "navierstokes") == "poisson":
+        from lbm_b200.cases import poisson_parameters
+        spec.equation = "poisson"
+        dt, rate = poisson_parameters(cfg["solver"], spec.n, ndim)
+        spec.poisson = dict(dt=dt, rate=rate)
     spec.config = cfg
     spec.surfaces = surfaces
     spec.digests = json.loads(str(g["digests_json"]))

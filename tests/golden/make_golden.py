@@ -61,6 +61,14 @@ CASES = {
     # (boundary refinement next to a pressure surface is not a valid reference configuration: the refined layer is two cells wide, so
     # the second inward neighbour of LBMBnd_Pressure does not exist and the reference reads m_vars[-1], bnd_pressure.h:68-84)
     "sphere_ml_p4u6": ("sphere/sphere_ns.json", 50, [1, 50], True, {"partitionLevel": 4, "uniformLevel": 6, "maxRfnmtLvl": 6}),
+    # Poisson equation types: the five Poisson cases of the reference's test/run.sh.  D1Q3 / D2Q5 / D2Q9, one
+    # variable (the potential), Dirichlet / Neumann NEEM boundary conditions; poisson2D_helmholtz has expression-valued boundaries
+    # (exprtk in the reference): the evaluated per-entry numbers are read back from the reference's own m_vars after step 1
+    "poisson1D": ("poisson/poisson1D.json", 100, [1, 2, 10, 100], True),
+    "poisson1D_reaction": ("poisson/poisson1D_reaction.json", 100, [1, 2, 10, 100], True),
+    "poisson2D": ("poisson/poisson2D.json", 100, [1, 10, 100], False),
+    "poisson2D_helmholtz": ("poisson/poisson2D_helmholtz.json", 50, [1, 50], False),
+    "poissonD2Q9": ("poisson/poissonD2Q9.json", 100, [1, 10, 100], False),
     "step_ml_p3u5": ("step/step_ns.json", 50, [1, 50], True, {"partitionLevel": 3, "uniformLevel": 5, "maxRfnmtLvl": 5}),
 }
 
@@ -128,6 +136,16 @@ def run_case(name):
         for k, s in enumerate(surfaces):
             out[f"surf{k}_cells"] = np.array(s["cells"], dtype=np.int32)
             out[f"surf{k}_normals"] = np.array(s["normals"], dtype=np.float64).reshape(len(s["cells"]), ndim)
+        if cfg["solver"].get("equation", "navierstokes") == "poisson":
+            # per-entry boundary values: the constant of the configuration, or -- for math expressions -- what the reference's exprtk
+            # evaluation produced, which the Dirichlet condition writes into m_vars of its cells in every apply (bnd_dirichlet.h:352)
+            v1 = np.fromfile(os.path.join(d, f"vars_{steps[0]}.f64"), dtype=np.float64).reshape(n, nvar)[:, 0]
+            bnd = cfg["solver"]["boundary"]
+            confs = {(f"{gk}_{sk}" if len(bnd[gk]) > 1 else gk): bnd[gk][sk] for gk in bnd for sk in bnd[gk]}
+            for k, s in enumerate(surfaces):
+                val = confs[s["name"]].get("value", 0)
+                cells = np.array(s["cells"], dtype=np.int64)
+                out[f"surf{k}_values"] = v1[cells].copy() if isinstance(val, str) else np.full(len(cells), float(val))
         digests = {}
         for s in steps:
             for arr, width in (("fold", q), ("f", q), ("vars", nvar), ("varsold", nvar)):

@@ -16,7 +16,9 @@ CASES = ["couette", "couette_bnd", "couette_bnd_bbDirichlet", "poiseuille", "poi
          "poiseuille_bnd_eq", "poiseuille_bnd_NEEM", "poiseuille_bnd_NEBB", "poiseuille_bnd_pressure",
          "poiseuille_bnd_pressure_neem2",
          # multi-level grids: every level is stepped as its own lattice
-         "couette_ml_p3u5", "couette_ml_u5m6", "couette_ml_p4u5m7", "sphere_ml_p4u6", "step_ml_p3u5"]
+         "couette_ml_p3u5", "couette_ml_u5m6", "couette_ml_p4u5m7", "sphere_ml_p4u6", "step_ml_p3u5",
+         # Poisson equation types: the five Poisson cases of the reference's test/run.sh
+         "poisson1D", "poisson1D_reaction", "poisson2D", "poisson2D_helmholtz", "poissonD2Q9"]
 
 
 def sha(a):
@@ -41,7 +43,7 @@ def test_oracle_matches_reference_bit_for_bit(name, oracle_mod):
     o.close()
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", [c for c in CASES if not c.startswith("poisson")])
 def test_omega_from_config(name):
     """omega derivation, src/lbm/solver.cpp:108-123, against the value the reference printed."""
     spec = load_golden(name)
