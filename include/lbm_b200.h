@@ -53,8 +53,8 @@ enum { LBM_B200_STRICT = 0, LBM_B200_FAST = 1 };
 
 typedef struct {
   int32_t abi_version;  /* LBM_B200_ABI_VERSION */
-  int32_t ndim;         /* 2 or 3 */
-  int32_t ndist;        /* 9 (D2Q9), 19 (D3Q19), 27 (D3Q27) -- src/lbm/constants.h:145-162 */
+  int32_t ndim;         /* 2 or 3 (1 for the Poisson lattice D1Q3) */
+  int32_t ndist;        /* 9 (D2Q9), 19 (D3Q19), 27 (D3Q27) -- src/lbm/constants.h:145-162; 3 (D1Q3), 5 (D2Q5): Poisson equation only */
   int32_t precision;    /* LBM_B200_FP64 / LBM_B200_FP32 */
   int32_t collision;    /* LBM_B200_BGK / TRT / MRT */
   int32_t arithmetic;   /* LBM_B200_STRICT / LBM_B200_FAST */
@@ -99,6 +99,17 @@ int lbm_b200_add_dirichlet_bb(lbm_b200_solver* s, const int64_t* cells, const do
 enum { LBM_B200_WALL_EQUILIBRIUM = 0, LBM_B200_WALL_NEEM = 1, LBM_B200_WALL_NEBB = 2 };
 int lbm_b200_add_wall_wetnode(lbm_b200_solver* s, int32_t model, const int64_t* cells, const double* normals, int64_t n,
                               int32_t has_velocity, const double* velocity);
+/* Poisson equation types (solver.equation = "poisson": LBEquationType::Poisson, src/lbm/solver.cpp:283-293,540-543,562-566,589-612;
+ * lattices D1Q3 / D2Q5 / D2Q9).  One variable per cell, the potential: lbm_b200_get_vars / get_moments / residual then use
+ * NVAR = 1.  dt = m_dt (solver.cpp:100,136), rate = poisson_D (equation_th for "simple_diff_reaction", 27.79 otherwise, :589-599).
+ * Call before lbm_b200_init; the only boundary conditions of this equation are the two NEEM conditions below.  A solver in this mode
+ * runs the reference's passes in the reference's order on the GPU (lbm_b200/csrc/poisson.cuh); fp64, BGK, single GPU. */
+int lbm_b200_set_poisson(lbm_b200_solver* s, double dt, double rate);
+/* LBMBnd_DirichletNEEM (neumann == 0, src/lbm/bnd/bnd_dirichlet.h:250-368) / LBMBnd_NeumannNEEM (neumann != 0,
+ * src/lbm/bnd/bnd_neumann.h:15-66).  values[k] = m_value of entry k: the constant of the configuration, or the configuration's math
+ * expression evaluated at the cell centre by the caller (the reference uses exprtk, bnd_dirichlet.h:268-281); gradient = m_gradValue. */
+int lbm_b200_add_poisson_neem(lbm_b200_solver* s, int32_t neumann, const int64_t* cells, const double* normals, int64_t n,
+                              const double* values, double gradient);
 /* LBMBnd_Pressure, anti-bounce-back (src/lbm/bnd/bnd_pressure.h:12-113). */
 int lbm_b200_add_pressure(lbm_b200_solver* s, const int64_t* cells, const double* normals, int64_t n, double pressure);
 /* LBMBnd_Periodic (src/lbm/bnd/bnd_periodic.h:175-215); connected = cell list of the connected surface;

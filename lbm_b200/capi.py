@@ -95,6 +95,8 @@ def load_library():
     L.lbm_b200_add_wall_bb.argtypes = [vp, pi64, pdbl, i64, dbl]
     L.lbm_b200_add_dirichlet_bb.argtypes = [vp, pi64, pdbl, i64, pdbl]
     L.lbm_b200_add_pressure.argtypes = [vp, pi64, pdbl, i64, dbl]
+    L.lbm_b200_set_poisson.argtypes = [vp, dbl, dbl]
+    L.lbm_b200_add_poisson_neem.argtypes = [vp, i32, pi64, pdbl, i64, pdbl, dbl]
     L.lbm_b200_add_wall_wetnode.argtypes = [vp, i32, pi64, pdbl, i64, i32, pdbl]
     L.lbm_b200_add_periodic.argtypes = [vp, pi64, pdbl, i64, pi64, i64, dbl]
     L.lbm_b200_set_forcing.argtypes = [vp, pi64, i64, pi64, i64, dbl]
@@ -195,6 +197,15 @@ class Solver:
         v = _f64(np.zeros(self.ndim) if velocity is None else velocity)
         self._check(self._lib.lbm_b200_add_wall_wetnode(self._h, kind, _i64(cells), _f64(normals), len(cells),
                                                         int(velocity is not None), v))
+
+    def set_poisson(self, dt, rate):
+        """Poisson equation types: one variable per cell (the potential)."""
+        self._check(self._lib.lbm_b200_set_poisson(self._h, float(dt), float(rate)))
+        self.nvar = 1
+
+    def add_poisson_neem(self, kind, cells, normals, values, grad=0.0):
+        self._check(self._lib.lbm_b200_add_poisson_neem(self._h, int(kind == "neumann"), _i64(cells), _f64(normals), len(cells),
+                                                        _f64(values), float(grad)))
 
     def add_pressure(self, cells, normals, pressure):
         self._check(self._lib.lbm_b200_add_pressure(self._h, _i64(cells), _f64(normals), len(cells), float(pressure)))

@@ -99,6 +99,30 @@ inline LatticeRT make_rt() {
 }
 
 inline bool lattice_rt(int ndim, int ndist, LatticeRT* out) {
+  // D1Q3 / D2Q5: Poisson equation types only (src/lbm/constants.h:248-292); no chunk geometry, they run in poisson.cuh
+  if(ndim == 1 && ndist == 3) {
+    LatticeRT r;
+    r.D = 1; r.Q = 3;
+    r.c[0][0] = -1; r.c[1][0] = 1;
+    r.opp[0] = 1; r.opp[1] = 0; r.opp[2] = 2;
+    r.w[0] = 1.0 / 6.0; r.w[1] = 1.0 / 6.0; r.w[2] = 2.0 / 3.0;
+    *out = r;
+    return true;
+  }
+  if(ndim == 2 && ndist == 5) {
+    LatticeRT r;
+    r.D = 2; r.Q = 5;
+    const int c5[5][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}, {0, 0}};
+    const int o5[5]    = {1, 0, 3, 2, 4};
+    for(int i = 0; i < 5; ++i) {
+      r.c[i][0] = c5[i][0];
+      r.c[i][1] = c5[i][1];
+      r.opp[i]  = o5[i];
+      r.w[i]    = i < 4 ? 1.0 / 6.0 : 1.0 / 3.0;
+    }
+    *out = r;
+    return true;
+  }
   if(ndim == 2 && ndist == 9) { *out = make_rt<Lattice<2, 9>>(); return true; }
   if(ndim == 3 && ndist == 19) { *out = make_rt<Lattice<3, 19>>(); return true; }
   if(ndim == 3 && ndist == 27) { *out = make_rt<Lattice<3, 27>>(); return true; }

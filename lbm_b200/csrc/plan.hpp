@@ -34,7 +34,8 @@ namespace lbm {
 static constexpr double kEps = std::numeric_limits<double>::epsilon(); // GDoubleEps, include/common/sfcmm_types.h:50
 
 enum BcKind { BC_WALL_BB = 1, BC_WALL_BB_TANGENTIAL = 2, BC_DIRICHLET_BB = 3, BC_PRESSURE = 4, BC_PERIODIC = 5,
-              BC_WALL_EQ = 6, BC_WALL_NEEM = 7, BC_WALL_NEBB = 8 }; // 6..8: wet-node walls, handled by sequential.cuh
+              BC_WALL_EQ = 6, BC_WALL_NEEM = 7, BC_WALL_NEBB = 8, // 6..8: wet-node walls, handled by sequential.cuh
+              BC_POISSON_DIRICHLET = 9, BC_POISSON_NEUMANN = 10 }; // Poisson equation types, handled by poisson.cuh
 
 struct BcInput {
   int                  kind = 0;
@@ -45,6 +46,8 @@ struct BcInput {
   double               pressure   = std::numeric_limits<double>::quiet_NaN();
   std::vector<int64_t> connected; // periodic
   bool                 has_velocity = false; // wet-node walls: the "velocity" key is present (value[] holds it)
+  std::vector<double>  values;               // Poisson NEEM conditions: m_value per entry
+  double               grad = 0;             // Neumann: m_gradValue
 };
 
 struct PlanInput {
@@ -57,6 +60,11 @@ struct PlanInput {
   bool                 forcing = false;
   std::vector<int64_t> inlet, outlet;
   double               gradient = 0;
+  // Poisson equation types (solver.cpp EQ == LBEquationType::Poisson): m_dt and poisson_D
+  bool                 poisson = false;
+  double               poisson_dt = 0, poisson_rate = 0;
+  std::vector<int32_t> nghbr_wide;      // D2Q5 only: all 8 columns of the caller's 2D table -- the NEEM conditions extrapolate
+                                        // along a DIAGONAL at corners (bnd_dirichlet.h:294-312), which the lattice itself lacks
   // multi-GPU: the last n_ghost cells of the list are copies of cells owned by other ranks (never updated here, their
   // populations arrive by halo exchange); halo lists are (local cell, direction) pairs per peer, already in wire order
   int64_t              n_ghost = 0;
@@ -260,7 +268,8 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
   }
 
   for(const BcInput& bc : in.bcs)
-    if(bc.kind >= BC_WALL_EQ) { P.error = "internal: wet-node walls are handled by the sequential path"; return false; }
+    if(bc.kind >= BC_WALL_EQ) { P.error = "internal: wet-node walls and Poisson conditions are handled by the sequential paths"; return false; }
+  if(in.poisson) { P.error = "internal: the Poisson equation has no fused device plan"; return false; }
   // ---- 2. boundary conditions, in the reference's order: preApply writes, then the push, then apply writes
   std::unordered_map<int64_t, SlotDesc> over;  // slot key c*Q+j -> final descriptor
   auto key = [&](int64_t c, int j) { return c * Q + j; };

@@ -16,6 +16,7 @@
 #include "grid_box.hpp"
 #include "nccl_dyn.hpp"
 #include "sequential.cuh"
+#include "poisson.cuh"
 
 namespace {
 
@@ -1131,6 +1132,255 @@ struct SequentialSolver final : SolverBase {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Poisson equation types (poisson.cuh) behind the same SolverBase interface: one variable per cell, the reference's passes in
+// the reference's order, Dirichlet / Neumann NEEM conditions as phase kernels in LBMBndManager order.
+struct PoissonSolver final : SolverBase {
+  lbm::poisson::Lat lat{};
+  DevBuf<double>  d_f, d_fold, d_feq, d_vars, d_varsold, d_scratch, d_partial;
+  DevBuf<int32_t> d_pull;
+  DevBuf<int64_t> d_nghbr;
+  std::vector<lbm::poisson::Bc> bcs;
+  std::vector<std::unique_ptr<DevBuf<int64_t>>> keep_i64;
+  std::vector<std::unique_ptr<DevBuf<double>>>  keep_f64;
+  int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+
+  lbm::poisson::State state() const {
+    lbm::poisson::State s{};
+    s.f = d_f.p; s.fold = d_fold.p; s.feq = d_feq.p; s.vars = d_vars.p; s.varsold = d_varsold.p;
+    s.pull = d_pull.p; s.nghbr = d_nghbr.p; s.n = in.n;
+    s.omega = cfg.omega;
+    s.om1   = 1 - cfg.omega;
+    // solver.cpp:606: diffusivity = m_poissonAlpha * pow(m_latticeVelocity = 1, 2) * (0.5 - m_relaxTime) * m_dt, m_relaxTime = 1 / omega
+    const double alpha       = (in.L.D == 2 && in.L.Q == 5) ? 1.0 / 2.0 : 1.0 / 3.0;
+    const double relax_time  = 1.0 / cfg.omega;
+    const double diffusivity = alpha * 1.0 * (0.5 - relax_time) * in.poisson_dt;
+    s.dt_diff = in.poisson_dt * diffusivity;
+    s.rate2   = in.poisson_rate * in.poisson_rate;
+    return s;
+  }
+  static int blocks(int64_t n) { return static_cast<int>((n + 127) / 128); }
+
+  template <class T, class Keep>
+  T* up(Keep& keep, const std::vector<T>& h, cudaError_t* err) {
+    keep.emplace_back(new DevBuf<T>());
+    std::vector<T> tmp = h;
+    if(tmp.empty()) tmp.resize(1);
+    cudaError_t e = keep.back()->upload(tmp);
+    if(e != cudaSuccess) *err = e;
+    return keep.back()->p;
+  }
+
+  int init() override {
+    const lbm::LatticeRT& LR = in.L;
+    const int     Q = LR.Q, QM = Q - 1, D = LR.D;
+    const int64_t N = in.n;
+    if(!((D == 1 && Q == 3) || (D == 2 && Q == 5) || (D == 2 && Q == 9)))
+      return fail(LBM_B200_EINVAL, "Unsupported model"); // m_canPoisson / solverExe.h:37-90
+    if(cfg.precision != LBM_B200_FP64) return fail(LBM_B200_EUNSUP, "the Poisson equation types run in fp64 only");
+    if(cfg.collision != LBM_B200_BGK) return fail(LBM_B200_EINVAL, "Invalid equation configuration!");
+    if(!in.peers.empty() || in.n_ghost > 0) return fail(LBM_B200_EUNSUP, "the Poisson equation types are not partitioned");
+    if(in.forcing) return fail(LBM_B200_EINVAL, "forcing is a Navier-Stokes feature");
+    if(in.nghbr.empty()) return fail(LBM_B200_ESTATE, "no topology set");
+    CUDA_TRY(cudaSetDevice(cfg.device));
+    lat.D = D;
+    lat.Q = Q;
+    for(int i = 0; i < Q; ++i) {
+      lat.w[i]  = LR.w[i];
+      lat.pw[i] = i == QM ? 0.0 : (Q == 3 ? 0.5 : (Q == 5 ? 0.25 : 1.0 / 8.0)); // constants.h:265,286,306
+    }
+    lat.inv_1mw = 1.0 / (1.0 - LR.w[QM]);
+    // neighbour in any of the grid's directions: the lattice's own columns, or (D2Q5 corners) the grid table's diagonal columns
+    const int NW = in.nghbr_wide.empty() ? QM : 8;
+    auto NB = [&](int64_t c, int j) -> int64_t {
+      if(j < QM) return in.nghbr[static_cast<size_t>(c) * QM + j];
+      return j < NW ? in.nghbr_wide[static_cast<size_t>(c) * 8 + j] : -1;
+    };
+    std::vector<int32_t> pull(static_cast<size_t>(N) * QM, -1);
+    for(int64_t c = 0; c < N; ++c)
+      for(int j = 0; j < QM; ++j) {
+        const int64_t t = NB(c, j);
+        if(t >= 0) pull[static_cast<size_t>(t) * QM + j] = static_cast<int32_t>(c);
+      }
+    std::vector<int64_t> nb64(in.nghbr.begin(), in.nghbr.end());
+    CUDA_TRY(d_pull.upload(pull));
+    CUDA_TRY(d_nghbr.upload(nb64));
+    const size_t nq = static_cast<size_t>(N) * Q;
+    CUDA_TRY(d_f.alloc(nq)); CUDA_TRY(d_fold.alloc(nq)); CUDA_TRY(d_feq.alloc(nq));
+    CUDA_TRY(d_vars.alloc(N)); CUDA_TRY(d_varsold.alloc(N)); CUDA_TRY(d_scratch.alloc(N));
+    CUDA_TRY(d_partial.alloc(64));
+    CUDA_TRY(cudaMemset(d_varsold.p, 0, d_varsold.bytes()));
+    std::vector<double> vars0(static_cast<size_t>(N), 0.0);
+    cudaError_t cerr = cudaSuccess;
+    static const int opp8[8] = {1, 0, 3, 2, 6, 7, 4, 5}; // cartesian::oppositeDir incl. the 2D diagonals
+    for(const lbm::BcInput& bc : in.bcs) {
+      if(bc.kind != lbm::BC_POISSON_DIRICHLET && bc.kind != lbm::BC_POISSON_NEUMANN)
+        return fail(LBM_B200_EINVAL, "this boundary condition does not exist for the Poisson equation types");
+      const int64_t n = static_cast<int64_t>(bc.cells.size());
+      std::vector<int64_t> ext(static_cast<size_t>(n)), ext2(static_cast<size_t>(n), -1);
+      std::vector<char>    is_cell(static_cast<size_t>(N), 0), is_ext(static_cast<size_t>(N), 0);
+      for(int64_t k = 0; k < n; ++k) {
+        // LBMBnd_DirichletNEEM constructor, bnd_dirichlet.h:287-317: opposite of the first missing axis neighbour, the diagonal
+        // neighbour at a 2D corner
+        const int64_t c = bc.cells[k];
+        int ed = -1;
+        for(int dist = 0; dist < 2 * D; ++dist) {
+          if(NB(c, dist) != -1) continue;
+          if(ed < 0) ed = dist;
+          else {
+            if(ed == 0 && dist == 2) ed = 6;
+            if(ed == 0 && dist == 3) ed = 7;
+            if(ed == 1 && dist == 3) ed = 4;
+            if(ed == 1 && dist == 2) ed = 5;
+          }
+        }
+        if(ed < 0) return fail(LBM_B200_EINVAL, "No valid extrapolation cellId");
+        const int edir = opp8[ed];
+        if(edir >= NW) return fail(LBM_B200_EINVAL, "No valid extrapolation cellId (corner: pass the grid's 8-column table, stride >= 8)");
+        ext[k] = NB(c, edir);
+        if(ext[k] < 0) return fail(LBM_B200_EINVAL, "No valid extrapolation cellId");
+        if(bc.kind == lbm::BC_POISSON_NEUMANN) {
+          ext2[k] = NB(ext[k], edir);
+          if(ext2[k] < 0) return fail(LBM_B200_EINVAL, "Neumann boundary: no second extrapolation cell");
+        }
+        if(is_cell[c]) return fail(LBM_B200_EUNSUP, "Poisson boundary: a cell is listed twice in one surface (order-dependent in the reference)");
+        is_cell[c] = 1;
+        is_ext[ext[k]] = 1;
+      }
+      for(int64_t k = 0; k < n; ++k) {
+        if(is_cell[ext[k]]) return fail(LBM_B200_EUNSUP, "Poisson boundary: extrapolation cell lies on the same surface (order-dependent in the reference)");
+        if(bc.kind == lbm::BC_POISSON_NEUMANN && is_ext[ext2[k]])
+          return fail(LBM_B200_EUNSUP, "Neumann boundary: a second extrapolation cell is another entry's first one (order-dependent in the reference)");
+      }
+      lbm::poisson::Bc b{};
+      b.neumann = bc.kind == lbm::BC_POISSON_NEUMANN;
+      b.n = n;
+      b.cells = up<int64_t>(keep_i64, bc.cells, &cerr);
+      b.ext = up<int64_t>(keep_i64, ext, &cerr);
+      b.ext2 = up<int64_t>(keep_i64, ext2, &cerr);
+      b.values = up<double>(keep_f64, bc.values, &cerr);
+      b.grad = bc.grad;
+      bcs.push_back(b);
+      if(bc.kind == lbm::BC_POISSON_DIRICHLET) // initCnd, bnd_dirichlet.h:335-341 (the Neumann condition has none, bnd_neumann.h:41)
+        for(int64_t k = 0; k < n; ++k) vars0[bc.cells[k]] = bc.values[k];
+    }
+    if(cerr != cudaSuccess) return fail(LBM_B200_ECUDA, cudaGetErrorString(cerr));
+    CUDA_TRY(cudaMemcpy(d_vars.p, vars0.data(), vars0.size() * sizeof(double), cudaMemcpyHostToDevice));
+    lbm::poisson::k_init<<<blocks(N), 128, 0, stream>>>(state(), lat);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    std::vector<int32_t>().swap(in.nghbr);
+    t = 0;
+    inited = true;
+    return LBM_B200_OK;
+  }
+
+  int step(int64_t n, float* ms_total, float* ms_main) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "lbm_b200_step before lbm_b200_init");
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if(ms_total != nullptr) {
+      CUDA_TRY(cudaEventCreate(&e0));
+      CUDA_TRY(cudaEventCreate(&e1));
+      CUDA_TRY(cudaEventRecord(e0, stream));
+    }
+    const lbm::poisson::State s = state();
+    for(int64_t it = 0; it < n; ++it) {
+      CUDA_TRY(cudaMemcpyAsync(d_varsold.p, d_vars.p, d_vars.bytes(), cudaMemcpyDeviceToDevice, stream)); // currToOldVars
+      lbm::poisson::k_cell<<<blocks(s.n), 128, 0, stream>>>(s, lat);
+      lbm::poisson::k_stream<<<blocks(s.n), 128, 0, stream>>>(s, lat);
+      launches += 2;
+      for(const auto& b : bcs) {
+        if(b.n == 0) continue;
+        if(b.neumann) {
+          lbm::poisson::k_neumann_value<<<blocks(b.n), 128, 0, stream>>>(s, lat, b);
+          ++launches;
+        }
+        lbm::poisson::k_ext_potential<<<blocks(b.n), 128, 0, stream>>>(s, lat, b);
+        lbm::poisson::k_dirichlet<<<blocks(b.n), 128, 0, stream>>>(s, lat, b);
+        launches += 2;
+      }
+      ++t;
+    }
+    CUDA_TRY(cudaGetLastError());
+    if(ms_total != nullptr) {
+      CUDA_TRY(cudaEventRecord(e1, stream));
+      CUDA_TRY(cudaEventSynchronize(e1));
+      CUDA_TRY(cudaEventElapsedTime(ms_total, e0, e1));
+      if(ms_main) *ms_main = *ms_total;
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
+    return LBM_B200_OK;
+  }
+
+  int sync() override {
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return LBM_B200_OK;
+  }
+  int d2h(const double* src, double* dst, size_t count) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    d2h_bytes += static_cast<int64_t>(count * sizeof(double));
+    return LBM_B200_OK;
+  }
+  int get_populations(double* fo, double* foldo) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
+    const size_t nq = static_cast<size_t>(in.n) * in.L.Q;
+    if(fo != nullptr) { int rc = d2h(d_f.p, fo, nq); if(rc) return rc; }
+    if(foldo != nullptr) { int rc = d2h(d_fold.p, foldo, nq); if(rc) return rc; }
+    return LBM_B200_OK;
+  }
+  int set_populations(const double* fi, const double* foldi) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
+    if(foldi == nullptr) return fail(LBM_B200_EINVAL, "set_populations needs m_fold");
+    const size_t nq = static_cast<size_t>(in.n) * in.L.Q;
+    if(fi != nullptr) CUDA_TRY(cudaMemcpyAsync(d_f.p, fi, nq * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(d_fold.p, foldi, nq * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    h2d_bytes += static_cast<int64_t>((fi != nullptr ? 2 : 1) * nq * sizeof(double));
+    return LBM_B200_OK;
+  }
+  int get_vars(double* v, double* vo) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
+    if(v != nullptr) { int rc = d2h(d_vars.p, v, static_cast<size_t>(in.n)); if(rc) return rc; }
+    if(vo != nullptr) { int rc = d2h(d_varsold.p, vo, static_cast<size_t>(in.n)); if(rc) return rc; }
+    return LBM_B200_OK;
+  }
+  int get_moments(double* m) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
+    lbm::poisson::k_potential<<<blocks(in.n), 128, 0, stream>>>(state(), lat, d_scratch.p);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    return d2h(d_scratch.p, m, static_cast<size_t>(in.n));
+  }
+  int residual(double* out, int32_t* diverged) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
+    const int nb = 64;
+    lbm::poisson::k_residual<<<nb, 256, 0, stream>>>(d_vars.p, d_varsold.p, in.n, d_partial.p);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    double h[64];
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaMemcpy(h, d_partial.p, sizeof(h), cudaMemcpyDeviceToHost));
+    double sum = 0;
+    for(int b = 0; b < nb; ++b) sum += h[b];
+    out[0] = sum;
+    if(diverged) *diverged = (std::isnan(sum) || std::isinf(sum)) ? 1 : 0;
+    return LBM_B200_OK;
+  }
+  int64_t owned() const override { return in.n; }
+  void stats(lbm_b200_stats* st) const override {
+    std::memset(st, 0, sizeof(*st));
+    st->ncells = in.n;
+    st->cells_generic = in.n;
+    st->device_bytes = static_cast<int64_t>(d_f.bytes() * 3 + d_vars.bytes() * 3);
+    st->launches = launches;
+    st->bytes_per_cell_alg = 2.0 * in.L.Q * sizeof(double);
+    st->h2d_bytes = h2d_bytes;
+    st->d2h_bytes = d2h_bytes;
+  }
+};
+
 SolverBase* make_sequential(const lbm_b200_config& c) {
   if(c.ndim == 2 && c.ndist == 9) return new SequentialSolver<lbm::Lattice<2, 9>>();
   if(c.ndim == 3 && c.ndist == 19) return new SequentialSolver<lbm::Lattice<3, 19>>();
@@ -1140,6 +1390,7 @@ SolverBase* make_sequential(const lbm_b200_config& c) {
 
 SolverBase* make_solver(const lbm_b200_config& c) {
   const bool dbl = c.precision == LBM_B200_FP64;
+  if((c.ndim == 1 && c.ndist == 3) || (c.ndim == 2 && c.ndist == 5)) return new PoissonSolver(); // Poisson-only lattices
 #ifdef LBM_EXPERIMENT_D3Q19_F64
   // tuning builds: one instantiation only, to keep compile times short
   if(c.ndim == 3 && c.ndist == 19 && dbl) return new Solver<lbm::Lattice<3, 19>, double>();
@@ -1237,6 +1488,16 @@ int lbm_b200_set_topology(lbm_b200_solver* s, const int64_t* nghbr, int32_t stri
     std::vector<int32_t>().swap(in.nghbr);
     return fail(LBM_B200_EINVAL, "neighbour id out of range");
   }
+  in.nghbr_wide.clear();
+  if(in.L.D == 2 && in.L.Q == 5 && stride >= 8) {
+    in.nghbr_wide.resize(static_cast<size_t>(N) * 8);
+    for(int64_t c = 0; c < N; ++c)
+      for(int j = 0; j < 8; ++j) {
+        const int64_t t = nghbr[c * stride + j];
+        if(t < -1 || t >= N) return fail(LBM_B200_EINVAL, "neighbour id out of range");
+        in.nghbr_wide[static_cast<size_t>(c) * 8 + j] = static_cast<int32_t>(t);
+      }
+  }
   return LBM_B200_OK;
 }
 
@@ -1293,6 +1554,29 @@ int lbm_b200_add_wall_wetnode(lbm_b200_solver* s, int32_t model, const int64_t* 
   bc.kind = model == LBM_B200_WALL_EQUILIBRIUM ? lbm::BC_WALL_EQ : (model == LBM_B200_WALL_NEEM ? lbm::BC_WALL_NEEM : lbm::BC_WALL_NEBB);
   bc.has_velocity = has_velocity != 0;
   for(int d = 0; d < s->impl->in.L.D; ++d) bc.value[d] = has_velocity ? velocity[d] : 0.0;
+  return add_bc(s, bc, cells, normals, n);
+}
+
+int lbm_b200_set_poisson(lbm_b200_solver* s, double dt, double rate) {
+  CHECK_HANDLE(s);
+  CHECK_NOT_INITED(s);
+  if(!(dt > 0.0) || std::isnan(rate)) return fail(LBM_B200_EINVAL, "bad Poisson parameters");
+  auto& in = s->impl->in;
+  if(!((in.L.D == 1 && in.L.Q == 3) || (in.L.D == 2 && (in.L.Q == 5 || in.L.Q == 9)))) return fail(LBM_B200_EINVAL, "Unsupported model");
+  in.poisson      = true;
+  in.poisson_dt   = dt;
+  in.poisson_rate = rate;
+  return LBM_B200_OK;
+}
+
+int lbm_b200_add_poisson_neem(lbm_b200_solver* s, int32_t neumann, const int64_t* cells, const double* normals, int64_t n,
+                              const double* values, double gradient) {
+  CHECK_HANDLE(s);
+  if(n > 0 && values == nullptr) return fail(LBM_B200_EINVAL, "null values");
+  lbm::BcInput bc;
+  bc.kind = neumann ? lbm::BC_POISSON_NEUMANN : lbm::BC_POISSON_DIRICHLET;
+  bc.grad = gradient;
+  if(n > 0) bc.values.assign(values, values + n);
   return add_bc(s, bc, cells, normals, n);
 }
 
@@ -1430,8 +1714,24 @@ int lbm_b200_init(lbm_b200_solver* s) {
   CHECK_NOT_INITED(s);
   if(s->impl->in.nghbr.empty()) return fail(LBM_B200_ESTATE, "lbm_b200_set_topology has not been called");
   if(s->impl->cfg.device < 0) return fail(LBM_B200_ECUDA, "inspection-only handle (device -1): there is no CPU compute path");
-  bool wet = false;
-  for(const lbm::BcInput& bc : s->impl->in.bcs) wet = wet || bc.kind >= lbm::BC_WALL_EQ;
+  bool wet = false, poisson_bc = false;
+  for(const lbm::BcInput& bc : s->impl->in.bcs) {
+    if(bc.kind >= lbm::BC_POISSON_DIRICHLET) poisson_bc = true;
+    else wet = wet || bc.kind >= lbm::BC_WALL_EQ;
+  }
+  const bool poisson_lattice = s->impl->in.L.Q == 3 || s->impl->in.L.Q == 5;
+  if(s->impl->in.poisson || poisson_lattice || poisson_bc) {
+    if(!s->impl->in.poisson) return fail(LBM_B200_ESTATE, "D1Q3 / D2Q5 and the NEEM Dirichlet / Neumann conditions belong to the Poisson equation: call lbm_b200_set_poisson");
+    if(wet) return fail(LBM_B200_EINVAL, "wall boundary conditions do not exist for the Poisson equation types");
+    if(dynamic_cast<PoissonSolver*>(s->impl.get()) == nullptr) {
+      SolverBase* q = new PoissonSolver();
+      q->cfg    = s->impl->cfg;
+      q->in     = std::move(s->impl->in);
+      q->stream = s->impl->stream;
+      s->impl.reset(q);
+    }
+    return s->impl->init();
+  }
   if(wet) {
     // order-dependent boundary conditions: hand the same inputs to the reference-order pipeline (sequential.cuh)
     SolverBase* q = make_sequential(s->impl->cfg);
@@ -1524,6 +1824,7 @@ int lbm_b200_box_topology(int32_t ndim, const int64_t* shape, const int32_t* per
 int lbm_b200_debug_plan(lbm_b200_solver* s, lbm_b200_plan_view* out) {
   CHECK_HANDLE(s);
   if(out == nullptr) return fail(LBM_B200_EINVAL, "null argument");
+  if(s->impl->in.poisson || s->impl->in.L.Q < 9) return fail(LBM_B200_EUNSUP, "the Poisson equation types have no fused device plan");
   for(const lbm::BcInput& bc : s->impl->in.bcs)
     if(bc.kind >= lbm::BC_WALL_EQ) return fail(LBM_B200_EUNSUP, "configurations with wet-node walls have no fused device plan");
   return s->impl->debug_plan(out);

@@ -150,3 +150,22 @@ def test_sfc_index_argument_checks():
     assert lib.lbm_b200_sfc_index(5, x, 2) == -1
     shape = np.array([4, 0], dtype=np.int64)
     assert lib.lbm_b200_box_ncells(2, shape) == -1
+
+
+def test_poisson_entry_points_check_their_arguments():
+    """Poisson equation types (lbm_b200_set_poisson / lbm_b200_add_poisson_neem): lattice and argument checks, no fused plan"""
+    g1 = np.array([[-1, 1], [0, 2], [1, 3], [2, -1]], dtype=np.int64)  # a 1D line of four cells
+    s = lbm_b200.Solver(1, 3, g1, 1.0, device=-1)
+    s.set_poisson(0.25, 27.79)
+    assert s.nvar == 1
+    s.add_poisson_neem("dirichlet", [0], np.array([[-1.0]]), [1.0])
+    s.add_poisson_neem("neumann", [3], np.array([[1.0]]), [0.0])
+    c, msg = code_of(s.debug_plan)
+    assert c == -5 and "Poisson" in msg
+    c, msg = code_of(s.set_poisson, 0.0, 1.0)
+    assert c == -1
+    s3, _ = make(ndim=3, ndist=19, shape=(4, 4, 4), periodic=(True, True, True))
+    c, msg = code_of(s3.set_poisson, 0.1, 1.0)
+    assert c == -1 and "Unsupported model" in msg   # m_canPoisson, constants.h
+    c, msg = code_of(lbm_b200.Solver, 1, 5, g1, 1.0, device=-1)
+    assert c == -1 and "Unsupported model" in msg
