@@ -204,11 +204,23 @@ def ncu_traffic(lattice, size):
     return None
 
 
-def cpu_sample(lattice, sample_size, budget_s, omp_collide=False):
+def collision_setup(name):
+    """(C ABI collision id, omega_minus, per-pair MRT rates) of a workload's collision operator.  TRT: odd-moment rate from the
+    'magic' parameter 3/16; MRT: per-direction-pair rates, even part relaxed with omega, odd part with the TRT rate."""
+    from lbm_b200.cases import trt_omega_minus
+    om_minus = trt_omega_minus(OMEGA)
+    rates = np.array([OMEGA if i % 2 == 0 else om_minus for i in range(27)])
+    return {"bgk": 0, "trt": 1, "mrt": 2}[name], om_minus, rates
+
+
+def cpu_sample(lattice, sample_size, budget_s, omp_collide=False, workload_name="box"):
     """Time the CPU restatement of the reference step (oracle port) on a bounded sample of the same workload."""
     from oracle import oracle
-    wl = workload(sample_size, lattice)
+    wl = workload(sample_size, lattice) if workload_name == "box" else case_workload(workload_name, sample_size)
     o = oracle.Oracle(wl["ndim"], wl["ndist"], wl["nghbr"], OMEGA)
+    if workload_name != "box":
+        coll, om_minus, rates = collision_setup(wl["collision"])
+        o.set_collision(coll, om_minus, rates)
     apply_bcs(o, wl)
     o.set_omp_collide(omp_collide)
     o.init()
@@ -271,9 +283,18 @@ def run_reference(args):
         return
     from oracle import oracle
     oracle.build()
-    sample = args.cpu_size
-    wl = workload(sample, args.lattice)
+    if args.workload == "box":
+        sample = args.cpu_size
+        wl = workload(sample, args.lattice)
+        args.collision = "bgk"
+    else:
+        sample = min(args.cpu_size, 64, args.size)
+        wl = case_workload(args.workload, sample)
+        args.lattice, args.collision = wl["lattice"], wl["collision"]
     o = oracle.Oracle(wl["ndim"], wl["ndist"], wl["nghbr"], OMEGA)
+    if args.workload != "box":
+        coll, om_minus, rates = collision_setup(args.collision)
+        o.set_collision(coll, om_minus, rates)
     apply_bcs(o, wl)
     o.init()
     o.step(args.warmup)
@@ -289,11 +310,11 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(args, "CPU port of the reference time step (oracle/lbm_oracle.c), OpenMP like the reference"),
         "cpu_baseline": {"value": mlups, "unit": unit, "cores": oracle.threads(), "kind": "port",
-                         "sample": f"{args.lattice} {sample}^{wl['ndim']} box ({n} cells), same BCs/omega as the workload, "
+                         "sample": f"{args.lattice} {sample}^{wl['ndim']} {args.workload} ({n} cells), same BCs/omega/collision as the workload, "
                                    f"{args.steps} steps; the reference binary cannot run D3Q19 (SURVEY section 0)"},
         "e2e": {"value": mlups, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    line["cpu_baseline"]["reference_binary_d2q9"] = reference_binary_d2q9()
+    line["cpu_baseline"]["reference_binary_d2q9"] = reference_binary_d2q9() if args.workload == "box" else None
     emit(line)
 
 
@@ -339,11 +360,7 @@ def run_ours(args):
     n = wl["n_owned"]
     n_local = wl["nghbr"].shape[0]
     stream = torch.cuda.current_stream().cuda_stream
-    from lbm_b200.cases import trt_omega_minus
-    coll = {"bgk": lbm_b200.BGK, "trt": lbm_b200.TRT, "mrt": lbm_b200.MRT}[args.collision]
-    om_minus = trt_omega_minus(OMEGA)
-    # MRT: per-direction-pair rates; even part relaxed with omega, odd part with the TRT 'magic' rate
-    rates = np.array([OMEGA if i % 2 == 0 else om_minus for i in range(27)])
+    coll, om_minus, rates = collision_setup(args.collision)
     s = lbm_b200.Solver(ndim, ndist, wl["nghbr"], OMEGA, arithmetic=arithmetic, device=local, track_vars=0, stream=stream,
                         collision=coll, omega_minus=om_minus, mrt_rates=rates)
     apply_bcs(s, wl)
@@ -425,14 +442,15 @@ def run_ours(args):
             "kernel": f"lbm::k_step (fused pull-stream + BC + moments + {args.collision.upper()} collide)",
             "bytes_per_cell_alg": b_alg, "cells_per_launch": n, "ms_per_launch": ms_main / args.steps}
     cpu = None
-    if world == 1 and not args.no_cpu and args.workload == "box":
+    if world == 1 and not args.no_cpu:
         from oracle import oracle
         oracle.build()
-        v, steps, nc, cores = cpu_sample(args.lattice, args.cpu_size, args.cpu_budget)
+        csize = args.cpu_size if args.workload == "box" else min(args.cpu_size, 64, args.size)
+        v, steps, nc, cores = cpu_sample(args.lattice, csize, args.cpu_budget, workload_name=args.workload)
         cpu = {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port",
-               "sample": f"{args.lattice} {args.cpu_size}^{ndim} box ({nc} cells), same BCs/omega, {steps} steps of oracle/lbm_oracle.c "
+               "sample": f"{args.lattice} {csize}^{ndim} {args.workload} ({nc} cells), same BCs/omega/collision, {steps} steps of oracle/lbm_oracle.c "
                          f"(reference algorithm; serial collision pass like src/lbm/solver.cpp:601)",
-               "reference_binary_d2q9": reference_binary_d2q9()}
+               "reference_binary_d2q9": reference_binary_d2q9() if args.workload == "box" else None}
     line = {
         "metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak" if args.workload == "box" else "strong",
