@@ -46,7 +46,9 @@ inline int64_t sfc_index_unit(int ndim, const double* x, int level) {
     int q = 0;
     for(int d = 0; d < ndim; ++d)
       if(pos[d] >= 0.5) q |= 1 << d;
-    index = (index << ndim) | sfc_lut(q);
+    // index += 2^(ndim * (level - 1 - l)) * LUT[q] (hilbert.h:40-41).  Written as a sum, not as a bit field: in 1D the LUT maps the upper
+    // half to 3, which does not fit one bit (keys 0, 3, 6, 9, ... -- still unique and ascending in x)
+    index = index * (int64_t(1) << ndim) + sfc_lut(q);
     for(int d = 0; d < ndim; ++d) pos[d] = 2 * pos[d] - ((q >> d) & 1);
   }
   return index;

@@ -71,7 +71,7 @@ class GridGen {
 
   void configure(const Json& cfg) {
     ndim = static_cast<int>(cfg.at("dim").as_int());
-    if(ndim < 2 || ndim > 3) throw std::runtime_error("Only dimensions 2 and 3 are supported by this host.");
+    if(ndim < 1 || ndim > 3) throw std::runtime_error("Only dimensions 1, 2 and 3 are supported by this host.");
     const long long part = cfg.at("partitionLevel").as_int(), uni = cfg.at("uniformLevel").as_int();
     const long long maxr = cfg.opt_int("maxRfnmtLvl", uni);
     if(part > uni) throw std::runtime_error("Invalid definition of grid level partitionLevel >= uniformLevel");
@@ -418,7 +418,7 @@ class SolverGrid {
   void load(const GridGen& g, const Json& solver_cfg) {
     ndim = g.ndim;
     nn_axis = 2 * ndim;
-    nn_diag = ndim == 2 ? 8 : 26;
+    nn_diag = ndim == 1 ? 2 : (ndim == 2 ? 8 : 26); // cartesian::maxNoNghbrsDiag<NDIM>()
     max_level = g.level;
     n = static_cast<int64_t>(g.cells.size());
     cell_length = g.length_on_level[g.level];

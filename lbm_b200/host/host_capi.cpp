@@ -4,6 +4,7 @@
 
 #include "lbm_solver.hpp"
 #include "uniform_grid.hpp"
+#include "expr.hpp"
 
 using namespace lbmhost;
 
@@ -179,6 +180,18 @@ void lbmhost_ugrid_surface_copy(void* h, int k, int64_t* cells, double* normals)
     cells[i] = s.cells[i];
     for(int d = 0; d < u->ndim; ++d) normals[i * u->ndim + d] = s.normal.at(s.cells[i])[d];
   }
+}
+
+// a boundary-value expression ("value": "cos(pi*x)", expr.hpp) at n points: points = [n][ndim]; returns 0, or -1 with a message
+int lbmhost_eval_expression(const char* text, const double* points, int64_t n, int ndim, double* out, char* err, int errlen) {
+  try {
+    const Expression e(text);
+    for(int64_t k = 0; k < n; ++k) out[k] = e.eval(points + k * ndim, ndim);
+  } catch(const std::exception& ex) {
+    set_err(err, errlen, ex.what());
+    return -1;
+  }
+  return 0;
 }
 
 void lbmhost_round15(const double* in, double* out, int64_t n) {

@@ -135,13 +135,20 @@ class LBMSolver final : public Runnable {
     m_cfg = all.at("solver");
     // solverExe.h:19-93
     m_model = m_cfg.opt_str("model", "D2Q9");
-    const std::string eq = m_cfg.opt_str("equation", "navierstokes");
-    if(eq != "navierstokes") TERMM(-1, "Only the Navier-Stokes equation type runs on this host (poisson: SURVEY.md section 8f N4)");
+    m_equation = m_cfg.opt_str("equation", "navierstokes");
+    if(m_equation != "navierstokes" && m_equation != "poisson") {
+      if(m_equation == "navierstokespoisson") TERMM(-1, "The Navier-Stokes-Poisson equation type does not run on this host");
+      TERMM(-1, "Invalid equation configuration!"); // constants.h:36-47
+    }
+    const bool poisson = m_equation == "poisson";
     if(m_model == "D2Q9") { m_ndim = 2; m_ndist = 9; }
     else if(m_model == "D3Q19") { m_ndim = 3; m_ndist = 19; }
     else if(m_model == "D3Q27") { m_ndim = 3; m_ndist = 27; }
-    else if(m_model == "D1Q3" || m_model == "D2Q5") TERMM(-1, "Unsupported model");
+    else if(m_model == "D1Q3") { m_ndim = 1; m_ndist = 3; }
+    else if(m_model == "D2Q5") { m_ndim = 2; m_ndist = 5; }
     else TERMM(-1, "Invalid model configuration!");
+    // solverExe.h:29-90: D1Q3 / D2Q5 exist for the Poisson equation only; the 3D models are this host's extension (Navier-Stokes only)
+    if((m_ndist == 3 || m_ndist == 5) != poisson && !(poisson && m_ndist == 9)) TERMM(-1, "Unsupported model");
     std::cout << m_ndim << "D LBM Solver started ||>" << std::endl;
   }
 
@@ -663,6 +670,7 @@ class LBMSolver final : public Runnable {
   }
 
   Json        m_cfg;
+  std::string m_equation = "navierstokes";
   std::string m_configFile, m_model = "D2Q9", m_outputDir = "out/", m_solutionName = "solution";
   int         m_ndim = 2, m_ndist = 9, m_collision = LBM_B200_BGK;
   bool        m_benchmark = false, m_diverged = false;

@@ -58,6 +58,7 @@ def lib():
         L.lbmhost_ugrid_surface_size.restype = C.c_int64
         L.lbmhost_ugrid_surface_size.argtypes = [vp, C.c_int]
         L.lbmhost_ugrid_surface_copy.argtypes = [vp, C.c_int, vp, vp]
+        L.lbmhost_eval_expression.argtypes = [C.c_char_p, vp, C.c_int64, C.c_int, vp, C.c_char_p, C.c_int]
         _LIB = L
     return _LIB
 
@@ -117,6 +118,16 @@ def run(config_path, nvars=0):
     rc = L.lbmhost_run(config_path.encode(), out.ctypes.data, vars_.ctypes.data if nvars else None, nvars, err, 2048)
     keys = ["max_error", "l2_error", "gre", "steps", "converged", "residual"]
     return rc, err.value.decode(), dict(zip(keys, out.tolist())), vars_
+
+
+def eval_expression(text, points):
+    """A boundary-value expression of a configuration ("value": "cos(pi*x)") at points [n, ndim] (lbm_b200/host/expr.hpp)."""
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    out = np.empty(len(pts))
+    err = C.create_string_buffer(512)
+    if lib().lbmhost_eval_expression(text.encode(), pts.ctypes.data, len(pts), pts.shape[1], out.ctypes.data, err, 512) != 0:
+        raise ValueError(err.value.decode())
+    return out
 
 
 class UniformGrid:

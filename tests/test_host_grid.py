@@ -15,7 +15,9 @@ CASES = ["couette", "couette_bnd", "couette_bnd_bbDirichlet", "poiseuille", "poi
          "poiseuille_bnd_eq", "poiseuille_bnd_NEEM", "poiseuille_bnd_NEBB", "poiseuille_bnd_pressure",
          "poiseuille_bnd_pressure_neem2",  # the *_aligned / poiseuille_bnd_* cases use alignNodesWithSurface
          # multi-level grids: partitionLevel < uniformLevel and / or boundary refinement
-         "couette_ml_p3u5", "couette_ml_u5m6", "couette_ml_p4u5m7", "sphere_ml_p4u6", "step_ml_p3u5"]
+         "couette_ml_p3u5", "couette_ml_u5m6", "couette_ml_p4u5m7", "sphere_ml_p4u6", "step_ml_p3u5",
+         # Poisson cases of test/run.sh: 1D grids (D1Q3; the curve's 1D keys are 0, 3, 6, ...), aligned 1D / 2D grids
+         "poisson1D", "poisson1D_reaction", "poisson2D", "poisson2D_helmholtz", "poissonD2Q9"]
 
 
 @pytest.mark.parametrize("name", CASES)
