@@ -120,7 +120,7 @@ int64_t lbmhost_postprocess_line(void* h, const double* vars, const char* out_pa
     const auto& lines = gh->solver.postprocessLines(3);
     if(lines.empty()) return 0;
     const SolverGrid& g = gh->solver.solverGrid();
-    for(const auto& cells : lines) LBMSolver::writeLineCsv(out_path, cells, g, vars, g.ndim + 1);
+    for(const auto& cells : lines) LBMSolver::writeLineCsv(out_path, cells, g, vars, gh->solver.noVars());
     return static_cast<int64_t>(lines.back().size());
   } catch(const std::exception& e) {
     set_err(err, errlen, e.what());

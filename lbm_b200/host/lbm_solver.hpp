@@ -29,6 +29,7 @@
 #include "grid.hpp"
 #include "json.hpp"
 #include "vtk_writer.hpp"
+#include "expr.hpp"
 
 namespace lbmhost {
 
@@ -172,6 +173,7 @@ class LBMSolver final : public Runnable {
 
   const GridInterface& grid() const override { return m_grid; }
   const SolverGrid& solverGrid() const { return m_grid.g; }
+  int noVars() const { return m_equation == "poisson" ? 1 : m_ndim + 1; }
 
   // LBMBndManager::addPeriodicBndry marks the cells of both surfaces of a periodic boundary CONDITION as periodic
   // (src/lbm/bnd/bnd.h:217-221, CellProperties::periodic = bit 0); dummies (generateBndry:false) are left alone
@@ -255,7 +257,7 @@ class LBMSolver final : public Runnable {
     loadConfiguration();
     initPostprocess();
     setupGpu();
-    vars.assign(static_cast<size_t>(m_grid.g.n) * (m_ndim + 1), 0.0);
+    vars.assign(static_cast<size_t>(m_grid.g.n) * nvar(), 0.0);
     executePostprocess(PP_ATSTART);
     using clk = std::chrono::steady_clock;
     auto    lastInfo = clk::now();
@@ -281,6 +283,10 @@ class LBMSolver final : public Runnable {
   }
 
  private:
+  bool poisson() const { return m_equation == "poisson"; }
+  // noVars<LBTYPE>(EQ), src/lbm/variables.h: velocity + density, or the potential alone
+  int  nvar() const { return poisson() ? 1 : m_ndim + 1; }
+
   void call(int rc) {
     if(rc != 0) TERMM(-1, std::string("lbm_b200: ") + lbm_b200_last_error());
   }
@@ -302,6 +308,34 @@ class LBMSolver final : public Runnable {
     if(m_outputDir.empty()) TERMM(-1, "Invalid output directory set! (value: " + m_outputDir + ")");
     if(m_outputDir.back() != '/') m_outputDir += '/';
     m_refLength = m_cfg.opt("refLength", 1.0);
+    // solver.cpp:100: m_finestGridSpacing = 1 / (size^(1/NDIM) - 1)
+    const double finestGridSpacing = 1.0 / (std::pow(static_cast<double>(m_grid.g.n), 1.0 / m_ndim) - 1);
+    const double lbm_cs = 1.0 / gcem_sqrt(3.0); // constants.h:26
+    if(poisson()) { // solver.cpp:128-137
+      if(method != "bgk") TERMM(-1, "Invalid equation configuration!");
+      if(!m_cfg.has("relaxation")) TERMM(-1, "The required configuration value is missing: relaxation");
+      m_relaxTime = m_cfg.at("relaxation").as_double();
+      m_re        = 0;
+      m_ma        = 1.0 / lbm_cs;
+      m_omega     = 1.0 / m_relaxTime;
+      m_nu        = (2.0 * m_relaxTime - 1) / 6.0;
+      m_dt        = finestGridSpacing * m_ma * lbm_cs / m_refLength;
+      // collisionStep, solver.cpp:589-599
+      const std::string app = m_cfg.opt_str("equation_application", "debye_huckel");
+      if(app == "simple_diff_reaction") {
+        if(!m_cfg.has("equation_th")) TERMM(-1, "The required configuration value is missing: equation_th");
+        m_poissonRate = m_cfg.at("equation_th").as_double();
+      } else if(app == "debye_huckel") {
+        m_poissonRate = 27.79;
+      } else {
+        TERMM(-1, "Invalid poisson equation application");
+      }
+      std::cerr << "<<<<<<<<<<<<>>>>>>>>>>>>>\nLBM Type " << method << "\nLBM Model " << m_model << "\nEquation poisson\nNo. of variables 1"
+                << "\nNo. Leaf cells: " << m_grid.g.n_leaf << "\nMax Mesh Level: " << m_grid.g.max_level << "\nNo. Bnd cells: " << m_grid.g.n_bnd
+                << "\nRelaxation Time: " << m_relaxTime << "\nTimestep: " << m_dt << "\nOmega: " << m_omega << "\nReynolds Number: " << m_re
+                << "\nViscosity: " << m_nu << "\n+++++++++++++++++++++++++" << std::endl;
+      return;
+    }
     if(m_cfg.has("reynoldsnumber") && m_cfg.has("relaxation")) TERMM(-1, "Only set either reynoldsnumber or relaxation");
     if(!m_cfg.has("ma")) TERMM(-1, "The required configuration value is missing: ma");
     m_ma = m_cfg.at("ma").as_double();
@@ -348,6 +382,7 @@ class LBMSolver final : public Runnable {
     call(lbm_b200_create(&cfg, g.n, &m_gpu));
     call(lbm_b200_set_topology(m_gpu, g.nghbr.data(), g.nn_diag));
     call(lbm_b200_set_geometry(m_gpu, g.center.data(), g.bbmin, g.bbmax, g.cell_length));
+    if(poisson()) call(lbm_b200_set_poisson(m_gpu, m_dt, m_poissonRate));
     // setupBndryCnds, bnd.h:71-142
     const Json& boundary = m_cfg.at("boundary");
     for(const auto& gk : boundary.obj) {
@@ -392,9 +427,32 @@ class LBMSolver final : public Runnable {
           call(lbm_b200_add_pressure(m_gpu, cells, normals.data(), nc, bc.at("pressure").as_double()));
         } else if(type == "outlet" || type == "inlet") {
           TERMM(-1, "Broken"); // bnd.h:176-183
+        } else if((type == "dirichlet" || type == "neumann") && bc.at("model").as_string() == "neem") {
+          // LBMBnd_DirichletNEEM / LBMBnd_NeumannNEEM (bnd.h:116-137): Poisson equation only (bnd_dirichlet.h:329-331 "FIX ME")
+          if(!generate) continue;
+          if(!poisson()) TERMM(-1, "FIX ME");
+          if(!bc.has("value")) TERMM(-1, "The required configuration value is missing: value");
+          const Json& val = bc.at("value");
+          std::vector<double> values(static_cast<size_t>(nc));
+          if(val.is_string()) { // math expression at the cell centres, bnd_dirichlet.h:268-281
+            const Expression e(val.as_string());
+            try {
+              for(int64_t k = 0; k < nc; ++k) values[k] = e.eval(&g.center[cells[k] * m_ndim], m_ndim);
+            } catch(const std::runtime_error& err) {
+              TERMM(-1, err.what());
+            }
+          } else if(val.is_array()) {
+            if(!val.arr.empty() && val.arr[0].is_string()) TERMM(-1, "Impl"); // bnd_dirichlet.h:270
+            std::fill(values.begin(), values.end(), val.as_doubles().at(0));
+          } else {
+            std::fill(values.begin(), values.end(), val.as_double());
+          }
+          if(bc.opt_bool("setAnalyticalValue", false)) TERMM(-1, "setAnalyticalValue is not supported by this host");
+          call(lbm_b200_add_poisson_neem(m_gpu, type == "neumann" ? 1 : 0, cells, normals.data(), nc, values.data(), 0.0));
         } else if(type == "dirichlet") {
           if(!generate) continue;
           const std::string model = bc.at("model").as_string();
+          if(poisson()) TERMM(-1, "dirichlet model " + model + " is not available for the Poisson equation on this host");
           if(model != "bounceback") TERMM(-1, "dirichlet model " + model + " is not available on the GPU path yet (SURVEY.md section 8f N1)");
           const auto v = bc.at("value").as_doubles();
           if(static_cast<int>(v.size()) < m_ndim) TERMM(-1, "dirichlet value needs one entry per dimension");
@@ -417,13 +475,13 @@ class LBMSolver final : public Runnable {
   // solver.cpp:233-263
   bool convergenceCondition() {
     if(!(m_timeStep > 0 && m_timeStep % m_convInterval == 0)) return false;
-    const int NVAR = m_ndim + 1;
+    const int NVAR = nvar();
     std::vector<double> conv(NVAR);
     int32_t bad = 0;
     call(lbm_b200_residual(m_gpu, conv.data(), &bad));
     static const char* names3[4] = {"U", "V", "W", "rho"};
     std::cerr << m_timeStep << ": ";
-    for(int v = 0; v < NVAR; ++v) std::cerr << "d" << (v == m_ndim ? "rho" : names3[v]) << "=" << conv[v] << " ";
+    for(int v = 0; v < NVAR; ++v) std::cerr << "d" << (poisson() ? "P" : (v == m_ndim ? "rho" : names3[v])) << "=" << conv[v] << " ";
     std::cerr << std::endl;
     double maxConv = conv[0];
     for(double c : conv) maxConv = std::max(maxConv, c);
@@ -453,14 +511,15 @@ class LBMSolver final : public Runnable {
     if(format == "ascii") return writeVtpAscii(stem + ".vtp");
     if(format != "binary") TERMM(-1, "Invalid output_format: " + format);
     const SolverGrid&     g    = m_grid.g;
-    const int             NVAR = m_ndim + 1;
+    const int             NVAR = nvar();
     std::vector<uint8_t>  keep = cellFilter();
     int64_t               nout = 0;
     for(uint8_t k : keep) nout += k;
     std::cerr << "  Writing " << stem << ".vtp with #" << nout << " cells" << std::endl; // IO.h:423
     static const char* names[4] = {"U", "V", "W", "rho"};                                // variables.h: VELSTR, "rho"
     std::vector<vtk::Column> cols;
-    for(int v = 0; v < NVAR; ++v) cols.push_back(vtk::Column{v == m_ndim ? "rho" : names[v], vars.data() + v, NVAR});
+    if(poisson()) cols.push_back(vtk::Column{"V", vars.data(), 1}); // the electric potential, solver.cpp:368-378
+    else for(int v = 0; v < NVAR; ++v) cols.push_back(vtk::Column{v == m_ndim ? "rho" : names[v], vars.data() + v, NVAR});
     if(nout == 0) TERMM(-1, "ERROR: Invalid call to encodeLE() with length = 0"); // base64.h:219-223 (the reference exits there)
     if(!vtk::write_points(stem + ".vtp", m_ndim, g.n, g.center.data(), keep.data(), cols))
       TERMM(-1, "Invalid output directory set! (value: " + m_outputDir + ")");
@@ -505,7 +564,7 @@ class LBMSolver final : public Runnable {
     const SolverGrid& g = m_grid.g;
     std::ofstream o(path);
     if(!o) TERMM(-1, "Invalid output directory set! (value: " + m_outputDir + ")");
-    const int NVAR = m_ndim + 1;
+    const int NVAR = nvar();
     std::cerr << "  Writing " << path << " with #" << g.n << " cells" << std::endl;
     o << "<?xml version=\"1.0\"?>\n<VTKFile type=\"PolyData\" version=\"0.1\" byte_order=\"LittleEndian\">\n<PolyData>\n<Piece NumberOfPoints=\""
       << g.n << "\" NumberOfVerts=\"0\" NumberOfLines=\"0\" NumberOfStrips=\"0\" NumberOfPolys=\"0\">\n<Points>\n"
@@ -518,7 +577,7 @@ class LBMSolver final : public Runnable {
     o << "</DataArray>\n</Points>\n<PointData>\n";
     static const char* names[4] = {"U", "V", "W", "rho"};
     for(int v = 0; v < NVAR; ++v) {
-      o << "<DataArray type=\"Float64\" Name=\"" << (v == m_ndim ? "rho" : names[v]) << "\" format=\"ascii\">\n";
+      o << "<DataArray type=\"Float64\" Name=\"" << (poisson() ? "V" : (v == m_ndim ? "rho" : names[v])) << "\" format=\"ascii\">\n";
       for(int64_t c = 0; c < g.n; ++c) o << vars[c * NVAR + v] << "\n";
       o << "</DataArray>\n";
     }
@@ -582,7 +641,7 @@ class LBMSolver final : public Runnable {
     static const char* hookName[PP_NUM] = {"atStart", "beforeTimestep", "afterTimestep", "atEnd"};
     std::cerr << "Executing postprocessing at hook:" << hookName[hook] << std::endl;
     const SolverGrid& g    = m_grid.g;
-    const int         NVAR = m_ndim + 1;
+    const int         NVAR = nvar();
     if(hook == PP_ATSTART) call(lbm_b200_get_moments(m_gpu, vars.data())); // atEnd: `vars` holds the last, forced output()
     for(const auto& cells : m_ppLines[hook]) {
       std::cerr << "  Writing line.csv" << std::endl;
@@ -613,16 +672,28 @@ class LBMSolver final : public Runnable {
   // solver.cpp:388-482 with analytical_solutions.h:16-33,51-59
   void compareToAnalyticalResult() {
     const std::string name = m_cfg.at("analyticalSolution").as_string();
-    if(m_ndim != 2) TERMM(-1, "Invalid analyticalSolution :" + name + " selected!");
+    // analytical::getAnalyticalSolution<NDIM> (src/lbm/analytical_solutions.h:101-131): the solution as a vector of NDIM components.
+    // The Poisson solutions are evaluated with libm here (the reference uses gcem's series at run time): the pass / fail thresholds
+    // are orders of magnitude away from that difference, the printed error may differ in its last digits.
     std::function<void(const double*, double*)> sol;
-    if(name == "couette2D_1_5") {
+    if(m_ndim == 2 && name == "couette2D_1_5") {
       const double reynoldsNum = 0.75, relaxTime = 0.9, refL = 1.0;
       const double dynViscosity = (2.0 * relaxTime - 1.0) / 6.0;
       const double refV = reynoldsNum * dynViscosity / refL;
       sol = [refV](const double* x, double* u) { u[0] = refV / 5.0 * x[1]; u[1] = 0; };
-    } else if(name == "poiseuille2D_1") {
+    } else if(m_ndim == 2 && name == "poiseuille2D_1") {
       const double dp = m_cfg.at("poiseuillePressureGradient").as_double(), nu = m_nu;
       sol = [dp, nu](const double* x, double* u) { u[0] = dp / (2.0 * nu) * x[1] * (1.0 - 0.0 - x[1]); u[1] = 0; };
+    } else if(m_ndim == 2 && name == "poissonCHAI08_2") { // :83-87
+      const double mu = std::sqrt(4 + M_PI * M_PI);
+      sol = [mu](const double* x, double* u) { u[0] = std::cos(M_PI * x[0]) * std::sinh(mu * (1 - x[1])) / std::sinh(mu); u[1] = 0; };
+    } else if(m_ndim == 1 && name == "poissonCHAI08_1") { // :70-78, Debye-Hueckel k = 27.79
+      sol = [](const double* x, double* u) {
+        const double k = 27.79, ep = std::exp(k), em = std::exp(-k);
+        u[0] = (ep - 1.0) / (ep - em) * std::exp(-k * x[0]) + (1.0 - em) / (ep - em) * std::exp(k * x[0]);
+      };
+    } else if(m_ndim == 1 && name == "poissonSimpleDiffReaction") { // :92-95
+      sol = [](const double* x, double* u) { u[0] = std::cosh(1.0 * (1.0 - x[0])) / std::cosh(1.0); };
     } else {
       TERMM(-1, "Invalid analyticalSolution :" + name + " selected!");
     }
@@ -634,19 +705,30 @@ class LBMSolver final : public Runnable {
         if(srf == nullptr) TERMM(-1, "Invalid bndryId \"" + s.as_string() + "\"");
         for(int64_t c : srf->cells) excluded[c] = 1;
       }
-    const int NVAR = m_ndim + 1;
+    const int NVAR = nvar();
     double sumError = 0, sumErrorSq = 0, sumSolution = 0, sumSolutionSq = 0;
     maxError = 0;
+    // shiftCenter (solver.cpp:485-501): poissonCHAI08_1 compares at points spaced equidistantly over (0, 1)
+    const bool   shift  = name == "poissonCHAI08_1";
+    const double extent = shift ? std::abs(g.center[0] - g.center[static_cast<size_t>(g.n - 1)]) : 0.0;
     for(int64_t c = 0; c < g.n; ++c) {
       if(excluded[c]) continue;
-      double u[2];
-      sol(&g.center[c * 2], u);
-      const double dx = vars[c * NVAR] - u[0], dy = vars[c * NVAR + 1] - u[1];
-      const double delta = std::sqrt(dx * dx + dy * dy);
+      double x[3] = {0, 0, 0}, u[3] = {0, 0, 0}, v[3] = {0, 0, 0};
+      for(int d = 0; d < m_ndim; ++d) x[d] = g.center[c * m_ndim + d];
+      if(shift) {
+        const double pos = std::floor(x[0] / (extent / static_cast<double>(g.n - 1)));
+        x[0] = pos * 1.0 / static_cast<double>(g.n - 1);
+      }
+      sol(x, u);
+      if(poisson()) v[0] = vars[c];                                        // the other components of the reference's vector are never set
+      else for(int d = 0; d < m_ndim; ++d) v[d] = vars[c * NVAR + d];
+      double d2 = 0, s2 = 0;
+      for(int d = 0; d < m_ndim; ++d) { d2 += (v[d] - u[d]) * (v[d] - u[d]); s2 += u[d] * u[d]; }
+      const double delta = std::sqrt(d2);
       sumError += delta;
       sumErrorSq += delta * delta;
-      sumSolution += std::sqrt(u[0] * u[0] + u[1] * u[1]);
-      sumSolutionSq += u[0] * u[0] + u[1] * u[1];
+      sumSolution += std::sqrt(s2);
+      sumSolutionSq += s2;
       maxError = std::max(delta, maxError);
     }
     l2Error = (gcem_sqrt(sumErrorSq) / gcem_sqrt(sumSolutionSq)) / std::pow(static_cast<double>(g.n), 1.0 / m_ndim);
@@ -675,6 +757,7 @@ class LBMSolver final : public Runnable {
   int         m_ndim = 2, m_ndist = 9, m_collision = LBM_B200_BGK;
   bool        m_benchmark = false, m_diverged = false;
   long long   m_infoInterval = 10, m_convInterval = 10, m_solutionInterval = 100, m_maxTimeStep = 0, m_timeStep = 0;
+  double      m_dt = 0, m_poissonRate = 27.79; // Poisson equation: m_dt (solver.cpp:136), poisson_D (solver.cpp:589-599)
   double      m_refLength = 1.0, m_ma = 0.01, m_re = 1, m_nu = 0, m_relaxTime = 0.9, m_omega = 1.0 / 0.9;
   LBMGrid     m_grid;
   lbm_b200_solver* m_gpu = nullptr;

@@ -100,7 +100,8 @@ def postprocess_line(config_path, vars_, out_path):
         raise RuntimeError(err.value.decode())
     try:
         v = np.ascontiguousarray(vars_, dtype=np.float64)
-        assert v.size == L.lbmhost_grid_ncells(h) * (L.lbmhost_grid_ndim(h) + 1)
+        n = L.lbmhost_grid_ncells(h)
+        assert v.size in (n, n * (L.lbmhost_grid_ndim(h) + 1))  # one variable per cell for the Poisson equation types
         n = L.lbmhost_postprocess_line(h, v.ctypes.data, out_path.encode(), err, 1024)
         if n < 0:
             raise RuntimeError(err.value.decode())

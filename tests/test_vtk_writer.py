@@ -62,7 +62,8 @@ def test_solution_file_is_byte_identical_to_the_reference(name, hostlib, oracle_
     out = str(tmp_path / INDEX[name]["file"])
     # default cell filter "leafCells" (solver.cpp:86, cell_filter.h:60-96): on multi-level grids only the childless cells are written
     keep = ((spec.golden["props"] >> 14) & 1).astype(np.uint8)
-    assert write(hostlib, out, spec.center, v, ["U", "V", "rho"], None if keep.all() else keep) == 0
+    names = ["V"] if spec.equation == "poisson" else ["U", "V", "rho"]  # the potential is written as "V" (solver.cpp:368-378)
+    assert write(hostlib, out, spec.center, v, names, None if keep.all() else keep) == 0
     data = open(out, "rb").read()
     whole = os.path.join(HERE, "golden", "vtp", f"{name}.vtp.gz")
     if os.path.exists(whole):
@@ -75,7 +76,7 @@ def test_solution_file_is_byte_identical_to_the_reference(name, hostlib, oracle_
 
 
 # executed steps of the full runs (tests/test_host_run_gpu.py::RUN_SH); the oracle reaches them in seconds for these three
-LINE_CASES = [("poiseuille", 34250), ("couette_bnd_eq", 14801), ("couette_bnd_eq_aligned", 14801)]
+LINE_CASES = [("poisson2D", 10000), ("poissonD2Q9", 10000), ("poiseuille", 34250), ("couette_bnd_eq", 14801), ("couette_bnd_eq_aligned", 14801)]
 
 
 @pytest.mark.parametrize("name,steps", LINE_CASES)
