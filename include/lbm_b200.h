@@ -149,6 +149,38 @@ int lbm_b200_comm_init(lbm_b200_solver* s, const char* id128, int32_t rank, int3
 int lbm_b200_box_rows(int32_t ndim, const int64_t* shape, const int32_t* periodic, const int64_t* cells, int64_t ncells,
                       int64_t* nghbr, int32_t stride, double* center);
 
+/* ---- partition helper (host code, no CUDA): the local problem of one rank, built from table rows the caller supplies through a
+ * callback -- a full table, the synthetic box, or an on-demand provider such as lbm_b200/host/uniform_grid.hpp -- so that no rank needs
+ * the whole table.  Equal-count contiguous ranges of the SFC-ordered list (uniform weights: the reference's only WeightMethod,
+ * src/loadbalancing_weights.h:19-29); ghosts = remote cells an owned cell pushes to or pulls from; halo lists in (global id,
+ * direction) order, identical on both sides without communication; pressure = the GLOBAL cell lists of all pressure boundary
+ * conditions in application order (velocity halo of their inward neighbours, see lbm_b200_set_vars_halo).
+ * rows_fn(user, ids, n, rows, sources): rows[r*stride + j] = N(ids[r], j), sources[r*stride + j] = the cell whose push in direction j
+ * lands in ids[r] (-1: none); either output pointer may be NULL; returns 0 on success. */
+typedef struct lbm_b200_partition lbm_b200_partition;
+typedef int (*lbm_b200_rows_fn)(void* user, const int64_t* ids, int64_t n, int64_t* rows, int64_t* sources);
+int lbm_b200_partition_create(int64_t ncells_global, int32_t ndim, int32_t ndist, int32_t stride, int32_t rank, int32_t world,
+                              lbm_b200_rows_fn rows_fn, void* user, int32_t npressure, const int64_t* const* pressure_cells,
+                              const double* const* pressure_normals, const int64_t* pressure_count, lbm_b200_partition** out);
+typedef struct {
+  int64_t lo, hi;              /* this rank owns the global cells [lo, hi) */
+  int64_t n_owned, n_ghost;    /* local list = owned cells, then ghosts */
+  const int64_t* ghosts;       /* [n_ghost] global ids, ascending */
+  const int64_t* nghbr;        /* [(n_owned + n_ghost) * stride] local ids: the table for lbm_b200_set_topology */
+  int32_t stride, npeers;
+  const int32_t* peers;
+  const int64_t *send_count, *recv_count, *send_cell, *recv_cell;   /* as lbm_b200_set_halo takes them */
+  const int32_t *send_dir, *recv_dir;
+  const int64_t *vsend_count, *vrecv_count, *vsend_cell, *vrecv_cell; /* as lbm_b200_set_vars_halo takes them */
+} lbm_b200_partition_view;
+int lbm_b200_partition_get(const lbm_b200_partition* p, lbm_b200_partition_view* out);
+/* Entries of a boundary-condition cell list that this rank owns, order kept: local_cells[k] = local id, index[k] = position in the
+ * input list (to pick the matching normals / values).  Returns the count. */
+int64_t lbm_b200_partition_restrict(const lbm_b200_partition* p, const int64_t* cells, int64_t n, int64_t* local_cells, int64_t* index);
+/* lbm_b200_set_ghosts + lbm_b200_set_halo (+ lbm_b200_set_vars_halo when there is one) on a solver created with n_owned + n_ghost cells. */
+int lbm_b200_partition_apply(const lbm_b200_partition* p, lbm_b200_solver* s);
+void lbm_b200_partition_destroy(lbm_b200_partition* p);
+
 /* Optional: run the kernels on this cudaStream_t (default: the legacy default stream). */
 int lbm_b200_set_stream(lbm_b200_solver* s, void* cuda_stream);
 

@@ -53,6 +53,19 @@ class PlanView(C.Structure):
         ("chunk_abb_base", C.POINTER(C.c_int32)), ("chunk_abb", C.POINTER(C.c_int32)), ("n_chunk_abb_rows", C.c_int64)]
 
 
+class PartitionView(C.Structure):
+    _fields_ = [("lo", C.c_int64), ("hi", C.c_int64), ("n_owned", C.c_int64), ("n_ghost", C.c_int64),
+                ("ghosts", C.POINTER(C.c_int64)), ("nghbr", C.POINTER(C.c_int64)), ("stride", C.c_int32), ("npeers", C.c_int32),
+                ("peers", C.POINTER(C.c_int32)),
+                ("send_count", C.POINTER(C.c_int64)), ("recv_count", C.POINTER(C.c_int64)), ("send_cell", C.POINTER(C.c_int64)),
+                ("recv_cell", C.POINTER(C.c_int64)), ("send_dir", C.POINTER(C.c_int32)), ("recv_dir", C.POINTER(C.c_int32)),
+                ("vsend_count", C.POINTER(C.c_int64)), ("vrecv_count", C.POINTER(C.c_int64)), ("vsend_cell", C.POINTER(C.c_int64)),
+                ("vrecv_cell", C.POINTER(C.c_int64))]
+
+
+ROWS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64))
+
+
 def library_path():
     # LBM_B200_LIB selects a tuning build of the same library (kernel experiments); never a different backend
     return os.environ.get("LBM_B200_LIB") or os.path.join(_HERE, "liblbm_b200.so")
@@ -120,6 +133,13 @@ def load_library():
     L.lbm_b200_set_ghosts.argtypes = [vp, i64]
     L.lbm_b200_set_halo.argtypes = [vp, i32, pi32, pi64, pi64, pi32, pi64, pi64, pi32]
     L.lbm_b200_set_vars_halo.argtypes = [vp, pi64, pi64, pi64, pi64]
+    L.lbm_b200_partition_create.argtypes = [i64, i32, i32, i32, i32, i32, ROWS_FN, vp, i32, C.POINTER(vp), C.POINTER(vp), pi64, C.POINTER(vp)]
+    L.lbm_b200_partition_get.argtypes = [vp, C.POINTER(PartitionView)]
+    L.lbm_b200_partition_restrict.argtypes = [vp, pi64, i64, pi64, pi64]
+    L.lbm_b200_partition_restrict.restype = i64
+    L.lbm_b200_partition_apply.argtypes = [vp, vp]
+    L.lbm_b200_partition_destroy.argtypes = [vp]
+    L.lbm_b200_partition_destroy.restype = None
     L.lbm_b200_comm_unique_id.argtypes = [C.c_char_p]
     L.lbm_b200_comm_init.argtypes = [vp, C.c_char_p, i32, i32]
     L.lbm_b200_box_rows.argtypes = [i32, pi64, pi32, pi64, i64, pi64, i32, vp]
@@ -383,3 +403,83 @@ def box_rows(shape, periodic, cells, want_center=False):
     if rc != 0:
         raise LbmB200Error(rc, L.lbm_b200_last_error().decode())
     return nghbr, center
+
+
+class NativePartition:
+    """The local problem of one rank, built by the library's own partition code (lbm_b200/csrc/partition.hpp) from a row provider
+    (anything with .n, .qm, .rows(ids), .sources(ids): lbm_b200.partition.TableRows / BoxRows / GridRows).  Same arrays as
+    lbm_b200.partition.plan_rank (the numpy twin, tests/test_partition_native.py)."""
+
+    def __init__(self, provider, ndim, ndist, stride, rank, world, pressure=None):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        qm = ndist - 1
+
+        def rows_cb(_user, ids_p, n, rows_p, src_p):
+            try:
+                ids = np.ctypeslib.as_array(ids_p, shape=(n,)).copy()
+                if rows_p:
+                    out = np.ctypeslib.as_array(rows_p, shape=(n, stride))
+                    out[:, :qm] = provider.rows(ids)[:, :qm]
+                    out[:, qm:] = -1
+                if src_p:
+                    out = np.ctypeslib.as_array(src_p, shape=(n, stride))
+                    out[:, :qm] = provider.sources(ids)[:, :qm]
+                    out[:, qm:] = -1
+                return 0
+            except Exception:  # noqa: BLE001 -- reported through the library's error path
+                return 1
+        self._cb = ROWS_FN(rows_cb)
+        pressure = pressure or []
+        keep = [(_i64(c), _f64(nrm)) for c, nrm in pressure]
+        cells = (C.c_void_p * max(1, len(keep)))(*[c.ctypes.data for c, _ in keep])
+        normals = (C.c_void_p * max(1, len(keep)))(*[nrm.ctypes.data for _, nrm in keep])
+        counts = _i64([len(c) for c, _ in keep] or [0])
+        rc = self._lib.lbm_b200_partition_create(int(provider.n), int(ndim), int(ndist), int(stride), int(rank), int(world), self._cb, None,
+                                                 len(keep), cells, normals, counts, C.byref(self._h))
+        if rc != 0:
+            raise LbmB200Error(rc, self._lib.lbm_b200_last_error().decode())
+        v = PartitionView()
+        self._lib.lbm_b200_partition_get(self._h, C.byref(v))
+
+        def arr(ptr, count, dtype):
+            return np.ctypeslib.as_array(ptr, shape=(int(count),)).astype(dtype) if count else np.zeros(0, dtype)
+        self.rank, self.world = rank, world
+        self.lo, self.hi, self.n_owned, self.n_ghost = int(v.lo), int(v.hi), int(v.n_owned), int(v.n_ghost)
+        self.ghosts = arr(v.ghosts, v.n_ghost, np.int64)
+        self.nghbr = arr(v.nghbr, (v.n_owned + v.n_ghost) * v.stride, np.int64).reshape(-1, int(v.stride))
+        np_ = int(v.npeers)
+        self.peers = arr(v.peers, np_, np.int32).tolist()
+        self.send_count = arr(v.send_count, np_, np.int64).tolist()
+        self.recv_count = arr(v.recv_count, np_, np.int64).tolist()
+        self.vsend_count = arr(v.vsend_count, np_, np.int64).tolist()
+        self.vrecv_count = arr(v.vrecv_count, np_, np.int64).tolist()
+        self.send_cell = arr(v.send_cell, sum(self.send_count), np.int64)
+        self.send_dir = arr(v.send_dir, sum(self.send_count), np.int32)
+        self.recv_cell = arr(v.recv_cell, sum(self.recv_count), np.int64)
+        self.recv_dir = arr(v.recv_dir, sum(self.recv_count), np.int32)
+        self.vsend_cell = arr(v.vsend_cell, sum(self.vsend_count), np.int64)
+        self.vrecv_cell = arr(v.vrecv_cell, sum(self.vrecv_count), np.int64)
+
+    def restrict(self, cells, normals):
+        """Boundary-condition entries of the cells this rank owns, order kept."""
+        cells = _i64(cells)
+        loc, idx = np.empty(len(cells), np.int64), np.empty(len(cells), np.int64)
+        m = int(self._lib.lbm_b200_partition_restrict(self._h, cells, len(cells), loc, idx))
+        return loc[:m], np.asarray(normals)[idx[:m]]
+
+    def apply_halo(self, solver):
+        rc = self._lib.lbm_b200_partition_apply(self._h, solver._h)
+        if rc != 0:
+            raise LbmB200Error(rc, self._lib.lbm_b200_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lbm_b200_partition_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass

@@ -17,6 +17,7 @@
 #include "nccl_dyn.hpp"
 #include "sequential.cuh"
 #include "poisson.cuh"
+#include "partition.hpp"
 
 namespace {
 
@@ -1411,6 +1412,9 @@ SolverBase* make_solver(const lbm_b200_config& c) {
 struct lbm_b200_solver {
   std::unique_ptr<SolverBase> impl;
 };
+struct lbm_b200_partition {
+  lbm::Partition p;
+};
 
 extern "C" {
 
@@ -1702,6 +1706,68 @@ int lbm_b200_box_rows(int32_t ndim, const int64_t* shape, const int32_t* periodi
   if(!lbm::box_rows(ndim, shape, periodic, cells, ncells, nghbr, stride, center, &err)) return fail(LBM_B200_EINVAL, err);
   return LBM_B200_OK;
 }
+
+int lbm_b200_partition_create(int64_t ncells_global, int32_t ndim, int32_t ndist, int32_t stride, int32_t rank, int32_t world,
+                              lbm_b200_rows_fn rows_fn, void* user, int32_t npressure, const int64_t* const* pressure_cells,
+                              const double* const* pressure_normals, const int64_t* pressure_count, lbm_b200_partition** out) {
+  if(out == nullptr || rows_fn == nullptr) return fail(LBM_B200_EINVAL, "null argument");
+  *out = nullptr;
+  if(npressure < 0 || (npressure > 0 && (!pressure_cells || !pressure_normals || !pressure_count))) return fail(LBM_B200_EINVAL, "bad pressure surface lists");
+  if(ndim < 1 || ndim > 3) return fail(LBM_B200_EINVAL, "bad dimension");
+  std::vector<lbm::PressureSurface> ps;
+  for(int k = 0; k < npressure; ++k) {
+    if(pressure_count[k] < 0 || (pressure_count[k] > 0 && (!pressure_cells[k] || !pressure_normals[k]))) return fail(LBM_B200_EINVAL, "bad pressure surface lists");
+    ps.push_back({pressure_cells[k], pressure_normals[k], pressure_count[k]});
+  }
+  auto* part = new lbm_b200_partition();
+  if(!lbm::build_partition(ncells_global, ndist, stride, ndim, rank, world, rows_fn, user, ps, part->p)) {
+    const std::string msg = part->p.error;
+    delete part;
+    return fail(LBM_B200_EINVAL, msg);
+  }
+  *out = part;
+  return LBM_B200_OK;
+}
+
+int lbm_b200_partition_get(const lbm_b200_partition* p, lbm_b200_partition_view* v) {
+  if(p == nullptr || v == nullptr) return fail(LBM_B200_EINVAL, "null argument");
+  const lbm::Partition& P = p->p;
+  std::memset(v, 0, sizeof(*v));
+  v->lo = P.lo; v->hi = P.hi; v->n_owned = P.n_owned(); v->n_ghost = P.n_ghost();
+  v->ghosts = P.ghosts.data(); v->nghbr = P.nghbr.data(); v->stride = P.stride; v->npeers = static_cast<int32_t>(P.peers.size());
+  v->peers = P.peers.data();
+  v->send_count = P.send_count.data(); v->recv_count = P.recv_count.data(); v->send_cell = P.send_cell.data(); v->recv_cell = P.recv_cell.data();
+  v->send_dir = P.send_dir.data(); v->recv_dir = P.recv_dir.data();
+  v->vsend_count = P.vsend_count.data(); v->vrecv_count = P.vrecv_count.data(); v->vsend_cell = P.vsend_cell.data(); v->vrecv_cell = P.vrecv_cell.data();
+  return LBM_B200_OK;
+}
+
+int64_t lbm_b200_partition_restrict(const lbm_b200_partition* p, const int64_t* cells, int64_t n, int64_t* local_cells, int64_t* index) {
+  if(p == nullptr || n < 0 || (n > 0 && cells == nullptr)) return -1;
+  int64_t m = 0;
+  for(int64_t k = 0; k < n; ++k) {
+    if(cells[k] < p->p.lo || cells[k] >= p->p.hi) continue;
+    if(local_cells != nullptr) local_cells[m] = cells[k] - p->p.lo;
+    if(index != nullptr) index[m] = k;
+    ++m;
+  }
+  return m;
+}
+
+int lbm_b200_partition_apply(const lbm_b200_partition* p, lbm_b200_solver* s) {
+  if(p == nullptr) return fail(LBM_B200_EINVAL, "null argument");
+  const lbm::Partition& P = p->p;
+  int rc = lbm_b200_set_ghosts(s, P.n_ghost());
+  if(rc != LBM_B200_OK) return rc;
+  rc = lbm_b200_set_halo(s, static_cast<int32_t>(P.peers.size()), P.peers.data(), P.send_count.data(), P.send_cell.data(), P.send_dir.data(),
+                         P.recv_count.data(), P.recv_cell.data(), P.recv_dir.data());
+  if(rc != LBM_B200_OK) return rc;
+  if(!P.vsend_cell.empty() || !P.vrecv_cell.empty())
+    rc = lbm_b200_set_vars_halo(s, P.vsend_count.data(), P.vsend_cell.data(), P.vrecv_count.data(), P.vrecv_cell.data());
+  return rc;
+}
+
+void lbm_b200_partition_destroy(lbm_b200_partition* p) { delete p; }
 
 int lbm_b200_set_stream(lbm_b200_solver* s, void* cuda_stream) {
   CHECK_HANDLE(s);
