@@ -11,9 +11,15 @@
 // cases of the reference's test/run.sh, tests/test_oracle_golden.py).  The reference's cases have 256 .. 65 536 cells: this path is
 // launch-latency bound, not a bandwidth kernel.
 #pragma once
+#ifndef LBM_POISSON_HOST_HARNESS // tests/c/poisson_harness.cpp compiles the kernel bodies for the CPU with its own stand-ins
 #include <cuda_runtime.h>
+#endif
 
 #include <cstdint>
+#include <string>
+#include <vector>
+
+#include "plan.hpp"
 
 namespace lbm {
 namespace poisson {
@@ -133,6 +139,112 @@ __global__ void k_dirichlet(State s, Lat L, Bc b) {
   }
 }
 
+// ---- host side: everything lbm_b200_init derives from the caller's tables before the first launch (no CUDA call in here, so the CPU
+// harness of the tests runs exactly this code)
+struct HostBc {
+  int                  neumann = 0;
+  std::vector<int64_t> cells, ext, ext2;
+  std::vector<double>  values;
+  double               grad = 0;
+};
+struct HostSetup {
+  Lat                  lat{};
+  std::vector<int32_t> pull;   // [n*(Q-1)]
+  std::vector<double>  vars0;  // [n] initial potential: the Dirichlet values (initCnd, bnd_dirichlet.h:335-341), 0 elsewhere
+  std::vector<HostBc>  bcs;
+  double omega = 1, om1 = 0, dt_diff = 0, rate2 = 0;
+  int    code = 0;             // 0, or the LBM_B200_E* code (-1 EINVAL, -5 EUNSUP)
+  std::string error;
+};
+
+inline bool prepare(const PlanInput& in, double omega, HostSetup& S) {
+  const LatticeRT& LR = in.L;
+  const int     Q = LR.Q, QM = Q - 1, D = LR.D;
+  const int64_t N = in.n;
+  auto bad = [&](int code, const char* msg) { S.code = code; S.error = msg; return false; };
+  if(!((D == 1 && Q == 3) || (D == 2 && Q == 5) || (D == 2 && Q == 9))) return bad(-1, "Unsupported model"); // m_canPoisson / solverExe.h:37-90
+  S.lat.D = D;
+  S.lat.Q = Q;
+  for(int i = 0; i < Q; ++i) {
+    S.lat.w[i]  = LR.w[i];
+    S.lat.pw[i] = i == QM ? 0.0 : (Q == 3 ? 0.5 : (Q == 5 ? 0.25 : 1.0 / 8.0)); // constants.h:265,286,306
+  }
+  S.lat.inv_1mw = 1.0 / (1.0 - LR.w[QM]);
+  S.omega = omega;
+  S.om1   = 1 - omega;
+  // solver.cpp:606: diffusivity = m_poissonAlpha * pow(m_latticeVelocity = 1, 2) * (0.5 - m_relaxTime) * m_dt, m_relaxTime = 1 / omega
+  const double alpha       = (D == 2 && Q == 5) ? 1.0 / 2.0 : 1.0 / 3.0;
+  const double relax_time  = 1.0 / omega;
+  const double diffusivity = alpha * 1.0 * (0.5 - relax_time) * in.poisson_dt;
+  S.dt_diff = in.poisson_dt * diffusivity;
+  S.rate2   = in.poisson_rate * in.poisson_rate;
+  // neighbour in any of the grid's directions: the lattice's own columns, or (D2Q5 corners) the grid table's diagonal columns
+  const int NW = in.nghbr_wide.empty() ? QM : 8;
+  auto NB = [&](int64_t c, int j) -> int64_t {
+    if(j < QM) return in.nghbr[static_cast<size_t>(c) * QM + j];
+    return j < NW ? in.nghbr_wide[static_cast<size_t>(c) * 8 + j] : -1;
+  };
+  S.pull.assign(static_cast<size_t>(N) * QM, -1);
+  for(int64_t c = 0; c < N; ++c)
+    for(int j = 0; j < QM; ++j) {
+      const int64_t t = NB(c, j);
+      if(t >= 0) S.pull[static_cast<size_t>(t) * QM + j] = static_cast<int32_t>(c); // the highest source wins
+    }
+  S.vars0.assign(static_cast<size_t>(N), 0.0);
+  static const int opp8[8] = {1, 0, 3, 2, 6, 7, 4, 5}; // cartesian::oppositeDir incl. the 2D diagonals
+  for(const BcInput& bc : in.bcs) {
+    if(bc.kind != BC_POISSON_DIRICHLET && bc.kind != BC_POISSON_NEUMANN)
+      return bad(-1, "this boundary condition does not exist for the Poisson equation types");
+    const int64_t n = static_cast<int64_t>(bc.cells.size());
+    HostBc b;
+    b.neumann = bc.kind == BC_POISSON_NEUMANN;
+    b.cells   = bc.cells;
+    b.values  = bc.values;
+    b.grad    = bc.grad;
+    b.ext.assign(static_cast<size_t>(n), -1);
+    b.ext2.assign(static_cast<size_t>(n), -1);
+    std::vector<char> is_cell(static_cast<size_t>(N), 0), is_ext(static_cast<size_t>(N), 0);
+    for(int64_t k = 0; k < n; ++k) {
+      // LBMBnd_DirichletNEEM constructor, bnd_dirichlet.h:287-317: opposite of the first missing axis neighbour, the diagonal
+      // neighbour at a 2D corner
+      const int64_t c = bc.cells[k];
+      int ed = -1;
+      for(int dist = 0; dist < 2 * D; ++dist) {
+        if(NB(c, dist) != -1) continue;
+        if(ed < 0) ed = dist;
+        else {
+          if(ed == 0 && dist == 2) ed = 6;
+          if(ed == 0 && dist == 3) ed = 7;
+          if(ed == 1 && dist == 3) ed = 4;
+          if(ed == 1 && dist == 2) ed = 5;
+        }
+      }
+      if(ed < 0) return bad(-1, "No valid extrapolation cellId");
+      const int edir = opp8[ed];
+      if(edir >= NW) return bad(-1, "No valid extrapolation cellId (corner: pass the grid's 8-column table, stride >= 8)");
+      b.ext[k] = NB(c, edir);
+      if(b.ext[k] < 0) return bad(-1, "No valid extrapolation cellId");
+      if(b.neumann) {
+        b.ext2[k] = NB(b.ext[k], edir);
+        if(b.ext2[k] < 0) return bad(-1, "Neumann boundary: no second extrapolation cell");
+      }
+      if(is_cell[c]) return bad(-5, "Poisson boundary: a cell is listed twice in one surface (order-dependent in the reference)");
+      is_cell[c]       = 1;
+      is_ext[b.ext[k]] = 1;
+    }
+    for(int64_t k = 0; k < n; ++k) {
+      if(is_cell[b.ext[k]]) return bad(-5, "Poisson boundary: extrapolation cell lies on the same surface (order-dependent in the reference)");
+      if(b.neumann && is_ext[b.ext2[k]])
+        return bad(-5, "Neumann boundary: a second extrapolation cell is another entry's first one (order-dependent in the reference)");
+    }
+    if(!b.neumann) // initCnd, bnd_dirichlet.h:335-341 (the Neumann condition has none, bnd_neumann.h:41)
+      for(int64_t k = 0; k < n; ++k) S.vars0[bc.cells[k]] = bc.values[k];
+    S.bcs.push_back(std::move(b));
+  }
+  return true;
+}
+
+#ifndef LBM_POISSON_HOST_HARNESS
 // sumAbsDiff (solver.cpp:809-815) over one variable, fixed-shape partial sums
 __global__ void k_residual(const double* __restrict__ v, const double* __restrict__ vo, int64_t n, double* __restrict__ partial) {
   __shared__ double sh[256];
@@ -147,6 +259,7 @@ __global__ void k_residual(const double* __restrict__ v, const double* __restric
   }
   if(threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
+#endif
 
 } // namespace poisson
 } // namespace lbm

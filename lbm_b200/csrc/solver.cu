@@ -1146,18 +1146,16 @@ struct PoissonSolver final : SolverBase {
   std::vector<std::unique_ptr<DevBuf<double>>>  keep_f64;
   int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
 
+  lbm::poisson::HostSetup setup;
+
   lbm::poisson::State state() const {
     lbm::poisson::State s{};
     s.f = d_f.p; s.fold = d_fold.p; s.feq = d_feq.p; s.vars = d_vars.p; s.varsold = d_varsold.p;
     s.pull = d_pull.p; s.nghbr = d_nghbr.p; s.n = in.n;
-    s.omega = cfg.omega;
-    s.om1   = 1 - cfg.omega;
-    // solver.cpp:606: diffusivity = m_poissonAlpha * pow(m_latticeVelocity = 1, 2) * (0.5 - m_relaxTime) * m_dt, m_relaxTime = 1 / omega
-    const double alpha       = (in.L.D == 2 && in.L.Q == 5) ? 1.0 / 2.0 : 1.0 / 3.0;
-    const double relax_time  = 1.0 / cfg.omega;
-    const double diffusivity = alpha * 1.0 * (0.5 - relax_time) * in.poisson_dt;
-    s.dt_diff = in.poisson_dt * diffusivity;
-    s.rate2   = in.poisson_rate * in.poisson_rate;
+    s.omega = setup.omega;
+    s.om1   = setup.om1;
+    s.dt_diff = setup.dt_diff;
+    s.rate2   = setup.rate2;
     return s;
   }
   static int blocks(int64_t n) { return static_cast<int>((n + 127) / 128); }
@@ -1173,104 +1171,45 @@ struct PoissonSolver final : SolverBase {
   }
 
   int init() override {
-    const lbm::LatticeRT& LR = in.L;
-    const int     Q = LR.Q, QM = Q - 1, D = LR.D;
+    const int     Q = in.L.Q;
     const int64_t N = in.n;
-    if(!((D == 1 && Q == 3) || (D == 2 && Q == 5) || (D == 2 && Q == 9)))
-      return fail(LBM_B200_EINVAL, "Unsupported model"); // m_canPoisson / solverExe.h:37-90
     if(cfg.precision != LBM_B200_FP64) return fail(LBM_B200_EUNSUP, "the Poisson equation types run in fp64 only");
     if(cfg.collision != LBM_B200_BGK) return fail(LBM_B200_EINVAL, "Invalid equation configuration!");
     if(!in.peers.empty() || in.n_ghost > 0) return fail(LBM_B200_EUNSUP, "the Poisson equation types are not partitioned");
     if(in.forcing) return fail(LBM_B200_EINVAL, "forcing is a Navier-Stokes feature");
     if(in.nghbr.empty()) return fail(LBM_B200_ESTATE, "no topology set");
+    // everything derived from the caller's tables (lattice constants, inverse push table, extrapolation cells, order-hazard checks,
+    // initial potential): host code shared with the CPU harness of the tests
+    if(!lbm::poisson::prepare(in, cfg.omega, setup)) return fail(setup.code, setup.error);
+    lat = setup.lat;
     CUDA_TRY(cudaSetDevice(cfg.device));
-    lat.D = D;
-    lat.Q = Q;
-    for(int i = 0; i < Q; ++i) {
-      lat.w[i]  = LR.w[i];
-      lat.pw[i] = i == QM ? 0.0 : (Q == 3 ? 0.5 : (Q == 5 ? 0.25 : 1.0 / 8.0)); // constants.h:265,286,306
-    }
-    lat.inv_1mw = 1.0 / (1.0 - LR.w[QM]);
-    // neighbour in any of the grid's directions: the lattice's own columns, or (D2Q5 corners) the grid table's diagonal columns
-    const int NW = in.nghbr_wide.empty() ? QM : 8;
-    auto NB = [&](int64_t c, int j) -> int64_t {
-      if(j < QM) return in.nghbr[static_cast<size_t>(c) * QM + j];
-      return j < NW ? in.nghbr_wide[static_cast<size_t>(c) * 8 + j] : -1;
-    };
-    std::vector<int32_t> pull(static_cast<size_t>(N) * QM, -1);
-    for(int64_t c = 0; c < N; ++c)
-      for(int j = 0; j < QM; ++j) {
-        const int64_t t = NB(c, j);
-        if(t >= 0) pull[static_cast<size_t>(t) * QM + j] = static_cast<int32_t>(c);
-      }
     std::vector<int64_t> nb64(in.nghbr.begin(), in.nghbr.end());
-    CUDA_TRY(d_pull.upload(pull));
+    CUDA_TRY(d_pull.upload(setup.pull));
     CUDA_TRY(d_nghbr.upload(nb64));
     const size_t nq = static_cast<size_t>(N) * Q;
     CUDA_TRY(d_f.alloc(nq)); CUDA_TRY(d_fold.alloc(nq)); CUDA_TRY(d_feq.alloc(nq));
     CUDA_TRY(d_vars.alloc(N)); CUDA_TRY(d_varsold.alloc(N)); CUDA_TRY(d_scratch.alloc(N));
     CUDA_TRY(d_partial.alloc(64));
     CUDA_TRY(cudaMemset(d_varsold.p, 0, d_varsold.bytes()));
-    std::vector<double> vars0(static_cast<size_t>(N), 0.0);
     cudaError_t cerr = cudaSuccess;
-    static const int opp8[8] = {1, 0, 3, 2, 6, 7, 4, 5}; // cartesian::oppositeDir incl. the 2D diagonals
-    for(const lbm::BcInput& bc : in.bcs) {
-      if(bc.kind != lbm::BC_POISSON_DIRICHLET && bc.kind != lbm::BC_POISSON_NEUMANN)
-        return fail(LBM_B200_EINVAL, "this boundary condition does not exist for the Poisson equation types");
-      const int64_t n = static_cast<int64_t>(bc.cells.size());
-      std::vector<int64_t> ext(static_cast<size_t>(n)), ext2(static_cast<size_t>(n), -1);
-      std::vector<char>    is_cell(static_cast<size_t>(N), 0), is_ext(static_cast<size_t>(N), 0);
-      for(int64_t k = 0; k < n; ++k) {
-        // LBMBnd_DirichletNEEM constructor, bnd_dirichlet.h:287-317: opposite of the first missing axis neighbour, the diagonal
-        // neighbour at a 2D corner
-        const int64_t c = bc.cells[k];
-        int ed = -1;
-        for(int dist = 0; dist < 2 * D; ++dist) {
-          if(NB(c, dist) != -1) continue;
-          if(ed < 0) ed = dist;
-          else {
-            if(ed == 0 && dist == 2) ed = 6;
-            if(ed == 0 && dist == 3) ed = 7;
-            if(ed == 1 && dist == 3) ed = 4;
-            if(ed == 1 && dist == 2) ed = 5;
-          }
-        }
-        if(ed < 0) return fail(LBM_B200_EINVAL, "No valid extrapolation cellId");
-        const int edir = opp8[ed];
-        if(edir >= NW) return fail(LBM_B200_EINVAL, "No valid extrapolation cellId (corner: pass the grid's 8-column table, stride >= 8)");
-        ext[k] = NB(c, edir);
-        if(ext[k] < 0) return fail(LBM_B200_EINVAL, "No valid extrapolation cellId");
-        if(bc.kind == lbm::BC_POISSON_NEUMANN) {
-          ext2[k] = NB(ext[k], edir);
-          if(ext2[k] < 0) return fail(LBM_B200_EINVAL, "Neumann boundary: no second extrapolation cell");
-        }
-        if(is_cell[c]) return fail(LBM_B200_EUNSUP, "Poisson boundary: a cell is listed twice in one surface (order-dependent in the reference)");
-        is_cell[c] = 1;
-        is_ext[ext[k]] = 1;
-      }
-      for(int64_t k = 0; k < n; ++k) {
-        if(is_cell[ext[k]]) return fail(LBM_B200_EUNSUP, "Poisson boundary: extrapolation cell lies on the same surface (order-dependent in the reference)");
-        if(bc.kind == lbm::BC_POISSON_NEUMANN && is_ext[ext2[k]])
-          return fail(LBM_B200_EUNSUP, "Neumann boundary: a second extrapolation cell is another entry's first one (order-dependent in the reference)");
-      }
+    for(const lbm::poisson::HostBc& hb : setup.bcs) {
       lbm::poisson::Bc b{};
-      b.neumann = bc.kind == lbm::BC_POISSON_NEUMANN;
-      b.n = n;
-      b.cells = up<int64_t>(keep_i64, bc.cells, &cerr);
-      b.ext = up<int64_t>(keep_i64, ext, &cerr);
-      b.ext2 = up<int64_t>(keep_i64, ext2, &cerr);
-      b.values = up<double>(keep_f64, bc.values, &cerr);
-      b.grad = bc.grad;
+      b.neumann = hb.neumann;
+      b.n = static_cast<int64_t>(hb.cells.size());
+      b.cells = up<int64_t>(keep_i64, hb.cells, &cerr);
+      b.ext = up<int64_t>(keep_i64, hb.ext, &cerr);
+      b.ext2 = up<int64_t>(keep_i64, hb.ext2, &cerr);
+      b.values = up<double>(keep_f64, hb.values, &cerr);
+      b.grad = hb.grad;
       bcs.push_back(b);
-      if(bc.kind == lbm::BC_POISSON_DIRICHLET) // initCnd, bnd_dirichlet.h:335-341 (the Neumann condition has none, bnd_neumann.h:41)
-        for(int64_t k = 0; k < n; ++k) vars0[bc.cells[k]] = bc.values[k];
     }
     if(cerr != cudaSuccess) return fail(LBM_B200_ECUDA, cudaGetErrorString(cerr));
-    CUDA_TRY(cudaMemcpy(d_vars.p, vars0.data(), vars0.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_vars.p, setup.vars0.data(), setup.vars0.size() * sizeof(double), cudaMemcpyHostToDevice));
     lbm::poisson::k_init<<<blocks(N), 128, 0, stream>>>(state(), lat);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(stream));
     std::vector<int32_t>().swap(in.nghbr);
+    std::vector<int32_t>().swap(setup.pull);
     t = 0;
     inited = true;
     return LBM_B200_OK;
