@@ -103,7 +103,7 @@ def sphere3d_config(level, model="D3Q27"):
             "outputDir": "out", "gridFileName": "gridD",
             "geometry": {"cube": {"type": "box", "body": "flowregion", "A": [0.0, 0.0, 0.0], "B": [10.0, 10.0, 10.0]},
                          "sphere": {"type": "sphere", "body": "flowregion", "subtract": True, "center": [5.0, 5.0, 5.0], "radius": 1.0}},
-            "solver": {"type": "lbm", "model": model, "relaxation": 0.6, "maxSteps": 10,
+            "solver": {"type": "lbm", "model": model, "relaxation": 0.6, "ma": 0.01, "maxSteps": 10,
                        "boundary": {"cube": {"+x": {"type": "pressure", "pressure": 1.0}, "-x": {"type": "pressure", "pressure": 1.0000008},
                                              "-y": WALL, "+y": WALL, "-z": WALL, "+z": WALL},
                                     "sphere": {"all": WALL}}}}
@@ -117,7 +117,7 @@ def step3d_config(level, model="D3Q19"):
             "geometry": {"cube": {"type": "box", "body": "flowregion", "A": [0.0, 0.0, 0.0], "B": [10.0, 9.0, 10.0]},
                          "step_a": {"type": "box", "body": "flowregion", "subtract": False, "A": [0.0, 9.0, 0.0], "B": [4.0, 10.0, 10.0]},
                          "step_b": {"type": "box", "body": "flowregion", "subtract": False, "A": [6.0, 9.0, 0.0], "B": [10.0, 10.0, 10.0]}},
-            "solver": {"type": "lbm", "model": model, "relaxation": 0.6, "maxSteps": 10,
+            "solver": {"type": "lbm", "model": model, "relaxation": 0.6, "ma": 0.01, "maxSteps": 10,
                        "boundary": {"cube": {"+x": {"type": "pressure", "pressure": 1.0}, "-x": {"type": "pressure", "pressure": 1.0000008},
                                              "-y": WALL, "+y": WALL, "-z": WALL, "+z": WALL},
                                     "step_a": {"+x": WALL, "-x": {"type": "pressure", "pressure": 1.0000008}, "+y": WALL, "-y": WALL,

@@ -127,6 +127,27 @@ int64_t lbmhost_postprocess_line(void* h, const double* vars, const char* out_pa
     return -1;
   }
 }
+// One rank's set-up of a partitioned run (LBMSolver::setupGpuPartitioned: on-demand grid rows, native partition, restricted boundary
+// conditions, halo lists) on an inspection-only handle (device -1): returns the lbm_b200_solver* for lbm_b200_debug_plan, NULL on error.
+// The caller destroys it with lbm_b200_destroy.  No GPU, no NCCL: this is the part of the multi-GPU host that can be checked on a CPU.
+void* lbmhost_partitioned_handle(const char* config_path, int rank, int world, char* err, int errlen) {
+  try {
+    GridGenerator gen;
+    gen.init(0, nullptr, config_path);
+    LBMSolver solver;
+    solver.init(0, nullptr, config_path);
+    solver.setRank(rank, world);
+    GridGen g; // transferGrid only needs the dimensionality in this mode
+    GeneratedGrid gg;
+    gg.gen.configure(Json::parse_file(config_path));
+    solver.transferGrid(gg);
+    return solver.buildPartitioned(-1);
+  } catch(const std::exception& e) {
+    set_err(err, errlen, e.what());
+    return nullptr;
+  }
+}
+
 // ---- single-level grid, rows on demand (uniform_grid.hpp): what one rank of a partitioned run asks the grid pipeline
 void* lbmhost_ugrid_build(const char* config_path, char* err, int errlen) {
   auto* u = new UniformGrid();

@@ -30,6 +30,9 @@
 #include "json.hpp"
 #include "vtk_writer.hpp"
 #include "expr.hpp"
+#include "uniform_grid.hpp"
+#include <thread>
+#include <unistd.h>
 
 namespace lbmhost {
 
@@ -60,6 +63,39 @@ inline double gcem_sqrt(double x) {
   }
   return m * xn;
 }
+
+// One process per GPU.  The reference starts its ranks with mpirun and reads MPI_Comm_rank / MPI_Comm_size (src/main.cpp:283-300); this
+// host has no MPI and takes rank / world size / local rank from the launcher's environment instead: LBM_B200_RANK / LBM_B200_WORLD /
+// LBM_B200_LOCAL_RANK, else torchrun's RANK / WORLD_SIZE / LOCAL_RANK, else Open MPI's or PMI's variables (so `mpirun -np N lbm` works
+// when an MPI launcher is around).  The 128-byte NCCL id travels through a file (LBM_B200_ID_FILE, default /tmp/lbm_b200_id_<port or ppid>).
+struct RankInfo {
+  int         rank = 0, world = 1, local = 0;
+  std::string id_file;
+  static int env_int(const char* name, int fallback) {
+    const char* v = std::getenv(name);
+    return v != nullptr && *v != 0 ? std::atoi(v) : fallback;
+  }
+  static RankInfo from_env() {
+    RankInfo r;
+    const char* sets[4][3] = {{"LBM_B200_RANK", "LBM_B200_WORLD", "LBM_B200_LOCAL_RANK"}, {"RANK", "WORLD_SIZE", "LOCAL_RANK"},
+                              {"OMPI_COMM_WORLD_RANK", "OMPI_COMM_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_RANK"}, {"PMI_RANK", "PMI_SIZE", "MPI_LOCALRANKID"}};
+    for(auto& s : sets) {
+      if(std::getenv(s[1]) == nullptr) continue;
+      r.world = env_int(s[1], 1);
+      r.rank  = env_int(s[0], 0);
+      r.local = env_int(s[2], r.rank);
+      break;
+    }
+    if(r.world < 1 || r.rank < 0 || r.rank >= r.world) throw std::runtime_error("Invalid rank / world size in the environment");
+    const char* f = std::getenv("LBM_B200_ID_FILE");
+    if(f != nullptr) r.id_file = f;
+    else {
+      const char* port = std::getenv("MASTER_PORT");
+      r.id_file = std::string("/tmp/lbm_b200_id_") + (port != nullptr ? std::string(port) : std::to_string(static_cast<long>(getppid())));
+    }
+    return r;
+  }
+};
 
 class GridInterface {
  public:
@@ -100,6 +136,11 @@ class GridGenerator final : public Runnable {
   }
   int64_t run() override {
     m_grid.gen.configure(m_config);
+    if(RankInfo::from_env().world > 1) {
+      // partitioned run: no rank builds the whole tree; the solver asks the on-demand provider (uniform_grid.hpp) for its own rows
+      std::cout << "    * partitioned run: grid rows are generated per rank" << std::endl;
+      return 0;
+    }
     m_grid.gen.generate();
     std::cout << "    * grid has " << m_grid.noCells() << " cells" << std::endl;
     const long long maxc = m_config.opt_int("maxNoCells", -1);
@@ -127,6 +168,7 @@ class LBMSolver final : public Runnable {
  public:
   ~LBMSolver() override {
     if(m_gpu != nullptr) lbm_b200_destroy(m_gpu);
+    if(m_part != nullptr) lbm_b200_partition_destroy(m_part);
   }
 
   void init(int /*argc*/, char** /*argv*/, std::string config_file) override {
@@ -150,6 +192,9 @@ class LBMSolver final : public Runnable {
     else TERMM(-1, "Invalid model configuration!");
     // solverExe.h:29-90: D1Q3 / D2Q5 exist for the Poisson equation only; the 3D models are this host's extension (Navier-Stokes only)
     if((m_ndist == 3 || m_ndist == 5) != poisson && !(poisson && m_ndist == 9)) TERMM(-1, "Unsupported model");
+    m_rank = RankInfo::from_env();
+    m_startTime = ::time(nullptr);
+    if(m_rank.world > 1 && m_rank.rank == 0) std::remove(m_rank.id_file.c_str()); // nothing stale may be picked up by the other ranks
     std::cout << m_ndim << "D LBM Solver started ||>" << std::endl;
   }
 
@@ -165,11 +210,29 @@ class LBMSolver final : public Runnable {
     const auto* gen = dynamic_cast<const GeneratedGrid*>(&grid);
     if(gen == nullptr) TERMM(-1, "transferGrid expects the generator's grid");
     try {
-      m_grid.g.load(gen->gen, m_cfg);
+      if(m_rank.world > 1) {
+        m_ugrid.configure(Json::parse_file(m_configFile));
+        m_grid.g.ndim = m_ugrid.ndim;
+        m_grid.g.max_level = m_ugrid.level;
+        m_grid.g.n = 0;
+      } else {
+        m_grid.g.load(gen->gen, m_cfg);
+      }
     } catch(const std::runtime_error& e) {
       TERMM(-1, e.what());
     }
   }
+
+  // multi-GPU set-up of one rank up to (not including) the NCCL bootstrap; with device == -1 an inspection-only handle that the tests
+  // compare with the Python path's plan (tests/test_host_partitioned.py).  The caller owns the returned handle.
+  lbm_b200_solver* buildPartitioned(int device) {
+    loadConfiguration();
+    setupGpuPartitioned(device);
+    lbm_b200_solver* h = m_gpu;
+    m_gpu = nullptr;
+    return h;
+  }
+  void setRank(int rank, int world) { m_rank.rank = rank; m_rank.world = world; m_rank.local = rank; }
 
   const GridInterface& grid() const override { return m_grid; }
   const SolverGrid& solverGrid() const { return m_grid.g; }
@@ -255,6 +318,7 @@ class LBMSolver final : public Runnable {
   int64_t run() override {
     if(m_benchmark) return runBenchmark();
     loadConfiguration();
+    if(m_rank.world > 1) return runPartitioned();
     initPostprocess();
     setupGpu();
     vars.assign(static_cast<size_t>(m_grid.g.n) * nvar(), 0.0);
@@ -283,6 +347,161 @@ class LBMSolver final : public Runnable {
   }
 
  private:
+  // ---- one rank of a partitioned run (the reference has no decomposition to mirror) --------------------------
+  static int rowsCallback(void* user, const int64_t* ids, int64_t n, int64_t* rows, int64_t* sources) {
+    const auto* u = static_cast<const UniformGrid*>(user);
+    std::string err;
+    if(rows != nullptr && !u->rows(ids, n, rows, u->nn_diag, nullptr, &err)) return 1;
+    if(sources != nullptr && !u->sources(ids, n, sources, u->nn_diag, &err)) return 1;
+    return 0;
+  }
+
+  void setupGpuPartitioned(int device) {
+    if(poisson()) TERMM(-1, "the Poisson equation types are not partitioned");
+    if(!m_cfg.opt_str("forcing", "").empty()) TERMM(-1, "forcing is not partitioned");
+    UniformGrid& u = m_ugrid;
+    if(u.n == 0) TERMM(-1, "partitioned run without a grid (transferGrid was not called)");
+    u.build_surfaces();
+    const Json& boundary = m_cfg.at("boundary");
+    struct BcRef { const Json* conf; const Surface* srf; std::vector<double> normals; };
+    std::vector<BcRef> order;
+    for(const auto& gk : boundary.obj) {
+      const size_t nkeys = gk.second.size();
+      for(const auto& sk : gk.second.obj) {
+        const std::string sname = nkeys > 1 ? gk.first + "_" + sk.first : gk.first;
+        const Surface* srf = nullptr;
+        for(const Surface& s : u.surfaces)
+          if(s.name == sname) srf = &s;
+        if(srf == nullptr) TERMM(-1, "Invalid bndryId \"" + sname + "\"");
+        if(srf->cells.empty() || !sk.second.opt_bool("generateBndry", true)) continue;
+        BcRef r{&sk.second, srf, {}};
+        for(int64_t c : srf->cells)
+          for(int d = 0; d < m_ndim; ++d) r.normals.push_back(srf->normal.at(c)[d]);
+        order.push_back(std::move(r));
+      }
+    }
+    // the pressure surfaces' GLOBAL lists, in application order: the velocity halo of their inward neighbours
+    std::vector<const int64_t*> pcells;
+    std::vector<const double*>  pnormals;
+    std::vector<int64_t>        pcount;
+    for(const BcRef& r : order)
+      if(r.conf->at("type").as_string() == "pressure") {
+        pcells.push_back(r.srf->cells.data());
+        pnormals.push_back(r.normals.data());
+        pcount.push_back(static_cast<int64_t>(r.srf->cells.size()));
+      }
+    call(lbm_b200_partition_create(u.n, m_ndim, m_ndist, u.nn_diag, m_rank.rank, m_rank.world, &LBMSolver::rowsCallback, &u,
+                                   static_cast<int32_t>(pcells.size()), pcells.data(), pnormals.data(), pcount.data(), &m_part));
+    lbm_b200_partition_view v;
+    call(lbm_b200_partition_get(m_part, &v));
+    m_nOwned = v.n_owned;
+    m_nLocal = v.n_owned + v.n_ghost;
+    m_lo     = v.lo;
+    lbm_b200_config cfg = gpuConfig();
+    cfg.device = device;
+    call(lbm_b200_create(&cfg, m_nLocal, &m_gpu));
+    call(lbm_b200_set_topology(m_gpu, v.nghbr, v.stride));
+    for(const BcRef& r : order) {
+      const Json&       bc   = *r.conf;
+      const std::string type = bc.at("type").as_string();
+      const int64_t     n    = static_cast<int64_t>(r.srf->cells.size());
+      std::vector<int64_t> local(static_cast<size_t>(n)), index(static_cast<size_t>(n));
+      const bool wall_bb = type == "wall" && bc.at("model").as_string() == "bounceback";
+      const bool dir_bb  = type == "dirichlet" && bc.at("model").as_string() == "bounceback";
+      if(!wall_bb && !dir_bb && type != "pressure") // every rank refuses, whether or not it owns a cell of the surface
+        TERMM(-1, "boundary condition type " + type + " is not partitioned (wall/bounceback, dirichlet/bounceback, pressure are)");
+      const int64_t m = lbm_b200_partition_restrict(m_part, r.srf->cells.data(), n, local.data(), index.data());
+      if(m == 0) continue;
+      std::vector<double> normals(static_cast<size_t>(m) * m_ndim);
+      for(int64_t k = 0; k < m; ++k)
+        for(int d = 0; d < m_ndim; ++d) normals[k * m_ndim + d] = r.normals[index[k] * m_ndim + d];
+      if(type == "wall" && bc.at("model").as_string() == "bounceback") {
+        call(lbm_b200_add_wall_bb(m_gpu, local.data(), normals.data(), m, bc.opt("tangentialVelocity", 0.0)));
+      } else if(type == "dirichlet" && bc.at("model").as_string() == "bounceback") {
+        const auto val = bc.at("value").as_doubles();
+        if(static_cast<int>(val.size()) < m_ndim) TERMM(-1, "dirichlet value needs one entry per dimension");
+        call(lbm_b200_add_dirichlet_bb(m_gpu, local.data(), normals.data(), m, val.data()));
+      } else if(type == "pressure") {
+        call(lbm_b200_add_pressure(m_gpu, local.data(), normals.data(), m, bc.at("pressure").as_double()));
+      } else {
+        TERMM(-1, "boundary condition type " + type + " is not partitioned (wall/bounceback, dirichlet/bounceback, pressure are)");
+      }
+    }
+    call(lbm_b200_partition_apply(m_part, m_gpu));
+  }
+
+  // NCCL bootstrap without MPI: rank 0 writes the 128-byte id next to a temporary name and renames it, the others wait for the file
+  void exchangeId(char* id) {
+    const std::string path = m_rank.id_file;
+    if(m_rank.rank == 0) {
+      call(lbm_b200_comm_unique_id(id));
+      const std::string tmp = path + ".tmp";
+      std::ofstream o(tmp, std::ios::binary | std::ios::trunc);
+      o.write(id, 128);
+      o.close();
+      if(!o || std::rename(tmp.c_str(), path.c_str()) != 0) TERMM(-1, "cannot write the NCCL id file " + path);
+      return;
+    }
+    for(int tries = 0; tries < 6000; ++tries) { // up to 10 minutes
+      struct stat st;
+      // a file left behind by a run that died is older than this process (minus a margin for staggered starts): not ours
+      if(::stat(path.c_str(), &st) == 0 && st.st_mtime + 120 >= m_startTime) {
+        std::ifstream i(path, std::ios::binary);
+        if(i && i.read(id, 128) && i.gcount() == 128) return;
+      }
+      std::this_thread::sleep_for(std::chrono::milliseconds(100));
+    }
+    TERMM(-1, "timed out waiting for the NCCL id file " + path);
+  }
+
+  int64_t runPartitioned() {
+    std::cerr << "Rank " << m_rank.rank << " of " << m_rank.world << ": partitioned run" << std::endl;
+    setupGpuPartitioned(m_rank.local);
+    char id[128];
+    exchangeId(id);
+    call(lbm_b200_comm_init(m_gpu, id, m_rank.rank, m_rank.world));
+    call(lbm_b200_init(m_gpu));
+    if(m_rank.rank == 0) std::remove(m_rank.id_file.c_str()); // every rank has joined the communicator by now
+    vars.assign(static_cast<size_t>(m_nLocal) * nvar(), 0.0);
+    for(m_timeStep = 0; m_timeStep < m_maxTimeStep && !converged; ++m_timeStep) {
+      if(m_rank.rank == 0 && m_timeStep > 0 && m_timeStep % m_infoInterval == 0) std::cerr << m_timeStep << "/" << m_maxTimeStep << " \n";
+      converged = convergenceCondition(); // lbm_b200_residual is collective here: every rank takes the same decision
+      call(lbm_b200_step(m_gpu, 1));
+      outputPartitioned(m_timeStep == m_maxTimeStep - 1 || converged);
+    }
+    stepsRun = m_timeStep;
+    if(m_diverged) TERMM(-1, "Solution diverged");
+    if(m_cfg.has("analyticalSolution") && m_rank.rank == 0)
+      std::cerr << "analyticalSolution is not evaluated in a partitioned run (it needs the fields of all ranks)" << std::endl;
+    lbm_b200_destroy(m_gpu); // NCCL communicator teardown before the process exits
+    m_gpu = nullptr;
+    std::cout << "LBM Solver finished <||" << std::endl;
+    return 0;
+  }
+
+  // every rank writes the cells it owns: out/<solution_filename>_<step>_rank<r>.vtp, the reference's file format
+  void outputPartitioned(bool forced) {
+    if(!((m_timeStep > 0 && m_timeStep % m_solutionInterval == 0) || forced)) return;
+    call(lbm_b200_get_moments(m_gpu, vars.data()));
+    if(!m_cfg.opt_bool("write_output", true)) return;
+    if(m_ownCenter.empty()) {
+      std::vector<int64_t> ids(static_cast<size_t>(m_nOwned)), rows(static_cast<size_t>(m_nOwned) * m_ugrid.nn_diag);
+      for(int64_t k = 0; k < m_nOwned; ++k) ids[k] = m_lo + k;
+      m_ownCenter.resize(static_cast<size_t>(m_nOwned) * m_ndim);
+      std::string err;
+      if(!m_ugrid.rows(ids.data(), m_nOwned, rows.data(), m_ugrid.nn_diag, m_ownCenter.data(), &err)) TERMM(-1, err);
+    }
+    ::mkdir(m_outputDir.c_str(), 0755);
+    const std::string stem = m_outputDir + m_solutionName + "_" + std::to_string(m_timeStep) + "_rank" + std::to_string(m_rank.rank);
+    const int NVAR = nvar();
+    static const char* names[4] = {"U", "V", "W", "rho"};
+    std::vector<vtk::Column> cols;
+    for(int v = 0; v < NVAR; ++v) cols.push_back(vtk::Column{v == m_ndim ? "rho" : names[v], vars.data() + v, NVAR});
+    std::cerr << "  Writing " << stem << ".vtp with #" << m_nOwned << " cells" << std::endl;
+    if(!vtk::write_points(stem + ".vtp", m_ndim, m_nOwned, m_ownCenter.data(), nullptr, cols))
+      TERMM(-1, "Invalid output directory set! (value: " + m_outputDir + ")");
+  }
+
   bool poisson() const { return m_equation == "poisson"; }
   // noVars<LBTYPE>(EQ), src/lbm/variables.h: velocity + density, or the potential alone
   int  nvar() const { return poisson() ? 1 : m_ndim + 1; }
@@ -357,9 +576,7 @@ class LBMSolver final : public Runnable {
               << "\n+++++++++++++++++++++++++" << std::endl;
   }
 
-  void setupGpu() {
-    markBoundaryProperties();
-    const SolverGrid& g = m_grid.g;
+  lbm_b200_config gpuConfig() const {
     lbm_b200_config cfg;
     lbm_b200_default_config(&cfg);
     cfg.ndim = m_ndim;
@@ -379,6 +596,13 @@ class LBMSolver final : public Runnable {
       for(size_t i = 0; i < r.size() && i < 27; ++i) cfg.mrt_rates[i] = r[i];
     }
     cfg.track_vars = static_cast<int32_t>(m_convInterval > 1 ? m_convInterval : 1);
+    return cfg;
+  }
+
+  void setupGpu() {
+    markBoundaryProperties();
+    const SolverGrid& g = m_grid.g;
+    lbm_b200_config cfg = gpuConfig();
     call(lbm_b200_create(&cfg, g.n, &m_gpu));
     call(lbm_b200_set_topology(m_gpu, g.nghbr.data(), g.nn_diag));
     call(lbm_b200_set_geometry(m_gpu, g.center.data(), g.bbmin, g.bbmax, g.cell_length));
@@ -761,6 +985,13 @@ class LBMSolver final : public Runnable {
   double      m_refLength = 1.0, m_ma = 0.01, m_re = 1, m_nu = 0, m_relaxTime = 0.9, m_omega = 1.0 / 0.9;
   LBMGrid     m_grid;
   lbm_b200_solver* m_gpu = nullptr;
+  // partitioned runs
+  RankInfo    m_rank;
+  UniformGrid m_ugrid;
+  lbm_b200_partition* m_part = nullptr;
+  int64_t     m_nOwned = 0, m_nLocal = 0, m_lo = 0;
+  time_t      m_startTime = 0;
+  std::vector<double> m_ownCenter;
 };
 
 } // namespace lbmhost

@@ -121,6 +121,26 @@ def run(config_path, nvars=0):
     return rc, err.value.decode(), dict(zip(keys, out.tolist())), vars_
 
 
+def partitioned_plan(config_path, rank, world, ndim, ndist):
+    """The device plan of rank `rank` of a `world`-rank run as the C++ host sets it up (LBMSolver::setupGpuPartitioned), on an
+    inspection-only handle -- for comparison with the Python path (lbm_b200.partition + lbm_b200.cases)."""
+    from . import capi
+    L = lib()
+    L.lbmhost_partitioned_handle.restype = C.c_void_p
+    L.lbmhost_partitioned_handle.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    err = C.create_string_buffer(1024)
+    h = L.lbmhost_partitioned_handle(str(config_path).encode(), int(rank), int(world), err, 1024)
+    if not h:
+        raise RuntimeError(err.value.decode())
+    s = capi.Solver.__new__(capi.Solver)
+    s._lib, s._h = capi.load_library(), C.c_void_p(h)
+    s.ndim, s.ndist, s.nvar, s.n = ndim, ndist, ndim + 1, 0
+    try:
+        return s.debug_plan()
+    finally:
+        s.close()
+
+
 def eval_expression(text, points):
     """A boundary-value expression of a configuration ("value": "cos(pi*x)") at points [n, ndim] (lbm_b200/host/expr.hpp)."""
     pts = np.ascontiguousarray(points, dtype=np.float64)

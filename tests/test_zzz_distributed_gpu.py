@@ -33,3 +33,53 @@ def test_partitioned_gpu_residual_allreduce_nccl(shape, ndist):
 def test_partitioned_gpu_baseline_configs_nccl(case, collision, level):
     _need_two_gpus()
     launch(2, "gpu", "0,0,0", 0, steps=10, extra=("--case", case, "--level", str(level), "--collision", collision))
+
+
+def test_cpp_host_two_ranks_match_one_rank(tmp_path):
+    """`lbm` as two processes (one GPU each; rank / world size from the environment, NCCL id through a file): the moments each rank
+    writes for its own cells must equal the single-process run's, bit for bit (STRICT fp64).  The set-up half is pinned on the CPU
+    (tests/test_host_partitioned.py); this is the NCCL bootstrap and the run loop."""
+    import base64
+    import json
+    import os
+    import re
+    import subprocess
+
+    import numpy as np
+
+    from lbm_b200 import cases
+    _need_two_gpus()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "lbm_b200", "lbm")
+    cfg = cases.CONFIGS["step3d"](5)
+    cfg["solver"]["maxSteps"] = 40
+    cfg["solver"]["solution_interval"] = 10 ** 9
+    cfg["solver"]["info_interval"] = 10
+    path = tmp_path / "case.json"
+    path.write_text(json.dumps(cfg))
+
+    def rho_of(file):
+        text = open(file).read()
+        m = re.search(r'Name="rho"[^>]*>\s*\n([A-Za-z0-9+/=]*)\n', text)
+        raw = base64.b64decode(m.group(1) + "=" * (-len(m.group(1)) % 4))
+        return np.frombuffer(raw[8:8 + (len(raw) - 8) // 8 * 8], dtype=np.float64)
+
+    one = tmp_path / "one"
+    one.mkdir()
+    r = subprocess.run([exe, str(path)], cwd=one, capture_output=True, text=True, timeout=600,
+                       env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = rho_of(one / "out" / "solution_39.vtp")
+    two = tmp_path / "two"
+    two.mkdir()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, LBM_B200_RANK=str(rank), LBM_B200_WORLD="2", LBM_B200_LOCAL_RANK=str(rank), LBM_B200_ID_FILE=str(two / "nccl_id"))
+        procs.append(subprocess.Popen([exe, str(path)], cwd=two, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    parts = [rho_of(two / "out" / f"solution_39_rank{rank}.vtp") for rank in range(2)]
+    n = len(ref)
+    assert len(parts[0]) == n // 2 and len(parts[0]) + len(parts[1]) == n
+    # the solution file stores values rounded to 15 decimals (the reference's writer): compare what both runs wrote
+    assert np.array_equal(np.concatenate(parts), ref)
