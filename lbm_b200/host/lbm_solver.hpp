@@ -75,8 +75,16 @@ struct RankInfo {
     const char* v = std::getenv(name);
     return v != nullptr && *v != 0 ? std::atoi(v) : fallback;
   }
+  // Only the `lbm` executable reads the launcher's environment (main.cpp switches this on): code that embeds the host library -- the
+  // Python tests and bench.py run under torchrun, whose WORLD_SIZE must not turn a grid build into a partitioned run -- stays single-rank
+  // unless it sets the rank explicitly.
+  static bool& use_environment() {
+    static bool on = false;
+    return on;
+  }
   static RankInfo from_env() {
     RankInfo r;
+    if(!use_environment()) return r;
     const char* sets[4][3] = {{"LBM_B200_RANK", "LBM_B200_WORLD", "LBM_B200_LOCAL_RANK"}, {"RANK", "WORLD_SIZE", "LOCAL_RANK"},
                               {"OMPI_COMM_WORLD_RANK", "OMPI_COMM_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_RANK"}, {"PMI_RANK", "PMI_SIZE", "MPI_LOCALRANKID"}};
     for(auto& s : sets) {
