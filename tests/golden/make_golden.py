@@ -69,6 +69,10 @@ CASES = {
     "poisson2D": ("poisson/poisson2D.json", 100, [1, 10, 100], False),
     "poisson2D_helmholtz": ("poisson/poisson2D_helmholtz.json", 50, [1, 50], False),
     "poissonD2Q9": ("poisson/poissonD2Q9.json", 100, [1, 10, 100], False),
+    # two more Poisson configurations of the reference's test directory (not part of run.sh): Neumann + Dirichlet in 2D, and the step
+    # geometry with twelve NEEM surfaces (concave corners, cells on several surfaces)
+    "poisson2D_reaction": ("poisson/poisson2D_reaction.json", 100, [1, 10, 100], True),
+    "step_poisson": ("step/step_poisson.json", 100, [1, 10, 100], True),
     "step_ml_p3u5": ("step/step_ns.json", 50, [1, 50], True, {"partitionLevel": 3, "uniformLevel": 5, "maxRfnmtLvl": 5}),
 }
 

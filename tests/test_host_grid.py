@@ -17,7 +17,7 @@ CASES = ["couette", "couette_bnd", "couette_bnd_bbDirichlet", "poiseuille", "poi
          # multi-level grids: partitionLevel < uniformLevel and / or boundary refinement
          "couette_ml_p3u5", "couette_ml_u5m6", "couette_ml_p4u5m7", "sphere_ml_p4u6", "step_ml_p3u5",
          # Poisson cases of test/run.sh: 1D grids (D1Q3; the curve's 1D keys are 0, 3, 6, ...), aligned 1D / 2D grids
-         "poisson1D", "poisson1D_reaction", "poisson2D", "poisson2D_helmholtz", "poissonD2Q9"]
+         "poisson1D", "poisson1D_reaction", "poisson2D", "poisson2D_helmholtz", "poissonD2Q9", "poisson2D_reaction", "step_poisson"]
 
 
 @pytest.mark.parametrize("name", CASES)

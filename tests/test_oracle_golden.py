@@ -18,7 +18,7 @@ CASES = ["couette", "couette_bnd", "couette_bnd_bbDirichlet", "poiseuille", "poi
          # multi-level grids: every level is stepped as its own lattice
          "couette_ml_p3u5", "couette_ml_u5m6", "couette_ml_p4u5m7", "sphere_ml_p4u6", "step_ml_p3u5",
          # Poisson equation types: the five Poisson cases of the reference's test/run.sh
-         "poisson1D", "poisson1D_reaction", "poisson2D", "poisson2D_helmholtz", "poissonD2Q9"]
+         "poisson1D", "poisson1D_reaction", "poisson2D", "poisson2D_helmholtz", "poissonD2Q9", "poisson2D_reaction", "step_poisson"]
 
 
 def sha(a):

@@ -13,7 +13,7 @@ import pytest
 from casebuilder import load_golden
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CASES = ["poisson1D", "poisson1D_reaction", "poisson2D", "poisson2D_helmholtz", "poissonD2Q9"]
+CASES = ["poisson1D", "poisson1D_reaction", "poisson2D", "poisson2D_helmholtz", "poissonD2Q9", "poisson2D_reaction", "step_poisson"]
 
 
 @pytest.fixture(scope="module")

@@ -14,7 +14,7 @@ from casebuilder import load_golden
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["poisson1D", "poisson1D_reaction", "poisson2D", "poisson2D_helmholtz", "poissonD2Q9"]
+CASES = ["poisson1D", "poisson1D_reaction", "poisson2D", "poisson2D_helmholtz", "poissonD2Q9", "poisson2D_reaction", "step_poisson"]
 
 
 def sha(a):
