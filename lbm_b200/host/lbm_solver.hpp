@@ -684,6 +684,9 @@ class LBMSolver final : public Runnable {
         } else if(type == "dirichlet") {
           if(!generate) continue;
           const std::string model = bc.at("model").as_string();
+          // the reference's bounce-back Dirichlet condition for the Poisson equation ends the run in its first apply():
+          // TERMM(-1, "this is incorrect!") (bnd_dirichlet.h:98-106, test/poisson/poisson1D_BBDirichlet.json); same outcome here
+          if(poisson() && model == "bounceback") TERMM(-1, "this is incorrect!");
           if(poisson()) TERMM(-1, "dirichlet model " + model + " is not available for the Poisson equation on this host");
           if(model != "bounceback") TERMM(-1, "dirichlet model " + model + " is not available on the GPU path yet (SURVEY.md section 8f N1)");
           const auto v = bc.at("value").as_doubles();
