@@ -1,0 +1,175 @@
+// kernels_harness.cpp -- TEST INFRASTRUCTURE: the device code of lbm_b200/csrc/kernels.cuh executed on the CPU.
+//
+// g++ compiles the unmodified kernels.cuh against tests/c/fake_cuda/cuda_runtime.h.  A driver loop walks the thread indices of the
+// kernels that need no barrier: k_gather_all (the gather of the fused kernel: link codes, chunk templates, wall descriptors,
+// pressure-face chunks, ghost blocks), the per-cell update (gather_any + update_and_store: what k_step does to a cell), k_halo_pack /
+// k_halo_unpack, k_velocity_pack and k_pressure_extrapolate (the velocity halo of the pressure boundary condition, which had no
+// hardware run in round 1).  The device tables are built from lbm_b200_debug_plan exactly as Solver::init (solver.cu) builds them.
+// tests/test_kernels_harness.py drives partitioned runs with it and compares with the single-domain oracle bit for bit.
+#include <cstring>
+#include <vector>
+
+#include "../../lbm_b200/csrc/kernels.cuh"
+#include "../../include/lbm_b200.h"
+
+namespace {
+using namespace lbm;
+
+template <class F>
+void launch(int64_t n, int threads, F&& body) {
+  blockDim.x = static_cast<unsigned>(threads);
+  gridDim.x  = static_cast<unsigned>((n + threads - 1) / threads);
+  for(unsigned b = 0; b < gridDim.x; ++b)
+    for(unsigned t = 0; t < static_cast<unsigned>(threads); ++t) {
+      blockIdx.x  = b;
+      threadIdx.x = t;
+      body();
+    }
+}
+
+struct Ctx {
+  int ndim = 0, ndist = 0;
+  lbm_b200_plan_view v{};
+  std::vector<AddEntryT<double>> wall, add;
+  std::vector<CopySrcDev>        copy;
+  std::vector<AbbDev<double>>    abb;
+  std::vector<double>            uext[2], values, A, B, vars, vrecv, scratch;
+  int    dyn = 0, first = 1;
+  double omega = 1;
+
+  DevParams<double> params() {
+    DevParams<double> p{};
+    p.A = A.data();
+    p.B = B.data();
+    p.stride = v.npad;
+    p.tmpl = v.tmpl;
+    p.chunk_nb = v.chunk_nb;
+    p.wall_desc = wall.data();
+    p.chunk_abb_base = v.chunk_abb_base;
+    p.chunk_abb = v.chunk_abb;
+    p.n_fast_chunks = static_cast<int32_t>(v.n_fast_chunks);
+    p.gen_begin = static_cast<int32_t>(v.gen_begin);
+    p.n_gen = static_cast<int32_t>(v.n_gen);
+    p.gen_stride = v.gen_stride;
+    p.codes = v.codes;
+    p.tabs.copytab = copy.data();
+    p.tabs.addtab = add.data();
+    p.tabs.abb = abb.data();
+    p.tabs.uext = uext[dyn].data();
+    p.tabs.values = values.data();
+    p.tabs.stride = v.npad;
+    p.omega = omega;
+    p.om1 = 1 - omega;
+    p.omega_minus = omega;
+    for(double& r : p.rates) r = omega;
+    p.vars_out = vars.data();
+    p.first = first;
+    return p;
+  }
+};
+
+template <class L>
+void gather_all(Ctx& c, double* fold_out, double* mom_out) {
+  const DevParams<double> p = c.params();
+  const int32_t nc = static_cast<int32_t>(c.v.ghost_begin);
+  launch(nc, 128, [&] { k_gather_all<L, double, true>(p, nc, fold_out, mom_out); });
+}
+// what k_step does to every owned cell (same device functions, without the persistent-CTA driver and its shared-memory template)
+template <class L>
+void update(Ctx& c) {
+  const DevParams<double> p = c.params();
+  for(int32_t cell = 0; cell < static_cast<int32_t>(c.v.ghost_begin); ++cell) {
+    double fold[L::Q];
+    gather_any<L, double, true>(p, p.A, cell, fold);
+    update_and_store<L, double, true, COLL_BGK>(p, cell, fold);
+  }
+}
+template <class L>
+void velocity_pack(Ctx& c, const int32_t* cells, int n, double* out) {
+  const DevParams<double> p = c.params();
+  launch(n, 128, [&] { k_velocity_pack<L, double, true>(p, cells, n, out); });
+}
+template <class L>
+void pressure_extrapolate(Ctx& c) {
+  const DevParams<double> p = c.params();
+  const int n = static_cast<int>(c.abb.size());
+  launch(n, 128, [&] { k_pressure_extrapolate<L, double, true>(p, n, c.uext[c.dyn ^ 1].data(), c.vrecv.data()); });
+}
+
+#define DISPATCH(c, call)                                                        \
+  do {                                                                           \
+    if((c)->ndim == 2) { using L = Lattice<2, 9>; call; }                        \
+    else if((c)->ndist == 19) { using L = Lattice<3, 19>; call; }               \
+    else { using L = Lattice<3, 27>; call; }                                     \
+  } while(0)
+
+} // namespace
+
+extern "C" {
+
+// solver = an inspection-only handle (device -1) whose set-up calls have been made; the harness keeps views into its plan
+void* kh_create(lbm_b200_solver* solver, int ndim, int ndist, double omega) {
+  auto* c = new Ctx();
+  c->ndim = ndim;
+  c->ndist = ndist;
+  c->omega = omega;
+  if(lbm_b200_debug_plan(solver, &c->v) != 0) { delete c; return nullptr; }
+  const lbm_b200_plan_view& v = c->v;
+  const int QM = ndist - 1;
+  // the conversions of Solver::init (solver.cu)
+  for(int64_t k = 0; k < v.n_wall; ++k) {
+    AddEntryT<double> e{};
+    for(int d = 0; d < 3; ++d) e.v[d] = v.wall_desc[k * 4 + d];
+    e.n = static_cast<int32_t>(v.wall_desc[k * 4 + 3]);
+    c->wall.push_back(e);
+  }
+  if(c->wall.empty()) c->wall.resize(static_cast<size_t>(QM));
+  for(int64_t k = 0; k < v.n_add; ++k) {
+    AddEntryT<double> e{};
+    for(int d = 0; d < 3; ++d) e.v[d] = v.addtab[k * 4 + d];
+    e.n = static_cast<int32_t>(v.addtab[k * 4 + 3]);
+    c->add.push_back(e);
+  }
+  for(int64_t k = 0; k < v.n_copy; ++k) c->copy.push_back({v.copytab[k * 2], v.copytab[k * 2 + 1]});
+  for(int64_t k = 0; k < v.n_abb; ++k) c->abb.push_back({v.abb_cells[k * 3], v.abb_cells[k * 3 + 1], v.abb_cells[k * 3 + 2], v.abb_p[k]});
+  for(int b = 0; b < 2; ++b) c->uext[b].assign(static_cast<size_t>(v.n_abb) * 3 + 3, 0.0);
+  c->values.assign(v.values, v.values + v.n_values);
+  c->A.assign(static_cast<size_t>(ndist) * v.npad, 0.0);
+  c->B = c->A;
+  c->vars.assign(static_cast<size_t>(ndim + 1) * v.npad, 0.0);
+  c->scratch.assign(static_cast<size_t>(ndist) * v.npad, 0.0);
+  return c;
+}
+void kh_destroy(void* p) { delete static_cast<Ctx*>(p); }
+int64_t kh_npad(void* p) { return static_cast<Ctx*>(p)->v.npad; }
+double* kh_A(void* p) { return static_cast<Ctx*>(p)->A.data(); }
+double* kh_B(void* p) { return static_cast<Ctx*>(p)->B.data(); }
+double* kh_vars(void* p) { return static_cast<Ctx*>(p)->vars.data(); }
+double* kh_values(void* p) { return static_cast<Ctx*>(p)->values.data(); }
+double* kh_uext(void* p, int next) { auto* c = static_cast<Ctx*>(p); return c->uext[next ? c->dyn ^ 1 : c->dyn].data(); }
+void kh_set_first(void* p, int first) { static_cast<Ctx*>(p)->first = first; }
+void kh_set_vrecv(void* p, const double* v, int64_t n) { static_cast<Ctx*>(p)->vrecv.assign(v, v + n); if(n == 0) static_cast<Ctx*>(p)->vrecv.assign(3, 0.0); }
+
+// m_fold (SoA, device order) and its moments from the current A: k_gather_all
+void kh_gather_all(void* p, double* fold_out, double* mom_out) { auto* c = static_cast<Ctx*>(p); DISPATCH(c, gather_all<L>(*c, fold_out, mom_out)); }
+// one time step of the owned cells: A -> B (and vars), like the fused kernel
+void kh_update(void* p) { auto* c = static_cast<Ctx*>(p); DISPATCH(c, update<L>(*c)); }
+void kh_velocity_pack(void* p, const int32_t* cells, int n, double* out) { auto* c = static_cast<Ctx*>(p); DISPATCH(c, velocity_pack<L>(*c, cells, n, out)); }
+void kh_pressure_extrapolate(void* p) { auto* c = static_cast<Ctx*>(p); DISPATCH(c, pressure_extrapolate<L>(*c)); }
+void kh_halo_pack(void* p, const int64_t* index, int64_t n, double* out) {
+  auto* c = static_cast<Ctx*>(p);
+  launch(n, 256, [&] { k_halo_pack<double>(c->B.data(), index, n, out); });
+}
+void kh_halo_unpack(void* p, const int64_t* index, int64_t n, const double* in) {
+  auto* c = static_cast<Ctx*>(p);
+  launch(n, 256, [&] { k_halo_unpack<double>(c->B.data(), index, n, in); });
+}
+// end of a step: B becomes A, the dynamic buffers written for the next step become current (Solver::one_step)
+void kh_swap(void* p, int dyn_written) {
+  auto* c = static_cast<Ctx*>(p);
+  c->A.swap(c->B);
+  if(dyn_written) c->dyn ^= 1;
+  c->first = 0;
+}
+
+} // extern "C"
