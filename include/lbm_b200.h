@@ -246,7 +246,8 @@ typedef struct {
   int64_t         n_copy;
   const double*   addtab;    /* [n_add*4] v0, v1, v2, count */
   int64_t         n_add;
-  const double*   wall_desc; /* [n_wall*4] per wall descriptor Q-1 entries of v0, v1, v2, count (count -1: anti-bounce-back slot) */
+  const double*   wall_desc; /* [n_wall*4] per wall descriptor nsel * (Q-1) entries [selector][direction] of v0, v1, v2, count (count -1:
+                                anti-bounce-back slot) */
   int64_t         n_wall;
   const double*   abb_p;     /* [n_abb] pressure of every anti-bounce-back entry */
   const int32_t*  abb_cells; /* [n_abb*3] device cell, inward neighbours n1, n2 (< 0: -(slot+1) of the received velocity halo) */

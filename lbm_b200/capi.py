@@ -272,7 +272,8 @@ class Solver:
         out["codes"] = arr(v.codes, qm * v.gen_stride, (qm, int(v.gen_stride)))
         out["copytab"] = arr(v.copytab, v.n_copy * 2, (int(v.n_copy), 2))
         out["addtab"] = arr(v.addtab, v.n_add * 4, (int(v.n_add), 4))
-        out["wall_desc"] = arr(v.wall_desc, v.n_wall * 4, (int(v.n_wall) // qm if v.n_wall else 0, qm, 4))
+        nsel = int(v.nsel)
+        out["wall_desc"] = arr(v.wall_desc, v.n_wall * 4, (int(v.n_wall) // (qm * nsel) if v.n_wall else 0, nsel, qm, 4))
         out["abb_p"] = arr(v.abb_p, v.n_abb)
         out["abb_cells"] = arr(v.abb_cells, v.n_abb * 3, (int(v.n_abb), 3))
         out["values"] = arr(v.values, v.n_values)

@@ -60,7 +60,8 @@ struct DevParams {
   // fast chunks
   const uint16_t* tmpl;     // [(Q-1)][CHUNK]
   const int32_t*  chunk_nb; // [n_fast_chunks][NSEL + 1]: neighbour chunk bases (-1 = wall), wall descriptor id
-  const AddEntryT<Real>* wall_desc; // [n_wall_desc][Q-1] bounce-back addends of wall chunks (n < 0: anti-bounce-back slot)
+  const AddEntryT<Real>* wall_desc; // [n_wall_desc][NSEL][Q-1] bounce-back addends of wall chunks per (missing neighbour chunk,
+                                    // direction); n < 0: anti-bounce-back slot
   const int32_t*  chunk_abb_base;   // [n_fast_chunks] row of chunk_abb for chunks on a pressure face, -1 otherwise
   const int32_t*  chunk_abb;        // [rows][CHUNK] pressure entry of the cell at that offset
   int32_t         n_fast_chunks;    // fast chunks [chunk_off, chunk_off + n_fast_chunks) are updated by this launch
@@ -329,9 +330,11 @@ __device__ __forceinline__ void gather_generic(const DevParams<Real>& p, const R
 // one slot of a fast chunk: pull at the template offset, or bounce back (+ addends) when the neighbour chunk is a wall
 template <class L, class Real, bool STRICT, int J>
 __device__ __forceinline__ Real fast_slot(const DevParams<Real>& p, const Real* __restrict__ Abuf, int32_t cell, int32_t nbv, uint32_t off,
-                                          const AddEntryT<Real>* __restrict__ wall) {
+                                          const AddEntryT<Real>* __restrict__ wall_of_chunk, uint32_t sel) {
   using A = Ar<Real, STRICT>;
   if(nbv >= 0) return Abuf[static_cast<size_t>(J) * p.stride + nbv + static_cast<int32_t>(off)];
+  // the descriptor of this (missing neighbour chunk, direction): on an edge of the domain the same direction bounces off different walls
+  const AddEntryT<Real>* __restrict__ wall = wall_of_chunk + sel * (L::Q - 1);
   const int n = wall[J].n;
   if(n < 0) {
     // chunk on a pressure in-/outlet face: anti-bounce-back with the cell's own pressure entry, evaluated by the same
@@ -350,7 +353,7 @@ __device__ __forceinline__ void gather_fast_global_rec(const DevParams<Real>& p,
   if constexpr(J < L::Q - 1) {
     const uint32_t t   = p.tmpl[J * L::CHUNK + o];
     const int32_t  nbv = p.chunk_nb[static_cast<size_t>(chunk) * (L::NSEL + 1) + (t >> 10)];
-    fold[J]            = fast_slot<L, Real, STRICT, J>(p, Abuf, cell, nbv, t & 1023u, wall);
+    fold[J]            = fast_slot<L, Real, STRICT, J>(p, Abuf, cell, nbv, t & 1023u, wall, t >> 10);
     gather_fast_global_rec<L, Real, STRICT, J + 1>(p, Abuf, cell, chunk, o, wall, fold);
   }
 }
@@ -366,7 +369,7 @@ __device__ __forceinline__ void gather_fast_global(const DevParams<Real>& p, con
   }
   const int chunk = cell / CH, o = cell % CH;
   const int32_t wid = p.chunk_nb[static_cast<size_t>(chunk) * (L::NSEL + 1) + L::NSEL];
-  const AddEntryT<Real>* wall = p.wall_desc + static_cast<size_t>(wid < 0 ? 0 : wid) * (Q - 1);
+  const AddEntryT<Real>* wall = p.wall_desc + static_cast<size_t>(wid < 0 ? 0 : wid) * (Q - 1) * L::NSEL;
   gather_fast_global_rec<L, Real, STRICT, 0>(p, Abuf, cell, chunk, o, wall, fold);
   fold[Q - 1] = Abuf[static_cast<size_t>(Q - 1) * p.stride + cell];
 }
@@ -417,7 +420,7 @@ __device__ __forceinline__ void fast_wall_gather(const DevParams<Real>& p, const
                                                  const AddEntryT<Real>* __restrict__ wall, Real (&fold)[L::Q]) {
   if constexpr(J < L::Q - 1) {
     const uint32_t t = s_tmpl[J * L::CHUNK + o];
-    fold[J]          = fast_slot<L, Real, STRICT, J>(p, Abuf, cell, nb[t >> 10], t & 1023u, wall);
+    fold[J]          = fast_slot<L, Real, STRICT, J>(p, Abuf, cell, nb[t >> 10], t & 1023u, wall, t >> 10);
     fast_wall_gather<L, Real, STRICT, J + 1>(p, Abuf, cell, o, s_tmpl, nb, wall, fold);
   }
 }
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, LBM_MINBLOCKS) k_step(const __grid_c
     const int32_t* nb  = s_nb[buf];
     buf ^= 1;
     const int32_t  wid = nb[NSEL]; // wall descriptor of this chunk, -1: interior chunk
-    const AddEntryT<Real>* wall = p.wall_desc + static_cast<size_t>(wid < 0 ? 0 : wid) * QM;
+    const AddEntryT<Real>* wall = p.wall_desc + static_cast<size_t>(wid < 0 ? 0 : wid) * QM * NSEL;
     const int32_t base = chunk * CH;
 #pragma unroll 1
     for(int o = threadIdx.x; o < CH; o += kThreads) {

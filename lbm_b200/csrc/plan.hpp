@@ -101,8 +101,8 @@ struct Plan {
   std::vector<int32_t>  ref2dev, dev2ref;
   std::vector<uint16_t> tmpl;       // (Q-1) * CH : sel << 10 | off
   std::vector<int32_t>  chunk_nb;   // n_fast_chunks * (NSEL + 1): device bases (-1: wall selector), then the wall descriptor id
-  std::vector<AddEntry> wall_desc;  // per wall descriptor: Q-1 addend entries (bounce-back slots of wall chunks); n = -1 marks an
-                                    // anti-bounce-back (pressure) slot, whose entry id comes from chunk_abb
+  std::vector<AddEntry> wall_desc;  // per wall descriptor: NSEL * (Q-1) addend entries [selector][direction] (bounce-back slots of
+                                    // wall chunks); n = -1 marks an anti-bounce-back (pressure) slot, whose entry id comes from chunk_abb
   std::vector<int32_t>  chunk_abb_base; // per fast chunk: row of chunk_abb, -1 if the chunk has no pressure cell
   std::vector<int32_t>  chunk_abb;      // [rows][CH] anti-bounce-back entry of the cell at that (device) offset, -1 elsewhere
   std::vector<int32_t>  codes;      // (Q-1) * gen_stride
@@ -584,8 +584,11 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
     bool ok = true, has_wall = false;
     int64_t* nbk = &nbref[static_cast<size_t>(k) * L.NSEL];
     nbk[SELF] = b;
-    std::vector<AddEntry> wd(static_cast<size_t>(QM));
-    std::vector<char>     wd_set(static_cast<size_t>(QM), 0);
+    // one descriptor entry per (missing neighbour chunk, direction): a chunk on an EDGE of the domain bounces some cells off one wall
+    // and some off the other in the same direction, but which wall it is follows from the selector of the missing source
+    const int             WD = L.NSEL * QM;
+    std::vector<AddEntry> wd(static_cast<size_t>(WD));
+    std::vector<char>     wd_set(static_cast<size_t>(WD), 0);
     std::vector<int32_t>  abb_of;
     for(int o = 0; o < CH && ok; ++o) {
       const int64_t c = b + o;
@@ -609,8 +612,9 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
             e.n = it->second.kind == LK_BB_ADD ? it->second.nadd : 0;
           }
           for(int d = 0; d < 3; ++d) e.v[d] = d < e.n ? it->second.add[d] : 0.0;
-          if(!wd_set[j]) { wd[j] = e; wd_set[j] = 1; }
-          else if(wd[j].n != e.n || std::memcmp(wd[j].v, e.v, sizeof(e.v)) != 0) { ok = false; break; }
+          const int wj = sel * QM + j;
+          if(!wd_set[wj]) { wd[wj] = e; wd_set[wj] = 1; }
+          else if(wd[wj].n != e.n || std::memcmp(wd[wj].v, e.v, sizeof(e.v)) != 0) { ok = false; break; }
           if(nbk[sel] == -1) nbk[sel] = WALL;
           else if(nbk[sel] != WALL) { ok = false; break; }
           has_wall = true;
@@ -632,7 +636,7 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
     }
     fast[k] = ok ? 1 : 0;
     if(ok && has_wall) {
-      for(int j = 0; j < QM; ++j) if(!wd_set[j]) { wd[j] = AddEntry{}; }
+      for(int j = 0; j < WD; ++j) if(!wd_set[j]) { wd[j] = AddEntry{}; }
       chunk_wall[k] = wd;
       chunk_abb_ids[k] = abb_of;
     }
@@ -641,17 +645,18 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
   for(int64_t k = 0; k < nc; ++k) {
     if(!fast[k] || chunk_wall[k].empty()) continue;
     int32_t id = -1;
-    for(size_t w = 0; w < P.wall_desc.size() / QM && id < 0; ++w) {
+    const size_t WD = static_cast<size_t>(L.NSEL) * QM;
+    for(size_t w = 0; w < P.wall_desc.size() / WD && id < 0; ++w) {
       bool same = true;
-      for(int j = 0; j < QM && same; ++j) {
-        const AddEntry& a = P.wall_desc[w * QM + j];
+      for(size_t j = 0; j < WD && same; ++j) {
+        const AddEntry& a = P.wall_desc[w * WD + j];
         const AddEntry& c2 = chunk_wall[k][j];
         same = a.n == c2.n && std::memcmp(a.v, c2.v, sizeof(a.v)) == 0;
       }
       if(same) id = static_cast<int32_t>(w);
     }
     if(id < 0) {
-      id = static_cast<int32_t>(P.wall_desc.size() / QM);
+      id = static_cast<int32_t>(P.wall_desc.size() / WD);
       P.wall_desc.insert(P.wall_desc.end(), chunk_wall[k].begin(), chunk_wall[k].end());
     }
     wall_of[k] = id;

@@ -245,7 +245,7 @@ struct Solver final : SolverBase {
         e.n = a.n;
         h.push_back(e);
       }
-      if(h.empty()) h.resize(Q - 1); // so that the pointer arithmetic in the kernel always has a valid base
+      if(h.empty()) h.resize(static_cast<size_t>(Q - 1) * L::NSEL); // so that the pointer arithmetic in the kernel always has a valid base
       CUDA_TRY(d_wall.upload(h));
     }
     {

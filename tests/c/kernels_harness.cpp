@@ -123,7 +123,7 @@ void* kh_create(lbm_b200_solver* solver, int ndim, int ndist, double omega) {
     e.n = static_cast<int32_t>(v.wall_desc[k * 4 + 3]);
     c->wall.push_back(e);
   }
-  if(c->wall.empty()) c->wall.resize(static_cast<size_t>(QM));
+  if(c->wall.empty()) c->wall.resize(static_cast<size_t>(QM) * 27);
   for(int64_t k = 0; k < v.n_add; ++k) {
     AddEntryT<double> e{};
     for(int d = 0; d < 3; ++d) e.v[d] = v.addtab[k * 4 + d];

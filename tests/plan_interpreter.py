@@ -50,12 +50,13 @@ def gather(plan, A, q, values=None, uext=None):
             val = np.empty(ch)
             pull = nbv >= 0
             val[pull] = A[j, nbv[pull] + off[pull]]
-            if (~pull).any():
-                v = A[opp[j], cells[~pull]].copy()
-                e = plan["wall_desc"][wid, j]
+            for s_miss in np.unique(sel[~pull]) if (~pull).any() else []:
+                m = (~pull) & (sel == s_miss)                     # the slots whose source lies in this missing neighbour chunk
+                v = A[opp[j], cells[m]].copy()
+                e = plan["wall_desc"][wid, s_miss, j]
                 if e[3] < 0:
                     # chunk on a pressure face: anti-bounce-back with the cell's own pressure entry (bnd_pressure.h:100)
-                    ent = plan["chunk_abb"][int(plan["chunk_abb_base"][k])][~pull].astype(np.int64)
+                    ent = plan["chunk_abb"][int(plan["chunk_abb_base"][k])][m].astype(np.int64)
                     assert (ent >= 0).all()
                     u = uext[ent]
                     cu = np.zeros(len(ent))
@@ -69,7 +70,7 @@ def gather(plan, A, q, values=None, uext=None):
                     v = -v + 2 * se
                 for a in range(max(int(e[3]), 0)):
                     v = v + e[a]
-                val[~pull] = v
+                val[m] = v
             fold_dev[j, cells] = val
         fold_dev[qm, cells] = A[qm, cells]
     # generic range: link codes

@@ -179,7 +179,7 @@ def test_plan_pressure_boundary_single_domain(shape, ndist, oracle_mod):
     plan = plan_only_solver(spec).debug_plan()
     assert plan["n_abb"] > 0
     if min(shape) >= 3 * (8 if len(shape) == 3 else 32):
-        assert plan["n_chunk_abb_rows"] == 2, "the two face-centre chunks of the pressure in-/outlet should be fast chunks"
+        assert plan["n_chunk_abb_rows"] >= 2, "the face-centre chunks of the pressure in-/outlet should be fast chunks (edge chunks too)"
     o = spec.apply_to(oracle_mod.Oracle(spec.ndim, ndist, spec.nghbr, spec.omega))
     o.init()
     dev2ref = np.full(plan["npad"], -1)
