@@ -1,8 +1,11 @@
 // TEST INFRASTRUCTURE: stand-in for <cuda_runtime.h> so that g++ can compile the device code of lbm_b200/csrc/kernels.cuh for the CPU
 // (tests/c/kernels_harness.cpp).  Qualifiers vanish, thread indices are variables a driver loop sets, IEEE intrinsics are the plain
 // operators (the harness is compiled with -ffp-contract=off, so a + b is __dadd_rn(a, b)), cache-hinted loads / stores are plain ones.
-// Kernels that need barriers or shuffles (k_step, k_residual) compile but are never called.
+// __syncthreads() is a real barrier over the OS threads the harness starts for one block (k_step runs that way, with its shared
+// memory as function-local statics: one block at a time); k_residual (warp shuffles) compiles but is never called.
 #pragma once
+#include <pthread.h>
+
 #include <cmath>
 #include <cstdint>
 
@@ -17,15 +20,20 @@
 #define __launch_bounds__(...)
 
 struct FakeDim3 { unsigned x = 0, y = 0, z = 0; };
-static FakeDim3 blockIdx, blockDim, threadIdx, gridDim;
+static FakeDim3 blockIdx, blockDim, gridDim;
+static thread_local FakeDim3 threadIdx;
 
-static inline void __syncthreads() {}
+static pthread_barrier_t g_block_barrier;
+static bool              g_block_barrier_on = false; // single-threaded driver loops: __syncthreads() has nothing to wait for
+static inline void __syncthreads() {
+  if(g_block_barrier_on) pthread_barrier_wait(&g_block_barrier);
+}
 template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline T __ldcg(const T* p) { return *p; }
 template <class T> static inline void __stcs(T* p, T v) { *p = v; }
 template <class T> static inline void __stcg(T* p, T v) { *p = v; }
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int) { return v; }
-static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p += v; return o; }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }

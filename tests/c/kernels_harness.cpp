@@ -7,6 +7,7 @@
 // hardware run in round 1).  The device tables are built from lbm_b200_debug_plan exactly as Solver::init (solver.cu) builds them.
 // tests/test_kernels_harness.py drives partitioned runs with it and compares with the single-domain oracle bit for bit.
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../../lbm_b200/csrc/kernels.cuh"
@@ -36,6 +37,7 @@ struct Ctx {
   std::vector<double>            uext[2], values, A, B, vars, vrecv, scratch;
   int    dyn = 0, first = 1;
   double omega = 1;
+  unsigned long long ticket = 0, ticket_next = 0;
 
   DevParams<double> params() {
     DevParams<double> p{};
@@ -84,6 +86,42 @@ void update(Ctx& c) {
     update_and_store<L, double, true, COLL_BGK>(p, cell, fold);
   }
 }
+// The fused kernel ITSELF: k_step<L, double, STRICT, BGK> with its generic blocks and its persistent chunk CTAs (ticket counter,
+// template in shared memory, double-buffered neighbour bases, one barrier per chunk).  Every block runs as kThreads OS threads with a
+// real barrier behind __syncthreads(); blocks run one after the other (legal for this kernel: a CTA that becomes resident late simply
+// draws fewer tickets).  Launch geometry as Solver::one_step sets it, with a handful of persistent CTAs.
+template <class L>
+void step_kernel(Ctx& c, int persistent_ctas) {
+  DevParams<double> p = c.params();
+  const int64_t nfast = c.v.n_fast_chunks;
+  p.gen_off = 0;
+  p.n_gen = static_cast<int32_t>(c.v.n_gen);
+  p.n_gen_blocks = static_cast<int32_t>((c.v.n_gen + kThreads - 1) / kThreads);
+  p.chunk_off = 0;
+  p.n_fast_chunks = static_cast<int32_t>(nfast);
+  p.n_fast_blocks = static_cast<int32_t>(nfast < persistent_ctas ? nfast : persistent_ctas);
+  p.ticket = &c.ticket;
+  p.ticket_base = c.ticket_next;
+  c.ticket_next += static_cast<unsigned long long>(nfast) + static_cast<unsigned long long>(p.n_fast_blocks);
+  const int grid = p.n_gen_blocks + p.n_fast_blocks;
+  blockDim.x = kThreads;
+  gridDim.x  = static_cast<unsigned>(grid);
+  pthread_barrier_init(&g_block_barrier, nullptr, kThreads);
+  g_block_barrier_on = true;
+  for(int b = 0; b < grid; ++b) {
+    blockIdx.x = static_cast<unsigned>(b);
+    std::vector<std::thread> th;
+    for(int t = 0; t < kThreads; ++t)
+      th.emplace_back([&p, t] {
+        threadIdx.x = static_cast<unsigned>(t);
+        k_step<L, double, true, COLL_BGK>(p);
+      });
+    for(auto& x : th) x.join();
+  }
+  g_block_barrier_on = false;
+  pthread_barrier_destroy(&g_block_barrier);
+}
+
 template <class L>
 void velocity_pack(Ctx& c, const int32_t* cells, int n, double* out) {
   const DevParams<double> p = c.params();
@@ -154,6 +192,8 @@ void kh_set_vrecv(void* p, const double* v, int64_t n) { static_cast<Ctx*>(p)->v
 void kh_gather_all(void* p, double* fold_out, double* mom_out) { auto* c = static_cast<Ctx*>(p); DISPATCH(c, gather_all<L>(*c, fold_out, mom_out)); }
 // one time step of the owned cells: A -> B (and vars), like the fused kernel
 void kh_update(void* p) { auto* c = static_cast<Ctx*>(p); DISPATCH(c, update<L>(*c)); }
+// the same step through the real kernel (generic blocks + persistent chunk CTAs)
+void kh_step_kernel(void* p, int persistent_ctas) { auto* c = static_cast<Ctx*>(p); DISPATCH(c, step_kernel<L>(*c, persistent_ctas)); }
 void kh_velocity_pack(void* p, const int32_t* cells, int n, double* out) { auto* c = static_cast<Ctx*>(p); DISPATCH(c, velocity_pack<L>(*c, cells, n, out)); }
 void kh_pressure_extrapolate(void* p) { auto* c = static_cast<Ctx*>(p); DISPATCH(c, pressure_extrapolate<L>(*c)); }
 void kh_halo_pack(void* p, const int64_t* index, int64_t n, double* out) {

@@ -24,6 +24,7 @@ def kh(tmp_path_factory):
     pkg = os.path.join(ROOT, "lbm_b200")
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
                            "-Wno-unused-variable", "-Wno-unused-but-set-variable", "-Wno-unknown-pragmas", "-I", os.path.join(HERE, "c", "fake_cuda"),
+                           "-DLBM_THREADS=32", "-pthread",  # 32 threads per block: enough for the NSEL + 1 loaders of a chunk, cheap to start
                            os.path.join(HERE, "c", "kernels_harness.cpp"), "-o", so, "-L", pkg, "-llbm_b200", f"-Wl,-rpath,{pkg}"])
     L = C.CDLL(so)
     vp, dp = C.c_void_p, C.POINTER(C.c_double)
@@ -41,6 +42,7 @@ def kh(tmp_path_factory):
     L.kh_set_vrecv.argtypes = [vp, vp, C.c_int64]
     L.kh_gather_all.argtypes = [vp, vp, vp]
     L.kh_update.argtypes = [vp]
+    L.kh_step_kernel.argtypes = [vp, C.c_int]
     L.kh_velocity_pack.argtypes = [vp, vp, C.c_int, vp]
     L.kh_pressure_extrapolate.argtypes = [vp]
     L.kh_halo_pack.argtypes = [vp, vp, C.c_int64, vp]
@@ -82,7 +84,7 @@ class Rank:
         self.solver.close()
 
 
-def emulate(L, spec, world, steps, oracle_mod):
+def emulate(L, spec, world, steps, oracle_mod, kernel=False):
     from cases3d import pressure_surfaces
     o = spec.apply_to(oracle_mod.Oracle(spec.ndim, spec.ndist, spec.nghbr, spec.omega))
     o.init()
@@ -96,7 +98,10 @@ def emulate(L, spec, world, steps, oracle_mod):
         for step in range(1, steps + 1):
             o.step(1)
             for rk in ranks:                                    # main kernel: every owned cell, A -> B
-                L.kh_update(rk.h)
+                if kernel:
+                    L.kh_step_kernel(rk.h, 3)                   # k_step itself: generic blocks + 3 persistent chunk CTAs
+                else:
+                    L.kh_update(rk.h)
             wires = {}
             for r, rk in enumerate(ranks):                      # k_halo_pack + k_velocity_pack, per peer in list order
                 so = vo = 0
@@ -171,3 +176,11 @@ def test_baseline_configs_on_the_device_code(name, world, kh, oracle_mod):
     stats = emulate(kh, build_case(name, 5), world, 4, oracle_mod)
     if world > 1:
         assert stats["ghost_blocks"] >= 0
+
+
+@pytest.mark.parametrize("world,shape,ndist", [(1, (24, 24, 24), 19), (2, (26, 24, 24), 19), (1, (16, 16, 16), 27), (2, (96, 64), 9)])
+def test_the_fused_kernel_itself_on_the_cpu(world, shape, ndist, kh, oracle_mod):
+    """k_step -- generic blocks and persistent chunk CTAs with the ticket counter, the template in shared memory and the per-chunk
+    barrier -- run as 32 OS threads per block: interior chunks, wall / edge / corner chunks, pressure-face chunks, ghost blocks."""
+    stats = emulate(kh, pressure_box(shape, ndist), world, 3, oracle_mod, kernel=True)
+    assert stats["fast"] > 0
