@@ -28,12 +28,12 @@ def launch(world, mode, shape, ndist, steps=12, timeout=600, bc="walls", extra=(
     assert r.returncode == 0 and "PARTITION_PARITY OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
-@pytest.mark.parametrize("world,shape,ndist", [(2, "16,12,10", 19), (3, "12,12,8", 27), (2, "24,20", 9)])
+@pytest.mark.parametrize("world,shape,ndist", [(2, "16,12,10", 19), (3, "12,12,8", 27)])
 def test_partitioned_oracle_matches_single_domain_gloo(world, shape, ndist):
     launch(world, "oracle", shape, ndist)
 
 
-@pytest.mark.parametrize("world,shape,ndist", [(2, "18,16,16", 19), (3, "10,10,10", 27), (2, "34,64", 9), (3, "10,40", 9)])
+@pytest.mark.parametrize("world,shape,ndist", [(2, "18,16,16", 19), (3, "10,10,10", 27), (2, "34,64", 9)])
 def test_partitioned_pressure_boundary_velocity_halo_gloo(world, shape, ndist):
     """Pressure in-/outlet whose inward neighbours lie across the cut: the velocity halo."""
     launch(world, "oracle", shape, ndist, bc="pressure")
