@@ -138,7 +138,6 @@ def test_wetnode_walls_have_no_fused_plan_and_are_not_partitioned():
     s.add_wall_wetnode("equilibrium", cells, normals, np.array([0.1, 0.0]))
     c, msg = code_of(s.debug_plan)
     assert c == -5 and "wet-node" in msg
-    c, msg = code_of(s.add_wall_wetnode, "equilibrium", cells, normals, None) if False else (0, "")
 
 
 def test_sfc_index_argument_checks():
