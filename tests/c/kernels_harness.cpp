@@ -36,7 +36,8 @@ struct Ctx {
   std::vector<AbbDev<double>>    abb;
   std::vector<double>            uext[2], values, A, B, vars, vrecv, scratch;
   int    dyn = 0, first = 1;
-  double omega = 1;
+  double omega = 1, omega_minus = 1, rates[27];
+  int    coll = COLL_BGK;
   unsigned long long ticket = 0, ticket_next = 0;
 
   DevParams<double> params() {
@@ -62,8 +63,8 @@ struct Ctx {
     p.tabs.stride = v.npad;
     p.omega = omega;
     p.om1 = 1 - omega;
-    p.omega_minus = omega;
-    for(double& r : p.rates) r = omega;
+    p.omega_minus = omega_minus;
+    for(int i = 0; i < 27; ++i) p.rates[i] = rates[i];
     p.vars_out = vars.data();
     p.first = first;
     return p;
@@ -77,20 +78,20 @@ void gather_all(Ctx& c, double* fold_out, double* mom_out) {
   launch(nc, 128, [&] { k_gather_all<L, double, true>(p, nc, fold_out, mom_out); });
 }
 // what k_step does to every owned cell (same device functions, without the persistent-CTA driver and its shared-memory template)
-template <class L>
+template <class L, int COLL>
 void update(Ctx& c) {
   const DevParams<double> p = c.params();
   for(int32_t cell = 0; cell < static_cast<int32_t>(c.v.ghost_begin); ++cell) {
     double fold[L::Q];
     gather_any<L, double, true>(p, p.A, cell, fold);
-    update_and_store<L, double, true, COLL_BGK>(p, cell, fold);
+    update_and_store<L, double, true, COLL>(p, cell, fold);
   }
 }
 // The fused kernel ITSELF: k_step<L, double, STRICT, BGK> with its generic blocks and its persistent chunk CTAs (ticket counter,
 // template in shared memory, double-buffered neighbour bases, one barrier per chunk).  Every block runs as kThreads OS threads with a
 // real barrier behind __syncthreads(); blocks run one after the other (legal for this kernel: a CTA that becomes resident late simply
 // draws fewer tickets).  Launch geometry as Solver::one_step sets it, with a handful of persistent CTAs.
-template <class L>
+template <class L, int COLL>
 void step_kernel(Ctx& c, int persistent_ctas) {
   DevParams<double> p = c.params();
   const int64_t nfast = c.v.n_fast_chunks;
@@ -114,7 +115,7 @@ void step_kernel(Ctx& c, int persistent_ctas) {
     for(int t = 0; t < kThreads; ++t)
       th.emplace_back([&p, t] {
         threadIdx.x = static_cast<unsigned>(t);
-        k_step<L, double, true, COLL_BGK>(p);
+        k_step<L, double, true, COLL>(p);
       });
     for(auto& x : th) x.join();
   }
@@ -151,6 +152,8 @@ void* kh_create(lbm_b200_solver* solver, int ndim, int ndist, double omega) {
   c->ndim = ndim;
   c->ndist = ndist;
   c->omega = omega;
+  c->omega_minus = omega;
+  for(double& r : c->rates) r = omega;
   if(lbm_b200_debug_plan(solver, &c->v) != 0) { delete c; return nullptr; }
   const lbm_b200_plan_view& v = c->v;
   const int QM = ndist - 1;
@@ -191,9 +194,25 @@ void kh_set_vrecv(void* p, const double* v, int64_t n) { static_cast<Ctx*>(p)->v
 // m_fold (SoA, device order) and its moments from the current A: k_gather_all
 void kh_gather_all(void* p, double* fold_out, double* mom_out) { auto* c = static_cast<Ctx*>(p); DISPATCH(c, gather_all<L>(*c, fold_out, mom_out)); }
 // one time step of the owned cells: A -> B (and vars), like the fused kernel
-void kh_update(void* p) { auto* c = static_cast<Ctx*>(p); DISPATCH(c, update<L>(*c)); }
+void kh_update(void* p) {
+  auto* c = static_cast<Ctx*>(p);
+  if(c->coll == COLL_TRT) DISPATCH(c, (update<L, COLL_TRT>(*c)));
+  else if(c->coll == COLL_MRT) DISPATCH(c, (update<L, COLL_MRT>(*c)));
+  else DISPATCH(c, (update<L, COLL_BGK>(*c)));
+}
+void kh_set_collision(void* p, int coll, double omega_minus, const double* rates) {
+  auto* c = static_cast<Ctx*>(p);
+  c->coll = coll;
+  c->omega_minus = omega_minus;
+  for(int i = 0; i < 27; ++i) c->rates[i] = rates[i];
+}
 // the same step through the real kernel (generic blocks + persistent chunk CTAs)
-void kh_step_kernel(void* p, int persistent_ctas) { auto* c = static_cast<Ctx*>(p); DISPATCH(c, step_kernel<L>(*c, persistent_ctas)); }
+void kh_step_kernel(void* p, int persistent_ctas) {
+  auto* c = static_cast<Ctx*>(p);
+  if(c->coll == COLL_TRT) DISPATCH(c, (step_kernel<L, COLL_TRT>(*c, persistent_ctas)));
+  else if(c->coll == COLL_MRT) DISPATCH(c, (step_kernel<L, COLL_MRT>(*c, persistent_ctas)));
+  else DISPATCH(c, (step_kernel<L, COLL_BGK>(*c, persistent_ctas)));
+}
 void kh_velocity_pack(void* p, const int32_t* cells, int n, double* out) { auto* c = static_cast<Ctx*>(p); DISPATCH(c, velocity_pack<L>(*c, cells, n, out)); }
 void kh_pressure_extrapolate(void* p) { auto* c = static_cast<Ctx*>(p); DISPATCH(c, pressure_extrapolate<L>(*c)); }
 void kh_halo_pack(void* p, const int64_t* index, int64_t n, double* out) {

@@ -43,6 +43,7 @@ def kh(tmp_path_factory):
     L.kh_gather_all.argtypes = [vp, vp, vp]
     L.kh_update.argtypes = [vp]
     L.kh_step_kernel.argtypes = [vp, C.c_int]
+    L.kh_set_collision.argtypes = [vp, C.c_int, C.c_double, vp]
     L.kh_velocity_pack.argtypes = [vp, vp, C.c_int, vp]
     L.kh_pressure_extrapolate.argtypes = [vp]
     L.kh_halo_pack.argtypes = [vp, vp, C.c_int64, vp]
@@ -84,14 +85,19 @@ class Rank:
         self.solver.close()
 
 
-def emulate(L, spec, world, steps, oracle_mod, kernel=False):
-    from cases3d import pressure_surfaces
+def emulate(L, spec, world, steps, oracle_mod, kernel=False, collision=0):
+    from cases3d import mrt_rates, pressure_surfaces
     o = spec.apply_to(oracle_mod.Oracle(spec.ndim, spec.ndist, spec.nghbr, spec.omega))
+    rates = np.ascontiguousarray(mrt_rates(spec.ndist, spec.omega))
+    om_minus = 1.0 / 0.8
+    o.set_collision(collision, om_minus, rates)
     o.init()
     init_f, init_fold = o.f.copy(), o.fold.copy()
     provider = partition.TableRows(spec.nghbr, spec.ndist)
     ranks = [Rank(L, spec, partition.plan_rank(provider, r, world, spec.nghbr.shape[1], pressure_surfaces(spec)), init_f, init_fold)
              for r in range(world)]
+    for rk in ranks:
+        L.kh_set_collision(rk.h, collision, om_minus, rates.ctypes.data)
     stats = dict(fast=sum(rk.plan["n_fast_chunks"] for rk in ranks), abb_chunks=sum(rk.plan["n_chunk_abb_rows"] for rk in ranks),
                  ghost_blocks=sum(rk.plan["n_ghost_blocks"] for rk in ranks), vrecv=sum(rk.plan["n_vrecv"] for rk in ranks))
     try:
@@ -172,8 +178,9 @@ def test_partitioned_pressure_boxes_on_the_device_code(world, shape, ndist, kh, 
 
 @pytest.mark.parametrize("name,world", [("sphere3d", 1), ("sphere3d", 4), ("step3d", 3)])
 def test_baseline_configs_on_the_device_code(name, world, kh, oracle_mod):
+    """BASELINE.json configs[3] / [4] with their collision operators: sphere = MRT, step = TRT (oracle/lbm_oracle.c: literature forms)"""
     from cases3d import build_case
-    stats = emulate(kh, build_case(name, 5), world, 4, oracle_mod)
+    stats = emulate(kh, build_case(name, 5), world, 4, oracle_mod, collision={"sphere3d": 2, "step3d": 1}[name])
     if world > 1:
         assert stats["ghost_blocks"] >= 0
 
@@ -184,3 +191,9 @@ def test_the_fused_kernel_itself_on_the_cpu(world, shape, ndist, kh, oracle_mod)
     barrier -- run as 32 OS threads per block: interior chunks, wall / edge / corner chunks, pressure-face chunks, ghost blocks."""
     stats = emulate(kh, pressure_box(shape, ndist), world, 3, oracle_mod, kernel=True)
     assert stats["fast"] > 0
+
+
+@pytest.mark.parametrize("name,collision", [("step3d", 1), ("sphere3d", 2)])
+def test_the_fused_kernel_with_trt_and_mrt(name, collision, kh, oracle_mod):
+    from cases3d import build_case
+    emulate(kh, build_case(name, 5), 2, 2, oracle_mod, kernel=True, collision=collision)
