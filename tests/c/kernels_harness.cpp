@@ -39,6 +39,7 @@ struct Ctx {
   double omega = 1, omega_minus = 1, rates[27];
   int    coll = COLL_BGK;
   unsigned long long ticket = 0, ticket_next = 0;
+  unsigned long long ticket2[2] = {0, 0}, ticket2_next[2] = {0, 0}; // the two launch classes of the overlapped path
 
   DevParams<double> params() {
     DevParams<double> p{};
@@ -123,6 +124,44 @@ void step_kernel(Ctx& c, int persistent_ctas) {
   pthread_barrier_destroy(&g_block_barrier);
 }
 
+// The overlapped path of Solver::one_step: two launches of the same kernel -- the outer cells (chunks / generic cells holding a
+// population a peer needs, placed first in the device layout) with their own ticket counter, then the inner ones.
+template <class L, int COLL>
+void step_kernel_split(Ctx& c, int persistent_ctas) {
+  const DevParams<double> base = c.params();
+  auto one = [&](int64_t g0, int64_t ng, int64_t c0, int64_t ncnk, int cls) {
+    DevParams<double> q = base;
+    q.gen_off       = static_cast<int32_t>(g0);
+    q.n_gen         = static_cast<int32_t>(ng);
+    q.n_gen_blocks  = static_cast<int32_t>((ng + kThreads - 1) / kThreads);
+    q.chunk_off     = static_cast<int32_t>(c0);
+    q.n_fast_chunks = static_cast<int32_t>(ncnk);
+    q.n_fast_blocks = static_cast<int32_t>(ncnk < persistent_ctas ? ncnk : persistent_ctas);
+    q.ticket        = &c.ticket2[cls];
+    q.ticket_base   = c.ticket2_next[cls];
+    c.ticket2_next[cls] += static_cast<unsigned long long>(ncnk) + static_cast<unsigned long long>(q.n_fast_blocks);
+    const int grid = q.n_gen_blocks + q.n_fast_blocks;
+    blockDim.x = kThreads;
+    gridDim.x  = static_cast<unsigned>(grid);
+    pthread_barrier_init(&g_block_barrier, nullptr, kThreads);
+    g_block_barrier_on = true;
+    for(int b = 0; b < grid; ++b) {
+      blockIdx.x = static_cast<unsigned>(b);
+      std::vector<std::thread> th;
+      for(int t = 0; t < kThreads; ++t)
+        th.emplace_back([&q, t] {
+          threadIdx.x = static_cast<unsigned>(t);
+          k_step<L, double, true, COLL>(q);
+        });
+      for(auto& x : th) x.join();
+    }
+    g_block_barrier_on = false;
+    pthread_barrier_destroy(&g_block_barrier);
+  };
+  one(0, c.v.n_gen_outer, 0, c.v.n_fast_outer, 1);
+  one(c.v.n_gen_outer, c.v.n_gen - c.v.n_gen_outer, c.v.n_fast_outer, c.v.n_fast_chunks - c.v.n_fast_outer, 0);
+}
+
 template <class L>
 void velocity_pack(Ctx& c, const int32_t* cells, int n, double* out) {
   const DevParams<double> p = c.params();
@@ -199,6 +238,13 @@ void kh_update(void* p) {
   if(c->coll == COLL_TRT) DISPATCH(c, (update<L, COLL_TRT>(*c)));
   else if(c->coll == COLL_MRT) DISPATCH(c, (update<L, COLL_MRT>(*c)));
   else DISPATCH(c, (update<L, COLL_BGK>(*c)));
+}
+// outer launch, then inner launch (the overlapped path of a partitioned run)
+void kh_step_kernel_split(void* p, int persistent_ctas) {
+  auto* c = static_cast<Ctx*>(p);
+  if(c->coll == COLL_TRT) DISPATCH(c, (step_kernel_split<L, COLL_TRT>(*c, persistent_ctas)));
+  else if(c->coll == COLL_MRT) DISPATCH(c, (step_kernel_split<L, COLL_MRT>(*c, persistent_ctas)));
+  else DISPATCH(c, (step_kernel_split<L, COLL_BGK>(*c, persistent_ctas)));
 }
 void kh_set_collision(void* p, int coll, double omega_minus, const double* rates) {
   auto* c = static_cast<Ctx*>(p);

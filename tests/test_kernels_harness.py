@@ -43,6 +43,7 @@ def kh(tmp_path_factory):
     L.kh_gather_all.argtypes = [vp, vp, vp]
     L.kh_update.argtypes = [vp]
     L.kh_step_kernel.argtypes = [vp, C.c_int]
+    L.kh_step_kernel_split.argtypes = [vp, C.c_int]
     L.kh_set_collision.argtypes = [vp, C.c_int, C.c_double, vp]
     L.kh_velocity_pack.argtypes = [vp, vp, C.c_int, vp]
     L.kh_pressure_extrapolate.argtypes = [vp]
@@ -104,7 +105,9 @@ def emulate(L, spec, world, steps, oracle_mod, kernel=False, collision=0):
         for step in range(1, steps + 1):
             o.step(1)
             for rk in ranks:                                    # main kernel: every owned cell, A -> B
-                if kernel:
+                if kernel == "split":
+                    L.kh_step_kernel_split(rk.h, 3)             # outer launch, then inner launch (overlapped path of one_step)
+                elif kernel:
                     L.kh_step_kernel(rk.h, 3)                   # k_step itself: generic blocks + 3 persistent chunk CTAs
                 else:
                     L.kh_update(rk.h)
@@ -197,3 +200,13 @@ def test_the_fused_kernel_itself_on_the_cpu(world, shape, ndist, kh, oracle_mod)
 def test_the_fused_kernel_with_trt_and_mrt(name, collision, kh, oracle_mod):
     from cases3d import build_case
     emulate(kh, build_case(name, 5), 2, 2, oracle_mod, kernel=True, collision=collision)
+
+
+@pytest.mark.parametrize("world,shape,ndist,periodic", [(2, (32, 16, 16), 19, True), (4, (32, 32, 16), 19, True), (2, (16, 16, 24), 27, True)])
+def test_outer_and_inner_launch_of_the_overlapped_path(world, shape, ndist, periodic, kh, oracle_mod):
+    """The benchmark box cut into SFC ranges, stepped the way the overlapped path does it: outer cells first (their own ticket
+    counter), then the inner cells; wall / edge chunks next to ghost blocks.  Bit-identical to the single-domain oracle."""
+    from test_plan_cpu import box_spec
+    spec, _ = box_spec(shape, ndist, (True, False, False), ("+z", (0.05, 0.0, 0.0)))
+    stats = emulate(kh, spec, world, 3, oracle_mod, kernel="split")
+    assert stats["fast"] > 0 and stats["ghost_blocks"] > 0
