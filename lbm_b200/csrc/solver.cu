@@ -465,7 +465,11 @@ struct Solver final : SolverBase {
       }
     };
     const bool has_aux = d_force.n > 0 || d_perp.n > 0 || d_abb.n > 0 || (vout != nullptr && d_varfix.n > 0);
-    const bool overlap = !in.peers.empty() && !has_aux && !has_velocity_halo() && overlap_enabled;
+    // forcing and the periodic-with-pressure values write populations of buffer B that a peer may need: they must precede the pack.
+    // The pressure extrapolation and the m_vars fix-ups only read buffer A and write uext / vars, so they do not stand in the way of
+    // the overlap (unless the extrapolation itself waits for this step's velocity halo).
+    const bool aux_before_exchange = d_force.n > 0 || d_perp.n > 0;
+    const bool overlap = !in.peers.empty() && !aux_before_exchange && !has_velocity_halo() && overlap_enabled;
     if(halo_pending) { // ghosts of the buffer we are about to read were filled on the communication stream
       CUDA_TRY(cudaStreamWaitEvent(stream, ev_halo, 0));
       halo_pending = false;
@@ -488,6 +492,13 @@ struct Solver final : SolverBase {
       launch(plan.n_gen_outer, plan.n_gen - plan.n_gen_outer, plan.n_fast_outer, plan.n_fast_chunks - plan.n_fast_outer, max_resident, 0);
       if(time_main) cudaEventRecord(evm1, stream);
       CUDA_TRY(cudaGetLastError());
+      if(has_aux) { // pressure boundary present: extrapolation + m_vars fix-ups behind the inner launch, the exchange still in flight
+        const int nd = dyn ^ 1;
+        bool      dyn_written = false;
+        rc = cfg.arithmetic == LBM_B200_STRICT ? aux_kernels<true>(p, vout, nd, 2, &dyn_written) : aux_kernels<false>(p, vout, nd, 2, &dyn_written);
+        if(rc != LBM_B200_OK) return rc;
+        if(dyn_written) dyn = nd;
+      }
     } else {
       launch(0, plan.n_gen, 0, plan.n_fast_chunks, max_resident, 0);
       if(time_main) cudaEventRecord(evm1, stream);
