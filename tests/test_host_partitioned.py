@@ -54,3 +54,27 @@ def test_unsupported_configurations_are_refused(tmp_path, monkeypatch):
     with pytest.raises(RuntimeError) as e:
         host_api.partitioned_plan(path, 0, 2, 3, 27)
     assert "not partitioned" in str(e.value)
+
+
+def test_lbm_executable_reads_its_rank_from_the_environment(tmp_path):
+    """`lbm` as rank 1 of 2: the grid generator skips the whole-tree build, the solver partitions through the on-demand provider and
+    asks for CUDA device LOCAL_RANK -- on a machine without a GPU that is where it must stop, loudly (no CPU fallback)."""
+    import os
+    import subprocess
+
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the run would wait for its peer")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "lbm_b200", "lbm")
+    path = tmp_path / "case.json"
+    path.write_text(json.dumps(cases.CONFIGS["step3d"](4)))
+    env = dict(os.environ, LBM_B200_RANK="1", LBM_B200_WORLD="2", LBM_B200_LOCAL_RANK="1", LBM_B200_ID_FILE=str(tmp_path / "id"))
+    r = subprocess.run([exe, str(path)], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 255
+    assert "partitioned run: grid rows are generated per rank" in r.stdout
+    assert "Rank 1 of 2: partitioned run" in r.stderr and "no CUDA device 1" in r.stderr
+    # the same file without rank variables is a single-process run and asks for device 0
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([exe, str(path)], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 255 and "no CUDA device 0" in r.stderr and "partitioned run" not in r.stdout
