@@ -325,12 +325,12 @@ def config_dict(args, note):
                           "sphere; BASELINE.json configs[3], 3D form of test/sphere/sphere_ns.json)",
                 "step": "channel with a step (block on the upper wall, pressure in-/outlet, bounce-back walls; BASELINE.json configs[4], "
                         "3D form of test/step/step_ns.json)"}[args.workload]
-        return {"workload": f"{args.workload}-3D {args.size}^3 {args.lattice} {args.collision.upper()} fp64: {what}, omega={OMEGA:.6f}",
+        return {"workload": f"{args.workload}-3D {args.size}^3 {args.lattice} {args.collision.upper()} {getattr(args, 'precision', 'fp64')}: {what}, omega={OMEGA:.6f}",
                 "lattice": args.lattice, "collision": args.collision, "arithmetic": args.arithmetic,
                 "l2_policy": "inputs larger than L2 (no flush needed)" if args.size >= 128 else "SMALL CASE: fits L2, not a bandwidth measurement",
                 "parallelism": (f"one cube of {args.size}^3 cells cut into {args.gpus} contiguous SFC ranges (fixed total size), ncclSend/ncclRecv "
                                 f"halo exchange of outgoing populations every step") if args.gpus > 1 else "single GPU", "note": note}
-    return {"workload": f"bench-3D cube {args.size}^{ndim} {args.lattice} BGK fp64 (BASELINE.json configs[2]; SURVEY 8d S3): "
+    return {"workload": f"bench-3D cube {args.size}^{ndim} {args.lattice} BGK {getattr(args, 'precision', 'fp64')} (BASELINE.json configs[2]; SURVEY 8d S3): "
                         f"periodic x, bounce-back walls, moving lid u={LID_U}, omega={OMEGA:.6f}",
             "cells_per_gpu": args.size ** ndim, "lattice": args.lattice, "collision": "bgk", "arithmetic": args.arithmetic,
             "l2_policy": "inputs larger than L2 (no flush needed)", "parallelism": (f"one box of {'x'.join(map(str, global_shape(args.size, ndim, args.gpus)))} cells cut into {args.gpus} contiguous "
@@ -361,8 +361,9 @@ def run_ours(args):
     n_local = wl["nghbr"].shape[0]
     stream = torch.cuda.current_stream().cuda_stream
     coll, om_minus, rates = collision_setup(args.collision)
+    precision = lbm_b200.FP32 if args.precision == "fp32" else lbm_b200.FP64
     s = lbm_b200.Solver(ndim, ndist, wl["nghbr"], OMEGA, arithmetic=arithmetic, device=local, track_vars=0, stream=stream,
-                        collision=coll, omega_minus=om_minus, mrt_rates=rates)
+                        collision=coll, omega_minus=om_minus, mrt_rates=rates, precision=precision)
     apply_bcs(s, wl)
     if world > 1:
         from lbm_b200.capi import comm_unique_id
@@ -454,7 +455,7 @@ def run_ours(args):
     line = {
         "metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak" if args.workload == "box" else "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f64", "data": "synthetic",
         "config": config_dict(args, f"{st0['cells_fast']} of {st0['ncells']} cells on the index-free chunk path; setup {t_setup:.1f} s"),
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
@@ -472,6 +473,9 @@ def main():
                          "--size = cells per side of the whole cube")
     ap.add_argument("--lattice", default="D3Q19", choices=sorted(LATTICES))
     ap.add_argument("--arithmetic", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"],
+                    help="fp64: the reference's arithmetic type and the metric's configuration (default); fp32: the opt-in of BASELINE.json's "
+                         "north_star (populations in float, 2*Q*4 algorithmic bytes per cell; tolerance stated in tests/test_gpu_parity.py)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-size", type=int, default=128, dest="cpu_size")
     ap.add_argument("--cpu-budget", type=float, default=15.0, dest="cpu_budget")
