@@ -37,3 +37,16 @@ def test_host_grid_tables_bit_exact(name, tmp_path):
         assert np.array_equal(cells, gold[f"surf{k}_cells"].astype(np.int64)), f"surface {sname}: cell list differs"
         assert np.array_equal(normals, gold[f"surf{k}_normals"]), f"surface {sname}: normals differ"
     assert g["cell_length"] == spec.cell_length
+
+
+def test_reference_configurations_that_abort_abort_the_same_way(tmp_path, monkeypatch):
+    """test/poiseuille/poiseuille_eq.json and test/step/step_ns_double.json name periodic connections that do not exist: the reference
+    ends with TERMM(-1, "Invalid periodic setup!") (src/cartesiangrid.h:636).  Same message here."""
+    broken = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "broken_configs.json")))
+    monkeypatch.chdir(tmp_path)
+    for name, item in broken.items():
+        cfg = tmp_path / f"{name}.json"
+        cfg.write_text(json.dumps(item["config"]))
+        with pytest.raises(RuntimeError) as e:
+            host_api.build_grid(str(cfg))
+        assert item["error"] in str(e.value), name
