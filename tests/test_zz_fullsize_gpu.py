@@ -1,0 +1,80 @@
+"""Parity at BASELINE.json's full size (configs[2]: 256^3 D3Q19 BGK fp64, the bench workload) through size-independent properties -- the
+oracle cannot run 1.7e7 cells in seconds, these can be checked without it:
+  * the workload is invariant in x (periodic in x, boundary conditions independent of x, uniform start): every x-column executes the
+    same arithmetic, so the fields must be BITWISE identical along x -- in STRICT and in FAST arithmetic.  An indexing slip in a chunk
+    template, a wall descriptor or a link code breaks this immediately;
+  * bounce-back walls reflect and the moving lid's addends cancel pairwise: total mass is conserved to rounding;
+  * FAST agrees with STRICT within 1e-12 relative (BASELINE.json north_star).
+Written late in round 1 (no GPU time left): sorts behind the verified tests."""
+import numpy as np
+import pytest
+
+import lbm_b200
+from lbm_b200.capi import box_topology
+
+pytestmark = pytest.mark.gpu
+
+SIZE, STEPS = 256, 20
+
+
+def s3_solver(arithmetic):
+    """the bench workload, set up like bench.py: periodic x, bounce-back walls on -y/+y/-z, moving lid on +z"""
+    shape = (SIZE,) * 3
+    nghbr, _, coords = box_topology(shape, (1, 0, 0), want_center=False, want_coords=True)
+    s = lbm_b200.Solver(3, 19, nghbr, 1.0 / 0.6, arithmetic=arithmetic, track_vars=0)
+    names = ["-x", "+x", "-y", "+y", "-z", "+z"]
+    for d, nm in sorted(enumerate(names), key=lambda t: t[1]):
+        cells = np.nonzero(nghbr[:, d] < 0)[0].astype(np.int64)
+        if len(cells) == 0:
+            continue
+        normal = np.zeros(3)
+        normal[d // 2] = -1.0 if d % 2 == 0 else 1.0
+        normals = np.tile(normal, (len(cells), 1))
+        if nm == "+z":
+            s.add_dirichlet_bb(cells, normals, np.array([0.05, 0.0, 0.0]))
+        else:
+            s.add_wall_bb(cells, normals, 0.0)
+    del nghbr
+    s.init()
+    return s, coords
+
+
+def columns(m, coords):
+    """[y, z, x, var] view of a field given in cell-list order"""
+    out = np.empty((SIZE, SIZE, SIZE, m.shape[1]))
+    out[coords[:, 1], coords[:, 2], coords[:, 0]] = m
+    return out
+
+
+@pytest.fixture(scope="module")
+def runs():
+    res = {}
+    for name, arith in (("strict", lbm_b200.STRICT), ("fast", lbm_b200.FAST)):
+        s, coords = s3_solver(arith)
+        st = s.stats()
+        s.step(STEPS)
+        res[name] = dict(m=s.moments(), coords=coords, fast=st["cells_fast"], n=st["ncells"])
+        s.close()
+    return res
+
+
+@pytest.mark.parametrize("name", ["strict", "fast"])
+def test_fields_are_bitwise_invariant_along_x(name, runs):
+    r = runs[name]
+    assert r["n"] == SIZE ** 3 and r["fast"] >= 0.99 * r["n"]          # the index-free chunk path carries the workload
+    f = columns(r["m"], r["coords"])
+    assert np.isfinite(f).all()
+    assert np.array_equal(f, np.broadcast_to(f[:, :, :1, :], f.shape)), "the x-invariant workload lost its invariance"
+    assert np.max(np.abs(f[..., 0])) > 1e-4                              # the lid has set the fluid in motion: not a trivial state
+
+
+@pytest.mark.parametrize("name", ["strict", "fast"])
+def test_total_mass_is_conserved(name, runs):
+    rho = runs[name]["m"][:, 3]
+    assert abs(np.sum(rho) / SIZE ** 3 - 1.0) < 1e-12
+
+
+def test_fast_agrees_with_strict(runs):
+    a, b = runs["fast"]["m"], runs["strict"]["m"]
+    assert np.max(np.abs(a[:, 3] - b[:, 3])) < 1e-12                     # density, relative to rho = 1
+    assert np.max(np.abs(a[:, :3] - b[:, :3])) < 1e-12 / np.sqrt(3.0)   # velocity: 1e-12 of the lattice speed of sound
