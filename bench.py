@@ -204,12 +204,26 @@ def ncu_traffic(lattice, size):
     return None
 
 
-def collision_setup(name):
-    """(C ABI collision id, omega_minus, per-pair MRT rates) of a workload's collision operator.  TRT: odd-moment rate from the
-    'magic' parameter 3/16; MRT: per-direction-pair rates, even part relaxed with omega, odd part with the TRT rate."""
+def mrt_kinds(lattice):
+    """kind of every moment of the MRT basis (0 conserved, 1 shear, 2 bulk, 3 ghost), read from the generated table header so that the
+    reference arm does not have to load the CUDA library for it"""
+    import re
+    text = open(os.path.join(ROOT, "oracle", "mrt_tables.h")).read()
+    m = re.search(r"#define LBM_MRT_%s_KIND \{([^}]*)\}" % lattice, text)
+    return np.array([int(x) for x in m.group(1).split(",")])
+
+
+def collision_setup(name, lattice):
+    """(C ABI collision id, omega_minus, MRT rates) of a workload's collision operator.  TRT: odd-moment rate from the 'magic' parameter
+    3/16.  MRT (moment space): shear moments relax with omega (same viscosity as the BGK / TRT runs), the bulk moment
+    with 1.19, the ghost moments with the d'Humieres et al. (2002) values 1.2 / 1.4 / 1.98 in turn -- all conserved moments untouched."""
     from lbm_b200.cases import trt_omega_minus
     om_minus = trt_omega_minus(OMEGA)
-    rates = np.array([OMEGA if i % 2 == 0 else om_minus for i in range(27)])
+    kinds = mrt_kinds(lattice)
+    rates = np.full(27, OMEGA)
+    rates[:len(kinds)][kinds == 2] = 1.19
+    ghost = np.nonzero(kinds == 3)[0]
+    rates[ghost] = np.array([1.2, 1.4, 1.98])[np.arange(len(ghost)) % 3]
     return {"bgk": 0, "trt": 1, "mrt": 2}[name], om_minus, rates
 
 
@@ -219,7 +233,7 @@ def cpu_sample(lattice, sample_size, budget_s, omp_collide=False, workload_name=
     wl = workload(sample_size, lattice) if workload_name == "box" else case_workload(workload_name, sample_size)
     o = oracle.Oracle(wl["ndim"], wl["ndist"], wl["nghbr"], OMEGA)
     if workload_name != "box":
-        coll, om_minus, rates = collision_setup(wl["collision"])
+        coll, om_minus, rates = collision_setup(wl["collision"], wl["lattice"])
         o.set_collision(coll, om_minus, rates)
     apply_bcs(o, wl)
     o.set_omp_collide(omp_collide)
@@ -293,7 +307,7 @@ def run_reference(args):
         args.lattice, args.collision = wl["lattice"], wl["collision"]
     o = oracle.Oracle(wl["ndim"], wl["ndist"], wl["nghbr"], OMEGA)
     if args.workload != "box":
-        coll, om_minus, rates = collision_setup(args.collision)
+        coll, om_minus, rates = collision_setup(args.collision, args.lattice)
         o.set_collision(coll, om_minus, rates)
     apply_bcs(o, wl)
     o.init()
@@ -360,7 +374,7 @@ def run_ours(args):
     n = wl["n_owned"]
     n_local = wl["nghbr"].shape[0]
     stream = torch.cuda.current_stream().cuda_stream
-    coll, om_minus, rates = collision_setup(args.collision)
+    coll, om_minus, rates = collision_setup(args.collision, args.lattice)
     precision = lbm_b200.FP32 if args.precision == "fp32" else lbm_b200.FP64
     s = lbm_b200.Solver(ndim, ndist, wl["nghbr"], OMEGA, arithmetic=arithmetic, device=local, track_vars=0, stream=stream,
                         collision=coll, omega_minus=om_minus, mrt_rates=rates, precision=precision)

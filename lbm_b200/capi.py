@@ -50,7 +50,56 @@ class PlanView(C.Structure):
         ("values", C.POINTER(C.c_double)), ("n_values", C.c_int64), ("stale_ref", C.POINTER(C.c_int64)), ("n_stale", C.c_int64),
         ("send_index", C.POINTER(C.c_int64)), ("n_send", C.c_int64), ("recv_index", C.POINTER(C.c_int64)), ("n_recv", C.c_int64),
         ("vsend_cells", C.POINTER(C.c_int32)), ("n_vsend", C.c_int64), ("n_vrecv", C.c_int64),
-        ("chunk_abb_base", C.POINTER(C.c_int32)), ("chunk_abb", C.POINTER(C.c_int32)), ("n_chunk_abb_rows", C.c_int64)]
+        ("chunk_abb_base", C.POINTER(C.c_int32)), ("chunk_abb", C.POINTER(C.c_int32)), ("n_chunk_abb_rows", C.c_int64),
+        ("perm_end", C.c_int64), ("gb_begin", C.c_int64), ("gb_end", C.c_int64), ("layout", C.POINTER(C.c_int32))]
+
+
+def mrt_moment_kinds(ndim, ndist):
+    """kind of every moment of the MRT basis: 0 conserved, 1 shear, 2 bulk, 3 ghost (lbm_b200_mrt_moments)"""
+    lib = load_library()
+    kinds = (C.c_int32 * 27)()
+    rc = lib.lbm_b200_mrt_moments(int(ndim), int(ndist), kinds)
+    if rc != 0:
+        raise LbmB200Error(rc, lib.lbm_b200_last_error().decode())
+    return np.array(kinds[:ndist], dtype=np.int32)
+
+
+def mrt_rates(ndim, ndist, shear, bulk=None, ghost=None):
+    """mrt_rates array for Solver(collision=MRT): `shear` sets the viscosity (= the BGK omega of the same viscosity); bulk / ghost
+    default to the shear rate (then the operator is BGK); ghost may be a sequence, one rate per ghost moment in basis order"""
+    kinds = mrt_moment_kinds(ndim, ndist)
+    rates = np.full(27, float(shear))
+    rates[:ndist][kinds == 2] = float(shear if bulk is None else bulk)
+    if ghost is not None:
+        g = np.atleast_1d(np.asarray(ghost, dtype=np.float64))
+        idx = np.nonzero(kinds == 3)[0]
+        rates[idx] = g[np.arange(len(idx)) % len(g)]
+    return rates
+
+
+def pop_slot(plan, j, cells):
+    """Position of device cells `cells` inside the population array of direction j (per-direction in-chunk layouts,
+    include/lbm_b200.h: lbm_b200_plan_view.layout).  `plan` is the dict Solver.debug_plan() returns."""
+    cells = np.asarray(cells, dtype=np.int64)
+    lay = int(plan["layout"][j])
+    if lay == 0:
+        return cells.copy()
+    inblock = (cells < plan["perm_end"]) | ((cells >= plan["gb_begin"]) & (cells < plan["gb_end"]))
+    o = cells & 511
+    perm = ((o >> 3) | ((o & 7) << 6)) if lay == 1 else ((o >> 6) | ((o & 63) << 3))
+    return np.where(inblock, (cells & ~np.int64(511)) | perm, cells)
+
+
+def pop_gather(plan, arr, cells):
+    """arr: population array [Q, npad] in device layout -> [len(cells), Q] values of the device cells `cells`"""
+    q = arr.shape[0]
+    return np.stack([arr[j, pop_slot(plan, j, cells)] for j in range(q)], axis=1)
+
+
+def pop_scatter(plan, arr, cells, values):
+    """inverse of pop_gather: values [len(cells), Q] -> arr [Q, npad]"""
+    for j in range(arr.shape[0]):
+        arr[j, pop_slot(plan, j, cells)] = values[:, j]
 
 
 class PartitionView(C.Structure):
@@ -75,7 +124,7 @@ def build(force=False):
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     if force and os.path.exists(library_path()):
         os.remove(library_path())
-    subprocess.check_call(["make", "-s", "-C", os.path.join(_HERE, "csrc")])
+    subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(_HERE, "csrc")])
     return library_path()
 
 
@@ -101,6 +150,7 @@ def load_library():
     L.lbm_b200_default_config.argtypes = [C.POINTER(Config)]
     L.lbm_b200_default_config.restype = None
     L.lbm_b200_create.argtypes = [C.POINTER(Config), i64, C.POINTER(vp)]
+    L.lbm_b200_mrt_moments.argtypes = [i32, i32, C.POINTER(C.c_int32)]
     L.lbm_b200_destroy.argtypes = [vp]
     L.lbm_b200_destroy.restype = None
     L.lbm_b200_set_topology.argtypes = [vp, pi64, i32]
@@ -283,6 +333,7 @@ class Solver:
         out["vsend_cells"] = arr(v.vsend_cells, v.n_vsend)
         out["chunk_abb_base"] = arr(v.chunk_abb_base, v.n_fast_chunks)
         out["chunk_abb"] = arr(v.chunk_abb, v.n_chunk_abb_rows * v.chunk, (int(v.n_chunk_abb_rows), int(v.chunk)))
+        out["layout"] = arr(v.layout, self.ndist)
         return out
 
     # ---- run

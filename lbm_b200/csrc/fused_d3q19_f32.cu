@@ -1,0 +1,6 @@
+// fused solver, Lattice<3, 19>, float: one translation unit per instantiation (parallel build)
+#include "solver_fused.cuh"
+
+namespace lbm_impl {
+SolverBase* make_fused_d3q19_f32() { return new Solver<lbm::Lattice<3, 19>, float>(); }
+} // namespace lbm_impl

@@ -21,6 +21,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstring>
 
 #include "lattice.h"
 
@@ -50,6 +51,7 @@ struct SlotTables {
   const Real*            uext;   // [n_abb][3]  extrapolated velocity of every pressure entry (current)
   const Real*            values; // static + dynamic slot values (current)
   int64_t                stride;
+  PermRange              pr;     // which device cells sit in chunk-shaped blocks (per-direction in-chunk layouts, lattice.h)
 };
 
 template <class Real>
@@ -57,6 +59,7 @@ struct DevParams {
   const Real* A;   // populations before the step (post-collision of the previous step), SoA [Q][stride]
   Real*       B;   // populations after the step
   int64_t     stride;
+  PermRange   pr;  // device cells below perm_end and in [gb_begin, gb_end) are stored in the per-direction in-chunk layouts
   // fast chunks
   const uint16_t* tmpl;     // [(Q-1)][CHUNK]
   const int32_t*  chunk_nb; // [n_fast_chunks][NSEL + 1]: neighbour chunk bases (-1 = wall), wall descriptor id
@@ -82,6 +85,12 @@ struct DevParams {
   Real*   vars_out; // SoA [NVAR][stride] or nullptr
   int32_t first;    // 1: step 0 -- m_fold is the initial condition itself, not a streamed state
 };
+
+// index of population (direction j, device cell) in the SoA arrays A / B
+template <class L>
+__device__ __forceinline__ size_t pop_index(int j, int32_t cell, int64_t stride, PermRange pr) {
+  return static_cast<size_t>(j) * stride + pop_slot(layout_of<L>(j), cell, pr);
+}
 
 // ------------------------------------------------------------------------------------------- arithmetic
 template <class Real, bool STRICT>
@@ -238,6 +247,42 @@ struct Phys {
   }
 
   // collision: BGK is the reference's formula (solver.cpp:603); TRT / MRT are extensions (see oracle/lbm_oracle.c)
+  //   TRT: f_i' = f_i - omega+ (f+_i - feq+_i) - omega- (f-_i - feq-_i), symmetric / antisymmetric parts over opposite pairs
+  //   MRT: f' = f - M^-1 S M (f - feq) in the orthogonal moment basis of lattice.h (MrtBasis); p.rates[k] = s_k / |row k|^2;
+  //        the conserved rows are never touched, every other row sums to zero and is orthogonal to the momentum rows, so mass
+  //        and momentum are conserved to rounding for any set of rates
+  // moment K of f - feq: sum over the non-zero entries of row K in ascending direction order (entries are compile-time constants)
+  template <int K, int I>
+  static __device__ __forceinline__ void mrt_moment(const Real (&fneq)[Q], Real& m, bool first) {
+    if constexpr(I < Q) {
+      constexpr int c = MrtBasis<L>::m(K, I);
+      if constexpr(c == 0) {
+        mrt_moment<K, I + 1>(fneq, m, first);
+      } else {
+        const Real t = c == 1 ? fneq[I] : (c == -1 ? -fneq[I] : A::mul(static_cast<Real>(c), fneq[I]));
+        m = first ? t : A::add(m, t);
+        mrt_moment<K, I + 1>(fneq, m, false);
+      }
+    }
+  }
+  template <int K, int I>
+  static __device__ __forceinline__ void mrt_back(Real d, Real (&f)[Q]) {
+    if constexpr(I < Q) {
+      constexpr int c = MrtBasis<L>::m(K, I);
+      if constexpr(c != 0) f[I] = A::sub(f[I], c == 1 ? d : (c == -1 ? -d : A::mul(static_cast<Real>(c), d)));
+      mrt_back<K, I + 1>(d, f);
+    }
+  }
+  template <int K>
+  static __device__ __forceinline__ void mrt_row(const DevParams<Real>& p, const Real (&fneq)[Q], Real (&f)[Q]) {
+    if constexpr(K < Q) {
+      Real m = 0;
+      mrt_moment<K, 0>(fneq, m, true);
+      mrt_back<K, 0>(A::mul(p.rates[K], m), f);
+      mrt_row<K + 1>(p, fneq, f);
+    }
+  }
+
   template <int COLL>
   static __device__ __forceinline__ void collide(const DevParams<Real>& p, const Real (&fo)[Q], const Real (&fe)[Q], Real (&f)[Q]) {
     if constexpr(COLL == COLL_BGK) {
@@ -246,30 +291,49 @@ struct Phys {
         if constexpr(STRICT) f[i] = A::add(A::mul(p.om1, fo[i]), A::mul(p.omega, fe[i]));
         else f[i] = fo[i] + p.omega * (fe[i] - fo[i]);
       }
-    } else {
+    } else if constexpr(COLL == COLL_TRT) {
 #pragma unroll
       for(int i = 0; i < Q; ++i) {
-        const int j  = L::opp(i);
-        Real      wp = p.omega, wm = p.omega_minus;
-        if constexpr(COLL == COLL_MRT) {
-          wp = p.rates[i < j ? i : j];
-          wm = p.rates[i < j ? j : i];
-        }
+        const int  j   = L::opp(i);
         const Real fp  = A::mul(Real(0.5), A::add(fo[i], fo[j]));
         const Real fm  = A::mul(Real(0.5), A::sub(fo[i], fo[j]));
         const Real fep = A::mul(Real(0.5), A::add(fe[i], fe[j]));
         const Real fem = A::mul(Real(0.5), A::sub(fe[i], fe[j]));
-        f[i]           = A::sub(A::sub(fo[i], A::mul(wp, A::sub(fp, fep))), A::mul(wm, A::sub(fm, fem)));
+        f[i]           = A::sub(A::sub(fo[i], A::mul(p.omega, A::sub(fp, fep))), A::mul(p.omega_minus, A::sub(fm, fem)));
       }
+    } else {
+      Real fneq[Q];
+#pragma unroll
+      for(int i = 0; i < Q; ++i) {
+        fneq[i] = A::sub(fo[i], fe[i]);
+        f[i]    = fo[i];
+      }
+      mrt_row<D + 1>(p, fneq, f);
     }
   }
 };
 
 // ------------------------------------------------------------------------------------------- gathers
+// anti-bounce-back slot of pressure entry `entry`, direction j, given the bounced population f[c, opp j]
+// (bnd_pressure.h:100: fold[c,opp] = -f[c,dist] + 2 * symmEq(dist, p, u_ext))
+template <class L, class Real, bool STRICT>
+__device__ __forceinline__ Real abb_value(const SlotTables<Real>& p, int32_t entry, int j, Real fopp) {
+  using P = Phys<L, Real, STRICT>;
+  using A = Ar<Real, STRICT>;
+  const int          oj = L::opp(j);
+  const AbbDev<Real> e  = p.abb[entry];
+  Real               u[L::D];
+#pragma unroll
+  for(int d = 0; d < L::D; ++d) u[d] = p.uext[static_cast<size_t>(entry) * 3 + d];
+  const Real vs  = P::vsq(u);
+  const Real cuv = P::cu_rt(oj, u);
+  const Real se  = P::symm_eq_one(static_cast<Real>(L::w(oj)), e.p, cuv, vs);
+  return A::add(-fopp, A::mul(Real(2), se));
+}
+
 // value of a non-pull slot of device cell `cell`, direction J (generic path)
 template <class L, class Real, bool STRICT>
 __device__ __noinline__ Real special_slot(const SlotTables<Real> p, const Real* __restrict__ Abuf, int32_t code, int32_t cell, int j) {
-  using P = Phys<L, Real, STRICT>;
   using A = Ar<Real, STRICT>;
   const int     kind = link_kind(code);
   const int32_t pl   = link_payload(code);
@@ -277,27 +341,17 @@ __device__ __noinline__ Real special_slot(const SlotTables<Real> p, const Real* 
   switch(kind) {
     case LK_COPY: {
       const CopySrcDev cs = p.copytab[pl];
-      return Abuf[static_cast<size_t>(cs.dir) * p.stride + cs.cell];
+      return Abuf[pop_index<L>(cs.dir, cs.cell, p.stride, p.pr)];
     }
-    case LK_BB: return Abuf[static_cast<size_t>(oj) * p.stride + cell];
+    case LK_BB: return Abuf[pop_index<L>(oj, cell, p.stride, p.pr)];
     case LK_BB_ADD: {
       // bnd_dirichlet.h:92,111-117: fold = f; then one += per addend
-      Real                  v = Abuf[static_cast<size_t>(oj) * p.stride + cell];
+      Real                  v = Abuf[pop_index<L>(oj, cell, p.stride, p.pr)];
       const AddEntryT<Real> e = p.addtab[pl];
       for(int t = 0; t < e.n; ++t) v = A::add(v, e.v[t]);
       return v;
     }
-    case LK_ABB: {
-      // bnd_pressure.h:100: fold[c,opp] = -f[c,dist] + 2 * symmEq(dist, p, u_ext)
-      const AbbDev<Real> e = p.abb[pl];
-      Real               u[L::D];
-#pragma unroll
-      for(int d = 0; d < L::D; ++d) u[d] = p.uext[static_cast<size_t>(pl) * 3 + d];
-      const Real vs  = P::vsq(u);
-      const Real cuv = P::cu_rt(oj, u);
-      const Real se  = P::symm_eq_one(static_cast<Real>(L::w(oj)), e.p, cuv, vs);
-      return A::add(-Abuf[static_cast<size_t>(oj) * p.stride + cell], A::mul(Real(2), se));
-    }
+    case LK_ABB: return abb_value<L, Real, STRICT>(p, pl, j, Abuf[pop_index<L>(oj, cell, p.stride, p.pr)]);
     default: return p.values[pl];
   }
 }
@@ -309,7 +363,7 @@ __device__ __forceinline__ void gather_generic(const DevParams<Real>& p, const R
   const int64_t g = cell - p.gen_begin;
   if(p.first) {
 #pragma unroll
-    for(int j = 0; j < Q; ++j) fold[j] = Abuf[static_cast<size_t>(j) * p.stride + cell];
+    for(int j = 0; j < Q; ++j) fold[j] = Abuf[pop_index<L>(j, cell, p.stride, p.pr)];
     return;
   }
   int32_t code[Q - 1];
@@ -317,7 +371,7 @@ __device__ __forceinline__ void gather_generic(const DevParams<Real>& p, const R
   for(int j = 0; j < Q - 1; ++j) code[j] = __ldg(&p.codes[static_cast<size_t>(j) * p.gen_stride + g]);
 #pragma unroll
   for(int j = 0; j < Q - 1; ++j) {
-    if(code[j] >= 0) fold[j] = Abuf[static_cast<size_t>(j) * p.stride + code[j]];
+    if(code[j] >= 0) fold[j] = Abuf[pop_index<L>(j, code[j], p.stride, p.pr)];
   }
   fold[Q - 1] = Abuf[static_cast<size_t>(Q - 1) * p.stride + cell];
 #pragma unroll
@@ -332,6 +386,7 @@ template <class L, class Real, bool STRICT, int J>
 __device__ __forceinline__ Real fast_slot(const DevParams<Real>& p, const Real* __restrict__ Abuf, int32_t cell, int32_t nbv, uint32_t off,
                                           const AddEntryT<Real>* __restrict__ wall_of_chunk, uint32_t sel) {
   using A = Ar<Real, STRICT>;
+  // template offsets are positions in direction J's own in-chunk layout (plan.hpp: build_template + lay_perm)
   if(nbv >= 0) return Abuf[static_cast<size_t>(J) * p.stride + nbv + static_cast<int32_t>(off)];
   // the descriptor of this (missing neighbour chunk, direction): on an edge of the domain the same direction bounces off different walls
   const AddEntryT<Real>* __restrict__ wall = wall_of_chunk + sel * (L::Q - 1);
@@ -342,7 +397,7 @@ __device__ __forceinline__ Real fast_slot(const DevParams<Real>& p, const Real* 
     const int32_t entry = p.chunk_abb[static_cast<size_t>(p.chunk_abb_base[cell / L::CHUNK]) * L::CHUNK + cell % L::CHUNK];
     return special_slot<L, Real, STRICT>(p.tabs, Abuf, link_code(LK_ABB, entry), cell, J);
   }
-  Real v = Abuf[static_cast<size_t>(L::opp(J)) * p.stride + cell]; // bnd_dirichlet.h:92
+  Real v = Abuf[pop_index<L>(L::opp(J), cell, p.stride, p.pr)]; // bnd_dirichlet.h:92
   for(int t = 0; t < n; ++t) v = A::add(v, wall[J].v[t]);            // bnd_dirichlet.h:111-117
   return v;
 }
@@ -364,7 +419,7 @@ __device__ __forceinline__ void gather_fast_global(const DevParams<Real>& p, con
   constexpr int Q = L::Q, CH = L::CHUNK;
   if(p.first) {
 #pragma unroll
-    for(int j = 0; j < Q; ++j) fold[j] = Abuf[static_cast<size_t>(j) * p.stride + cell];
+    for(int j = 0; j < Q; ++j) fold[j] = Abuf[pop_index<L>(j, cell, p.stride, p.pr)];
     return;
   }
   const int chunk = cell / CH, o = cell % CH;
@@ -380,30 +435,34 @@ __device__ __forceinline__ void gather_any(const DevParams<Real>& p, const Real*
   else gather_generic<L, Real, STRICT>(p, Abuf, cell, fold);
 }
 
-// ------------------------------------------------------------------------------------------- main kernel
+// ------------------------------------------------------------------------------------------- main kernels
+// moments, equilibrium, collision of one cell: m_fold -> m_f (solver.cpp:513-613)
 template <class L, class Real, bool STRICT, int COLL>
-__device__ __forceinline__ void update_and_store(const DevParams<Real>& p, int32_t cell, const Real (&fold)[L::Q]) {
+__device__ __forceinline__ void collide_cell(const DevParams<Real>& p, const Real (&fold)[L::Q], Real (&f)[L::Q], Real& rho, Real (&u)[L::D]) {
   using P = Phys<L, Real, STRICT>;
-  constexpr int Q = L::Q, D = L::D;
-  Real rho, u[D], feq[Q], f[Q];
+  Real feq[L::Q];
   P::moments(fold, rho, u);
   P::equilibrium(rho, u, feq);
   P::template collide<COLL>(p, fold, feq, f);
-#pragma unroll
-  for(int j = 0; j < Q; ++j) {
-#if defined(LBM_STORE_CS)
-    __stcs(&p.B[static_cast<size_t>(j) * p.stride + cell], f[j]);
-#elif defined(LBM_STORE_CG)
-    __stcg(&p.B[static_cast<size_t>(j) * p.stride + cell], f[j]);
-#else
-    p.B[static_cast<size_t>(j) * p.stride + cell] = f[j];
-#endif
-  }
+}
+
+template <class L, class Real>
+__device__ __forceinline__ void store_vars(const DevParams<Real>& p, int32_t cell, Real rho, const Real (&u)[L::D]) {
   if(p.vars_out != nullptr) {
 #pragma unroll
-    for(int d = 0; d < D; ++d) p.vars_out[static_cast<size_t>(d) * p.stride + cell] = u[d];
-    p.vars_out[static_cast<size_t>(D) * p.stride + cell] = rho;
+    for(int d = 0; d < L::D; ++d) p.vars_out[static_cast<size_t>(d) * p.stride + cell] = u[d];
+    p.vars_out[static_cast<size_t>(L::D) * p.stride + cell] = rho;
   }
+}
+
+template <class L, class Real, bool STRICT, int COLL>
+__device__ __forceinline__ void update_and_store(const DevParams<Real>& p, int32_t cell, const Real (&fold)[L::Q]) {
+  constexpr int Q = L::Q, D = L::D;
+  Real rho, u[D], f[Q];
+  collide_cell<L, Real, STRICT, COLL>(p, fold, f, rho, u);
+#pragma unroll
+  for(int j = 0; j < Q; ++j) p.B[pop_index<L>(j, cell, p.stride, p.pr)] = f[j];
+  store_vars<L, Real>(p, cell, rho, u);
 }
 
 #ifndef LBM_THREADS
@@ -414,89 +473,418 @@ __device__ __forceinline__ void update_and_store(const DevParams<Real>& p, int32
 #endif
 constexpr int kThreads = LBM_THREADS;
 
-template <class L, class Real, bool STRICT, int J>
-__device__ __forceinline__ void fast_wall_gather(const DevParams<Real>& p, const Real* __restrict__ Abuf, int32_t cell, int o,
-                                                 const uint16_t* __restrict__ s_tmpl, const int32_t* __restrict__ nb,
-                                                 const AddEntryT<Real>* __restrict__ wall, Real (&fold)[L::Q]) {
+// ---- generic path: one thread per cell, per-slot link codes (cells next to obstacles, ragged ends, slow chunks)
+template <class L, class Real, bool STRICT, int COLL>
+__global__ void __launch_bounds__(kThreads, LBM_MINBLOCKS) k_step_generic(const __grid_constant__ DevParams<Real> p) {
+  const int32_t gl = blockIdx.x * kThreads + threadIdx.x;
+  if(gl >= p.n_gen) return;
+  const int32_t cell = p.gen_begin + p.gen_off + gl;
+  Real          fold[L::Q];
+  gather_generic<L, Real, STRICT>(p, p.A, cell, fold);
+  update_and_store<L, Real, STRICT, COLL>(p, cell, fold);
+}
+
+// ---- chunk path: persistent CTAs, the pulled populations of a whole chunk staged in shared memory ------------------------
+// One CTA per SM walks SFC chunks handed out by a global ticket counter.  For every chunk the (Q-1) moving populations of
+// its CH cells -- already PULLED, i.e. shifted by c_j -- are copied global -> shared with cp.async, NSTAGE chunks deep, so
+// the loads of the next chunks are in flight while this one is collided.  Thanks to the per-direction in-chunk layouts
+// (lattice.h) every copy is a 16-byte piece of a whole 64-byte row that lies in exactly one (neighbour) chunk: no partially
+// used DRAM sector, no per-cell index, no template table -- the source of a row follows from the direction's constants and
+// 3^D neighbour-chunk bases.  Rows whose source chunk is a wall are redirected to the bounce-back source (same row of the
+// opposite direction, which shares the layout); addends / anti-bounce-back are applied when the cell is collided.  Threads
+// then read their cell's Q-1 values from shared memory (XOR-swizzled 16-byte units: conflict free), collide, write the
+// result back IN PLACE, and the stage is copied out shared -> global as contiguous 4 KB blocks per direction with 128-bit
+// loads / stores.  The rest population never moves: it goes through registers.
+#ifndef LBM_FAST_THREADS
+#define LBM_FAST_THREADS 512
+#endif
+constexpr int kFastThreads = LBM_FAST_THREADS;
+
+template <class L, class Real>
+struct FastCfg {
+  static constexpr int D = L::D, Q = L::Q, QM = L::Q - 1, CH = L::CHUNK, NSEL = L::NSEL;
+  static constexpr int LB  = L::CHUNK_LEVELS;            // bits per axis inside a chunk
+  static constexpr int S   = 1 << LB;                    // cells per axis
+  static constexpr int EPU = 16 / static_cast<int>(sizeof(Real)); // reals per 16-byte unit
+  static constexpr int UPD = CH / EPU;                   // 16-byte units per direction
+  static constexpr int STAGE_BYTES = QM * CH * static_cast<int>(sizeof(Real));
+#ifdef LBM_FAST_STAGES
+  static constexpr int NSTAGE = LBM_FAST_STAGES;
+#else
+  static constexpr int NSTAGE = (220 * 1024 / STAGE_BYTES) >= 4 ? 4 : (220 * 1024 / STAGE_BYTES);
+#endif
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES;
+  static constexpr int RN = NSTAGE + 1;                  // ring of neighbour-base rows
+  static constexpr int RT = NSTAGE + 2;                  // ring of tickets
+  static constexpr int PAST_END = NSTAGE + 1;            // tickets every CTA draws beyond the last chunk
+  static constexpr int CPT = (CH + kFastThreads - 1) / kFastThreads; // cells per thread and chunk
+  static constexpr int SELF = D == 2 ? 4 : 13;
+  static_assert(NSTAGE >= 2, "the chunk pipeline needs two stages");
+};
+
+// per-direction constants of the copy engine, packed (computed at compile time, kept in shared memory for run-time indexing)
+//   bits 0-1 layout | 2-3 shift along the fastest axis + 1 | 4-5 middle + 1 | 6-7 slowest + 1 | 8-12 opposite direction |
+//   13-16 / 17-20 / 21-24 selector weight (3^axis) of the fastest / middle / slowest axis
+template <class L>
+__device__ __forceinline__ constexpr uint32_t dir_word(int j) {
+  const int lay = layout_of<L>(j);
+  int ax[3] = {0, 1, 2};
+  if(lay == 1) { ax[0] = 1; ax[1] = 2; ax[2] = 0; }
+  if(lay == 2) { ax[0] = 2; ax[1] = 0; ax[2] = 1; }
+  const int pow3[3] = {1, 3, 9};
+  uint32_t  w = static_cast<uint32_t>(lay) | (static_cast<uint32_t>(L::opp(j)) << 8);
+  for(int k = 0; k < 3; ++k) {
+    const int c = ax[k] < L::D ? L::c(j, ax[k] < L::D ? ax[k] : 0) : 0;
+    w |= static_cast<uint32_t>(c + 1) << (2 + 2 * k);
+    w |= static_cast<uint32_t>(ax[k] < L::D ? pow3[ax[k]] : 0) << (13 + 4 * k);
+  }
+  return w;
+}
+template <class L, int J>
+__device__ __forceinline__ void fill_dir_words(uint32_t* s_dir, int tid) {
   if constexpr(J < L::Q - 1) {
-    const uint32_t t = s_tmpl[J * L::CHUNK + o];
-    fold[J]          = fast_slot<L, Real, STRICT, J>(p, Abuf, cell, nb[t >> 10], t & 1023u, wall, t >> 10);
-    fast_wall_gather<L, Real, STRICT, J + 1>(p, Abuf, cell, o, s_tmpl, nb, wall, fold);
+    constexpr uint32_t w = dir_word<L>(J);
+    if(tid == J) s_dir[J] = w;
+    fill_dir_words<L, J + 1>(s_dir, tid);
+  }
+}
+template <class L>
+__device__ __forceinline__ constexpr bool dir_aligned(int j) { return ((dir_word<L>(j) >> 2) & 3u) == 1u; }
+template <class L>
+__device__ __forceinline__ constexpr int count_aligned() {
+  int n = 0;
+  for(int j = 0; j < L::Q - 1; ++j) n += dir_aligned<L>(j) ? 1 : 0;
+  return n;
+}
+// k-th aligned (unaligned) direction
+template <class L>
+__device__ __forceinline__ constexpr int nth_dir(int k, bool aligned) {
+  for(int j = 0; j < L::Q - 1; ++j)
+    if(dir_aligned<L>(j) == aligned) {
+      if(k == 0) return j;
+      --k;
+    }
+  return 0;
+}
+template <class L, int K>
+__device__ __forceinline__ void fill_dir_lists(uint8_t* s_list, int tid) {
+  constexpr int NA = count_aligned<L>();
+  if constexpr(K < L::Q - 1) {
+    constexpr int j = K < NA ? nth_dir<L>(K, true) : nth_dir<L>(K - NA, false);
+    if(tid == K) s_list[K] = static_cast<uint8_t>(j);
+    fill_dir_lists<L, K + 1>(s_list, tid);
+  }
+}
+
+// position inside a stage of element `pos` (in the direction's layout): XOR swizzle of the 16-byte unit index, so that the
+// cells of a (half-)warp hit different banks whichever axis is the fastest one of the direction
+template <class L, class Real>
+__device__ __forceinline__ constexpr int stage_swizzle(int lay, int pos) {
+  if(L::D != 3) return pos;
+  if(sizeof(Real) == 8) {
+    if(lay == 0) return pos ^ (((pos >> 6) & 1) << 2);
+    if(lay == 1) return pos ^ (((pos >> 6) & 3) << 1);
+    return pos ^ ((((pos >> 4) & 1) << 1) | (((pos >> 6) & 1) << 2));
+  }
+  if(lay == 0) return pos ^ (((pos >> 6) & 1) << 4);
+  if(lay == 1) return pos ^ ((((pos >> 6) & 1) << 2) | (((pos >> 7) & 1) << 4));
+  return pos ^ (((pos >> 6) & 1) << 2);
+}
+
+// virtual thread index -> lexicographic in-chunk offset.  3D: lane bits are (x0, x1, y0, z0, x2), which together with the
+// swizzle above makes the shared-memory accesses of all three layouts conflict free (fp64); 2D: plain row order.
+template <class L>
+__device__ __forceinline__ constexpr int thread_cell(int v) {
+  if(L::D != 3) return v;
+  const int x = (v & 3) | (((v >> 4) & 1) << 2);
+  const int y = ((v >> 2) & 1) | (((v >> 5) & 3) << 1);
+  const int z = ((v >> 3) & 1) | (((v >> 7) & 3) << 1);
+  return x | (y << 3) | (z << 6);
+}
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+#if defined(__CUDA_ARCH__)
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+#else
+  std::memcpy(smem_dst, gsrc, 16);
+#endif
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async_small(void* smem_dst, const void* gsrc) {
+#if defined(__CUDA_ARCH__)
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
+#else
+  std::memcpy(smem_dst, gsrc, BYTES);
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+#endif
+}
+
+#if defined(__CUDACC__)
+extern __shared__ __align__(128) unsigned char lbm_dyn_smem[];
+#else
+alignas(128) static unsigned char lbm_dyn_smem[232448]; // CPU harness: one block at a time
+#endif
+
+// ---- the copy engine: which row of which (neighbour) chunk a 16-byte unit of a stage comes from.  The direction is a template
+// parameter, so shifts, selector weights and layout fold to immediates; what is left per unit and chunk is one shared-memory read
+// of the neighbour base, one address and the cp.async itself.
+template <class L, class Real, int J, bool ALIGNED>
+__device__ __forceinline__ void issue_unit(const DevParams<Real>& p, const Real* __restrict__ Abuf, Real* __restrict__ stg,
+                                           const int32_t* __restrict__ nb, int32_t base, int pos0) {
+  using C = FastCfg<L, Real>;
+  constexpr int lay  = layout_of<L>(J);
+  constexpr int AX0  = lay == 0 ? 0 : (lay == 1 ? 1 : 2), AX1 = lay == 0 ? 1 : (lay == 1 ? 2 : 0), AX2 = lay == 0 ? 2 : (lay == 1 ? 0 : 1);
+  constexpr int P3[3] = {1, 3, 9};
+  constexpr int sa = ALIGNED ? 0 : L::c(J, AX0);
+  constexpr int sb = AX1 < L::D ? L::c(J, AX1 < L::D ? AX1 : 0) : 0;
+  constexpr int sc = AX2 < L::D ? L::c(J, AX2 < L::D ? AX2 : 0) : 0;
+  constexpr int MASK = C::S - 1;
+  int sel = C::SELF, srcpos = pos0;
+  if constexpr(sa != 0) {
+    const int a2 = (pos0 & MASK) - sa;
+    sel += (a2 >> C::LB) * P3[AX0];
+    srcpos = (srcpos & ~MASK) | (a2 & MASK);
+  }
+  if constexpr(sb != 0) {
+    const int b2 = ((pos0 >> C::LB) & MASK) - sb;
+    sel += (b2 >> C::LB) * P3[AX1];
+    srcpos = (srcpos & ~(MASK << C::LB)) | ((b2 & MASK) << C::LB);
+  }
+  if constexpr(sc != 0) {
+    const int c2 = (pos0 >> (2 * C::LB)) - sc;
+    sel += (c2 >> C::LB) * P3[AX2];
+    srcpos = (srcpos & (C::S * C::S - 1)) | ((c2 & MASK) << (2 * C::LB));
+  }
+  const int32_t nbv = nb[sel];
+  // wall: the bounce-back source, i.e. the same row of the opposite direction's array (bnd_dirichlet.h:92)
+  const Real* src = nbv >= 0 ? Abuf + static_cast<size_t>(J) * p.stride + nbv + srcpos
+                             : Abuf + static_cast<size_t>(L::opp(J)) * p.stride + base + pos0;
+  Real* dst = stg + J * C::CH + stage_swizzle<L, Real>(lay, pos0);
+  if constexpr(ALIGNED) cp_async_16(dst, src);
+  else cp_async_small<static_cast<int>(sizeof(Real))>(dst, src);
+}
+
+// directions whose fastest layout axis is free of the shift: 16-byte units; the others (2D with c_x != 0, D3Q27 corners): reals
+template <class L, class Real, int LI>
+__device__ __forceinline__ void issue_aligned_dirs(const DevParams<Real>& p, const Real* __restrict__ Abuf, Real* __restrict__ stg,
+                                                   const int32_t* __restrict__ nb, int32_t base, int tid) {
+  using C = FastCfg<L, Real>;
+  if constexpr(LI < count_aligned<L>()) {
+    constexpr int J = nth_dir<L>(LI, true);
+    if constexpr(kFastThreads >= C::UPD) {
+      static_assert(kFastThreads % C::UPD == 0, "thread count must be a multiple of the units per direction");
+      if(tid / C::UPD == LI % (kFastThreads / C::UPD)) issue_unit<L, Real, J, true>(p, Abuf, stg, nb, base, (tid % C::UPD) * C::EPU);
+    } else {
+      for(int u = tid; u < C::UPD; u += kFastThreads) issue_unit<L, Real, J, true>(p, Abuf, stg, nb, base, u * C::EPU);
+    }
+    issue_aligned_dirs<L, Real, LI + 1>(p, Abuf, stg, nb, base, tid);
+  }
+}
+template <class L, class Real, int LI>
+__device__ __forceinline__ void issue_unaligned_dirs(const DevParams<Real>& p, const Real* __restrict__ Abuf, Real* __restrict__ stg,
+                                                     const int32_t* __restrict__ nb, int32_t base, int tid) {
+  using C = FastCfg<L, Real>;
+  if constexpr(LI < C::QM - count_aligned<L>()) {
+    constexpr int J = nth_dir<L>(LI, false);
+    if constexpr(kFastThreads >= C::CH) {
+      if(tid / C::CH == LI % (kFastThreads / C::CH)) issue_unit<L, Real, J, false>(p, Abuf, stg, nb, base, tid % C::CH);
+    } else {
+      for(int u = tid; u < C::CH; u += kFastThreads) issue_unit<L, Real, J, false>(p, Abuf, stg, nb, base, u);
+    }
+    issue_unaligned_dirs<L, Real, LI + 1>(p, Abuf, stg, nb, base, tid);
+  }
+}
+
+// issue the copies of one chunk into a stage: all moving populations of its CH cells, pulled
+template <class L, class Real>
+__device__ __forceinline__ void issue_chunk_loads(const DevParams<Real>& p, const Real* __restrict__ Abuf, Real* __restrict__ stg,
+                                                  const int32_t* __restrict__ nb, int32_t base, const uint32_t* __restrict__ s_dir, int tid) {
+  using C = FastCfg<L, Real>;
+  if(p.first) {
+    // step 0: m_fold is the initial condition itself -- every cell reads its own slots (no shift, no walls)
+    for(int g = tid; g < C::QM * C::UPD; g += kFastThreads) {
+      const int J = g / C::UPD, pos0 = (g % C::UPD) * C::EPU;
+      cp_async_16(stg + J * C::CH + stage_swizzle<L, Real>(s_dir[J] & 3, pos0), Abuf + static_cast<size_t>(J) * p.stride + base + pos0);
+    }
+    return;
+  }
+  issue_aligned_dirs<L, Real, 0>(p, Abuf, stg, nb, base, tid);
+  issue_unaligned_dirs<L, Real, 0>(p, Abuf, stg, nb, base, tid);
+}
+
+// copy a collided stage out: per direction one contiguous CH-real block of buffer B, 128-bit shared loads and global stores
+template <class L, class Real, int J>
+__device__ __forceinline__ void copy_out_dirs(const DevParams<Real>& p, const Real* __restrict__ stg, int32_t base, int tid) {
+  using C = FastCfg<L, Real>;
+  if constexpr(J < C::QM) {
+    constexpr int lay = layout_of<L>(J);
+    if constexpr(kFastThreads >= C::UPD) {
+      if(tid / C::UPD == J % (kFastThreads / C::UPD)) {
+        const int pos0 = (tid % C::UPD) * C::EPU;
+        *reinterpret_cast<uint4*>(p.B + static_cast<size_t>(J) * p.stride + base + pos0) =
+            *reinterpret_cast<const uint4*>(stg + J * C::CH + stage_swizzle<L, Real>(lay, pos0));
+      }
+    } else {
+      for(int u = tid; u < C::UPD; u += kFastThreads) {
+        const int pos0 = u * C::EPU;
+        *reinterpret_cast<uint4*>(p.B + static_cast<size_t>(J) * p.stride + base + pos0) =
+            *reinterpret_cast<const uint4*>(stg + J * C::CH + stage_swizzle<L, Real>(lay, pos0));
+      }
+    }
+    copy_out_dirs<L, Real, J + 1>(p, stg, base, tid);
+  }
+}
+
+// the staged (pulled or bounced) value of slot J of a wall chunk's cell -> m_fold: moving-wall addends (bnd_dirichlet.h:111-117) or
+// the anti-bounce-back form of a pressure face (bnd_pressure.h:100); interior slots pass through
+template <class L, class Real, bool STRICT, int J>
+__device__ __forceinline__ void wall_fixups(const DevParams<Real>& p, const int32_t* __restrict__ nb, const AddEntryT<Real>* __restrict__ wall,
+                                            int32_t cell, int o, const int (&edge)[3][2], Real (&fold)[L::Q]) {
+  using A = Ar<Real, STRICT>;
+  using C = FastCfg<L, Real>;
+  if constexpr(J < L::Q - 1) {
+    // selector of the pull source: one step against c_J; edge[d][0] = the cell sits at coordinate 0 of axis d, [1] = at S-1
+    int sel = C::SELF, w3 = 1;
+#pragma unroll
+    for(int d = 0; d < L::D; ++d) {
+      if(L::c(J, d) > 0) sel -= edge[d][0] * w3;
+      if(L::c(J, d) < 0) sel += edge[d][1] * w3;
+      w3 *= 3;
+    }
+    if(sel != C::SELF && nb[sel] < 0) {
+      const AddEntryT<Real> e = wall[sel * (L::Q - 1) + J];
+      if(e.n < 0) {
+        const int32_t entry = p.chunk_abb[static_cast<size_t>(p.chunk_abb_base[cell / L::CHUNK]) * L::CHUNK + o];
+        fold[J] = abb_value<L, Real, STRICT>(p.tabs, entry, J, fold[J]);
+      } else {
+        Real v = fold[J]; // statically indexed: the entry stays in registers
+        if(e.n > 0) v = A::add(v, e.v[0]);
+        if(e.n > 1) v = A::add(v, e.v[1]);
+        if(e.n > 2) v = A::add(v, e.v[2]);
+        fold[J] = v;
+      }
+    }
+    wall_fixups<L, Real, STRICT, J + 1>(p, nb, wall, cell, o, edge, fold);
   }
 }
 
 template <class L, class Real, bool STRICT, int COLL>
-__global__ void __launch_bounds__(kThreads, LBM_MINBLOCKS) k_step(const __grid_constant__ DevParams<Real> p) {
-  constexpr int Q = L::Q, QM = Q - 1, CH = L::CHUNK, NSEL = L::NSEL;
-  __shared__ uint16_t s_tmpl[QM * CH];
-  __shared__ int32_t  s_nb[2][NSEL + 1];
-  __shared__ int32_t  s_ticket[2];
+__global__ void __launch_bounds__(kFastThreads, 1) k_step_fast(const __grid_constant__ DevParams<Real> p) {
+  using C = FastCfg<L, Real>;
+  constexpr int Q = L::Q, QM = Q - 1, CH = L::CHUNK, NSEL = L::NSEL, NSTAGE = C::NSTAGE;
+  __shared__ int32_t  s_nb[C::RN][NSEL + 1];
+  __shared__ int32_t  s_tk[C::RT];
+  __shared__ uint32_t s_dir[32];
+  Real* const stages = reinterpret_cast<Real*>(lbm_dyn_smem);
   const Real* __restrict__ Abuf = p.A;
+  const int tid = threadIdx.x;
 
-  if(static_cast<int>(blockIdx.x) < p.n_gen_blocks) {
-    // ---- generic path: one thread per cell, per-slot link codes. Scheduled first: these blocks are the slow ones.
-    const int32_t gl = blockIdx.x * kThreads + threadIdx.x;
-    if(gl >= p.n_gen) return;
-    const int32_t cell = p.gen_begin + p.gen_off + gl;
-    Real          fold[Q];
-    gather_generic<L, Real, STRICT>(p, Abuf, cell, fold);
-    update_and_store<L, Real, STRICT, COLL>(p, cell, fold);
-    return;
+  fill_dir_words<L, 0>(s_dir, tid);
+  // Chunks are handed out dynamically, in curve order, from a global ticket counter that only ever grows: a launch over n
+  // chunks with B CTAs advances it by exactly n + B * PAST_END (every CTA draws PAST_END tickets beyond the end), so the
+  // host knows the first ticket of every launch and never resets anything.
+  if(tid == 0) {
+    unsigned long long t[NSTAGE + 1];
+#pragma unroll
+    for(int k = 0; k <= NSTAGE; ++k) t[k] = atomicAdd(p.ticket, 1ull);
+#pragma unroll
+    for(int k = 0; k <= NSTAGE; ++k) s_tk[k] = static_cast<int32_t>(t[k] - p.ticket_base);
   }
-
-  // ---- fast path: persistent CTA over SFC chunks, template in shared memory, no per-cell index traffic
-  // Chunks are handed out dynamically, in curve order, from a global ticket counter: a CTA that becomes resident late
-  // (another kernel holds its slot) simply takes fewer chunks, and there is no tail of unevenly loaded CTAs.  The counter
-  // only ever grows: a launch over n chunks with B CTAs advances it by exactly n + B (every CTA draws one ticket past the
-  // end), so the host knows the first ticket of every launch and never has to reset anything.
-  for(int t = threadIdx.x; t < QM * CH; t += kThreads) s_tmpl[t] = p.tmpl[t];
-  if(threadIdx.x == 0) s_ticket[0] = static_cast<int32_t>(atomicAdd(p.ticket, 1ull) - p.ticket_base);
   __syncthreads();
-  int32_t ticket = s_ticket[0];
-  int     buf    = 0;
-  while(ticket < p.n_fast_chunks) {
-    const int chunk = p.chunk_off + ticket;
-    // neighbour-chunk bases and the next ticket are double buffered: one barrier per chunk is enough (a thread can run at
-    // most one chunk ahead of the slowest one, and then it touches the other buffer)
-    if(threadIdx.x < NSEL + 1) s_nb[buf][threadIdx.x] = p.chunk_nb[static_cast<size_t>(chunk) * (NSEL + 1) + threadIdx.x];
-    if(threadIdx.x == 0) s_ticket[buf ^ 1] = static_cast<int32_t>(atomicAdd(p.ticket, 1ull) - p.ticket_base);
-    __syncthreads();
-    ticket = s_ticket[buf ^ 1];
-    const int32_t* nb  = s_nb[buf];
-    buf ^= 1;
-    const int32_t  wid = nb[NSEL]; // wall descriptor of this chunk, -1: interior chunk
-    const AddEntryT<Real>* wall = p.wall_desc + static_cast<size_t>(wid < 0 ? 0 : wid) * QM * NSEL;
-    const int32_t base = chunk * CH;
-#pragma unroll 1
-    for(int o = threadIdx.x; o < CH; o += kThreads) {
-      const int32_t cell = base + o;
-      Real          fold[Q];
-      if(p.first) {
-#pragma unroll
-        for(int j = 0; j < Q; ++j) fold[j] = Abuf[static_cast<size_t>(j) * p.stride + cell];
-      } else if(wid < 0) {
-        // interior chunk: pure pulls
-#pragma unroll
-        for(int j = 0; j < QM; ++j) {
-          const uint32_t t   = s_tmpl[j * CH + o];
-          const int32_t  src = nb[t >> 10] + static_cast<int32_t>(t & 1023u);
-#if defined(LBM_LOAD_NC)
-          fold[j]            = __ldg(&Abuf[static_cast<size_t>(j) * p.stride + src]);
-#elif defined(LBM_LOAD_CG)
-          fold[j]            = __ldcg(&Abuf[static_cast<size_t>(j) * p.stride + src]);
-#else
-          fold[j]            = Abuf[static_cast<size_t>(j) * p.stride + src];
-#endif
-        }
-        fold[QM] = Abuf[static_cast<size_t>(QM) * p.stride + cell];
-      } else {
-        // wall chunk: slots whose neighbour chunk is a wall bounce back
-        fast_wall_gather<L, Real, STRICT, 0>(p, Abuf, cell, o, s_tmpl, nb, wall, fold);
-        fold[QM] = Abuf[static_cast<size_t>(QM) * p.stride + cell];
-      }
-      update_and_store<L, Real, STRICT, COLL>(p, cell, fold);
-    }
+  if(s_tk[0] >= p.n_fast_chunks) return;
+  // neighbour bases of the first NSTAGE chunks
+  for(int k = 0; k < NSTAGE; ++k) {
+    const int32_t tk = s_tk[k];
+    if(tk < p.n_fast_chunks && tid < NSEL + 1) s_nb[k][tid] = p.chunk_nb[static_cast<size_t>(p.chunk_off + tk) * (NSEL + 1) + tid];
   }
+  __syncthreads();
+  for(int k = 0; k < NSTAGE - 1; ++k) {
+    const int32_t tk = s_tk[k];
+    if(tk < p.n_fast_chunks) issue_chunk_loads<L, Real>(p, Abuf, stages + static_cast<size_t>(k) * (QM * CH), s_nb[k], (p.chunk_off + tk) * CH, s_dir, tid);
+    cp_async_commit();
+  }
+
+  for(int i = 0;; ++i) {
+    const int32_t ticket = s_tk[i % C::RT];
+    if(ticket >= p.n_fast_chunks) break;
+    const int      chunk = p.chunk_off + ticket;
+    const int32_t  base  = chunk * CH;
+    Real* const    stg   = stages + static_cast<size_t>(i % NSTAGE) * (QM * CH);
+    const int32_t* nb    = s_nb[i % C::RN];
+    // the rest population does not move: straight through registers
+    Real frest[C::CPT];
+#pragma unroll
+    for(int k = 0; k < C::CPT; ++k) {
+      const int v = tid + k * kFastThreads;
+      if(v < CH) frest[k] = Abuf[static_cast<size_t>(QM) * p.stride + base + thread_cell<L>(v)];
+    }
+    cp_async_wait<NSTAGE - 2>();
+    __syncthreads(); // B1: this chunk's stage is complete; every thread has left the previous iteration
+    {
+      // chunk i + NSTAGE - 1 goes into the stage the previous iteration has just copied out
+      const int32_t tk = s_tk[(i + NSTAGE - 1) % C::RT];
+      if(tk < p.n_fast_chunks)
+        issue_chunk_loads<L, Real>(p, Abuf, stages + static_cast<size_t>((i + NSTAGE - 1) % NSTAGE) * (QM * CH), s_nb[(i + NSTAGE - 1) % C::RN],
+                                   (p.chunk_off + tk) * CH, s_dir, tid);
+      cp_async_commit();
+    }
+    // neighbour bases of chunk i + NSTAGE and the ticket of chunk i + NSTAGE + 1: fetched now, published before B2
+    const int32_t tk_nb  = s_tk[(i + NSTAGE) % C::RT];
+    int32_t       nb_val = 0;
+    if(tk_nb < p.n_fast_chunks && tid < NSEL + 1) nb_val = p.chunk_nb[static_cast<size_t>(p.chunk_off + tk_nb) * (NSEL + 1) + tid];
+    unsigned long long tk_new = 0;
+    if(tid == 0) tk_new = atomicAdd(p.ticket, 1ull);
+
+    const int32_t wid = nb[NSEL]; // wall descriptor of this chunk, -1: interior chunk
+    const AddEntryT<Real>* wall = p.wall_desc + static_cast<size_t>(wid < 0 ? 0 : wid) * QM * NSEL;
+#pragma unroll
+    for(int k = 0; k < C::CPT; ++k) {
+      const int v = tid + k * kFastThreads;
+      if(v < CH) {
+        const int o = thread_cell<L>(v);
+        int pos[3];
+        pos[0] = stage_swizzle<L, Real>(0, o);
+        pos[1] = L::D == 3 ? stage_swizzle<L, Real>(1, lay_perm(1, o)) : o;
+        pos[2] = L::D == 3 ? stage_swizzle<L, Real>(2, lay_perm(2, o)) : o;
+        Real fold[Q], f[Q], rho, u[L::D];
+#pragma unroll
+        for(int j = 0; j < QM; ++j) fold[j] = stg[j * CH + pos[layout_of<L>(j)]];
+        fold[QM] = frest[k];
+        if(wid >= 0 && !p.first) {
+          int edge[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+#pragma unroll
+          for(int d = 0; d < L::D; ++d) {
+            const int x = (o >> (d * C::LB)) & (C::S - 1);
+            edge[d][0]  = x == 0 ? 1 : 0;
+            edge[d][1]  = x == C::S - 1 ? 1 : 0;
+          }
+          wall_fixups<L, Real, STRICT, 0>(p, nb, wall, base + o, o, edge, fold);
+        }
+        collide_cell<L, Real, STRICT, COLL>(p, fold, f, rho, u);
+#pragma unroll
+        for(int j = 0; j < QM; ++j) stg[j * CH + pos[layout_of<L>(j)]] = f[j];
+        p.B[static_cast<size_t>(QM) * p.stride + base + o] = f[QM];
+        store_vars<L, Real>(p, base + o, rho, u);
+      }
+    }
+    if(tk_nb < p.n_fast_chunks && tid < NSEL + 1) s_nb[(i + NSTAGE) % C::RN][tid] = nb_val;
+    if(tid == 0) s_tk[(i + NSTAGE + 1) % C::RT] = static_cast<int32_t>(tk_new - p.ticket_base);
+    __syncthreads(); // B2: the stage holds m_f of the whole chunk
+    copy_out_dirs<L, Real, 0>(p, stg, base, tid);
+  }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------- auxiliary kernels
@@ -521,8 +909,8 @@ __global__ void k_forcing(const __grid_constant__ DevParams<Real> p, const Force
 #pragma unroll
   for(int i = 0; i < Q; ++i) {
     const Real cuv = A::mul(u[0], static_cast<Real>(L::c(i, 0)));
-    const Real fv  = p.B[static_cast<size_t>(i) * p.stride + e.val];
-    p.B[static_cast<size_t>(i) * p.stride + e.target] = A::sub(A::add(P::eq_one(static_cast<Real>(L::w(i)), e.p, cuv, vs), fv), feq[i]);
+    const Real fv  = p.B[pop_index<L>(i, e.val, p.stride, p.pr)];
+    p.B[pop_index<L>(i, e.target, p.stride, p.pr)] = A::sub(A::add(P::eq_one(static_cast<Real>(L::w(i)), e.p, cuv, vs), fv), feq[i]);
   }
 }
 
@@ -544,7 +932,7 @@ __global__ void k_periodic_pressure(const __grid_constant__ DevParams<Real> p, c
 #pragma unroll
   for(int i = 0; i < Q; ++i) {
     const Real cuv = P::cu_rt(i, u);
-    const Real fv  = p.B[static_cast<size_t>(i) * p.stride + e.cell];
+    const Real fv  = p.B[pop_index<L>(i, e.cell, p.stride, p.pr)];
     values_next[e.vbase + i] = A::sub(A::add(P::eq_one(static_cast<Real>(L::w(i)), e.p, cuv, vs), fv), feq[i]);
   }
 }
@@ -623,19 +1011,22 @@ __global__ void k_gather_all(const __grid_constant__ DevParams<Real> p, int32_t 
 }
 
 // host layout (reference: array of structures, double, reference cell order) <-> device layout (SoA, Real, plan order)
-template <class Real>
-__global__ void k_unpack_aos(const double* __restrict__ aos, const int32_t* __restrict__ ref2dev, int64_t n, int width, Real* __restrict__ soa, int64_t stride) {
+// POP: the SoA array is a population array (per-direction in-chunk layouts); otherwise a plain per-cell array (m_vars, scratch)
+template <class L, class Real, bool POP>
+__global__ void k_unpack_aos(const double* __restrict__ aos, const int32_t* __restrict__ ref2dev, int64_t n, int width, Real* __restrict__ soa, int64_t stride,
+                             PermRange pr) {
   const int64_t c = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if(c >= n) return;
   const int32_t dv = ref2dev[c];
-  for(int j = 0; j < width; ++j) soa[static_cast<size_t>(j) * stride + dv] = static_cast<Real>(aos[c * width + j]);
+  for(int j = 0; j < width; ++j) soa[POP ? pop_index<L>(j, dv, stride, pr) : static_cast<size_t>(j) * stride + dv] = static_cast<Real>(aos[c * width + j]);
 }
-template <class Real>
-__global__ void k_pack_aos(const Real* __restrict__ soa, const int32_t* __restrict__ ref2dev, int64_t n, int width, double* __restrict__ aos, int64_t stride) {
+template <class L, class Real, bool POP>
+__global__ void k_pack_aos(const Real* __restrict__ soa, const int32_t* __restrict__ ref2dev, int64_t n, int width, double* __restrict__ aos, int64_t stride,
+                           PermRange pr) {
   const int64_t c = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if(c >= n) return;
   const int32_t dv = ref2dev[c];
-  for(int j = 0; j < width; ++j) aos[c * width + j] = static_cast<double>(soa[static_cast<size_t>(j) * stride + dv]);
+  for(int j = 0; j < width; ++j) aos[c * width + j] = static_cast<double>(soa[POP ? pop_index<L>(j, dv, stride, pr) : static_cast<size_t>(j) * stride + dv]);
 }
 
 // halo exchange: gather the outgoing populations into one contiguous buffer / scatter the received ones into the ghosts
@@ -652,7 +1043,7 @@ __global__ void k_halo_unpack(Real* __restrict__ f, const int64_t* __restrict__ 
 
 // initialCondition(): rho = 1, u = preset, f = feq  (solver.cpp:267-295)
 template <class L, class Real, bool STRICT>
-__global__ void k_init(Real* __restrict__ f, const Real* __restrict__ vars0, int64_t stride, int32_t ncells) {
+__global__ void k_init(Real* __restrict__ f, const Real* __restrict__ vars0, int64_t stride, int32_t ncells, PermRange pr) {
   using P = Phys<L, Real, STRICT>;
   constexpr int Q = L::Q, D = L::D;
   const int32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
@@ -663,7 +1054,7 @@ __global__ void k_init(Real* __restrict__ f, const Real* __restrict__ vars0, int
   const Real rho = vars0[static_cast<size_t>(D) * stride + cell];
   P::equilibrium(rho, u, feq);
 #pragma unroll
-  for(int j = 0; j < Q; ++j) f[static_cast<size_t>(j) * stride + cell] = feq[j];
+  for(int j = 0; j < Q; ++j) f[pop_index<L>(j, cell, stride, pr)] = feq[j];
 }
 
 // residual: sum_c |vars - varsold| per variable (solver.cpp:809-815). Two-pass and fixed-shape, so it is

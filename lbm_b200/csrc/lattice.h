@@ -7,6 +7,8 @@
 #pragma once
 #include <cstdint>
 
+#include "mrt_tables.h"
+
 #if defined(__CUDACC__)
 #define LBM_HD __host__ __device__ __forceinline__
 #else
@@ -74,12 +76,70 @@ struct Lattice<3, 27> {
   }
 };
 
+
+// ---- per-direction in-chunk layouts (3D) ---------------------------------------------------------------------------------
+// Inside an 8^3 chunk the population array of direction j is stored with an axis the direction does NOT move along as the
+// fastest one: a pull shifted by c_j then only ever moves whole 64-byte rows (8 reals along the fastest axis), so every
+// 32-byte DRAM sector a chunk reads is used completely -- with x fastest for all directions the ten D3Q19 directions with
+// c_x != 0 fetched one extra, 7/8 wasted sector per row from the x-neighbour chunk (+26 % sectors, profiles/r01_ncu_*).
+//   layout 0: pos = x + 8 y + 64 z   (directions without x component; D3Q27 corners, which have no free axis; all of 2D)
+//   layout 1: pos = y + 8 z + 64 x   (+-x, xz diagonals)
+//   layout 2: pos = z + 8 x + 64 y   (+-y, xy diagonals)
+// Opposite directions share a layout (c_opp = -c), so a bounce-back source row is the same row of the opposite array.
+LBM_HD constexpr int layout_of_c(int D, int cx, int cy, int cz) {
+  if(D != 3) return 0;
+  const bool x = cx != 0, y = cy != 0, z = cz != 0;
+  if(x && !y && !z) return 1;
+  if(!x && y && !z) return 2;
+  if(x && y && !z) return 2;
+  if(x && !y && z) return 1;
+  return 0;
+}
+template <class L>
+LBM_HD constexpr int layout_of(int j) {
+  return layout_of_c(L::D, L::c(j, 0), L::D > 1 ? L::c(j, 1) : 0, L::D > 2 ? L::c(j, 2) : 0);
+}
+// lexicographic in-chunk offset (x fastest) -> position in the array of a direction with layout `lay`; 3D chunks only (9 bits)
+LBM_HD constexpr int lay_perm(int lay, int o) {
+  return lay == 0 ? o : (lay == 1 ? ((o >> 3) | ((o & 7) << 6)) : ((o >> 6) | ((o & 63) << 3)));
+}
+LBM_HD constexpr int lay_perm_inv(int lay, int pos) {
+  return lay == 0 ? pos : (lay == 1 ? (((pos & 63) << 3) | (pos >> 6)) : (((pos & 7) << 6) | (pos >> 3)));
+}
+// Which device cells live in chunk-shaped blocks (fast chunks, slow chunks, ghost blocks): only those are permuted.
+struct PermRange { int32_t perm_end, gb_begin, gb_end; };
+LBM_HD constexpr int32_t pop_slot(int lay, int32_t cell, PermRange r) {
+  if(lay == 0) return cell;
+  if(!(cell < r.perm_end || (cell >= r.gb_begin && cell < r.gb_end))) return cell;
+  return (cell & ~511) | lay_perm(lay, cell & 511);
+}
+
+// ---- MRT moment bases (generated: tools/gen_mrt_tables.py -> mrt_tables.h) --------------------------------------------------
+// Orthogonal integer basis M, rows: conserved moments first (density, momentum), then the non-conserved ones; kind 1 = shear
+// (traceless second-order moments: their rate sets the viscosity), 2 = bulk, 3 = ghost (higher order).
+template <class L>
+struct MrtBasis;
+#define LBM_MRT_BASIS(LATT, NAME, QQ)                                                                              \
+  template <>                                                                                                      \
+  struct MrtBasis<LATT> {                                                                                          \
+    LBM_HD static constexpr int m(int k, int i) { constexpr int t[QQ][QQ] = LBM_MRT_##NAME##_M; return t[k][i]; }  \
+    LBM_HD static constexpr int norm(int k) { constexpr int t[QQ] = LBM_MRT_##NAME##_NORM; return t[k]; }          \
+    LBM_HD static constexpr int kind(int k) { constexpr int t[QQ] = LBM_MRT_##NAME##_KIND; return t[k]; }          \
+  };
+#define LBM_COMMA ,
+LBM_MRT_BASIS(Lattice<2 LBM_COMMA 9>, D2Q9, 9)
+LBM_MRT_BASIS(Lattice<3 LBM_COMMA 19>, D3Q19, 19)
+LBM_MRT_BASIS(Lattice<3 LBM_COMMA 27>, D3Q27, 27)
+#undef LBM_COMMA
+#undef LBM_MRT_BASIS
+
 // Runtime view of the same tables for host-side planning code.
 struct LatticeRT {
   int    D = 0, Q = 0, NSEL = 0, CHUNK = 0, CHUNK_LEVELS = 0;
   int    c[27][3] = {};
   int    opp[27]  = {};
   double w[27]    = {};
+  int    lay[27]  = {}; // in-chunk layout of every direction's population array (layout_of)
 };
 
 template <class L>
@@ -94,6 +154,7 @@ inline LatticeRT make_rt() {
     for(int d = 0; d < L::D; ++d) r.c[i][d] = L::c(i, d);
     r.opp[i] = L::opp(i);
     r.w[i]   = L::w(i);
+    r.lay[i] = layout_of<L>(i);
   }
   return r;
 }

@@ -118,7 +118,12 @@ struct Plan {
   std::vector<int32_t>    u0_cells; // cells with a preset initial velocity (Dirichlet BB, bnd_dirichlet.h:44-50)
   std::vector<double>     u0_vals;  // D per entry
   int64_t slots_bc = 0, slots_stale = 0;
-  int64_t n_owned = 0, n_ghost = 0, ghost_begin = 0; // device range [ghost_begin, ghost_begin + n_ghost) holds the ghosts
+  int64_t n_owned = 0, n_ghost = 0, ghost_begin = 0; // owned device cells are [0, ghost_begin); the ghosts follow
+  // per-direction in-chunk layouts (lattice.h): device cells of chunk-shaped blocks -- fast and slow chunks [0, perm_end), ghost
+  // blocks [gb_begin, gb_end) -- are permuted inside their aligned CH-cell block, loose cells are not
+  int64_t perm_end = 0, gb_begin = 0, gb_end = 0;
+  PermRange perm_range() const { return PermRange{static_cast<int32_t>(perm_end), static_cast<int32_t>(gb_begin), static_cast<int32_t>(gb_end)}; }
+  int64_t pop_index(int j, int64_t dev_cell) const { return static_cast<int64_t>(j) * npad + pop_slot(L.lay[j], static_cast<int32_t>(dev_cell), perm_range()); }
   std::vector<int64_t> send_index, recv_index;       // flat device indices dir * npad + cell, wire order
   std::vector<int32_t> vsend_cells;                  // device cells whose velocity travels with the halo, wire order
   int64_t              n_vrecv = 0;                  // velocity items received (3 reals each)
@@ -270,6 +275,13 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
   for(const BcInput& bc : in.bcs)
     if(bc.kind >= BC_WALL_EQ) { P.error = "internal: wet-node walls and Poisson conditions are handled by the sequential paths"; return false; }
   if(in.poisson) { P.error = "internal: the Poisson equation has no fused device plan"; return false; }
+  // forcing and the periodic boundary condition rebuild m_fold of OTHER cells (x-neighbours, linked cells), which a partition cut
+  // may hand to another rank: not partitioned (the value cells would be ghosts without links of their own)
+  if(in.n_ghost > 0) {
+    if(in.forcing) { P.error = "forcing is not partitioned"; return false; }
+    for(const BcInput& bc : in.bcs)
+      if(bc.kind == BC_PERIODIC) { P.error = "the periodic boundary condition is not partitioned (use grid-level periodic links)"; return false; }
+  }
   // ---- 2. boundary conditions, in the reference's order: preApply writes, then the push, then apply writes
   std::unordered_map<int64_t, SlotDesc> over;  // slot key c*Q+j -> final descriptor
   auto key = [&](int64_t c, int j) { return c * Q + j; };
@@ -457,7 +469,12 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
   // ---- 5. SFC chunks: runs of CH consecutive cells that are internally ordered like the curve template
   std::vector<uint16_t> tmpl_sfc;
   build_template(L, tmpl_sfc, false); // reference (curve) order: chunk recognition
-  build_template(L, P.tmpl, true);    // device order: what the kernel reads
+  build_template(L, P.tmpl, true);    // device order: what the kernels read -- offsets in each direction's own in-chunk layout
+  for(int j = 0; j < QM; ++j)
+    for(int o = 0; o < CH; ++o) {
+      uint16_t& t = P.tmpl[static_cast<size_t>(j) * CH + o];
+      t = static_cast<uint16_t>((t & ~1023) | lay_perm(L.lay[j], t & 1023));
+    }
   std::vector<int32_t> sfc2lex(static_cast<size_t>(CH));
   for(int o = 0; o < CH; ++o) {
     int xyz[3];
@@ -687,26 +704,32 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
       }
   P.n_fast_chunks = static_cast<int64_t>(fast_order.size());
   P.gen_begin = pos;
+  // slow chunks first (all of them count as outer: they are few, and keeping every chunk-shaped block in one leading range makes
+  // "is this cell stored in the per-direction layouts?" a single comparison), then the loose cells, outer ones first
+  for(int64_t k = 0; k < nc; ++k)
+    if(!fast[k]) { cand_dev[k] = pos; pos += CH; ++P.n_slow_chunks; }
+  P.perm_end = pos;
   for(int pass = 0; pass < 2; ++pass) {
-    for(int64_t k = 0; k < nc; ++k)
-      if(!fast[k] && (outer_chunk[k] != 0) == (pass == 0)) { cand_dev[k] = pos; pos += CH; ++P.n_slow_chunks; }
     for(int64_t c = 0; c < NO; ++c)
       if(chunk_of[c] < 0 && (is_send[c] != 0) == (pass == 0)) { P.ref2dev[c] = static_cast<int32_t>(pos++); ++P.n_loose; }
-    if(pass == 0) P.n_gen_outer = pos - P.gen_begin;
+    if(pass == 0) P.n_gen_outer = in.send_cell.empty() ? 0 : pos - P.gen_begin;
   }
   for(int64_t k = 0; k < nc; ++k)
     for(int o = 0; o < CH; ++o) P.ref2dev[cand_base[k] + o] = static_cast<int32_t>(cand_dev[k] + sfc2lex[o]);
   P.n_gen  = pos - P.gen_begin;
   P.ghost_begin = pos;
+  if(n_ghost_blocks > 0) pos = (pos + CH - 1) / CH * CH; // ghost blocks are chunk-shaped: aligned like chunks
   const int64_t ghost_block_base = pos;
+  P.gb_begin = pos;
   pos += static_cast<int64_t>(n_ghost_blocks) * CH;
+  P.gb_end = pos;
   P.n_ghost_blocks = n_ghost_blocks;
   for(int64_t c = NO; c < N; ++c) {
     const size_t g = static_cast<size_t>(c - NO);
     if(ghost_group[g] >= 0) P.ref2dev[c] = static_cast<int32_t>(ghost_block_base + static_cast<int64_t>(ghost_group[g]) * CH + sfc2lex[ghost_off[g]]);
     else P.ref2dev[c] = static_cast<int32_t>(pos++);
   }
-  P.npad   = (pos + 63) / 64 * 64;
+  P.npad   = (pos + CH - 1) / CH * CH; // whole blocks: the in-chunk permutation never leaves the arrays
   P.gen_stride = (P.n_gen + 63) / 64 * 64;
   P.dev2ref.assign(static_cast<size_t>(P.npad), -1);
   for(int64_t c = 0; c < N; ++c) P.dev2ref[P.ref2dev[c]] = static_cast<int32_t>(c);
@@ -855,12 +878,12 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
     for(size_t k = 0; k < in.send_cell.size(); ++k) {
       const int64_t c = in.send_cell[k];
       if(c < 0 || c >= NO || in.send_dir[k] < 0 || in.send_dir[k] >= Q) { P.error = "halo send entry out of range"; return false; }
-      P.send_index[k] = static_cast<int64_t>(in.send_dir[k]) * P.npad + P.ref2dev[c];
+      P.send_index[k] = P.pop_index(in.send_dir[k], P.ref2dev[c]);
     }
     for(size_t k = 0; k < in.recv_cell.size(); ++k) {
       const int64_t c = in.recv_cell[k];
       if(c < NO || c >= N || in.recv_dir[k] < 0 || in.recv_dir[k] >= Q) { P.error = "halo receive entry is not a ghost cell"; return false; }
-      P.recv_index[k] = static_cast<int64_t>(in.recv_dir[k]) * P.npad + P.ref2dev[c];
+      P.recv_index[k] = P.pop_index(in.recv_dir[k], P.ref2dev[c]);
     }
   }
   {

@@ -52,6 +52,12 @@
 #endif
 
 #define ORC_MAXQ 27
+#include "mrt_tables.h"
+/* MRT moment bases, padded to ORC_MAXQ columns so that one pointer type serves the three lattices */
+static const int mrt_m9[9][ORC_MAXQ]   = LBM_MRT_D2Q9_M;
+static const int mrt_m19[19][ORC_MAXQ] = LBM_MRT_D3Q19_M;
+static const int mrt_m27[27][ORC_MAXQ] = LBM_MRT_D3Q27_M;
+static const int mrt_n9[9] = LBM_MRT_D2Q9_NORM, mrt_n19[19] = LBM_MRT_D3Q19_NORM, mrt_n27[27] = LBM_MRT_D3Q27_NORM;
 #define ORC_MAXD 3
 
 enum { ORC_BGK = 0, ORC_TRT = 1, ORC_MRT = 2 };
@@ -276,8 +282,10 @@ void orc_set_geometry(Orc* o, const double* center, const double* bbmin, const d
 
 /* New behaviour (not in the reference): two-relaxation-time and multiple-relaxation-time collision.
  * TRT: f_i' = f_i - omega (f+_i - feq+_i) - omega_minus (f-_i - feq-_i) with the symmetric / antisymmetric
- * split over opposite pairs.  MRT here is the pairwise "raw-moment by parity" form: rates[i] for the even part of
- * pair (i, opp i) is rates[min], for the odd part rates[max]; with all rates equal it is exactly the BGK formula. */
+ * split over opposite pairs.
+ * MRT: moment space, f' = f - M^-1 S M (f - feq) with the orthogonal integer basis of oracle/mrt_tables.h (generated by
+ * tools/gen_mrt_tables.py: d'Humieres-type, reference direction order), S = diag(rates), M^-1 = M^T diag(1/|row|^2).  Conserved rows
+ * (density, momentum) are never relaxed; all rates equal = BGK up to rounding.  PARITY UNPINNED (literature form, no reference run). */
 void orc_set_collision(Orc* o, int model, double omega_minus, const double* rates) {
   o->model       = model;
   o->omega_minus = omega_minus;
@@ -665,14 +673,31 @@ static void collide_cell(const Orc* o, int64_t c) {
   }
   if(o->model == ORC_BGK) {
     for(int i = 0; i < Q; ++i) f[i] = (1 - o->omega) * fo[i] + o->omega * fe[i];
+  } else if(o->model == ORC_MRT) {
+    const int (*M)[ORC_MAXQ] = Q == 9 ? mrt_m9 : (Q == 19 ? mrt_m19 : mrt_m27);
+    const int* norm          = Q == 9 ? mrt_n9 : (Q == 19 ? mrt_n19 : mrt_n27);
+    double     fneq[ORC_MAXQ];
+    for(int i = 0; i < Q; ++i) {
+      fneq[i] = fo[i] - fe[i];
+      f[i]    = fo[i];
+    }
+    for(int k = L->ndim + 1; k < Q; ++k) { /* rows 0 .. ndim are density and momentum */
+      double m     = 0;
+      int    first = 1;
+      for(int i = 0; i < Q; ++i) {
+        if(M[k][i] == 0) continue;
+        const double t = (double)M[k][i] * fneq[i];
+        m              = first ? t : m + t;
+        first          = 0;
+      }
+      const double d = (o->mrt_rates[k] / (double)norm[k]) * m;
+      for(int i = 0; i < Q; ++i)
+        if(M[k][i] != 0) f[i] = f[i] - (double)M[k][i] * d;
+    }
   } else {
     for(int i = 0; i < Q; ++i) {
       const int    j  = L->opp[i];
-      double       wp = o->omega, wm = o->omega_minus;
-      if(o->model == ORC_MRT) {
-        wp = o->mrt_rates[i < j ? i : j];
-        wm = o->mrt_rates[i < j ? j : i];
-      }
+      const double wp = o->omega, wm = o->omega_minus;
       const double fp  = 0.5 * (fo[i] + fo[j]);
       const double fm  = 0.5 * (fo[i] - fo[j]);
       const double fep = 0.5 * (fe[i] + fe[j]);

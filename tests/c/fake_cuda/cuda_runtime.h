@@ -19,6 +19,7 @@
 #define __grid_constant__
 #define __launch_bounds__(...)
 
+struct uint4 { unsigned x, y, z, w; };
 struct FakeDim3 { unsigned x = 0, y = 0, z = 0; };
 static FakeDim3 blockIdx, blockDim, gridDim;
 static thread_local FakeDim3 threadIdx;

@@ -46,6 +46,7 @@ struct Ctx {
     p.A = A.data();
     p.B = B.data();
     p.stride = v.npad;
+    p.pr = PermRange{static_cast<int32_t>(v.perm_end), static_cast<int32_t>(v.gb_begin), static_cast<int32_t>(v.gb_end)};
     p.tmpl = v.tmpl;
     p.chunk_nb = v.chunk_nb;
     p.wall_desc = wall.data();
@@ -62,6 +63,7 @@ struct Ctx {
     p.tabs.uext = uext[dyn].data();
     p.tabs.values = values.data();
     p.tabs.stride = v.npad;
+    p.tabs.pr = p.pr;
     p.omega = omega;
     p.om1 = 1 - omega;
     p.omega_minus = omega_minus;
@@ -88,78 +90,55 @@ void update(Ctx& c) {
     update_and_store<L, double, true, COLL>(p, cell, fold);
   }
 }
-// The fused kernel ITSELF: k_step<L, double, STRICT, BGK> with its generic blocks and its persistent chunk CTAs (ticket counter,
-// template in shared memory, double-buffered neighbour bases, one barrier per chunk).  Every block runs as kThreads OS threads with a
-// real barrier behind __syncthreads(); blocks run one after the other (legal for this kernel: a CTA that becomes resident late simply
-// draws fewer tickets).  Launch geometry as Solver::one_step sets it, with a handful of persistent CTAs.
+// The kernels of a time step THEMSELVES: k_step_generic (one thread per link-code cell) and k_step_fast, the persistent chunk CTAs
+// (ticket counter, cp.async pipeline of whole chunks through shared memory, per-direction in-chunk layouts, in-place collision,
+// 128-bit copy-out).  Every chunk CTA runs as kFastThreads OS threads with a real barrier behind __syncthreads(); cp.async is a memcpy
+// (tests/c/fake_cuda); blocks run one after the other (legal for this kernel: a CTA that becomes resident late simply draws fewer
+// tickets).  Launch geometry as Solver::one_step sets it, with a handful of persistent CTAs.
 template <class L, int COLL>
-void step_kernel(Ctx& c, int persistent_ctas) {
-  DevParams<double> p = c.params();
-  const int64_t nfast = c.v.n_fast_chunks;
-  p.gen_off = 0;
-  p.n_gen = static_cast<int32_t>(c.v.n_gen);
-  p.n_gen_blocks = static_cast<int32_t>((c.v.n_gen + kThreads - 1) / kThreads);
-  p.chunk_off = 0;
-  p.n_fast_chunks = static_cast<int32_t>(nfast);
-  p.n_fast_blocks = static_cast<int32_t>(nfast < persistent_ctas ? nfast : persistent_ctas);
-  p.ticket = &c.ticket;
-  p.ticket_base = c.ticket_next;
-  c.ticket_next += static_cast<unsigned long long>(nfast) + static_cast<unsigned long long>(p.n_fast_blocks);
-  const int grid = p.n_gen_blocks + p.n_fast_blocks;
-  blockDim.x = kThreads;
-  gridDim.x  = static_cast<unsigned>(grid);
-  pthread_barrier_init(&g_block_barrier, nullptr, kThreads);
+void launch_step(const DevParams<double>& base, int64_t g0, int64_t ng, int64_t c0, int64_t ncnk, int persistent_ctas, unsigned long long* ticket,
+                 unsigned long long* ticket_next) {
+  DevParams<double> q = base;
+  q.gen_off       = static_cast<int32_t>(g0);
+  q.n_gen         = static_cast<int32_t>(ng);
+  q.n_gen_blocks  = static_cast<int32_t>((ng + kThreads - 1) / kThreads);
+  q.chunk_off     = static_cast<int32_t>(c0);
+  q.n_fast_chunks = static_cast<int32_t>(ncnk);
+  q.n_fast_blocks = static_cast<int32_t>(ncnk < persistent_ctas ? ncnk : persistent_ctas);
+  q.ticket        = ticket;
+  q.ticket_base   = *ticket_next;
+  *ticket_next += static_cast<unsigned long long>(ncnk) + static_cast<unsigned long long>(q.n_fast_blocks) * FastCfg<L, double>::PAST_END;
+  launch(ng, kThreads, [&] { k_step_generic<L, double, true, COLL>(q); });
+  blockDim.x = kFastThreads;
+  gridDim.x  = static_cast<unsigned>(q.n_fast_blocks);
+  pthread_barrier_init(&g_block_barrier, nullptr, kFastThreads);
   g_block_barrier_on = true;
-  for(int b = 0; b < grid; ++b) {
+  for(int b = 0; b < q.n_fast_blocks; ++b) {
     blockIdx.x = static_cast<unsigned>(b);
     std::vector<std::thread> th;
-    for(int t = 0; t < kThreads; ++t)
-      th.emplace_back([&p, t] {
+    for(int t = 0; t < kFastThreads; ++t)
+      th.emplace_back([&q, t] {
         threadIdx.x = static_cast<unsigned>(t);
-        k_step<L, double, true, COLL>(p);
+        k_step_fast<L, double, true, COLL>(q);
       });
     for(auto& x : th) x.join();
   }
   g_block_barrier_on = false;
   pthread_barrier_destroy(&g_block_barrier);
 }
+template <class L, int COLL>
+void step_kernel(Ctx& c, int persistent_ctas) {
+  launch_step<L, COLL>(c.params(), 0, c.v.n_gen, 0, c.v.n_fast_chunks, persistent_ctas, &c.ticket, &c.ticket_next);
+}
 
-// The overlapped path of Solver::one_step: two launches of the same kernel -- the outer cells (chunks / generic cells holding a
-// population a peer needs, placed first in the device layout) with their own ticket counter, then the inner ones.
+// The overlapped path of Solver::one_step: two launches -- the outer cells (chunks / generic cells holding a population a peer needs,
+// placed first in the device layout) with their own ticket counter, then the inner ones.
 template <class L, int COLL>
 void step_kernel_split(Ctx& c, int persistent_ctas) {
   const DevParams<double> base = c.params();
-  auto one = [&](int64_t g0, int64_t ng, int64_t c0, int64_t ncnk, int cls) {
-    DevParams<double> q = base;
-    q.gen_off       = static_cast<int32_t>(g0);
-    q.n_gen         = static_cast<int32_t>(ng);
-    q.n_gen_blocks  = static_cast<int32_t>((ng + kThreads - 1) / kThreads);
-    q.chunk_off     = static_cast<int32_t>(c0);
-    q.n_fast_chunks = static_cast<int32_t>(ncnk);
-    q.n_fast_blocks = static_cast<int32_t>(ncnk < persistent_ctas ? ncnk : persistent_ctas);
-    q.ticket        = &c.ticket2[cls];
-    q.ticket_base   = c.ticket2_next[cls];
-    c.ticket2_next[cls] += static_cast<unsigned long long>(ncnk) + static_cast<unsigned long long>(q.n_fast_blocks);
-    const int grid = q.n_gen_blocks + q.n_fast_blocks;
-    blockDim.x = kThreads;
-    gridDim.x  = static_cast<unsigned>(grid);
-    pthread_barrier_init(&g_block_barrier, nullptr, kThreads);
-    g_block_barrier_on = true;
-    for(int b = 0; b < grid; ++b) {
-      blockIdx.x = static_cast<unsigned>(b);
-      std::vector<std::thread> th;
-      for(int t = 0; t < kThreads; ++t)
-        th.emplace_back([&q, t] {
-          threadIdx.x = static_cast<unsigned>(t);
-          k_step<L, double, true, COLL>(q);
-        });
-      for(auto& x : th) x.join();
-    }
-    g_block_barrier_on = false;
-    pthread_barrier_destroy(&g_block_barrier);
-  };
-  one(0, c.v.n_gen_outer, 0, c.v.n_fast_outer, 1);
-  one(c.v.n_gen_outer, c.v.n_gen - c.v.n_gen_outer, c.v.n_fast_outer, c.v.n_fast_chunks - c.v.n_fast_outer, 0);
+  launch_step<L, COLL>(base, 0, c.v.n_gen_outer, 0, c.v.n_fast_outer, persistent_ctas, &c.ticket2[1], &c.ticket2_next[1]);
+  launch_step<L, COLL>(base, c.v.n_gen_outer, c.v.n_gen - c.v.n_gen_outer, c.v.n_fast_outer, c.v.n_fast_chunks - c.v.n_fast_outer, persistent_ctas,
+                       &c.ticket2[0], &c.ticket2_next[0]);
 }
 
 template <class L>
@@ -250,7 +229,12 @@ void kh_set_collision(void* p, int coll, double omega_minus, const double* rates
   auto* c = static_cast<Ctx*>(p);
   c->coll = coll;
   c->omega_minus = omega_minus;
-  for(int i = 0; i < 27; ++i) c->rates[i] = rates[i];
+  // MRT: the kernel takes the rate of moment k divided by the squared norm of its basis row (Solver::params, solver_fused.cuh)
+  for(int i = 0; i < 27; ++i) {
+    double norm = 1;
+    if(i < c->ndist) DISPATCH(c, norm = MrtBasis<L>::norm(i));
+    c->rates[i] = coll == COLL_MRT ? rates[i] / norm : rates[i];
+  }
 }
 // the same step through the real kernel (generic blocks + persistent chunk CTAs)
 void kh_step_kernel(void* p, int persistent_ctas) {

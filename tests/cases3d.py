@@ -65,7 +65,7 @@ def add_restricted(solver, spec, lp):
     return solver
 
 
-# per-pair MRT rates used by the tests (distinct even / odd rates so that a mix-up shows)
+# per-moment MRT rates used by the tests: every non-conserved moment relaxes at its own rate, so that a mix-up shows
 def mrt_rates(ndist, omega):
     r = np.full(27, omega)
     r[:ndist] = omega * (1.0 + 0.01 * np.arange(ndist) / ndist)

@@ -4,6 +4,8 @@ chunk templates, wall descriptors, ghost blocks, halo lists) can be checked agai
 in the product."""
 import numpy as np
 
+from lbm_b200.capi import pop_scatter, pop_slot
+
 OPP = {9: [1, 0, 3, 2, 6, 7, 4, 5, 8],
        19: [1, 0, 3, 2, 5, 4, 9, 8, 7, 6, 13, 12, 11, 10, 17, 16, 15, 14, 18],
        27: [1, 0, 3, 2, 5, 4, 9, 8, 7, 6, 13, 12, 11, 10, 17, 16, 15, 14, 25, 24, 23, 22, 21, 20, 19, 18, 26]}
@@ -24,12 +26,15 @@ def weights(q):
 def to_device(plan, aos, q):
     """reference-order AoS [n, Q] -> device SoA [Q, npad]"""
     dev = np.zeros((q, plan["npad"]))
-    dev[:, plan["ref2dev"]] = aos.T
+    pop_scatter(plan, dev, plan["ref2dev"].astype(np.int64), aos)   # per-direction in-chunk layouts (include/lbm_b200.h)
     return dev
 
 
 def gather(plan, A, q, values=None, uext=None):
-    """m_fold of every owned cell, in REFERENCE order, from device populations A [Q, npad]"""
+    """m_fold of every owned cell, in REFERENCE order, from device populations A [Q, npad] (population layout: direction j of
+    device cell c sits at pop_slot(plan, j, c); the result fold_dev is a plain per-cell array)"""
+    def P(j, cells):
+        return pop_slot(plan, j, cells)
     qm, ch, nsel = q - 1, plan["chunk"], plan["nsel"]
     opp = OPP[q]
     w = weights(q)
@@ -49,10 +54,10 @@ def gather(plan, A, q, values=None, uext=None):
             nbv = nb[sel]
             val = np.empty(ch)
             pull = nbv >= 0
-            val[pull] = A[j, nbv[pull] + off[pull]]
+            val[pull] = A[j, nbv[pull] + off[pull]]                # template offsets are layout positions already
             for s_miss in np.unique(sel[~pull]) if (~pull).any() else []:
                 m = (~pull) & (sel == s_miss)                     # the slots whose source lies in this missing neighbour chunk
-                v = A[opp[j], cells[m]].copy()
+                v = A[opp[j], P(opp[j], cells[m])].copy()
                 e = plan["wall_desc"][wid, s_miss, j]
                 if e[3] < 0:
                     # chunk on a pressure face: anti-bounce-back with the cell's own pressure entry (bnd_pressure.h:100)
@@ -73,6 +78,7 @@ def gather(plan, A, q, values=None, uext=None):
                 val[m] = v
             fold_dev[j, cells] = val
         fold_dev[qm, cells] = A[qm, cells]
+        assert plan["layout"][qm] == 0
     # generic range: link codes
     g0 = plan["gen_begin"]
     for g in range(plan["n_gen"]):
@@ -80,16 +86,16 @@ def gather(plan, A, q, values=None, uext=None):
         for j in range(qm):
             code = int(plan["codes"][j, g])
             if code >= 0:
-                fold_dev[j, cell] = A[j, code]
+                fold_dev[j, cell] = A[j, P(j, code)]
                 continue
             kind, pl = (code >> 28) & 7, code & 0x0FFFFFFF
             if kind == 0:
                 sc, sd = plan["copytab"][pl]
-                fold_dev[j, cell] = A[sd, sc]
+                fold_dev[j, cell] = A[sd, P(sd, sc)]
             elif kind == 1:
-                fold_dev[j, cell] = A[opp[j], cell]
+                fold_dev[j, cell] = A[opp[j], P(opp[j], cell)]
             elif kind == 2:
-                v = A[opp[j], cell]
+                v = A[opp[j], P(opp[j], cell)]
                 e = plan["addtab"][pl]
                 for a in range(int(e[3])):
                     v = v + e[a]
@@ -101,7 +107,7 @@ def gather(plan, A, q, values=None, uext=None):
                 vs = float(np.dot(u, u))
                 cs = 1.0 / 3.0
                 se = w[opp[j]] * p * (1.0 + cu * cu / (2.0 * cs * cs) - vs / (2.0 * cs))
-                fold_dev[j, cell] = -A[opp[j], cell] + 2 * se
+                fold_dev[j, cell] = -A[opp[j], P(opp[j], cell)] + 2 * se
             else:
                 fold_dev[j, cell] = values[pl]
         fold_dev[qm, cell] = A[qm, cell]
@@ -145,7 +151,7 @@ def partitioned_fold(r, plans, lps, f_glob, vars_glob, init_fold_glob, q, ndim):
     dev2glob = np.full(plan["npad"], -1)
     dev2glob[plan["ref2dev"][:lp.n_owned]] = own
     A = np.zeros((q, plan["npad"]))
-    A[:, plan["ref2dev"][:lp.n_owned]] = f_glob[own].T
+    pop_scatter(plan, A, plan["ref2dev"][:lp.n_owned].astype(np.int64), f_glob[own])
     vrecv = np.zeros((plan["n_vrecv"], ndim))
     ro = vo = 0
     for k, peer in enumerate(lp.peers):
@@ -155,7 +161,7 @@ def partitioned_fold(r, plans, lps, f_glob, vars_glob, init_fold_glob, q, ndim):
         q2glob = np.full(pq["npad"], -1)
         q2glob[pq["ref2dev"][:lq.n_owned]] = ownq
         Aq = np.zeros((q, pq["npad"]))
-        Aq[:, pq["ref2dev"][:lq.n_owned]] = f_glob[ownq].T
+        pop_scatter(pq, Aq, pq["ref2dev"][:lq.n_owned].astype(np.int64), f_glob[ownq])
         so, ns = sum(lq.send_count[:kq]), lq.send_count[kq]
         assert ns == lp.recv_count[k]
         A.reshape(-1)[plan["recv_index"][ro:ro + ns].astype(np.int64)] = Aq.reshape(-1)[pq["send_index"][so:so + ns].astype(np.int64)]

@@ -13,6 +13,7 @@ import pytest
 
 import lbm_b200
 from lbm_b200 import partition
+from lbm_b200.capi import pop_gather, pop_scatter
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -24,7 +25,7 @@ def kh(tmp_path_factory):
     pkg = os.path.join(ROOT, "lbm_b200")
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
                            "-Wno-unused-variable", "-Wno-unused-but-set-variable", "-Wno-unknown-pragmas", "-I", os.path.join(HERE, "c", "fake_cuda"),
-                           "-DLBM_THREADS=32", "-pthread",  # 32 threads per block: enough for the NSEL + 1 loaders of a chunk, cheap to start
+                           "-DLBM_THREADS=32", "-DLBM_FAST_THREADS=32", "-pthread",  # 32 threads per block: enough for the NSEL + 1 loaders of a chunk, cheap to start
                            os.path.join(HERE, "c", "kernels_harness.cpp"), "-o", so, "-L", pkg, "-llbm_b200", f"-Wl,-rpath,{pkg}"])
     L = C.CDLL(so)
     vp, dp = C.c_void_p, C.POINTER(C.c_double)
@@ -68,7 +69,7 @@ class Rank:
         self.glob = np.concatenate([np.arange(lp.lo, lp.hi), lp.ghosts])     # local cell -> global id
         self.r2d = self.plan["ref2dev"].astype(np.int64)
         A = self.arr("kh_A", self.q)
-        A[:, self.r2d[:lp.n_owned]] = init_f[lp.lo:lp.hi].T                     # lbm_b200_init: f = feq of the initial condition
+        pop_scatter(self.plan, A, self.r2d[:lp.n_owned], init_f[lp.lo:lp.hi])   # lbm_b200_init: f = feq of the initial condition
         vals = np.ctypeslib.as_array(L.kh_values(self.h), shape=(max(1, self.plan["n_values"]),))
         dev2loc = np.full(self.npad, -1)
         dev2loc[self.r2d] = np.arange(len(self.r2d))
@@ -79,7 +80,8 @@ class Rank:
         return np.ctypeslib.as_array(getattr(self.L, fn)(self.h), shape=(width, self.npad))
 
     def owned(self, fn, width):
-        return self.arr(fn, width)[:, self.r2d[:self.lp.n_owned]].T
+        """populations of the owned cells, [n_owned, Q], read through the per-direction in-chunk layouts"""
+        return pop_gather(self.plan, self.arr(fn, width), self.r2d[:self.lp.n_owned])
 
     def close(self):
         self.L.kh_destroy(self.h)

@@ -3,6 +3,8 @@ arrays lbm_b200_debug_plan exports and must reproduce the oracle's m_fold (= wha
 Covers the inverted push table, bounce-back / moving-wall / periodic-copy resolution, stale slots, chunk templates in device order,
 wall descriptors, and -- for partitioned plans -- ghost blocks and the halo index lists."""
 import numpy as np
+
+from lbm_b200.capi import pop_scatter
 import pytest
 
 import lbm_b200
@@ -121,7 +123,7 @@ def test_partitioned_plan_ghost_blocks_and_halo_lists(world, oracle_mod):
         # device state of this rank: owned cells from the global state; ghosts only through the halo lists of the peers
         A = np.zeros((ndist, plan["npad"]))
         own = np.arange(lp.lo, lp.hi)
-        A[:, plan["ref2dev"][:lp.n_owned]] = o.f[own].T
+        pop_scatter(plan, A, plan["ref2dev"][:lp.n_owned].astype(np.int64), o.f[own])
         ro = 0
         for k, q in enumerate(lp.peers):
             pq, lq = plans[q], lps[q]
@@ -131,7 +133,7 @@ def test_partitioned_plan_ghost_blocks_and_halo_lists(world, oracle_mod):
             assert ns == lp.recv_count[k]
             # what rank q packs for me: flat indices into ITS device arrays
             Aq = np.zeros((ndist, pq["npad"]))
-            Aq[:, pq["ref2dev"][:lq.n_owned]] = o.f[np.arange(lq.lo, lq.hi)].T
+            pop_scatter(pq, Aq, pq["ref2dev"][:lq.n_owned].astype(np.int64), o.f[np.arange(lq.lo, lq.hi)])
             wire = Aq.reshape(-1)[pq["send_index"][so:so + ns]]
             A.reshape(-1)[plan["recv_index"][ro:ro + ns]] = wire
             ro += ns
@@ -221,7 +223,7 @@ def test_partitioned_plan_pressure_velocity_halo(world, shape, ndist, oracle_mod
             dev2glob = np.full(plan["npad"], -1)
             dev2glob[plan["ref2dev"][:lp.n_owned]] = own
             A = np.zeros((ndist, plan["npad"]))
-            A[:, plan["ref2dev"][:lp.n_owned]] = o.f[own].T
+            pop_scatter(plan, A, plan["ref2dev"][:lp.n_owned].astype(np.int64), o.f[own])
             vrecv = np.zeros((plan["n_vrecv"], ndim))
             ro = vo = 0
             for k, q in enumerate(lp.peers):
@@ -230,7 +232,7 @@ def test_partitioned_plan_pressure_velocity_halo(world, shape, ndist, oracle_mod
                 q2glob = np.full(pq["npad"], -1)
                 q2glob[pq["ref2dev"][:lq.n_owned]] = np.arange(lq.lo, lq.hi)
                 Aq = np.zeros((ndist, pq["npad"]))
-                Aq[:, pq["ref2dev"][:lq.n_owned]] = o.f[np.arange(lq.lo, lq.hi)].T
+                pop_scatter(pq, Aq, pq["ref2dev"][:lq.n_owned].astype(np.int64), o.f[np.arange(lq.lo, lq.hi)])
                 so, ns = sum(lq.send_count[:kq]), lq.send_count[kq]
                 assert ns == lp.recv_count[k]
                 A.reshape(-1)[plan["recv_index"][ro:ro + ns]] = Aq.reshape(-1)[pq["send_index"][so:so + ns]]
