@@ -25,12 +25,17 @@ import time
 
 # torchrun exports OMP_NUM_THREADS=1; the host-side set-up (table generation, device plan) is OpenMP code, so give every
 # rank its share of the host cores before any OpenMP runtime is loaded
-if os.environ.get("OMP_NUM_THREADS", "1") == "1":
+# the reference arm runs on rank 0 alone (the other ranks exit at once): it gets ALL host cores whatever the launcher's world size is
+if "reference" in sys.argv and int(os.environ.get("RANK", "0")) == 0:
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+elif os.environ.get("OMP_NUM_THREADS", "1") == "1":
     os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
 
 # stdout carries exactly ONE JSON line: everything libraries print (NCCL banner, torchrun notes) goes to stderr
-_JSON_FD = os.dup(1)
-os.dup2(2, 1)
+_JSON_FD = 1
+if __name__ == "__main__":
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
 
 import numpy as np
 
@@ -60,20 +65,69 @@ def global_shape(size, ndim, world):
     return tuple(size * m for m in mult)
 
 
-def workload(size, lattice, rank=0, world=1):
+def box_table_numpy(shape, periodic, ndist):
+    """The benchmark box's push table in the reference's format, in plain numpy: cells in ascending order of the reference's curve key
+    (include/common/math/hilbert.h:16-48), column i = the cell one step along direction i of LBMethod<>::m_dirs (src/lbm/constants.h),
+    -1 outside.  Used by the reference arm so that it never loads the CUDA library; equal to lbm_b200_box_topology
+    (tests/test_bench_contract.py)."""
+    shape = tuple(int(v) for v in shape)
+    ndim = len(shape)
+    level = max(int(np.ceil(np.log2(max(shape)))), 1)
+    lut = np.array([0, 3, 1, 2, 5, 4, 6, 7], dtype=np.int64)
+    d2 = [[-1, 0], [1, 0], [0, -1], [0, 1], [1, 1], [1, -1], [-1, -1], [-1, 1]]
+    d3 = [[-1, 0, 0], [1, 0, 0], [0, -1, 0], [0, 1, 0], [0, 0, -1], [0, 0, 1], [-1, -1, 0], [-1, 1, 0], [1, -1, 0], [1, 1, 0],
+          [-1, 0, -1], [-1, 0, 1], [1, 0, -1], [1, 0, 1], [0, -1, -1], [0, -1, 1], [0, 1, -1], [0, 1, 1], [-1, -1, -1], [-1, -1, 1],
+          [-1, 1, -1], [-1, 1, 1], [1, -1, -1], [1, -1, 1], [1, 1, -1], [1, 1, 1]]
+    coords = [g.ravel() for g in np.meshgrid(*[np.arange(v, dtype=np.int32) for v in shape], indexing="ij")]
+    key = np.zeros(coords[0].shape[0], dtype=np.int64)
+    for l in range(level):
+        q = np.zeros(key.shape[0], dtype=np.int64)
+        for d in range(ndim):
+            q |= ((coords[d] >> (level - 1 - l)) & 1).astype(np.int64) << d
+        key = (key << ndim) | lut[q]
+    order = np.argsort(key, kind="stable")
+    del key
+    coords = [c[order] for c in coords]
+    n = order.shape[0]
+    strides = [int(np.prod(shape[d + 1:])) for d in range(ndim)]
+    lin2cell = np.empty(n, dtype=np.int64)
+    lin2cell[order] = np.arange(n)
+    nghbr = np.full((n, ndist - 1), -1, dtype=np.int64)
+    for i, dv in enumerate((d2 if ndim == 2 else d3)[:ndist - 1]):
+        lin = np.zeros(n, dtype=np.int64)
+        ok = np.ones(n, dtype=bool)
+        for d in range(ndim):
+            c = coords[d].astype(np.int64) + dv[d]
+            if periodic[d]:
+                c %= shape[d]
+            else:
+                ok &= (c >= 0) & (c < shape[d])
+            lin += np.clip(c, 0, shape[d] - 1) * strides[d]
+        col = lin2cell[lin]
+        col[~ok] = -1
+        nghbr[:, i] = col
+    return nghbr
+
+
+def workload(size, lattice, rank=0, world=1, native=True, shape=None):
     """Tables of the benchmark box in the reference's format + boundary conditions in application order.
-    world > 1: this rank's contiguous range of the SFC-ordered list plus ghost cells (lbm_b200/partition.py)."""
-    from lbm_b200.capi import box_topology
+    world > 1: this rank's contiguous range of the SFC-ordered list plus ghost cells (lbm_b200/partition.py).
+    native = False: tables from plain numpy (the reference arm must not touch the CUDA library)."""
     ndim, ndist = LATTICES[lattice]
     periodic = (1,) + (0,) * (ndim - 1)
     lp = None
     if world == 1:
-        shape = (size,) * ndim
-        nghbr, center, _ = box_topology(shape, periodic, want_center=True)
+        shape = (size,) * ndim if shape is None else tuple(shape)
+        center = None
+        if native:
+            from lbm_b200.capi import box_topology
+            nghbr, center, _ = box_topology(shape, periodic, want_center=True)
+        else:
+            nghbr = box_table_numpy(shape, periodic, ndist)
         n_owned = nghbr.shape[0]
     else:
         from lbm_b200 import partition
-        shape = global_shape(size, ndim, world)
+        shape = global_shape(size, ndim, world) if shape is None else tuple(shape)
         lp = partition.plan_rank(partition.BoxRows(shape, periodic, ndist), rank, world, 8 if ndim == 2 else 26)
         nghbr, center, n_owned = lp.nghbr, None, lp.n_owned
     names = ["-x", "+x", "-y", "+y", "-z", "+z"][:2 * ndim]
@@ -141,49 +195,68 @@ def case_workload(name, size, rank=0, world=1):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons of the device DURING the measurement, sampled in-process through NVML every few milliseconds
+    by a thread (the timed region of the default run lasts ~20 ms, too short for an `nvidia-smi -lms` loop; ctypes releases the GIL
+    while the C ABI call runs).  Covers warm-up and the timed steps."""
 
     def __init__(self, device):
-        self.path = tempfile.mktemp(prefix="lbm_clocks_", suffix=".csv")
-        self.proc = None
+        import threading
+        self.samples, self.reasons, self.ok, self._stop = [], set(), False, threading.Event()
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(device)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            import torch
+            # NVML enumerates physical devices: map through the UUID so that CUDA_VISIBLE_DEVICES does not shift the index
+            uuid = str(torch.cuda.get_device_properties(device).uuid)
+            self.h = None
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                u = pynvml.nvmlDeviceGetUUID(h)
+                u = u.decode() if isinstance(u, bytes) else u
+                if uuid in u:
+                    self.h = h
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.nv = pynvml
+            self.ok = True
+        except Exception as e:  # noqa: BLE001 -- any NVML problem just means "no clock record from here"
+            self.err = repr(e)
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, pw, util))
+                for k, b in bits.items():
+                    if r & b:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.004)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["NVML unavailable: " + getattr(self, "err", "?")]}
+        self._stop.set()
+        self.t.join(timeout=2)
         try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
-            t = [x.strip() for x in line.split(",")]
-            if len(t) < 7:
-                continue
-            try:
-                sm.append(float(t[0]))
-                smax.append(float(t[1]))
-                power.append(float(t[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, t[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        try:
-            os.remove(self.path)
-        except OSError:
-            pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+            smax = float(self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            smax = None
+        sm = [x[0] for x in self.samples]
+        busy = [x[0] for x in self.samples if x[1] > 250.0]   # samples with the device visibly under load (power above idle)
+        return {"sm_mhz": float(np.median(busy if busy else sm)) if sm else None, "sm_max_mhz": smax,
+                "power_w_max": max((x[1] for x in self.samples), default=None), "samples": len(sm), "samples_under_load": len(busy),
+                "reasons": sorted(self.reasons), "how": "NVML in-process (one query set takes several ms) from the first warm-up step to the end of the timed steps, incl. the residual-mode run"}
 
 
 def measured_peak():
@@ -298,14 +371,18 @@ def run_reference(args):
     from oracle import oracle
     oracle.build()
     if args.workload == "box":
-        sample = args.cpu_size
-        wl = workload(sample, args.lattice)
+        # the configuration of the GPU arm itself (default 256^3): ~0.8 s per step on 16 cores, so --steps 20 --warmup 5 ends in well
+        # under a minute; tables from plain numpy, the CUDA library is never loaded in this arm
+        sample = args.size
+        wl = workload(sample, args.lattice, native=False)
         args.collision = "bgk"
     else:
         sample = min(args.cpu_size, 64, args.size)
         wl = case_workload(args.workload, sample)
         args.lattice, args.collision = wl["lattice"], wl["collision"]
     o = oracle.Oracle(wl["ndim"], wl["ndist"], wl["nghbr"], OMEGA)
+    n = wl["nghbr"].shape[0]
+    del wl["nghbr"]
     if args.workload != "box":
         coll, om_minus, rates = collision_setup(args.collision, args.lattice)
         o.set_collision(coll, om_minus, rates)
@@ -315,7 +392,6 @@ def run_reference(args):
     t0 = time.perf_counter()
     o.step(args.steps)
     dt = time.perf_counter() - t0
-    n = wl["nghbr"].shape[0]
     mlups = n * args.steps / dt / 1e6
     unit = "MLUPS"
     line = {
@@ -324,8 +400,8 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(args, "CPU port of the reference time step (oracle/lbm_oracle.c), OpenMP like the reference"),
         "cpu_baseline": {"value": mlups, "unit": unit, "cores": oracle.threads(), "kind": "port",
-                         "sample": f"{args.lattice} {sample}^{wl['ndim']} {args.workload} ({n} cells), same BCs/omega/collision as the workload, "
-                                   f"{args.steps} steps; the reference binary cannot run D3Q19 (SURVEY section 0)"},
+                         "sample": f"{args.lattice} {sample}^{wl['ndim']} {args.workload} ({n} cells: the whole workload of the GPU arm), same "
+                                   f"BCs/omega/collision, {args.steps} steps; the reference binary cannot run D3Q19 (SURVEY section 0)"},
         "e2e": {"value": mlups, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     line["cpu_baseline"]["reference_binary_d2q9"] = reference_binary_d2q9() if args.workload == "box" else None
@@ -334,6 +410,8 @@ def run_reference(args):
 
 def config_dict(args, note):
     ndim, ndist = LATTICES[args.lattice]
+    if args.impl == "reference" and args.workload != "box":
+        args = argparse.Namespace(**{**vars(args), "size": min(args.cpu_size, 64, args.size)})   # the size that arm actually runs
     if args.workload != "box":
         what = {"sphere": "flow past a sphere (radius L/10 at the centre of a cube, pressure in-/outlet on -x/+x, bounce-back walls and "
                           "sphere; BASELINE.json configs[3], 3D form of test/sphere/sphere_ns.json)",
@@ -352,6 +430,52 @@ def config_dict(args, note):
             if args.gpus > 1 else "single GPU", "note": note}
 
 
+def parity_check(rank, world, local, dist, torch, lbm_b200):
+    """Driver-visible parity of the (multi-rank) path: 5 STRICT steps of a D3Q19 box with 64^3 cells per rank, cut into `world`
+    contiguous SFC ranges and exchanged over NCCL exactly like the timed run; rank 0 compares the owned m_f of all ranks, bit for bit,
+    with the single-domain CPU oracle (the checker, never the thing measured) and reports the SHA-256 of both."""
+    import hashlib
+    per, steps = 64, 5
+    wl = workload(per, "D3Q19", rank, world)
+    s = lbm_b200.Solver(3, 19, wl["nghbr"], OMEGA, arithmetic=lbm_b200.STRICT, device=local, track_vars=0,
+                        stream=torch.cuda.current_stream().cuda_stream)
+    apply_bcs(s, wl)
+    if world > 1:
+        from lbm_b200.capi import comm_unique_id
+        uid = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        wl["lp"].apply_halo(s)
+        s.comm_init(uid[0], rank, world)
+    s.init()
+    s.step(steps)
+    mine = torch.from_numpy(np.ascontiguousarray(s.f[:wl["n_owned"]])).cuda()
+    parts = [mine]
+    if world > 1:
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        torch.cuda.synchronize()
+        dist.barrier()
+    s.close()
+    if rank != 0:
+        return None
+    from oracle import oracle
+    oracle.build()
+    shape = wl["shape"]
+    ref = workload(per, "D3Q19", native=False, shape=shape)
+    o = oracle.Oracle(3, 19, ref["nghbr"], OMEGA)
+    apply_bcs(o, ref)
+    o.init()
+    o.step(steps)
+    got = torch.cat(parts).cpu().numpy()
+    want = np.ascontiguousarray(o.f)
+    same = got.shape == want.shape and np.array_equal(got, want)
+    out = {"result": "bit-identical" if same else "DIFFERENT", "what": f"owned m_f of {world} rank(s) after {steps} STRICT fp64 steps, D3Q19 box "
+           f"{'x'.join(map(str, shape))} ({per}^3 per rank), vs the single-domain CPU oracle",
+           "sha256_gpu": hashlib.sha256(got.tobytes()).hexdigest()[:16], "sha256_oracle": hashlib.sha256(want.tobytes()).hexdigest()[:16]}
+    o.close()
+    return out
+
+
 def run_ours(args):
     import torch
     import lbm_b200
@@ -363,6 +487,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     arithmetic = lbm_b200.FAST if args.arithmetic == "fast" else lbm_b200.STRICT
+    parity = None if args.no_parity else parity_check(rank, world, local, dist if world > 1 else None, torch, lbm_b200)
     t_setup = time.perf_counter()
     if args.workload == "box":
         wl = workload(args.size, args.lattice, rank, world)
@@ -386,6 +511,7 @@ def run_ours(args):
         wl["lp"].apply_halo(s)
         s.comm_init(uid[0], rank, world)
     s.init()
+    nghbr_keep = wl["nghbr"] if args.conv_interval > 0 else None   # the residual-mode run below sets up a second solver
     del wl["nghbr"]
     t_setup = time.perf_counter() - t_setup
     st0 = s.stats()
@@ -396,20 +522,54 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None
     s.step(args.warmup)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = s.stats()["launches"]
     ms_total, ms_main = s.step_timed(args.steps)
     launches = s.stats()["launches"] - l0
     barrier()
-    clocks = sampler.stop() if sampler else None
     if world > 1:
         t = torch.tensor([ms_total, ms_main], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, ms_main = float(t[0]), float(t[1])
     n_global = args.size ** ndim * world if args.workload == "box" else wl["n_global"]
     value = n_global * args.steps / (ms_total * 1e-3) / 1e6
+    # ---- the same steps with the residual bookkeeping the reference does (convergenceCondition every conv_interval steps,
+    # src/lbm/solver.cpp:233-263): m_vars / m_varsold are written by the fused kernel on the steps the residual needs, the reduction
+    # and (partitioned) its all-reduce run inside the timed region
+    with_residual = None
+    if args.conv_interval > 0:
+        s.close()
+        s = lbm_b200.Solver(ndim, ndist, nghbr_keep, OMEGA, arithmetic=arithmetic, device=local, track_vars=args.conv_interval, stream=stream,
+                            collision=coll, omega_minus=om_minus, mrt_rates=rates, precision=precision)
+        apply_bcs(s, wl)
+        if world > 1:
+            uid = [comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            wl["lp"].apply_halo(s)
+            s.comm_init(uid[0], rank, world)
+        s.init()
+        s.step(args.conv_interval * max(1, args.warmup // args.conv_interval))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        done, res = 0, None
+        while done < args.steps:
+            k = min(args.conv_interval, args.steps - done)
+            s.step(k)
+            done += k
+            if k == args.conv_interval:
+                res = s.residual()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        with_residual = {"value": n_global * args.steps / (float(t[0]) * 1e-3) / 1e6, "unit": "MLUPS", "conv_interval": args.conv_interval,
+                         "residual": None if res is None else [float(x) for x in res[0]], "diverged": None if res is None else bool(res[1])}
+
+    clocks = sampler.stop() if sampler else None   # NVML queries contend with the driver: none while the host-side e2e path is timed
 
     # ---- e2e: state in pinned host buffers, through the C ABI: upload m_fold (the input of a time step; m_f is overwritten by the
     # collision before anything reads it, solver.cpp:601-613), K steps, download the fields
@@ -472,6 +632,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f64", "data": "synthetic",
         "config": config_dict(args, f"{st0['cells_fast']} of {st0['ncells']} cells on the index-free chunk path; setup {t_setup:.1f} s"),
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "with_residual": with_residual, "parity": parity,
     }
     emit(line)
 
@@ -495,6 +656,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, dest="cpu_budget")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
     ap.add_argument("--no-e2e", action="store_true", dest="no_e2e")
+    ap.add_argument("--conv-interval", type=int, default=10, dest="conv_interval",
+                    help="second measurement with the reference's residual bookkeeping every N steps inside the timed region (0: skip)")
+    ap.add_argument("--no-parity", action="store_true", dest="no_parity")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

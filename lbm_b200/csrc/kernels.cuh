@@ -460,8 +460,10 @@ __device__ __forceinline__ void update_and_store(const DevParams<Real>& p, int32
   constexpr int Q = L::Q, D = L::D;
   Real rho, u[D], f[Q];
   collide_cell<L, Real, STRICT, COLL>(p, fold, f, rho, u);
+  if(p.B != nullptr) { // nullptr: moments only (lbm_b200_get_moments)
 #pragma unroll
-  for(int j = 0; j < Q; ++j) p.B[pop_index<L>(j, cell, p.stride, p.pr)] = f[j];
+    for(int j = 0; j < Q; ++j) p.B[pop_index<L>(j, cell, p.stride, p.pr)] = f[j];
+  }
   store_vars<L, Real>(p, cell, rho, u);
 }
 
@@ -484,19 +486,23 @@ __global__ void __launch_bounds__(kThreads, LBM_MINBLOCKS) k_step_generic(const 
   update_and_store<L, Real, STRICT, COLL>(p, cell, fold);
 }
 
-// ---- chunk path: persistent CTAs, the pulled populations of a whole chunk staged in shared memory ------------------------
-// One CTA per SM walks SFC chunks handed out by a global ticket counter.  For every chunk the (Q-1) moving populations of
-// its CH cells -- already PULLED, i.e. shifted by c_j -- are copied global -> shared with cp.async, NSTAGE chunks deep, so
-// the loads of the next chunks are in flight while this one is collided.  Thanks to the per-direction in-chunk layouts
-// (lattice.h) every copy is a 16-byte piece of a whole 64-byte row that lies in exactly one (neighbour) chunk: no partially
-// used DRAM sector, no per-cell index, no template table -- the source of a row follows from the direction's constants and
-// 3^D neighbour-chunk bases.  Rows whose source chunk is a wall are redirected to the bounce-back source (same row of the
-// opposite direction, which shares the layout); addends / anti-bounce-back are applied when the cell is collided.  Threads
-// then read their cell's Q-1 values from shared memory (XOR-swizzled 16-byte units: conflict free), collide, write the
-// result back IN PLACE, and the stage is copied out shared -> global as contiguous 4 KB blocks per direction with 128-bit
-// loads / stores.  The rest population never moves: it goes through registers.
+// ---- chunk path: persistent CTAs, the pulled populations of a tile staged in shared memory ----------------------------------
+// Two CTAs per SM walk TILES (a whole SFC chunk, or -- fp64 -- its lower / upper half along the slowest lexicographic axis)
+// handed out by a global ticket counter.  For every tile the (Q-1) moving populations of its cells -- already PULLED, i.e.
+// shifted by c_j -- are copied global -> shared with cp.async, NSTAGE tiles deep, so the loads of the next tiles are in flight
+// while this one is collided.  Thanks to the per-direction in-chunk layouts (lattice.h) every copy is a 16-byte piece of a
+// whole 32-byte sector that lies in exactly one (neighbour) chunk: no partially used DRAM sector, no per-cell index, no
+// template table -- the source of a piece follows from the direction's constants and 3^D neighbour-chunk bases.  Pieces whose
+// source chunk is a wall are redirected to the bounce-back source (same position in the opposite direction's array, which
+// shares the layout); addends / anti-bounce-back are applied when the cell is collided.  Threads then read their cell's Q-1
+// values from shared memory (XOR-swizzled 16-byte units: conflict free), collide, write the result back IN PLACE, and the
+// stage is copied out shared -> global with 128-bit loads / stores.  The rest population never moves: it goes through
+// registers.  Two independent CTAs per SM overlap each other's phases (copy issue / collide / copy out).
 #ifndef LBM_FAST_THREADS
-#define LBM_FAST_THREADS 512
+#define LBM_FAST_THREADS 256
+#endif
+#ifndef LBM_FAST_MINBLOCKS
+#define LBM_FAST_MINBLOCKS 2
 #endif
 constexpr int kFastThreads = LBM_FAST_THREADS;
 
@@ -506,50 +512,69 @@ struct FastCfg {
   static constexpr int LB  = L::CHUNK_LEVELS;            // bits per axis inside a chunk
   static constexpr int S   = 1 << LB;                    // cells per axis
   static constexpr int EPU = 16 / static_cast<int>(sizeof(Real)); // reals per 16-byte unit
-  static constexpr int UPD = CH / EPU;                   // 16-byte units per direction
-  static constexpr int STAGE_BYTES = QM * CH * static_cast<int>(sizeof(Real));
+  // tiles per chunk: halves along the slowest lexicographic axis, as long as a half still covers whole 32-byte sectors along
+  // that axis (3D fp32: 8 floats = one sector, so the chunk stays whole)
+#ifdef LBM_FAST_NSPLIT
+  static constexpr int NSPLIT = LBM_FAST_NSPLIT;
+#else
+  static constexpr int NSPLIT = (D == 3 && sizeof(Real) == 4) ? 1 : 2;
+#endif
+  static constexpr int TS  = CH / NSPLIT;                // cells per tile
+  static constexpr int TB  = NSPLIT == 2 ? LB - 1 : LB;  // bits of the slowest axis inside a tile
+  static constexpr int UPD = TS / EPU;                   // 16-byte units per direction and tile
+  static constexpr int STAGE_BYTES = QM * TS * static_cast<int>(sizeof(Real));
 #ifdef LBM_FAST_STAGES
   static constexpr int NSTAGE = LBM_FAST_STAGES;
 #else
-  static constexpr int NSTAGE = (220 * 1024 / STAGE_BYTES) >= 4 ? 4 : (220 * 1024 / STAGE_BYTES);
+  static constexpr int NSTAGE = (112000 / STAGE_BYTES) >= 4 ? 4 : (112000 / STAGE_BYTES);
 #endif
   static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES;
   static constexpr int RN = NSTAGE + 1;                  // ring of neighbour-base rows
   static constexpr int RT = NSTAGE + 2;                  // ring of tickets
-  static constexpr int PAST_END = NSTAGE + 1;            // tickets every CTA draws beyond the last chunk
-  static constexpr int CPT = (CH + kFastThreads - 1) / kFastThreads; // cells per thread and chunk
+  static constexpr int PAST_END = NSTAGE + 2;            // tickets every CTA draws beyond the last tile
+  static constexpr int CPT = (TS + kFastThreads - 1) / kFastThreads; // cells per thread and tile
   static constexpr int SELF = D == 2 ? 4 : 13;
-  static_assert(NSTAGE >= 2, "the chunk pipeline needs two stages");
+  static_assert(NSTAGE >= 2, "the tile pipeline needs two stages");
 };
 
-// per-direction constants of the copy engine, packed (computed at compile time, kept in shared memory for run-time indexing)
-//   bits 0-1 layout | 2-3 shift along the fastest axis + 1 | 4-5 middle + 1 | 6-7 slowest + 1 | 8-12 opposite direction |
-//   13-16 / 17-20 / 21-24 selector weight (3^axis) of the fastest / middle / slowest axis
-template <class L>
-__device__ __forceinline__ constexpr uint32_t dir_word(int j) {
-  const int lay = layout_of<L>(j);
-  int ax[3] = {0, 1, 2};
-  if(lay == 1) { ax[0] = 1; ax[1] = 2; ax[2] = 0; }
-  if(lay == 2) { ax[0] = 2; ax[1] = 0; ax[2] = 1; }
-  const int pow3[3] = {1, 3, 9};
-  uint32_t  w = static_cast<uint32_t>(lay) | (static_cast<uint32_t>(L::opp(j)) << 8);
-  for(int k = 0; k < 3; ++k) {
-    const int c = ax[k] < L::D ? L::c(j, ax[k] < L::D ? ax[k] : 0) : 0;
-    w |= static_cast<uint32_t>(c + 1) << (2 + 2 * k);
-    w |= static_cast<uint32_t>(ax[k] < L::D ? pow3[ax[k]] : 0) << (13 + 4 * k);
-  }
-  return w;
+// lexicographic in-chunk offset o (x fastest) -> position in a direction's array: lay_perm (lattice.h).  Inside a TILE the same
+// order is kept with the slowest lexicographic axis (z; y in 2D) reduced to its TB tile bits:
+//   tile-local lexicographic offset ot = x | y << LB | zt << 2 LB      (3D; 2D: x | yt << LB)
+//   tile position of layout 0: ot;  layout 1: y | zt << LB | x << (LB + TB);  layout 2: zt | x << TB | y << (TB + LB)
+template <class L, class Real>
+__device__ __forceinline__ constexpr int tile_perm(int lay, int ot) {
+  using C = FastCfg<L, Real>;
+  if(L::D != 3 || lay == 0) return ot;
+  const int M = C::S - 1, x = ot & M, y = (ot >> C::LB) & M, zt = ot >> (2 * C::LB);
+  return lay == 1 ? (y | (zt << C::LB) | (x << (C::LB + C::TB))) : (zt | (x << C::TB) | (y << (C::TB + C::LB)));
 }
+// tile position (layout `lay`, tile half h) -> position in the chunk's array of that direction
+template <class L, class Real>
+__device__ __forceinline__ constexpr int tile_to_chunk_pos(int lay, int tp, int h) {
+  using C = FastCfg<L, Real>;
+  if(C::NSPLIT == 1) return tp;
+  if(L::D != 3 || lay == 0) return tp + h * C::TS;
+  const int M = C::S - 1, MT = (1 << C::TB) - 1;
+  if(lay == 1) return (tp & M) | ((((tp >> C::LB) & MT) | (h << C::TB)) << C::LB) | ((tp >> (C::LB + C::TB)) << (2 * C::LB));
+  return (tp & MT) | (h << C::TB) | (((tp >> C::TB) & M) << C::LB) | ((tp >> (C::TB + C::LB)) << (2 * C::LB));
+}
+
+// per-direction layout ids kept in shared memory for run-time indexing (the step-0 copy loop)
 template <class L, int J>
 __device__ __forceinline__ void fill_dir_words(uint32_t* s_dir, int tid) {
   if constexpr(J < L::Q - 1) {
-    constexpr uint32_t w = dir_word<L>(J);
+    constexpr uint32_t w = static_cast<uint32_t>(layout_of<L>(J));
     if(tid == J) s_dir[J] = w;
     fill_dir_words<L, J + 1>(s_dir, tid);
   }
 }
 template <class L>
-__device__ __forceinline__ constexpr bool dir_aligned(int j) { return ((dir_word<L>(j) >> 2) & 3u) == 1u; }
+__device__ __forceinline__ constexpr bool dir_aligned(int j) {
+  // the direction does not move along the fastest axis of its layout
+  const int lay = layout_of<L>(j);
+  const int ax0 = lay == 0 ? 0 : (lay == 1 ? 1 : 2);
+  return L::c(j, ax0 < L::D ? ax0 : 0) == 0;
+}
 template <class L>
 __device__ __forceinline__ constexpr int count_aligned() {
   int n = 0;
@@ -566,32 +591,30 @@ __device__ __forceinline__ constexpr int nth_dir(int k, bool aligned) {
     }
   return 0;
 }
-template <class L, int K>
-__device__ __forceinline__ void fill_dir_lists(uint8_t* s_list, int tid) {
-  constexpr int NA = count_aligned<L>();
-  if constexpr(K < L::Q - 1) {
-    constexpr int j = K < NA ? nth_dir<L>(K, true) : nth_dir<L>(K - NA, false);
-    if(tid == K) s_list[K] = static_cast<uint8_t>(j);
-    fill_dir_lists<L, K + 1>(s_list, tid);
-  }
-}
 
-// position inside a stage of element `pos` (in the direction's layout): XOR swizzle of the 16-byte unit index, so that the
-// cells of a (half-)warp hit different banks whichever axis is the fastest one of the direction
+// position inside a stage of element `tp` (tile position in the direction's layout): XOR swizzle of the 16-byte unit index, so
+// that the cells of a (half-)warp hit different banks whichever axis is the fastest one of the direction (verified by brute force
+// for fp64: conflict free in all three layouts, whole chunks and half-chunk tiles)
 template <class L, class Real>
-__device__ __forceinline__ constexpr int stage_swizzle(int lay, int pos) {
-  if(L::D != 3) return pos;
+__device__ __forceinline__ constexpr int stage_swizzle(int lay, int tp) {
+  using C = FastCfg<L, Real>;
+  if(L::D != 3) return tp;
   if(sizeof(Real) == 8) {
-    if(lay == 0) return pos ^ (((pos >> 6) & 1) << 2);
-    if(lay == 1) return pos ^ (((pos >> 6) & 3) << 1);
-    return pos ^ ((((pos >> 4) & 1) << 1) | (((pos >> 6) & 1) << 2));
+    if(C::NSPLIT == 2) {
+      if(lay == 0) return tp ^ (((tp >> 6) & 1) << 2);
+      if(lay == 1) return tp ^ (((tp >> 5) & 3) << 1);
+      return tp ^ (((tp >> 5) & 1) << 1);
+    }
+    if(lay == 0) return tp ^ (((tp >> 6) & 1) << 2);
+    if(lay == 1) return tp ^ (((tp >> 6) & 3) << 1);
+    return tp ^ ((((tp >> 4) & 1) << 1) | (((tp >> 6) & 1) << 2));
   }
-  if(lay == 0) return pos ^ (((pos >> 6) & 1) << 4);
-  if(lay == 1) return pos ^ ((((pos >> 6) & 1) << 2) | (((pos >> 7) & 1) << 4));
-  return pos ^ (((pos >> 6) & 1) << 2);
+  if(lay == 0) return tp ^ (((tp >> 6) & 1) << 4);
+  if(lay == 1) return tp ^ ((((tp >> 6) & 1) << 2) | (((tp >> 7) & 1) << 4));
+  return tp ^ (((tp >> 6) & 1) << 2);
 }
 
-// virtual thread index -> lexicographic in-chunk offset.  3D: lane bits are (x0, x1, y0, z0, x2), which together with the
+// virtual thread index -> tile-local lexicographic offset.  3D: lane bits are (x0, x1, y0, z0, x2), which together with the
 // swizzle above makes the shared-memory accesses of all three layouts conflict free (fp64); 2D: plain row order.
 template <class L>
 __device__ __forceinline__ constexpr int thread_cell(int v) {
@@ -637,12 +660,14 @@ extern __shared__ __align__(128) unsigned char lbm_dyn_smem[];
 alignas(128) static unsigned char lbm_dyn_smem[232448]; // CPU harness: one block at a time
 #endif
 
-// ---- the copy engine: which row of which (neighbour) chunk a 16-byte unit of a stage comes from.  The direction is a template
-// parameter, so shifts, selector weights and layout fold to immediates; what is left per unit and chunk is one shared-memory read
-// of the neighbour base, one address and the cp.async itself.
-template <class L, class Real, int J, bool ALIGNED>
+// ---- the copy engine: which sector of which (neighbour) chunk a 16-byte unit of a stage comes from.  The direction is a template
+// parameter, so shifts, selector weights and layout fold to immediates; what is left per unit and tile is one shared-memory read
+// of the neighbour base, one address and the cp.async itself.  WALLS = false is the variant for interior chunks (no neighbour is
+// missing, the chunk's wall descriptor id is -1): it skips the bounce-back redirection.  tp = tile position of the unit's first
+// element in direction J's layout, h = which half of the chunk the tile is.
+template <class L, class Real, int J, bool ALIGNED, bool WALLS>
 __device__ __forceinline__ void issue_unit(const DevParams<Real>& p, const Real* __restrict__ Abuf, Real* __restrict__ stg,
-                                           const int32_t* __restrict__ nb, int32_t base, int pos0) {
+                                           const int32_t* __restrict__ nb, int32_t base, int tp, int h) {
   using C = FastCfg<L, Real>;
   constexpr int lay  = layout_of<L>(J);
   constexpr int AX0  = lay == 0 ? 0 : (lay == 1 ? 1 : 2), AX1 = lay == 0 ? 1 : (lay == 1 ? 2 : 0), AX2 = lay == 0 ? 2 : (lay == 1 ? 0 : 1);
@@ -651,6 +676,7 @@ __device__ __forceinline__ void issue_unit(const DevParams<Real>& p, const Real*
   constexpr int sb = AX1 < L::D ? L::c(J, AX1 < L::D ? AX1 : 0) : 0;
   constexpr int sc = AX2 < L::D ? L::c(J, AX2 < L::D ? AX2 : 0) : 0;
   constexpr int MASK = C::S - 1;
+  const int pos0 = tile_to_chunk_pos<L, Real>(lay, tp, h);
   int sel = C::SELF, srcpos = pos0;
   if constexpr(sa != 0) {
     const int a2 = (pos0 & MASK) - sa;
@@ -668,82 +694,91 @@ __device__ __forceinline__ void issue_unit(const DevParams<Real>& p, const Real*
     srcpos = (srcpos & (C::S * C::S - 1)) | ((c2 & MASK) << (2 * C::LB));
   }
   const int32_t nbv = nb[sel];
-  // wall: the bounce-back source, i.e. the same row of the opposite direction's array (bnd_dirichlet.h:92)
-  const Real* src = nbv >= 0 ? Abuf + static_cast<size_t>(J) * p.stride + nbv + srcpos
-                             : Abuf + static_cast<size_t>(L::opp(J)) * p.stride + base + pos0;
-  Real* dst = stg + J * C::CH + stage_swizzle<L, Real>(lay, pos0);
-  if constexpr(ALIGNED) cp_async_16(dst, src);
-  else cp_async_small<static_cast<int>(sizeof(Real))>(dst, src);
+  // element offsets fit 32 bits (plan.hpp refuses Q * npad >= 2^32)
+  const uint32_t jbase = static_cast<uint32_t>(J) * static_cast<uint32_t>(p.stride);
+  uint32_t off = jbase + static_cast<uint32_t>(nbv + srcpos);
+  if constexpr(WALLS) {
+    // wall: the bounce-back source, i.e. the same position in the opposite direction's array (bnd_dirichlet.h:92)
+    if(nbv < 0) off = static_cast<uint32_t>(L::opp(J)) * static_cast<uint32_t>(p.stride) + static_cast<uint32_t>(base + pos0);
+  }
+  Real* dst = stg + J * C::TS + stage_swizzle<L, Real>(lay, tp);
+  if constexpr(ALIGNED) cp_async_16(dst, Abuf + off);
+  else cp_async_small<static_cast<int>(sizeof(Real))>(dst, Abuf + off);
 }
 
-// directions whose fastest layout axis is free of the shift: 16-byte units; the others (2D with c_x != 0, D3Q27 corners): reals
-template <class L, class Real, int LI>
-__device__ __forceinline__ void issue_aligned_dirs(const DevParams<Real>& p, const Real* __restrict__ Abuf, Real* __restrict__ stg,
-                                                   const int32_t* __restrict__ nb, int32_t base, int tid) {
+// Work distribution: the kFastThreads threads form NG = kFastThreads / UNITS groups (UNITS = units per direction and tile);
+// group g serves the directions LI = g, g + NG, ... of the list, every thread one unit per direction -- the same unit for all of
+// them, so the decode of the unit index is shared.  With fewer threads than units a thread loops over its units instead.
+template <class L, class Real, bool ALIGNED, bool WALLS, int LI, int STEP>
+__device__ __forceinline__ void issue_dirs(const DevParams<Real>& p, const Real* __restrict__ Abuf, Real* __restrict__ stg,
+                                           const int32_t* __restrict__ nb, int32_t base, int h, int unit_first, int unit_step) {
   using C = FastCfg<L, Real>;
-  if constexpr(LI < count_aligned<L>()) {
-    constexpr int J = nth_dir<L>(LI, true);
-    if constexpr(kFastThreads >= C::UPD) {
-      static_assert(kFastThreads % C::UPD == 0, "thread count must be a multiple of the units per direction");
-      if(tid / C::UPD == LI % (kFastThreads / C::UPD)) issue_unit<L, Real, J, true>(p, Abuf, stg, nb, base, (tid % C::UPD) * C::EPU);
-    } else {
-      for(int u = tid; u < C::UPD; u += kFastThreads) issue_unit<L, Real, J, true>(p, Abuf, stg, nb, base, u * C::EPU);
-    }
-    issue_aligned_dirs<L, Real, LI + 1>(p, Abuf, stg, nb, base, tid);
+  constexpr int N = ALIGNED ? count_aligned<L>() : C::QM - count_aligned<L>();
+  constexpr int UNITS = ALIGNED ? C::UPD : C::TS, EPU = ALIGNED ? C::EPU : 1;
+  if constexpr(LI < N) {
+    constexpr int J = nth_dir<L>(LI, ALIGNED);
+    for(int u = unit_first; u < UNITS; u += unit_step) issue_unit<L, Real, J, ALIGNED, WALLS>(p, Abuf, stg, nb, base, u * EPU, h);
+    issue_dirs<L, Real, ALIGNED, WALLS, LI + STEP, STEP>(p, Abuf, stg, nb, base, h, unit_first, unit_step);
   }
 }
-template <class L, class Real, int LI>
-__device__ __forceinline__ void issue_unaligned_dirs(const DevParams<Real>& p, const Real* __restrict__ Abuf, Real* __restrict__ stg,
-                                                     const int32_t* __restrict__ nb, int32_t base, int tid) {
+template <class L, class Real, bool ALIGNED, bool WALLS, int G>
+__device__ __forceinline__ void issue_groups(const DevParams<Real>& p, const Real* __restrict__ Abuf, Real* __restrict__ stg,
+                                             const int32_t* __restrict__ nb, int32_t base, int h, int tid) {
   using C = FastCfg<L, Real>;
-  if constexpr(LI < C::QM - count_aligned<L>()) {
-    constexpr int J = nth_dir<L>(LI, false);
-    if constexpr(kFastThreads >= C::CH) {
-      if(tid / C::CH == LI % (kFastThreads / C::CH)) issue_unit<L, Real, J, false>(p, Abuf, stg, nb, base, tid % C::CH);
-    } else {
-      for(int u = tid; u < C::CH; u += kFastThreads) issue_unit<L, Real, J, false>(p, Abuf, stg, nb, base, u);
-    }
-    issue_unaligned_dirs<L, Real, LI + 1>(p, Abuf, stg, nb, base, tid);
+  constexpr int UNITS = ALIGNED ? C::UPD : C::TS;
+  constexpr int NG = kFastThreads >= UNITS ? kFastThreads / UNITS : 1;
+  static_assert(kFastThreads >= UNITS ? kFastThreads % UNITS == 0 : UNITS % kFastThreads == 0, "thread count vs units per direction");
+  if constexpr(G < NG) {
+    if(NG == 1 || tid / UNITS == G)
+      issue_dirs<L, Real, ALIGNED, WALLS, G, NG>(p, Abuf, stg, nb, base, h, NG == 1 ? tid : tid % UNITS, NG == 1 ? kFastThreads : UNITS);
+    issue_groups<L, Real, ALIGNED, WALLS, G + 1>(p, Abuf, stg, nb, base, h, tid);
   }
 }
 
-// issue the copies of one chunk into a stage: all moving populations of its CH cells, pulled
+// issue the copies of one tile into a stage: all moving populations of its cells, pulled
 template <class L, class Real>
-__device__ __forceinline__ void issue_chunk_loads(const DevParams<Real>& p, const Real* __restrict__ Abuf, Real* __restrict__ stg,
-                                                  const int32_t* __restrict__ nb, int32_t base, const uint32_t* __restrict__ s_dir, int tid) {
+__device__ __forceinline__ void issue_tile_loads(const DevParams<Real>& p, const Real* __restrict__ Abuf, Real* __restrict__ stg,
+                                                 const int32_t* __restrict__ nb, int32_t base, int h, const uint32_t* __restrict__ s_dir, int tid) {
   using C = FastCfg<L, Real>;
   if(p.first) {
     // step 0: m_fold is the initial condition itself -- every cell reads its own slots (no shift, no walls)
     for(int g = tid; g < C::QM * C::UPD; g += kFastThreads) {
-      const int J = g / C::UPD, pos0 = (g % C::UPD) * C::EPU;
-      cp_async_16(stg + J * C::CH + stage_swizzle<L, Real>(s_dir[J] & 3, pos0), Abuf + static_cast<size_t>(J) * p.stride + base + pos0);
+      const int J = g / C::UPD, tp = (g % C::UPD) * C::EPU, lay = static_cast<int>(s_dir[J]);
+      cp_async_16(stg + J * C::TS + stage_swizzle<L, Real>(lay, tp),
+                  Abuf + static_cast<size_t>(J) * p.stride + base + tile_to_chunk_pos<L, Real>(lay, tp, h));
     }
     return;
   }
-  issue_aligned_dirs<L, Real, 0>(p, Abuf, stg, nb, base, tid);
-  issue_unaligned_dirs<L, Real, 0>(p, Abuf, stg, nb, base, tid);
+  if(nb[C::NSEL] < 0) { // interior chunk
+    issue_groups<L, Real, true, false, 0>(p, Abuf, stg, nb, base, h, tid);
+    issue_groups<L, Real, false, false, 0>(p, Abuf, stg, nb, base, h, tid);
+  } else {
+    issue_groups<L, Real, true, true, 0>(p, Abuf, stg, nb, base, h, tid);
+    issue_groups<L, Real, false, true, 0>(p, Abuf, stg, nb, base, h, tid);
+  }
 }
 
-// copy a collided stage out: per direction one contiguous CH-real block of buffer B, 128-bit shared loads and global stores
-template <class L, class Real, int J>
-__device__ __forceinline__ void copy_out_dirs(const DevParams<Real>& p, const Real* __restrict__ stg, int32_t base, int tid) {
+// copy a collided stage out to buffer B: 128-bit shared loads and global stores, whole 32-byte sectors
+template <class L, class Real, int J, int STEP>
+__device__ __forceinline__ void copy_out_dirs(const DevParams<Real>& p, const Real* __restrict__ stg, int32_t base, int h, int unit_first, int unit_step) {
   using C = FastCfg<L, Real>;
   if constexpr(J < C::QM) {
     constexpr int lay = layout_of<L>(J);
-    if constexpr(kFastThreads >= C::UPD) {
-      if(tid / C::UPD == J % (kFastThreads / C::UPD)) {
-        const int pos0 = (tid % C::UPD) * C::EPU;
-        *reinterpret_cast<uint4*>(p.B + static_cast<size_t>(J) * p.stride + base + pos0) =
-            *reinterpret_cast<const uint4*>(stg + J * C::CH + stage_swizzle<L, Real>(lay, pos0));
-      }
-    } else {
-      for(int u = tid; u < C::UPD; u += kFastThreads) {
-        const int pos0 = u * C::EPU;
-        *reinterpret_cast<uint4*>(p.B + static_cast<size_t>(J) * p.stride + base + pos0) =
-            *reinterpret_cast<const uint4*>(stg + J * C::CH + stage_swizzle<L, Real>(lay, pos0));
-      }
+    for(int u = unit_first; u < C::UPD; u += unit_step) {
+      const int tp = u * C::EPU;
+      const uint32_t off = static_cast<uint32_t>(J) * static_cast<uint32_t>(p.stride) + static_cast<uint32_t>(base + tile_to_chunk_pos<L, Real>(lay, tp, h));
+      *reinterpret_cast<uint4*>(p.B + off) = *reinterpret_cast<const uint4*>(stg + J * C::TS + stage_swizzle<L, Real>(lay, tp));
     }
-    copy_out_dirs<L, Real, J + 1>(p, stg, base, tid);
+    copy_out_dirs<L, Real, J + STEP, STEP>(p, stg, base, h, unit_first, unit_step);
+  }
+}
+template <class L, class Real, int G>
+__device__ __forceinline__ void copy_out_groups(const DevParams<Real>& p, const Real* __restrict__ stg, int32_t base, int h, int tid) {
+  using C = FastCfg<L, Real>;
+  constexpr int NG = kFastThreads >= C::UPD ? kFastThreads / C::UPD : 1;
+  if constexpr(G < NG) {
+    if(NG == 1 || tid / C::UPD == G) copy_out_dirs<L, Real, G, NG>(p, stg, base, h, NG == 1 ? tid : tid % C::UPD, NG == 1 ? kFastThreads : C::UPD);
+    copy_out_groups<L, Real, G + 1>(p, stg, base, h, tid);
   }
 }
 
@@ -781,86 +816,91 @@ __device__ __forceinline__ void wall_fixups(const DevParams<Real>& p, const int3
 }
 
 template <class L, class Real, bool STRICT, int COLL>
-__global__ void __launch_bounds__(kFastThreads, 1) k_step_fast(const __grid_constant__ DevParams<Real> p) {
+__global__ void __launch_bounds__(kFastThreads, LBM_FAST_MINBLOCKS) k_step_fast(const __grid_constant__ DevParams<Real> p) {
   using C = FastCfg<L, Real>;
-  constexpr int Q = L::Q, QM = Q - 1, CH = L::CHUNK, NSEL = L::NSEL, NSTAGE = C::NSTAGE;
+  constexpr int Q = L::Q, QM = Q - 1, CH = L::CHUNK, TS = C::TS, NSEL = L::NSEL, NSTAGE = C::NSTAGE, NSPLIT = C::NSPLIT;
   __shared__ int32_t  s_nb[C::RN][NSEL + 1];
   __shared__ int32_t  s_tk[C::RT];
   __shared__ uint32_t s_dir[32];
   Real* const stages = reinterpret_cast<Real*>(lbm_dyn_smem);
   const Real* __restrict__ Abuf = p.A;
   const int tid = threadIdx.x;
+  const int32_t n_tiles = p.n_fast_chunks * NSPLIT;
 
   fill_dir_words<L, 0>(s_dir, tid);
-  // Chunks are handed out dynamically, in curve order, from a global ticket counter that only ever grows: a launch over n
-  // chunks with B CTAs advances it by exactly n + B * PAST_END (every CTA draws PAST_END tickets beyond the end), so the
+  // Tiles are handed out dynamically, in curve order, from a global ticket counter that only ever grows: a launch over n
+  // tiles with B CTAs advances it by exactly n + B * PAST_END (every CTA draws PAST_END tickets beyond the end), so the
   // host knows the first ticket of every launch and never resets anything.
+  // Thread 0 always has one more ticket in flight (tk_pending): it is published an iteration after it was drawn, so that the
+  // latency of the atomic never sits in front of a barrier.
+  unsigned long long tk_pending = 0;
   if(tid == 0) {
-    unsigned long long t[NSTAGE + 1];
+    unsigned long long t[NSTAGE + 2];
 #pragma unroll
-    for(int k = 0; k <= NSTAGE; ++k) t[k] = atomicAdd(p.ticket, 1ull);
+    for(int k = 0; k <= NSTAGE + 1; ++k) t[k] = atomicAdd(p.ticket, 1ull);
 #pragma unroll
     for(int k = 0; k <= NSTAGE; ++k) s_tk[k] = static_cast<int32_t>(t[k] - p.ticket_base);
+    tk_pending = t[NSTAGE + 1];
   }
   __syncthreads();
-  if(s_tk[0] >= p.n_fast_chunks) return;
-  // neighbour bases of the first NSTAGE chunks
+  if(s_tk[0] >= n_tiles) return;
+  // neighbour bases of the first NSTAGE tiles
   for(int k = 0; k < NSTAGE; ++k) {
     const int32_t tk = s_tk[k];
-    if(tk < p.n_fast_chunks && tid < NSEL + 1) s_nb[k][tid] = p.chunk_nb[static_cast<size_t>(p.chunk_off + tk) * (NSEL + 1) + tid];
+    if(tk < n_tiles && tid < NSEL + 1) s_nb[k][tid] = p.chunk_nb[static_cast<size_t>(p.chunk_off + tk / NSPLIT) * (NSEL + 1) + tid];
   }
   __syncthreads();
   for(int k = 0; k < NSTAGE - 1; ++k) {
     const int32_t tk = s_tk[k];
-    if(tk < p.n_fast_chunks) issue_chunk_loads<L, Real>(p, Abuf, stages + static_cast<size_t>(k) * (QM * CH), s_nb[k], (p.chunk_off + tk) * CH, s_dir, tid);
+    if(tk < n_tiles)
+      issue_tile_loads<L, Real>(p, Abuf, stages + static_cast<size_t>(k) * (QM * TS), s_nb[k], (p.chunk_off + tk / NSPLIT) * CH, tk % NSPLIT, s_dir, tid);
     cp_async_commit();
   }
 
   for(int i = 0;; ++i) {
     const int32_t ticket = s_tk[i % C::RT];
-    if(ticket >= p.n_fast_chunks) break;
-    const int      chunk = p.chunk_off + ticket;
+    if(ticket >= n_tiles) break;
+    const int      chunk = p.chunk_off + ticket / NSPLIT;
+    const int      h     = ticket % NSPLIT;
     const int32_t  base  = chunk * CH;
-    Real* const    stg   = stages + static_cast<size_t>(i % NSTAGE) * (QM * CH);
+    Real* const    stg   = stages + static_cast<size_t>(i % NSTAGE) * (QM * TS);
     const int32_t* nb    = s_nb[i % C::RN];
     // the rest population does not move: straight through registers
     Real frest[C::CPT];
 #pragma unroll
     for(int k = 0; k < C::CPT; ++k) {
       const int v = tid + k * kFastThreads;
-      if(v < CH) frest[k] = Abuf[static_cast<size_t>(QM) * p.stride + base + thread_cell<L>(v)];
+      if(v < TS) frest[k] = Abuf[static_cast<size_t>(QM) * p.stride + base + h * TS + thread_cell<L>(v)];
     }
     cp_async_wait<NSTAGE - 2>();
-    __syncthreads(); // B1: this chunk's stage is complete; every thread has left the previous iteration
-    {
-      // chunk i + NSTAGE - 1 goes into the stage the previous iteration has just copied out
-      const int32_t tk = s_tk[(i + NSTAGE - 1) % C::RT];
-      if(tk < p.n_fast_chunks)
-        issue_chunk_loads<L, Real>(p, Abuf, stages + static_cast<size_t>((i + NSTAGE - 1) % NSTAGE) * (QM * CH), s_nb[(i + NSTAGE - 1) % C::RN],
-                                   (p.chunk_off + tk) * CH, s_dir, tid);
-      cp_async_commit();
-    }
-    // neighbour bases of chunk i + NSTAGE and the ticket of chunk i + NSTAGE + 1: fetched now, published before B2
+    __syncthreads(); // B1: this tile's stage is complete; every thread has left the previous iteration
+    // neighbour bases of tile i + NSTAGE: fetched now, published before B2
     const int32_t tk_nb  = s_tk[(i + NSTAGE) % C::RT];
     int32_t       nb_val = 0;
-    if(tk_nb < p.n_fast_chunks && tid < NSEL + 1) nb_val = p.chunk_nb[static_cast<size_t>(p.chunk_off + tk_nb) * (NSEL + 1) + tid];
-    unsigned long long tk_new = 0;
-    if(tid == 0) tk_new = atomicAdd(p.ticket, 1ull);
-
+    if(tk_nb < n_tiles && tid < NSEL + 1) nb_val = __ldg(&p.chunk_nb[static_cast<size_t>(p.chunk_off + tk_nb / NSPLIT) * (NSEL + 1) + tid]);
+    {
+      // tile i + NSTAGE - 1 goes into the stage the previous iteration has just copied out
+      const int32_t tk = s_tk[(i + NSTAGE - 1) % C::RT];
+      if(tk < n_tiles)
+        issue_tile_loads<L, Real>(p, Abuf, stages + static_cast<size_t>((i + NSTAGE - 1) % NSTAGE) * (QM * TS), s_nb[(i + NSTAGE - 1) % C::RN],
+                                  (p.chunk_off + tk / NSPLIT) * CH, tk % NSPLIT, s_dir, tid);
+      cp_async_commit();
+    }
     const int32_t wid = nb[NSEL]; // wall descriptor of this chunk, -1: interior chunk
     const AddEntryT<Real>* wall = p.wall_desc + static_cast<size_t>(wid < 0 ? 0 : wid) * QM * NSEL;
 #pragma unroll
     for(int k = 0; k < C::CPT; ++k) {
       const int v = tid + k * kFastThreads;
-      if(v < CH) {
-        const int o = thread_cell<L>(v);
+      if(v < TS) {
+        const int ot = thread_cell<L>(v);   // tile-local lexicographic offset
+        const int o  = ot + h * TS;         // in-chunk lexicographic offset
         int pos[3];
-        pos[0] = stage_swizzle<L, Real>(0, o);
-        pos[1] = L::D == 3 ? stage_swizzle<L, Real>(1, lay_perm(1, o)) : o;
-        pos[2] = L::D == 3 ? stage_swizzle<L, Real>(2, lay_perm(2, o)) : o;
+        pos[0] = stage_swizzle<L, Real>(0, ot);
+        pos[1] = L::D == 3 ? stage_swizzle<L, Real>(1, tile_perm<L, Real>(1, ot)) : ot;
+        pos[2] = L::D == 3 ? stage_swizzle<L, Real>(2, tile_perm<L, Real>(2, ot)) : ot;
         Real fold[Q], f[Q], rho, u[L::D];
 #pragma unroll
-        for(int j = 0; j < QM; ++j) fold[j] = stg[j * CH + pos[layout_of<L>(j)]];
+        for(int j = 0; j < QM; ++j) fold[j] = stg[j * TS + pos[layout_of<L>(j)]];
         fold[QM] = frest[k];
         if(wid >= 0 && !p.first) {
           int edge[3][2] = {{0, 0}, {0, 0}, {0, 0}};
@@ -873,16 +913,21 @@ __global__ void __launch_bounds__(kFastThreads, 1) k_step_fast(const __grid_cons
           wall_fixups<L, Real, STRICT, 0>(p, nb, wall, base + o, o, edge, fold);
         }
         collide_cell<L, Real, STRICT, COLL>(p, fold, f, rho, u);
+        if(p.B != nullptr) {
 #pragma unroll
-        for(int j = 0; j < QM; ++j) stg[j * CH + pos[layout_of<L>(j)]] = f[j];
-        p.B[static_cast<size_t>(QM) * p.stride + base + o] = f[QM];
+          for(int j = 0; j < QM; ++j) stg[j * TS + pos[layout_of<L>(j)]] = f[j];
+          p.B[static_cast<size_t>(QM) * p.stride + base + o] = f[QM];
+        }
         store_vars<L, Real>(p, base + o, rho, u);
       }
     }
-    if(tk_nb < p.n_fast_chunks && tid < NSEL + 1) s_nb[(i + NSTAGE) % C::RN][tid] = nb_val;
-    if(tid == 0) s_tk[(i + NSTAGE + 1) % C::RT] = static_cast<int32_t>(tk_new - p.ticket_base);
-    __syncthreads(); // B2: the stage holds m_f of the whole chunk
-    copy_out_dirs<L, Real, 0>(p, stg, base, tid);
+    if(tk_nb < n_tiles && tid < NSEL + 1) s_nb[(i + NSTAGE) % C::RN][tid] = nb_val;
+    if(tid == 0) { // the ticket of tile i + NSTAGE + 1 was drawn an iteration ago; draw the next one
+      s_tk[(i + NSTAGE + 1) % C::RT] = static_cast<int32_t>(tk_pending - p.ticket_base);
+      tk_pending = atomicAdd(p.ticket, 1ull);
+    }
+    __syncthreads(); // B2: the stage holds m_f of the whole tile
+    if(p.B != nullptr) copy_out_groups<L, Real, 0>(p, stg, base, h, tid);
   }
   cp_async_wait<0>();
 }
@@ -1019,6 +1064,24 @@ __global__ void k_unpack_aos(const double* __restrict__ aos, const int32_t* __re
   if(c >= n) return;
   const int32_t dv = ref2dev[c];
   for(int j = 0; j < width; ++j) soa[POP ? pop_index<L>(j, dv, stride, pr) : static_cast<size_t>(j) * stride + dv] = static_cast<Real>(aos[c * width + j]);
+}
+// population upload, indexed by DESTINATION: thread t fills position t of every direction's array (coalesced stores); the cell
+// that lives there follows from the direction's in-chunk layout, its row of the host array from dev2ref (reads stay inside the
+// 512-row window of the chunk, which L1 / L2 absorb)
+template <class L, class Real>
+__global__ void k_unpack_aos_pop(const double* __restrict__ aos, const int32_t* __restrict__ dev2ref, int64_t npad, Real* __restrict__ soa, int64_t stride,
+                                 PermRange pr) {
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if(t >= npad) return;
+  const int32_t ti = static_cast<int32_t>(t);
+  const bool inblock = L::D == 3 && (ti < pr.perm_end || (ti >= pr.gb_begin && ti < pr.gb_end));
+#pragma unroll
+  for(int j = 0; j < L::Q; ++j) {
+    const int     lay  = layout_of<L>(j);
+    const int32_t cell = (inblock && lay != 0) ? ((ti & ~511) | lay_perm_inv(lay, ti & 511)) : ti;
+    const int32_t ref  = dev2ref[cell];
+    if(ref >= 0) soa[static_cast<size_t>(j) * stride + t] = static_cast<Real>(aos[static_cast<size_t>(ref) * L::Q + j]);
+  }
 }
 template <class L, class Real, bool POP>
 __global__ void k_pack_aos(const Real* __restrict__ soa, const int32_t* __restrict__ ref2dev, int64_t n, int width, double* __restrict__ aos, int64_t stride,

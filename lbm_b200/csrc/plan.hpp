@@ -730,6 +730,7 @@ inline bool build_plan(const PlanInput& in, Plan& P) {
     else P.ref2dev[c] = static_cast<int32_t>(pos++);
   }
   P.npad   = (pos + CH - 1) / CH * CH; // whole blocks: the in-chunk permutation never leaves the arrays
+  if(static_cast<int64_t>(Q) * P.npad >= (int64_t(1) << 32)) { P.error = "too many populations for 32-bit element offsets (Q * cells >= 2^32)"; return false; }
   P.gen_stride = (P.n_gen + 63) / 64 * 64;
   P.dev2ref.assign(static_cast<size_t>(P.npad), -1);
   for(int64_t c = 0; c < N; ++c) P.dev2ref[P.ref2dev[c]] = static_cast<int32_t>(c);

@@ -157,6 +157,7 @@ __global__ void k_pre_apply(State s, BcDev b) {
   } else if(b.kind == BC_PERIODIC) {
     const int64_t l0 = b.link[k * Q];
     if(b.has_pressure) {
+      if(b.nset[k] < 0) return; // a later entry rewrites the same linked cell: the last writer wins (resolved on the host)
       double u[D];
 #pragma unroll
       for(int d = 0; d < D; ++d) u[d] = s.vars[c * NV + d];
@@ -169,6 +170,7 @@ __global__ void k_pre_apply(State s, BcDev b) {
     } else {
       for(int id = 0; id < b.nset[k]; ++id) {
         const int dist = b.linkdist[k * Q + id];
+        if(dist < 0) continue; // overwritten by a later entry (resolved on the host)
         s.fold[b.link[k * Q + id] * Q + dist] = s.f[c * Q + dist];
       }
       s.vars[l0 * NV + D] = 1.0;

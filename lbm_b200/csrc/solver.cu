@@ -8,6 +8,7 @@
 #include <limits>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/lbm_b200.h"
@@ -152,6 +153,22 @@ struct SequentialSolver final : SolverBase {
           if(!lbm::periodic_links(in, bc, k, setd, links, &ns, &err)) return fail(LBM_B200_EINVAL, err);
           nset[k] = ns;
           for(int id = 0; id < ns; ++id) { link[k * Q + id] = links[id]; ldist[k * Q + id] = setd[id]; }
+        }
+        // The reference applies the entries one after the other, so when several entries write one slot (in 3D many entries resolve to
+        // the same first connected cell, bnd_periodic.h:75-91) the LAST one wins.  The kernel runs one thread per entry: only the
+        // winning writer of every slot may remain, decided here once.
+        {
+          const bool with_p = !std::isnan(bc.pressure);
+          std::unordered_map<int64_t, int64_t> last; // slot (or linked cell) -> packed (entry, index in entry)
+          for(int64_t k = 0; k < n; ++k) {
+            if(with_p) last[link[k * Q]] = k;        // bnd_periodic.h:101-108: all Q populations of the first linked cell
+            else for(int id = 0; id < nset[k]; ++id) last[link[k * Q + id] * Q + ldist[k * Q + id]] = k * Q + id;
+          }
+          for(int64_t k = 0; k < n; ++k) {
+            if(with_p) { if(last[link[k * Q]] != k) nset[k] = -1; }
+            else for(int id = 0; id < nset[k]; ++id)
+              if(last[link[k * Q + id] * Q + ldist[k * Q + id]] != k * Q + id) ldist[k * Q + id] = -1;
+          }
         }
         b.link = up<int64_t>(keep_i64, link, &cerr);
         b.linkdist = up<int>(keep_i32, ldist, &cerr);
@@ -978,6 +995,10 @@ int lbm_b200_init(lbm_b200_solver* s) {
   if(s->impl->in.poisson || poisson_lattice || poisson_bc) {
     if(!s->impl->in.poisson) return fail(LBM_B200_ESTATE, "D1Q3 / D2Q5 and the NEEM Dirichlet / Neumann conditions belong to the Poisson equation: call lbm_b200_set_poisson");
     if(wet) return fail(LBM_B200_EINVAL, "wall boundary conditions do not exist for the Poisson equation types");
+    // everything that can be refused is refused BEFORE the handle changes hands: a failed init leaves the set-up calls intact
+    if(s->impl->cfg.precision != LBM_B200_FP64) return fail(LBM_B200_EUNSUP, "the Poisson equation types run in fp64 only");
+    if(s->impl->in.n_ghost > 0 || !s->impl->in.peers.empty() || s->impl->comm != nullptr)
+      return fail(LBM_B200_EUNSUP, "the Poisson equation types are not partitioned");
     if(dynamic_cast<PoissonSolver*>(s->impl.get()) == nullptr) {
       SolverBase* q = new PoissonSolver();
       q->cfg    = s->impl->cfg;
@@ -989,6 +1010,9 @@ int lbm_b200_init(lbm_b200_solver* s) {
   }
   if(wet) {
     // order-dependent boundary conditions: hand the same inputs to the reference-order pipeline (sequential.cuh)
+    if(s->impl->cfg.precision != LBM_B200_FP64) return fail(LBM_B200_EUNSUP, "wet-node walls (equilibrium / NEEM / NEBB) run in fp64 only");
+    if(s->impl->in.n_ghost > 0 || !s->impl->in.peers.empty() || s->impl->comm != nullptr)
+      return fail(LBM_B200_EUNSUP, "wet-node wall boundary conditions are not partitioned yet");
     SolverBase* q = make_sequential(s->impl->cfg);
     if(q == nullptr) return fail(LBM_B200_EINVAL, "Unsupported model");
     q->cfg    = s->impl->cfg;

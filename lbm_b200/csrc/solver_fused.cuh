@@ -26,7 +26,7 @@ struct Solver final : SolverBase {
   DevBuf<Real>     d_uext[2], d_values[2];
   DevBuf<double>   d_partial;
   DevBuf<double>   stage;     // AoS staging for host transfers [n][Q]
-  DevBuf<int32_t>  d_ref2dev;
+  DevBuf<int32_t>  d_ref2dev, d_dev2ref;
   DevBuf<int64_t>  d_send_idx, d_recv_idx;
   DevBuf<unsigned long long> d_ticket; // [0]: inner / whole-domain launches, [1]: outer launches
   unsigned long long ticket_next[2] = {0, 0};
@@ -39,7 +39,7 @@ struct Solver final : SolverBase {
   int dyn = 0;       // d_uext[dyn] / d_values[dyn] are the ones the next gather must use
   int vcur = 0;      // vars[vcur] = m_vars, vars[vcur^1] = m_varsold
   int64_t vars_step[2] = {-1, -1};
-  bool    overlap_enabled = true, debug_identity = false;
+  bool    overlap_enabled = true, debug_identity = false, extrap_side_enabled = false;
   bool    first = true; // next step is step 0 of the reference loop (m_fold = initial condition)
   int     n_fast_blocks = 0, n_gen_blocks = 0, max_resident = 0;
   cudaStream_t comm_stream = nullptr;   // halo exchange runs here, overlapped with the update of the inner cells
@@ -48,13 +48,13 @@ struct Solver final : SolverBase {
   cudaEvent_t  ev_outer = nullptr, ev_halo = nullptr, ev_pack = nullptr;
   bool         halo_pending = false;
   int64_t launches = 0, launches_main = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr; // evm0 / evm1 point into ev_ring while a timed run records
+  std::vector<cudaEvent_t> ev_ring;
 
   ~Solver() override {
     if(ev0) cudaEventDestroy(ev0);
     if(ev1) cudaEventDestroy(ev1);
-    if(evm0) cudaEventDestroy(evm0);
-    if(evm1) cudaEventDestroy(evm1);
+    for(cudaEvent_t e : ev_ring) cudaEventDestroy(e);
     if(ev_outer) cudaEventDestroy(ev_outer);
     if(ev_halo) cudaEventDestroy(ev_halo);
     if(ev_pack) cudaEventDestroy(ev_pack);
@@ -120,6 +120,7 @@ struct Solver final : SolverBase {
 
   int init() override {
     debug_identity = std::getenv("LBM_B200_DEBUG_IDENTITY") != nullptr;
+    extrap_side_enabled = std::getenv("LBM_B200_EXTRAP_SIDE") != nullptr;
     if(const char* e = std::getenv("LBM_B200_NO_OVERLAP")) overlap_enabled = e[0] == '0' || e[0] == 0;
     if(!lbm::build_plan(in, plan)) return fail(plan.error.find("order-dependent") != std::string::npos ? LBM_B200_EUNSUP : LBM_B200_EINVAL, plan.error);
     std::vector<int32_t>().swap(in.nghbr);
@@ -143,6 +144,7 @@ struct Solver final : SolverBase {
     CUDA_TRY(d_chunk_abb.upload(plan.chunk_abb));
     CUDA_TRY(d_codes.upload(plan.codes));
     CUDA_TRY(d_ref2dev.upload(plan.ref2dev));
+    CUDA_TRY(d_dev2ref.upload(plan.dev2ref));
     if(!in.peers.empty()) {
       if(comm == nullptr) return fail(LBM_B200_ESTATE, "halo lists set but lbm_b200_comm_init has not been called");
       CUDA_TRY(d_send_idx.upload(plan.send_index));
@@ -206,8 +208,6 @@ struct Solver final : SolverBase {
     }
     CUDA_TRY(cudaEventCreate(&ev0));
     CUDA_TRY(cudaEventCreate(&ev1));
-    CUDA_TRY(cudaEventCreate(&evm0));
-    CUDA_TRY(cudaEventCreate(&evm1));
     CUDA_TRY(cudaStreamCreateWithFlags(&gen_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
@@ -291,6 +291,7 @@ struct Solver final : SolverBase {
     return (s + 1) % k == 0 || (s + 2) % k == 0;
   }
 
+  // phases (bit mask) -- 1: forcing, periodic-with-pressure values; 2: pressure extrapolation; 4: m_vars fix-ups.  Old wording:
   // phase 1: forcing, periodic-with-pressure values; phase 2: pressure extrapolation (needs the velocity halo of THIS step when
   // a partition cut separates a pressure cell from its inward neighbours) and the m_vars fix-ups.  nd = the dynamic buffers
   // written for the next step; the caller flips `dyn` once both phases have run.
@@ -314,7 +315,7 @@ struct Solver final : SolverBase {
       ++launches;
       dyn_written = true;
     }
-    if((phases & 2) && vars_out != nullptr && d_varfix.n > 0) {
+    if((phases & 4) && vars_out != nullptr && d_varfix.n > 0) {
       const int n = static_cast<int>(d_varfix.n);
       lbm::k_varfix<Real><<<(n + 127) / 128, 128, 0, stream>>>(d_varfix.p, n, d_uext[nd].p, vars_out, plan.npad);
       ++launches;
@@ -376,46 +377,60 @@ struct Solver final : SolverBase {
 
   bool has_velocity_halo() const { return !in.vsend_cell.empty() || !in.vrecv_cell.empty(); }
 
+  // a launch over generic cells [g0, g0+ng) and fast chunks [c0, c0+ncnk): the link-code cells on the side stream (they are
+  // latency bound and few), the persistent chunk CTAs on the solver's stream; both read buffer A and write disjoint cells of B
+  // extrap_nd >= 0: also run the pressure extrapolation of this step (it only reads buffer A and writes d_uext[extrap_nd]) on the side stream
+  int launch_main(const lbm::DevParams<Real>& p, int64_t g0, int64_t ng, int64_t c0, int64_t ncnk, int resident_cap, int cls, int extrap_nd = -1) {
+    lbm::DevParams<Real> q = p;
+    q.gen_off       = static_cast<int32_t>(g0);
+    q.n_gen         = static_cast<int32_t>(ng);
+    q.n_gen_blocks  = static_cast<int>((ng + lbm::kThreads - 1) / lbm::kThreads);
+    q.chunk_off     = static_cast<int32_t>(c0);
+    q.n_fast_chunks = static_cast<int32_t>(ncnk);
+    const int64_t ntiles = ncnk * lbm::FastCfg<L, Real>::NSPLIT; // the persistent CTAs draw tiles (whole chunks or their halves)
+    q.n_fast_blocks = static_cast<int32_t>(ntiles < resident_cap ? ntiles : resident_cap);
+    q.ticket        = d_ticket.p + cls;
+    q.ticket_base   = ticket_next[cls];
+    ticket_next[cls] += static_cast<unsigned long long>(ntiles)
+                        + static_cast<unsigned long long>(q.n_fast_blocks) * lbm::FastCfg<L, Real>::PAST_END;
+    const bool extrap = extrap_nd >= 0 && d_abb.n > 0;
+    const bool side = q.n_fast_blocks > 0 && (q.n_gen_blocks > 0 || extrap);
+    if(side) {
+      CUDA_TRY(cudaEventRecord(ev_fork, stream));
+      CUDA_TRY(cudaStreamWaitEvent(gen_stream, ev_fork, 0));
+    }
+    if(q.n_gen_blocks > 0) {
+      main_kernel(1)<<<q.n_gen_blocks, lbm::kThreads, 0, side ? gen_stream : stream>>>(q);
+      ++launches;
+      ++launches_main;
+    }
+    if(extrap) {
+      const int n = static_cast<int>(d_abb.n);
+      cudaStream_t st = side ? gen_stream : stream;
+      if(cfg.arithmetic == LBM_B200_STRICT) lbm::k_pressure_extrapolate<L, Real, true><<<(n + 127) / 128, 128, 0, st>>>(p, n, d_uext[extrap_nd].p, d_vrecvbuf.p);
+      else lbm::k_pressure_extrapolate<L, Real, false><<<(n + 127) / 128, 128, 0, st>>>(p, n, d_uext[extrap_nd].p, d_vrecvbuf.p);
+      ++launches;
+    }
+    if(q.n_fast_blocks > 0) {
+      main_kernel(0)<<<q.n_fast_blocks, lbm::kFastThreads, kFastSmem, stream>>>(q);
+      ++launches;
+      ++launches_main;
+    }
+    if(side) {
+      CUDA_TRY(cudaEventRecord(ev_join, gen_stream));
+      CUDA_TRY(cudaStreamWaitEvent(stream, ev_join, 0));
+    }
+    return LBM_B200_OK;
+  }
+
   int one_step(bool time_main) {
     const int src = cur, dst = cur ^ 1;
     Real*     vout = nullptr;
     if(want_vars(t)) vout = vars[vcur ^ 1].p;
     lbm::DevParams<Real> p = params(src, dst, vout);
     if(prev_fold.p != nullptr) p.A = prev_fold.p; // explicit m_fold supplied by set_populations
-    // a launch over generic cells [g0, g0+ng) and fast chunks [c0, c0+ncnk): the link-code cells on the side stream (they are
-    // latency bound and few), the persistent chunk CTAs on the solver's stream; both read buffer A and write disjoint cells of B
-    auto launch = [&](int64_t g0, int64_t ng, int64_t c0, int64_t ncnk, int resident_cap, int cls) -> int {
-      lbm::DevParams<Real> q = p;
-      q.gen_off       = static_cast<int32_t>(g0);
-      q.n_gen         = static_cast<int32_t>(ng);
-      q.n_gen_blocks  = static_cast<int>((ng + lbm::kThreads - 1) / lbm::kThreads);
-      q.chunk_off     = static_cast<int32_t>(c0);
-      q.n_fast_chunks = static_cast<int32_t>(ncnk);
-      q.n_fast_blocks = static_cast<int32_t>(ncnk < resident_cap ? ncnk : resident_cap);
-      q.ticket        = d_ticket.p + cls;
-      q.ticket_base   = ticket_next[cls];
-      ticket_next[cls] += static_cast<unsigned long long>(ncnk)
-                          + static_cast<unsigned long long>(q.n_fast_blocks) * lbm::FastCfg<L, Real>::PAST_END;
-      const bool side = q.n_gen_blocks > 0 && q.n_fast_blocks > 0;
-      if(side) {
-        CUDA_TRY(cudaEventRecord(ev_fork, stream));
-        CUDA_TRY(cudaStreamWaitEvent(gen_stream, ev_fork, 0));
-      }
-      if(q.n_gen_blocks > 0) {
-        main_kernel(1)<<<q.n_gen_blocks, lbm::kThreads, 0, side ? gen_stream : stream>>>(q);
-        ++launches;
-        ++launches_main;
-      }
-      if(q.n_fast_blocks > 0) {
-        main_kernel(0)<<<q.n_fast_blocks, lbm::kFastThreads, kFastSmem, stream>>>(q);
-        ++launches;
-        ++launches_main;
-      }
-      if(side) {
-        CUDA_TRY(cudaEventRecord(ev_join, gen_stream));
-        CUDA_TRY(cudaStreamWaitEvent(stream, ev_join, 0));
-      }
-      return LBM_B200_OK;
+    auto launch = [&](int64_t g0, int64_t ng, int64_t c0, int64_t ncnk, int resident_cap, int cls, int extrap_nd = -1) -> int {
+      return launch_main(p, g0, ng, c0, ncnk, resident_cap, cls, extrap_nd);
     };
     const bool has_aux = d_force.n > 0 || d_perp.n > 0 || d_abb.n > 0 || (vout != nullptr && d_varfix.n > 0);
     // forcing and the periodic-with-pressure values write populations of buffer B that a peer may need: they must precede the pack.
@@ -443,24 +458,31 @@ struct Solver final : SolverBase {
       CUDA_TRY(cudaEventRecord(ev_halo, comm_stream));
       halo_pending = true;
       CUDA_TRY(cudaStreamWaitEvent(stream, ev_pack, 0));
-      rc = launch(plan.n_gen_outer, plan.n_gen - plan.n_gen_outer, plan.n_fast_outer, plan.n_fast_chunks - plan.n_fast_outer, max_resident, 0);
+      // pressure boundary present: the extrapolation runs beside the inner launch (side stream), the m_vars fix-ups behind it
+      const int nd = dyn ^ 1;
+      rc = launch(plan.n_gen_outer, plan.n_gen - plan.n_gen_outer, plan.n_fast_outer, plan.n_fast_chunks - plan.n_fast_outer, max_resident, 0,
+                  extrap_side_enabled ? nd : -1);
       if(rc != LBM_B200_OK) return rc;
       if(time_main) cudaEventRecord(evm1, stream);
       CUDA_TRY(cudaGetLastError());
-      if(has_aux) { // pressure boundary present: extrapolation + m_vars fix-ups behind the inner launch, the exchange still in flight
-        const int nd = dyn ^ 1;
-        bool      dyn_written = false;
-        rc = cfg.arithmetic == LBM_B200_STRICT ? aux_kernels<true>(p, vout, nd, 2, &dyn_written) : aux_kernels<false>(p, vout, nd, 2, &dyn_written);
+      if(has_aux) {
+        bool      dyn_written = extrap_side_enabled && d_abb.n > 0;
+        const int phases = extrap_side_enabled ? 4 : (2 | 4);
+        rc = cfg.arithmetic == LBM_B200_STRICT ? aux_kernels<true>(p, vout, nd, phases, &dyn_written) : aux_kernels<false>(p, vout, nd, phases, &dyn_written);
         if(rc != LBM_B200_OK) return rc;
         if(dyn_written) dyn = nd;
       }
     } else {
-      rc = launch(0, plan.n_gen, 0, plan.n_fast_chunks, max_resident, 0);
+      const int  nd = dyn ^ 1;
+      // The pressure extrapolation depends on buffer A only and could run beside the main kernels (launch_main: extrap_nd); measured on
+      // B200 (3D step / sphere workloads, 256^3) that is no faster than running it behind them -- it rebuilds m_fold of two neighbours
+      // per entry and competes with the bandwidth-bound chunk kernel -- so it stays behind (LBM_B200_EXTRAP_SIDE=1 switches it on).
+      const bool extrap_side = extrap_side_enabled && !has_velocity_halo() && d_abb.n > 0;
+      rc = launch(0, plan.n_gen, 0, plan.n_fast_chunks, max_resident, 0, extrap_side ? nd : -1);
       if(rc != LBM_B200_OK) return rc;
       if(time_main) cudaEventRecord(evm1, stream);
       CUDA_TRY(cudaGetLastError());
-      const int  nd = dyn ^ 1;
-      bool       dyn_written = false;
+      bool       dyn_written = extrap_side;
       const bool strict = cfg.arithmetic == LBM_B200_STRICT;
       auto aux = [&](int phases) { return strict ? aux_kernels<true>(p, vout, nd, phases, &dyn_written) : aux_kernels<false>(p, vout, nd, phases, &dyn_written); };
       if(has_velocity_halo()) {
@@ -469,10 +491,10 @@ struct Solver final : SolverBase {
         if(rc != LBM_B200_OK) return rc;
         rc = halo_exchange(f[dst].p, stream, nullptr, &p);
         if(rc != LBM_B200_OK) return rc;
-        rc = aux(2);
+        rc = aux(2 | 4);
         if(rc != LBM_B200_OK) return rc;
       } else {
-        rc = aux(3);
+        rc = aux(extrap_side ? (1 | 4) : (1 | 2 | 4));
         if(rc != LBM_B200_OK) return rc;
         rc = halo_exchange(f[dst].p, stream);
         if(rc != LBM_B200_OK) return rc;
@@ -499,15 +521,19 @@ struct Solver final : SolverBase {
     const bool timed = ms_total != nullptr;
     double     main_acc = 0;
     if(timed) CUDA_TRY(cudaEventRecord(ev0, stream));
-    for(int64_t s = 0; s < n; ++s) {
-      int rc = one_step(timed && ms_main != nullptr);
-      if(rc != LBM_B200_OK) return rc;
-      if(timed && ms_main != nullptr) {
-        CUDA_TRY(cudaEventSynchronize(evm1));
-        float ms = 0;
-        CUDA_TRY(cudaEventElapsedTime(&ms, evm0, evm1));
-        main_acc += ms;
+    // per-launch timing: one event pair per step, recorded on the stream and read only after the loop -- the host never waits inside
+    // the timed region, so launches run ahead of the device exactly as in an untimed run
+    const bool per_launch = timed && ms_main != nullptr;
+    if(per_launch)
+      while(static_cast<int64_t>(ev_ring.size()) < 2 * n) {
+        cudaEvent_t e = nullptr;
+        CUDA_TRY(cudaEventCreate(&e));
+        ev_ring.push_back(e);
       }
+    for(int64_t s = 0; s < n; ++s) {
+      if(per_launch) { evm0 = ev_ring[2 * s]; evm1 = ev_ring[2 * s + 1]; }
+      int rc = one_step(per_launch);
+      if(rc != LBM_B200_OK) return rc;
     }
     if(halo_pending) { // the step is complete only when the ghosts have arrived
       CUDA_TRY(cudaStreamWaitEvent(stream, ev_halo, 0));
@@ -517,7 +543,14 @@ struct Solver final : SolverBase {
       CUDA_TRY(cudaEventRecord(ev1, stream));
       CUDA_TRY(cudaEventSynchronize(ev1));
       CUDA_TRY(cudaEventElapsedTime(ms_total, ev0, ev1));
-      if(ms_main) *ms_main = static_cast<float>(main_acc);
+      if(per_launch) {
+        for(int64_t s = 0; s < n; ++s) {
+          float ms = 0;
+          CUDA_TRY(cudaEventElapsedTime(&ms, ev_ring[2 * s], ev_ring[2 * s + 1]));
+          main_acc += ms;
+        }
+        *ms_main = static_cast<float>(main_acc);
+      }
     }
     return LBM_B200_OK;
   }
@@ -554,8 +587,13 @@ struct Solver final : SolverBase {
     if(rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(stage.p, src, sizeof(double) * static_cast<size_t>(plan.n) * width, cudaMemcpyHostToDevice, stream));
     const int nb = static_cast<int>((plan.n + 255) / 256);
-    if(pop) lbm::k_unpack_aos<L, Real, true><<<nb, 256, 0, stream>>>(stage.p, d_ref2dev.p, plan.n, width, ddst, plan.npad, plan.perm_range());
-    else lbm::k_unpack_aos<L, Real, false><<<nb, 256, 0, stream>>>(stage.p, d_ref2dev.p, plan.n, width, ddst, plan.npad, plan.perm_range());
+    if(pop) {
+      // population arrays: one thread per destination position, so that every direction's array is written with full coalescing
+      const int nbp = static_cast<int>((plan.npad + 255) / 256);
+      lbm::k_unpack_aos_pop<L, Real><<<nbp, 256, 0, stream>>>(stage.p, d_dev2ref.p, plan.npad, ddst, plan.npad, plan.perm_range());
+    } else {
+      lbm::k_unpack_aos<L, Real, false><<<nb, 256, 0, stream>>>(stage.p, d_ref2dev.p, plan.n, width, ddst, plan.npad, plan.perm_range());
+    }
     ++launches;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(stream));
@@ -597,14 +635,23 @@ struct Solver final : SolverBase {
     if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
     if(foldi == nullptr) return fail(LBM_B200_EINVAL, "set_populations needs m_fold");
     CUDA_TRY(cudaStreamSynchronize(stream));
+    if(comm_stream) CUDA_TRY(cudaStreamSynchronize(comm_stream));
+    halo_pending = false;
     int rc = LBM_B200_OK;
-    if(fi != nullptr) { // m_f is not an input of the next step (the collision overwrites it, solver.cpp:603); kept for read-back only
+    if(fi != nullptr) {
+      // m_f is not an input of the next step (the collision overwrites it, solver.cpp:603); kept for read-back only, with the
+      // supplied m_fold in a buffer of its own until the next step has consumed it
       rc = upload_aos(fi, Q, f[cur].p, true);
       if(rc) return rc;
+      CUDA_TRY(prev_fold.alloc(static_cast<size_t>(plan.npad) * Q));
+      CUDA_TRY(cudaMemset(prev_fold.p, 0, prev_fold.bytes()));
+      rc = upload_aos(foldi, Q, prev_fold.p, true);
+    } else {
+      // no m_f given: the supplied m_fold takes its place in the current buffer (no allocation, one pass); until the next step
+      // lbm_b200_get_populations reports it as m_f as well
+      prev_fold.alloc(0);
+      rc = upload_aos(foldi, Q, f[cur].p, true);
     }
-    CUDA_TRY(prev_fold.alloc(static_cast<size_t>(plan.npad) * Q));
-    CUDA_TRY(cudaMemset(prev_fold.p, 0, prev_fold.bytes()));
-    rc = upload_aos(foldi, Q, prev_fold.p, true);
     if(rc) return rc;
     // slots nothing ever writes now keep the supplied m_fold value
     if(!plan.stale_ref.empty()) {
@@ -639,10 +686,20 @@ struct Solver final : SolverBase {
     return LBM_B200_OK;
   }
 
+  // The moments output() wants (solver.cpp:336: updateMacroscopicValues of the current m_fold) are what the next time step's kernels
+  // compute on their way: run them once with the population stores switched off (B = nullptr) and m_vars going to the scratch buffer.
   int get_moments(double* m) override {
     if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
-    int rc = gather_all(nullptr, scratch.p);
+    if(halo_pending) {
+      CUDA_TRY(cudaStreamWaitEvent(stream, ev_halo, 0));
+      halo_pending = false;
+    }
+    lbm::DevParams<Real> p = params(cur, cur ^ 1, scratch.p);
+    if(prev_fold.p != nullptr) p.A = prev_fold.p;
+    p.B = nullptr;
+    int rc = launch_main(p, 0, plan.n_gen, 0, plan.n_fast_chunks, max_resident, 0);
     if(rc) return rc;
+    CUDA_TRY(cudaGetLastError());
     return download(scratch.p, NVAR, m, false);
   }
 

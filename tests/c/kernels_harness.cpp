@@ -104,10 +104,11 @@ void launch_step(const DevParams<double>& base, int64_t g0, int64_t ng, int64_t 
   q.n_gen_blocks  = static_cast<int32_t>((ng + kThreads - 1) / kThreads);
   q.chunk_off     = static_cast<int32_t>(c0);
   q.n_fast_chunks = static_cast<int32_t>(ncnk);
-  q.n_fast_blocks = static_cast<int32_t>(ncnk < persistent_ctas ? ncnk : persistent_ctas);
+  const int64_t ntiles = ncnk * FastCfg<L, double>::NSPLIT;
+  q.n_fast_blocks = static_cast<int32_t>(ntiles < persistent_ctas ? ntiles : persistent_ctas);
   q.ticket        = ticket;
   q.ticket_base   = *ticket_next;
-  *ticket_next += static_cast<unsigned long long>(ncnk) + static_cast<unsigned long long>(q.n_fast_blocks) * FastCfg<L, double>::PAST_END;
+  *ticket_next += static_cast<unsigned long long>(ntiles) + static_cast<unsigned long long>(q.n_fast_blocks) * FastCfg<L, double>::PAST_END;
   launch(ng, kThreads, [&] { k_step_generic<L, double, true, COLL>(q); });
   blockDim.x = kFastThreads;
   gridDim.x  = static_cast<unsigned>(q.n_fast_blocks);

@@ -10,7 +10,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("extra", [[], ["--workload", "step"]])
+@pytest.mark.parametrize("extra", [["--size", "32"], ["--workload", "step"]])
 def test_reference_arm_prints_one_json_line(extra):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "3", "--cpu-size", "32", *extra],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
@@ -25,6 +25,28 @@ def test_reference_arm_prints_one_json_line(extra):
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    if "--size" in extra:
+        assert "32^3" in d["config"]["workload"] and "32^3" in cb["sample"]      # the arm runs the size it prints
+
+
+def test_reference_arm_never_loads_the_cuda_library():
+    """the box workload of the reference arm builds its tables in numpy (bench.box_table_numpy) -- equal to lbm_b200_box_topology"""
+    code = ("import sys, json; sys.argv=['bench.py','--impl','reference','--size','16','--steps','3','--warmup','3']; import runpy;"
+            "runpy.run_path('bench.py', run_name='__main__'); import ctypes;"
+            "maps=open('/proc/self/maps').read(); assert 'liblbm_b200' not in maps, 'CUDA library loaded'; assert 'liblbm_oracle' in maps")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("shape,ndist", [((16, 8, 8), 19), ((8, 8, 8), 27), ((32, 16), 9)])
+def test_numpy_box_table_equals_the_native_one(shape, ndist):
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from lbm_b200.capi import box_topology
+    periodic = (1,) + (0,) * (len(shape) - 1)
+    native = box_topology(shape, periodic)[0]
+    assert np.array_equal(bench.box_table_numpy(shape, periodic, ndist), native[:, :ndist - 1])
 
 
 def test_gpu_arm_fails_loudly_without_a_device():
