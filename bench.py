@@ -128,7 +128,9 @@ def workload(size, lattice, rank=0, world=1, native=True, shape=None):
     else:
         from lbm_b200 import partition
         shape = global_shape(size, ndim, world) if shape is None else tuple(shape)
-        lp = partition.plan_rank(partition.BoxRows(shape, periodic, ndist), rank, world, 8 if ndim == 2 else 26)
+        from lbm_b200.capi import NativePartition
+        # the library's own partition code (lbm_b200_partition_*, csrc/partition.hpp) over on-demand box rows
+        lp = NativePartition(partition.BoxRows(shape, periodic, ndist), ndim, ndist, 8 if ndim == 2 else 26, rank, world)
         nghbr, center, n_owned = lp.nghbr, None, lp.n_owned
     names = ["-x", "+x", "-y", "+y", "-z", "+z"][:2 * ndim]
     lid = names[-1]
@@ -551,6 +553,8 @@ def run_ours(args):
             s.comm_init(uid[0], rank, world)
         s.init()
         s.step(args.conv_interval * max(1, args.warmup // args.conv_interval))
+        s.residual()   # warm-up of the reduction (and, partitioned, of NCCL's all-reduce channels)
+        s.step(args.conv_interval)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

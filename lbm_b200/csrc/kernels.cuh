@@ -758,27 +758,53 @@ __device__ __forceinline__ void issue_tile_loads(const DevParams<Real>& p, const
   }
 }
 
-// copy a collided stage out to buffer B: 128-bit shared loads and global stores, whole 32-byte sectors
+// copy a collided stage out to buffer B: 128-bit shared loads and global stores, whole 32-byte sectors.  Every thread serves the
+// same 16-byte unit in all of its directions, so where that unit sits -- in the stage (swizzled) and in the chunk -- is computed
+// once per kernel for the three layouts (UnitPos) instead of once per direction and tile.
+struct UnitPos { int soff[3]; int cpos[3]; };
+template <class L, class Real>
+__device__ __forceinline__ constexpr int half_stride(int lay) { // what tile half h adds to a chunk position
+  using C = FastCfg<L, Real>;
+  if(C::NSPLIT == 1) return 0;
+  if(L::D != 3 || lay == 0) return C::TS;
+  return lay == 1 ? (1 << (C::TB + C::LB)) : (1 << C::TB);
+}
+template <class L, class Real>
+__device__ __forceinline__ UnitPos unit_positions(int tp) {
+  UnitPos u;
+#pragma unroll
+  for(int lay = 0; lay < 3; ++lay) {
+    u.soff[lay] = stage_swizzle<L, Real>(lay, tp);
+    u.cpos[lay] = tile_to_chunk_pos<L, Real>(lay, tp, 0);
+  }
+  return u;
+}
 template <class L, class Real, int J, int STEP>
-__device__ __forceinline__ void copy_out_dirs(const DevParams<Real>& p, const Real* __restrict__ stg, int32_t base, int h, int unit_first, int unit_step) {
+__device__ __forceinline__ void copy_out_dirs(const DevParams<Real>& p, const Real* __restrict__ stg, int32_t base, int h, int unit_first, int unit_step,
+                                              const UnitPos& up) {
   using C = FastCfg<L, Real>;
   if constexpr(J < C::QM) {
     constexpr int lay = layout_of<L>(J);
-    for(int u = unit_first; u < C::UPD; u += unit_step) {
-      const int tp = u * C::EPU;
-      const uint32_t off = static_cast<uint32_t>(J) * static_cast<uint32_t>(p.stride) + static_cast<uint32_t>(base + tile_to_chunk_pos<L, Real>(lay, tp, h));
-      *reinterpret_cast<uint4*>(p.B + off) = *reinterpret_cast<const uint4*>(stg + J * C::TS + stage_swizzle<L, Real>(lay, tp));
+    if constexpr(kFastThreads >= C::UPD) {
+      const uint32_t off = static_cast<uint32_t>(J) * static_cast<uint32_t>(p.stride) + static_cast<uint32_t>(base + up.cpos[lay] + h * half_stride<L, Real>(lay));
+      *reinterpret_cast<uint4*>(p.B + off) = *reinterpret_cast<const uint4*>(stg + J * C::TS + up.soff[lay]);
+    } else {
+      for(int u = unit_first; u < C::UPD; u += unit_step) {
+        const int tp = u * C::EPU;
+        const uint32_t off = static_cast<uint32_t>(J) * static_cast<uint32_t>(p.stride) + static_cast<uint32_t>(base + tile_to_chunk_pos<L, Real>(lay, tp, h));
+        *reinterpret_cast<uint4*>(p.B + off) = *reinterpret_cast<const uint4*>(stg + J * C::TS + stage_swizzle<L, Real>(lay, tp));
+      }
     }
-    copy_out_dirs<L, Real, J + STEP, STEP>(p, stg, base, h, unit_first, unit_step);
+    copy_out_dirs<L, Real, J + STEP, STEP>(p, stg, base, h, unit_first, unit_step, up);
   }
 }
 template <class L, class Real, int G>
-__device__ __forceinline__ void copy_out_groups(const DevParams<Real>& p, const Real* __restrict__ stg, int32_t base, int h, int tid) {
+__device__ __forceinline__ void copy_out_groups(const DevParams<Real>& p, const Real* __restrict__ stg, int32_t base, int h, int tid, const UnitPos& up) {
   using C = FastCfg<L, Real>;
   constexpr int NG = kFastThreads >= C::UPD ? kFastThreads / C::UPD : 1;
   if constexpr(G < NG) {
-    if(NG == 1 || tid / C::UPD == G) copy_out_dirs<L, Real, G, NG>(p, stg, base, h, NG == 1 ? tid : tid % C::UPD, NG == 1 ? kFastThreads : C::UPD);
-    copy_out_groups<L, Real, G + 1>(p, stg, base, h, tid);
+    if(NG == 1 || tid / C::UPD == G) copy_out_dirs<L, Real, G, NG>(p, stg, base, h, NG == 1 ? tid : tid % C::UPD, NG == 1 ? kFastThreads : C::UPD, up);
+    copy_out_groups<L, Real, G + 1>(p, stg, base, h, tid, up);
   }
 }
 
@@ -826,6 +852,7 @@ __global__ void __launch_bounds__(kFastThreads, LBM_FAST_MINBLOCKS) k_step_fast(
   const Real* __restrict__ Abuf = p.A;
   const int tid = threadIdx.x;
   const int32_t n_tiles = p.n_fast_chunks * NSPLIT;
+  const UnitPos upos = unit_positions<L, Real>((tid % (kFastThreads >= C::UPD ? C::UPD : kFastThreads)) * C::EPU);
 
   fill_dir_words<L, 0>(s_dir, tid);
   // Tiles are handed out dynamically, in curve order, from a global ticket counter that only ever grows: a launch over n
@@ -927,7 +954,7 @@ __global__ void __launch_bounds__(kFastThreads, LBM_FAST_MINBLOCKS) k_step_fast(
       tk_pending = atomicAdd(p.ticket, 1ull);
     }
     __syncthreads(); // B2: the stage holds m_f of the whole tile
-    if(p.B != nullptr) copy_out_groups<L, Real, 0>(p, stg, base, h, tid);
+    if(p.B != nullptr) copy_out_groups<L, Real, 0>(p, stg, base, h, tid, upos);
   }
   cp_async_wait<0>();
 }

@@ -100,3 +100,25 @@ def test_invalid_wall_model_is_reported(tmp_path):
     p.write_text(json.dumps(cfg))
     rc, msg, _, _ = host_api.run(str(p))
     assert rc == -1 and "Invalid wall boundary model: slippery" in msg
+
+
+def test_diverging_run_ends_like_the_reference(tmp_path):
+    """src/lbm/solver.cpp:254-260, 327-333, 201-203: a NaN / Inf in the residual sets m_diverged; the loop stops, output() writes one more
+    solution file with the suffix "bdiv", and run() ends in TERMM(-1, "Solution diverged") -- exit status 255.  Configuration: the
+    reference's sphere case at level 5 with an absurd inlet pressure (3.0) and relaxation 0.501; the REFERENCE BINARY run on it here
+    (oracle/_ref/lbm_ref) detects the divergence at step 500 and leaves out/solution_500bdiv.vtp."""
+    import subprocess
+    cfg = json.loads(str(load_golden("sphere_ns").golden["config_orig_json"]))
+    for k in ("partitionLevel", "uniformLevel", "maxRfnmtLvl"):
+        cfg[k] = 5
+    s = cfg["solver"]
+    s.pop("reynoldsnumber")
+    s.pop("postprocessing", None)
+    s.update(relaxation=0.501, maxSteps=4000, info_interval=100, solution_interval=1000000)
+    s["boundary"]["cube"]["-x"]["pressure"] = 3.0
+    (tmp_path / "case.json").write_text(json.dumps(cfg))
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lbm_b200", "lbm")
+    r = subprocess.run([exe, "case.json"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 255, (r.returncode, r.stderr[-1500:])
+    assert "Solution diverged!" in r.stderr and "Solution diverged" in r.stderr.split("Solution diverged!")[-1]
+    assert (tmp_path / "out" / "solution_500bdiv.vtp").exists(), os.listdir(tmp_path / "out")

@@ -74,6 +74,32 @@ def test_total_mass_is_conserved(name, runs):
     assert abs(np.sum(rho) / SIZE ** 3 - 1.0) < 1e-12
 
 
+def test_cross_section_equals_the_oracle_on_a_thin_slab(runs, oracle_mod):
+    """x-invariance cannot see an error that is itself x-invariant (say a wrong wall descriptor applied to a whole row).  The y-z cross
+    section of the 256^3 run must therefore equal, BIT FOR BIT in strict arithmetic, the same cross section computed by the CPU oracle on a
+    slab that is 8 cells thick in the periodic x direction: every column of the slab executes exactly the arithmetic of a column of the
+    cube, and 8 x 256 x 256 cells are few enough for the oracle."""
+    from gridgen import box_grid
+    g = box_grid((8, SIZE, SIZE), (True, False, False))
+    o = oracle_mod.Oracle(3, 19, g["nghbr"][:, :18], 1.0 / 0.6)
+    for nm in sorted(["-y", "+y", "-z", "+z"]):
+        cells, normals = g["surfaces"][nm]
+        if nm == "+z":
+            o.add_dirichlet_bb(cells, normals, np.array([0.05, 0.0, 0.0]))
+        else:
+            o.add_wall_bb(cells, normals, 0.0)
+    o.init()
+    o.step(STEPS)
+    o.update_moments()
+    c = g["coords"]
+    want = np.empty((SIZE, SIZE, 4))
+    sel = c[:, 0] == 0
+    want[c[sel, 1], c[sel, 2]] = o.vars[sel]
+    r = runs["strict"]
+    got = columns(r["m"], r["coords"])[:, :, 0, :]
+    assert np.array_equal(got, want), f"max difference {np.max(np.abs(got - want)):.3e}"
+
+
 def test_fast_agrees_with_strict(runs):
     a, b = runs["fast"]["m"], runs["strict"]["m"]
     assert np.max(np.abs(a[:, 3] - b[:, 3])) < 1e-12                     # density, relative to rho = 1
