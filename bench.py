@@ -410,6 +410,9 @@ def run_reference(args):
     emit(line)
 
 
+HALO_TEXT = {"p2p": "peer-to-peer (CUDA IPC mailboxes over NVLink, copy engines, one launch per step)", "nccl": "ncclSend/ncclRecv"}
+
+
 def config_dict(args, note):
     ndim, ndist = LATTICES[args.lattice]
     if args.impl == "reference" and args.workload != "box":
@@ -422,17 +425,17 @@ def config_dict(args, note):
         return {"workload": f"{args.workload}-3D {args.size}^3 {args.lattice} {args.collision.upper()} {getattr(args, 'precision', 'fp64')}: {what}, omega={OMEGA:.6f}",
                 "lattice": args.lattice, "collision": args.collision, "arithmetic": args.arithmetic,
                 "l2_policy": "inputs larger than L2 (no flush needed)" if args.size >= 128 else "SMALL CASE: fits L2, not a bandwidth measurement",
-                "parallelism": (f"one cube of {args.size}^3 cells cut into {args.gpus} contiguous SFC ranges (fixed total size), ncclSend/ncclRecv "
-                                f"halo exchange of outgoing populations every step") if args.gpus > 1 else "single GPU", "note": note}
+                "parallelism": (f"one cube of {args.size}^3 cells cut into {args.gpus} contiguous SFC ranges (fixed total size), "
+                                f"{HALO_TEXT[getattr(args, 'halo', 'p2p')]} halo exchange of outgoing populations every step") if args.gpus > 1 else "single GPU", "note": note}
     return {"workload": f"bench-3D cube {args.size}^{ndim} {args.lattice} BGK {getattr(args, 'precision', 'fp64')} (BASELINE.json configs[2]; SURVEY 8d S3): "
                         f"periodic x, bounce-back walls, moving lid u={LID_U}, omega={OMEGA:.6f}",
             "cells_per_gpu": args.size ** ndim, "lattice": args.lattice, "collision": "bgk", "arithmetic": args.arithmetic,
             "l2_policy": "inputs larger than L2 (no flush needed)", "parallelism": (f"one box of {'x'.join(map(str, global_shape(args.size, ndim, args.gpus)))} cells cut into {args.gpus} contiguous "
-                            f"SFC ranges, ncclSend/ncclRecv halo exchange of outgoing populations every step")
+                            f"SFC ranges, {HALO_TEXT[getattr(args, 'halo', 'p2p')]} halo exchange of outgoing populations every step")
             if args.gpus > 1 else "single GPU", "note": note}
 
 
-def parity_check(rank, world, local, dist, torch, lbm_b200):
+def parity_check(rank, world, local, dist, torch, lbm_b200, halo):
     """Driver-visible parity of the (multi-rank) path: 5 STRICT steps of a D3Q19 box with 64^3 cells per rank, cut into `world`
     contiguous SFC ranges and exchanged over NCCL exactly like the timed run; rank 0 compares the owned m_f of all ranks, bit for bit,
     with the single-domain CPU oracle (the checker, never the thing measured) and reports the SHA-256 of both."""
@@ -449,7 +452,10 @@ def parity_check(rank, world, local, dist, torch, lbm_b200):
         wl["lp"].apply_halo(s)
         s.comm_init(uid[0], rank, world)
     s.init()
+    if world > 1 and halo == "p2p":
+        s.p2p_connect(dist)
     s.step(steps)
+    s.synchronize()
     mine = torch.from_numpy(np.ascontiguousarray(s.f[:wl["n_owned"]])).cuda()
     parts = [mine]
     if world > 1:
@@ -489,7 +495,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     arithmetic = lbm_b200.FAST if args.arithmetic == "fast" else lbm_b200.STRICT
-    parity = None if args.no_parity else parity_check(rank, world, local, dist if world > 1 else None, torch, lbm_b200)
+    parity = None if args.no_parity else parity_check(rank, world, local, dist if world > 1 else None, torch, lbm_b200, args.halo)
     t_setup = time.perf_counter()
     if args.workload == "box":
         wl = workload(args.size, args.lattice, rank, world)
@@ -513,6 +519,8 @@ def run_ours(args):
         wl["lp"].apply_halo(s)
         s.comm_init(uid[0], rank, world)
     s.init()
+    if world > 1 and args.halo == "p2p":
+        s.p2p_connect(dist)
     nghbr_keep = wl["nghbr"] if args.conv_interval > 0 else None   # the residual-mode run below sets up a second solver
     del wl["nghbr"]
     t_setup = time.perf_counter() - t_setup
@@ -552,6 +560,8 @@ def run_ours(args):
             wl["lp"].apply_halo(s)
             s.comm_init(uid[0], rank, world)
         s.init()
+        if world > 1 and args.halo == "p2p":
+            s.p2p_connect(dist)
         s.step(args.conv_interval * max(1, args.warmup // args.conv_interval))
         s.residual()   # warm-up of the reduction (and, partitioned, of NCCL's all-reduce channels)
         s.step(args.conv_interval)
@@ -663,6 +673,9 @@ def main():
     ap.add_argument("--conv-interval", type=int, default=10, dest="conv_interval",
                     help="second measurement with the reference's residual bookkeeping every N steps inside the timed region (0: skip)")
     ap.add_argument("--no-parity", action="store_true", dest="no_parity")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU halo exchange: p2p = CUDA IPC mailboxes + copy engines + flag words, one launch per step (default); "
+                         "nccl = ncclSend / ncclRecv with an outer and an inner launch")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -165,6 +165,8 @@ def load_library():
     L.lbm_b200_set_forcing.argtypes = [vp, pi64, i64, pi64, i64, dbl]
     L.lbm_b200_set_stream.argtypes = [vp, vp]
     L.lbm_b200_init.argtypes = [vp]
+    L.lbm_b200_p2p_export.argtypes = [vp, vp]
+    L.lbm_b200_p2p_import.argtypes = [vp, i32, vp]
     L.lbm_b200_step.argtypes = [vp, i64]
     L.lbm_b200_step_timed.argtypes = [vp, i64, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.lbm_b200_synchronize.argtypes = [vp]
@@ -339,6 +341,27 @@ class Solver:
     # ---- run
     def init(self):
         self._check(self._lib.lbm_b200_init(self._h))
+
+    P2P_BLOB = 1024
+
+    def p2p_export(self):
+        """this rank's mailbox description for the peer-to-peer halo (bytes; all-gather them in rank order and call p2p_import)"""
+        buf = C.create_string_buffer(self.P2P_BLOB)
+        self._check(self._lib.lbm_b200_p2p_export(self._h, buf))
+        return buf.raw
+
+    def p2p_import(self, blobs):
+        """blobs: the exported descriptions of ALL ranks, in rank order"""
+        raw = b"".join(blobs)
+        assert len(raw) == self.P2P_BLOB * len(blobs)
+        self._check(self._lib.lbm_b200_p2p_import(self._h, len(blobs), raw))
+
+    def p2p_connect(self, dist):
+        """export -> torch.distributed all-gather -> import; call on every rank after init()"""
+        mine = self.p2p_export()
+        blobs = [None] * dist.get_world_size()
+        dist.all_gather_object(blobs, mine)
+        self.p2p_import(blobs)
 
     def step(self, n=1):
         self._check(self._lib.lbm_b200_step(self._h, int(n)))

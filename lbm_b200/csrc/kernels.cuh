@@ -72,6 +72,10 @@ struct DevParams {
   int32_t         n_fast_blocks;
   unsigned long long* ticket;      // global chunk ticket counter of this launch class
   unsigned long long  ticket_base; // value of the counter when this launch starts
+  // peer-to-peer halo: the first n_outer_tiles tiles of the launch hold populations a peer needs; every such tile that has been
+  // written out bumps *outer_done, which the communication stream watches (nullptr: not used)
+  unsigned long long* outer_done;
+  int32_t             n_outer_tiles;
   // generic range
   int32_t        gen_begin, n_gen, n_gen_blocks; // generic cells [gen_off, gen_off + n_gen) of the generic range
   int32_t        gen_off;
@@ -955,6 +959,13 @@ __global__ void __launch_bounds__(kFastThreads, LBM_FAST_MINBLOCKS) k_step_fast(
     }
     __syncthreads(); // B2: the stage holds m_f of the whole tile
     if(p.B != nullptr) copy_out_groups<L, Real, 0>(p, stg, base, h, tid, upos);
+    if(p.outer_done != nullptr && ticket < p.n_outer_tiles) {
+      __syncthreads(); // every thread's part of the tile is on its way to global memory
+      if(tid == 0) {
+        __threadfence();
+        atomicAdd(p.outer_done, 1ull);
+      }
+    }
   }
   cp_async_wait<0>();
 }
@@ -1129,6 +1140,45 @@ template <class Real>
 __global__ void k_halo_unpack(Real* __restrict__ f, const int64_t* __restrict__ index, int64_t n, const Real* __restrict__ in) {
   const int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if(k < n) f[index[k]] = in[k];
+}
+
+// ---- peer-to-peer halo (solver_fused.cuh: p2p_exchange): small kernels of the communication stream.  They are sized to fit beside
+// the persistent chunk CTAs (one warp, a handful of registers), which is what lets the exchange run while the inner tiles are updated.
+#if defined(__CUDACC__)
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
+#else
+static inline unsigned long long ld_volatile_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+#endif
+constexpr long long kSpinLimit = 1ll << 31; // ~ tens of seconds: a peer that never signals ends in an error, not in a hung GPU
+
+// wait until a local counter has reached `target` (the outer tiles of this step are written)
+static __global__ void k_wait_counter(const unsigned long long* ctr, unsigned long long target, int* err) {
+  if(threadIdx.x != 0) return;
+  long long spins = 0;
+  while(ld_volatile_u64(ctr) < target) {
+    __nanosleep(200);
+    if(++spins > kSpinLimit) { *err = 1; break; }
+  }
+  __threadfence();
+}
+// tell every peer that this rank's populations of exchange `seq` have landed in its mailbox
+static __global__ void k_p2p_signal(unsigned long long* const* flags, int n, unsigned long long seq) {
+  const int k = threadIdx.x;
+  if(k >= n) return;
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned long long*>(flags[k]) = seq;
+  __threadfence_system();
+}
+// wait until every peer has signalled exchange `seq` in this rank's mailbox
+static __global__ void k_p2p_wait(const unsigned long long* flags, int n, unsigned long long seq, int* err) {
+  const int k = threadIdx.x;
+  if(k >= n) return;
+  long long spins = 0;
+  while(ld_volatile_u64(flags + k) < seq) {
+    __nanosleep(200);
+    if(++spins > kSpinLimit) { *err = 2; break; }
+  }
+  __threadfence_system();
 }
 
 // initialCondition(): rho = 1, u = preset, f = feq  (solver.cpp:267-295)

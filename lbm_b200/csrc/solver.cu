@@ -905,6 +905,18 @@ int lbm_b200_comm_init(lbm_b200_solver* s, const char* id128, int32_t rank, int3
   return LBM_B200_OK;
 }
 
+int lbm_b200_p2p_export(lbm_b200_solver* s, void* blob) {
+  CHECK_HANDLE(s);
+  if(blob == nullptr) return fail(LBM_B200_EINVAL, "null argument");
+  return s->impl->p2p_export(blob);
+}
+
+int lbm_b200_p2p_import(lbm_b200_solver* s, int32_t nranks, const void* blobs) {
+  CHECK_HANDLE(s);
+  if(blobs == nullptr || nranks < 1) return fail(LBM_B200_EINVAL, "bad argument");
+  return s->impl->p2p_import(nranks, blobs);
+}
+
 int lbm_b200_box_rows(int32_t ndim, const int64_t* shape, const int32_t* periodic, const int64_t* cells, int64_t ncells, int64_t* nghbr,
                       int32_t stride, double* center) {
   if(shape == nullptr || periodic == nullptr || nghbr == nullptr || (ncells > 0 && cells == nullptr)) return fail(LBM_B200_EINVAL, "null argument");

@@ -48,6 +48,29 @@ struct Solver final : SolverBase {
   cudaEvent_t  ev_outer = nullptr, ev_halo = nullptr, ev_pack = nullptr;
   bool         halo_pending = false;
   int64_t launches = 0, launches_main = 0;
+  // ---- peer-to-peer halo over NVLink (CUDA IPC): every rank owns a mailbox = flag words + two receive buffers (exchange parity);
+  // peers write into it with device-to-device copies on the copy engines and then raise their flag
+  static constexpr int kMaxP2PPeers = 40;
+  struct P2PBlob {
+    cudaIpcMemHandle_t mem;
+    int32_t rank, npeers, real_bytes, pad;
+    int64_t slot_elems;
+    int32_t peers[kMaxP2PPeers];
+    int64_t recv_off[kMaxP2PPeers], recv_cnt[kMaxP2PPeers];
+  };
+  static_assert(sizeof(P2PBlob) <= LBM_B200_P2P_BLOB, "blob size");
+  static constexpr size_t kFlagBytes = 512;
+  DevBuf<unsigned char> mailbox;
+  DevBuf<unsigned long long> d_outer_done;
+  DevBuf<unsigned long long*> d_flag_ptrs;
+  DevBuf<int> d_p2p_err;
+  std::vector<void*>  p2p_peer_base;   // opened mailboxes, one per peer in list order
+  std::vector<size_t> p2p_peer_off;    // byte offset of my segment inside the peer's receive buffer
+  std::vector<size_t> p2p_peer_slot;   // bytes of one receive buffer of the peer
+  int64_t p2p_slot_elems = 0;
+  unsigned long long p2p_seq = 0, outer_total = 0;
+  bool p2p_on = false;
+  cudaEvent_t ev_step = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr; // evm0 / evm1 point into ev_ring while a timed run records
   std::vector<cudaEvent_t> ev_ring;
 
@@ -58,6 +81,8 @@ struct Solver final : SolverBase {
     if(ev_outer) cudaEventDestroy(ev_outer);
     if(ev_halo) cudaEventDestroy(ev_halo);
     if(ev_pack) cudaEventDestroy(ev_pack);
+    if(ev_step) cudaEventDestroy(ev_step);
+    for(void* b : p2p_peer_base) if(b) cudaIpcCloseMemHandle(b);
     if(comm_stream) cudaStreamDestroy(comm_stream);
     if(ev_fork) cudaEventDestroy(ev_fork);
     if(ev_join) cudaEventDestroy(ev_join);
@@ -234,6 +259,17 @@ struct Solver final : SolverBase {
       CUDA_TRY(cudaEventCreateWithFlags(&ev_outer, cudaEventDisableTiming));
       CUDA_TRY(cudaEventCreateWithFlags(&ev_halo, cudaEventDisableTiming));
       CUDA_TRY(cudaEventCreateWithFlags(&ev_pack, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&ev_step, cudaEventDisableTiming));
+      // mailbox of the peer-to-peer halo (used once lbm_b200_p2p_import has mapped the peers)
+      int64_t nrecv = 0;
+      for(int64_t v : in.recv_count) nrecv += v;
+      p2p_slot_elems = (nrecv + 63) / 64 * 64;
+      CUDA_TRY(mailbox.alloc(kFlagBytes + 2 * static_cast<size_t>(p2p_slot_elems) * sizeof(Real)));
+      CUDA_TRY(cudaMemset(mailbox.p, 0, mailbox.bytes()));
+      CUDA_TRY(d_outer_done.alloc(1));
+      CUDA_TRY(cudaMemset(d_outer_done.p, 0, sizeof(unsigned long long)));
+      CUDA_TRY(d_p2p_err.alloc(1));
+      CUDA_TRY(cudaMemset(d_p2p_err.p, 0, sizeof(int)));
     }
 
     // ---- initialCondition(): vars = 0, boundary presets, rho = 1, f = fold = feq   (solver.cpp:267-295)
@@ -375,12 +411,96 @@ struct Solver final : SolverBase {
     return LBM_B200_OK;
   }
 
+  int p2p_export(void* out) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "lbm_b200_p2p_export: call after lbm_b200_init");
+    if(in.peers.empty()) return fail(LBM_B200_ESTATE, "lbm_b200_p2p_export: this rank has no halo lists");
+    if(in.peers.size() > static_cast<size_t>(kMaxP2PPeers)) return fail(LBM_B200_EUNSUP, "peer-to-peer halo: too many neighbour ranks");
+    P2PBlob b{};
+    CUDA_TRY(cudaIpcGetMemHandle(&b.mem, mailbox.p));
+    b.rank = comm_rank;
+    b.npeers = static_cast<int32_t>(in.peers.size());
+    b.real_bytes = static_cast<int32_t>(sizeof(Real));
+    b.slot_elems = p2p_slot_elems;
+    int64_t off = 0;
+    for(size_t k = 0; k < in.peers.size(); ++k) {
+      b.peers[k] = in.peers[k];
+      b.recv_off[k] = off;
+      b.recv_cnt[k] = in.recv_count[k];
+      off += in.recv_count[k];
+    }
+    std::memset(out, 0, LBM_B200_P2P_BLOB);
+    std::memcpy(out, &b, sizeof(b));
+    return LBM_B200_OK;
+  }
+
+  int p2p_import(int32_t nranks, const void* blobs) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "lbm_b200_p2p_import: call after lbm_b200_init");
+    if(p2p_on) return fail(LBM_B200_ESTATE, "lbm_b200_p2p_import: already imported");
+    if(has_velocity_halo()) return fail(LBM_B200_EUNSUP, "peer-to-peer halo: the velocity halo of a pressure boundary across a cut travels over NCCL");
+    const unsigned char* base = static_cast<const unsigned char*>(blobs);
+    std::vector<unsigned long long*> flag_ptrs;
+    for(size_t k = 0; k < in.peers.size(); ++k) {
+      const int r = in.peers[k];
+      if(r < 0 || r >= nranks) return fail(LBM_B200_EINVAL, "peer-to-peer halo: peer rank out of range");
+      P2PBlob b;
+      std::memcpy(&b, base + static_cast<size_t>(r) * LBM_B200_P2P_BLOB, sizeof(b));
+      if(b.rank != r || b.real_bytes != static_cast<int32_t>(sizeof(Real))) return fail(LBM_B200_EINVAL, "peer-to-peer halo: blob does not belong to that rank / precision");
+      int j = -1;
+      for(int q = 0; q < b.npeers; ++q) if(b.peers[q] == comm_rank) j = q;
+      if(j < 0 || b.recv_cnt[j] != in.send_count[k]) return fail(LBM_B200_EINVAL, "peer-to-peer halo: the peer's receive list does not match this rank's send list");
+      void* pb = nullptr;
+      CUDA_TRY(cudaIpcOpenMemHandle(&pb, b.mem, cudaIpcMemLazyEnablePeerAccess));
+      p2p_peer_base.push_back(pb);
+      p2p_peer_off.push_back(static_cast<size_t>(b.recv_off[j]) * sizeof(Real));
+      p2p_peer_slot.push_back(static_cast<size_t>(b.slot_elems) * sizeof(Real));
+      flag_ptrs.push_back(reinterpret_cast<unsigned long long*>(pb) + j);
+    }
+    CUDA_TRY(d_flag_ptrs.upload(flag_ptrs));
+    p2p_on = true;
+    return LBM_B200_OK;
+  }
+
+  // Outgoing populations of this step -> the peers' mailboxes, theirs -> my ghost cells, without a single SM-sized kernel: one small
+  // pack kernel, device-to-device copies over NVLink on the copy engines, a one-warp kernel that raises my flag in every peer's
+  // mailbox, a one-warp kernel that waits for the peers' flags, one small unpack kernel.  All of them fit beside the persistent chunk
+  // CTAs, so the exchange really runs while the inner tiles are updated.
+  int p2p_exchange(Real* buf, cudaStream_t st) {
+    const int64_t ns = static_cast<int64_t>(plan.send_index.size()), nr = static_cast<int64_t>(plan.recv_index.size());
+    const unsigned long long seq = ++p2p_seq;
+    const size_t parity = static_cast<size_t>(seq & 1);
+    if(ns > 0) {
+      lbm::k_halo_pack<Real><<<static_cast<int>((ns + 127) / 128), 128, 0, st>>>(buf, d_send_idx.p, ns, d_sendbuf.p);
+      ++launches;
+    }
+    int64_t so = 0;
+    for(size_t k = 0; k < in.peers.size(); ++k) {
+      if(in.send_count[k] > 0) {
+        unsigned char* dstp = static_cast<unsigned char*>(p2p_peer_base[k]) + kFlagBytes + parity * p2p_peer_slot[k] + p2p_peer_off[k];
+        CUDA_TRY(cudaMemcpyAsync(dstp, d_sendbuf.p + so, static_cast<size_t>(in.send_count[k]) * sizeof(Real), cudaMemcpyDeviceToDevice, st));
+      }
+      so += in.send_count[k];
+    }
+    const int np = static_cast<int>(in.peers.size());
+    lbm::k_p2p_signal<<<1, 64, 0, st>>>(d_flag_ptrs.p, np, seq);
+    lbm::k_p2p_wait<<<1, 64, 0, st>>>(reinterpret_cast<const unsigned long long*>(mailbox.p), np, seq, d_p2p_err.p);
+    launches += 2;
+    if(nr > 0) {
+      const Real* rb = reinterpret_cast<const Real*>(mailbox.p + kFlagBytes) + parity * static_cast<size_t>(p2p_slot_elems);
+      lbm::k_halo_unpack<Real><<<static_cast<int>((nr + 127) / 128), 128, 0, st>>>(buf, d_recv_idx.p, nr, rb);
+      ++launches;
+    }
+    halo_bytes += (ns + nr) * static_cast<int64_t>(sizeof(Real));
+    CUDA_TRY(cudaGetLastError());
+    return LBM_B200_OK;
+  }
+
   bool has_velocity_halo() const { return !in.vsend_cell.empty() || !in.vrecv_cell.empty(); }
 
   // a launch over generic cells [g0, g0+ng) and fast chunks [c0, c0+ncnk): the link-code cells on the side stream (they are
   // latency bound and few), the persistent chunk CTAs on the solver's stream; both read buffer A and write disjoint cells of B
   // extrap_nd >= 0: also run the pressure extrapolation of this step (it only reads buffer A and writes d_uext[extrap_nd]) on the side stream
-  int launch_main(const lbm::DevParams<Real>& p, int64_t g0, int64_t ng, int64_t c0, int64_t ncnk, int resident_cap, int cls, int extrap_nd = -1) {
+  int launch_main(const lbm::DevParams<Real>& p, int64_t g0, int64_t ng, int64_t c0, int64_t ncnk, int resident_cap, int cls, int extrap_nd = -1,
+                  int64_t outer_chunks = 0) {
     lbm::DevParams<Real> q = p;
     q.gen_off       = static_cast<int32_t>(g0);
     q.n_gen         = static_cast<int32_t>(ng);
@@ -389,6 +509,8 @@ struct Solver final : SolverBase {
     q.n_fast_chunks = static_cast<int32_t>(ncnk);
     const int64_t ntiles = ncnk * lbm::FastCfg<L, Real>::NSPLIT; // the persistent CTAs draw tiles (whole chunks or their halves)
     q.n_fast_blocks = static_cast<int32_t>(ntiles < resident_cap ? ntiles : resident_cap);
+    q.outer_done    = outer_chunks > 0 ? d_outer_done.p : nullptr;
+    q.n_outer_tiles = static_cast<int32_t>(outer_chunks * lbm::FastCfg<L, Real>::NSPLIT);
     q.ticket        = d_ticket.p + cls;
     q.ticket_base   = ticket_next[cls];
     ticket_next[cls] += static_cast<unsigned long long>(ntiles)
@@ -444,7 +566,35 @@ struct Solver final : SolverBase {
     }
     if(time_main) cudaEventRecord(evm0, stream);
     int rc = LBM_B200_OK;
-    if(overlap) {
+    if(overlap && p2p_on) {
+      // Peer-to-peer halo: ONE launch over all tiles, the outer ones first in ticket order.  The communication stream waits (a one-warp
+      // kernel) until the device-side counter says they are written, then moves them; the persistent CTAs just carry on with the inner
+      // tiles.  No split launch, no SM-sized communication kernel.
+      CUDA_TRY(cudaEventRecord(ev_step, stream));
+      CUDA_TRY(cudaStreamWaitEvent(comm_stream, ev_step, 0));
+      const bool gen_side = plan.n_gen > 0 && plan.n_fast_chunks > 0;
+      rc = launch_main(p, 0, plan.n_gen, 0, plan.n_fast_chunks, max_resident, 0, -1, plan.n_fast_outer);
+      if(rc != LBM_B200_OK) return rc;
+      if(time_main) cudaEventRecord(evm1, stream);
+      if(gen_side) CUDA_TRY(cudaStreamWaitEvent(comm_stream, ev_join, 0)); // the link-code cells (all of them, they are few) are written
+      else if(plan.n_fast_chunks == 0) { CUDA_TRY(cudaEventRecord(ev_outer, stream)); CUDA_TRY(cudaStreamWaitEvent(comm_stream, ev_outer, 0)); }
+      if(plan.n_fast_outer > 0) {
+        outer_total += static_cast<unsigned long long>(plan.n_fast_outer) * lbm::FastCfg<L, Real>::NSPLIT;
+        lbm::k_wait_counter<<<1, 32, 0, comm_stream>>>(d_outer_done.p, outer_total, d_p2p_err.p);
+        ++launches;
+      }
+      rc = p2p_exchange(f[dst].p, comm_stream);
+      if(rc != LBM_B200_OK) return rc;
+      CUDA_TRY(cudaEventRecord(ev_halo, comm_stream));
+      halo_pending = true;
+      if(has_aux) { // pressure boundary present: extrapolation + m_vars fix-ups behind the launch, the exchange in flight
+        const int nd = dyn ^ 1;
+        bool      dyn_written = false;
+        rc = cfg.arithmetic == LBM_B200_STRICT ? aux_kernels<true>(p, vout, nd, 2 | 4, &dyn_written) : aux_kernels<false>(p, vout, nd, 2 | 4, &dyn_written);
+        if(rc != LBM_B200_OK) return rc;
+        if(dyn_written) dyn = nd;
+      }
+    } else if(overlap) {
       // 1. outer cells (whatever a peer needs) with the whole GPU; 2. their populations are packed and travel (NCCL group on
       // the high-priority communication stream) while 3. the inner cells are updated.  The inner launch is released by the
       // same event that releases the NCCL kernel, so the (higher-priority, whole-SM-sized) NCCL CTAs are placed first and
@@ -496,7 +646,7 @@ struct Solver final : SolverBase {
       } else {
         rc = aux(extrap_side ? (1 | 4) : (1 | 2 | 4));
         if(rc != LBM_B200_OK) return rc;
-        rc = halo_exchange(f[dst].p, stream);
+        rc = (p2p_on && !in.peers.empty()) ? p2p_exchange(f[dst].p, stream) : halo_exchange(f[dst].p, stream);
         if(rc != LBM_B200_OK) return rc;
       }
       if(dyn_written) dyn = nd;
@@ -558,6 +708,11 @@ struct Solver final : SolverBase {
   int sync() override {
     if(comm_stream) CUDA_TRY(cudaStreamSynchronize(comm_stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
+    if(p2p_on) {
+      int e = 0;
+      CUDA_TRY(cudaMemcpy(&e, d_p2p_err.p, sizeof(int), cudaMemcpyDeviceToHost));
+      if(e != 0) return fail(LBM_B200_ECUDA, e == 1 ? "peer-to-peer halo: the outer tiles of a step never completed" : "peer-to-peer halo: a peer never signalled its populations");
+    }
     return LBM_B200_OK;
   }
 

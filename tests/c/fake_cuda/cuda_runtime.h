@@ -29,6 +29,9 @@ static bool              g_block_barrier_on = false; // single-threaded driver l
 static inline void __syncthreads() {
   if(g_block_barrier_on) pthread_barrier_wait(&g_block_barrier);
 }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __nanosleep(unsigned) {}
 template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline T __ldcg(const T* p) { return *p; }
 template <class T> static inline void __stcs(T* p, T v) { *p = v; }

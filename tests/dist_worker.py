@@ -113,6 +113,7 @@ def main():
     ap.add_argument("--level", type=int, default=5)
     ap.add_argument("--collision", default="bgk", choices=["bgk", "trt", "mrt"])
     ap.add_argument("--check-residual", action="store_true", dest="check_residual")
+    ap.add_argument("--p2p", action="store_true", help="peer-to-peer halo (CUDA IPC mailboxes, copy engines) instead of ncclSend / ncclRecv")
     ap.add_argument("--bc", default="walls", help="walls: periodic x, walls, moving lid; pressure: pressure in-/outlet on -x/+x")
     args = ap.parse_args()
     shape = tuple(int(x) for x in args.shape.split(","))
@@ -190,7 +191,10 @@ def main():
         lp.apply_halo(s)
         s.comm_init(uid[0], rank, world)
         s.init()
+        if args.p2p:
+            s.p2p_connect(dist)
         s.step(args.steps)
+        s.synchronize()
         mine_f, mine_fold = s.f[:lp.n_owned], s.fold[:lp.n_owned]
         # residual of the whole domain: ncclAllReduce over the ranks' owned cells (order of the sum differs from the serial one)
         if args.check_residual:

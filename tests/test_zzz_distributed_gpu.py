@@ -35,6 +35,21 @@ def test_partitioned_gpu_baseline_configs_nccl(case, collision, level):
     launch(2, "gpu", "0,0,0", 0, steps=10, extra=("--case", case, "--level", str(level), "--collision", collision))
 
 
+@pytest.mark.parametrize("shape,ndist", [("32,32,32", 19), ("24,16,16", 27), ("64,64", 9), ("64,32,32", 19)])
+def test_partitioned_gpu_peer_to_peer_halo(shape, ndist):
+    """The peer-to-peer halo (lbm_b200_p2p_export / _import: CUDA IPC mailboxes, device-to-device copies on the copy engines, flag words,
+    ONE launch per step with the outer tiles first) instead of ncclSend / ncclRecv: owned cells bit-identical to the single-domain oracle,
+    and the all-reduced residual (still NCCL) agrees."""
+    _need_two_gpus()
+    launch(2, "gpu", shape, ndist, steps=14, extra=("--p2p", "--check-residual"))
+
+
+@pytest.mark.parametrize("case,collision,level", [("step3d", "trt", 6)])
+def test_partitioned_gpu_peer_to_peer_halo_with_pressure_boundary(case, collision, level):
+    _need_two_gpus()
+    launch(2, "gpu", "0,0,0", 0, steps=10, extra=("--case", case, "--level", str(level), "--collision", collision, "--p2p"))
+
+
 def test_cpp_host_two_ranks_match_one_rank(tmp_path):
     """`lbm` as two processes (one GPU each; rank / world size from the environment, NCCL id through a file): the moments each rank
     writes for its own cells must equal the single-process run's, bit for bit (STRICT fp64).  The set-up half is pinned on the CPU
