@@ -356,12 +356,22 @@ class Solver:
         assert len(raw) == self.P2P_BLOB * len(blobs)
         self._check(self._lib.lbm_b200_p2p_import(self._h, len(blobs), raw))
 
-    def p2p_connect(self, dist):
-        """export -> torch.distributed all-gather -> import; call on every rank after init()"""
+    def p2p_connect(self, dist, lp=None):
+        """export -> torch.distributed all-gather -> import; call on every rank after init().  Returns False (and leaves the exchange on
+        NCCL, on ALL ranks) when some rank cannot take part: a velocity halo of a pressure boundary across a cut (lp.vsend_count /
+        lp.vrecv_count), or no halo lists at all."""
+        able = True
+        if lp is not None:
+            able = not (sum(lp.vsend_count or [0]) or sum(lp.vrecv_count or [0])) and len(lp.peers) > 0
+        flags = [None] * dist.get_world_size()
+        dist.all_gather_object(flags, bool(able))
+        if not all(flags):
+            return False
         mine = self.p2p_export()
         blobs = [None] * dist.get_world_size()
         dist.all_gather_object(blobs, mine)
         self.p2p_import(blobs)
+        return True
 
     def step(self, n=1):
         self._check(self._lib.lbm_b200_step(self._h, int(n)))

@@ -888,6 +888,7 @@ __global__ void __launch_bounds__(kFastThreads, LBM_FAST_MINBLOCKS) k_step_fast(
     cp_async_commit();
   }
 
+  int outer_mine = 0; // outer tiles this CTA has written since it last told the communication stream
   for(int i = 0;; ++i) {
     const int32_t ticket = s_tk[i % C::RT];
     if(ticket >= n_tiles) break;
@@ -905,6 +906,15 @@ __global__ void __launch_bounds__(kFastThreads, LBM_FAST_MINBLOCKS) k_step_fast(
     }
     cp_async_wait<NSTAGE - 2>();
     __syncthreads(); // B1: this tile's stage is complete; every thread has left the previous iteration
+    // peer-to-peer halo: tickets grow, so the first inner tile means every outer tile of this CTA has been copied out (by all of
+    // its threads: B1) -- ONE fence and ONE atomic per CTA and step tell the communication stream how many those were
+    if(p.outer_done != nullptr && outer_mine > 0 && ticket >= p.n_outer_tiles) {
+      if(tid == 0) {
+        __threadfence();
+        atomicAdd(p.outer_done, static_cast<unsigned long long>(outer_mine));
+      }
+      outer_mine = 0;
+    }
     // neighbour bases of tile i + NSTAGE: fetched now, published before B2
     const int32_t tk_nb  = s_tk[(i + NSTAGE) % C::RT];
     int32_t       nb_val = 0;
@@ -959,15 +969,16 @@ __global__ void __launch_bounds__(kFastThreads, LBM_FAST_MINBLOCKS) k_step_fast(
     }
     __syncthreads(); // B2: the stage holds m_f of the whole tile
     if(p.B != nullptr) copy_out_groups<L, Real, 0>(p, stg, base, h, tid, upos);
-    if(p.outer_done != nullptr && ticket < p.n_outer_tiles) {
-      __syncthreads(); // every thread's part of the tile is on its way to global memory
-      if(tid == 0) {
-        __threadfence();
-        atomicAdd(p.outer_done, 1ull);
-      }
-    }
+    if(ticket < p.n_outer_tiles) ++outer_mine;
   }
   cp_async_wait<0>();
+  if(p.outer_done != nullptr && outer_mine > 0) { // this CTA ended on an outer tile
+    __syncthreads();
+    if(tid == 0) {
+      __threadfence();
+      atomicAdd(p.outer_done, static_cast<unsigned long long>(outer_mine));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------- auxiliary kernels

@@ -415,6 +415,7 @@ struct Solver final : SolverBase {
     if(!inited) return fail(LBM_B200_ESTATE, "lbm_b200_p2p_export: call after lbm_b200_init");
     if(in.peers.empty()) return fail(LBM_B200_ESTATE, "lbm_b200_p2p_export: this rank has no halo lists");
     if(in.peers.size() > static_cast<size_t>(kMaxP2PPeers)) return fail(LBM_B200_EUNSUP, "peer-to-peer halo: too many neighbour ranks");
+    if(has_velocity_halo()) return fail(LBM_B200_EUNSUP, "peer-to-peer halo: the velocity halo of a pressure boundary across a cut travels over NCCL");
     P2PBlob b{};
     CUDA_TRY(cudaIpcGetMemHandle(&b.mem, mailbox.p));
     b.rank = comm_rank;

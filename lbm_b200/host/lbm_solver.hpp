@@ -11,6 +11,7 @@
 // stderr text and exit status.
 #pragma once
 #include <algorithm>
+#include <cctype>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -100,6 +101,16 @@ struct RankInfo {
     else {
       const char* port = std::getenv("MASTER_PORT");
       r.id_file = std::string("/tmp/lbm_b200_id_") + (port != nullptr ? std::string(port) : std::to_string(static_cast<long>(getppid())));
+      // a per-launch nonce when the launcher provides one: two runs that reuse a port never read each other's file
+      for(const char* name : {"LBM_B200_RUN_ID", "TORCHELASTIC_RUN_ID", "SLURM_JOB_ID"}) {
+        const char* v = std::getenv(name);
+        if(v != nullptr && v[0] != 0) {
+          std::string clean;
+          for(const char* c = v; *c; ++c) clean += (std::isalnum(static_cast<unsigned char>(*c)) ? *c : '_');
+          r.id_file += "_" + clean.substr(0, 64);
+          break;
+        }
+      }
     }
     return r;
   }
@@ -462,6 +473,45 @@ class LBMSolver final : public Runnable {
     TERMM(-1, "timed out waiting for the NCCL id file " + path);
   }
 
+  // Peer-to-peer halo (lbm_b200_p2p_export / _import): the mailbox descriptions travel through files next to the NCCL id file, the
+  // way the reference would MPI_Allgather them.  Every file starts with the run's NCCL id (unique per launch), so a file left behind by
+  // an earlier run is never mistaken for this one's; a rank that cannot take part (velocity halo across a cut) says so in its file and
+  // then ALL ranks stay on NCCL.  LBM_B200_HALO=nccl switches the mailboxes off.
+  void connectPeerToPeer(const char* id) {
+    const char* mode = std::getenv("LBM_B200_HALO");
+    if(mode != nullptr && std::string(mode) == "nccl") return;
+    std::vector<char> mine(128 + 1 + LBM_B200_P2P_BLOB, 0);
+    std::memcpy(mine.data(), id, 128);
+    mine[128] = lbm_b200_p2p_export(m_gpu, mine.data() + 129) == LBM_B200_OK ? 1 : 0;
+    const std::string base = m_rank.id_file + ".p2p.";
+    {
+      const std::string path = base + std::to_string(m_rank.rank), tmp = path + ".tmp";
+      std::ofstream o(tmp, std::ios::binary | std::ios::trunc);
+      o.write(mine.data(), static_cast<std::streamsize>(mine.size()));
+      o.close();
+      if(!o || std::rename(tmp.c_str(), path.c_str()) != 0) TERMM(-1, "cannot write " + path);
+    }
+    std::vector<char> blobs(static_cast<size_t>(m_rank.world) * LBM_B200_P2P_BLOB, 0);
+    bool all_able = true;
+    for(int r = 0; r < m_rank.world; ++r) {
+      const std::string path = base + std::to_string(r);
+      std::vector<char> buf(mine.size());
+      bool got = false;
+      for(int tries = 0; tries < 6000 && !got; ++tries) { // up to 10 minutes
+        std::ifstream i(path, std::ios::binary);
+        if(i && i.read(buf.data(), static_cast<std::streamsize>(buf.size())) && std::memcmp(buf.data(), id, 128) == 0) got = true;
+        else std::this_thread::sleep_for(std::chrono::milliseconds(100));
+      }
+      if(!got) TERMM(-1, "timed out waiting for " + path);
+      all_able = all_able && buf[128] == 1;
+      std::memcpy(blobs.data() + static_cast<size_t>(r) * LBM_B200_P2P_BLOB, buf.data() + 129, LBM_B200_P2P_BLOB);
+    }
+    if(all_able) call(lbm_b200_p2p_import(m_gpu, m_rank.world, blobs.data()));
+    else if(m_rank.rank == 0) std::cerr << "peer-to-peer halo not available for this configuration: NCCL send / receive" << std::endl;
+    // every rank has read every file once it has passed the residual's first all-reduce; rank r removes its own file at exit
+    m_p2pFile = base + std::to_string(m_rank.rank);
+  }
+
   int64_t runPartitioned() {
     std::cerr << "Rank " << m_rank.rank << " of " << m_rank.world << ": partitioned run" << std::endl;
     setupGpuPartitioned(m_rank.local);
@@ -469,6 +519,7 @@ class LBMSolver final : public Runnable {
     exchangeId(id);
     call(lbm_b200_comm_init(m_gpu, id, m_rank.rank, m_rank.world));
     call(lbm_b200_init(m_gpu));
+    connectPeerToPeer(id);
     if(m_rank.rank == 0) std::remove(m_rank.id_file.c_str()); // every rank has joined the communicator by now
     vars.assign(static_cast<size_t>(m_nLocal) * nvar(), 0.0);
     for(m_timeStep = 0; m_timeStep < m_maxTimeStep && !converged; ++m_timeStep) {
@@ -483,6 +534,7 @@ class LBMSolver final : public Runnable {
       std::cerr << "analyticalSolution is not evaluated in a partitioned run (it needs the fields of all ranks)" << std::endl;
     lbm_b200_destroy(m_gpu); // NCCL communicator teardown before the process exits
     m_gpu = nullptr;
+    if(!m_p2pFile.empty()) std::remove(m_p2pFile.c_str());
     std::cout << "LBM Solver finished <||" << std::endl;
     return 0;
   }
@@ -991,6 +1043,7 @@ class LBMSolver final : public Runnable {
   std::string m_configFile, m_model = "D2Q9", m_outputDir = "out/", m_solutionName = "solution";
   int         m_ndim = 2, m_ndist = 9, m_collision = LBM_B200_BGK;
   bool        m_benchmark = false, m_diverged = false;
+  std::string m_p2pFile;
   long long   m_infoInterval = 10, m_convInterval = 10, m_solutionInterval = 100, m_maxTimeStep = 0, m_timeStep = 0;
   double      m_dt = 0, m_poissonRate = 27.79; // Poisson equation: m_dt (solver.cpp:136), poisson_D (solver.cpp:589-599)
   double      m_refLength = 1.0, m_ma = 0.01, m_re = 1, m_nu = 0, m_relaxTime = 0.9, m_omega = 1.0 / 0.9;
