@@ -199,7 +199,7 @@ class LBMSolver final : public Runnable {
     m_model = m_cfg.opt_str("model", "D2Q9");
     m_equation = m_cfg.opt_str("equation", "navierstokes");
     if(m_equation != "navierstokes" && m_equation != "poisson") {
-      if(m_equation == "navierstokespoisson") TERMM(-1, "The Navier-Stokes-Poisson equation type does not run on this host");
+      if(m_equation == "navierstokespoisson") TERMM(-1, "Unsupported equation type"); // like the reference: solverExe.h:43,53,69 (every Navier_Stokes_Poisson case is commented out)
       TERMM(-1, "Invalid equation configuration!"); // constants.h:36-47
     }
     const bool poisson = m_equation == "poisson";

@@ -74,3 +74,18 @@ def test_push_table_invariants_of_periodic_box():
     for i in range(26):
         assert sorted(nb[:, i]) == list(range(n))              # every direction is a permutation
         assert np.array_equal(nb[nb[:, i], opp[i]], np.arange(n))  # and the opposite direction inverts it
+
+
+def test_navierstokespoisson_ends_like_the_reference(tmp_path):
+    """`solver.equation: "navierstokespoisson"` parses (src/lbm/constants.h:43) but every Navier_Stokes_Poisson case of the executor and every
+    instantiation is commented out (solverExe.h:45-47,62-64,80-82; solver_inst_*.cpp), so the reference ends in
+    TERMM(-1, "Unsupported equation type") (solverExe.h:86; confirmed on the reference binary) -- there is no such solver to build."""
+    import json
+    import subprocess
+    from casebuilder import load_golden
+    cfg = json.loads(str(load_golden("couette").golden["config_orig_json"]))
+    cfg["solver"]["equation"] = "navierstokespoisson"
+    (tmp_path / "case.json").write_text(json.dumps(cfg))
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lbm_b200", "lbm")
+    r = subprocess.run([exe, "case.json"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 255 and "Unsupported equation type" in r.stderr
