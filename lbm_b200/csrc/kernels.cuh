@@ -252,7 +252,9 @@ struct Phys {
 
   // collision: BGK is the reference's formula (solver.cpp:603); TRT / MRT are extensions (see oracle/lbm_oracle.c)
   //   TRT: f_i' = f_i - omega+ (f+_i - feq+_i) - omega- (f-_i - feq-_i), symmetric / antisymmetric parts over opposite pairs
-  //   MRT: f' = f - M^-1 S M (f - feq) in the orthogonal moment basis of lattice.h (MrtBasis); p.rates[k] = s_k / |row k|^2;
+  //   MRT: f' = f - M^-1 S M (f - feq) in the orthogonal moment basis of lattice.h (MrtBasis), evaluated as
+  //        f' = f - s0 (f - feq) - sum_k (s_k - s0) / |M_k|^2 M_k^T M_k (f - feq)   with s0 = p.omega the most common rate
+  //        (mrt_base_rate) and p.rates[k] = (s_k - s0) / |row k|^2: rows relaxing at s0 are skipped (a uniform branch);
   //        the conserved rows are never touched, every other row sums to zero and is orthogonal to the momentum rows, so mass
   //        and momentum are conserved to rounding for any set of rates
   // moment K of f - feq: sum over the non-zero entries of row K in ascending direction order (entries are compile-time constants)
@@ -280,9 +282,11 @@ struct Phys {
   template <int K>
   static __device__ __forceinline__ void mrt_row(const DevParams<Real>& p, const Real (&fneq)[Q], Real (&f)[Q]) {
     if constexpr(K < Q) {
-      Real m = 0;
-      mrt_moment<K, 0>(fneq, m, true);
-      mrt_back<K, 0>(A::mul(p.rates[K], m), f);
+      if(p.rates[K] != Real(0)) { // same for every thread: rows relaxing at the base rate are done already
+        Real m = 0;
+        mrt_moment<K, 0>(fneq, m, true);
+        mrt_back<K, 0>(A::mul(p.rates[K], m), f);
+      }
       mrt_row<K + 1>(p, fneq, f);
     }
   }
@@ -310,7 +314,7 @@ struct Phys {
 #pragma unroll
       for(int i = 0; i < Q; ++i) {
         fneq[i] = A::sub(fo[i], fe[i]);
-        f[i]    = fo[i];
+        f[i]    = A::sub(fo[i], A::mul(p.omega, fneq[i]));
       }
       mrt_row<D + 1>(p, fneq, f);
     }
@@ -491,9 +495,9 @@ __global__ void __launch_bounds__(kThreads, LBM_MINBLOCKS) k_step_generic(const 
 }
 
 // ---- chunk path: persistent CTAs, the pulled populations of a tile staged in shared memory ----------------------------------
-// Two CTAs per SM walk TILES (a whole SFC chunk, or -- fp64 -- its lower / upper half along the slowest lexicographic axis)
+// Up to three CTAs per SM walk TILES (a whole SFC chunk, or -- fp64 -- its lower / upper half along the slowest lexicographic axis)
 // handed out by a global ticket counter.  For every tile the (Q-1) moving populations of its cells -- already PULLED, i.e.
-// shifted by c_j -- are copied global -> shared with cp.async, NSTAGE tiles deep, so the loads of the next tiles are in flight
+// shifted by c_j -- are copied global -> shared with cp.async, NSTAGE (2) tiles deep, so the loads of the next tile are in flight
 // while this one is collided.  Thanks to the per-direction in-chunk layouts (lattice.h) every copy is a 16-byte piece of a
 // whole 32-byte sector that lies in exactly one (neighbour) chunk: no partially used DRAM sector, no per-cell index, no
 // template table -- the source of a piece follows from the direction's constants and 3^D neighbour-chunk bases.  Pieces whose
@@ -501,12 +505,9 @@ __global__ void __launch_bounds__(kThreads, LBM_MINBLOCKS) k_step_generic(const 
 // shares the layout); addends / anti-bounce-back are applied when the cell is collided.  Threads then read their cell's Q-1
 // values from shared memory (XOR-swizzled 16-byte units: conflict free), collide, write the result back IN PLACE, and the
 // stage is copied out shared -> global with 128-bit loads / stores.  The rest population never moves: it goes through
-// registers.  Two independent CTAs per SM overlap each other's phases (copy issue / collide / copy out).
+// registers.  Independent CTAs on one SM overlap each other's phases (copy issue / collide / copy out).
 #ifndef LBM_FAST_THREADS
 #define LBM_FAST_THREADS 256
-#endif
-#ifndef LBM_FAST_MINBLOCKS
-#define LBM_FAST_MINBLOCKS 2
 #endif
 constexpr int kFastThreads = LBM_FAST_THREADS;
 
@@ -527,12 +528,21 @@ struct FastCfg {
   static constexpr int TB  = NSPLIT == 2 ? LB - 1 : LB;  // bits of the slowest axis inside a tile
   static constexpr int UPD = TS / EPU;                   // 16-byte units per direction and tile
   static constexpr int STAGE_BYTES = QM * TS * static_cast<int>(sizeof(Real));
+  // Two stages per CTA and as many CTAs per SM as the 228 KB of shared memory hold (up to three): measured on B200 (256^3 D3Q19
+  // fp64), 3 CTAs x 2 stages x 36.9 KB reach 0.97 of the copy bandwidth where 2 CTAs x 3 stages reached 0.87 -- independent CTAs hide
+  // each other's barrier-separated phases better than deeper prefetch does.  The register budget follows (<= 85 at three CTAs; the
+  // compiler fits the D3Q19 kernels into 76-80 without spilling).
 #ifdef LBM_FAST_STAGES
   static constexpr int NSTAGE = LBM_FAST_STAGES;
 #else
-  static constexpr int NSTAGE = (112000 / STAGE_BYTES) >= 4 ? 4 : (112000 / STAGE_BYTES);
+  static constexpr int NSTAGE = 2;
 #endif
   static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES;
+#ifdef LBM_FAST_MINBLOCKS
+  static constexpr int MINB = LBM_FAST_MINBLOCKS;
+#else
+  static constexpr int MINB = (229000 / (SMEM_BYTES + 2048)) >= 3 ? 3 : ((229000 / (SMEM_BYTES + 2048)) >= 1 ? (229000 / (SMEM_BYTES + 2048)) : 1);
+#endif
   static constexpr int RN = NSTAGE + 1;                  // ring of neighbour-base rows
   static constexpr int RT = NSTAGE + 2;                  // ring of tickets
   static constexpr int PAST_END = NSTAGE + 2;            // tickets every CTA draws beyond the last tile
@@ -846,7 +856,7 @@ __device__ __forceinline__ void wall_fixups(const DevParams<Real>& p, const int3
 }
 
 template <class L, class Real, bool STRICT, int COLL>
-__global__ void __launch_bounds__(kFastThreads, LBM_FAST_MINBLOCKS) k_step_fast(const __grid_constant__ DevParams<Real> p) {
+__global__ void __launch_bounds__(kFastThreads, FastCfg<L, Real>::MINB) k_step_fast(const __grid_constant__ DevParams<Real> p) {
   using C = FastCfg<L, Real>;
   constexpr int Q = L::Q, QM = Q - 1, CH = L::CHUNK, TS = C::TS, NSEL = L::NSEL, NSTAGE = C::NSTAGE, NSPLIT = C::NSPLIT;
   __shared__ int32_t  s_nb[C::RN][NSEL + 1];

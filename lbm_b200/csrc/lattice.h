@@ -133,6 +133,20 @@ LBM_MRT_BASIS(Lattice<3 LBM_COMMA 27>, D3Q27, 27)
 #undef LBM_COMMA
 #undef LBM_MRT_BASIS
 
+// MRT base rate: the rate shared by the most non-conserved moments (ties: the one met first in basis order).  The operator is
+// evaluated as  f' = f - s0 (f - feq) - sum_k (s_k - s0) / |M_k|^2 M_k^T M_k (f - feq):  rows whose rate equals s0 cost nothing, so a
+// parametrisation with one common ghost rate needs the projections of the shear and bulk rows only.
+inline double mrt_base_rate(const double* rates, int q, int ndim) {
+  double best = rates[ndim + 1];
+  int    best_n = 0;
+  for(int k = ndim + 1; k < q; ++k) {
+    int n = 0;
+    for(int j = ndim + 1; j < q; ++j) n += rates[j] == rates[k] ? 1 : 0;
+    if(n > best_n) { best_n = n; best = rates[k]; }
+  }
+  return best;
+}
+
 // Runtime view of the same tables for host-side planning code.
 struct LatticeRT {
   int    D = 0, Q = 0, NSEL = 0, CHUNK = 0, CHUNK_LEVELS = 0;

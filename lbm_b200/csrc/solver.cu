@@ -55,7 +55,11 @@ struct SequentialSolver final : SolverBase {
     s.f = d_f.p; s.fold = d_fold.p; s.feq = d_feq.p; s.vars = d_vars.p; s.varsold = d_varsold.p;
     s.pull = d_pull.p; s.nghbr = d_nghbr.p; s.stride = QM; s.n = in.n;
     s.omega = cfg.omega; s.om1 = 1 - cfg.omega; s.omega_minus = cfg.omega_minus;
-    for(int i = 0; i < 27; ++i) s.rates[i] = i < Q ? cfg.mrt_rates[i] / lbm::MrtBasis<L>::norm(i) : 0.0;
+    if(cfg.collision == LBM_B200_MRT) { // base rate + per-moment differences, as Solver::params (solver_fused.cuh)
+      const double s0 = lbm::mrt_base_rate(cfg.mrt_rates, Q, D);
+      s.omega = s0;
+      for(int i = 0; i < 27; ++i) s.rates[i] = (i > D && i < Q) ? (cfg.mrt_rates[i] - s0) / lbm::MrtBasis<L>::norm(i) : 0.0;
+    }
     return s;
   }
   static int blocks(int64_t n) { return static_cast<int>((n + 127) / 128); }

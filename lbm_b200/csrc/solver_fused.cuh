@@ -119,8 +119,12 @@ struct Solver final : SolverBase {
     p.omega = static_cast<Real>(cfg.omega);
     p.om1 = static_cast<Real>(1 - cfg.omega);
     p.omega_minus = static_cast<Real>(cfg.omega_minus);
-    // MRT: rate of moment k divided by the squared norm of its basis row (kernels.cuh: Phys::mrt_row)
-    for(int i = 0; i < 27; ++i) p.rates[i] = i < Q ? static_cast<Real>(cfg.mrt_rates[i] / lbm::MrtBasis<L>::norm(i)) : Real(0);
+    // MRT: base rate s0 in p.omega, (s_k - s0) / |row k|^2 per moment (kernels.cuh: Phys::mrt_row; lattice.h: mrt_base_rate)
+    if(cfg.collision == LBM_B200_MRT) {
+      const double s0 = lbm::mrt_base_rate(cfg.mrt_rates, Q, D);
+      p.omega = static_cast<Real>(s0);
+      for(int i = 0; i < 27; ++i) p.rates[i] = (i > D && i < Q) ? static_cast<Real>((cfg.mrt_rates[i] - s0) / lbm::MrtBasis<L>::norm(i)) : Real(0);
+    }
     p.vars_out = vars_out;
     p.first = first ? 1 : 0;
     if(debug_identity) p.first = 1; // timing experiments only (LBM_B200_DEBUG_IDENTITY): every step reads its own cell, no gather

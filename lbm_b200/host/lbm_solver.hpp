@@ -788,11 +788,17 @@ class LBMSolver final : public Runnable {
 
   // solver.cpp:323-384: the moments of the current fold go to out/<solution_filename>_<step>.vtp in the reference's own binary
   // VTK flavour (vtk_writer.hpp, byte-identical to the reference's file); "output_format": "ascii" is an extension
-  void output(bool forced) {
+  void output(bool forced, const std::string& postfix = "") {
+    // solver.cpp:327-333: once the solution has diverged, the next call writes one forced file with the postfix "bdiv" and nothing else
+    if(m_diverged && !m_wroteDiverged) {
+      m_wroteDiverged = true;
+      output(true, "bdiv");
+      return;
+    }
     if(!((m_timeStep > 0 && m_timeStep % m_solutionInterval == 0) || forced)) return;
     call(lbm_b200_get_moments(m_gpu, vars.data()));
     if(!m_cfg.opt_bool("write_output", true)) return;
-    const std::string stem = m_outputDir + m_solutionName + "_" + std::to_string(m_timeStep);
+    const std::string stem = m_outputDir + m_solutionName + "_" + std::to_string(m_timeStep) + postfix;
     ::mkdir(m_outputDir.c_str(), 0755);
     const std::string format = m_cfg.opt_str("output_format", "binary");
     if(format == "ascii") return writeVtpAscii(stem + ".vtp");
@@ -1042,7 +1048,7 @@ class LBMSolver final : public Runnable {
   std::string m_equation = "navierstokes";
   std::string m_configFile, m_model = "D2Q9", m_outputDir = "out/", m_solutionName = "solution";
   int         m_ndim = 2, m_ndist = 9, m_collision = LBM_B200_BGK;
-  bool        m_benchmark = false, m_diverged = false;
+  bool        m_benchmark = false, m_diverged = false, m_wroteDiverged = false;
   std::string m_p2pFile;
   long long   m_infoInterval = 10, m_convInterval = 10, m_solutionInterval = 100, m_maxTimeStep = 0, m_timeStep = 0;
   double      m_dt = 0, m_poissonRate = 27.79; // Poisson equation: m_dt (solver.cpp:136), poisson_D (solver.cpp:589-599)

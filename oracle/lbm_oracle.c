@@ -676,12 +676,23 @@ static void collide_cell(const Orc* o, int64_t c) {
   } else if(o->model == ORC_MRT) {
     const int (*M)[ORC_MAXQ] = Q == 9 ? mrt_m9 : (Q == 19 ? mrt_m19 : mrt_m27);
     const int* norm          = Q == 9 ? mrt_n9 : (Q == 19 ? mrt_n19 : mrt_n27);
+    /* base rate s0 = the rate most non-conserved moments share (ties: first in basis order); evaluated as
+     * f' = f - s0 (f - feq) - sum_k (s_k - s0)/|M_k|^2 M_k^T M_k (f - feq), rows with s_k == s0 skipped */
+    double s0 = o->mrt_rates[L->ndim + 1];
+    int    best_n = 0;
+    for(int k = L->ndim + 1; k < Q; ++k) {
+      int n = 0;
+      for(int j = L->ndim + 1; j < Q; ++j) n += o->mrt_rates[j] == o->mrt_rates[k] ? 1 : 0;
+      if(n > best_n) { best_n = n; s0 = o->mrt_rates[k]; }
+    }
     double     fneq[ORC_MAXQ];
     for(int i = 0; i < Q; ++i) {
       fneq[i] = fo[i] - fe[i];
-      f[i]    = fo[i];
+      f[i]    = fo[i] - s0 * fneq[i];
     }
     for(int k = L->ndim + 1; k < Q; ++k) { /* rows 0 .. ndim are density and momentum */
+      const double sk = (o->mrt_rates[k] - s0) / (double)norm[k];
+      if(sk == 0) continue;
       double m     = 0;
       int    first = 1;
       for(int i = 0; i < Q; ++i) {
@@ -690,7 +701,7 @@ static void collide_cell(const Orc* o, int64_t c) {
         m              = first ? t : m + t;
         first          = 0;
       }
-      const double d = (o->mrt_rates[k] / (double)norm[k]) * m;
+      const double d = sk * m;
       for(int i = 0; i < Q; ++i)
         if(M[k][i] != 0) f[i] = f[i] - (double)M[k][i] * d;
     }

@@ -10,8 +10,5 @@ $B --arithmetic strict > gpurun_out/r02f_box256_strict.json 2>/dev/null
 $B --workload sphere --size 256 --steps 50 --warmup 10 > gpurun_out/r02f_sphere256.json 2>/dev/null
 $B --workload step --size 256 --steps 50 --warmup 10 > gpurun_out/r02f_step256.json 2>/dev/null
 $B --size 512 --steps 30 --warmup 5 > gpurun_out/r02f_box512.json 2>gpurun_out/r02f_box512.err; tail -2 gpurun_out/r02f_box512.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r02f_launches_default.csv python bench.py --steps 4 --warmup 3 --no-cpu --no-parity --conv-interval 0 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_step_fast -s 6 -c 1 -o gpurun_out/r02f_prof_box256 python bench.py --steps 8 --warmup 3 --no-cpu --no-e2e --no-parity --conv-interval 0 > /dev/null 2>&1
-ncu --set full --clock-control none -k regex:k_step_fast -s 4 -c 1 -o gpurun_out/r02f_prof_sphere256 python bench.py --workload sphere --size 256 --steps 6 --warmup 3 --no-cpu --no-e2e --no-parity --conv-interval 0 > /dev/null 2>&1
-ncu --set full --clock-control none -k regex:k_step_fast -s 4 -c 1 -o gpurun_out/r02f_prof_q27 python bench.py --lattice D3Q27 --steps 6 --warmup 3 --no-cpu --no-e2e --no-parity --conv-interval 0 > /dev/null 2>&1
-ls -la gpurun_out | grep r02f | head -30
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r02f_launches_default.csv python bench.py --steps 4 --warmup 3 --prewarm 0 --no-cpu --no-parity --conv-interval 0 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_step_fast -s 6 -c 1 -o gpurun_out/r02f_prof_box256 python bench.py --steps 8 --warmup 3 --prewarm 0 --no-cpu --no-e2e --no-parity --conv-interval 0 > /dev/null 2>&1

@@ -230,11 +230,17 @@ void kh_set_collision(void* p, int coll, double omega_minus, const double* rates
   auto* c = static_cast<Ctx*>(p);
   c->coll = coll;
   c->omega_minus = omega_minus;
-  // MRT: the kernel takes the rate of moment k divided by the squared norm of its basis row (Solver::params, solver_fused.cuh)
-  for(int i = 0; i < 27; ++i) {
-    double norm = 1;
-    if(i < c->ndist) DISPATCH(c, norm = MrtBasis<L>::norm(i));
-    c->rates[i] = coll == COLL_MRT ? rates[i] / norm : rates[i];
+  // MRT: the kernel takes the base rate in omega and (s_k - s0) / |row k|^2 per moment (Solver::params, solver_fused.cuh)
+  for(int i = 0; i < 27; ++i) c->rates[i] = rates[i];
+  if(coll == COLL_MRT) {
+    const int d = c->ndim, q = c->ndist;
+    const double s0 = mrt_base_rate(rates, q, d);
+    c->omega = s0;
+    for(int i = 0; i < 27; ++i) {
+      double norm = 1;
+      if(i < q) DISPATCH(c, norm = MrtBasis<L>::norm(i));
+      c->rates[i] = (i > d && i < q) ? (rates[i] - s0) / norm : 0.0;
+    }
   }
 }
 // the same step through the real kernel (generic blocks + persistent chunk CTAs)
