@@ -302,14 +302,19 @@ def mrt_kinds(lattice):
 def collision_setup(name, lattice):
     """(C ABI collision id, omega_minus, MRT rates) of a workload's collision operator.  TRT: odd-moment rate from the 'magic' parameter
     3/16.  MRT (moment space): shear moments relax with omega (same viscosity as the BGK / TRT runs), the bulk moment
-    with 1.19, the ghost moments with the d'Humieres et al. (2002) values 1.2 / 1.4 / 1.98 in turn -- all conserved moments untouched."""
+    with 1.19, every ghost moment with 1.2 -- a common three-rate parametrisation; the kernel then projects the six shear / bulk rows only
+    (rows at the most common rate are skipped), all conserved moments untouched.  LBM_BENCH_MRT_GHOSTS=cycle gives every third ghost
+    moment 1.2 / 1.4 / 1.98 instead (d'Humieres et al. 2002): 17 of 23 rows projected."""
     from lbm_b200.cases import trt_omega_minus
     om_minus = trt_omega_minus(OMEGA)
     kinds = mrt_kinds(lattice)
     rates = np.full(27, OMEGA)
     rates[:len(kinds)][kinds == 2] = 1.19
     ghost = np.nonzero(kinds == 3)[0]
-    rates[ghost] = np.array([1.2, 1.4, 1.98])[np.arange(len(ghost)) % 3]
+    if os.environ.get("LBM_BENCH_MRT_GHOSTS") == "cycle":
+        rates[ghost] = np.array([1.2, 1.4, 1.98])[np.arange(len(ghost)) % 3]
+    else:
+        rates[ghost] = 1.2
     return {"bgk": 0, "trt": 1, "mrt": 2}[name], om_minus, rates
 
 
@@ -433,7 +438,8 @@ def config_dict(args, note):
                           "sphere; BASELINE.json configs[3], 3D form of test/sphere/sphere_ns.json)",
                 "step": "channel with a step (block on the upper wall, pressure in-/outlet, bounce-back walls; BASELINE.json configs[4], "
                         "3D form of test/step/step_ns.json)"}[args.workload]
-        return {"workload": f"{args.workload}-3D {args.size}^3 {args.lattice} {args.collision.upper()} {getattr(args, 'precision', 'fp64')}: {what}, omega={OMEGA:.6f}",
+        coll_note = " (MRT rates: shear omega, bulk 1.19, ghost moments " + ("1.2/1.4/1.98 in turn" if os.environ.get("LBM_BENCH_MRT_GHOSTS") == "cycle" else "1.2") + ")" if args.collision == "mrt" else ""
+        return {"workload": f"{args.workload}-3D {args.size}^3 {args.lattice} {args.collision.upper()} {getattr(args, 'precision', 'fp64')}: {what}, omega={OMEGA:.6f}{coll_note}",
                 "lattice": args.lattice, "collision": args.collision, "arithmetic": args.arithmetic,
                 "l2_policy": "inputs larger than L2 (no flush needed)" if args.size >= 128 else "SMALL CASE: fits L2, not a bandwidth measurement",
                 "parallelism": (f"one cube of {args.size}^3 cells cut into {args.gpus} contiguous SFC ranges (fixed total size), "

@@ -511,6 +511,17 @@ __global__ void __launch_bounds__(kThreads, LBM_MINBLOCKS) k_step_generic(const 
 #endif
 constexpr int kFastThreads = LBM_FAST_THREADS;
 
+template <class L>
+__device__ __forceinline__ constexpr int count_unaligned_dirs() {
+  int n = 0;
+  for(int j = 0; j < L::Q - 1; ++j) {
+    const int lay = layout_of<L>(j);
+    const int ax0 = lay == 0 ? 0 : (lay == 1 ? 1 : 2);
+    n += L::c(j, ax0 < L::D ? ax0 : 0) != 0 ? 1 : 0;
+  }
+  return n;
+}
+
 template <class L, class Real>
 struct FastCfg {
   static constexpr int D = L::D, Q = L::Q, QM = L::Q - 1, CH = L::CHUNK, NSEL = L::NSEL;
@@ -527,7 +538,15 @@ struct FastCfg {
   static constexpr int TS  = CH / NSPLIT;                // cells per tile
   static constexpr int TB  = NSPLIT == 2 ? LB - 1 : LB;  // bits of the slowest axis inside a tile
   static constexpr int UPD = TS / EPU;                   // 16-byte units per direction and tile
-  static constexpr int STAGE_BYTES = QM * TS * static_cast<int>(sizeof(Real));
+  // directions that move along the fastest axis of their own layout (D3Q27 corners; 2D: c_x != 0) are staged UNSHIFTED along that
+  // axis -- whole aligned rows like every other direction -- plus one extra column per direction with the element that comes from
+  // the neighbour chunk in that axis; the shift happens when the cell reads its slot
+  static constexpr int NU   = count_unaligned_dirs<L>();
+  static constexpr int ROWS = TS / S;                    // rows (along the fastest lexicographic axis) per tile
+  static constexpr int XCOL = NU * ROWS;                 // reals of all extra columns
+  static constexpr int STAGE_ELEMS = QM * TS + XCOL;
+  static constexpr int STAGE_BYTES = STAGE_ELEMS * static_cast<int>(sizeof(Real));
+  static_assert(STAGE_BYTES % 16 == 0, "stages must keep 16-byte alignment");
   // Two stages per CTA and as many CTAs per SM as the 228 KB of shared memory hold (up to three): measured on B200 (256^3 D3Q19
   // fp64), 3 CTAs x 2 stages x 36.9 KB reach 0.97 of the copy bandwidth where 2 CTAs x 3 stages reached 0.87 -- independent CTAs hide
   // each other's barrier-separated phases better than deeper prefetch does.  The register budget follows (<= 85 at three CTAs; the
@@ -593,6 +612,13 @@ template <class L>
 __device__ __forceinline__ constexpr int count_aligned() {
   int n = 0;
   for(int j = 0; j < L::Q - 1; ++j) n += dir_aligned<L>(j) ? 1 : 0;
+  return n;
+}
+// position of an unaligned direction among the unaligned ones
+template <class L>
+__device__ __forceinline__ constexpr int unaligned_index(int j) {
+  int n = 0;
+  for(int i = 0; i < j; ++i) n += dir_aligned<L>(i) ? 0 : 1;
   return n;
 }
 // k-th aligned (unaligned) direction
@@ -681,7 +707,7 @@ alignas(128) static unsigned char lbm_dyn_smem[232448]; // CPU harness: one bloc
 // element in direction J's layout, h = which half of the chunk the tile is.
 template <class L, class Real, int J, bool ALIGNED, bool WALLS>
 __device__ __forceinline__ void issue_unit(const DevParams<Real>& p, const Real* __restrict__ Abuf, Real* __restrict__ stg,
-                                           const int32_t* __restrict__ nb, int32_t base, int tp, int h) {
+                                           const int32_t* __restrict__ nb, int32_t base, int tp, int h, Real* dst_override = nullptr) {
   using C = FastCfg<L, Real>;
   constexpr int lay  = layout_of<L>(J);
   constexpr int AX0  = lay == 0 ? 0 : (lay == 1 ? 1 : 2), AX1 = lay == 0 ? 1 : (lay == 1 ? 2 : 0), AX2 = lay == 0 ? 2 : (lay == 1 ? 0 : 1);
@@ -715,7 +741,7 @@ __device__ __forceinline__ void issue_unit(const DevParams<Real>& p, const Real*
     // wall: the bounce-back source, i.e. the same position in the opposite direction's array (bnd_dirichlet.h:92)
     if(nbv < 0) off = static_cast<uint32_t>(L::opp(J)) * static_cast<uint32_t>(p.stride) + static_cast<uint32_t>(base + pos0);
   }
-  Real* dst = stg + J * C::TS + stage_swizzle<L, Real>(lay, tp);
+  Real* dst = dst_override != nullptr ? dst_override : stg + J * C::TS + stage_swizzle<L, Real>(lay, tp);
   if constexpr(ALIGNED) cp_async_16(dst, Abuf + off);
   else cp_async_small<static_cast<int>(sizeof(Real))>(dst, Abuf + off);
 }
@@ -723,29 +749,39 @@ __device__ __forceinline__ void issue_unit(const DevParams<Real>& p, const Real*
 // Work distribution: the kFastThreads threads form NG = kFastThreads / UNITS groups (UNITS = units per direction and tile);
 // group g serves the directions LI = g, g + NG, ... of the list, every thread one unit per direction -- the same unit for all of
 // them, so the decode of the unit index is shared.  With fewer threads than units a thread loops over its units instead.
-template <class L, class Real, bool ALIGNED, bool WALLS, int LI, int STEP>
+// DIRS: 0 = the aligned directions, 1 = the rows of the unaligned ones (copied like aligned rows: the shift along the fastest axis
+// is left to the reader), 2 = their extra columns (one real per row: the element that comes from the neighbour in that axis)
+template <class L, class Real, int DIRS, bool WALLS, int LI, int STEP>
 __device__ __forceinline__ void issue_dirs(const DevParams<Real>& p, const Real* __restrict__ Abuf, Real* __restrict__ stg,
                                            const int32_t* __restrict__ nb, int32_t base, int h, int unit_first, int unit_step) {
   using C = FastCfg<L, Real>;
-  constexpr int N = ALIGNED ? count_aligned<L>() : C::QM - count_aligned<L>();
-  constexpr int UNITS = ALIGNED ? C::UPD : C::TS, EPU = ALIGNED ? C::EPU : 1;
+  constexpr int N = DIRS == 0 ? count_aligned<L>() : C::NU;
+  constexpr int UNITS = DIRS == 2 ? C::ROWS : C::UPD;
   if constexpr(LI < N) {
-    constexpr int J = nth_dir<L>(LI, ALIGNED);
-    for(int u = unit_first; u < UNITS; u += unit_step) issue_unit<L, Real, J, ALIGNED, WALLS>(p, Abuf, stg, nb, base, u * EPU, h);
-    issue_dirs<L, Real, ALIGNED, WALLS, LI + STEP, STEP>(p, Abuf, stg, nb, base, h, unit_first, unit_step);
+    constexpr int J = nth_dir<L>(LI, DIRS == 0);
+    for(int u = unit_first; u < UNITS; u += unit_step) {
+      if constexpr(DIRS == 2) {
+        // row u of the tile: the cell at the end the direction comes from takes its value from the neighbour along the fastest axis
+        constexpr int a_edge = L::c(J, 0) > 0 ? 0 : C::S - 1;
+        issue_unit<L, Real, J, false, WALLS>(p, Abuf, stg, nb, base, u * C::S + a_edge, h, stg + C::QM * C::TS + LI * C::ROWS + u);
+      } else {
+        issue_unit<L, Real, J, true, WALLS>(p, Abuf, stg, nb, base, u * C::EPU, h);
+      }
+    }
+    issue_dirs<L, Real, DIRS, WALLS, LI + STEP, STEP>(p, Abuf, stg, nb, base, h, unit_first, unit_step);
   }
 }
-template <class L, class Real, bool ALIGNED, bool WALLS, int G>
+template <class L, class Real, int DIRS, bool WALLS, int G>
 __device__ __forceinline__ void issue_groups(const DevParams<Real>& p, const Real* __restrict__ Abuf, Real* __restrict__ stg,
                                              const int32_t* __restrict__ nb, int32_t base, int h, int tid) {
   using C = FastCfg<L, Real>;
-  constexpr int UNITS = ALIGNED ? C::UPD : C::TS;
+  constexpr int UNITS = DIRS == 2 ? C::ROWS : C::UPD;
   constexpr int NG = kFastThreads >= UNITS ? kFastThreads / UNITS : 1;
   static_assert(kFastThreads >= UNITS ? kFastThreads % UNITS == 0 : UNITS % kFastThreads == 0, "thread count vs units per direction");
   if constexpr(G < NG) {
     if(NG == 1 || tid / UNITS == G)
-      issue_dirs<L, Real, ALIGNED, WALLS, G, NG>(p, Abuf, stg, nb, base, h, NG == 1 ? tid : tid % UNITS, NG == 1 ? kFastThreads : UNITS);
-    issue_groups<L, Real, ALIGNED, WALLS, G + 1>(p, Abuf, stg, nb, base, h, tid);
+      issue_dirs<L, Real, DIRS, WALLS, G, NG>(p, Abuf, stg, nb, base, h, NG == 1 ? tid : tid % UNITS, NG == 1 ? kFastThreads : UNITS);
+    issue_groups<L, Real, DIRS, WALLS, G + 1>(p, Abuf, stg, nb, base, h, tid);
   }
 }
 
@@ -764,11 +800,17 @@ __device__ __forceinline__ void issue_tile_loads(const DevParams<Real>& p, const
     return;
   }
   if(nb[C::NSEL] < 0) { // interior chunk
-    issue_groups<L, Real, true, false, 0>(p, Abuf, stg, nb, base, h, tid);
-    issue_groups<L, Real, false, false, 0>(p, Abuf, stg, nb, base, h, tid);
+    issue_groups<L, Real, 0, false, 0>(p, Abuf, stg, nb, base, h, tid);
+    if constexpr(C::NU > 0) {
+      issue_groups<L, Real, 1, false, 0>(p, Abuf, stg, nb, base, h, tid);
+      issue_groups<L, Real, 2, false, 0>(p, Abuf, stg, nb, base, h, tid);
+    }
   } else {
-    issue_groups<L, Real, true, true, 0>(p, Abuf, stg, nb, base, h, tid);
-    issue_groups<L, Real, false, true, 0>(p, Abuf, stg, nb, base, h, tid);
+    issue_groups<L, Real, 0, true, 0>(p, Abuf, stg, nb, base, h, tid);
+    if constexpr(C::NU > 0) {
+      issue_groups<L, Real, 1, true, 0>(p, Abuf, stg, nb, base, h, tid);
+      issue_groups<L, Real, 2, true, 0>(p, Abuf, stg, nb, base, h, tid);
+    }
   }
 }
 
@@ -819,6 +861,44 @@ __device__ __forceinline__ void copy_out_groups(const DevParams<Real>& p, const 
   if constexpr(G < NG) {
     if(NG == 1 || tid / C::UPD == G) copy_out_dirs<L, Real, G, NG>(p, stg, base, h, NG == 1 ? tid : tid % C::UPD, NG == 1 ? kFastThreads : C::UPD, up);
     copy_out_groups<L, Real, G + 1>(p, stg, base, h, tid, up);
+  }
+}
+
+// read the staged values of one cell.  Aligned directions: the cell's own slot.  Unaligned directions (rows staged unshifted along
+// the fastest axis): the slot one step against the direction -- or the extra column at the row's end, or, when the row's source chunk
+// is a wall and the row therefore holds the bounce-back sources, the cell's own slot.
+template <class L, class Real, int J>
+__device__ __forceinline__ void read_stage(const Real* __restrict__ stg, const int32_t* __restrict__ nb, bool walls, bool first, int ot, int o,
+                                           const int (&pos)[3], Real (&fold)[L::Q]) {
+  using C = FastCfg<L, Real>;
+  if constexpr(J < L::Q - 1) {
+    constexpr int lay = layout_of<L>(J);
+    if constexpr(dir_aligned<L>(J)) {
+      fold[J] = stg[J * C::TS + pos[lay]];
+    } else {
+      constexpr int sa = L::c(J, 0), a_edge = sa > 0 ? 0 : C::S - 1, LI = unaligned_index<L>(J);
+      const int a = ot & (C::S - 1);
+      if(first) {
+        fold[J] = stg[J * C::TS + pos[0]];
+      } else if(a == a_edge) {
+        fold[J] = stg[C::QM * C::TS + LI * C::ROWS + (ot >> C::LB)];
+      } else {
+        bool wallrow = false;
+        if(walls) { // selector of the row's source chunk: the shifts along the other axes only
+          int sel = C::SELF, w3 = 3;
+#pragma unroll
+          for(int d = 1; d < L::D; ++d) {
+            const int x = (o >> (d * C::LB)) & (C::S - 1);
+            if(L::c(J, d) > 0 && x == 0) sel -= w3;
+            if(L::c(J, d) < 0 && x == C::S - 1) sel += w3;
+            w3 *= 3;
+          }
+          wallrow = nb[sel] < 0;
+        }
+        fold[J] = stg[J * C::TS + stage_swizzle<L, Real>(0, wallrow ? ot : ot - sa)];
+      }
+    }
+    read_stage<L, Real, J + 1>(stg, nb, walls, first, ot, o, pos, fold);
   }
 }
 
@@ -894,7 +974,7 @@ __global__ void __launch_bounds__(kFastThreads, FastCfg<L, Real>::MINB) k_step_f
   for(int k = 0; k < NSTAGE - 1; ++k) {
     const int32_t tk = s_tk[k];
     if(tk < n_tiles)
-      issue_tile_loads<L, Real>(p, Abuf, stages + static_cast<size_t>(k) * (QM * TS), s_nb[k], (p.chunk_off + tk / NSPLIT) * CH, tk % NSPLIT, s_dir, tid);
+      issue_tile_loads<L, Real>(p, Abuf, stages + static_cast<size_t>(k) * C::STAGE_ELEMS, s_nb[k], (p.chunk_off + tk / NSPLIT) * CH, tk % NSPLIT, s_dir, tid);
     cp_async_commit();
   }
 
@@ -905,7 +985,7 @@ __global__ void __launch_bounds__(kFastThreads, FastCfg<L, Real>::MINB) k_step_f
     const int      chunk = p.chunk_off + ticket / NSPLIT;
     const int      h     = ticket % NSPLIT;
     const int32_t  base  = chunk * CH;
-    Real* const    stg   = stages + static_cast<size_t>(i % NSTAGE) * (QM * TS);
+    Real* const    stg   = stages + static_cast<size_t>(i % NSTAGE) * C::STAGE_ELEMS;
     const int32_t* nb    = s_nb[i % C::RN];
     // the rest population does not move: straight through registers
     Real frest[C::CPT];
@@ -933,12 +1013,30 @@ __global__ void __launch_bounds__(kFastThreads, FastCfg<L, Real>::MINB) k_step_f
       // tile i + NSTAGE - 1 goes into the stage the previous iteration has just copied out
       const int32_t tk = s_tk[(i + NSTAGE - 1) % C::RT];
       if(tk < n_tiles)
-        issue_tile_loads<L, Real>(p, Abuf, stages + static_cast<size_t>((i + NSTAGE - 1) % NSTAGE) * (QM * TS), s_nb[(i + NSTAGE - 1) % C::RN],
+        issue_tile_loads<L, Real>(p, Abuf, stages + static_cast<size_t>((i + NSTAGE - 1) % NSTAGE) * C::STAGE_ELEMS, s_nb[(i + NSTAGE - 1) % C::RN],
                                   (p.chunk_off + tk / NSPLIT) * CH, tk % NSPLIT, s_dir, tid);
       cp_async_commit();
     }
     const int32_t wid = nb[NSEL]; // wall descriptor of this chunk, -1: interior chunk
     const AddEntryT<Real>* wall = p.wall_desc + static_cast<size_t>(wid < 0 ? 0 : wid) * QM * NSEL;
+    // With unaligned directions a cell reads slots that a neighbour writes its result to: all cells of the tile read first (the
+    // values wait in registers), one more barrier, then they collide and write.  Without them every cell owns its slots.
+    Real folds[C::NU > 0 ? C::CPT : 1][Q];
+    if constexpr(C::NU > 0) {
+#pragma unroll
+      for(int k = 0; k < C::CPT; ++k) {
+        const int v = tid + k * kFastThreads;
+        if(v < TS) {
+          const int ot = thread_cell<L>(v), o = ot + h * TS;
+          int pos[3];
+          pos[0] = stage_swizzle<L, Real>(0, ot);
+          pos[1] = L::D == 3 ? stage_swizzle<L, Real>(1, tile_perm<L, Real>(1, ot)) : ot;
+          pos[2] = L::D == 3 ? stage_swizzle<L, Real>(2, tile_perm<L, Real>(2, ot)) : ot;
+          read_stage<L, Real, 0>(stg, nb, wid >= 0, p.first != 0, ot, o, pos, folds[k]);
+        }
+      }
+      __syncthreads();
+    }
 #pragma unroll
     for(int k = 0; k < C::CPT; ++k) {
       const int v = tid + k * kFastThreads;
@@ -950,8 +1048,13 @@ __global__ void __launch_bounds__(kFastThreads, FastCfg<L, Real>::MINB) k_step_f
         pos[1] = L::D == 3 ? stage_swizzle<L, Real>(1, tile_perm<L, Real>(1, ot)) : ot;
         pos[2] = L::D == 3 ? stage_swizzle<L, Real>(2, tile_perm<L, Real>(2, ot)) : ot;
         Real fold[Q], f[Q], rho, u[L::D];
+        if constexpr(C::NU > 0) {
 #pragma unroll
-        for(int j = 0; j < QM; ++j) fold[j] = stg[j * TS + pos[layout_of<L>(j)]];
+          for(int j = 0; j < QM; ++j) fold[j] = folds[k][j];
+        } else {
+#pragma unroll
+          for(int j = 0; j < QM; ++j) fold[j] = stg[j * TS + pos[layout_of<L>(j)]];
+        }
         fold[QM] = frest[k];
         if(wid >= 0 && !p.first) {
           int edge[3][2] = {{0, 0}, {0, 0}, {0, 0}};
