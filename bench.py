@@ -538,7 +538,7 @@ def run_ours(args):
     s.init()
     if world > 1 and args.halo == "p2p" and not s.p2p_connect(dist, wl["lp"]):
         args.halo = "nccl"   # some rank cannot use the mailboxes (velocity halo of a pressure boundary across a cut)
-    nghbr_keep = wl["nghbr"] if args.conv_interval > 0 else None   # the residual-mode run below sets up a second solver
+    nghbr_keep = wl["nghbr"] if (args.conv_interval > 0 or not args.no_strict) else None   # the residual-mode / STRICT runs below set up more solvers
     del wl["nghbr"]
     t_setup = time.perf_counter() - t_setup
     st0 = s.stats()
@@ -603,6 +603,21 @@ def run_ours(args):
         with_residual = {"value": n_global * args.steps / (float(t[0]) * 1e-3) / 1e6, "unit": "MLUPS", "conv_interval": args.conv_interval,
                          "residual": None if res is None else [float(x) for x in res[0]], "diverged": None if res is None else bool(res[1])}
 
+    # ---- the same steps in STRICT arithmetic (the ABI's default: bit-identical to the reference's CPU solver in fp64)
+    strict = None
+    if args.arithmetic == "fast" and not args.no_strict and world == 1 and nghbr_keep is not None and n <= 40_000_000:  # a second solver must fit
+        s2 = lbm_b200.Solver(ndim, ndist, nghbr_keep, OMEGA, arithmetic=lbm_b200.STRICT, device=local, track_vars=0, stream=stream,
+                             collision=coll, omega_minus=om_minus, mrt_rates=rates, precision=precision)
+        apply_bcs(s2, wl)
+        s2.init()
+        s2.step(args.prewarm + args.warmup)
+        barrier()
+        ms_s, ms_sm = s2.step_timed(args.steps)
+        s2.close()
+        strict = {"value": n_global * args.steps / (ms_s * 1e-3) / 1e6, "unit": "MLUPS", "ms_per_launch": ms_sm / args.steps,
+                  "frac": st0["bytes_per_cell_alg"] * n * args.steps / (ms_sm * 1e-3) / 1e9 / measured_peak()[0],
+                  "note": "same workload, LBM_B200_STRICT: the reference's operation order, never contracted, divisions kept (by constants: "
+                          "correctly rounded through two fused multiply-adds) -- bit-identical to the reference in fp64"}
     clocks = sampler.stop() if sampler else None   # NVML queries contend with the driver: none while the host-side e2e path is timed
 
     # ---- e2e: state in pinned host buffers, through the C ABI: upload m_fold (the input of a time step; m_f is overwritten by the
@@ -666,7 +681,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f64", "data": "synthetic",
         "config": config_dict(args, f"{st0['cells_fast']} of {st0['ncells']} cells on the index-free chunk path; setup {t_setup:.1f} s"),
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "with_residual": with_residual, "parity": parity, "prewarm_steps": args.prewarm,
+        "with_residual": with_residual, "strict": strict, "parity": parity, "prewarm_steps": args.prewarm,
     }
     emit(line)
 
@@ -693,6 +708,7 @@ def main():
     ap.add_argument("--conv-interval", type=int, default=10, dest="conv_interval",
                     help="second measurement with the reference's residual bookkeeping every N steps inside the timed region (0: skip)")
     ap.add_argument("--no-parity", action="store_true", dest="no_parity")
+    ap.add_argument("--no-strict", action="store_true", dest="no_strict", help="skip the extra measurement in STRICT arithmetic")
     ap.add_argument("--prewarm", type=int, default=40, help="extra untimed steps before the W warm-up steps (device steady state)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU halo exchange: p2p = CUDA IPC mailboxes + copy engines + flag words, one launch per step (default); "

@@ -105,6 +105,14 @@ struct Ar<double, true> {
   static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
   static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
   static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+  // a / d for a CONSTANT divisor d with y = RN(1 / d): q0 = RN(a y), r = a - q0 d (exact in one fused operation), RN(q0 + r y) -- the
+  // final step of the classical fused-multiply-add division, correctly rounded for every a whose quotient neither overflows nor is
+  // subnormal (Markstein 1990).  Bit-identical to __ddiv_rn at a quarter of its cost; the divisors here are cs^2 and two multiples.
+  static __device__ __forceinline__ double div_const(double a, double d, double y) {
+    const double q0 = __dmul_rn(a, y);
+    const double r  = __fma_rn(-q0, d, a);
+    return __fma_rn(r, y, q0);
+  }
 };
 template <>
 struct Ar<float, true> {
@@ -112,6 +120,11 @@ struct Ar<float, true> {
   static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
   static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
   static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+  static __device__ __forceinline__ float div_const(float a, float d, float y) {
+    const float q0 = __fmul_rn(a, y);
+    const float r  = __fmaf_rn(-q0, d, a);
+    return __fmaf_rn(r, y, q0);
+  }
 };
 template <class Real>
 struct Ar<Real, false> {
@@ -119,6 +132,7 @@ struct Ar<Real, false> {
   static __device__ __forceinline__ Real sub(Real a, Real b) { return a - b; }
   static __device__ __forceinline__ Real mul(Real a, Real b) { return a * b; }
   static __device__ __forceinline__ Real div(Real a, Real b) { return a / b; }
+  static __device__ __forceinline__ Real div_const(Real a, Real d, Real) { return a / d; }
 };
 
 // c * x for c in {-1,0,1} is exact; adding an exact zero never changes a sum, so zero terms are skipped.
@@ -131,6 +145,10 @@ struct Phys {
   static __device__ __forceinline__ Real cssq() { return static_cast<Real>(1.0 / 3.0); }
   static __device__ __forceinline__ Real c2() { return static_cast<Real>(2.0 * (1.0 / 3.0) * (1.0 / 3.0)); }
   static __device__ __forceinline__ Real c3() { return static_cast<Real>(2.0 * (1.0 / 3.0)); }
+  // correctly rounded reciprocals of the three constant divisors, in the arithmetic type (Ar::div_const)
+  static __device__ __forceinline__ Real r_cssq() { return Real(1) / static_cast<Real>(1.0 / 3.0); }
+  static __device__ __forceinline__ Real r_c2() { return Real(1) / static_cast<Real>(2.0 * (1.0 / 3.0) * (1.0 / 3.0)); }
+  static __device__ __forceinline__ Real r_c3() { return Real(1) / static_cast<Real>(2.0 * (1.0 / 3.0)); }
 
   // solver.cpp:527-535: rho = sum ascending from 0.0; u_d = (sum_{i<Q-1} c_id f_i) / rho
   static __device__ __forceinline__ void moments(const Real (&f)[Q], Real& rho, Real (&u)[D]) {
@@ -183,7 +201,7 @@ struct Phys {
   // equilibrium_func.h:52-54: w*rho*(1.0 + cu/cssq + cu*cu/(2.0*cssq*cssq) - vsq/(2.0*cssq))
   static __device__ __forceinline__ Real eq_one(Real w, Real rho, Real cuv, Real vs) {
     if constexpr(STRICT) {
-      const Real t = A::sub(A::add(A::add(Real(1), A::div(cuv, cssq())), A::div(A::mul(cuv, cuv), c2())), A::div(vs, c3()));
+      const Real t = A::sub(A::add(A::add(Real(1), A::div_const(cuv, cssq(), r_cssq())), A::div_const(A::mul(cuv, cuv), c2(), r_c2())), A::div_const(vs, c3(), r_c3()));
       return A::mul(A::mul(w, rho), t);
     } else {
       return w * rho * (Real(1) + Real(3) * cuv + Real(4.5) * cuv * cuv - Real(1.5) * vs);
@@ -192,7 +210,7 @@ struct Phys {
   // equilibrium_func.h:109-111
   static __device__ __forceinline__ Real symm_eq_one(Real w, Real rho, Real cuv, Real vs) {
     if constexpr(STRICT) {
-      const Real t = A::sub(A::add(Real(1), A::div(A::mul(cuv, cuv), c2())), A::div(vs, c3()));
+      const Real t = A::sub(A::add(Real(1), A::div_const(A::mul(cuv, cuv), c2(), r_c2())), A::div_const(vs, c3(), r_c3()));
       return A::mul(A::mul(w, rho), t);
     } else {
       return w * rho * (Real(1) + Real(4.5) * cuv * cuv - Real(1.5) * vs);
@@ -204,7 +222,7 @@ struct Phys {
   static __device__ __forceinline__ void equilibrium(Real rho, const Real (&u)[D], Real (&feq)[Q]) {
     const Real vs = vsq(u);
     if constexpr(STRICT) {
-      const Real vterm = A::div(vs, c3());
+      const Real vterm = A::div_const(vs, c3(), r_c3());
       static_for_eq<0>(rho, u, vterm, feq);
     } else {
       const Real base = Real(1) - Real(1.5) * vs;
@@ -222,8 +240,8 @@ struct Phys {
           feq[I] = A::mul(wr, A::sub(Real(1), vterm));
         } else {
           const Real cuv = cu<I>(u);
-          const Real a   = A::div(cuv, cssq());
-          const Real b   = A::div(A::mul(cuv, cuv), c2());
+          const Real a   = A::div_const(cuv, cssq(), r_cssq());
+          const Real b   = A::div_const(A::mul(cuv, cuv), c2(), r_c2());
           feq[I]         = A::mul(wr, A::sub(A::add(A::add(Real(1), a), b), vterm));
           feq[J]         = A::mul(wr, A::sub(A::add(A::add(Real(1), -a), b), vterm));
         }

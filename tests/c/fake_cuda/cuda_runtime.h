@@ -39,6 +39,8 @@ template <class T> static inline void __stcg(T* p, T v) { *p = v; }
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int) { return v; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 
+static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
