@@ -260,6 +260,20 @@ void kh_halo_unpack(void* p, const int64_t* index, int64_t n, const double* in) 
   auto* c = static_cast<Ctx*>(p);
   launch(n, 256, [&] { k_halo_unpack<double>(c->B.data(), index, n, in); });
 }
+// Ar<double, true>::div_const against true division, for the three constant divisors of the equilibrium (cs^2, 2 cs^4, 2 cs^2): the number
+// of operands whose results differ (must be 0: the scheme is correctly rounded; the sign of a zero quotient is the one exception)
+int64_t kh_check_div_const(const double* a, int64_t n) {
+  const double d[3] = {1.0 / 3.0, 2.0 * (1.0 / 3.0) * (1.0 / 3.0), 2.0 * (1.0 / 3.0)};
+  int64_t bad = 0;
+  for(int k = 0; k < 3; ++k) {
+    const double y = 1.0 / d[k];
+    for(int64_t i = 0; i < n; ++i) {
+      const double q = Ar<double, true>::div_const(a[i], d[k], y), t = a[i] / d[k];
+      bad += q != t ? 1 : 0; // numeric comparison: a = -0 gives +0 where IEEE gives -0; the quotient only ever enters a sum with 1
+    }
+  }
+  return bad;
+}
 // end of a step: B becomes A, the dynamic buffers written for the next step become current (Solver::one_step)
 void kh_swap(void* p, int dyn_written) {
   auto* c = static_cast<Ctx*>(p);

@@ -51,6 +51,8 @@ def kh(tmp_path_factory):
     L.kh_halo_pack.argtypes = [vp, vp, C.c_int64, vp]
     L.kh_halo_unpack.argtypes = [vp, vp, C.c_int64, vp]
     L.kh_swap.argtypes = [vp, C.c_int]
+    L.kh_check_div_const.restype = C.c_int64
+    L.kh_check_div_const.argtypes = [vp, C.c_int64]
     return L
 
 
@@ -212,3 +214,13 @@ def test_outer_and_inner_launch_of_the_overlapped_path(world, shape, ndist, peri
     spec, _ = box_spec(shape, ndist, (True, False, False), ("+z", (0.05, 0.0, 0.0)))
     stats = emulate(kh, spec, world, 3, oracle_mod, kernel="split")
     assert stats["fast"] > 0 and stats["ghost_blocks"] > 0
+
+
+def test_division_by_the_lattice_constants_is_correctly_rounded(kh):
+    """STRICT arithmetic divides by cs^2, 2 cs^4 and 2 cs^2 like the reference (equilibrium_func.h:53), but through two fused multiply-adds
+    (Ar::div_const).  The result must equal true IEEE division bit for bit: 3 x 3 M operands over 30 decades, both signs, plus edge values."""
+    rng = np.random.default_rng(11)
+    a = np.concatenate([rng.standard_normal(1_500_000) * 10.0 ** rng.uniform(-25, 5, 1_500_000), rng.random(1_500_000) * 0.2,
+                        np.array([0.0, -0.0, 1.0, 3.0, 1.0 / 3.0, 2.0 / 9.0, 2.0 / 3.0, 1e-200, -1e-200, 1e200])])
+    a = np.ascontiguousarray(a)
+    assert kh.kh_check_div_const(a.ctypes.data, len(a)) == 0
