@@ -663,7 +663,7 @@ def run_ours(args):
     achieved = b_alg * n * args.steps / (ms_main * 1e-3) / 1e9
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": ncu_traffic(args.lattice, args.size) if args.workload == "box" else None, "peak_source": peak_src,
-            "kernel": f"lbm::k_step (fused pull-stream + BC + moments + {args.collision.upper()} collide)",
+            "kernel": f"lbm::k_step_fast (persistent tile pipeline: cp.async pull -> shared memory -> BC + moments + {args.collision.upper()} collide in place -> 128-bit copy-out)",
             "bytes_per_cell_alg": b_alg, "cells_per_launch": n, "ms_per_launch": ms_main / args.steps}
     cpu = None
     if world == 1 and not args.no_cpu:

@@ -2,7 +2,7 @@
 //
 // g++ compiles the unmodified kernels.cuh against tests/c/fake_cuda/cuda_runtime.h.  A driver loop walks the thread indices of the
 // kernels that need no barrier: k_gather_all (the gather of the fused kernel: link codes, chunk templates, wall descriptors,
-// pressure-face chunks, ghost blocks), the per-cell update (gather_any + update_and_store: what k_step does to a cell), k_halo_pack /
+// pressure-face chunks, ghost blocks), the per-cell update (gather_any + update_and_store: what a time step does to a cell), k_halo_pack /
 // k_halo_unpack, k_velocity_pack and k_pressure_extrapolate (the velocity halo of the pressure boundary condition, which had no
 // hardware run in round 1).  The device tables are built from lbm_b200_debug_plan exactly as Solver::init (solver.cu) builds them.
 // tests/test_kernels_harness.py drives partitioned runs with it and compares with the single-domain oracle bit for bit.
@@ -80,7 +80,7 @@ void gather_all(Ctx& c, double* fold_out, double* mom_out) {
   const int32_t nc = static_cast<int32_t>(c.v.ghost_begin);
   launch(nc, 128, [&] { k_gather_all<L, double, true>(p, nc, fold_out, mom_out); });
 }
-// what k_step does to every owned cell (same device functions, without the persistent-CTA driver and its shared-memory template)
+// what a time step does to every owned cell (same device functions, without the persistent-CTA driver and its shared-memory stages)
 template <class L, int COLL>
 void update(Ctx& c) {
   const DevParams<double> p = c.params();

@@ -112,7 +112,7 @@ def emulate(L, spec, world, steps, oracle_mod, kernel=False, collision=0):
                 if kernel == "split":
                     L.kh_step_kernel_split(rk.h, 3)             # outer launch, then inner launch (overlapped path of one_step)
                 elif kernel:
-                    L.kh_step_kernel(rk.h, 3)                   # k_step itself: generic blocks + 3 persistent chunk CTAs
+                    L.kh_step_kernel(rk.h, 3)                   # the kernels themselves: k_step_generic + 3 persistent k_step_fast CTAs
                 else:
                     L.kh_update(rk.h)
             wires = {}
@@ -194,7 +194,7 @@ def test_baseline_configs_on_the_device_code(name, world, kh, oracle_mod):
 
 @pytest.mark.parametrize("world,shape,ndist", [(1, (24, 24, 24), 19), (2, (26, 24, 24), 19), (1, (16, 16, 16), 27), (2, (96, 64), 9)])
 def test_the_fused_kernel_itself_on_the_cpu(world, shape, ndist, kh, oracle_mod):
-    """k_step -- generic blocks and persistent chunk CTAs with the ticket counter, the template in shared memory and the per-chunk
+    """k_step_generic and k_step_fast -- persistent chunk CTAs with the ticket counter, the cp.async tile pipeline through swizzled shared memory and its
     barrier -- run as 32 OS threads per block: interior chunks, wall / edge / corner chunks, pressure-face chunks, ghost blocks."""
     stats = emulate(kh, pressure_box(shape, ndist), world, 3, oracle_mod, kernel=True)
     assert stats["fast"] > 0
