@@ -175,6 +175,9 @@ def load_library():
     L.lbm_b200_set_populations.argtypes = [vp, vp, pdbl]
     L.lbm_b200_get_vars.argtypes = [vp, vp, vp]
     L.lbm_b200_get_moments.argtypes = [vp, pdbl]
+    L.lbm_b200_output_chars.argtypes = [i64]
+    L.lbm_b200_output_chars.restype = i64
+    L.lbm_b200_encode_output.argtypes = [vp, vp, vp, i64, C.POINTER(i64)]
     L.lbm_b200_steps_done.argtypes = [vp]
     L.lbm_b200_steps_done.restype = i64
     L.lbm_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -420,6 +423,17 @@ class Solver:
         out = np.empty((self.n, self.nvar))
         self._check(self._lib.lbm_b200_get_moments(self._h, out))
         return out
+
+    def encode_output(self, keep=None):
+        """Device side of LBMSolver::output: list of NVAR byte strings, the base64 payload of every field of the kept cells as the
+        reference's binary VTK file stores it (lbm_b200_encode_output); keep: bool / uint8 per owned cell or None"""
+        k = None if keep is None else np.ascontiguousarray(keep, dtype=np.uint8)
+        nkeep = self.n if k is None else int(k.sum())
+        per = int(self._lib.lbm_b200_output_chars(nkeep))
+        buf = C.create_string_buffer(max(1, per * self.nvar))
+        off = (C.c_int64 * (self.nvar + 1))()
+        self._check(self._lib.lbm_b200_encode_output(self._h, None if k is None else k.ctypes.data, buf, per * self.nvar, off))
+        return [buf.raw[off[v]:off[v + 1]] for v in range(self.nvar)]
 
     def set_populations(self, f, fold):
         """m_fold (and m_f unless None: it is not an input of the next step) in the reference's layout."""

@@ -1077,6 +1077,14 @@ int lbm_b200_get_vars(lbm_b200_solver* s, double* vars, double* varsold) {
   return s->impl->get_vars(vars, varsold);
 }
 
+int64_t lbm_b200_output_chars(int64_t n_values) { return n_values > 0 ? (8 + 8 * n_values + 2) / 3 * 4 : 0; }
+
+int lbm_b200_encode_output(lbm_b200_solver* s, const uint8_t* keep, char* text, int64_t capacity, int64_t* offsets) {
+  CHECK_HANDLE(s);
+  if(text == nullptr || offsets == nullptr) return fail(LBM_B200_EINVAL, "null argument");
+  return s->impl->encode_output(keep, text, capacity, offsets);
+}
+
 int lbm_b200_get_moments(lbm_b200_solver* s, double* moments) {
   CHECK_HANDLE(s);
   if(moments == nullptr) return fail(LBM_B200_EINVAL, "null argument");

@@ -74,6 +74,10 @@ struct SolverBase {
   virtual int get_moments(double* m)                                     = 0;
   virtual void stats(lbm_b200_stats* st) const                           = 0;
   virtual int64_t owned() const                                          = 0;
+  virtual int encode_output(const uint8_t* keep, char* text, int64_t capacity, int64_t* offsets) {
+    (void)keep; (void)text; (void)capacity; (void)offsets;
+    return fail(LBM_B200_EUNSUP, "no device-side output encoder for this solver kind (use lbm_b200_get_moments and a host writer)");
+  }
   virtual int p2p_export(void* blob) { (void)blob; return fail(LBM_B200_EUNSUP, "peer-to-peer halo: only the fused solver is partitioned"); }
   virtual int p2p_import(int32_t nranks, const void* blobs) { (void)nranks; (void)blobs; return fail(LBM_B200_EUNSUP, "peer-to-peer halo: only the fused solver is partitioned"); }
   virtual int debug_plan(lbm_b200_plan_view* out) { (void)out; return fail(LBM_B200_EUNSUP, "no device plan for this solver kind"); }

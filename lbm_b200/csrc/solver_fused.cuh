@@ -2,6 +2,7 @@
 // SolverBase interface; instantiated by fused_*.cu.
 #pragma once
 #include "solver_common.cuh"
+#include "output.cuh"
 
 namespace lbm_impl {
 
@@ -824,6 +825,66 @@ struct Solver final : SolverBase {
       for(int b = 0; b < 2; ++b) CUDA_TRY(cudaMemcpy(d_values[b].p, hv.data(), hv.size() * sizeof(Real), cudaMemcpyHostToDevice));
     }
     first = true; // the next step consumes the supplied m_fold directly
+    return LBM_B200_OK;
+  }
+
+  // Device side of LBMSolver::output (output.cuh): moments pass, cell filter, 15-decimal rounding and base64 on the device; the host
+  // receives the text of the NVAR <DataArray> payloads.  keep: one byte per OWNED reference cell (nullptr: all).
+  DevBuf<int32_t> d_out_sel;
+  DevBuf<double>  d_out_col;
+  DevBuf<char>    d_out_text;
+  DevBuf<int>     d_out_slow;
+  std::vector<uint8_t> out_keep_cached;
+  int64_t              out_n_cached = -1;
+  int encode_output(const uint8_t* keep, char* text, int64_t capacity, int64_t* offsets) override {
+    if(!inited) return fail(LBM_B200_ESTATE, "not initialised");
+    const int64_t no = plan.n_owned;
+    // selection list (device cells of the kept reference cells), rebuilt only when the filter changes
+    const bool same = out_n_cached >= 0 && (keep == nullptr ? out_keep_cached.empty() : (out_keep_cached.size() == static_cast<size_t>(no)
+                                                                                         && std::memcmp(out_keep_cached.data(), keep, static_cast<size_t>(no)) == 0));
+    if(!same) {
+      std::vector<int32_t> sel;
+      sel.reserve(static_cast<size_t>(no));
+      for(int64_t c = 0; c < no; ++c)
+        if(keep == nullptr || keep[c]) sel.push_back(plan.ref2dev[c]);
+      out_n_cached = static_cast<int64_t>(sel.size());
+      if(keep == nullptr) out_keep_cached.clear(); else out_keep_cached.assign(keep, keep + no);
+      if(sel.empty()) return fail(LBM_B200_EINVAL, "ERROR: Invalid call to encodeLE() with length = 0"); // base64.h:219-223
+      CUDA_TRY(d_out_sel.upload(sel));
+      CUDA_TRY(d_out_col.alloc(sel.size()));
+      CUDA_TRY(d_out_text.alloc(static_cast<size_t>(NVAR) * lbm::out::base64_chars(out_n_cached)));
+      CUDA_TRY(d_out_slow.alloc(1));
+    }
+    const int64_t n = out_n_cached, chars = lbm::out::base64_chars(n);
+    if(capacity < chars * NVAR) return fail(LBM_B200_EINVAL, "lbm_b200_encode_output: text buffer too small");
+    // the moments output() recomputes (solver.cpp:336): one pass of the step kernels without population stores
+    if(halo_pending) {
+      CUDA_TRY(cudaStreamWaitEvent(stream, ev_halo, 0));
+      halo_pending = false;
+    }
+    lbm::DevParams<Real> p = params(cur, cur ^ 1, scratch.p);
+    if(prev_fold.p != nullptr) p.A = prev_fold.p;
+    p.B = nullptr;
+    int rc = launch_main(p, 0, plan.n_gen, 0, plan.n_fast_chunks, max_resident, 0);
+    if(rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(d_out_slow.p, 0, sizeof(int), stream));
+    const int nbk = static_cast<int>((n + 255) / 256);
+    const int64_t ngroups = chars / 4;
+    for(int v = 0; v < NVAR; ++v) {
+      lbm::out::k_output_column<Real><<<nbk, 256, 0, stream>>>(scratch.p, plan.npad, v, d_out_sel.p, n, d_out_col.p, d_out_slow.p);
+      lbm::out::k_base64_field<<<static_cast<int>((ngroups + 255) / 256), 256, 0, stream>>>(d_out_col.p, n, static_cast<unsigned long long>(n) * 8ull,
+                                                                                           d_out_text.p + static_cast<size_t>(v) * chars, ngroups);
+      launches += 2;
+      offsets[v] = static_cast<int64_t>(v) * chars;
+    }
+    offsets[NVAR] = static_cast<int64_t>(NVAR) * chars;
+    CUDA_TRY(cudaGetLastError());
+    int slow = 0;
+    CUDA_TRY(cudaMemcpyAsync(text, d_out_text.p, static_cast<size_t>(NVAR) * chars, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(&slow, d_out_slow.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    d2h_bytes += static_cast<int64_t>(NVAR) * chars;
+    if(slow) return fail(LBM_B200_EUNSUP, "a value is outside the range of the device's exact 15-decimal rounding (not finite or |x| >= 9.007): use the host writer");
     return LBM_B200_OK;
   }
 

@@ -813,6 +813,20 @@ class LBMSolver final : public Runnable {
     std::vector<vtk::Column> cols;
     if(poisson()) cols.push_back(vtk::Column{"V", vars.data(), 1}); // the electric potential, solver.cpp:368-378
     else for(int v = 0; v < NVAR; ++v) cols.push_back(vtk::Column{v == m_ndim ? "rho" : names[v], vars.data() + v, NVAR});
+    // device side of the output path (lbm_b200_encode_output): the cell filter, the 15-decimal rounding and the base64 text of every
+    // field are produced on the GPU; the host only assembles the file.  Solver kinds / values the device encoder does not take
+    // (LBM_B200_EUNSUP) go through the host writer, which produces the same bytes.  LBM_B200_HOST_OUTPUT=1 forces the host writer.
+    std::vector<char> enc;
+    if(!poisson() && nout > 0 && std::getenv("LBM_B200_HOST_OUTPUT") == nullptr) {
+      enc.resize(static_cast<size_t>(NVAR) * static_cast<size_t>(lbm_b200_output_chars(nout)));
+      std::vector<int64_t> off(static_cast<size_t>(NVAR) + 1, 0);
+      if(lbm_b200_encode_output(m_gpu, keep.data(), enc.data(), static_cast<int64_t>(enc.size()), off.data()) == LBM_B200_OK) {
+        for(int v = 0; v < NVAR; ++v) {
+          cols[v].encoded     = enc.data() + off[v];
+          cols[v].encoded_len = static_cast<size_t>(off[v + 1] - off[v]);
+        }
+      }
+    }
     if(nout == 0) TERMM(-1, "ERROR: Invalid call to encodeLE() with length = 0"); // base64.h:219-223 (the reference exits there)
     if(!vtk::write_points(stem + ".vtp", m_ndim, g.n, g.center.data(), keep.data(), cols))
       TERMM(-1, "Invalid output directory set! (value: " + m_outputDir + ")");

@@ -107,6 +107,9 @@ struct Column {
   std::string   name;
   const double* values; // [n_all * stride]
   int64_t       stride; // distance between consecutive cells
+  // payload already encoded on the device (lbm_b200_encode_output: filter, rounding and base64 done there): written as is
+  const char*   encoded     = nullptr;
+  size_t        encoded_len = 0;
 };
 
 // The file, handed to `sink(const std::string&)` piece by piece (one piece per array, the buffer is reused).
@@ -148,9 +151,13 @@ inline void points_stream(Sink&& sink, int ndim, int64_t n_all, const double* ce
   for(const Column& c : columns) {
     t.clear();
     t += "<DataArray type=\"Float64\" Name=\"" + c.name + "\" format=\"binary\">\n";
+    if(c.encoded != nullptr) {
+      t.append(c.encoded, c.encoded_len);
+    } else {
 #pragma omp parallel for schedule(static) if(n > (1 << 14))
-    for(int64_t k = 0; k < n; ++k) col[k] = round15(c.values[id(k) * c.stride]);
-    append_array(t, col.data(), n);
+      for(int64_t k = 0; k < n; ++k) col[k] = round15(c.values[id(k) * c.stride]);
+      append_array(t, col.data(), n);
+    }
     t += "\n        </DataArray> \n";
     sink(t);
   }

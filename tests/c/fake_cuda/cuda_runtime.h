@@ -39,6 +39,8 @@ template <class T> static inline void __stcg(T* p, T v) { *p = v; }
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int) { return v; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 
+static inline long long __double_as_longlong(double x) { long long b; __builtin_memcpy(&b, &x, 8); return b; }
+static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return static_cast<unsigned long long>((static_cast<unsigned __int128>(a) * b) >> 64); }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 static inline double __dadd_rn(double a, double b) { return a + b; }

@@ -1,0 +1,45 @@
+// output_harness.cpp -- TEST INFRASTRUCTURE: the device code of lbm_b200/csrc/output.cuh (15-decimal rounding, base64 of a field) executed
+// on the CPU against the host writer lbm_b200/host/vtk_writer.hpp, which tests/test_vtk_writer.py pins byte for byte against files written
+// by the reference binary.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../lbm_b200/csrc/output.cuh"
+#include "../../lbm_b200/host/vtk_writer.hpp"
+
+extern "C" {
+
+// number of values whose device rounding differs from the host's (values flagged "slow" by the device must be exactly those the host sends
+// through its strtod path: they are skipped in the comparison and counted in *n_slow)
+int64_t oh_check_round15(const double* x, int64_t n, int64_t* n_slow) {
+  int64_t bad = 0;
+  *n_slow = 0;
+  for(int64_t i = 0; i < n; ++i) {
+    int slow = 0;
+    const double d = lbm::out::round15(x[i], &slow);
+    if(slow) { ++*n_slow; continue; }
+    const double h = lbmhost::vtk::round15(x[i]);
+    bad += std::memcmp(&d, &h, 8) != 0 ? 1 : 0;
+  }
+  return bad;
+}
+
+// base64 payload of one field from k_base64_field (one "thread" per group) == vtk::append_array's text ?
+int oh_check_base64(const double* col, int64_t n) {
+  const int64_t chars = lbm::out::base64_chars(n), ngroups = chars / 4;
+  std::vector<char> text(static_cast<size_t>(chars));
+  blockDim.x = 256;
+  gridDim.x  = static_cast<unsigned>((ngroups + 255) / 256);
+  for(unsigned b = 0; b < gridDim.x; ++b)
+    for(unsigned t = 0; t < 256; ++t) {
+      blockIdx.x = b;
+      threadIdx.x = t;
+      lbm::out::k_base64_field(col, n, static_cast<unsigned long long>(n) * 8ull, text.data(), ngroups);
+    }
+  std::string want;
+  lbmhost::vtk::append_array(want, col, n);
+  return want.size() == text.size() && std::memcmp(want.data(), text.data(), text.size()) == 0 ? 0 : 1;
+}
+
+} // extern "C"

@@ -185,3 +185,25 @@ def test_fp32_opt_in_tolerance_3d(case, oracle_mod):
     g.init()
     g.step(steps)
     assert rel_err(g.f, o.f) < 1e-5
+
+
+@pytest.mark.parametrize("case", ["box3d", "couette"])
+def test_device_side_output_encoding(case, oracle_mod):
+    """lbm_b200_encode_output: the fields of the kept cells exactly as the reference's binary VTK writer stores them -- every value through
+    the 15-decimal text round trip (string_helper.h:93-107, IO.h:479), base64(uint64 header = 8 * count || doubles), '=' padding -- with
+    the filter gather, the rounding and the base64 done on the device.  Reference here: the same bytes built in Python from the moments."""
+    import base64
+    import struct
+    spec = box_spec((24, 16, 16), 19, (True, False, False), lid=("+z", (0.05, 0, 0))) if case == "box3d" else load_golden("couette")
+    g = spec.apply_to(lbm_b200.Solver(spec.ndim, spec.ndist, spec.nghbr, spec.omega))
+    g.init()
+    g.step(25)
+    m = g.moments()
+    rng = np.random.default_rng(3)
+    for keep in (None, rng.random(m.shape[0]) < 0.37):
+        got = g.encode_output(keep)
+        sel = m if keep is None else m[keep]
+        for v in range(m.shape[1]):
+            col = np.array([float(f"{x:.15f}") for x in sel[:, v]])
+            want = base64.b64encode(struct.pack("<Q", 8 * len(col)) + col.astype("<f8").tobytes())
+            assert got[v] == want, f"field {v} differs"
