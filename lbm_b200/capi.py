@@ -178,6 +178,8 @@ def load_library():
     L.lbm_b200_output_chars.argtypes = [i64]
     L.lbm_b200_output_chars.restype = i64
     L.lbm_b200_encode_output.argtypes = [vp, vp, vp, i64, C.POINTER(i64)]
+    L.lbm_b200_host_alloc.argtypes = [C.POINTER(vp), i64]
+    L.lbm_b200_host_free.argtypes = [vp]
     L.lbm_b200_steps_done.argtypes = [vp]
     L.lbm_b200_steps_done.restype = i64
     L.lbm_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -424,16 +426,20 @@ class Solver:
         self._check(self._lib.lbm_b200_get_moments(self._h, out))
         return out
 
-    def encode_output(self, keep=None):
+    def encode_output(self, keep=None, out=None, raw=False):
         """Device side of LBMSolver::output: list of NVAR byte strings, the base64 payload of every field of the kept cells as the
-        reference's binary VTK file stores it (lbm_b200_encode_output); keep: bool / uint8 per owned cell or None"""
+        reference's binary VTK file stores it (lbm_b200_encode_output); keep: bool / uint8 per owned cell or None.
+        out: uint8 array to receive the text (e.g. pinned memory); raw: return views of it instead of bytes objects"""
         k = None if keep is None else np.ascontiguousarray(keep, dtype=np.uint8)
         nkeep = self.n if k is None else int(k.sum())
-        per = int(self._lib.lbm_b200_output_chars(nkeep))
-        buf = C.create_string_buffer(max(1, per * self.nvar))
+        total = int(self._lib.lbm_b200_output_chars(nkeep)) * self.nvar
+        buf = np.empty(max(1, total), dtype=np.uint8) if out is None else out
+        if buf.dtype != np.uint8 or buf.size < total or not buf.flags.c_contiguous:
+            raise ValueError("encode_output: `out` must be a contiguous uint8 array of at least nvar * output_chars(kept) elements")
         off = (C.c_int64 * (self.nvar + 1))()
-        self._check(self._lib.lbm_b200_encode_output(self._h, None if k is None else k.ctypes.data, buf, per * self.nvar, off))
-        return [buf.raw[off[v]:off[v + 1]] for v in range(self.nvar)]
+        self._check(self._lib.lbm_b200_encode_output(self._h, None if k is None else k.ctypes.data, buf.ctypes.data, total, off))
+        views = [buf[off[v]:off[v + 1]] for v in range(self.nvar)]
+        return views if raw else [v.tobytes() for v in views]
 
     def set_populations(self, f, fold):
         """m_fold (and m_f unless None: it is not an input of the next step) in the reference's layout."""
@@ -448,6 +454,31 @@ class Solver:
         st = Stats()
         self._check(self._lib.lbm_b200_get_stats(self._h, C.byref(st)))
         return {k: getattr(st, k) for k, _ in Stats._fields_}
+
+
+class HostBuffer:
+    """Page-locked host memory (lbm_b200_host_alloc) as a uint8 numpy array `.array`; `.view(dtype, shape)` reinterprets it.  The memory
+    lives as long as this object: keep it while any view is in use"""
+
+    def __init__(self, nbytes):
+        self._lib = load_library()
+        self._p = C.c_void_p()
+        rc = self._lib.lbm_b200_host_alloc(C.byref(self._p), int(nbytes))
+        if rc != 0:
+            raise LbmB200Error(rc, self._lib.lbm_b200_last_error().decode())
+        self.array = np.ctypeslib.as_array((C.c_uint8 * int(nbytes)).from_address(self._p.value))
+
+    def view(self, dtype, shape):
+        return self.array[:int(np.prod(shape)) * np.dtype(dtype).itemsize].view(dtype).reshape(shape)
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            self._lib.lbm_b200_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        self.close()
 
 
 def box_topology(shape, periodic, want_center=True, want_coords=False):

@@ -1085,6 +1085,23 @@ int lbm_b200_encode_output(lbm_b200_solver* s, const uint8_t* keep, char* text, 
   return s->impl->encode_output(keep, text, capacity, offsets);
 }
 
+int lbm_b200_host_alloc(void** ptr, int64_t bytes) {
+  if(ptr == nullptr || bytes <= 0) return fail(LBM_B200_EINVAL, "lbm_b200_host_alloc: null pointer or non-positive size");
+  *ptr = nullptr;
+  const cudaError_t e = cudaMallocHost(ptr, static_cast<size_t>(bytes));
+  if(e != cudaSuccess) {
+    *ptr = nullptr;
+    return fail(LBM_B200_ECUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+  }
+  return LBM_B200_OK;
+}
+
+int lbm_b200_host_free(void* ptr) {
+  if(ptr == nullptr) return LBM_B200_OK;
+  const cudaError_t e = cudaFreeHost(ptr);
+  return e == cudaSuccess ? LBM_B200_OK : fail(LBM_B200_ECUDA, std::string("cudaFreeHost: ") + cudaGetErrorString(e));
+}
+
 int lbm_b200_get_moments(lbm_b200_solver* s, double* moments) {
   CHECK_HANDLE(s);
   if(moments == nullptr) return fail(LBM_B200_EINVAL, "null argument");

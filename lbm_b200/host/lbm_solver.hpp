@@ -186,6 +186,7 @@ class LBMGrid final : public GridInterface {
 class LBMSolver final : public Runnable {
  public:
   ~LBMSolver() override {
+    lbm_b200_host_free(m_encBuf);
     if(m_gpu != nullptr) lbm_b200_destroy(m_gpu);
     if(m_part != nullptr) lbm_b200_partition_destroy(m_part);
   }
@@ -277,6 +278,9 @@ class LBMSolver final : public Runnable {
 
   // results for callers that embed the solver (tests): macroscopic fields of the last output(), errors of the analytic check
   std::vector<double> vars;
+  bool                m_varsFresh = false;
+  char*               m_encBuf    = nullptr; // page-locked text of the output fields (lbm_b200_encode_output)
+  int64_t             m_encCap    = 0;
   double  maxError = NAN, l2Error = NAN, gre = NAN;
   int64_t stepsRun = 0;
   bool    converged = false;
@@ -358,6 +362,7 @@ class LBMSolver final : public Runnable {
       output(m_timeStep == m_maxTimeStep - 1 || converged);
     }
     stepsRun = m_timeStep;
+    fetchVars(); // the final state for the atEnd hooks, the analytic comparison and the callers of vars (output() leaves it on the device)
     executePostprocess(PP_ATEND);
     if(m_diverged) TERMM(-1, "Solution diverged");
     if(m_cfg.has("analyticalSolution")) compareToAnalyticalResult();
@@ -786,6 +791,13 @@ class LBMSolver final : public Runnable {
     return false;
   }
 
+  // moments of the current fold in the reference's cell order, once per output step
+  void fetchVars() {
+    if(m_varsFresh) return;
+    call(lbm_b200_get_moments(m_gpu, vars.data()));
+    m_varsFresh = true;
+  }
+
   // solver.cpp:323-384: the moments of the current fold go to out/<solution_filename>_<step>.vtp in the reference's own binary
   // VTK flavour (vtk_writer.hpp, byte-identical to the reference's file); "output_format": "ascii" is an extension
   void output(bool forced, const std::string& postfix = "") {
@@ -795,13 +807,16 @@ class LBMSolver final : public Runnable {
       output(true, "bdiv");
       return;
     }
+    m_varsFresh = false; // `vars` is fetched only by the paths that read it on the host (fetchVars)
     if(!((m_timeStep > 0 && m_timeStep % m_solutionInterval == 0) || forced)) return;
-    call(lbm_b200_get_moments(m_gpu, vars.data()));
     if(!m_cfg.opt_bool("write_output", true)) return;
     const std::string stem = m_outputDir + m_solutionName + "_" + std::to_string(m_timeStep) + postfix;
     ::mkdir(m_outputDir.c_str(), 0755);
     const std::string format = m_cfg.opt_str("output_format", "binary");
-    if(format == "ascii") return writeVtpAscii(stem + ".vtp");
+    if(format == "ascii") {
+      fetchVars();
+      return writeVtpAscii(stem + ".vtp");
+    }
     if(format != "binary") TERMM(-1, "Invalid output_format: " + format);
     const SolverGrid&     g    = m_grid.g;
     const int             NVAR = nvar();
@@ -811,22 +826,34 @@ class LBMSolver final : public Runnable {
     std::cerr << "  Writing " << stem << ".vtp with #" << nout << " cells" << std::endl; // IO.h:423
     static const char* names[4] = {"U", "V", "W", "rho"};                                // variables.h: VELSTR, "rho"
     std::vector<vtk::Column> cols;
+    if(poisson()) fetchVars();
     if(poisson()) cols.push_back(vtk::Column{"V", vars.data(), 1}); // the electric potential, solver.cpp:368-378
     else for(int v = 0; v < NVAR; ++v) cols.push_back(vtk::Column{v == m_ndim ? "rho" : names[v], vars.data() + v, NVAR});
     // device side of the output path (lbm_b200_encode_output): the cell filter, the 15-decimal rounding and the base64 text of every
     // field are produced on the GPU; the host only assembles the file.  Solver kinds / values the device encoder does not take
     // (LBM_B200_EUNSUP) go through the host writer, which produces the same bytes.  LBM_B200_HOST_OUTPUT=1 forces the host writer.
-    std::vector<char> enc;
     if(!poisson() && nout > 0 && std::getenv("LBM_B200_HOST_OUTPUT") == nullptr) {
-      enc.resize(static_cast<size_t>(NVAR) * static_cast<size_t>(lbm_b200_output_chars(nout)));
+      // the text lands in page-locked memory kept from one output step to the next (lbm_b200_host_alloc)
+      const int64_t need = static_cast<int64_t>(NVAR) * lbm_b200_output_chars(nout);
+      if(need > m_encCap) {
+        lbm_b200_host_free(m_encBuf);
+        m_encBuf = nullptr;
+        m_encCap = 0;
+        void* ptr = nullptr;
+        if(lbm_b200_host_alloc(&ptr, need) == LBM_B200_OK) {
+          m_encBuf = static_cast<char*>(ptr);
+          m_encCap = need;
+        }
+      }
       std::vector<int64_t> off(static_cast<size_t>(NVAR) + 1, 0);
-      if(lbm_b200_encode_output(m_gpu, keep.data(), enc.data(), static_cast<int64_t>(enc.size()), off.data()) == LBM_B200_OK) {
+      if(m_encBuf != nullptr && lbm_b200_encode_output(m_gpu, keep.data(), m_encBuf, m_encCap, off.data()) == LBM_B200_OK) {
         for(int v = 0; v < NVAR; ++v) {
-          cols[v].encoded     = enc.data() + off[v];
+          cols[v].encoded     = m_encBuf + off[v];
           cols[v].encoded_len = static_cast<size_t>(off[v + 1] - off[v]);
         }
       }
     }
+    if(!poisson() && cols[0].encoded == nullptr) fetchVars(); // host writer: the moments come to the host
     if(nout == 0) TERMM(-1, "ERROR: Invalid call to encodeLE() with length = 0"); // base64.h:219-223 (the reference exits there)
     if(!vtk::write_points(stem + ".vtp", m_ndim, g.n, g.center.data(), keep.data(), cols))
       TERMM(-1, "Invalid output directory set! (value: " + m_outputDir + ")");
@@ -949,7 +976,8 @@ class LBMSolver final : public Runnable {
     std::cerr << "Executing postprocessing at hook:" << hookName[hook] << std::endl;
     const SolverGrid& g    = m_grid.g;
     const int         NVAR = nvar();
-    if(hook == PP_ATSTART) call(lbm_b200_get_moments(m_gpu, vars.data())); // atEnd: `vars` holds the last, forced output()
+    if(hook == PP_ATSTART) m_varsFresh = false;
+    fetchVars(); // atEnd: the state of the last, forced output()
     for(const auto& cells : m_ppLines[hook]) {
       std::cerr << "  Writing line.csv" << std::endl;
       writeLineCsv("line.csv", cells, g, vars.data(), NVAR); // relative to the working directory, like the reference

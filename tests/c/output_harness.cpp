@@ -42,4 +42,19 @@ int oh_check_base64(const double* col, int64_t n) {
   return want.size() == text.size() && std::memcmp(want.data(), text.data(), text.size()) == 0 ? 0 : 1;
 }
 
+// the host writer's work for the fields of one file (vtk_writer.hpp, points_stream): per variable, the strided column of the kept cells
+// through round15, then base64.  Returns the number of characters produced; timed by tools/bench_output.py beside the device encoder.
+int64_t oh_host_encode(const double* vars, int64_t n, int nvar) {
+  int64_t             chars = 0;
+  std::vector<double> col(static_cast<size_t>(n));
+  for(int v = 0; v < nvar; ++v) {
+#pragma omp parallel for schedule(static) if(n > (1 << 14))
+    for(int64_t k = 0; k < n; ++k) col[k] = lbmhost::vtk::round15(vars[k * nvar + v]);
+    std::string t;
+    lbmhost::vtk::append_array(t, col.data(), n);
+    chars += static_cast<int64_t>(t.size());
+  }
+  return chars;
+}
+
 } // extern "C"

@@ -168,3 +168,17 @@ def test_poisson_entry_points_check_their_arguments():
     assert c == -1 and "Unsupported model" in msg   # m_canPoisson, constants.h
     c, msg = code_of(lbm_b200.Solver, 1, 5, g1, 1.0, device=-1)
     assert c == -1 and "Unsupported model" in msg
+
+
+def test_host_alloc_argument_checks_and_no_device():
+    """lbm_b200_host_alloc / lbm_b200_host_free: argument errors are return codes; without a CUDA device the allocation fails loudly
+    (no silent pageable substitute), freeing NULL is accepted"""
+    import torch
+    lib = load_library()
+    p = C.c_void_p()
+    assert lib.lbm_b200_host_alloc(None, 64) == -1
+    assert lib.lbm_b200_host_alloc(C.byref(p), 0) == -1 and lib.lbm_b200_host_alloc(C.byref(p), -8) == -1
+    assert lib.lbm_b200_host_free(None) == 0
+    if not torch.cuda.is_available():
+        c, msg = code_of(lbm_b200.HostBuffer, 1 << 20)
+        assert c != 0 and "cudaMallocHost" in msg

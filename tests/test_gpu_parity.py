@@ -207,3 +207,7 @@ def test_device_side_output_encoding(case, oracle_mod):
             col = np.array([float(f"{x:.15f}") for x in sel[:, v]])
             want = base64.b64encode(struct.pack("<Q", 8 * len(col)) + col.astype("<f8").tobytes())
             assert got[v] == want, f"field {v} differs"
+    pinned = lbm_b200.HostBuffer(sum(len(t) for t in got))                  # page-locked destination (lbm_b200_host_alloc): same text
+    again = g.encode_output(keep, out=pinned.array, raw=True)
+    assert [bytes(a) for a in again] == got
+    pinned.close()
