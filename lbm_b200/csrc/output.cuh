@@ -3,8 +3,9 @@
 // LBMSolver::output (/root/reference/src/lbm/solver.cpp:323-384) recomputes the macroscopic fields, filters the cells
 // (cell_filter.h:84-96), turns every value into a 15-decimal string and back (string_helper.h:93-107, IO.h:479), and writes each
 // field as base64( uint64 header || little-endian doubles ) with '=' padding (base64.h:216-270, IO.h:395-399).  On the host that
-// costs about 3 s per 256^3 output even with lbm_b200/host/vtk_writer.hpp's fast rounding; here the filter gather, the rounding and
-// the base64 text are produced on the device, and what crosses PCIe is the text the file stores.
+// costs 0.48 s per 256^3 output on 16 cores even with lbm_b200/host/vtk_writer.hpp's fast rounding (3 s on two); here the filter gather,
+// the rounding and the base64 text are produced on the device, and what crosses PCIe is the text the file stores (16 ms into page-locked
+// memory).
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -82,8 +83,9 @@ static __global__ void k_base64_field(const double* __restrict__ col, int64_t n,
   char c0 = T[v >> 18], c1 = T[(v >> 12) & 63], c2 = T[(v >> 6) & 63], c3 = T[v & 63];
   if(have == 1) { c2 = '='; c3 = '='; }
   if(have == 2) c3 = '=';
-  char* o = text + 4 * g;
-  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+  // one 32-bit store per group (text and every field's offset in it are multiples of four characters)
+  reinterpret_cast<uint32_t*>(text)[g] = static_cast<uint32_t>(static_cast<unsigned char>(c0)) | (static_cast<uint32_t>(static_cast<unsigned char>(c1)) << 8)
+                                         | (static_cast<uint32_t>(static_cast<unsigned char>(c2)) << 16) | (static_cast<uint32_t>(static_cast<unsigned char>(c3)) << 24);
 }
 
 static inline int64_t base64_chars(int64_t n_values) { return (8 + 8 * n_values + 2) / 3 * 4; }

@@ -8,6 +8,32 @@
 #include "../../lbm_b200/csrc/output.cuh"
 #include "../../lbm_b200/host/vtk_writer.hpp"
 
+// k_output_column over a fake launch: column `var` of the cells sel[] of a [nvar][stride] array, rounded; returns the number of entries
+// that differ from the host's round15 of the same value (entries the device flags as slow are compared as passed through unchanged)
+template <class Real>
+static int64_t check_column(const Real* src, int64_t stride, int var, const int32_t* sel, int64_t n, int* slow_out) {
+  std::vector<double> col(static_cast<size_t>(n), -1.0);
+  int slow = 0;
+  blockDim.x = 128;
+  gridDim.x  = static_cast<unsigned>((n + 127) / 128);
+  for(unsigned b = 0; b < gridDim.x; ++b)
+    for(unsigned t = 0; t < 128; ++t) {
+      blockIdx.x = b;
+      threadIdx.x = t;
+      lbm::out::k_output_column<Real>(src, stride, var, sel, n, col.data(), &slow);
+    }
+  int64_t bad = 0;
+  for(int64_t k = 0; k < n; ++k) {
+    const double x = static_cast<double>(src[static_cast<size_t>(var) * stride + sel[k]]);
+    int s = 0;
+    lbm::out::round15(x, &s);
+    const double want = s ? x : lbmhost::vtk::round15(x);
+    bad += std::memcmp(&col[k], &want, 8) != 0 ? 1 : 0;
+  }
+  *slow_out = slow;
+  return bad;
+}
+
 extern "C" {
 
 // number of values whose device rounding differs from the host's (values flagged "slow" by the device must be exactly those the host sends
@@ -41,6 +67,9 @@ int oh_check_base64(const double* col, int64_t n) {
   lbmhost::vtk::append_array(want, col, n);
   return want.size() == text.size() && std::memcmp(want.data(), text.data(), text.size()) == 0 ? 0 : 1;
 }
+
+int64_t oh_check_column_f64(const double* src, int64_t stride, int var, const int32_t* sel, int64_t n, int* slow) { return check_column(src, stride, var, sel, n, slow); }
+int64_t oh_check_column_f32(const float* src, int64_t stride, int var, const int32_t* sel, int64_t n, int* slow) { return check_column(src, stride, var, sel, n, slow); }
 
 // the host writer's work for the fields of one file (vtk_writer.hpp, points_stream): per variable, the strided column of the kept cells
 // through round15, then base64.  Returns the number of characters produced; timed by tools/bench_output.py beside the device encoder.

@@ -20,6 +20,9 @@ def oh(tmp_path_factory):
     L.oh_check_round15.restype = C.c_int64
     L.oh_check_round15.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     L.oh_check_base64.argtypes = [C.c_void_p, C.c_int64]
+    for fn in (L.oh_check_column_f64, L.oh_check_column_f32):
+        fn.restype = C.c_int64
+        fn.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int)]
     return L
 
 
@@ -42,3 +45,20 @@ def test_round15_equals_the_host_writer(oh):
 def test_base64_field_equals_the_host_writer(oh, n):
     col = np.ascontiguousarray(np.random.default_rng(n).standard_normal(n))
     assert oh.oh_check_base64(col.ctypes.data, n) == 0
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_output_column_gathers_the_kept_cells_and_flags_what_it_cannot_round(oh, dtype):
+    """k_output_column: the kept cells (a selection list in reference order pointing at permuted device cells) of one variable of the
+    [nvar][stride] moment array, rounded like the host writer; one value outside the exact range raises the flag for the whole call"""
+    rng = np.random.default_rng(11)
+    stride, nvar, n = 4096, 4, 1500
+    src = np.ascontiguousarray((rng.standard_normal((nvar, stride)) * 0.1).astype(dtype))
+    sel = np.ascontiguousarray(rng.permutation(stride)[:n].astype(np.int32))
+    fn = oh.oh_check_column_f64 if dtype == np.float64 else oh.oh_check_column_f32
+    slow = C.c_int(7)
+    for var in range(nvar):
+        assert fn(src.ctypes.data, stride, var, sel.ctypes.data, n, C.byref(slow)) == 0 and slow.value == 0
+    src[2, sel[17]] = np.nan
+    assert fn(src.ctypes.data, stride, 2, sel.ctypes.data, n, C.byref(slow)) == 0 and slow.value == 1
+    assert fn(src.ctypes.data, stride, 1, sel.ctypes.data, n, C.byref(slow)) == 0 and slow.value == 0
