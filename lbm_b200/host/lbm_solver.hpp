@@ -29,6 +29,7 @@
 #include "../../include/lbm_b200.h"
 #include "grid.hpp"
 #include "json.hpp"
+#include "run_log.hpp"
 #include "vtk_writer.hpp"
 #include "expr.hpp"
 #include "uniform_grid.hpp"
@@ -144,9 +145,17 @@ class GeneratedGrid final : public GridInterface {
 
 class GridGenerator final : public Runnable {
  public:
-  void init(int /*argc*/, char** /*argv*/, std::string config_file) override {
+  void init(int argc, char** argv, std::string config_file) override {
+    RunRecord& rec = RunRecord::get();
+    rec.timers.start(rec.gridTotal);
+    rec.timers.start(rec.gridInit);
+    const RankInfo rank = RankInfo::from_env();
+    if(rec.enabled) rec.grid_log.open("gridgen_log", argc, argv, rank.rank, rank.world); // gridGenerator.cpp:22-29
     m_config = Json::parse_file(config_file);
     std::cout << "Grid generator started ||>" << std::endl;
+    rec.grid_log("Grid generator started ||>");
+    rec.grid_log("Loading configuration file [" + config_file + "]");
+    rec.timers.stop(rec.gridInit);
   }
   void initBenchmark(int /*argc*/, char** /*argv*/) override {
     // gridGenerator.cpp:43-54: 3D, uniform level 5, default cube geometry
@@ -154,16 +163,23 @@ class GridGenerator final : public Runnable {
       "geometry":{"cube":{"type":"box","A":[0.0,0.0,0.0],"B":[1.0,1.0,1.0]}}})");
   }
   int64_t run() override {
+    RunRecord& rec = RunRecord::get();
+    rec.timers.start(rec.gridCreate);
     m_grid.gen.configure(m_config);
+    rec.grid_log("Generating a grid[" + std::to_string(m_grid.gen.ndim) + "D]");
     if(RankInfo::from_env().world > 1) {
       // partitioned run: no rank builds the whole tree; the solver asks the on-demand provider (uniform_grid.hpp) for its own rows
       std::cout << "    * partitioned run: grid rows are generated per rank" << std::endl;
+      rec.grid_log("    * partitioned run: grid rows are generated per rank");
+      finish(rec);
       return 0;
     }
     m_grid.gen.generate();
     std::cout << "    * grid has " << m_grid.noCells() << " cells" << std::endl;
+    rec.grid_log("      * grid has " + std::to_string(m_grid.noCells()) + " cells");
     const long long maxc = m_config.opt_int("maxNoCells", -1);
     if(maxc >= 0 && m_grid.noCells() > maxc) TERMM(-1, "Out of memory!"); // cartesiangrid_generation.h:336
+    finish(rec);
     return 0;
   }
   const GridInterface& grid() const override { return m_grid; }
@@ -171,6 +187,14 @@ class GridGenerator final : public Runnable {
   const Json& config() const { return m_config; }
 
  private:
+  // gridGenerator.cpp:88-100: the generator's log ends with the timer table as it stands when the generator is done
+  static void finish(RunRecord& rec) {
+    rec.timers.stop(rec.gridCreate);
+    rec.timers.stop(rec.gridTotal);
+    rec.grid_log("Grid generator finished <||");
+    rec.timers.display(rec.grid_log);
+    rec.grid_log.close();
+  }
   Json          m_config;
   GeneratedGrid m_grid;
 };
@@ -191,8 +215,16 @@ class LBMSolver final : public Runnable {
     if(m_part != nullptr) lbm_b200_partition_destroy(m_part);
   }
 
-  void init(int /*argc*/, char** /*argv*/, std::string config_file) override {
+  void init(int argc, char** argv, std::string config_file) override {
+    RunRecord& rec = RunRecord::get();
+    rec.createLbmTimers();
+    rec.timers.start(rec.lbmTotal);
+    rec.timers.start(rec.lbmInit);
     m_configFile = config_file;
+    {
+      const RankInfo rank = RankInfo::from_env();
+      if(rec.enabled) rec.lbm_log.open("lbm_log", argc, argv, rank.rank, rank.world); // solver.cpp:13-20
+    }
     const Json all = Json::parse_file(config_file);
     if(!all.has("solver")) TERMM(-1, "The required configuration value is missing: solver");
     m_cfg = all.at("solver");
@@ -216,6 +248,8 @@ class LBMSolver final : public Runnable {
     m_startTime = ::time(nullptr);
     if(m_rank.world > 1 && m_rank.rank == 0) std::remove(m_rank.id_file.c_str()); // nothing stale may be picked up by the other ranks
     std::cout << m_ndim << "D LBM Solver started ||>" << std::endl;
+    rec.lbm_log(std::to_string(m_ndim) + "D LBM Solver started ||>"); // solver.cpp:29-30
+    rec.lbm_log("Loading configuration file [" + config_file + "]");
   }
 
   void initBenchmark(int /*argc*/, char** /*argv*/) override {
@@ -225,7 +259,7 @@ class LBMSolver final : public Runnable {
   }
 
   void transferGrid(const GridInterface& grid) override {
-    std::cerr << "Transferring " << m_ndim << "D Grid to LBM solver" << std::endl;
+    say("Transferring " + std::to_string(m_ndim) + "D Grid to LBM solver");
     if(grid.dim() != m_ndim) TERMM(-1, "Invalid configuration the grid dimensionality is not matching!");
     const auto* gen = dynamic_cast<const GeneratedGrid*>(&grid);
     if(gen == nullptr) TERMM(-1, "transferGrid expects the generator's grid");
@@ -342,10 +376,16 @@ class LBMSolver final : public Runnable {
     if(m_benchmark) return runBenchmark();
     loadConfiguration();
     if(m_rank.world > 1) return runPartitioned();
+    RunRecord& rec = RunRecord::get();
+    rec.createLbmTimers();
     initPostprocess();
     setupGpu();
     vars.assign(static_cast<size_t>(m_grid.g.n) * nvar(), 0.0);
+    rec.timers.stop(rec.lbmInit);
+    rec.timers.start(rec.lbmMain);
+    rec.timers.start(rec.lbmPost);
     executePostprocess(PP_ATSTART);
+    rec.timers.stop(rec.lbmPost);
     using clk = std::chrono::steady_clock;
     auto    lastInfo = clk::now();
     int64_t lastStep = 0;
@@ -357,17 +397,47 @@ class LBMSolver final : public Runnable {
         lastInfo = clk::now();
         lastStep = m_timeStep;
       }
+      rec.timers.start(rec.lbmComp);
       converged = convergenceCondition();
       call(lbm_b200_step(m_gpu, 1));
-      output(m_timeStep == m_maxTimeStep - 1 || converged);
+      const bool last = m_timeStep == m_maxTimeStep - 1 || converged;
+      // the launches are asynchronous: before a file is written the device catches up, so that "Computation" holds the device's time
+      // and "IO" only the output
+      if(outputDue(last)) call(lbm_b200_synchronize(m_gpu));
+      rec.timers.stop(rec.lbmComp);
+      rec.timers.start(rec.lbmIO);
+      output(last);
+      rec.timers.stop(rec.lbmIO);
     }
     stepsRun = m_timeStep;
+    rec.timers.start(rec.lbmPost);
     fetchVars(); // the final state for the atEnd hooks, the analytic comparison and the callers of vars (output() leaves it on the device)
     executePostprocess(PP_ATEND);
+    rec.timers.stop(rec.lbmPost);
+    rec.timers.stop(rec.lbmMain);
     if(m_diverged) TERMM(-1, "Solution diverged");
     if(m_cfg.has("analyticalSolution")) compareToAnalyticalResult();
     std::cout << "LBM Solver finished <||" << std::endl;
+    finishLog();
     return 0;
+  }
+
+  // the end of lbm_log: the closing message and the timer table (main.cpp:289-300 of the reference prints it when the run is over)
+  void finishLog() {
+    RunRecord& rec = RunRecord::get();
+    rec.createLbmTimers();
+    rec.timers.stop(rec.lbmTotal);
+    rec.lbm_log("LBM Solver finished <||");
+    rec.timers.display(rec.lbm_log);
+    rec.lbm_log.close();
+  }
+  // a line on stderr that the reference also writes to its log
+  static void say(const std::string& text) {
+    std::cerr << text << std::endl;
+    RunRecord::get().lbm_log(text);
+  }
+  bool outputDue(bool forced) const {
+    return (m_diverged && !m_wroteDiverged) || (m_timeStep > 0 && m_timeStep % m_solutionInterval == 0) || forced;
   }
 
  private:
@@ -541,6 +611,7 @@ class LBMSolver final : public Runnable {
     m_gpu = nullptr;
     if(!m_p2pFile.empty()) std::remove(m_p2pFile.c_str());
     std::cout << "LBM Solver finished <||" << std::endl;
+    finishLog();
     return 0;
   }
 
@@ -772,19 +843,22 @@ class LBMSolver final : public Runnable {
     int32_t bad = 0;
     call(lbm_b200_residual(m_gpu, conv.data(), &bad));
     static const char* names3[4] = {"U", "V", "W", "rho"};
-    std::cerr << m_timeStep << ": ";
-    for(int v = 0; v < NVAR; ++v) std::cerr << "d" << (poisson() ? "P" : (v == m_ndim ? "rho" : names3[v])) << "=" << conv[v] << " ";
-    std::cerr << std::endl;
+    std::ostringstream line;
+    line << m_timeStep << ": ";
+    for(int v = 0; v < NVAR; ++v) line << "d" << (poisson() ? "P" : (v == m_ndim ? "rho" : names3[v])) << "=" << conv[v] << " ";
+    say(line.str());
     double maxConv = conv[0];
     for(double c : conv) maxConv = std::max(maxConv, c);
     lastResidual = maxConv;
     const double crit = m_cfg.opt("convergence", 1E-12);
     if(m_timeStep > 1 && maxConv < crit) {
-      std::cerr << "Reached convergence to: " << maxConv << std::endl;
+      std::ostringstream line;
+      line << "Reached convergence to: " << maxConv;
+      say(line.str());
       return true;
     }
     if(m_timeStep > 1 && (bad || std::isnan(maxConv) || std::isinf(maxConv))) {
-      std::cerr << "Solution diverged!" << std::endl;
+      say("Solution diverged!");
       m_diverged = true;
       return true;
     }
@@ -823,7 +897,7 @@ class LBMSolver final : public Runnable {
     std::vector<uint8_t>  keep = cellFilter();
     int64_t               nout = 0;
     for(uint8_t k : keep) nout += k;
-    std::cerr << "  Writing " << stem << ".vtp with #" << nout << " cells" << std::endl; // IO.h:423
+    say("  Writing " + stem + ".vtp with #" + std::to_string(nout) + " cells"); // IO.h:423
     static const char* names[4] = {"U", "V", "W", "rho"};                                // variables.h: VELSTR, "rho"
     std::vector<vtk::Column> cols;
     if(poisson()) fetchVars();
@@ -1068,8 +1142,16 @@ class LBMSolver final : public Runnable {
     }
     l2Error = (gcem_sqrt(sumErrorSq) / gcem_sqrt(sumSolutionSq)) / std::pow(static_cast<double>(g.n), 1.0 / m_ndim);
     gre     = sumError / sumSolution;
-    std::cerr << "Comparing to analytical result " << name << "\nmax. Error: " << maxError << "\navg. L2: " << l2Error
-              << "\nglobal relative error: " << gre << std::endl;
+    {
+      std::ostringstream l1, l2, l3;
+      l1 << "max. Error: " << maxError;
+      l2 << "avg. L2: " << l2Error;
+      l3 << "global relative error: " << gre;
+      say("Comparing to analytical result " + name); // one log message per line, like solver.cpp:473-480
+      say(l1.str());
+      say(l2.str());
+      say(l3.str());
+    }
     bool failed = false;
     if(m_cfg.opt("errorMax", 1.0) < maxError) {
       failed = true;

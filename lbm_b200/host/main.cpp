@@ -43,6 +43,7 @@ int main(int argc, char** argv) {
     std::cerr << "Unknown option " << a << std::endl;
     return 255;
   }
+  RunRecord::get().enabled = true;    // gridgen_log / lbm_log in the working directory, like the reference (run_log.hpp)
   RankInfo::use_environment() = true; // one process per GPU: rank / world size from the launcher (lbm_solver.hpp: RankInfo)
   try {
     if(bench) { // the reference's --bench is unimplemented for the LBM solver (src/lbm/solver.cpp:39-46); here it runs

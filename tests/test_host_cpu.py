@@ -89,3 +89,71 @@ def test_navierstokespoisson_ends_like_the_reference(tmp_path):
     exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lbm_b200", "lbm")
     r = subprocess.run([exe, "case.json"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
     assert r.returncode == 255 and "Unsupported equation type" in r.stderr
+
+
+TIMER_LINE = r"^ *\[\d{2,3}\.\d%\] .{1,44}? +[0-9.e+-]+ \[sec\]$"
+
+
+def read_run_log(path):
+    """messages of a reference-style log file (include/common/log.h): well-formed XML, <meta> entries, <m d="0" >text\\n</m> elements"""
+    import xml.etree.ElementTree as ET
+    root = ET.parse(path).getroot()
+    assert root.tag == "root"
+    meta = {m.get("name"): m.get("content") for m in root.findall("meta")}
+    assert {"noDomains", "dateCreation", "fileFormatVersion", "user", "host", "dir", "executionCommand", "revision", "build", "dateClosing"} <= set(meta)
+    msgs = [m.text for m in root.findall("m")]
+    assert all(m.get("d") == "0" for m in root.findall("m")) and all(t.endswith("\n") for t in msgs)
+    return meta, [t[:-1] for t in msgs]
+
+
+def test_lbm_executable_leaves_the_reference_style_run_logs(tmp_path):
+    """`gridgen_log` and `lbm_log` in the working directory (lbm_b200/host/run_log.hpp): XML envelope, messages and
+    the timer table in the reference's layout.  Without a device the solver stops at lbm_b200_create (exit status 255, like TERMM) and the
+    logs are still closed properly; with one the run goes through and lbm_log ends with the whole table."""
+    import json
+    import re
+    import subprocess
+    from casebuilder import load_golden
+    cfg = json.loads(str(load_golden("couette").golden["config_orig_json"]))
+    (tmp_path / "case.json").write_text(json.dumps(cfg))
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lbm_b200", "lbm")
+    r = subprocess.run([exe, "case.json"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode in (0, 255), r.stderr[-1500:]
+    meta, msgs = read_run_log(tmp_path / "gridgen_log")
+    assert meta["noDomains"] == "1" and meta["executionCommand"].endswith("lbm case.json") and meta["dir"] == str(tmp_path)
+    assert msgs[0] == "Grid generator started ||>" and "Loading configuration file [case.json]" in msgs and "Generating a grid[2D]" in msgs
+    assert "      * grid has 640 cells" in msgs and "Grid generator finished <||" in msgs
+    table = msgs[msgs.index("-" * 80):]
+    assert table[1] == "Group".ljust(50) + "Application".ljust(40)
+    names = [re.sub(r"^ *\[[0-9.]+%\] ", "", t)[:-26].rstrip() for t in table[2:]]
+    assert names == ["Total", "Total run time of the grid generator", "Init", "Create the grid.", "Grid IO."]   # the solver's timers do not exist yet
+    assert all(re.match(TIMER_LINE, t) for t in table[2:]), table
+    assert table[2].startswith("[100.0%] Total") and table[3].startswith("  [") and table[4].startswith("    [")
+    assert len(table[2]) == 50 + 20 + len(" [sec]")
+    meta, msgs = read_run_log(tmp_path / "lbm_log")
+    assert msgs[:3] == ["2D LBM Solver started ||>", "Loading configuration file [case.json]", "Transferring 2D Grid to LBM solver"]
+    if r.returncode == 0:
+        assert "Reached convergence to: 1.41541e-11" in msgs and "max. Error: 1.7692e-12" in msgs and "LBM Solver finished <||" in msgs
+        assert "1300: dU=1.41541e-11 dV=2.44249e-14 drho=5.77316e-14 " in msgs       # the reference's lbm_log holds the same line
+        assert any(m.startswith("  Writing ") and m.endswith("couette_1300.vtp with #640 cells") for m in msgs)
+        table = msgs[msgs.index("-" * 80):]
+        names = [re.sub(r"^ *\[[0-9.]+%\] ", "", t)[:-26].rstrip() for t in table[2:]]
+        assert names == ["Total", "Total run time of the grid generator", "Init", "Create the grid.", "Grid IO.", "Total run time of the LBM Solver.",
+                         "Initialization of the LBM solver!", "Main Loop of the LBM solver!", "Computation", "Postprocessing", "IO"]
+        assert all(re.match(TIMER_LINE, t) for t in table[2:]), table
+
+
+def test_run_log_escapes_the_five_xml_characters(tmp_path):
+    """log.h:45-75"""
+    import ctypes as C
+    import subprocess
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "run_log.hpp"\nint main(int argc, char** argv) { lbmhost::RunLog l; l.open("x_log", argc, argv); '
+                   'l("a<b & \\"c\\" > \'d\'"); return 0; }\n')
+    host = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lbm_b200", "host")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I", host, str(src), "-o", str(tmp_path / "t")])
+    subprocess.check_call([str(tmp_path / "t"), "<arg>"], cwd=tmp_path)
+    text = (tmp_path / "x_log").read_text()
+    assert "a&lt;b &amp; &quot;c&quot; &gt; &apos;d&apos;\n</m>" in text and "&lt;arg&gt;" in text
+    meta, msgs = read_run_log(tmp_path / "x_log")
+    assert msgs == ["a<b & \"c\" > 'd'"]
