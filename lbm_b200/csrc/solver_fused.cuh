@@ -847,13 +847,14 @@ struct Solver final : SolverBase {
       sel.reserve(static_cast<size_t>(no));
       for(int64_t c = 0; c < no; ++c)
         if(keep == nullptr || keep[c]) sel.push_back(plan.ref2dev[c]);
-      out_n_cached = static_cast<int64_t>(sel.size());
-      if(keep == nullptr) out_keep_cached.clear(); else out_keep_cached.assign(keep, keep + no);
+      out_n_cached = -1; // nothing is cached until the buffers below exist
       if(sel.empty()) return fail(LBM_B200_EINVAL, "ERROR: Invalid call to encodeLE() with length = 0"); // base64.h:219-223
+      if(keep == nullptr) out_keep_cached.clear(); else out_keep_cached.assign(keep, keep + no);
       CUDA_TRY(d_out_sel.upload(sel));
       CUDA_TRY(d_out_col.alloc(sel.size()));
-      CUDA_TRY(d_out_text.alloc(static_cast<size_t>(NVAR) * lbm::out::base64_chars(out_n_cached)));
+      CUDA_TRY(d_out_text.alloc(static_cast<size_t>(NVAR) * lbm::out::base64_chars(static_cast<int64_t>(sel.size()))));
       CUDA_TRY(d_out_slow.alloc(1));
+      out_n_cached = static_cast<int64_t>(sel.size());
     }
     const int64_t n = out_n_cached, chars = lbm::out::base64_chars(n);
     if(capacity < chars * NVAR) return fail(LBM_B200_EINVAL, "lbm_b200_encode_output: text buffer too small");

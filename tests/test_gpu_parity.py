@@ -207,6 +207,10 @@ def test_device_side_output_encoding(case, oracle_mod):
             col = np.array([float(f"{x:.15f}") for x in sel[:, v]])
             want = base64.b64encode(struct.pack("<Q", 8 * len(col)) + col.astype("<f8").tobytes())
             assert got[v] == want, f"field {v} differs"
+    for _ in range(2):                                                      # an empty selection is the reference's encodeLE error, every time
+        with pytest.raises(lbm_b200.LbmB200Error, match="length = 0"):
+            g.encode_output(np.zeros(m.shape[0], dtype=bool))
+    assert g.encode_output(keep) == got                                     # and leaves the encoder usable
     pinned = lbm_b200.HostBuffer(sum(len(t) for t in got))                  # page-locked destination (lbm_b200_host_alloc): same text
     again = g.encode_output(keep, out=pinned.array, raw=True)
     assert [bytes(a) for a in again] == got
