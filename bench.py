@@ -278,6 +278,33 @@ def kernel_source_hash():
     return h.hexdigest()[:16]
 
 
+def output_path_sample(s, reps=3):
+    """SURVEY.md section 8f N2 beside the step: the fields of one solution file (all cells kept) through lbm_b200_encode_output -- filter
+    gather, 15-decimal rounding and base64 on the device, the text into page-locked memory -- and, for scale, lbm_b200_get_moments into
+    pageable host memory, which is where the host writer's route only starts (tools/bench_output.py times that route completely)"""
+    import lbm_b200
+    n = s.n
+    total = s.nvar * int(s._lib.lbm_b200_output_chars(n))
+    mem = lbm_b200.HostBuffer(total)
+    try:
+        enc, mom = [], []
+        for _ in range(reps + 1):
+            t0 = time.perf_counter()
+            s.encode_output(None, out=mem.array, raw=True)
+            enc.append(time.perf_counter() - t0)
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            s.moments()
+            mom.append(time.perf_counter() - t0)
+    finally:
+        mem.close()
+    enc_ms, mom_ms = float(np.median(enc[1:])) * 1e3, float(np.median(mom)) * 1e3      # the first call builds the selection list
+    return {"what": "fields of one solution file, all cells kept: lbm_b200_encode_output into page-locked memory (C ABI, host buffer out)",
+            "cells": int(n), "fields": int(s.nvar), "text_bytes": int(total), "device_encode_ms": enc_ms,
+            "Mcells_per_s": n / enc_ms / 1e3, "moments_to_pageable_host_ms": mom_ms,
+            "host_route": "profiles/r02_bench_output_path.json: moments to host + rounding + base64 on 16 cores = 480 ms at 256^3"}
+
+
 def ncu_traffic(lattice, size):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the chunk kernel from the committed ncu capture
     (profiles/traffic.json), or None when the capture is of other device code than the one in the tree"""
@@ -650,6 +677,14 @@ def run_ours(args):
                "region": f"lbm_b200_set_populations(pinned m_fold) + {k} x lbm_b200_step + lbm_b200_get_moments(pinned)",
                "finite": bool(torch.isfinite(mom_host[:n]).all())}
 
+    # ---- output path, after everything that is timed for the headline: never allowed to cost the line
+    output_path = None
+    if world == 1 and not args.no_output and n <= (1 << 25):
+        try:
+            output_path = output_path_sample(s)
+        except Exception as e:  # noqa: BLE001 -- an optional measurement
+            output_path = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     if world > 1:
         # orderly teardown: every rank destroys its NCCL communicator and leaves the process group together
         barrier()
@@ -681,7 +716,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f64", "data": "synthetic",
         "config": config_dict(args, f"{st0['cells_fast']} of {st0['ncells']} cells on the index-free chunk path; setup {t_setup:.1f} s"),
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "with_residual": with_residual, "strict": strict, "parity": parity, "prewarm_steps": args.prewarm,
+        "with_residual": with_residual, "strict": strict, "parity": parity, "prewarm_steps": args.prewarm, "output_path": output_path,
     }
     emit(line)
 
@@ -705,6 +740,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, dest="cpu_budget")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
     ap.add_argument("--no-e2e", action="store_true", dest="no_e2e")
+    ap.add_argument("--no-output", action="store_true", dest="no_output", help="skip the output-path measurement (output_path field)")
     ap.add_argument("--conv-interval", type=int, default=10, dest="conv_interval",
                     help="second measurement with the reference's residual bookkeeping every N steps inside the timed region (0: skip)")
     ap.add_argument("--no-parity", action="store_true", dest="no_parity")

@@ -56,3 +56,20 @@ def test_gpu_arm_fails_loudly_without_a_device():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--size", "16", "--no-cpu", "--no-e2e"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0 and r.stdout.strip() == ""              # no CPU fallback, no JSON line
+
+
+def test_output_path_sample_fails_with_an_ordinary_exception_without_a_device():
+    """bench.py wraps its optional output-path measurement (output_path field) in try/except: whatever goes wrong there must arrive as a
+    Python exception, never take the bench line with it.  Without a device the page-locked allocation is the first thing to fail."""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    sys.path.insert(0, ROOT)
+    import bench
+    import lbm_b200
+    nghbr = np.full((64, 8), -1, dtype=np.int64)
+    s = lbm_b200.Solver(2, 9, nghbr, 1.2, device=-1)
+    with pytest.raises(Exception) as e:
+        bench.output_path_sample(s)
+    assert "cudaMallocHost" in str(e.value)
